@@ -1,0 +1,86 @@
+"""ctypes binding of libcreste_b200.so (the C ABI declared in include/creste_b200.h).
+
+The library is the product: there is no PyTorch / CPU fallback.  Importing this module never
+needs a GPU (the driver tier imports the package on a CPU box), but every op raises loudly if
+the shared library is missing or its tensors are not CUDA tensors.
+"""
+import ctypes as C
+import os
+
+import torch
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, "csrc", "libcreste_b200.so")
+
+EXPORTS = [
+    "creste_version", "creste_last_error", "creste_num_sms",
+    "creste_vi_workspace_bytes", "creste_vi_solve",
+    "creste_svf_workspace_bytes", "creste_svf",
+    "creste_frustum_to_bev", "creste_zmlp_concat",
+    "creste_splat_workspace_bytes", "creste_splat_soft",
+    "creste_lidar_raster", "creste_depth_expectation",
+    "creste_conv2d", "creste_conv2d_workspace_bytes",
+    "creste_dwconv_bn_swish", "creste_se_gate",
+    "creste_upsample_concat", "creste_maxpool2_concat",
+    "creste_nchw_to_nhwc", "creste_nhwc_to_nchw",
+    "creste_expert_visitation",
+]
+
+
+class ConvDesc(C.Structure):
+    """creste_conv_desc (include/creste_b200.h)."""
+    _fields_ = [(n, C.c_int) for n in (
+        "N", "H", "W", "C", "K", "R", "S", "stride", "pad_t", "pad_l", "P", "Q", "act",
+        "out_nchw", "precision")]
+
+
+_lib = None
+
+
+def build(verbose=False):
+    """Compile csrc/*.cu for sm_100a into csrc/libcreste_b200.so (nvcc cross-compiles on CPU)."""
+    import subprocess
+    cmd = ["make", "-C", os.path.join(_HERE, "csrc"), "-j8"]
+    res = subprocess.run(cmd, capture_output=not verbose, text=True)
+    if res.returncode != 0:
+        raise RuntimeError("building libcreste_b200.so failed:\n" + (res.stdout or "") + (res.stderr or ""))
+    return LIB_PATH
+
+
+def lib():
+    global _lib
+    if _lib is None:
+        if not os.path.exists(LIB_PATH):
+            raise RuntimeError(
+                f"{LIB_PATH} is missing: run `python -c 'import __graft_entry__ as g; g.build()'` "
+                "(creste_public_b200 has no CPU or PyTorch fallback)")
+        L = C.CDLL(LIB_PATH)
+        L.creste_last_error.restype = C.c_char_p
+        for name in ("creste_vi_workspace_bytes", "creste_svf_workspace_bytes",
+                     "creste_splat_workspace_bytes", "creste_conv2d_workspace_bytes"):
+            getattr(L, name).restype = C.c_size_t
+        _lib = L
+    return _lib
+
+
+def check(rc, what):
+    if rc != 0:
+        msg = lib().creste_last_error().decode(errors="replace")
+        raise RuntimeError(f"{what} failed (rc={rc}): {msg}")
+
+
+def ptr(t, dtype=None):
+    """Raw device pointer of a contiguous CUDA tensor (None -> NULL)."""
+    if t is None:
+        return C.c_void_p(0)
+    if not t.is_cuda:
+        raise RuntimeError("creste_public_b200 ops need CUDA tensors (no CPU fallback)")
+    if not t.is_contiguous():
+        raise RuntimeError("creste_public_b200 ops need contiguous tensors")
+    if dtype is not None and t.dtype != dtype:
+        raise RuntimeError(f"expected dtype {dtype}, got {t.dtype}")
+    return C.c_void_p(t.data_ptr())
+
+
+def stream():
+    return C.c_void_p(torch.cuda.current_stream().cuda_stream)

@@ -1,0 +1,171 @@
+// conv.cu -- dispatcher of the conv family (creste_conv2d) + the EfficientNet trunk's
+// memory-bound kernels (depthwise conv + BN + swish + SE partial sums, SE gate).
+#include "common.cuh"
+
+namespace creste {
+int conv_simt_launch(const creste_conv_desc* d, const float* x, const float* w, int ldw,
+                     const float* scale, const float* shift, const float* gate,
+                     const float* residual, float* out, cudaStream_t st);
+int conv_tc_launch(const creste_conv_desc* d, const float* x, const float* w_packed,
+                   const float* scale, const float* shift, const float* gate, const float* residual,
+                   float* out, void* ws, size_t ws_bytes, cudaStream_t st);
+size_t conv_tc_workspace_bytes(const creste_conv_desc* d);
+bool conv_tc_supported(const creste_conv_desc* d);
+
+// ---- depthwise conv + folded BN + swish + per-(n,c) spatial sum (for the SE block).
+// NHWC: one thread per (pixel, 4-channel group); consecutive threads = consecutive channel
+// groups, so every tap is a coalesced float4 load.  The SE sum is reduced per block in shared
+// memory (block = 64 pixels x C4 groups slice) then one atomicAdd per (block, channel).
+template <int R>
+__global__ void __launch_bounds__(256) dwconv_kernel(const float* __restrict__ x,
+                                                     const float* __restrict__ w,
+                                                     const float* __restrict__ scale,
+                                                     const float* __restrict__ shift, int N, int H,
+                                                     int W, int C, int stride, int pad_t, int pad_l,
+                                                     int P, int Q, float* __restrict__ out,
+                                                     float* __restrict__ chan_sum) {
+  // grid: x = pixel tiles of PIX_PER_BLOCK within one image, y = image
+  const int C4 = C / 4;
+  const int n = blockIdx.y;
+  const int PQ = P * Q;
+  const int pix_per_block = gridDim.x > 0 ? ceil_div(PQ, (int)gridDim.x) : PQ;
+  const int pix0 = blockIdx.x * pix_per_block;
+  const int pix1 = min(pix0 + pix_per_block, PQ);
+  // thread -> channel group cg = t % C4s ; pixel lane = t / C4s   (C4s = min(C4, 256))
+  for (int cg0 = 0; cg0 < C4; cg0 += 256) {
+    const int cgs = min(C4 - cg0, 256);
+    const int lanes = 256 / cgs;  // pixels processed concurrently by the block
+    const int cg = cg0 + (threadIdx.x % cgs);
+    const int pl = threadIdx.x / cgs;
+    float4 sum = make_float4(0.f, 0.f, 0.f, 0.f);
+    if (pl < lanes) {
+      const float4 sc = __ldg(reinterpret_cast<const float4*>(scale) + cg);
+      const float4 sh = __ldg(reinterpret_cast<const float4*>(shift) + cg);
+      float4 wk[R * R];
+#pragma unroll
+      for (int i = 0; i < R * R; ++i) wk[i] = __ldg(reinterpret_cast<const float4*>(w + (size_t)i * C) + cg);
+      for (int pix = pix0 + pl; pix < pix1; pix += lanes) {
+        const int oy = pix / Q, ox = pix - oy * Q;
+        const int iy0 = oy * stride - pad_t, ix0 = ox * stride - pad_l;
+        float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
+#pragma unroll
+        for (int r = 0; r < R; ++r) {
+          const int iy = iy0 + r;
+          if (iy < 0 || iy >= H) continue;
+#pragma unroll
+          for (int s = 0; s < R; ++s) {
+            const int ix = ix0 + s;
+            if (ix < 0 || ix >= W) continue;
+            const float4 v = __ldg(reinterpret_cast<const float4*>(x + (((size_t)n * H + iy) * W + ix) * C) + cg);
+            const float4 k = wk[r * R + s];
+            acc.x = fmaf(v.x, k.x, acc.x); acc.y = fmaf(v.y, k.y, acc.y);
+            acc.z = fmaf(v.z, k.z, acc.z); acc.w = fmaf(v.w, k.w, acc.w);
+          }
+        }
+        float4 o;
+        o.x = fmaf(acc.x, sc.x, sh.x); o.y = fmaf(acc.y, sc.y, sh.y);
+        o.z = fmaf(acc.z, sc.z, sh.z); o.w = fmaf(acc.w, sc.w, sh.w);
+        o.x = o.x / (1.0f + expf(-o.x)); o.y = o.y / (1.0f + expf(-o.y));
+        o.z = o.z / (1.0f + expf(-o.z)); o.w = o.w / (1.0f + expf(-o.w));
+        reinterpret_cast<float4*>(out + ((size_t)n * PQ + pix) * C)[cg] = o;
+        sum.x += o.x; sum.y += o.y; sum.z += o.z; sum.w += o.w;
+      }
+      float* cs = chan_sum + (size_t)n * C + cg * 4;
+      atomicAdd(cs + 0, sum.x); atomicAdd(cs + 1, sum.y);
+      atomicAdd(cs + 2, sum.z); atomicAdd(cs + 3, sum.w);
+    }
+  }
+}
+
+// ---- SE gate: one block per image
+__global__ void __launch_bounds__(256) se_gate_kernel(const float* __restrict__ chan_sum, float inv_hw,
+                                                      int C, int Csq, const float* __restrict__ w_red,
+                                                      const float* __restrict__ b_red,
+                                                      const float* __restrict__ w_exp,
+                                                      const float* __restrict__ b_exp,
+                                                      float* __restrict__ gate) {
+  extern __shared__ float sm[];  // mean[C], sq[Csq]
+  float* mean = sm;
+  float* sq = sm + C;
+  const int n = blockIdx.x;
+  for (int c = threadIdx.x; c < C; c += blockDim.x) mean[c] = chan_sum[(size_t)n * C + c] * inv_hw;
+  __syncthreads();
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nw = blockDim.x >> 5;
+  for (int j = warp; j < Csq; j += nw) {
+    float a = 0.0f;
+    for (int c = lane; c < C; c += 32) a = fmaf(w_red[(size_t)j * C + c], mean[c], a);
+    a = warp_sum(a);
+    if (lane == 0) {
+      a += b_red[j];
+      sq[j] = a / (1.0f + expf(-a));  // swish
+    }
+  }
+  __syncthreads();
+  for (int c = threadIdx.x; c < C; c += blockDim.x) {
+    float a = b_exp[c];
+    for (int j = 0; j < Csq; ++j) a = fmaf(w_exp[(size_t)c * Csq + j], sq[j], a);
+    gate[(size_t)n * C + c] = 1.0f / (1.0f + expf(-a));
+  }
+}
+
+}  // namespace creste
+
+using namespace creste;
+
+extern "C" size_t creste_conv2d_workspace_bytes(const creste_conv_desc* d) {
+  if (!d || d->precision == 0) return 0;
+  return conv_tc_workspace_bytes(d);
+}
+
+extern "C" int creste_conv2d(const creste_conv_desc* d, const float* x, const float* w_packed,
+                             const float* scale, const float* shift, const float* gate,
+                             const float* residual, float* out, void* ws, size_t ws_bytes,
+                             void* stream) {
+  CRESTE_CHECK_ARG(d && x && w_packed && out, "creste_conv2d: null pointer");
+  CRESTE_CHECK_ARG(d->N > 0 && d->H > 0 && d->W > 0 && d->C > 0 && d->K > 0 && d->R > 0 && d->S > 0 &&
+                       d->stride > 0 && d->P > 0 && d->Q > 0,
+                   "creste_conv2d: bad shape");
+  CRESTE_CHECK_ARG(d->C % 4 == 0, "creste_conv2d: C must be a multiple of 4 (got %d)", d->C);
+  CRESTE_CHECK_ARG((d->P - 1) * d->stride - d->pad_t + d->R - 1 >= 0, "creste_conv2d: bad padding");
+  cudaStream_t st = (cudaStream_t)stream;
+  if (d->precision == 0) {
+    const int ldw = (d->K + 3) / 4 * 4;
+    return conv_simt_launch(d, x, w_packed, ldw, scale, shift, gate, residual, out, st);
+  }
+  if (!conv_tc_supported(d)) {
+    set_error("creste_conv2d: precision mode %d is not available for this shape "
+              "(C=%d K=%d R=%d stride=%d); use precision 0", d->precision, d->C, d->K, d->R, d->stride);
+    return CRESTE_ERR_ARG;
+  }
+  return conv_tc_launch(d, x, w_packed, scale, shift, gate, residual, out, ws, ws_bytes, st);
+}
+
+extern "C" int creste_dwconv_bn_swish(const float* x, const float* w, const float* scale,
+                                      const float* shift, int N, int H, int W, int C, int R,
+                                      int stride, int pad_t, int pad_l, int P, int Q, float* out,
+                                      float* chan_sum, void* stream) {
+  CRESTE_CHECK_ARG(x && w && scale && shift && out && chan_sum, "creste_dwconv_bn_swish: null pointer");
+  CRESTE_CHECK_ARG(C % 4 == 0 && (R == 3 || R == 5), "creste_dwconv_bn_swish: C%%4==0, R in {3,5}");
+  cudaStream_t st = (cudaStream_t)stream;
+  CRESTE_CUDA(cudaMemsetAsync(chan_sum, 0, (size_t)N * C * sizeof(float), st));
+  const int PQ = P * Q;
+  int tiles = ceil_div(PQ, 64);
+  const int cap = ceil_div(148 * 8, N);
+  if (tiles > cap) tiles = cap;
+  dim3 grid(tiles, N);
+  if (R == 3)
+    dwconv_kernel<3><<<grid, 256, 0, st>>>(x, w, scale, shift, N, H, W, C, stride, pad_t, pad_l, P, Q, out, chan_sum);
+  else
+    dwconv_kernel<5><<<grid, 256, 0, st>>>(x, w, scale, shift, N, H, W, C, stride, pad_t, pad_l, P, Q, out, chan_sum);
+  return launch_check("dwconv_kernel");
+}
+
+extern "C" int creste_se_gate(const float* chan_sum, float inv_hw, int N, int C, int Csq,
+                              const float* w_red, const float* b_red, const float* w_exp,
+                              const float* b_exp, float* gate, void* stream) {
+  CRESTE_CHECK_ARG(chan_sum && w_red && b_red && w_exp && b_exp && gate, "creste_se_gate: null pointer");
+  const size_t smem = (size_t)(C + Csq) * sizeof(float);
+  se_gate_kernel<<<N, 256, smem, (cudaStream_t)stream>>>(chan_sum, inv_hw, C, Csq, w_red, b_red, w_exp,
+                                                        b_exp, gate);
+  return launch_check("se_gate_kernel");
+}

@@ -1,0 +1,212 @@
+// layout.cu -- memory-bound glue kernels (NHWC): layout shuffles at the module boundary,
+// bilinear upsample + channel concat, 2x2 max-pool + concat + crop, expert-visitation raster.
+// All are pure HBM streaming kernels: float4-vectorised, channel-contiguous, grid-stride.
+#include "common.cuh"
+
+namespace creste {
+
+// ---- NCHW <-> NHWC through a 32x32 shared tile (both sides coalesced)
+__global__ void __launch_bounds__(256) transpose_kernel(const float* __restrict__ in, int rows,
+                                                        int cols, float* __restrict__ out) {
+  // in: [batch][rows][cols] -> out: [batch][cols][rows]
+  __shared__ float tile[32][33];
+  const size_t base = (size_t)blockIdx.z * rows * cols;
+  const int c0 = blockIdx.x * 32, r0 = blockIdx.y * 32;
+  const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;
+  for (int j = ty; j < 32; j += 8) {
+    const int r = r0 + j, c = c0 + tx;
+    tile[j][tx] = (r < rows && c < cols) ? in[base + (size_t)r * cols + c] : 0.0f;
+  }
+  __syncthreads();
+  for (int j = ty; j < 32; j += 8) {
+    const int c = c0 + j, r = r0 + tx;
+    if (r < rows && c < cols) out[base + (size_t)c * rows + r] = tile[tx][j];
+  }
+}
+
+// ---- cat([skip, bilinear(x)], C) in NHWC; Cs % 4 == 0, Cx % 4 == 0.
+// PyTorch upsample_bilinear2d (align_corners=False): src = max(r*(dst+0.5)-0.5, 0); i0 = (int)src;
+// i1 = i0 + (i0 < in-1); l1 = src - i0; l0 = 1 - l1;
+// out = l0h*(l0w*v00 + l1w*v01) + l1h*(l0w*v10 + l1w*v11).
+__global__ void __launch_bounds__(256) upsample_concat_kernel(const float* __restrict__ skip, int Cs,
+                                                              const float* __restrict__ x, int N,
+                                                              int Hi, int Wi, int Cx, int Ho, int Wo,
+                                                              float rh, float rw,
+                                                              float* __restrict__ out) {
+  const int Ct = Cs + Cx;
+  const int c4t = Ct / 4, cs4 = Cs / 4;
+  const long long total = (long long)N * Ho * Wo * c4t;
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total;
+       i += (long long)gridDim.x * blockDim.x) {
+    const int c4 = (int)(i % c4t);
+    const long long pix = i / c4t;
+    float4 v;
+    if (c4 < cs4) {
+      v = __ldg(reinterpret_cast<const float4*>(skip + pix * Cs) + c4);
+    } else {
+      const int ox = (int)(pix % Wo);
+      const int oy = (int)((pix / Wo) % Ho);
+      const int n = (int)(pix / ((long long)Wo * Ho));
+      const float sy = fmaxf(__fsub_rn(__fmul_rn(rh, __fadd_rn((float)oy, 0.5f)), 0.5f), 0.0f);
+      const float sx = fmaxf(__fsub_rn(__fmul_rn(rw, __fadd_rn((float)ox, 0.5f)), 0.5f), 0.0f);
+      const int y0 = (int)sy, x0 = (int)sx;
+      const int y1 = y0 + (y0 < Hi - 1 ? 1 : 0), x1 = x0 + (x0 < Wi - 1 ? 1 : 0);
+      const float l1h = __fsub_rn(sy, (float)y0), l0h = __fsub_rn(1.0f, l1h);
+      const float l1w = __fsub_rn(sx, (float)x0), l0w = __fsub_rn(1.0f, l1w);
+      const int cc = c4 - cs4;
+      const float* b = x + (size_t)n * Hi * Wi * Cx;
+      const float4 v00 = __ldg(reinterpret_cast<const float4*>(b + ((size_t)y0 * Wi + x0) * Cx) + cc);
+      const float4 v01 = __ldg(reinterpret_cast<const float4*>(b + ((size_t)y0 * Wi + x1) * Cx) + cc);
+      const float4 v10 = __ldg(reinterpret_cast<const float4*>(b + ((size_t)y1 * Wi + x0) * Cx) + cc);
+      const float4 v11 = __ldg(reinterpret_cast<const float4*>(b + ((size_t)y1 * Wi + x1) * Cx) + cc);
+#define CRESTE_LERP(f) (l0h * (l0w * v00.f + l1w * v01.f) + l1h * (l0w * v10.f + l1w * v11.f))
+      v.x = CRESTE_LERP(x); v.y = CRESTE_LERP(y); v.z = CRESTE_LERP(z); v.w = CRESTE_LERP(w);
+#undef CRESTE_LERP
+    }
+    reinterpret_cast<float4*>(out + pix * Ct)[c4] = v;
+  }
+}
+
+// ---- 2x2/2 max-pool of channel-concatenated NHWC sources, cropped to rows_out rows
+struct PoolSrcs { const float* p[3]; int c[3]; int n; };
+__global__ void __launch_bounds__(256) maxpool2_concat_kernel(PoolSrcs s, int N, int H, int W,
+                                                              int rows_out, int Ct,
+                                                              float* __restrict__ out_nhwc,
+                                                              float* __restrict__ out_nchw) {
+  const int Wo = W / 2;
+  const long long total = (long long)N * rows_out * Wo * Ct;
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total;
+       i += (long long)gridDim.x * blockDim.x) {
+    int c = (int)(i % Ct);
+    const long long pix = i / Ct;
+    const int ox = (int)(pix % Wo);
+    const int oy = (int)((pix / Wo) % rows_out);
+    const int n = (int)(pix / ((long long)Wo * rows_out));
+    const int ctot = c;
+    int k = 0;
+    while (k < s.n - 1 && c >= s.c[k]) { c -= s.c[k]; ++k; }
+    const float* b = s.p[k] + ((size_t)n * H * W) * s.c[k] + c;
+    const int Ck = s.c[k];
+    const size_t r0 = ((size_t)(2 * oy) * W + 2 * ox) * Ck, r1 = r0 + (size_t)W * Ck;
+    const float m = fmaxf(fmaxf(__ldg(b + r0), __ldg(b + r0 + Ck)), fmaxf(__ldg(b + r1), __ldg(b + r1 + Ck)));
+    if (out_nhwc) out_nhwc[i] = m;
+    if (out_nchw) out_nchw[(((size_t)n * Ct + ctot) * rows_out + oy) * Wo + ox] = m;
+  }
+}
+
+// ---- expert visitation raster (loss_utils.py:1055-1116, second definition)
+template <typename T>
+__global__ void expert_visitation_kernel(const T* __restrict__ traj, int B, int Tn, T map_ds,
+                                         int max_steps, int H, int W, float* __restrict__ counts) {
+  // one thread per (b, t, k): k-th interpolation sample of segment t; plus the appended last pose
+  const long long per_b = (long long)(Tn - 1) * max_steps + 1;
+  const long long total = (long long)B * per_b;
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total;
+       i += (long long)gridDim.x * blockDim.x) {
+    const int b = (int)(i / per_b);
+    const long long j = i - (long long)b * per_b;
+    T pr, pc;
+    if (j == per_b - 1) {
+      pr = traj[((size_t)b * Tn + Tn - 1) * 2] / map_ds;
+      pc = traj[((size_t)b * Tn + Tn - 1) * 2 + 1] / map_ds;
+    } else {
+      const int t = (int)(j / max_steps), k = (int)(j - (long long)t * max_steps);
+      const T r0 = traj[((size_t)b * Tn + t) * 2] / map_ds, c0 = traj[((size_t)b * Tn + t) * 2 + 1] / map_ds;
+      const T r1 = traj[((size_t)b * Tn + t + 1) * 2] / map_ds, c1 = traj[((size_t)b * Tn + t + 1) * 2 + 1] / map_ds;
+      // torch.linspace(0, 1, max_steps) is float32 whatever the trajectory dtype
+      float f = 0.0f;
+      if (max_steps > 1) {
+        const float step = __fdiv_rn(1.0f, (float)(max_steps - 1));
+        f = (k < max_steps / 2) ? __fmul_rn(step, (float)k)
+                                : __fsub_rn(1.0f, __fmul_rn(step, (float)(max_steps - 1 - k)));
+      }
+      const T ft = (T)f;
+      if (sizeof(T) == 4) {
+        pr = (T)__fadd_rn((float)r0, __fmul_rn((float)ft, __fsub_rn((float)r1, (float)r0)));
+        pc = (T)__fadd_rn((float)c0, __fmul_rn((float)ft, __fsub_rn((float)c1, (float)c0)));
+      } else {
+        pr = (T)__dadd_rn((double)r0, __dmul_rn((double)ft, __dsub_rn((double)r1, (double)r0)));
+        pc = (T)__dadd_rn((double)c0, __dmul_rn((double)ft, __dsub_rn((double)c1, (double)c0)));
+      }
+    }
+    pr = pr < (T)0 ? (T)0 : (pr > (T)(H - 1) ? (T)(H - 1) : pr);
+    pc = pc < (T)0 ? (T)0 : (pc > (T)(W - 1) ? (T)(W - 1) : pc);
+    const long long ir = (long long)pr, ic = (long long)pc;
+    counts[((size_t)b * H + ir) * W + ic] = 1.0f;  // scatter_add of ones, then clipped to 1
+  }
+}
+
+}  // namespace creste
+
+using namespace creste;
+
+static int grid_for(long long total, int threads = 256) {
+  long long b = (total + threads - 1) / threads;
+  const long long cap = 148LL * 16;
+  return (int)(b < cap ? (b > 0 ? b : 1) : cap);
+}
+
+extern "C" int creste_nchw_to_nhwc(const float* in, int N, int C, int H, int W, float* out,
+                                   void* stream) {
+  CRESTE_CHECK_ARG(in && out && N > 0 && C > 0 && H > 0 && W > 0, "creste_nchw_to_nhwc: bad args");
+  dim3 grid(ceil_div(H * W, 32), ceil_div(C, 32), N);
+  transpose_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(in, C, H * W, out);
+  return launch_check("transpose_kernel");
+}
+
+extern "C" int creste_nhwc_to_nchw(const float* in, int N, int H, int W, int C, float* out,
+                                   void* stream) {
+  CRESTE_CHECK_ARG(in && out && N > 0 && C > 0 && H > 0 && W > 0, "creste_nhwc_to_nchw: bad args");
+  dim3 grid(ceil_div(C, 32), ceil_div(H * W, 32), N);
+  transpose_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(in, H * W, C, out);
+  return launch_check("transpose_kernel");
+}
+
+extern "C" int creste_upsample_concat(const float* skip, int Cs, const float* x, int N, int Hi,
+                                      int Wi, int Cx, int Ho, int Wo, float rh, float rw, float* out,
+                                      void* stream) {
+  CRESTE_CHECK_ARG(x && out, "creste_upsample_concat: null pointer");
+  CRESTE_CHECK_ARG((Cs == 0 || skip) && Cs % 4 == 0 && Cx % 4 == 0 && Cx > 0,
+                   "creste_upsample_concat: channel counts must be multiples of 4");
+  const long long total = (long long)N * Ho * Wo * ((Cs + Cx) / 4);
+  upsample_concat_kernel<<<grid_for(total), 256, 0, (cudaStream_t)stream>>>(skip, Cs, x, N, Hi, Wi, Cx,
+                                                                           Ho, Wo, rh, rw, out);
+  return launch_check("upsample_concat_kernel");
+}
+
+extern "C" int creste_maxpool2_concat(const float* const* srcs, const int* chans, int nsrc, int N,
+                                      int H, int W, int rows_out, float* out_nhwc, float* out_nchw,
+                                      void* stream) {
+  CRESTE_CHECK_ARG(srcs && chans && nsrc >= 1 && nsrc <= 3, "creste_maxpool2_concat: 1..3 sources");
+  CRESTE_CHECK_ARG(H % 2 == 0 && W % 2 == 0 && rows_out > 0 && rows_out <= H / 2,
+                   "creste_maxpool2_concat: bad shape");
+  PoolSrcs s;
+  int Ct = 0;
+  s.n = nsrc;
+  for (int i = 0; i < 3; ++i) {
+    s.p[i] = i < nsrc ? srcs[i] : nullptr;
+    s.c[i] = i < nsrc ? chans[i] : 0;
+    Ct += s.c[i];
+  }
+  const long long total = (long long)N * rows_out * (W / 2) * Ct;
+  maxpool2_concat_kernel<<<grid_for(total), 256, 0, (cudaStream_t)stream>>>(s, N, H, W, rows_out, Ct,
+                                                                           out_nhwc, out_nchw);
+  return launch_check("maxpool2_concat_kernel");
+}
+
+extern "C" int creste_expert_visitation(const void* traj, int is_f64, int B, int T, double map_ds,
+                                        int max_steps, int H, int W, float* counts, void* stream) {
+  CRESTE_CHECK_ARG(traj && counts && B > 0 && T > 0 && H > 0 && W > 0 && max_steps >= 0,
+                   "creste_expert_visitation: bad args");
+  cudaStream_t st = (cudaStream_t)stream;
+  CRESTE_CUDA(cudaMemsetAsync(counts, 0, (size_t)B * H * W * sizeof(float), st));
+  const long long total = (long long)B * ((long long)(T - 1) * max_steps + 1);
+  if (is_f64)
+    expert_visitation_kernel<double><<<grid_for(total), 256, 0, st>>>((const double*)traj, B, T, map_ds,
+                                                                      max_steps, H, W, counts);
+  else
+    expert_visitation_kernel<float><<<grid_for(total), 256, 0, st>>>((const float*)traj, B, T,
+                                                                     (float)map_ds, max_steps, H, W,
+                                                                     counts);
+  return launch_check("expert_visitation_kernel");
+}

@@ -1,0 +1,257 @@
+"""Tensor-level wrappers over the C ABI (include/creste_b200.h).
+
+PyTorch is used for device memory and streams only: every function here takes CUDA tensors,
+allocates outputs / scratch with torch's caching allocator on the same device and launches the
+sm_100a kernels on torch's current stream.  No function has a CPU or PyTorch-eager fallback.
+"""
+import ctypes as C
+
+import torch
+
+from . import _lib
+from ._lib import ConvDesc, check, lib, ptr, stream
+
+ACT = {"none": 0, None: 0, "relu": 1, "swish": 2, "sigmoid": 3}
+PRECISION = {"fp32": 0, "3xtf32": 1, "tf32": 2, "bf16": 3}
+
+
+def _ws(nbytes, device):
+    return torch.empty(max(int(nbytes), 16), dtype=torch.uint8, device=device)
+
+
+# ------------------------------------------------------------------------------------------ VI
+def vi_solve(r, gamma=0.99, thr=1e-3, max_sweeps=4096, want_q=True):
+    """Value iteration (reference vin.py:48-80).  r [B,1,H,W] or [B,H,W] fp32 CUDA.
+    Returns v [B,1,H,W], q [B,8,H,W], pi [B,8,H,W], info int32[2] (device: sweeps, hit_max)."""
+    r3 = r.reshape(r.shape[0], r.shape[-2], r.shape[-1]).contiguous().float()
+    B, H, W = r3.shape
+    v = torch.empty_like(r3)
+    q = torch.empty(B, 8, H, W, device=r.device) if want_q else None
+    pi = torch.empty(B, 8, H, W, device=r.device) if want_q else None
+    info = torch.zeros(2, dtype=torch.int32, device=r.device)
+    n = lib().creste_vi_workspace_bytes(B, H, W, max_sweeps)
+    ws = _ws(n, r.device)
+    check(lib().creste_vi_solve(ptr(r3), ptr(v), ptr(q), ptr(pi), B, H, W, C.c_float(gamma),
+                                C.c_float(thr), max_sweeps, ptr(info), ptr(ws), C.c_size_t(n),
+                                stream()), "creste_vi_solve")
+    return v.view(B, 1, H, W), q, pi, info
+
+
+# ----------------------------------------------------------------------------------------- SVF
+def svf(policy, expert_rc, fov, T, ds=2, sharpen=True, temperature=0.005, zero_terminal=False):
+    """Expected SVF + greedy rollout (reference lfd.py:156-277).  policy [B,8,H,W];
+    expert_rc [B,T,2] fp32; fov [H,W] uint8/bool.  Returns exp_svf [B,H,W],
+    states [B,T,2] int64, states_grid [B,H,W]."""
+    policy = policy.contiguous().float()
+    expert_rc = expert_rc.contiguous().float()
+    fov = fov.to(torch.uint8).contiguous()
+    B, A, H, W = policy.shape
+    assert A == 8 and tuple(expert_rc.shape) == (B, T, 2) and tuple(fov.shape) == (H, W)
+    out = torch.empty(B, H, W, device=policy.device)
+    states = torch.empty(B, T, 2, dtype=torch.int64, device=policy.device)
+    grid = torch.empty(B, H, W, device=policy.device)
+    n = lib().creste_svf_workspace_bytes(B, H, W, T)
+    ws = _ws(n, policy.device)
+    check(lib().creste_svf(ptr(policy), ptr(expert_rc), ptr(fov), B, H, W, T, ds,
+                           int(bool(sharpen)), C.c_float(temperature), int(bool(zero_terminal)),
+                           ptr(out), ptr(states), ptr(grid), ptr(ws), C.c_size_t(n), stream()),
+          "creste_svf")
+    return out, states, grid
+
+
+# --------------------------------------------------------------------------------------- splat
+def frustum_to_bev(depth, p2p, pc_range, voxel):
+    """depth [N,Hs,Ws] m, p2p [N,4,4] -> xy [N,P,2], z [N,P], mask [N,P] uint8
+    (reference splat_projection.py:19-51, :169, :175-189).  pc_range/voxel: python floats."""
+    depth = depth.contiguous().float()
+    p2p = p2p.contiguous().float()
+    N, Hs, Ws = depth.shape
+    P = Hs * Ws
+    xy = torch.empty(N, P, 2, device=depth.device)
+    z = torch.empty(N, P, device=depth.device)
+    mask = torch.empty(N, P, dtype=torch.uint8, device=depth.device)
+    rng = (C.c_float * 6)(*[float(v) for v in pc_range])
+    vox = (C.c_float * 2)(float(voxel[0]), float(voxel[1]))
+    check(lib().creste_frustum_to_bev(ptr(depth), ptr(p2p), N, Hs, Ws, rng, vox, ptr(xy), ptr(z),
+                                      ptr(mask), stream()), "creste_frustum_to_bev")
+    return xy, z, mask
+
+
+def zmlp_concat(feats_nhwc, z, w1, b1, w2, b2):
+    """feats NHWC [...,C] + MLP(z) -> NHWC [...,C+32] (reference splat_projection.py:152-158)."""
+    Cc = feats_nhwc.shape[-1]
+    NP = feats_nhwc.numel() // Cc
+    out = torch.empty(*feats_nhwc.shape[:-1], Cc + 32, device=feats_nhwc.device)
+    check(lib().creste_zmlp_concat(ptr(feats_nhwc), ptr(z.contiguous()), NP, Cc, ptr(w1), ptr(b1),
+                                   ptr(w2), ptr(b2), ptr(out), stream()), "creste_zmlp_concat")
+    return out
+
+
+def splat_soft(xy, feats_nhwc, mask, H, W, min_weight=1.0, want_nhwc=True, want_nchw=True,
+               want_idx=False):
+    """Bilinear splat (reference splat_projection.py:262-354).  xy [N,P,2]; feats NHWC [N,P,F];
+    mask [N,P] uint8 or None.  Returns dict(bev_nhwc [N,H,W,F], bev_nchw [N,F,H,W],
+    dens [N,1,H,W], idx [N,P,4] int64)."""
+    xy = xy.contiguous().float()
+    N, P, _ = xy.shape
+    dev = xy.device
+    F = 0
+    if feats_nhwc is not None:
+        feats_nhwc = feats_nhwc.contiguous().float()
+        F = feats_nhwc.shape[-1]
+        assert feats_nhwc.numel() == N * P * F
+    want_feats = feats_nhwc is not None and (want_nhwc or want_nchw)
+    nhwc = torch.empty(N, H, W, F, device=dev) if (want_feats and want_nhwc) else None
+    nchw = torch.empty(N, F, H, W, device=dev) if (want_feats and want_nchw) else None
+    dens = torch.empty(N, 1, H, W, device=dev)
+    idx = torch.empty(N, P, 4, dtype=torch.int64, device=dev) if want_idx else None
+    n = lib().creste_splat_workspace_bytes(N, H, W, max(F, 1)) if want_feats else 0
+    ws = _ws(n, dev)
+    check(lib().creste_splat_soft(ptr(xy), ptr(feats_nhwc), ptr(mask), N, P, F, H, W,
+                                  C.c_float(min_weight), ptr(nhwc), ptr(nchw), ptr(dens), ptr(idx),
+                                  ptr(ws), C.c_size_t(n), stream()), "creste_splat_soft")
+    return {"bev_nhwc": nhwc, "bev_nchw": nchw, "dens": dens, "idx": idx}
+
+
+# --------------------------------------------------------------------------------------- LiDAR
+def lidar_raster(pc, P34, H, W):
+    """pc [n,>=3] fp32 CUDA; P34 [3,4] float64 (host array-like) -> depth_m [H,W], depth_mm [H,W]
+    (reference projection.py:64-134 + build_dense_depth.py:461-463)."""
+    pc = pc.contiguous().float()
+    flat = [float(v) for row in P34 for v in row]
+    assert len(flat) == 12
+    Pm = (C.c_double * 12)(*flat)
+    dm = torch.empty(H, W, device=pc.device)
+    dmm = torch.empty(H, W, device=pc.device)
+    ws = _ws(H * W * 8, pc.device)
+    check(lib().creste_lidar_raster(ptr(pc), pc.shape[0], pc.shape[1], Pm, H, W, ptr(dm), ptr(dmm),
+                                    ptr(ws), C.c_size_t(H * W * 8), stream()), "creste_lidar_raster")
+    return dm, dmm
+
+
+def depth_expectation(logits_nhwc, dmin=300.0, dmax=25600.0):
+    """logits NHWC [N,Hs,Ws,128] -> metric [N,Hs,Ws] (m), bins [N,Hs,Ws] int64
+    (reference depth_utils.py:300-313, depth.py:60-100)."""
+    D = logits_nhwc.shape[-1]
+    shp = logits_nhwc.shape[:-1]
+    NP = logits_nhwc.numel() // D
+    metric = torch.empty(shp, device=logits_nhwc.device)
+    bins = torch.empty(shp, dtype=torch.int64, device=logits_nhwc.device)
+    check(lib().creste_depth_expectation(ptr(logits_nhwc), NP, D, C.c_float(dmin), C.c_float(dmax),
+                                         ptr(metric), ptr(bins), stream()),
+          "creste_depth_expectation")
+    return metric, bins
+
+
+# ---------------------------------------------------------------------------------- conv family
+def pack_conv_weight(w):
+    """[K,C,R,S] (torch layout) -> [R*S*C, ldw] row-major, ldw = K rounded up to 4."""
+    K, Cc, R, S = w.shape
+    ldw = (K + 3) // 4 * 4
+    p = w.permute(2, 3, 1, 0).reshape(R * S * Cc, K)
+    if ldw != K:
+        p = torch.cat([p, p.new_zeros(R * S * Cc, ldw - K)], dim=1)
+    return p.contiguous()
+
+
+def conv2d(x_nhwc, w_packed, K, R, S, stride=1, pad=(0, 0, 0, 0), scale=None, shift=None,
+           gate=None, residual=None, act="none", out_nchw=False, precision="fp32"):
+    """NHWC conv + folded BN/bias + residual + activation.  pad = (top, bottom, left, right)."""
+    N, H, W, Cc = x_nhwc.shape
+    pt, pb, pl, pr = pad
+    P = (H + pt + pb - R) // stride + 1
+    Q = (W + pl + pr - S) // stride + 1
+    d = ConvDesc(N, H, W, Cc, K, R, S, stride, pt, pl, P, Q, ACT[act], int(out_nchw),
+                 PRECISION[precision])
+    out = torch.empty((N, K, P, Q) if out_nchw else (N, P, Q, K), device=x_nhwc.device)
+    n = lib().creste_conv2d_workspace_bytes(C.byref(d))
+    ws = _ws(n, x_nhwc.device) if n else None
+    check(lib().creste_conv2d(C.byref(d), ptr(x_nhwc), ptr(w_packed), ptr(scale), ptr(shift),
+                              ptr(gate), ptr(residual), ptr(out), ptr(ws), C.c_size_t(n), stream()),
+          "creste_conv2d")
+    return out
+
+
+def dwconv_bn_swish(x_nhwc, w_rsc, scale, shift, R, stride, pad):
+    """Depthwise conv + BN + swish; returns (out NHWC, chan_sum [N,C])."""
+    N, H, W, Cc = x_nhwc.shape
+    pt, pb, pl, pr = pad
+    P = (H + pt + pb - R) // stride + 1
+    Q = (W + pl + pr - R) // stride + 1
+    out = torch.empty(N, P, Q, Cc, device=x_nhwc.device)
+    csum = torch.empty(N, Cc, device=x_nhwc.device)
+    check(lib().creste_dwconv_bn_swish(ptr(x_nhwc), ptr(w_rsc), ptr(scale), ptr(shift), N, H, W, Cc,
+                                       R, stride, pt, pl, P, Q, ptr(out), ptr(csum), stream()),
+          "creste_dwconv_bn_swish")
+    return out, csum
+
+
+def se_gate(chan_sum, hw, w_red, b_red, w_exp, b_exp):
+    N, Cc = chan_sum.shape
+    Csq = w_red.shape[0]
+    gate = torch.empty(N, Cc, device=chan_sum.device)
+    check(lib().creste_se_gate(ptr(chan_sum), C.c_float(1.0 / hw), N, Cc, Csq, ptr(w_red), ptr(b_red),
+                               ptr(w_exp), ptr(b_exp), ptr(gate), stream()), "creste_se_gate")
+    return gate
+
+
+def upsample_concat(skip_nhwc, x_nhwc, out_hw, scale_factor=None):
+    """cat([skip, bilinear(x)], C) in NHWC.  scale_factor: the nn.Upsample argument (number or
+    (sh, sw)); when given, the sampling ratio is 1/scale_factor exactly as PyTorch does."""
+    N, Hi, Wi, Cx = x_nhwc.shape
+    Ho, Wo = out_hw
+    if scale_factor is None:
+        rh, rw = Hi / Ho, Wi / Wo
+    else:
+        sh, sw = (scale_factor, scale_factor) if not isinstance(scale_factor, (tuple, list)) \
+            else scale_factor
+        rh, rw = 1.0 / sh, 1.0 / sw
+    Cs = 0 if skip_nhwc is None else skip_nhwc.shape[-1]
+    out = torch.empty(N, Ho, Wo, Cs + Cx, device=x_nhwc.device)
+    check(lib().creste_upsample_concat(ptr(skip_nhwc), Cs, ptr(x_nhwc), N, Hi, Wi, Cx, Ho, Wo,
+                                       C.c_float(rh), C.c_float(rw), ptr(out), stream()),
+          "creste_upsample_concat")
+    return out
+
+
+def maxpool2_concat(srcs_nhwc, rows_out=None, want_nchw=False):
+    """2x2/2 max-pool of the channel concat of NHWC sources, cropped to `rows_out` output rows."""
+    N, H, W, _ = srcs_nhwc[0].shape
+    chans = [int(s.shape[-1]) for s in srcs_nhwc]
+    rows_out = H // 2 if rows_out is None else rows_out
+    Ct = sum(chans)
+    out = torch.empty(N, rows_out, W // 2, Ct, device=srcs_nhwc[0].device)
+    nchw = torch.empty(N, Ct, rows_out, W // 2, device=out.device) if want_nchw else None
+    ps = (C.c_void_p * len(srcs_nhwc))(*[ptr(s).value for s in srcs_nhwc])
+    cs = (C.c_int * len(chans))(*chans)
+    check(lib().creste_maxpool2_concat(ps, cs, len(chans), N, H, W, rows_out, ptr(out), ptr(nchw),
+                                       stream()), "creste_maxpool2_concat")
+    return (out, nchw) if want_nchw else out
+
+
+def nchw_to_nhwc(x):
+    N, Cc, H, W = x.shape
+    out = torch.empty(N, H, W, Cc, device=x.device)
+    check(lib().creste_nchw_to_nhwc(ptr(x.contiguous()), N, Cc, H, W, ptr(out), stream()),
+          "creste_nchw_to_nhwc")
+    return out
+
+
+def nhwc_to_nchw(x):
+    N, H, W, Cc = x.shape
+    out = torch.empty(N, Cc, H, W, device=x.device)
+    check(lib().creste_nhwc_to_nchw(ptr(x.contiguous()), N, H, W, Cc, ptr(out), stream()),
+          "creste_nhwc_to_nchw")
+    return out
+
+
+def expert_visitation(traj_rc, map_ds, max_steps, H, W):
+    """traj_rc [B,T,2] fp32 or fp64 CUDA -> counts [B,H,W] (reference loss_utils.py:1055-1116)."""
+    traj_rc = traj_rc.contiguous()
+    assert traj_rc.dtype in (torch.float32, torch.float64)
+    B, T, _ = traj_rc.shape
+    counts = torch.empty(B, H, W, device=traj_rc.device)
+    check(lib().creste_expert_visitation(ptr(traj_rc), int(traj_rc.dtype == torch.float64), B, T,
+                                         C.c_double(float(map_ds)), int(max_steps), H, W,
+                                         ptr(counts), stream()), "creste_expert_visitation")
+    return counts

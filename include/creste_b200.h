@@ -1,0 +1,183 @@
+/*
+ * creste_b200.h -- C ABI of libcreste_b200.so: the sm_100a kernels behind the CREStE
+ * perception->costmap + IRL hot path.
+ *
+ * The reference (ut-amrl/creste_public) is pure Python/PyTorch and has no FFI layer; each entry
+ * point below replaces a group of PyTorch library dispatches inside one reference function
+ * (file:line cited per entry; paths relative to the reference root).  The reference-side
+ * binding is a ctypes stub inside the nn.Module that owns the op -- see INTEGRATION.md.
+ *
+ * Conventions
+ *   - every pointer is a DEVICE pointer borrowed for the duration of the call (PyTorch owns all
+ *     memory); nothing is retained or freed; scratch comes from the caller (`ws`, `ws_bytes`);
+ *   - all tensors are dense, fp32 unless stated; activations of the conv family are NHWC;
+ *   - `stream` is a cudaStream_t passed as void* (use torch.cuda.current_stream().cuda_stream);
+ *     no call synchronises the device unless documented;
+ *   - return value: 0 = ok, otherwise a negative creste error or a positive cudaError_t;
+ *     creste_last_error() returns a thread-local message for the last failure.
+ */
+#ifndef CRESTE_B200_H
+#define CRESTE_B200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define CRESTE_OK 0
+#define CRESTE_ERR_ARG (-1)       /* bad argument / unsupported shape */
+#define CRESTE_ERR_WORKSPACE (-2) /* workspace too small */
+#define CRESTE_ERR_NO_DEVICE (-3) /* no sm_100 device */
+
+int creste_version(void);
+const char* creste_last_error(void);
+/* number of SMs of the current device (0 when no device) */
+int creste_num_sms(void);
+
+/* ---------------------------------------------------------------------------------------------
+ * Value iteration.  Replaces VIN.value_iteration_manual, creste/models/blocks/vin.py:48-80
+ * (stencil weights vin.py:36-46): v<-0; repeat { q = conv3x3(r + gamma*v); v' = max_a q;
+ * delta = max over the WHOLE batch |v'-v| } while delta > thr; then q = conv(r+gamma*v),
+ * pi = softmax_a(q).  One persistent cooperative launch, device-side convergence test.
+ *   r [B,H,W]; v_out [B,H,W]; q_out, pi_out [B,8,H,W] (either may be NULL);
+ *   sweeps_out: DEVICE int[2] = {number of sweeps K, 1 if max_sweeps was hit};
+ *   ws: >= creste_vi_workspace_bytes(B,H,W,max_sweeps) bytes. */
+size_t creste_vi_workspace_bytes(int B, int H, int W, int max_sweeps);
+int creste_vi_solve(const float* r, float* v_out, float* q_out, float* pi_out, int B, int H,
+                    int W, float gamma, float thr, int max_sweeps, int* sweeps_out, void* ws,
+                    size_t ws_bytes, void* stream);
+
+/* ---------------------------------------------------------------------------------------------
+ * Expected state-visitation frequency + greedy rollout.  Replaces
+ * MaxEntIRL.expected_state_visitation_frequency, creste/models/lfd.py:156-277 and
+ * earliest_pose_in_fov, creste/utils/train_utils.py:765-803.
+ *   policy [B,8,H,W]; expert_rc [B,T,2] = expert[:,:,:2,2] (row, col; un-pooled BEV cells);
+ *   fov [H,W] uint8; ds = reward_cfg.ds; sharpen/temperature = policy_kwargs;
+ *   exp_svf [B,H,W]; states [B,T,2] int64; states_grid [B,H,W];
+ *   ws: >= creste_svf_workspace_bytes(B,H,W,T). */
+size_t creste_svf_workspace_bytes(int B, int H, int W, int T);
+int creste_svf(const float* policy, const float* expert_rc, const uint8_t* fov, int B, int H, int W,
+               int T, int ds, int sharpen, float temperature, int zero_terminal_state,
+               float* exp_svf, int64_t* states, float* states_grid, void* ws, size_t ws_bytes,
+               void* stream);
+
+/* ---------------------------------------------------------------------------------------------
+ * Camera frustum -> LiDAR xyz -> BEV voxel coordinates.  Replaces Camera2World.forward
+ * (creste/models/blocks/splat_projection.py:19-51), the bounds mask (:169) and
+ * _points_to_voxels (:175-189).
+ *   depth [N,Hs,Ws] metres; p2p [N,4,4]; range[6] = point_cloud_range; voxel[2] (host floats);
+ *   xy [N,P,2] float voxel coords (the reference's `bev_coords`), z [N,P], mask [N,P] uint8. */
+int creste_frustum_to_bev(const float* depth, const float* p2p, int N, int Hs, int Ws,
+                          const float* range_host6, const float* voxel_host2, float* xy, float* z,
+                          uint8_t* mask, void* stream);
+
+/* z -> MLP(1->64->32, ReLU) and concat with the 256 image features into one NHWC row per point.
+ * Replaces splat_projection.py:152-158 (z_proj) + the torch.cat at :158.
+ *   feats NHWC [NP, C]; z [NP]; w1[64], b1[64], w2[32,64], b2[32]; out NHWC [NP, C+32]. */
+int creste_zmlp_concat(const float* feats, const float* z, int NP, int C, const float* w1,
+                       const float* b1, const float* w2, const float* b2, float* out, void* stream);
+
+/* Bilinear 4-tap scatter-add splat with mean normalisation.  Replaces
+ * Camera2MapMulti.splat_soft, creste/models/blocks/splat_projection.py:262-354
+ * (scatter_mode='mean') and the `feats * xyz_mask` at :219.
+ *   xy [N,P,2]; feats NHWC [N,P,F]; mask [N,P] uint8 (NULL = all ones);
+ *   bev_nhwc [N,H,W,F] (may be NULL), bev_nchw [N,F,H,W] (may be NULL), dens [N,H,W];
+ *   idx_out [N,P,4] int64 (may be NULL): linear cell index of each tap in the reference's
+ *   (xdiff,ydiff) loop order, -1 when the tap is out of bounds -- the bit-exact criterion.
+ *   ws: >= N*H*W*F*4 bytes (accumulator) */
+size_t creste_splat_workspace_bytes(int N, int H, int W, int F);
+int creste_splat_soft(const float* xy, const float* feats, const uint8_t* mask, int N, int P, int F,
+                      int H, int W, float min_weight, float* bev_nhwc, float* bev_nchw, float* dens,
+                      int64_t* idx_out, void* ws, size_t ws_bytes, void* stream);
+
+/* ---------------------------------------------------------------------------------------------
+ * LiDAR -> sparse depth raster.  Replaces pixels_to_depth, creste/utils/projection.py:64-134
+ * (float64 projection, truncation to int32, per-pixel max) and the mm quantisation of
+ * scripts/preprocessing/build_dense_depth.py:461-463.
+ *   pc [npts, stride] float32 (xyz first); P34 host double[12] (lidar2camrect);
+ *   depth_m [H,W] float32 (may be NULL), depth_mm [H,W] float32 (may be NULL);
+ *   ws: >= H*W*8 bytes. */
+int creste_lidar_raster(const float* pc, int npts, int stride, const double* P34_host, int H, int W,
+                        float* depth_m, float* depth_mm, void* ws, size_t ws_bytes, void* stream);
+
+/* Softmax-expectation metric depth + arg-max bin.  Replaces
+ * convert_to_metric_depth_differentiable, creste/utils/depth_utils.py:300-313 and
+ * DepthCompletion._convert_to_metric_depth, creste/models/depth.py:60-100.
+ *   logits NHWC [NP, D] (D = 128); metric [NP] metres; bins [NP] int64. */
+int creste_depth_expectation(const float* logits, int NP, int D, float depth_min_mm,
+                             float depth_max_mm, float* metric, int64_t* bins, void* stream);
+
+/* ---------------------------------------------------------------------------------------------
+ * Convolution family (NHWC, fp32 storage).  One descriptor covers every dense conv / linear on
+ * the path: F.conv2d + BatchNorm(eval) + activation (+ residual) as issued
+ * by creste/models/blocks/effnet.py:12-28,74; conv.py:22-29,48-55,63-85; inpainting.py:52-68,
+ * 96-109; torchvision BasicBlock; efficientnet_pytorch MBConv 1x1 convs. */
+typedef struct {
+  int N, H, W, C;       /* input NHWC */
+  int K;                /* output channels */
+  int R, S;             /* filter height, width */
+  int stride;
+  int pad_t, pad_l;     /* zero padding on top / left (bottom/right implied by P, Q) */
+  int P, Q;             /* output height, width */
+  int act;              /* 0 none, 1 relu, 2 swish, 3 sigmoid */
+  int out_nchw;         /* 0: out is NHWC [N,P,Q,K]; 1: out is NCHW [N,K,P,Q] */
+  int precision;        /* 0: fp32 FFMA (exact fp32 products, CUDA cores);
+                           1: 3xTF32 split on tcgen05 (fp32-faithful);
+                           2: single-pass TF32 on tcgen05; 3: single-pass BF16 on tcgen05 */
+} creste_conv_desc;
+
+/* w_packed: [R*S*C, K] row-major (k index = (r*S+s)*C + c); scale/shift [K] (folded BN / bias;
+ * NULL = 1 / 0); gate [N,C] multiplies the input per (n,c) (SE gate; NULL = none);
+ * residual NHWC [N,P,Q,K] added before the activation (NULL = none). */
+int creste_conv2d(const creste_conv_desc* d, const float* x, const float* w_packed,
+                  const float* scale, const float* shift, const float* gate, const float* residual,
+                  float* out, void* ws, size_t ws_bytes, void* stream);
+size_t creste_conv2d_workspace_bytes(const creste_conv_desc* d);
+
+/* Depthwise conv + folded BN + swish, also accumulating the per-(n,c) spatial sum that the SE
+ * block needs (efficientnet_pytorch MBConvBlock: _depthwise_conv -> _bn1 -> swish -> avg-pool).
+ *   x NHWC [N,H,W,C]; w [R*S, C]; out NHWC [N,P,Q,C]; chan_sum [N,C] (zeroed by the call). */
+int creste_dwconv_bn_swish(const float* x, const float* w, const float* scale, const float* shift,
+                           int N, int H, int W, int C, int R, int stride, int pad_t, int pad_l,
+                           int P, int Q, float* out, float* chan_sum, void* stream);
+
+/* SE gate: mean -> 1x1 reduce(+b) -> swish -> 1x1 expand(+b) -> sigmoid.
+ *   chan_sum [N,C]; w_red [Csq,C], b_red [Csq], w_exp [C,Csq], b_exp [C]; gate [N,C]. */
+int creste_se_gate(const float* chan_sum, float inv_hw, int N, int C, int Csq, const float* w_red,
+                   const float* b_red, const float* w_exp, const float* b_exp, float* gate,
+                   void* stream);
+
+/* cat([skip, bilinear_upsample(x, align_corners=False)], channel) in NHWC.  Replaces nn.Upsample +
+ * torch.cat in Up.forward (creste/models/blocks/effnet.py:26-28), DeconvHead.up2[0]
+ * (inpainting.py:56) and MultiScaleFCN trunk upsample (conv.py:128).
+ *   skip NHWC [N,Ho,Wo,Cs] (NULL / Cs = 0: no concat); x NHWC [N,Hi,Wi,Cx];
+ *   rh, rw: source-per-destination ratios (1/scale_factor); out NHWC [N,Ho,Wo,Cs+Cx]. */
+int creste_upsample_concat(const float* skip, int Cs, const float* x, int N, int Hi, int Wi, int Cx,
+                           int Ho, int Wo, float rh, float rw, float* out, void* stream);
+
+/* 2x2/2 max-pool over the channel-concatenation of up to 3 NCHW or NHWC sources, cropped to the
+ * first `rows_out` output rows.  Replaces vin.py:104-115 (cat + max_pool2d + crop) and
+ * conv.py:117 (trunk MaxPool2d).   srcs: `nsrc` NHWC tensors [N,H,W,Ci]; out NHWC
+ * [N,rows_out,W/2,sum Ci]; out_nchw (may be NULL) [N,sum Ci,rows_out,W/2]. */
+int creste_maxpool2_concat(const float* const* srcs_host, const int* chans_host, int nsrc, int N,
+                           int H, int W, int rows_out, float* out_nhwc, float* out_nchw,
+                           void* stream);
+
+/* layout shuffles used at the module boundary (the reference's tensors are NCHW) */
+int creste_nchw_to_nhwc(const float* in, int N, int C, int H, int W, float* out, void* stream);
+int creste_nhwc_to_nchw(const float* in, int N, int H, int W, int C, float* out, void* stream);
+
+/* Expert / counterfactual visitation raster.  Replaces MaxEntIRLLoss.compute_expert_visitation,
+ * creste/utils/loss_utils.py:1055-1116 (second definition).
+ *   traj [B,T,2] (row,col) float32 (is_f64 = 0) or float64 (is_f64 = 1), un-pooled cells;
+ *   max_steps: host int = ceil(max segment length) (the reference's `.item()` sync);
+ *   counts [B,H,W] in {0,1}. */
+int creste_expert_visitation(const void* traj, int is_f64, int B, int T, double map_ds,
+                             int max_steps, int H, int W, float* counts, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* CRESTE_B200_H */

@@ -104,7 +104,7 @@ using namespace creste;
 extern "C" int creste_lidar_raster(const float* pc, int npts, int stride, const double* P34_host,
                                    int H, int W, float* depth_m, float* depth_mm, void* ws,
                                    size_t ws_bytes, void* stream) {
-  CRESTE_CHECK_ARG(pc && P34_host && ws, "creste_lidar_raster: null pointer");
+  CRESTE_CHECK_ARG((pc || npts == 0) && P34_host && ws, "creste_lidar_raster: null pointer");
   CRESTE_CHECK_ARG(npts >= 0 && stride >= 3 && H > 0 && W > 0, "creste_lidar_raster: bad shape");
   const size_t need = (size_t)H * W * 8;
   if (ws_bytes < need) {

@@ -1,0 +1,97 @@
+"""Host-side execution helpers shared by the mirrored modules: BatchNorm folding, weight
+packing caches and the global precision policy of the conv family.
+
+Nothing here computes on the CPU at run time: folding and packing are a handful of tiny
+tensor ops executed on the GPU once per parameter version, cached, and reused every frame.
+"""
+import torch
+
+from . import ops
+
+_PRECISION = "fp32"
+
+
+def set_precision(mode):
+    """Conv-family arithmetic: 'fp32' (FFMA, exact products), '3xtf32' (tcgen05, fp32-faithful
+    split), 'tf32' / 'bf16' (tcgen05 single pass; measured error is reported, never asserted)."""
+    global _PRECISION
+    assert mode in ops.PRECISION, mode
+    _PRECISION = mode
+
+
+def get_precision():
+    return _PRECISION
+
+
+def require_eval(module):
+    if module.training:
+        raise NotImplementedError(
+            f"{type(module).__name__}: training-mode forward (BatchNorm batch statistics, "
+            "drop-connect, autograd) is not implemented in creste_public_b200 yet; call "
+            ".eval() -- the reference semantics for inference (running statistics) are what "
+            "the sm_100a engine implements.  No PyTorch fallback is provided on purpose.")
+
+
+def _ver(*tensors):
+    return tuple((t.data_ptr(), t._version, str(t.device)) for t in tensors if t is not None)
+
+
+class PackCache:
+    """Per-module cache of device-side packed tensors, invalidated by parameter version."""
+
+    def __init__(self):
+        self._store = {}
+
+    def get(self, key, tensors, builder):
+        v = _ver(*tensors)
+        hit = self._store.get(key)
+        if hit is not None and hit[0] == v:
+            return hit[1]
+        with torch.no_grad():
+            val = builder()
+        self._store[key] = (v, val)
+        return val
+
+
+def bn_scale_shift(bn, conv_bias=None):
+    """Eval-mode BatchNorm as y = x*scale + shift, with an optional preceding conv bias."""
+    scale = bn.weight / torch.sqrt(bn.running_var + bn.eps)
+    shift = bn.bias - bn.running_mean * scale
+    if conv_bias is not None:
+        shift = shift + conv_bias * scale
+    return scale.float().contiguous(), shift.float().contiguous()
+
+
+class FusedConv:
+    """conv (+bias) (+BN eval) packed for creste_conv2d; built lazily from live parameters."""
+
+    def __init__(self, conv, bn=None):
+        self.conv, self.bn = conv, bn
+        self.cache = PackCache()
+
+    def packed(self):
+        conv, bn = self.conv, self.bn
+        tensors = [conv.weight, conv.bias] + ([bn.weight, bn.bias, bn.running_mean, bn.running_var]
+                                              if bn is not None else [])
+
+        def build():
+            w = ops.pack_conv_weight(conv.weight.detach().float())
+            if bn is not None:
+                scale, shift = bn_scale_shift(bn, conv.bias)
+            else:
+                scale = None
+                shift = conv.bias.detach().float().contiguous() if conv.bias is not None else None
+            return w, scale, shift
+        return self.cache.get("w", tensors, build)
+
+    def __call__(self, x_nhwc, act="none", pad=None, gate=None, residual=None, out_nchw=False,
+                 precision=None):
+        conv = self.conv
+        w, scale, shift = self.packed()
+        K, _, R, S = conv.weight.shape
+        if pad is None:
+            ph, pw = conv.padding if isinstance(conv.padding, tuple) else (conv.padding,) * 2
+            pad = (ph, ph, pw, pw)
+        stride = conv.stride[0] if isinstance(conv.stride, tuple) else conv.stride
+        return ops.conv2d(x_nhwc, w, K, R, S, stride, pad, scale, shift, gate, residual, act,
+                          out_nchw, precision or _PRECISION)

@@ -1,0 +1,106 @@
+"""Mirror of reference creste/models/blocks/splat_projection.py: Camera2World (:12-51) and
+Camera2MapMulti (:53-354), eval mode, scatter_mode='mean', mode='bilinear'.
+
+Kernels (include/creste_b200.h): creste_frustum_to_bev (un-projection, bounds mask, voxel
+coordinates -- bit-exact indices), creste_zmlp_concat (z-MLP + concat), creste_conv2d (1x1 fusion
+conv + BN + ReLU), creste_splat_soft (bilinear scatter-add + mean normalisation).
+"""
+import torch
+from torch import nn
+
+from creste_public_b200 import ops
+from creste_public_b200.engine import PackCache, require_eval
+from .conv import ConvEncoder
+
+
+class Camera2World(nn.Module):
+    """depth [B,N,H,W] + p2p [B,N,4,4] -> xyz [B,N,3,H,W] in the LiDAR frame."""
+
+    def forward(self, x):
+        raise NotImplementedError(
+            "Camera2World is fused into creste_frustum_to_bev (xyz is never materialised); "
+            "use Camera2MapMulti.frustum(depth, p2p) for xy / z / mask")
+
+
+class Camera2MapMulti(nn.Module):
+    def __init__(self, model_cfg, mode="bilinear", scatter_mode="mean"):
+        super().__init__()
+        self.model_cfg = model_cfg
+        self.register_buffer("point_cloud_range", torch.tensor(model_cfg.point_cloud_range))
+        self.register_buffer("max_bound", self.point_cloud_range[3:].reshape(1, -1))
+        self.register_buffer("min_bound", self.point_cloud_range[:3].reshape(1, -1))
+        self.register_buffer("voxel_size", torch.tensor(model_cfg.voxel_size))
+        self.register_buffer("grid_size", ((self.point_cloud_range[3:] - self.point_cloud_range[:3])
+                                           / self.voxel_size).long())
+        self.register_buffer("lidar2map", torch.tensor([
+            [0, -1, 0, -self.min_bound[0, 0]], [-1, 0, 0, -self.min_bound[0, 1]],
+            [0, 0, -1, -self.min_bound[0, 2]], [0, 0, 0, 1]]).float())
+        if mode != "bilinear":
+            raise Exception("Unknown splat mode:", mode)
+        if scatter_mode != "mean":
+            raise NotImplementedError("only scatter_mode='mean' is on the hot path (the 'max' branch "
+                                      "is used by the disabled multiview distillation only)")
+        self.mode, self.scatter_mode, self.min_weight = mode, scatter_mode, 1.0
+        self.NC = model_cfg.get("num_cams", 2)
+        self.cam2world = Camera2World()
+        if model_cfg["z_embed_mode"] != "mlp":
+            raise Exception("Unknown z_embed_mode:", model_cfg["z_embed_mode"])
+        zd = model_cfg["z_embed_dim"]
+        self.z_proj = nn.Sequential(nn.Linear(1, zd * 2, bias=True), nn.ReLU(),
+                                    nn.Linear(zd * 2, zd, bias=True), nn.ReLU())
+        self.vision_fusion = ConvEncoder(model_cfg.vision_fusion)
+        self._cache = PackCache()
+        self._host_geom = None
+
+    def _geom(self):
+        """point_cloud_range / voxel_size / grid as host floats (read once; they are buffers)."""
+        if self._host_geom is None:
+            self._host_geom = ([float(v) for v in self.point_cloud_range.tolist()],
+                               [float(v) for v in self.voxel_size.tolist()],
+                               [int(v) for v in self.grid_size.tolist()])
+        return self._host_geom
+
+    def frustum(self, depth, p2p):
+        """depth [M,Hs,Ws], p2p [M,4,4] -> xy [M,P,2], z [M,P], mask [M,P]."""
+        rng, vox, _ = self._geom()
+        return ops.frustum_to_bev(depth, p2p, rng, vox)
+
+    def forward_nhwc(self, depth, feats_nhwc, p2p, want_nchw=True):
+        """depth [M,Hs,Ws] (m), feats NHWC [M,Hs,Ws,F], p2p [M,4,4]; NC == 1 (one camera per
+        BEV map, `num_cams: 1` in the shipped configs)."""
+        require_eval(self)
+        if self.NC != 1:
+            raise NotImplementedError("num_cams != 1 is not used by the shipped configs")
+        if self.z_proj[0].out_features != 64 or self.z_proj[2].out_features != 32:
+            raise NotImplementedError("creste_zmlp_concat is specialised for z_embed_dim = 32")
+        M, Hs, Ws, F = feats_nhwc.shape
+        _, _, grid = self._geom()
+        xy, z, mask = self.frustum(depth, p2p)
+        l0, l2 = self.z_proj[0], self.z_proj[2]
+        w1, b1, w2, b2 = self._cache.get(
+            "z", [l0.weight, l0.bias, l2.weight, l2.bias],
+            lambda: (l0.weight.detach().float().reshape(-1).contiguous(),
+                     l0.bias.detach().float().contiguous(),
+                     l2.weight.detach().float().contiguous(), l2.bias.detach().float().contiguous()))
+        cat = ops.zmlp_concat(feats_nhwc, z, w1, b1, w2, b2)
+        fused = self.vision_fusion.forward_nhwc(cat)                     # [M,Hs,Ws,96]
+        Cf = fused.shape[-1]
+        # grid_size = (nx, ny, nz); the BEV map is [grid[0] rows, grid[1] cols] (:248-250)
+        out = ops.splat_soft(xy, fused.view(M, Hs * Ws, Cf), mask, grid[0], grid[1], self.min_weight,
+                             want_nhwc=True, want_nchw=want_nchw)
+        ret = {"bev_densities": out["dens"], "bev_coords": xy}
+        if want_nchw:
+            ret["bev_features"] = out["bev_nchw"]
+        return ret, out["bev_nhwc"]
+
+    def forward(self, x):
+        assert len(x) >= 3, "Input must contain depth, features and camera projection matrix."
+        if len(x) == 4 and self.training:
+            raise NotImplementedError("movability masks are a training-only branch")
+        depth, feats, p2p = x[:3]
+        B, N, F, H, W = feats.shape
+        assert N % self.NC == 0, f"Number of frames must be divisible by {self.NC}"
+        f = ops.nchw_to_nhwc(feats.reshape(B * N, F, H, W).float())
+        ret, _ = self.forward_nhwc(depth.reshape(B * N, H, W).float(), f,
+                                   p2p.reshape(B * N, 4, 4).float())
+        return ret

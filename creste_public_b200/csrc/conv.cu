@@ -14,8 +14,10 @@ bool conv_tc_supported(const creste_conv_desc* d);
 
 // ---- depthwise conv + folded BN + swish + per-(n,c) spatial sum (for the SE block).
 // NHWC: one thread per (pixel, 4-channel group); consecutive threads = consecutive channel
-// groups, so every tap is a coalesced float4 load.  The SE sum is reduced per block in shared
-// memory (block = 64 pixels x C4 groups slice) then one atomicAdd per (block, channel).
+// groups, so every tap is a coalesced float4 load.  The SE sum is reduced in a FIXED order
+// (per-thread sequential -> shared memory across the block's pixel lanes -> one partial row per
+// block; creste_se_gate adds the rows in order): no atomics, bit-reproducible run to run, which
+// matters because the encoder->depth->splat chain amplifies 1e-7 perturbations.
 template <int R>
 __global__ void __launch_bounds__(256) dwconv_kernel(const float* __restrict__ x,
                                                      const float* __restrict__ w,
@@ -23,8 +25,9 @@ __global__ void __launch_bounds__(256) dwconv_kernel(const float* __restrict__ x
                                                      const float* __restrict__ shift, int N, int H,
                                                      int W, int C, int stride, int pad_t, int pad_l,
                                                      int P, int Q, float* __restrict__ out,
-                                                     float* __restrict__ chan_sum) {
-  // grid: x = pixel tiles of PIX_PER_BLOCK within one image, y = image
+                                                     float* __restrict__ chan_part) {
+  // grid: x = pixel tiles within one image, y = image; chan_part [N, gridDim.x, C]
+  __shared__ float4 s_part[256];
   const int C4 = C / 4;
   const int n = blockIdx.y;
   const int PQ = P * Q;
@@ -38,6 +41,7 @@ __global__ void __launch_bounds__(256) dwconv_kernel(const float* __restrict__ x
     const int cg = cg0 + (threadIdx.x % cgs);
     const int pl = threadIdx.x / cgs;
     float4 sum = make_float4(0.f, 0.f, 0.f, 0.f);
+    __syncthreads();
     if (pl < lanes) {
       const float4 sc = __ldg(reinterpret_cast<const float4*>(scale) + cg);
       const float4 sh = __ldg(reinterpret_cast<const float4*>(shift) + cg);
@@ -70,16 +74,24 @@ __global__ void __launch_bounds__(256) dwconv_kernel(const float* __restrict__ x
         reinterpret_cast<float4*>(out + ((size_t)n * PQ + pix) * C)[cg] = o;
         sum.x += o.x; sum.y += o.y; sum.z += o.z; sum.w += o.w;
       }
-      float* cs = chan_sum + (size_t)n * C + cg * 4;
-      atomicAdd(cs + 0, sum.x); atomicAdd(cs + 1, sum.y);
-      atomicAdd(cs + 2, sum.z); atomicAdd(cs + 3, sum.w);
+    }
+    s_part[threadIdx.x] = sum;
+    __syncthreads();
+    if (pl == 0 && threadIdx.x < cgs) {
+      float4 tot = s_part[threadIdx.x];
+      for (int l = 1; l < lanes; ++l) {
+        const float4 o = s_part[l * cgs + threadIdx.x];
+        tot.x += o.x; tot.y += o.y; tot.z += o.z; tot.w += o.w;
+      }
+      reinterpret_cast<float4*>(chan_part + ((size_t)n * gridDim.x + blockIdx.x) * C)[cg] = tot;
     }
   }
 }
 
 // ---- SE gate: one block per image
-__global__ void __launch_bounds__(256) se_gate_kernel(const float* __restrict__ chan_sum, float inv_hw,
-                                                      int C, int Csq, const float* __restrict__ w_red,
+__global__ void __launch_bounds__(256) se_gate_kernel(const float* __restrict__ chan_part, int nparts,
+                                                      float inv_hw, int C, int Csq,
+                                                      const float* __restrict__ w_red,
                                                       const float* __restrict__ b_red,
                                                       const float* __restrict__ w_exp,
                                                       const float* __restrict__ b_exp,
@@ -88,7 +100,11 @@ __global__ void __launch_bounds__(256) se_gate_kernel(const float* __restrict__ 
   float* mean = sm;
   float* sq = sm + C;
   const int n = blockIdx.x;
-  for (int c = threadIdx.x; c < C; c += blockDim.x) mean[c] = chan_sum[(size_t)n * C + c] * inv_hw;
+  for (int c = threadIdx.x; c < C; c += blockDim.x) {
+    float tot = 0.0f;
+    for (int j = 0; j < nparts; ++j) tot += chan_part[((size_t)n * nparts + j) * C + c];
+    mean[c] = tot * inv_hw;
+  }
   __syncthreads();
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nw = blockDim.x >> 5;
   for (int j = warp; j < Csq; j += nw) {
@@ -140,32 +156,36 @@ extern "C" int creste_conv2d(const creste_conv_desc* d, const float* x, const fl
   return conv_tc_launch(d, x, w_packed, scale, shift, gate, residual, out, ws, ws_bytes, st);
 }
 
+extern "C" int creste_dwconv_num_parts(int N, int P, int Q) {
+  // independent of N on purpose: the per-image summation order (hence the result bits) must not
+  // depend on how many frames share the launch (frames are the data-parallel sharding unit)
+  (void)N;
+  const int tiles = ceil_div(P * Q, 64);
+  return tiles > 592 ? 592 : tiles;
+}
+
 extern "C" int creste_dwconv_bn_swish(const float* x, const float* w, const float* scale,
                                       const float* shift, int N, int H, int W, int C, int R,
                                       int stride, int pad_t, int pad_l, int P, int Q, float* out,
-                                      float* chan_sum, void* stream) {
-  CRESTE_CHECK_ARG(x && w && scale && shift && out && chan_sum, "creste_dwconv_bn_swish: null pointer");
+                                      float* chan_part, int nparts, void* stream) {
+  CRESTE_CHECK_ARG(x && w && scale && shift && out && chan_part, "creste_dwconv_bn_swish: null pointer");
   CRESTE_CHECK_ARG(C % 4 == 0 && (R == 3 || R == 5), "creste_dwconv_bn_swish: C%%4==0, R in {3,5}");
+  CRESTE_CHECK_ARG(nparts == creste_dwconv_num_parts(N, P, Q), "creste_dwconv_bn_swish: nparts");
   cudaStream_t st = (cudaStream_t)stream;
-  CRESTE_CUDA(cudaMemsetAsync(chan_sum, 0, (size_t)N * C * sizeof(float), st));
-  const int PQ = P * Q;
-  int tiles = ceil_div(PQ, 64);
-  const int cap = ceil_div(148 * 8, N);
-  if (tiles > cap) tiles = cap;
-  dim3 grid(tiles, N);
+  dim3 grid(nparts, N);
   if (R == 3)
-    dwconv_kernel<3><<<grid, 256, 0, st>>>(x, w, scale, shift, N, H, W, C, stride, pad_t, pad_l, P, Q, out, chan_sum);
+    dwconv_kernel<3><<<grid, 256, 0, st>>>(x, w, scale, shift, N, H, W, C, stride, pad_t, pad_l, P, Q, out, chan_part);
   else
-    dwconv_kernel<5><<<grid, 256, 0, st>>>(x, w, scale, shift, N, H, W, C, stride, pad_t, pad_l, P, Q, out, chan_sum);
+    dwconv_kernel<5><<<grid, 256, 0, st>>>(x, w, scale, shift, N, H, W, C, stride, pad_t, pad_l, P, Q, out, chan_part);
   return launch_check("dwconv_kernel");
 }
 
-extern "C" int creste_se_gate(const float* chan_sum, float inv_hw, int N, int C, int Csq,
+extern "C" int creste_se_gate(const float* chan_part, int nparts, float inv_hw, int N, int C, int Csq,
                               const float* w_red, const float* b_red, const float* w_exp,
                               const float* b_exp, float* gate, void* stream) {
-  CRESTE_CHECK_ARG(chan_sum && w_red && b_red && w_exp && b_exp && gate, "creste_se_gate: null pointer");
+  CRESTE_CHECK_ARG(chan_part && w_red && b_red && w_exp && b_exp && gate && nparts > 0, "creste_se_gate: null pointer");
   const size_t smem = (size_t)(C + Csq) * sizeof(float);
-  se_gate_kernel<<<N, 256, smem, (cudaStream_t)stream>>>(chan_sum, inv_hw, C, Csq, w_red, b_red, w_exp,
+  se_gate_kernel<<<N, 256, smem, (cudaStream_t)stream>>>(chan_part, nparts, inv_hw, C, Csq, w_red, b_red, w_exp,
                                                         b_exp, gate);
   return launch_check("se_gate_kernel");
 }

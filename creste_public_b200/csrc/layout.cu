@@ -31,18 +31,19 @@ __global__ void __launch_bounds__(256) transpose_kernel(const float* __restrict_
 __global__ void __launch_bounds__(256) upsample_concat_kernel(const float* __restrict__ skip, int Cs,
                                                               const float* __restrict__ x, int N,
                                                               int Hi, int Wi, int Cx, int Ho, int Wo,
-                                                              float rh, float rw,
+                                                              float rh, float rw, int x_first,
                                                               float* __restrict__ out) {
   const int Ct = Cs + Cx;
-  const int c4t = Ct / 4, cs4 = Cs / 4;
+  const int c4t = Ct / 4, cs4 = Cs / 4, cx4 = Cx / 4;
   const long long total = (long long)N * Ho * Wo * c4t;
   for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total;
        i += (long long)gridDim.x * blockDim.x) {
     const int c4 = (int)(i % c4t);
     const long long pix = i / c4t;
     float4 v;
-    if (c4 < cs4) {
-      v = __ldg(reinterpret_cast<const float4*>(skip + pix * Cs) + c4);
+    const bool is_skip = x_first ? (c4 >= cx4) : (c4 < cs4);
+    if (is_skip) {
+      v = __ldg(reinterpret_cast<const float4*>(skip + pix * Cs) + (x_first ? c4 - cx4 : c4));
     } else {
       const int ox = (int)(pix % Wo);
       const int oy = (int)((pix / Wo) % Ho);
@@ -53,7 +54,7 @@ __global__ void __launch_bounds__(256) upsample_concat_kernel(const float* __res
       const int y1 = y0 + (y0 < Hi - 1 ? 1 : 0), x1 = x0 + (x0 < Wi - 1 ? 1 : 0);
       const float l1h = __fsub_rn(sy, (float)y0), l0h = __fsub_rn(1.0f, l1h);
       const float l1w = __fsub_rn(sx, (float)x0), l0w = __fsub_rn(1.0f, l1w);
-      const int cc = c4 - cs4;
+      const int cc = x_first ? c4 : c4 - cs4;
       const float* b = x + (size_t)n * Hi * Wi * Cx;
       const float4 v00 = __ldg(reinterpret_cast<const float4*>(b + ((size_t)y0 * Wi + x0) * Cx) + cc);
       const float4 v01 = __ldg(reinterpret_cast<const float4*>(b + ((size_t)y0 * Wi + x1) * Cx) + cc);
@@ -163,14 +164,14 @@ extern "C" int creste_nhwc_to_nchw(const float* in, int N, int H, int W, int C, 
 }
 
 extern "C" int creste_upsample_concat(const float* skip, int Cs, const float* x, int N, int Hi,
-                                      int Wi, int Cx, int Ho, int Wo, float rh, float rw, float* out,
-                                      void* stream) {
+                                      int Wi, int Cx, int Ho, int Wo, float rh, float rw, int x_first,
+                                      float* out, void* stream) {
   CRESTE_CHECK_ARG(x && out, "creste_upsample_concat: null pointer");
   CRESTE_CHECK_ARG((Cs == 0 || skip) && Cs % 4 == 0 && Cx % 4 == 0 && Cx > 0,
                    "creste_upsample_concat: channel counts must be multiples of 4");
   const long long total = (long long)N * Ho * Wo * ((Cs + Cx) / 4);
   upsample_concat_kernel<<<grid_for(total), 256, 0, (cudaStream_t)stream>>>(skip, Cs, x, N, Hi, Wi, Cx,
-                                                                           Ho, Wo, rh, rw, out);
+                                                                           Ho, Wo, rh, rw, x_first, out);
   return launch_check("upsample_concat_kernel");
 }
 

@@ -22,13 +22,13 @@ __constant__ int c_dyn[8][2] = {{-1, -1}, {-1, 0}, {-1, 1}, {0, -1}, {0, 1}, {1,
 
 struct SvfParams {
   const float* policy;      // [B,8,H,W]
-  const float* expert_rc;   // [B,T,2]
+  const float* expert_rc;   // [B,Te,2]
   const uint8_t* fov;       // [H,W]
   float* pol_ws;            // [B,8,Wh*Ww] sharpened policy of the window
   float* exp_svf;           // [B,H,W]   (zeroed by the host wrapper)
   long long* states;        // [B,T,2]
   float* states_grid;       // [B,H,W]   (zeroed by the host wrapper)
-  int B, H, W, T, ds, sharpen, zero_terminal;
+  int B, H, W, T, Te, ds, sharpen, zero_terminal;  // T: horizon, Te: expert poses
   int Wh, Ww;               // window size
   float temperature;
 };
@@ -40,7 +40,7 @@ __global__ void __launch_bounds__(SVF_THREADS) svf_kernel(SvfParams p) {
   extern __shared__ float sm[];  // mu ping-pong: 2 * (Wh+2)*(Ww+2) with a zero halo
   __shared__ int s_pose[4];      // s0r, s0c, s1r, s1c
   const int b = blockIdx.x;
-  const int H = p.H, W = p.W, T = p.T;
+  const int H = p.H, W = p.W, T = p.T, Te = p.Te;
   const int tid = threadIdx.x;
   const size_t HW = (size_t)H * W;
   const float* P = p.policy + (size_t)b * 8 * HW;
@@ -50,15 +50,15 @@ __global__ void __launch_bounds__(SVF_THREADS) svf_kernel(SvfParams p) {
     // else (H-1, W//2) (train_utils.py:765-803); S1 = last pose.
     int s0r = H - 1, s0c = W / 2, s1r = 0, s1c = 0;
     bool found = false;
-    for (int t = 0; t < T; ++t) {
-      const float er = p.expert_rc[((size_t)b * T + t) * 2 + 0];
-      const float ec = p.expert_rc[((size_t)b * T + t) * 2 + 1];
+    for (int t = 0; t < Te; ++t) {
+      const float er = p.expert_rc[((size_t)b * Te + t) * 2 + 0];
+      const float ec = p.expert_rc[((size_t)b * Te + t) * 2 + 1];
       long long rr = (long long)floorf(__fdiv_rn(er, (float)p.ds));
       long long cc = (long long)floorf(__fdiv_rn(ec, (float)p.ds));
       rr = rr < 0 ? 0 : (rr > H - 1 ? H - 1 : rr);
       cc = cc < 0 ? 0 : (cc > W - 1 ? W - 1 : cc);
       if (!found && p.fov[rr * W + cc]) { s0r = (int)rr; s0c = (int)cc; found = true; }
-      if (t == T - 1) { s1r = (int)rr; s1c = (int)cc; }
+      if (t == Te - 1) { s1r = (int)rr; s1c = (int)cc; }
     }
     s_pose[0] = s0r; s_pose[1] = s0c; s_pose[2] = s1r; s_pose[3] = s1c;
   }
@@ -211,12 +211,12 @@ extern "C" size_t creste_svf_workspace_bytes(int B, int H, int W, int T) {
 }
 
 extern "C" int creste_svf(const float* policy, const float* expert_rc, const uint8_t* fov, int B,
-                          int H, int W, int T, int ds, int sharpen, float temperature,
+                          int H, int W, int T, int T_expert, int ds, int sharpen, float temperature,
                           int zero_terminal_state, float* exp_svf, int64_t* states,
                           float* states_grid, void* ws, size_t ws_bytes, void* stream) {
   CRESTE_CHECK_ARG(policy && expert_rc && fov && exp_svf && states && states_grid && ws,
                    "creste_svf: null pointer");
-  CRESTE_CHECK_ARG(B > 0 && H > 0 && W > 0 && T > 0 && ds > 0, "creste_svf: bad shape");
+  CRESTE_CHECK_ARG(B > 0 && H > 0 && W > 0 && T > 0 && T_expert > 0 && ds > 0, "creste_svf: bad shape");
   if (ws_bytes < creste_svf_workspace_bytes(B, H, W, T)) {
     set_error("creste_svf: workspace too small");
     return CRESTE_ERR_WORKSPACE;
@@ -232,7 +232,7 @@ extern "C" int creste_svf(const float* policy, const float* expert_rc, const uin
   p.policy = policy; p.expert_rc = expert_rc; p.fov = fov;
   p.pol_ws = (float*)ws;
   p.exp_svf = exp_svf; p.states = (long long*)states; p.states_grid = states_grid;
-  p.B = B; p.H = H; p.W = W; p.T = T; p.ds = ds; p.sharpen = sharpen;
+  p.B = B; p.H = H; p.W = W; p.T = T; p.Te = T_expert; p.ds = ds; p.sharpen = sharpen;
   p.zero_terminal = zero_terminal_state; p.temperature = temperature;
   const size_t n = (size_t)B * H * W * sizeof(float);
   CRESTE_CUDA(cudaMemsetAsync(exp_svf, 0, n, st));

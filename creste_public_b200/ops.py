@@ -40,19 +40,20 @@ def vi_solve(r, gamma=0.99, thr=1e-3, max_sweeps=4096, want_q=True):
 # ----------------------------------------------------------------------------------------- SVF
 def svf(policy, expert_rc, fov, T, ds=2, sharpen=True, temperature=0.005, zero_terminal=False):
     """Expected SVF + greedy rollout (reference lfd.py:156-277).  policy [B,8,H,W];
-    expert_rc [B,T,2] fp32; fov [H,W] uint8/bool.  Returns exp_svf [B,H,W],
-    states [B,T,2] int64, states_grid [B,H,W]."""
+    expert_rc [B,Te,2] fp32 (Te expert poses; T = action horizon); fov [H,W] uint8/bool.
+    Returns exp_svf [B,H,W], states [B,T,2] int64, states_grid [B,H,W]."""
     policy = policy.contiguous().float()
     expert_rc = expert_rc.contiguous().float()
     fov = fov.to(torch.uint8).contiguous()
     B, A, H, W = policy.shape
-    assert A == 8 and tuple(expert_rc.shape) == (B, T, 2) and tuple(fov.shape) == (H, W)
+    Te = expert_rc.shape[1]
+    assert A == 8 and tuple(expert_rc.shape) == (B, Te, 2) and tuple(fov.shape) == (H, W)
     out = torch.empty(B, H, W, device=policy.device)
     states = torch.empty(B, T, 2, dtype=torch.int64, device=policy.device)
     grid = torch.empty(B, H, W, device=policy.device)
     n = lib().creste_svf_workspace_bytes(B, H, W, T)
     ws = _ws(n, policy.device)
-    check(lib().creste_svf(ptr(policy), ptr(expert_rc), ptr(fov), B, H, W, T, ds,
+    check(lib().creste_svf(ptr(policy), ptr(expert_rc), ptr(fov), B, H, W, T, Te, ds,
                            int(bool(sharpen)), C.c_float(temperature), int(bool(zero_terminal)),
                            ptr(out), ptr(states), ptr(grid), ptr(ws), C.c_size_t(n), stream()),
           "creste_svf")
@@ -173,29 +174,30 @@ def conv2d(x_nhwc, w_packed, K, R, S, stride=1, pad=(0, 0, 0, 0), scale=None, sh
 
 
 def dwconv_bn_swish(x_nhwc, w_rsc, scale, shift, R, stride, pad):
-    """Depthwise conv + BN + swish; returns (out NHWC, chan_sum [N,C])."""
+    """Depthwise conv + BN + swish; returns (out NHWC, chan_part [N,nparts,C] SE partial sums)."""
     N, H, W, Cc = x_nhwc.shape
     pt, pb, pl, pr = pad
     P = (H + pt + pb - R) // stride + 1
     Q = (W + pl + pr - R) // stride + 1
     out = torch.empty(N, P, Q, Cc, device=x_nhwc.device)
-    csum = torch.empty(N, Cc, device=x_nhwc.device)
+    nparts = lib().creste_dwconv_num_parts(N, P, Q)
+    csum = torch.empty(N, nparts, Cc, device=x_nhwc.device)
     check(lib().creste_dwconv_bn_swish(ptr(x_nhwc), ptr(w_rsc), ptr(scale), ptr(shift), N, H, W, Cc,
-                                       R, stride, pt, pl, P, Q, ptr(out), ptr(csum), stream()),
+                                       R, stride, pt, pl, P, Q, ptr(out), ptr(csum), nparts, stream()),
           "creste_dwconv_bn_swish")
     return out, csum
 
 
-def se_gate(chan_sum, hw, w_red, b_red, w_exp, b_exp):
-    N, Cc = chan_sum.shape
+def se_gate(chan_part, hw, w_red, b_red, w_exp, b_exp):
+    N, nparts, Cc = chan_part.shape
     Csq = w_red.shape[0]
-    gate = torch.empty(N, Cc, device=chan_sum.device)
-    check(lib().creste_se_gate(ptr(chan_sum), C.c_float(1.0 / hw), N, Cc, Csq, ptr(w_red), ptr(b_red),
+    gate = torch.empty(N, Cc, device=chan_part.device)
+    check(lib().creste_se_gate(ptr(chan_part), nparts, C.c_float(1.0 / hw), N, Cc, Csq, ptr(w_red), ptr(b_red),
                                ptr(w_exp), ptr(b_exp), ptr(gate), stream()), "creste_se_gate")
     return gate
 
 
-def upsample_concat(skip_nhwc, x_nhwc, out_hw, scale_factor=None):
+def upsample_concat(skip_nhwc, x_nhwc, out_hw, scale_factor=None, x_first=False):
     """cat([skip, bilinear(x)], C) in NHWC.  scale_factor: the nn.Upsample argument (number or
     (sh, sw)); when given, the sampling ratio is 1/scale_factor exactly as PyTorch does."""
     N, Hi, Wi, Cx = x_nhwc.shape
@@ -209,7 +211,8 @@ def upsample_concat(skip_nhwc, x_nhwc, out_hw, scale_factor=None):
     Cs = 0 if skip_nhwc is None else skip_nhwc.shape[-1]
     out = torch.empty(N, Ho, Wo, Cs + Cx, device=x_nhwc.device)
     check(lib().creste_upsample_concat(ptr(skip_nhwc), Cs, ptr(x_nhwc), N, Hi, Wi, Cx, Ho, Wo,
-                                       C.c_float(rh), C.c_float(rw), ptr(out), stream()),
+                                       C.c_float(rh), C.c_float(rw), int(bool(x_first)), ptr(out),
+                                       stream()),
           "creste_upsample_concat")
     return out
 

@@ -53,13 +53,14 @@ int creste_vi_solve(const float* r, float* v_out, float* q_out, float* pi_out, i
  * Expected state-visitation frequency + greedy rollout.  Replaces
  * MaxEntIRL.expected_state_visitation_frequency, creste/models/lfd.py:156-277 and
  * earliest_pose_in_fov, creste/utils/train_utils.py:765-803.
- *   policy [B,8,H,W]; expert_rc [B,T,2] = expert[:,:,:2,2] (row, col; un-pooled BEV cells);
- *   fov [H,W] uint8; ds = reward_cfg.ds; sharpen/temperature = policy_kwargs;
+ *   policy [B,8,H,W]; expert_rc [B,T_expert,2] = expert[:,:,:2,2] (row, col; un-pooled BEV
+ *   cells); T = action_horizon; fov [H,W] uint8; ds = reward_cfg.ds; sharpen/temperature =
+ *   policy_kwargs;
  *   exp_svf [B,H,W]; states [B,T,2] int64; states_grid [B,H,W];
  *   ws: >= creste_svf_workspace_bytes(B,H,W,T). */
 size_t creste_svf_workspace_bytes(int B, int H, int W, int T);
 int creste_svf(const float* policy, const float* expert_rc, const uint8_t* fov, int B, int H, int W,
-               int T, int ds, int sharpen, float temperature, int zero_terminal_state,
+               int T, int T_expert, int ds, int sharpen, float temperature, int zero_terminal_state,
                float* exp_svf, int64_t* states, float* states_grid, void* ws, size_t ws_bytes,
                void* stream);
 
@@ -136,16 +137,21 @@ int creste_conv2d(const creste_conv_desc* d, const float* x, const float* w_pack
                   float* out, void* ws, size_t ws_bytes, void* stream);
 size_t creste_conv2d_workspace_bytes(const creste_conv_desc* d);
 
-/* Depthwise conv + folded BN + swish, also accumulating the per-(n,c) spatial sum that the SE
- * block needs (efficientnet_pytorch MBConvBlock: _depthwise_conv -> _bn1 -> swish -> avg-pool).
- *   x NHWC [N,H,W,C]; w [R*S, C]; out NHWC [N,P,Q,C]; chan_sum [N,C] (zeroed by the call). */
+/* Depthwise conv + folded BN + swish, also producing the per-(n,c) spatial partial sums that the
+ * SE block needs (efficientnet_pytorch MBConvBlock: _depthwise_conv -> _bn1 -> swish -> avg-pool).
+ * Partial sums are written per pixel tile in a fixed order (no atomics: bit-reproducible).
+ *   x NHWC [N,H,W,C]; w [R*S, C]; out NHWC [N,P,Q,C];
+ *   chan_part [N, nparts, C] with nparts = creste_dwconv_num_parts(N, P, Q). */
+int creste_dwconv_num_parts(int N, int P, int Q);
 int creste_dwconv_bn_swish(const float* x, const float* w, const float* scale, const float* shift,
                            int N, int H, int W, int C, int R, int stride, int pad_t, int pad_l,
-                           int P, int Q, float* out, float* chan_sum, void* stream);
+                           int P, int Q, float* out, float* chan_part, int nparts, void* stream);
 
 /* SE gate: mean -> 1x1 reduce(+b) -> swish -> 1x1 expand(+b) -> sigmoid.
- *   chan_sum [N,C]; w_red [Csq,C], b_red [Csq], w_exp [C,Csq], b_exp [C]; gate [N,C]. */
-int creste_se_gate(const float* chan_sum, float inv_hw, int N, int C, int Csq, const float* w_red,
+ *   chan_part [N,nparts,C] (summed in order); w_red [Csq,C], b_red [Csq], w_exp [C,Csq],
+ *   b_exp [C]; gate [N,C]. */
+int creste_se_gate(const float* chan_part, int nparts, float inv_hw, int N, int C, int Csq,
+                   const float* w_red,
                    const float* b_red, const float* w_exp, const float* b_exp, float* gate,
                    void* stream);
 
@@ -153,9 +159,12 @@ int creste_se_gate(const float* chan_sum, float inv_hw, int N, int C, int Csq, c
  * torch.cat in Up.forward (creste/models/blocks/effnet.py:26-28), DeconvHead.up2[0]
  * (inpainting.py:56) and MultiScaleFCN trunk upsample (conv.py:128).
  *   skip NHWC [N,Ho,Wo,Cs] (NULL / Cs = 0: no concat); x NHWC [N,Hi,Wi,Cx];
- *   rh, rw: source-per-destination ratios (1/scale_factor); out NHWC [N,Ho,Wo,Cs+Cx]. */
+ *   rh, rw: source-per-destination ratios (1/scale_factor); out NHWC [N,Ho,Wo,Cs+Cx];
+ *   x_first = 0: channels [skip, up(x)] (Up.forward); 1: [up(x), skip] (MultiScaleFCN.forward,
+ *   conv.py:156). */
 int creste_upsample_concat(const float* skip, int Cs, const float* x, int N, int Hi, int Wi, int Cx,
-                           int Ho, int Wo, float rh, float rw, float* out, void* stream);
+                           int Ho, int Wo, float rh, float rw, int x_first, float* out,
+                           void* stream);
 
 /* 2x2/2 max-pool over the channel-concatenation of up to 3 NCHW or NHWC sources, cropped to the
  * first `rows_out` output rows.  Replaces vin.py:104-115 (cat + max_pool2d + crop) and

@@ -134,7 +134,7 @@ def depth_completion(sd, x, image_size):
     logits = F.relu(_bn(F.conv2d(feats, sd[PFX_DEPTH + "0.weight"], sd[PFX_DEPTH + "0.bias"],
                                  padding=1), sd, PFX_DEPTH + "1"))
     probs = F.softmax(logits, dim=1)
-    vals = torch.linspace(300, 25600, 128).view(1, -1, 1, 1)
+    vals = torch.linspace(300, 25600, 128).to(logits.dtype).view(1, -1, 1, 1)
     metric = torch.sum(probs * vals, dim=1) / 1000
     return {"depth_preds_logits": logits, "depth_preds_metric": metric,
             "depth_preds_bins": logits.argmax(dim=1), "depth_preds_feats": feats}
@@ -237,12 +237,23 @@ def vin_forward(sd, feat_map, ds=2,
 
 
 @torch.no_grad()
-def forward(sd, rgbd, p2p):
-    """rgbd [B,1,4,H,W], p2p [B,1,4,4] -> the reference's output dict (solve_mdp=False)."""
+def forward(sd, rgbd, p2p, encoder_fp64=False):
+    """rgbd [B,1,4,H,W], p2p [B,1,4,4] -> the reference's output dict (solve_mdp=False).
+
+    encoder_fp64=True evaluates the RGB-D encoder + depth head in float64 (i.e. exactly) and
+    hands the rounded result to the unchanged fp32 rest: the distance between that output and
+    the plain fp32 one measures how far the reference's OWN rounding noise moves each tensor
+    (the conditioning yardstick of the end-to-end parity test)."""
     B, V, C, H, W = rgbd.shape
     assert V == 1
     x = rgbd.view(B, C, H, W)
-    out = depth_completion(sd, x, (H, W))
+    if encoder_fp64:
+        sd64 = {k: (v.double() if v.is_floating_point() else v) for k, v in sd.items()
+                if k.startswith("backbone.depthcomp.")}
+        out = depth_completion(sd64, x.double(), (H, W))
+        out = {k: (v.float() if v.is_floating_point() else v) for k, v in out.items()}
+    else:
+        out = depth_completion(sd, x, (H, W))
     out["dino_pe_feats"] = dino_head(sd, out["depth_preds_feats"]).unsqueeze(1)
     bev = cam2map(sd, out["depth_preds_metric"], out["depth_preds_feats"], p2p.view(B, 4, 4))
     out.update({k: v for k, v in bev.items()})

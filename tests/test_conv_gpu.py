@@ -81,7 +81,7 @@ def test_dwconv_se(cuda, C, R, stride, pad):
                                     w.to(cuda).permute(2, 3, 1, 0).reshape(R * R, C).contiguous(),
                                     scale.to(cuda), shift.to(cuda), R, stride, pad)
     _close(out.cpu().permute(0, 3, 1, 2), y)
-    _close(csum.cpu(), y.sum(dim=(2, 3)), 1e-4)
+    _close(csum.cpu().sum(dim=1), y.sum(dim=(2, 3)), 1e-4)
     Csq = max(1, C // 24)
     wr, br = torch.randn(Csq, C, generator=g) / C ** 0.5, torch.randn(Csq, generator=g) * 0.1
     we, be = torch.randn(C, Csq, generator=g) / Csq ** 0.5, torch.randn(C, generator=g) * 0.1

@@ -1,0 +1,354 @@
+#!/usr/bin/env python
+"""bench.py -- headline benchmark of the CREStE perception->costmap hot path on B200.
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--batch B] [--precision fp32|3xtf32|...]
+    python bench.py --impl reference ...      # the reference algorithm on the host CPU cores
+
+Metric (BASELINE.json): frames/sec RGB+LiDAR -> BEV costmap @ 960x512.  Workload = configs[1]:
+per frame one 3x512x960 RGB image + one 128x1024-beam OS1 LiDAR sweep (131072 points) ->
+LiDAR depth raster (mm) -> MaxEntIRL.forward((rgbd, p2p)) -> full reference output dict incl. the
+costmap `traversability_preds`.  Synthetic inputs, seeded random weights (no network here).
+
+One "step" = `--batch` frames through the whole path on each GPU.  `value` = frames/s with the
+inputs already resident in HBM; `e2e` = the same through the public module API with pinned HOST
+buffers (H2D of RGB + LiDAR + p2p and D2H of the costmap inside the timed region).  N > 1 is
+launched by torchrun, one rank per GPU, frames sharded across ranks with no data-path
+collective (weak scaling); time = max over ranks, measured with CUDA events.
+
+Extra objects in the JSON line: `roofline` (dominant conv kernel, tensor bound), `cpu_baseline`
+(oracle port on the host cores, rank 0, N = 1 only), `irl` (VI + SVF at 256x256, HBM bound),
+`clocks`, `gpu_launches`.
+"""
+import argparse
+import json
+import os
+import statistics
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+H, W = 512, 960
+NPTS = 131072
+GFLOP_PER_FRAME = 657.5          # BASELINE.md section 2 (2*MAC, dead _conv_head excluded)
+METRIC = "frames/sec RGB+LiDAR->BEV costmap @ 960x512"
+
+
+def load_peaks():
+    try:
+        with open(os.path.join(ROOT, "MEASURED_PEAKS.json")) as f:
+            p = json.load(f)
+        return {"hbm_gbs": p["hbm_gbs"], "bf16_burst": p["bf16_tflops"],
+                "bf16_sustained": p["bf16_tflops_sustained"], "src": "measured"}
+    except Exception:  # noqa: BLE001
+        return {"hbm_gbs": 6650.0, "bf16_burst": 1590.0, "bf16_sustained": 1400.0, "src": "fallback"}
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons sampled DURING the timed region."""
+    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,"
+         "clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+         "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, gpu_index):
+        self.idx, self.proc, self.lines = gpu_index, None, []
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(
+                ["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-lms", "100",
+                 "-i", str(self.idx)], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.thr = threading.Thread(target=self._read, daemon=True)
+            self.thr.start()
+        except Exception:  # noqa: BLE001
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.lines.append(line.strip())
+
+    def stop(self):
+        if self.proc is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        time.sleep(0.15)
+        self.proc.terminate()
+        sm, smax, reasons = [], [], set()
+        for l in self.lines:
+            f = [x.strip() for x in l.split(",")]
+            if len(f) < 9:
+                continue
+            try:
+                sm.append(float(f[1]))
+                smax.append(float(f[2]))
+            except ValueError:
+                continue
+            for name, v in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown",
+                                "sw_power_cap"), f[5:9]):
+                if v.lower().startswith("active"):
+                    reasons.add(name)
+        return {"sm_mhz": statistics.median(sm) if sm else None,
+                "sm_max_mhz": max(smax) if smax else None, "reasons": sorted(reasons),
+                "samples": len(sm)}
+
+
+def dist_env():
+    rank = int(os.environ.get("RANK", 0))
+    local = int(os.environ.get("LOCAL_RANK", 0))
+    world = int(os.environ.get("WORLD_SIZE", 1))
+    return rank, local, world
+
+
+# ------------------------------------------------------------------------------- reference arm
+def cpu_forward_baseline(steps, warmup, seed=0):
+    """The reference's algorithm for this path on the host cores: the torch-CPU fp32 oracle port
+    (oracle/net_oracle.py -- the reference itself is Python and cannot travel to this box) on a
+    bounded sample: 1 frame per step."""
+    import torch
+    from oracle import c_oracle, net_oracle, synth
+    import creste_public_b200 as cb
+    torch.set_num_threads(os.cpu_count() or 1)
+    model = cb.build_maxentirl(image_size=(H, W)).eval()
+    sd = synth.seeded_state_dict(model.state_dict(), seed, "peaky")
+    rgb = torch.from_numpy(synth.rgb_frames(1, H, W, seed))
+    pc = synth.os1_scan(seed)
+    P = synth.lidar2camrect(H, W)
+    p2p = torch.from_numpy(synth.make_p2p(H, W)).view(1, 1, 4, 4)
+
+    def one():
+        _, dmm = c_oracle.lidar_raster(pc, P, H, W)
+        rgbd = torch.cat([rgb, torch.from_numpy(dmm).view(1, 1, 1, H, W)], dim=2)
+        return net_oracle.forward(sd, rgbd, p2p)["traversability_preds"]
+    for _ in range(warmup):
+        one()
+    t0 = time.perf_counter()
+    for _ in range(steps):
+        one()
+    dt = time.perf_counter() - t0
+    return steps / dt, dt / steps * 1e3, torch.get_num_threads()
+
+
+def run_reference(args):
+    rank, local, world = dist_env()
+    if rank != 0:
+        return
+    fps, ms, cores = cpu_forward_baseline(args.steps, args.warmup)
+    line = {
+        "impl": "reference", "metric": METRIC, "value": fps, "unit": "frames/s",
+        "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms,
+        "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32",
+        "data": "synthetic",
+        "config": {"workload": "configs[1]: RGB+LiDAR->BEV costmap forward, 1x3x512x960 + 131072-pt "
+                               "OS1 sweep", "frames_per_step": 1},
+        "cpu_baseline": {"value": fps, "unit": "frames/s", "cores": cores, "kind": "port",
+                         "sample": f"{args.steps} steps x 1 frame (+{args.warmup} warm-up), full "
+                                   "512x960 forward, torch CPU fp32 oracle port of the reference"},
+        "e2e": {"value": fps, "unit": "frames/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+    }
+    print(json.dumps(line))
+
+
+# ------------------------------------------------------------------------------------- our arm
+def run_ours(args):
+    import torch
+    import torch.distributed as dist
+    import creste_public_b200 as cb
+    from creste_public_b200 import _lib, ops
+    from oracle import synth   # seeded synthetic inputs / weights only (no oracle compute here)
+
+    rank, local, world = dist_env()
+    assert torch.cuda.is_available(), "bench.py needs a CUDA device (no CPU fallback)"
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+    peaks = load_peaks()
+    cb.set_precision(args.precision)
+    B = args.batch
+
+    model = cb.build_maxentirl(image_size=(H, W)).eval()
+    model.load_state_dict(synth.seeded_state_dict(model.state_dict(), 0, "peaky"))
+    model = model.to(dev)
+
+    # ---- synthetic inputs: a ring of R distinct frame sets per rank (working set >> L2)
+    R = 4
+    P34 = synth.lidar2camrect(H, W)
+    host_rgb = [torch.from_numpy(synth.rgb_frames(B, H, W, 100 * rank + r)).pin_memory() for r in range(R)]
+    host_pc = [torch.stack([torch.from_numpy(synth.os1_scan(1000 * rank + 10 * r + b)) for b in range(B)])
+               .pin_memory() for r in range(R)]
+    host_p2p = torch.from_numpy(synth.make_p2p(H, W)).view(1, 1, 4, 4).repeat(B, 1, 1, 1).pin_memory()
+    dev_rgbd = []
+    for r in range(R):
+        x = torch.zeros(B, 1, 4, H, W, device=dev)
+        x[:, :, :3] = host_rgb[r].to(dev)
+        dev_rgbd.append(x)
+    dev_pc = [p.to(dev) for p in host_pc]
+    dev_p2p = host_p2p.to(dev)
+
+    def step_resident(i):
+        r = i % R
+        x = dev_rgbd[r]
+        for b in range(B):
+            ops.lidar_raster(dev_pc[r][b], P34, H, W, out_mm=x[b, 0, 3], want_m=False)
+        return model((x, dev_p2p))
+
+    stage = torch.zeros(B, 1, 4, H, W, device=dev)
+    host_out = torch.empty(B, 1, 64, 128).pin_memory()
+
+    def step_e2e(i):
+        r = i % R
+        stage[:, :, :3].copy_(host_rgb[r], non_blocking=True)
+        pc = host_pc[r].to(dev, non_blocking=True)
+        p2p = host_p2p.to(dev, non_blocking=True)
+        for b in range(B):
+            ops.lidar_raster(pc[b], P34, H, W, out_mm=stage[b, 0, 3], want_m=False)
+        out = model((stage, p2p))
+        host_out.copy_(out["traversability_preds"], non_blocking=True)
+        return out
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    def timed(fn, steps, warmup):
+        with torch.no_grad():
+            for i in range(warmup):
+                fn(i)
+            barrier()
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            n0 = _lib.lib().creste_launch_count()
+            e0.record()
+            for i in range(steps):
+                fn(warmup + i)
+            e1.record()
+            barrier()
+            ms = e0.elapsed_time(e1)
+            launches = _lib.lib().creste_launch_count() - n0
+        if world > 1:
+            t = torch.tensor([ms], device=dev)
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+            ms = float(t)
+        return ms, launches
+
+    sampler = ClockSampler(local)
+    if rank == 0:
+        sampler.start()
+    ms, launches = timed(step_resident, args.steps, args.warmup)
+    clocks = sampler.stop() if rank == 0 else None
+    ms_e2e, _ = timed(step_e2e, args.steps, max(3, args.warmup // 2))
+
+    frames = B * world * args.steps
+    value = frames / (ms / 1e3)
+    e2e_value = frames / (ms_e2e / 1e3)
+    h2d = B * (3 * H * W * 4 + NPTS * 3 * 4 + 64)
+    d2h = B * 64 * 128 * 4
+
+    # ---- roofline of the dominant kernel: the up3 3x3 conv 496->496 @128x240 (41 % of the
+    # frame's flops), timed with CUDA events on its launch stream inside instrumented steps
+    roof = None
+    irl = None
+    cpu = None
+    if rank == 0:
+        up3 = model.backbone.depthcomp.depthcomp.vision_backbone.model.up3
+        xin = torch.randn(B, 128, 240, 496, device=dev)
+        with torch.no_grad():
+            for _ in range(2):
+                up3._f1(xin, act="relu")
+            ev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True))
+                  for _ in range(5)]
+            for a, b_ in ev:
+                a.record()
+                up3._f1(xin, act="relu")
+                b_.record()
+            torch.cuda.synchronize()
+        kms = statistics.median(a.elapsed_time(b_) for a, b_ in ev)
+        flops = 2.0 * B * 128 * 240 * 496 * (9 * 496)
+        ach = flops / (kms / 1e3) / 1e12
+        roof = {"kernel": "conv3x3 496->496 @128x240 (effnet up3.conv.3), precision=" + args.precision,
+                "bound": "tensor", "achieved": ach, "peak": peaks["bf16_sustained"], "unit": "TFLOP/s",
+                "frac": ach / peaks["bf16_sustained"], "traffic": None,
+                "peak_source": peaks["src"] + " bf16 sustained (cuBLAS)", "kernel_ms": kms,
+                "step_flop_share": round(136.04 / GFLOP_PER_FRAME, 3)}
+        del xin
+
+        # ---- IRL metric: value iteration + SVF at 256x256, B = 8 per GPU (configs[3] shard)
+        Bi = 8
+        r = torch.from_numpy(synth.vi_inputs(7, Bi, 256, 256)).to(dev)
+        expert = torch.from_numpy(synth.expert_poses(Bi, 50, 512, 512, 7)[:, :, :2, 2].copy()).to(dev)
+        fov = torch.ones(256, 256, dtype=torch.uint8, device=dev)
+        for _ in range(2):
+            v, q, pi, info = ops.vi_solve(r, 0.99, 1e-3)
+        a, b_ = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        a.record()
+        v, q, pi, info = ops.vi_solve(r, 0.99, 1e-3)
+        b_.record()
+        c, d = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        c.record()
+        ops.svf(pi, expert, fov, 50, 2, True, 0.005, False)
+        d.record()
+        torch.cuda.synchronize()
+        K = int(info[0])
+        vi_ms, svf_ms = a.elapsed_time(b_), c.elapsed_time(d)
+        vi_bytes = Bi * 256 * 256 * (12.0 * K + 76.0)
+        gbs = vi_bytes / (vi_ms / 1e3) / 1e9
+        irl = {"workload": "configs[3] shard: VI + SVF, B=8, 256x256 grid, gamma=0.99, thr=1e-3",
+               "sweeps": K, "vi_ms": vi_ms, "svf_ms": svf_ms,
+               "irl_solves_per_s": 1e3 / (vi_ms + svf_ms),
+               "roofline": {"bound": "hbm", "achieved": gbs, "peak": peaks["hbm_gbs"], "unit": "GB/s",
+                            "frac": gbs / peaks["hbm_gbs"], "traffic": None,
+                            "note": "algorithmic 12 B/cell/sweep + 76 B/cell; state is L2/SMEM "
+                                    "resident so this can exceed the HBM copy peak"}}
+        if world == 1 and not args.no_cpu:
+            fps_cpu, ms_cpu, cores = cpu_forward_baseline(3, 1)
+            cpu = {"value": fps_cpu, "unit": "frames/s", "cores": cores, "kind": "port",
+                   "sample": "3 frames (+1 warm-up) of the same 512x960 forward, torch CPU fp32 "
+                             "oracle port of the reference, all host threads"}
+
+    if rank == 0:
+        line = {
+            "metric": METRIC, "value": value, "unit": "frames/s", "n_gpus": world,
+            "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms / args.steps,
+            "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+            "dtype": {"fp32": "f32", "3xtf32": "f32 (3xTF32 tcgen05)", "tf32": "tf32",
+                      "bf16": "bf16"}[args.precision],
+            "data": "synthetic",
+            "config": {"workload": "configs[1]: RGB+LiDAR->BEV costmap forward, 3x512x960 RGB + "
+                                   "131072-pt OS1 sweep per frame, full output dict",
+                       "frames_per_step_per_gpu": B, "precision": args.precision,
+                       "l2": f"no flush: per-step working set (~1 GB activations/frame) >> 126 MB "
+                             f"L2; ring of {R} distinct input sets",
+                       "parallelism": f"dp{world} (frames sharded, no data-path collective)"},
+            "e2e": {"value": e2e_value, "unit": "frames/s", "h2d_bytes_per_step": h2d,
+                    "d2h_bytes_per_step": d2h, "ms_per_step": ms_e2e / args.steps},
+            "gpu_launches": int(launches),
+            "clocks": clocks, "roofline": roof, "cpu_baseline": cpu, "irl": irl,
+            "achieved_tflops_whole_step": GFLOP_PER_FRAME * 1e9 * value / world / 1e12,
+        }
+        print(json.dumps(line))
+    if world > 1:
+        dist.destroy_process_group()
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=10)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--batch", type=int, default=2, help="frames per step per GPU")
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--precision", default="fp32", choices=["fp32", "3xtf32", "tf32", "bf16"])
+    ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
+    args = ap.parse_args()
+    if args.warmup < 3 and args.impl == "ours":
+        args.warmup = 3
+    if args.impl == "reference":
+        run_reference(args)
+    else:
+        run_ours(args)
+
+
+if __name__ == "__main__":
+    main()

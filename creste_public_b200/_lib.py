@@ -13,7 +13,7 @@ _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(_HERE, "csrc", "libcreste_b200.so")
 
 EXPORTS = [
-    "creste_version", "creste_last_error", "creste_num_sms",
+    "creste_version", "creste_last_error", "creste_num_sms", "creste_launch_count",
     "creste_vi_workspace_bytes", "creste_vi_solve",
     "creste_svf_workspace_bytes", "creste_svf",
     "creste_frustum_to_bev", "creste_zmlp_concat",
@@ -56,6 +56,7 @@ def lib():
                 "(creste_public_b200 has no CPU or PyTorch fallback)")
         L = C.CDLL(LIB_PATH)
         L.creste_last_error.restype = C.c_char_p
+        L.creste_launch_count.restype = C.c_ulonglong
         for name in ("creste_vi_workspace_bytes", "creste_svf_workspace_bytes",
                      "creste_splat_workspace_bytes", "creste_conv2d_workspace_bytes"):
             getattr(L, name).restype = C.c_size_t

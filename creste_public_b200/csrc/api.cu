@@ -9,6 +9,8 @@ void set_error(const char* fmt, ...) {
   vsnprintf(g_err, sizeof(g_err), fmt, ap);
   va_end(ap);
 }
+static unsigned long long g_launches = 0;
+void count_launch() { ++g_launches; }
 int num_sms() {
   static int cached = -1;
   if (cached >= 0) return cached;
@@ -23,3 +25,4 @@ int num_sms() {
 extern "C" int creste_version(void) { return 100; }
 extern "C" const char* creste_last_error(void) { return creste::g_err; }
 extern "C" int creste_num_sms(void) { return creste::num_sms(); }
+extern "C" unsigned long long creste_launch_count(void) { return creste::g_launches; }

@@ -29,7 +29,10 @@ void set_error(const char* fmt, ...);
     }                                                                                \
   } while (0)
 
+void count_launch();
+
 inline int launch_check(const char* what) {
+  count_launch();
   cudaError_t e = cudaGetLastError();
   if (e != cudaSuccess) {
     set_error("launch of %s failed: %s", what, cudaGetErrorString(e));

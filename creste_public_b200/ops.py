@@ -115,15 +115,18 @@ def splat_soft(xy, feats_nhwc, mask, H, W, min_weight=1.0, want_nhwc=True, want_
 
 
 # --------------------------------------------------------------------------------------- LiDAR
-def lidar_raster(pc, P34, H, W):
+def lidar_raster(pc, P34, H, W, out_mm=None, want_m=True):
     """pc [n,>=3] fp32 CUDA; P34 [3,4] float64 (host array-like) -> depth_m [H,W], depth_mm [H,W]
-    (reference projection.py:64-134 + build_dense_depth.py:461-463)."""
+    (reference projection.py:64-134 + build_dense_depth.py:461-463).  `out_mm`: optional
+    contiguous [H,W] view to write the millimetre raster into (e.g. channel 3 of the RGB-D
+    network input)."""
     pc = pc.contiguous().float()
     flat = [float(v) for row in P34 for v in row]
     assert len(flat) == 12
     Pm = (C.c_double * 12)(*flat)
-    dm = torch.empty(H, W, device=pc.device)
-    dmm = torch.empty(H, W, device=pc.device)
+    dm = torch.empty(H, W, device=pc.device) if want_m else None
+    dmm = out_mm if out_mm is not None else torch.empty(H, W, device=pc.device)
+    assert tuple(dmm.shape) == (H, W)
     ws = _ws(H * W * 8, pc.device)
     check(lib().creste_lidar_raster(ptr(pc), pc.shape[0], pc.shape[1], Pm, H, W, ptr(dm), ptr(dmm),
                                     ptr(ws), C.c_size_t(H * W * 8), stream()), "creste_lidar_raster")

@@ -35,6 +35,8 @@ int creste_version(void);
 const char* creste_last_error(void);
 /* number of SMs of the current device (0 when no device) */
 int creste_num_sms(void);
+/* number of kernels this library has launched in this process (bench.py's gpu_launches) */
+unsigned long long creste_launch_count(void);
 
 /* ---------------------------------------------------------------------------------------------
  * Value iteration.  Replaces VIN.value_iteration_manual, creste/models/blocks/vin.py:48-80

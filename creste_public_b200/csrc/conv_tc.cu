@@ -1,0 +1,519 @@
+// conv_tc.cu -- implicit-GEMM convolution on the 5th-generation tensor cores (tcgen05 + TMEM),
+// operands staged by TMA (precision modes 1 = 3xTF32 split, 2 = single-pass TF32).
+//
+// Covers the stride-1 1x1 / 3x3 convolutions that hold 97 % of the frame's flops (SURVEY.md
+// App. D1: effnet up1-3, eff.conv, depth head, dino head, fusion, ResNet-18 BEV layers, the three
+// DeconvHeads).  GEMM view: M = output pixels, N = output channels, K = R*S*C.
+//
+// Data movement
+//   A (activations, NHWC fp32): one 4-D tensor map (C, W, H, N).  An M-tile is a spatial box of
+//     Wbox x Hbox = 128 output pixels; for filter tap (r,s) and channel block cb the producer
+//     issues ONE cp.async.bulk.tensor.4d with box {32 ch, Wbox, Hbox, 1} at coordinates
+//     (32*cb, x0+s-pad, y0+r-pad, n).  TMA zero-fills everything outside the tensor, which is the
+//     conv's zero padding, the ragged right/bottom tiles and the C % 32 tail in one mechanism.
+//     The box lands as 128 rows x 128 B with the 128-byte swizzle = the K-major UMMA operand layout.
+//   B (weights): packed [Npad][R*S*Cpad] (Cpad = C rounded up to 32, zero filled), 2-D tensor map,
+//     box {32, BLOCK_N}; same swizzle.
+//   D: fp32 accumulator in TMEM (128 lanes x BLOCK_N columns), read back with tcgen05.ld by four
+//     epilogue warps (one TMEM lane quarter each) that apply folded BN / bias, residual, activation
+//     and store NHWC.
+//
+// Precision: tf32 MMAs read fp32 words and ignore the low 13 mantissa bits.  Mode 1 feeds
+// pre-rounded hi = rna_tf32(x) and lo = rna_tf32(x - hi) operands (the split pre-pass
+// `tf32_split_kernel`, which also applies the optional SE gate) and issues
+// D += Alo*Bhi + Ahi*Blo + Ahi*Bhi per k-step: products carry ~21 mantissa bits, accumulation is
+// fp32, which measures as fp32-faithful on the costmap (DESIGN.md "Precision").  Round-to-nearest
+// in the split matters: truncation splits bias every product the same way and cost 10x accuracy.
+//
+// Warp roles (192 threads): warp 0 = TMA producer, warp 1 = TMEM alloc + MMA issuer (one elected
+// lane issues tcgen05.mma; tcgen05.commit releases smem stages / signals the epilogue),
+// warps 2-5 = epilogue.  mbarrier ring of NSTAGES smem stages.
+#include <cuda.h>
+
+#include "common.cuh"
+
+namespace creste {
+
+// ------------------------------------------------------------------------------------ PTX
+__device__ __forceinline__ uint32_t smem_u32(const void* p) {
+  return (uint32_t)__cvta_generic_to_shared(p);
+}
+__device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%1], %0;" ::"r"(count), "r"(smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ void mbar_expect_tx(uint64_t* bar, uint32_t bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%1], %0;" ::"r"(bytes), "r"(smem_u32(bar))
+               : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
+  asm volatile(
+      "{\n\t"
+      ".reg .pred P1;\n\t"
+      "WAIT_LOOP:\n\t"
+      "mbarrier.try_wait.parity.shared::cta.b64 P1, [%0], %1;\n\t"
+      "@P1 bra WAIT_DONE;\n\t"
+      "bra WAIT_LOOP;\n\t"
+      "WAIT_DONE:\n\t"
+      "}" ::"r"(smem_u32(bar)), "r"(parity)
+      : "memory");
+}
+__device__ __forceinline__ void fence_barrier_init() {
+  asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+}
+__device__ __forceinline__ void tma_load_4d(const CUtensorMap* map, uint64_t* bar, void* dst, int c0,
+                                            int c1, int c2, int c3) {
+  asm volatile(
+      "cp.async.bulk.tensor.4d.shared::cluster.global.mbarrier::complete_tx::bytes"
+      " [%0], [%1, {%3, %4, %5, %6}], [%2];" ::"r"(smem_u32(dst)),
+      "l"((uint64_t)map), "r"(smem_u32(bar)), "r"(c0), "r"(c1), "r"(c2), "r"(c3)
+      : "memory");
+}
+__device__ __forceinline__ void tma_load_2d(const CUtensorMap* map, uint64_t* bar, void* dst, int c0,
+                                            int c1) {
+  asm volatile(
+      "cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes"
+      " [%0], [%1, {%3, %4}], [%2];" ::"r"(smem_u32(dst)),
+      "l"((uint64_t)map), "r"(smem_u32(bar)), "r"(c0), "r"(c1)
+      : "memory");
+}
+__device__ __forceinline__ void prefetch_tmap(const CUtensorMap* map) {
+  asm volatile("prefetch.tensormap [%0];" ::"l"((uint64_t)map) : "memory");
+}
+__device__ __forceinline__ void tmem_alloc(uint32_t* dst_smem, uint32_t ncols) {
+  asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(dst_smem)),
+               "r"(ncols)
+               : "memory");
+  asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+}
+__device__ __forceinline__ void tmem_dealloc(uint32_t addr, uint32_t ncols) {
+  asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(addr), "r"(ncols) : "memory");
+}
+__device__ __forceinline__ void tc_fence_before() {
+  asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+}
+__device__ __forceinline__ void tc_fence_after() {
+  asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+}
+__device__ __forceinline__ void umma_commit(uint64_t* bar) {
+  asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(
+                   smem_u32(bar))
+               : "memory");
+}
+__device__ __forceinline__ void umma_tf32(uint32_t tmem_d, uint64_t a_desc, uint64_t b_desc,
+                                          uint32_t idesc, uint32_t accumulate) {
+  asm volatile(
+      "{\n\t"
+      ".reg .pred p;\n\t"
+      "setp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::1.kind::tf32 [%0], %1, %2, %3, p;\n\t"
+      "}" ::"r"(tmem_d),
+      "l"(a_desc), "l"(b_desc), "r"(idesc), "r"(accumulate)
+      : "memory");
+}
+__device__ __forceinline__ void tmem_ld32(uint32_t addr, uint32_t (&v)[32]) {
+  asm volatile(
+      "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
+      "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
+      "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"
+      : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7]),
+        "=r"(v[8]), "=r"(v[9]), "=r"(v[10]), "=r"(v[11]), "=r"(v[12]), "=r"(v[13]), "=r"(v[14]),
+        "=r"(v[15]), "=r"(v[16]), "=r"(v[17]), "=r"(v[18]), "=r"(v[19]), "=r"(v[20]), "=r"(v[21]),
+        "=r"(v[22]), "=r"(v[23]), "=r"(v[24]), "=r"(v[25]), "=r"(v[26]), "=r"(v[27]), "=r"(v[28]),
+        "=r"(v[29]), "=r"(v[30]), "=r"(v[31])
+      : "r"(addr)
+      : "memory");
+}
+__device__ __forceinline__ void tmem_ld_wait() {
+  asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+}
+__device__ __forceinline__ bool elect_one() {
+  uint32_t pred;
+  asm volatile(
+      "{\n\t"
+      ".reg .pred P1;\n\t"
+      "elect.sync _|P1, 0xffffffff;\n\t"
+      "selp.b32 %0, 1, 0, P1;\n\t"
+      "}"
+      : "=r"(pred));
+  return pred != 0;
+}
+
+// K-major, 128-byte-swizzled shared-memory operand descriptor (UMMA::SmemDescriptor):
+// start>>4 | LBO(ignored)=1 | SBO = 1024 B (8 rows x 128 B) | version 1 | SWIZZLE_128B
+__device__ __forceinline__ uint64_t make_sw128_desc(uint32_t saddr) {
+  return (uint64_t)((saddr >> 4) & 0x3FFFu) | (1ull << 16) | (64ull << 32) | (1ull << 46) | (2ull << 61);
+}
+// UMMA::InstrDescriptor for kind::tf32, fp32 accumulate, K-major A and B, M = 128
+__host__ __device__ constexpr uint32_t make_idesc_tf32(int n) {
+  return (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(n >> 3) << 17) | ((128u >> 4) << 24);
+}
+
+// ------------------------------------------------------------------------------------ kernels
+struct TcParams {
+  const float* scale; const float* shift; const float* residual; float* out;
+  int N, P, Q, K;              // output NHWC [N,P,Q,K]
+  int R, S, pad_t, pad_l;
+  int cblocks;                 // ceil(C / 32)
+  int wbox, hbox, tiles_x, tiles_y;
+  int block_n, act, split;     // split: 1 = 3xTF32 (hi/lo operands), 0 = single TF32
+  int out_nchw;
+};
+
+constexpr int TC_THREADS = 192;
+constexpr int A_TILE_BYTES = 128 * 128;   // 128 rows x 32 fp32
+
+__device__ __forceinline__ float tc_act(float v, int act) {
+  if (act == 1) return fmaxf(v, 0.0f);
+  if (act == 2) return v / (1.0f + expf(-v));
+  if (act == 3) return 1.0f / (1.0f + expf(-v));
+  return v;
+}
+
+__global__ void __launch_bounds__(TC_THREADS, 1)
+conv_tc_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_constant__ CUtensorMap map_a_lo,
+               const __grid_constant__ CUtensorMap map_b_hi, const __grid_constant__ CUtensorMap map_b_lo,
+               TcParams p, int nstages) {
+  extern __shared__ uint8_t smem_raw[];
+  __shared__ uint64_t full_bar[8], empty_bar[8], tmem_full_bar;
+  __shared__ uint32_t tmem_base_smem;
+  uint8_t* smem = (uint8_t*)(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int nops = p.split ? 2 : 1;
+  const int b_tile_bytes = p.block_n * 128;
+  const int stage_bytes = nops * (A_TILE_BYTES + b_tile_bytes);
+
+  // tile coordinates
+  int t = blockIdx.x;
+  const int tx = t % p.tiles_x; t /= p.tiles_x;
+  const int ty = t % p.tiles_y;
+  const int img = t / p.tiles_y;
+  const int x0 = tx * p.wbox, y0 = ty * p.hbox;
+  const int n0 = blockIdx.y * p.block_n;
+  const int kblocks = p.R * p.S * p.cblocks;
+  // split mode keeps TWO accumulators: hi*hi in columns [0, block_n) and the two small cross
+  // terms in [acc2, acc2 + block_n).  The tensor core truncates (round-toward-zero) the fp32
+  // accumulator at every MMA, an error proportional to |acc| per accumulation; separating the
+  // cross terms (2^-11 of the main sum) means the large accumulator is rounded K/8 times
+  // instead of 3K/8 times.  The epilogue adds the two in fp32 round-to-nearest.
+  const uint32_t acc_cols = p.block_n <= 32 ? 32 : (p.block_n <= 64 ? 64 : (p.block_n <= 128 ? 128 : 256));
+  const uint32_t acc2 = acc_cols;
+  const uint32_t tmem_cols = p.split ? 2 * acc_cols : acc_cols;
+
+  if (warp == 0 && lane == 0) {
+    prefetch_tmap(&map_a_hi);
+    prefetch_tmap(&map_b_hi);
+    if (p.split) { prefetch_tmap(&map_a_lo); prefetch_tmap(&map_b_lo); }
+    for (int i = 0; i < nstages; ++i) { mbar_init(&full_bar[i], 1); mbar_init(&empty_bar[i], 1); }
+    mbar_init(&tmem_full_bar, 1);
+    fence_barrier_init();
+  }
+  if (warp == 1) tmem_alloc(&tmem_base_smem, tmem_cols);
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = tmem_base_smem;
+
+  if (warp == 0) {
+    // ===== TMA producer =====
+    if (elect_one()) {
+      for (int kb = 0; kb < kblocks; ++kb) {
+        const int stage = kb % nstages;
+        const uint32_t parity = ((kb / nstages) & 1) ^ 1;
+        mbar_wait(&empty_bar[stage], parity);
+        const int cb = kb % p.cblocks;
+        const int tap = kb / p.cblocks;
+        const int r = tap / p.S, s = tap - r * p.S;
+        uint8_t* st = smem + (size_t)stage * stage_bytes;
+        mbar_expect_tx(&full_bar[stage], (uint32_t)stage_bytes);
+        const int cx = x0 + s - p.pad_l, cy = y0 + r - p.pad_t;
+        tma_load_4d(&map_a_hi, &full_bar[stage], st, cb * 32, cx, cy, img);
+        tma_load_2d(&map_b_hi, &full_bar[stage], st + nops * A_TILE_BYTES, kb * 32, n0);
+        if (p.split) {
+          tma_load_4d(&map_a_lo, &full_bar[stage], st + A_TILE_BYTES, cb * 32, cx, cy, img);
+          tma_load_2d(&map_b_lo, &full_bar[stage], st + 2 * A_TILE_BYTES + b_tile_bytes, kb * 32, n0);
+        }
+      }
+    }
+  } else if (warp == 1) {
+    // ===== MMA issuer =====
+    const uint32_t idesc = make_idesc_tf32(p.block_n);
+    for (int kb = 0; kb < kblocks; ++kb) {
+      const int stage = kb % nstages;
+      const uint32_t parity = (kb / nstages) & 1;
+      mbar_wait(&full_bar[stage], parity);
+      tc_fence_after();
+      if (elect_one()) {
+        const uint32_t st = smem_u32(smem + (size_t)stage * stage_bytes);
+        const uint32_t a_hi = st, a_lo = st + A_TILE_BYTES;
+        const uint32_t b_hi = st + nops * A_TILE_BYTES, b_lo = b_hi + b_tile_bytes;
+#pragma unroll
+        for (int k = 0; k < 4; ++k) {   // 4 x (K = 8 tf32 = 32 B) per 128-byte swizzle row
+          const uint32_t koff = k * 32;
+          if (p.split) {
+            umma_tf32(tmem_base + acc2, make_sw128_desc(a_lo + koff), make_sw128_desc(b_hi + koff),
+                      idesc, (kb | k) != 0);
+            umma_tf32(tmem_base + acc2, make_sw128_desc(a_hi + koff), make_sw128_desc(b_lo + koff),
+                      idesc, 1);
+            umma_tf32(tmem_base, make_sw128_desc(a_hi + koff), make_sw128_desc(b_hi + koff), idesc,
+                      (kb | k) != 0);
+          } else {
+            umma_tf32(tmem_base, make_sw128_desc(a_hi + koff), make_sw128_desc(b_hi + koff), idesc,
+                      (kb | k) != 0);
+          }
+        }
+        umma_commit(&empty_bar[stage]);                 // smem stage free once these MMAs retire
+        if (kb == kblocks - 1) umma_commit(&tmem_full_bar);
+      }
+      __syncwarp();
+    }
+  } else {
+    // ===== epilogue: warps 2..5, TMEM lane quarter = warp % 4 =====
+    const int quarter = warp & 3;
+    const int m = quarter * 32 + lane;               // accumulator row = box-order pixel index
+    const int wx = m % p.wbox, hy = m / p.wbox;
+    const int ox = x0 + wx, oy = y0 + hy;
+    const bool pix_ok = (ox < p.Q) && (oy < p.P);
+    const size_t pix = ((size_t)img * p.P + oy) * p.Q + ox;
+    mbar_wait(&tmem_full_bar, 0);
+    tc_fence_after();
+    for (int c0 = 0; c0 < p.block_n; c0 += 32) {
+      uint32_t v[32];
+      tmem_ld32(tmem_base + ((uint32_t)(quarter * 32) << 16) + (uint32_t)c0, v);
+      if (p.split) {
+        uint32_t v2[32];
+        tmem_ld32(tmem_base + ((uint32_t)(quarter * 32) << 16) + acc2 + (uint32_t)c0, v2);
+        tmem_ld_wait();
+#pragma unroll
+        for (int j = 0; j < 32; ++j) v[j] = __float_as_uint(__uint_as_float(v[j]) + __uint_as_float(v2[j]));
+      } else {
+        tmem_ld_wait();
+      }
+      if (pix_ok) {
+#pragma unroll
+        for (int j = 0; j < 32; j += 4) {
+          const int n = n0 + c0 + j;
+          if (n >= p.K) break;
+          float o[4];
+#pragma unroll
+          for (int q = 0; q < 4; ++q) {
+            const int nn = n + q;
+            float val = __uint_as_float(v[j + q]);
+            if (nn < p.K) {
+              const float sc = p.scale ? __ldg(p.scale + nn) : 1.0f;
+              const float sh = p.shift ? __ldg(p.shift + nn) : 0.0f;
+              val = fmaf(val, sc, sh);
+              if (p.residual) val += __ldg(p.residual + pix * p.K + nn);
+              val = tc_act(val, p.act);
+            }
+            o[q] = val;
+          }
+          if (p.out_nchw) {
+            const size_t PQ = (size_t)p.P * p.Q;
+            const size_t pp = (size_t)oy * p.Q + ox;
+#pragma unroll
+            for (int q = 0; q < 4; ++q)
+              if (n + q < p.K) p.out[((size_t)img * p.K + n + q) * PQ + pp] = o[q];
+          } else if (n + 3 < p.K && (p.K & 3) == 0) {
+            *reinterpret_cast<float4*>(p.out + pix * p.K + n) = make_float4(o[0], o[1], o[2], o[3]);
+          } else {
+#pragma unroll
+            for (int q = 0; q < 4; ++q)
+              if (n + q < p.K) p.out[pix * p.K + n + q] = o[q];
+          }
+        }
+      }
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 1) {
+    tc_fence_after();
+    tmem_dealloc(tmem_base, tmem_cols);
+  }
+}
+
+// x (* gate) -> hi = rna_tf32(x), lo = rna_tf32(x - hi); also used with lo == nullptr to pre-round
+__global__ void __launch_bounds__(256) tf32_split_kernel(const float4* __restrict__ x,
+                                                         const float* __restrict__ gate, int C,
+                                                         long long hwc4, long long n4,
+                                                         float4* __restrict__ hi,
+                                                         float4* __restrict__ lo) {
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n4;
+       i += (long long)gridDim.x * blockDim.x) {
+    float4 v = __ldg(x + i);
+    if (gate) {
+      const int img = (int)(i / hwc4);
+      const int c = (int)((i * 4) % C);
+      const float4 g = __ldg(reinterpret_cast<const float4*>(gate + (size_t)img * C + c));
+      v.x *= g.x; v.y *= g.y; v.z *= g.z; v.w *= g.w;
+    }
+    float4 h, l;
+    uint32_t u;
+#define CRESTE_SPLIT(f)                                                   \
+    asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(u) : "f"(v.f));                 \
+    h.f = __uint_as_float(u);                                             \
+    asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(u) : "f"(v.f - h.f));           \
+    l.f = __uint_as_float(u);
+    CRESTE_SPLIT(x) CRESTE_SPLIT(y) CRESTE_SPLIT(z) CRESTE_SPLIT(w)
+#undef CRESTE_SPLIT
+    hi[i] = h;
+    if (lo) lo[i] = l;
+  }
+}
+
+// ------------------------------------------------------------------------------------ host
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
+                                  const cuuint64_t*, const cuuint32_t*, const cuuint32_t*,
+                                  CUtensorMapInterleave, CUtensorMapSwizzle, CUtensorMapL2promotion,
+                                  CUtensorMapFloatOOBfill);
+
+static EncodeTiledFn get_encode() {
+  static EncodeTiledFn fn = nullptr;
+  if (fn) return fn;
+  void* ptr = nullptr;
+  cudaDriverEntryPointQueryResult qres;
+  if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &ptr, cudaEnableDefault, &qres) != cudaSuccess ||
+      qres != cudaDriverEntryPointSuccess)
+    return nullptr;
+  fn = (EncodeTiledFn)ptr;
+  return fn;
+}
+
+static int make_map_a(CUtensorMap* m, const float* base, int N, int H, int W, int C, int wbox, int hbox) {
+  EncodeTiledFn enc = get_encode();
+  if (!enc) { set_error("cuTensorMapEncodeTiled unavailable"); return CRESTE_ERR_NO_DEVICE; }
+  cuuint64_t dims[4] = {(cuuint64_t)C, (cuuint64_t)W, (cuuint64_t)H, (cuuint64_t)N};
+  cuuint64_t strides[3] = {(cuuint64_t)C * 4, (cuuint64_t)W * C * 4, (cuuint64_t)H * W * C * 4};
+  cuuint32_t box[4] = {32, (cuuint32_t)wbox, (cuuint32_t)hbox, 1};
+  cuuint32_t es[4] = {1, 1, 1, 1};
+  CUresult r = enc(m, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 4, (void*)base, dims, strides, box, es,
+                   CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B,
+                   CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS) { set_error("cuTensorMapEncodeTiled(A) failed: %d", (int)r); return CRESTE_ERR_ARG; }
+  return 0;
+}
+
+static int make_map_b(CUtensorMap* m, const float* base, int ktot, int npad, int block_n) {
+  EncodeTiledFn enc = get_encode();
+  if (!enc) { set_error("cuTensorMapEncodeTiled unavailable"); return CRESTE_ERR_NO_DEVICE; }
+  cuuint64_t dims[2] = {(cuuint64_t)ktot, (cuuint64_t)npad};
+  cuuint64_t strides[1] = {(cuuint64_t)ktot * 4};
+  cuuint32_t box[2] = {32, (cuuint32_t)block_n};
+  cuuint32_t es[2] = {1, 1};
+  CUresult r = enc(m, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, (void*)base, dims, strides, box, es,
+                   CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B,
+                   CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS) { set_error("cuTensorMapEncodeTiled(B) failed: %d", (int)r); return CRESTE_ERR_ARG; }
+  return 0;
+}
+
+// N tile: the whole (16-rounded) channel count when it fits one 256-column accumulator,
+// otherwise the divisor-friendliest tile <= 256
+static int pick_block_n(int K) {
+  const int k16 = (K + 15) / 16 * 16;
+  if (k16 <= 256) return k16;
+  const int tiles = (k16 + 255) / 256;
+  return ((k16 + tiles - 1) / tiles + 15) / 16 * 16;
+}
+
+static void pick_box(int P, int Q, int* wbox, int* hbox) {
+  int best_w = 16;
+  double best = -1.0;
+  for (int w = 128; w >= 1; w >>= 1) {
+    const int h = 128 / w;
+    const double util = ((double)P * Q) / ((double)ceil_div(Q, w) * w * ceil_div(P, h) * h);
+    // prefer squarer boxes on ties (fewer halo re-reads from L2)
+    const double score = util - 1e-3 * fabs(log2((double)w / h) - 1.0);
+    if (score > best) { best = score; best_w = w; }
+  }
+  *wbox = best_w;
+  *hbox = 128 / best_w;
+}
+
+bool conv_tc_supported(const creste_conv_desc* d) {
+  if (d->precision != 1 && d->precision != 2) return false;
+  if (d->stride != 1 || d->C % 4 != 0 || d->K < 8) return false;
+  if (d->R > 5 || d->S > 5) return false;
+  if ((long long)d->N * d->P * d->Q < 128) return false;
+  return true;
+}
+
+int conv_tc_layout(int K, int C, int R, int S, int* block_n, int* npad, int* cpad) {
+  *block_n = pick_block_n(K);
+  *npad = ceil_div(K, *block_n) * *block_n;
+  *cpad = (C + 31) / 32 * 32;
+  (void)R; (void)S;
+  return 0;
+}
+
+size_t conv_tc_workspace_bytes(const creste_conv_desc* d) {
+  const size_t n = (size_t)d->N * d->H * d->W * d->C * sizeof(float);
+  return d->precision == 1 ? 2 * align_up(n, 1024) : align_up(n, 1024);
+}
+
+int conv_tc_launch(const creste_conv_desc* d, const float* x, const float* w_packed, const float* scale,
+                   const float* shift, const float* gate, const float* residual, float* out, void* ws,
+                   size_t ws_bytes, cudaStream_t st) {
+  if (ws_bytes < conv_tc_workspace_bytes(d) || !ws) {
+    set_error("creste_conv2d(tc): workspace %zu < %zu", ws_bytes, conv_tc_workspace_bytes(d));
+    return CRESTE_ERR_WORKSPACE;
+  }
+  const int split = d->precision == 1;
+  int block_n, npad, cpad;
+  conv_tc_layout(d->K, d->C, d->R, d->S, &block_n, &npad, &cpad);
+  const int ktot = d->R * d->S * cpad;
+  const size_t numel = (size_t)d->N * d->H * d->W * d->C;
+  float* x_hi = (float*)ws;
+  float* x_lo = split ? (float*)((char*)ws + align_up(numel * 4, 1024)) : nullptr;
+  {
+    const long long n4 = (long long)(numel / 4);
+    long long blocks = (n4 + 255) / 256;
+    if (blocks > 148 * 16) blocks = 148 * 16;
+    tf32_split_kernel<<<(int)blocks, 256, 0, st>>>((const float4*)x, gate, d->C,
+                                                   (long long)d->H * d->W * d->C / 4, n4, (float4*)x_hi,
+                                                   (float4*)x_lo);
+    int rc = launch_check("tf32_split_kernel");
+    if (rc) return rc;
+  }
+  TcParams p;
+  p.scale = scale; p.shift = shift; p.residual = residual; p.out = out;
+  p.N = d->N; p.P = d->P; p.Q = d->Q; p.K = d->K;
+  p.R = d->R; p.S = d->S; p.pad_t = d->pad_t; p.pad_l = d->pad_l;
+  p.cblocks = cpad / 32;
+  pick_box(d->P, d->Q, &p.wbox, &p.hbox);
+  p.tiles_x = ceil_div(d->Q, p.wbox);
+  p.tiles_y = ceil_div(d->P, p.hbox);
+  p.block_n = block_n; p.act = d->act; p.split = split; p.out_nchw = d->out_nchw;
+
+  CUtensorMap ma_hi, ma_lo, mb_hi, mb_lo;
+  int rc;
+  if ((rc = make_map_a(&ma_hi, x_hi, d->N, d->H, d->W, d->C, p.wbox, p.hbox))) return rc;
+  if ((rc = make_map_a(&ma_lo, split ? x_lo : x_hi, d->N, d->H, d->W, d->C, p.wbox, p.hbox))) return rc;
+  const float* w_hi = w_packed;
+  const float* w_lo = w_packed + (size_t)npad * ktot;
+  if ((rc = make_map_b(&mb_hi, w_hi, ktot, npad, block_n))) return rc;
+  if ((rc = make_map_b(&mb_lo, split ? w_lo : w_hi, ktot, npad, block_n))) return rc;
+
+  const int nops = split ? 2 : 1;
+  const size_t stage_bytes = (size_t)nops * (A_TILE_BYTES + block_n * 128);
+  int nstages = (int)((200 * 1024) / stage_bytes);
+  if (nstages > 8) nstages = 8;
+  if (nstages < 2) { set_error("creste_conv2d(tc): stage too large"); return CRESTE_ERR_ARG; }
+  const size_t smem = (size_t)nstages * stage_bytes + 1024;
+  CRESTE_CUDA(cudaFuncSetAttribute(conv_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  dim3 grid(d->N * p.tiles_y * p.tiles_x, npad / block_n);
+  conv_tc_kernel<<<grid, TC_THREADS, smem, st>>>(ma_hi, ma_lo, mb_hi, mb_lo, p, nstages);
+  return launch_check("conv_tc_kernel");
+}
+
+}  // namespace creste
+
+extern "C" int creste_conv2d_tc_supported(const creste_conv_desc* d) {
+  return d && creste::conv_tc_supported(d) ? 1 : 0;
+}
+
+// weight layout helper for the host side (Python packs on the GPU with torch; this reports sizes)
+extern "C" int creste_conv2d_tc_layout(int K, int C, int R, int S, int* block_n, int* npad, int* cpad) {
+  return creste::conv_tc_layout(K, C, R, S, block_n, npad, cpad);
+}

@@ -69,29 +69,38 @@ class FusedConv:
         self.conv, self.bn = conv, bn
         self.cache = PackCache()
 
-    def packed(self):
+    def packed(self, mode="fp32"):
+        """mode: 'fp32' (SIMT layout), '3xtf32' / 'tf32' (tcgen05 layout, pre-rounded)."""
         conv, bn = self.conv, self.bn
         tensors = [conv.weight, conv.bias] + ([bn.weight, bn.bias, bn.running_mean, bn.running_var]
                                               if bn is not None else [])
 
         def build():
-            w = ops.pack_conv_weight(conv.weight.detach().float())
+            if mode == "fp32":
+                w = ops.pack_conv_weight(conv.weight.detach().float())
+            else:
+                w = ops.pack_conv_weight_tc(conv.weight.detach().float(), split=(mode == "3xtf32"))
             if bn is not None:
                 scale, shift = bn_scale_shift(bn, conv.bias)
             else:
                 scale = None
                 shift = conv.bias.detach().float().contiguous() if conv.bias is not None else None
             return w, scale, shift
-        return self.cache.get("w", tensors, build)
+        return self.cache.get("w_" + mode, tensors, build)
 
     def __call__(self, x_nhwc, act="none", pad=None, gate=None, residual=None, out_nchw=False,
                  precision=None):
         conv = self.conv
-        w, scale, shift = self.packed()
         K, _, R, S = conv.weight.shape
         if pad is None:
             ph, pw = conv.padding if isinstance(conv.padding, tuple) else (conv.padding,) * 2
             pad = (ph, ph, pw, pw)
         stride = conv.stride[0] if isinstance(conv.stride, tuple) else conv.stride
+        mode = precision or _PRECISION
+        # shapes the tensor-core kernel does not serve (strided, C = 4 stem, K < 8 heads) run on
+        # the exact-fp32 CUDA-core kernel -- a stricter precision, never a looser one
+        if mode != "fp32" and not ops.tc_supported(tuple(x_nhwc.shape), K, R, S, stride, pad, mode):
+            mode = "fp32"
+        w, scale, shift = self.packed(mode)
         return ops.conv2d(x_nhwc, w, K, R, S, stride, pad, scale, shift, gate, residual, act,
-                          out_nchw, precision or _PRECISION)
+                          out_nchw, mode)

@@ -158,6 +158,47 @@ def pack_conv_weight(w):
     return p.contiguous()
 
 
+def rna_tf32(t):
+    """Round fp32 to tf32 (10-bit mantissa), nearest with ties away from zero = cvt.rna.tf32.f32."""
+    u = t.contiguous().view(torch.int32)
+    return ((u + 0x1000) & ~0x1FFF).view(torch.float32)
+
+
+def tc_layout(K, Cc, R, S):
+    bn, npad, cpad = C.c_int(0), C.c_int(0), C.c_int(0)
+    lib().creste_conv2d_tc_layout(K, Cc, R, S, C.byref(bn), C.byref(npad), C.byref(cpad))
+    return bn.value, npad.value, cpad.value
+
+
+def pack_conv_weight_tc(w, split):
+    """[K,C,R,S] -> [Npad][R*S*Cpad] tf32-rounded hi (+ lo when split), one flat buffer."""
+    K, Cc, R, S = w.shape
+    _, npad, cpad = tc_layout(K, Cc, R, S)
+    p = w.new_zeros(npad, R * S, cpad)
+    p[:K, :, :Cc] = w.permute(0, 2, 3, 1).reshape(K, R * S, Cc)
+    hi = rna_tf32(p)
+    if not split:
+        return hi.reshape(-1).contiguous()
+    lo = rna_tf32(p - hi)
+    return torch.cat([hi.reshape(-1), lo.reshape(-1)]).contiguous()
+
+
+def conv_desc(x_shape, K, R, S, stride, pad, act="none", out_nchw=False, precision="fp32"):
+    N, H, W, Cc = x_shape
+    pt, pb, pl, pr = pad
+    P = (H + pt + pb - R) // stride + 1
+    Q = (W + pl + pr - S) // stride + 1
+    return ConvDesc(N, H, W, Cc, K, R, S, stride, pt, pl, P, Q, ACT[act], int(out_nchw),
+                    PRECISION[precision])
+
+
+def tc_supported(x_shape, K, R, S, stride, pad, precision):
+    if PRECISION[precision] == 0:
+        return False
+    d = conv_desc(x_shape, K, R, S, stride, pad, precision=precision)
+    return bool(lib().creste_conv2d_tc_supported(C.byref(d)))
+
+
 def conv2d(x_nhwc, w_packed, K, R, S, stride=1, pad=(0, 0, 0, 0), scale=None, shift=None,
            gate=None, residual=None, act="none", out_nchw=False, precision="fp32"):
     """NHWC conv + folded BN/bias + residual + activation.  pad = (top, bottom, left, right)."""

@@ -1,0 +1,73 @@
+"""GPU parity of the tcgen05 conv path (TMA + UMMA + TMEM) against torch CPU fp32 convolutions.
+
+3xTF32 (precision 1) is the high-precision tensor-core mode: products carry ~21 mantissa bits;
+the residual error is the tensor core's round-toward-zero fp32 accumulation, ~K/8 * 2^-25
+relative (measured 1e-5 at K = 4464), so the tolerance is 3e-5 * max|ref| (FFMA path: 2e-5).
+Single-pass TF32 (precision 2) is a fast mode: its error is measured and bounded loosely (1e-3
+relative), never presented as fp32 parity."""
+import pytest
+import torch
+import torch.nn.functional as F
+
+pytestmark = pytest.mark.gpu
+
+CASES = [
+    # N, C, H, W, K, R, act, gate, residual
+    (1, 32, 8, 16, 32, 1, "none", False, False),        # one tile, one k-block
+    (1, 64, 16, 16, 64, 1, "relu", False, False),       # 2 tiles, 2 k-blocks
+    (1, 64, 16, 24, 96, 3, "relu", False, False),       # 3x3 halo via TMA OOB fill
+    (1, 40, 13, 21, 72, 3, "none", False, True),        # ragged tiles, C % 32 != 0, residual
+    (2, 256, 12, 20, 128, 3, "relu", False, False),     # depth-head-like
+    (1, 288, 16, 30, 96, 1, "relu", False, False),      # fusion conv
+    (1, 496, 16, 30, 496, 3, "relu", False, False),     # up3-like: two N tiles of 256
+    (1, 432, 16, 15, 432, 3, "relu", False, False),     # N tile 224
+    (2, 96, 16, 16, 24, 1, "none", True, True),         # gate + residual (MBConv project)
+    (1, 128, 32, 32, 32, 1, "none", False, False),      # proj head K=32
+    (1, 320, 16, 16, 256, 3, "swish", False, False),
+]
+
+
+def _ref(case, g):
+    N, C, H, W, K, R, act, use_gate, use_res = case
+    x = torch.randn(N, C, H, W, generator=g)
+    w = torch.randn(K, C, R, R, generator=g) / (C * R * R) ** 0.5
+    scale = torch.rand(K, generator=g) + 0.5
+    shift = torch.randn(K, generator=g) * 0.1
+    gate = torch.rand(N, C, generator=g) if use_gate else None
+    xin = x * gate.view(N, C, 1, 1) if use_gate else x
+    ref = F.conv2d(xin, w, padding=R // 2) * scale.view(1, -1, 1, 1) + shift.view(1, -1, 1, 1)
+    res = torch.randn(ref.shape, generator=g) if use_res else None
+    if use_res:
+        ref = ref + res
+    ref = {"none": lambda t: t, "relu": F.relu, "swish": lambda t: t * torch.sigmoid(t)}[act](ref)
+    return x, w, scale, shift, gate, res, ref
+
+
+@pytest.mark.parametrize("case", CASES)
+@pytest.mark.parametrize("mode,tol", [("3xtf32", 3e-5), ("tf32", 2e-3)])
+def test_conv_tc_matches_torch(cuda, case, mode, tol):
+    from creste_public_b200 import ops
+    N, C, H, W, K, R, act, use_gate, use_res = case
+    g = torch.Generator().manual_seed(sum(case[:6]))
+    x, w, scale, shift, gate, res, ref = _ref(case, g)
+    pad = (R // 2,) * 4
+    assert ops.tc_supported((N, H, W, C), K, R, R, 1, pad, mode)
+    wp = ops.pack_conv_weight_tc(w.to(cuda), split=(mode == "3xtf32"))
+    out = ops.conv2d(x.to(cuda).permute(0, 2, 3, 1).contiguous(), wp, K, R, R, 1, pad, scale.to(cuda),
+                     shift.to(cuda), gate.to(cuda) if use_gate else None,
+                     res.to(cuda).permute(0, 2, 3, 1).contiguous() if use_res else None, act,
+                     precision=mode)
+    torch.cuda.synchronize()
+    out = out.cpu().permute(0, 3, 1, 2)
+    err = float((out - ref).abs().max())
+    assert err <= tol * float(ref.abs().max()), f"err {err:.3e} vs max {float(ref.abs().max()):.3e}"
+
+
+def test_tc_unsupported_shapes_are_refused(cuda):
+    from creste_public_b200 import ops
+    assert not ops.tc_supported((1, 32, 32, 4), 32, 3, 3, 2, (0, 1, 0, 1), "3xtf32")   # strided stem
+    assert not ops.tc_supported((1, 32, 32, 128), 6, 1, 1, 1, (0, 0, 0, 0), "3xtf32")   # K = 6 head
+    x = torch.randn(1, 16, 16, 64, device=cuda)
+    w = ops.pack_conv_weight(torch.randn(6, 64, 1, 1, device=cuda))
+    with pytest.raises(RuntimeError, match="precision mode"):
+        ops.conv2d(x, w, 6, 1, 1, 1, (0, 0, 0, 0), precision="3xtf32")

@@ -26,7 +26,8 @@ __global__ void __launch_bounds__(256) dwconv_kernel(const float* __restrict__ x
                                                      int W, int C, int stride, int pad_t, int pad_l,
                                                      int P, int Q, float* __restrict__ out,
                                                      float* __restrict__ chan_part) {
-  // grid: x = pixel tiles within one image, y = image; chan_part [N, gridDim.x, C]
+  // grid: x = pixel tiles within one image, y = image, z = chunks of 256 channel groups;
+  // chan_part [N, gridDim.x, C]
   __shared__ float4 s_part[256];
   const int C4 = C / 4;
   const int n = blockIdx.y;
@@ -35,13 +36,13 @@ __global__ void __launch_bounds__(256) dwconv_kernel(const float* __restrict__ x
   const int pix0 = blockIdx.x * pix_per_block;
   const int pix1 = min(pix0 + pix_per_block, PQ);
   // thread -> channel group cg = t % C4s ; pixel lane = t / C4s   (C4s = min(C4, 256))
-  for (int cg0 = 0; cg0 < C4; cg0 += 256) {
+  {
+    const int cg0 = blockIdx.z * 256;
     const int cgs = min(C4 - cg0, 256);
     const int lanes = 256 / cgs;  // pixels processed concurrently by the block
     const int cg = cg0 + (threadIdx.x % cgs);
     const int pl = threadIdx.x / cgs;
     float4 sum = make_float4(0.f, 0.f, 0.f, 0.f);
-    __syncthreads();
     if (pl < lanes) {
       const float4 sc = __ldg(reinterpret_cast<const float4*>(scale) + cg);
       const float4 sh = __ldg(reinterpret_cast<const float4*>(shift) + cg);
@@ -89,7 +90,7 @@ __global__ void __launch_bounds__(256) dwconv_kernel(const float* __restrict__ x
 }
 
 // ---- SE gate: one block per image
-__global__ void __launch_bounds__(256) se_gate_kernel(const float* __restrict__ chan_part, int nparts,
+__global__ void __launch_bounds__(1024) se_gate_kernel(const float* __restrict__ chan_part, int nparts,
                                                       float inv_hw, int C, int Csq,
                                                       const float* __restrict__ w_red,
                                                       const float* __restrict__ b_red,
@@ -101,8 +102,18 @@ __global__ void __launch_bounds__(256) se_gate_kernel(const float* __restrict__ 
   float* sq = sm + C;
   const int n = blockIdx.x;
   for (int c = threadIdx.x; c < C; c += blockDim.x) {
+    // fixed summation order (row 0, 1, 2, ...) with 8 independent loads in flight
+    const float* src = chan_part + (size_t)n * nparts * C + c;
     float tot = 0.0f;
-    for (int j = 0; j < nparts; ++j) tot += chan_part[((size_t)n * nparts + j) * C + c];
+    int j = 0;
+    for (; j + 8 <= nparts; j += 8) {
+      float v[8];
+#pragma unroll
+      for (int u = 0; u < 8; ++u) v[u] = __ldg(src + (size_t)(j + u) * C);
+#pragma unroll
+      for (int u = 0; u < 8; ++u) tot += v[u];
+    }
+    for (; j < nparts; ++j) tot += __ldg(src + (size_t)j * C);
     mean[c] = tot * inv_hw;
   }
   __syncthreads();
@@ -158,9 +169,12 @@ extern "C" int creste_conv2d(const creste_conv_desc* d, const float* x, const fl
 
 extern "C" int creste_dwconv_num_parts(int N, int P, int Q) {
   // independent of N on purpose: the per-image summation order (hence the result bits) must not
-  // depend on how many frames share the launch (frames are the data-parallel sharding unit)
+  // depend on how many frames share the launch (frames are the data-parallel sharding unit).
+  // >= 2 CTAs per SM worth of tiles even for the 16x30 layers, <= 64 pixels per tile.
   (void)N;
-  const int tiles = ceil_div(P * Q, 64);
+  const int PQ = P * Q;
+  int tiles = ceil_div(PQ, 64);
+  if (tiles < 296) tiles = PQ < 296 ? PQ : 296;
   return tiles > 592 ? 592 : tiles;
 }
 
@@ -172,7 +186,7 @@ extern "C" int creste_dwconv_bn_swish(const float* x, const float* w, const floa
   CRESTE_CHECK_ARG(C % 4 == 0 && (R == 3 || R == 5), "creste_dwconv_bn_swish: C%%4==0, R in {3,5}");
   CRESTE_CHECK_ARG(nparts == creste_dwconv_num_parts(N, P, Q), "creste_dwconv_bn_swish: nparts");
   cudaStream_t st = (cudaStream_t)stream;
-  dim3 grid(nparts, N);
+  dim3 grid(nparts, N, ceil_div(C / 4, 256));
   if (R == 3)
     dwconv_kernel<3><<<grid, 256, 0, st>>>(x, w, scale, shift, N, H, W, C, stride, pad_t, pad_l, P, Q, out, chan_part);
   else
@@ -185,7 +199,7 @@ extern "C" int creste_se_gate(const float* chan_part, int nparts, float inv_hw, 
                               const float* b_exp, float* gate, void* stream) {
   CRESTE_CHECK_ARG(chan_part && w_red && b_red && w_exp && b_exp && gate && nparts > 0, "creste_se_gate: null pointer");
   const size_t smem = (size_t)(C + Csq) * sizeof(float);
-  se_gate_kernel<<<N, 256, smem, (cudaStream_t)stream>>>(chan_part, nparts, inv_hw, C, Csq, w_red, b_red, w_exp,
+  se_gate_kernel<<<N, 1024, smem, (cudaStream_t)stream>>>(chan_part, nparts, inv_hw, C, Csq, w_red, b_red, w_exp,
                                                         b_exp, gate);
   return launch_check("se_gate_kernel");
 }

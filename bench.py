@@ -337,9 +337,9 @@ def main():
     ap.add_argument("--gpus", type=int, default=1)
     ap.add_argument("--steps", type=int, default=10)
     ap.add_argument("--warmup", type=int, default=3)
-    ap.add_argument("--batch", type=int, default=2, help="frames per step per GPU")
+    ap.add_argument("--batch", type=int, default=8, help="frames per step per GPU")
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
-    ap.add_argument("--precision", default="fp32", choices=["fp32", "3xtf32", "tf32", "bf16"])
+    ap.add_argument("--precision", default="3xtf32", choices=["fp32", "3xtf32", "tf32"])
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
     args = ap.parse_args()
     if args.warmup < 3 and args.impl == "ours":

@@ -25,6 +25,10 @@
 // fp32, which measures as fp32-faithful on the costmap (DESIGN.md "Precision").  Round-to-nearest
 // in the split matters: truncation splits bias every product the same way and cost 10x accuracy.
 //
+// CTA pairs: two CTAs on adjacent M tiles run as one cta_group::2 pair (M = 256 MMAs issued by the
+// leader, each CTA staging its own A tile and half of the weight tile), which halves the
+// shared-memory operand traffic per MMA -- the single-CTA form measured ~50 % of the tensor peak.
+//
 // Warp roles (192 threads): warp 0 = TMA producer, warp 1 = TMEM alloc + MMA issuer (one elected
 // lane issues tcgen05.mma; tcgen05.commit releases smem stages / signals the epilogue),
 // warps 2-5 = epilogue.  mbarrier ring of NSTAGES smem stages.
@@ -75,6 +79,74 @@ __device__ __forceinline__ void tma_load_2d(const CUtensorMap* map, uint64_t* ba
       " [%0], [%1, {%3, %4}], [%2];" ::"r"(smem_u32(dst)),
       "l"((uint64_t)map), "r"(smem_u32(bar)), "r"(c0), "r"(c1)
       : "memory");
+}
+__device__ __forceinline__ void tma_load_2d_mc(const CUtensorMap* map, uint64_t* bar, void* dst, int c0,
+                                               int c1, uint16_t mask) {
+  asm volatile(
+      "cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes.multicast::cluster"
+      " [%0], [%1, {%4, %5}], [%2], %3;" ::"r"(smem_u32(dst)),
+      "l"((uint64_t)map), "r"(smem_u32(bar)), "h"(mask), "r"(c0), "r"(c1)
+      : "memory");
+}
+__device__ __forceinline__ void umma_commit_mc(uint64_t* bar, uint16_t mask) {
+  asm volatile(
+      "tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;" ::"r"(
+          smem_u32(bar)),
+      "h"(mask)
+      : "memory");
+}
+// ---- cta_group::2 (CTA pair) variants: TMA signals the LEADER CTA's mbarrier (peer bit cleared)
+constexpr uint32_t PEER_BIT_MASK = 0xFEFFFFFFu;
+__device__ __forceinline__ void tma_load_4d_2sm(const CUtensorMap* map, uint64_t* bar, void* dst, int c0,
+                                                int c1, int c2, int c3) {
+  asm volatile(
+      "cp.async.bulk.tensor.4d.cta_group::2.shared::cluster.global.mbarrier::complete_tx::bytes"
+      " [%0], [%1, {%3, %4, %5, %6}], [%2];" ::"r"(smem_u32(dst)),
+      "l"((uint64_t)map), "r"(smem_u32(bar) & PEER_BIT_MASK), "r"(c0), "r"(c1), "r"(c2), "r"(c3)
+      : "memory");
+}
+__device__ __forceinline__ void tma_load_2d_2sm(const CUtensorMap* map, uint64_t* bar, void* dst, int c0,
+                                                int c1) {
+  asm volatile(
+      "cp.async.bulk.tensor.2d.cta_group::2.shared::cluster.global.mbarrier::complete_tx::bytes"
+      " [%0], [%1, {%3, %4}], [%2];" ::"r"(smem_u32(dst)),
+      "l"((uint64_t)map), "r"(smem_u32(bar) & PEER_BIT_MASK), "r"(c0), "r"(c1)
+      : "memory");
+}
+__device__ __forceinline__ void tmem_alloc_2sm(uint32_t* dst_smem, uint32_t ncols) {
+  asm volatile("tcgen05.alloc.cta_group::2.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(dst_smem)),
+               "r"(ncols)
+               : "memory");
+  asm volatile("tcgen05.relinquish_alloc_permit.cta_group::2.sync.aligned;" ::: "memory");
+}
+__device__ __forceinline__ void tmem_dealloc_2sm(uint32_t addr, uint32_t ncols) {
+  asm volatile("tcgen05.dealloc.cta_group::2.sync.aligned.b32 %0, %1;" ::"r"(addr), "r"(ncols) : "memory");
+}
+__device__ __forceinline__ void umma_commit_2sm(uint64_t* bar) {
+  asm volatile(
+      "tcgen05.commit.cta_group::2.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;" ::"r"(
+          smem_u32(bar)),
+      "h"((uint16_t)3)
+      : "memory");
+}
+__device__ __forceinline__ void umma_tf32_2sm(uint32_t tmem_d, uint64_t a_desc, uint64_t b_desc,
+                                              uint32_t idesc, uint32_t accumulate) {
+  asm volatile(
+      "{\n\t"
+      ".reg .pred p;\n\t"
+      "setp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::2.kind::tf32 [%0], %1, %2, %3, p;\n\t"
+      "}" ::"r"(tmem_d),
+      "l"(a_desc), "l"(b_desc), "r"(idesc), "r"(accumulate)
+      : "memory");
+}
+__device__ __forceinline__ void cluster_sync_all() {
+  asm volatile("barrier.cluster.arrive.aligned;\n\tbarrier.cluster.wait.aligned;" ::: "memory");
+}
+__device__ __forceinline__ uint32_t cluster_ctarank() {
+  uint32_t r;
+  asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r));
+  return r;
 }
 __device__ __forceinline__ void prefetch_tmap(const CUtensorMap* map) {
   asm volatile("prefetch.tensormap [%0];" ::"l"((uint64_t)map) : "memory");
@@ -144,8 +216,8 @@ __device__ __forceinline__ uint64_t make_sw128_desc(uint32_t saddr) {
   return (uint64_t)((saddr >> 4) & 0x3FFFu) | (1ull << 16) | (64ull << 32) | (1ull << 46) | (2ull << 61);
 }
 // UMMA::InstrDescriptor for kind::tf32, fp32 accumulate, K-major A and B, M = 128
-__host__ __device__ constexpr uint32_t make_idesc_tf32(int n) {
-  return (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(n >> 3) << 17) | ((128u >> 4) << 24);
+__host__ __device__ constexpr uint32_t make_idesc_tf32(int n, int m = 128) {
+  return (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(n >> 3) << 17) | ((uint32_t)(m >> 4) << 24);
 }
 
 // ------------------------------------------------------------------------------------ kernels
@@ -157,6 +229,7 @@ struct TcParams {
   int wbox, hbox, tiles_x, tiles_y;
   int block_n, act, split;     // split: 1 = 3xTF32 (hi/lo operands), 0 = single TF32
   int out_nchw;
+  int cl;                      // cluster size along the M tiles; the B tile is TMA-multicast in cl slices
 };
 
 constexpr int TC_THREADS = 192;
@@ -169,6 +242,12 @@ __device__ __forceinline__ float tc_act(float v, int act) {
   return v;
 }
 
+// PAIR = true: the two CTAs of a cluster form a tcgen05 CTA pair (cta_group::2).  Each CTA stages
+// its own 128-pixel A tile and HALF of the weight tile (block_n/2 rows); the leader CTA issues
+// M = 256 MMAs that read both CTAs' shared memory and write each CTA's half of D into that CTA's
+// TMEM.  Operand bytes read from shared memory per MMA-cycle halve -- the single-CTA form is bound
+// by shared-memory bandwidth ((128 + 256) rows x 32 B per 128-cycle MMA + the TMA fill).
+template <bool PAIR>
 __global__ void __launch_bounds__(TC_THREADS, 1)
 conv_tc_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_constant__ CUtensorMap map_a_lo,
                const __grid_constant__ CUtensorMap map_b_hi, const __grid_constant__ CUtensorMap map_b_lo,
@@ -180,7 +259,10 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_consta
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int nops = p.split ? 2 : 1;
-  const int b_tile_bytes = p.block_n * 128;
+  const uint32_t rank = PAIR ? cluster_ctarank() : 0;
+  const bool leader = rank == 0;
+  const int b_rows = PAIR ? p.block_n / 2 : p.block_n;     // weight rows staged by THIS CTA
+  const int b_tile_bytes = b_rows * 128;
   const int stage_bytes = nops * (A_TILE_BYTES + b_tile_bytes);
 
   // tile coordinates
@@ -208,14 +290,18 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_consta
     mbar_init(&tmem_full_bar, 1);
     fence_barrier_init();
   }
-  if (warp == 1) tmem_alloc(&tmem_base_smem, tmem_cols);
+  if (warp == 1) {
+    if (PAIR) tmem_alloc_2sm(&tmem_base_smem, tmem_cols);
+    else tmem_alloc(&tmem_base_smem, tmem_cols);
+  }
   tc_fence_before();
   __syncthreads();
+  if (PAIR) cluster_sync_all();       // barrier inits + TMEM allocation of both CTAs in place
   tc_fence_after();
   const uint32_t tmem_base = tmem_base_smem;
 
   if (warp == 0) {
-    // ===== TMA producer =====
+    // ===== TMA producer (both CTAs of a pair; completion bytes land on the leader's barrier) =====
     if (elect_one()) {
       for (int kb = 0; kb < kblocks; ++kb) {
         const int stage = kb % nstages;
@@ -225,47 +311,69 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_consta
         const int tap = kb / p.cblocks;
         const int r = tap / p.S, s = tap - r * p.S;
         uint8_t* st = smem + (size_t)stage * stage_bytes;
-        mbar_expect_tx(&full_bar[stage], (uint32_t)stage_bytes);
         const int cx = x0 + s - p.pad_l, cy = y0 + r - p.pad_t;
-        tma_load_4d(&map_a_hi, &full_bar[stage], st, cb * 32, cx, cy, img);
-        tma_load_2d(&map_b_hi, &full_bar[stage], st + nops * A_TILE_BYTES, kb * 32, n0);
-        if (p.split) {
-          tma_load_4d(&map_a_lo, &full_bar[stage], st + A_TILE_BYTES, cb * 32, cx, cy, img);
-          tma_load_2d(&map_b_lo, &full_bar[stage], st + 2 * A_TILE_BYTES + b_tile_bytes, kb * 32, n0);
+        uint8_t* b_hi = st + nops * A_TILE_BYTES;
+        uint8_t* b_lo = b_hi + b_tile_bytes;
+        const int nrow = n0 + (int)rank * b_rows;
+        if (PAIR) {
+          if (leader) mbar_expect_tx(&full_bar[stage], (uint32_t)(2 * stage_bytes));
+          tma_load_4d_2sm(&map_a_hi, &full_bar[stage], st, cb * 32, cx, cy, img);
+          tma_load_2d_2sm(&map_b_hi, &full_bar[stage], b_hi, kb * 32, nrow);
+          if (p.split) {
+            tma_load_4d_2sm(&map_a_lo, &full_bar[stage], st + A_TILE_BYTES, cb * 32, cx, cy, img);
+            tma_load_2d_2sm(&map_b_lo, &full_bar[stage], b_lo, kb * 32, nrow);
+          }
+        } else {
+          mbar_expect_tx(&full_bar[stage], (uint32_t)stage_bytes);
+          tma_load_4d(&map_a_hi, &full_bar[stage], st, cb * 32, cx, cy, img);
+          tma_load_2d(&map_b_hi, &full_bar[stage], b_hi, kb * 32, nrow);
+          if (p.split) {
+            tma_load_4d(&map_a_lo, &full_bar[stage], st + A_TILE_BYTES, cb * 32, cx, cy, img);
+            tma_load_2d(&map_b_lo, &full_bar[stage], b_lo, kb * 32, nrow);
+          }
         }
       }
     }
+    __syncwarp();   // reconverge before the CTA / cluster barriers below
   } else if (warp == 1) {
-    // ===== MMA issuer =====
-    const uint32_t idesc = make_idesc_tf32(p.block_n);
-    for (int kb = 0; kb < kblocks; ++kb) {
-      const int stage = kb % nstages;
-      const uint32_t parity = (kb / nstages) & 1;
-      mbar_wait(&full_bar[stage], parity);
-      tc_fence_after();
-      if (elect_one()) {
-        const uint32_t st = smem_u32(smem + (size_t)stage * stage_bytes);
-        const uint32_t a_hi = st, a_lo = st + A_TILE_BYTES;
-        const uint32_t b_hi = st + nops * A_TILE_BYTES, b_lo = b_hi + b_tile_bytes;
+    // ===== MMA issuer (leader CTA only in pair mode) =====
+    if (leader) {
+      const uint32_t idesc = make_idesc_tf32(p.block_n, PAIR ? 256 : 128);
+      for (int kb = 0; kb < kblocks; ++kb) {
+        const int stage = kb % nstages;
+        const uint32_t parity = (kb / nstages) & 1;
+        mbar_wait(&full_bar[stage], parity);
+        tc_fence_after();
+        if (elect_one()) {
+          const uint32_t st = smem_u32(smem + (size_t)stage * stage_bytes);
+          const uint32_t a_hi = st, a_lo = st + A_TILE_BYTES;
+          const uint32_t b_hi = st + nops * A_TILE_BYTES, b_lo = b_hi + b_tile_bytes;
 #pragma unroll
-        for (int k = 0; k < 4; ++k) {   // 4 x (K = 8 tf32 = 32 B) per 128-byte swizzle row
-          const uint32_t koff = k * 32;
-          if (p.split) {
-            umma_tf32(tmem_base + acc2, make_sw128_desc(a_lo + koff), make_sw128_desc(b_hi + koff),
-                      idesc, (kb | k) != 0);
-            umma_tf32(tmem_base + acc2, make_sw128_desc(a_hi + koff), make_sw128_desc(b_lo + koff),
-                      idesc, 1);
-            umma_tf32(tmem_base, make_sw128_desc(a_hi + koff), make_sw128_desc(b_hi + koff), idesc,
-                      (kb | k) != 0);
-          } else {
-            umma_tf32(tmem_base, make_sw128_desc(a_hi + koff), make_sw128_desc(b_hi + koff), idesc,
-                      (kb | k) != 0);
+          for (int k = 0; k < 4; ++k) {   // 4 x (K = 8 tf32 = 32 B) per 128-byte swizzle row
+            const uint32_t koff = k * 32;
+            const uint32_t first = (kb | k) != 0;
+            if (PAIR) {
+              if (p.split) {
+                umma_tf32_2sm(tmem_base + acc2, make_sw128_desc(a_lo + koff), make_sw128_desc(b_hi + koff), idesc, first);
+                umma_tf32_2sm(tmem_base + acc2, make_sw128_desc(a_hi + koff), make_sw128_desc(b_lo + koff), idesc, 1);
+              }
+              umma_tf32_2sm(tmem_base, make_sw128_desc(a_hi + koff), make_sw128_desc(b_hi + koff), idesc, first);
+            } else {
+              if (p.split) {
+                umma_tf32(tmem_base + acc2, make_sw128_desc(a_lo + koff), make_sw128_desc(b_hi + koff), idesc, first);
+                umma_tf32(tmem_base + acc2, make_sw128_desc(a_hi + koff), make_sw128_desc(b_lo + koff), idesc, 1);
+              }
+              umma_tf32(tmem_base, make_sw128_desc(a_hi + koff), make_sw128_desc(b_hi + koff), idesc, first);
+            }
+          }
+          // smem stage free (in both CTAs of a pair) once these MMAs retire
+          if (PAIR) umma_commit_2sm(&empty_bar[stage]); else umma_commit(&empty_bar[stage]);
+          if (kb == kblocks - 1) {
+            if (PAIR) umma_commit_2sm(&tmem_full_bar); else umma_commit(&tmem_full_bar);
           }
         }
-        umma_commit(&empty_bar[stage]);                 // smem stage free once these MMAs retire
-        if (kb == kblocks - 1) umma_commit(&tmem_full_bar);
+        __syncwarp();
       }
-      __syncwarp();
     }
   } else {
     // ===== epilogue: warps 2..5, TMEM lane quarter = warp % 4 =====
@@ -273,7 +381,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_consta
     const int m = quarter * 32 + lane;               // accumulator row = box-order pixel index
     const int wx = m % p.wbox, hy = m / p.wbox;
     const int ox = x0 + wx, oy = y0 + hy;
-    const bool pix_ok = (ox < p.Q) && (oy < p.P);
+    const bool pix_ok = (ox < p.Q) && (oy < p.P) && (img < p.N);
     const size_t pix = ((size_t)img * p.P + oy) * p.Q + ox;
     mbar_wait(&tmem_full_bar, 0);
     tc_fence_after();
@@ -327,9 +435,11 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_consta
   }
   tc_fence_before();
   __syncthreads();
+  if (PAIR) cluster_sync_all();       // no CTA exits while its peer's MMAs / TMA can still touch it
   if (warp == 1) {
     tc_fence_after();
-    tmem_dealloc(tmem_base, tmem_cols);
+    if (PAIR) tmem_dealloc_2sm(tmem_base, tmem_cols);
+    else tmem_dealloc(tmem_base, tmem_cols);
   }
 }
 
@@ -486,24 +596,39 @@ int conv_tc_launch(const creste_conv_desc* d, const float* x, const float* w_pac
   p.tiles_y = ceil_div(d->P, p.hbox);
   p.block_n = block_n; p.act = d->act; p.split = split; p.out_nchw = d->out_nchw;
 
+  // two CTAs on adjacent M tiles form a tcgen05 CTA pair (cta_group::2, M = 256)
+  const int m_tiles = d->N * p.tiles_y * p.tiles_x;
+  const int cl = (m_tiles >= 2 && (block_n % 16) == 0 && !getenv("CRESTE_TC_NO_PAIR")) ? 2 : 1;
+  p.cl = cl;
   CUtensorMap ma_hi, ma_lo, mb_hi, mb_lo;
   int rc;
   if ((rc = make_map_a(&ma_hi, x_hi, d->N, d->H, d->W, d->C, p.wbox, p.hbox))) return rc;
   if ((rc = make_map_a(&ma_lo, split ? x_lo : x_hi, d->N, d->H, d->W, d->C, p.wbox, p.hbox))) return rc;
   const float* w_hi = w_packed;
   const float* w_lo = w_packed + (size_t)npad * ktot;
-  if ((rc = make_map_b(&mb_hi, w_hi, ktot, npad, block_n))) return rc;
-  if ((rc = make_map_b(&mb_lo, split ? w_lo : w_hi, ktot, npad, block_n))) return rc;
+  if ((rc = make_map_b(&mb_hi, w_hi, ktot, npad, block_n / cl))) return rc;
+  if ((rc = make_map_b(&mb_lo, split ? w_lo : w_hi, ktot, npad, block_n / cl))) return rc;
 
   const int nops = split ? 2 : 1;
-  const size_t stage_bytes = (size_t)nops * (A_TILE_BYTES + block_n * 128);
+  const size_t stage_bytes = (size_t)nops * (A_TILE_BYTES + (block_n / cl) * 128);
   int nstages = (int)((200 * 1024) / stage_bytes);
   if (nstages > 8) nstages = 8;
   if (nstages < 2) { set_error("creste_conv2d(tc): stage too large"); return CRESTE_ERR_ARG; }
   const size_t smem = (size_t)nstages * stage_bytes + 1024;
-  CRESTE_CUDA(cudaFuncSetAttribute(conv_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-  dim3 grid(d->N * p.tiles_y * p.tiles_x, npad / block_n);
-  conv_tc_kernel<<<grid, TC_THREADS, smem, st>>>(ma_hi, ma_lo, mb_hi, mb_lo, p, nstages);
+  auto kern = cl == 2 ? conv_tc_kernel<true> : conv_tc_kernel<false>;
+  CRESTE_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  dim3 grid(ceil_div(m_tiles, cl) * cl, npad / block_n);
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = grid;
+  cfg.blockDim = dim3(TC_THREADS);
+  cfg.dynamicSmemBytes = smem;
+  cfg.stream = st;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeClusterDimension;
+  attr[0].val.clusterDim.x = cl; attr[0].val.clusterDim.y = 1; attr[0].val.clusterDim.z = 1;
+  cfg.attrs = attr;
+  cfg.numAttrs = 1;
+  CRESTE_CUDA(cudaLaunchKernelEx(&cfg, kern, ma_hi, ma_lo, mb_hi, mb_lo, p, nstages));
   return launch_check("conv_tc_kernel");
 }
 

@@ -25,6 +25,12 @@ EXPORTS = [
     "creste_upsample_concat", "creste_maxpool2_concat",
     "creste_nchw_to_nhwc", "creste_nhwc_to_nchw",
     "creste_expert_visitation",
+    "creste_chan_affine", "creste_relu_bwd", "creste_chan_dot_workspace_bytes", "creste_chan_dot",
+    "creste_maxpool2_bwd", "creste_maxpool2_gather", "creste_upsample_adjoint",
+    "creste_conv2d_wgrad_workspace_bytes", "creste_conv2d_wgrad",
+    "creste_row_dot", "creste_row_scale", "creste_row_normalize",
+    "creste_grad_penalty_workspace_bytes", "creste_grad_penalty", "creste_grad_penalty_bwd",
+    "creste_adam_step",
 ]
 
 
@@ -59,7 +65,9 @@ def lib():
         L.creste_last_error.restype = C.c_char_p
         L.creste_launch_count.restype = C.c_ulonglong
         for name in ("creste_vi_workspace_bytes", "creste_svf_workspace_bytes",
-                     "creste_splat_workspace_bytes", "creste_conv2d_workspace_bytes"):
+                     "creste_splat_workspace_bytes", "creste_conv2d_workspace_bytes",
+                     "creste_chan_dot_workspace_bytes", "creste_conv2d_wgrad_workspace_bytes",
+                     "creste_grad_penalty_workspace_bytes"):
             getattr(L, name).restype = C.c_size_t
         _lib = L
     return _lib

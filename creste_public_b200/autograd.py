@@ -1,0 +1,340 @@
+"""Differentiable wrappers of the sm_100a kernels for the stage-3 (IRL) training step.
+
+The reference trains the reward FCN with PyTorch autograd, including a *double backward*: the
+SMODICE gradient penalty differentiates d(sum r)/d(input_view) w.r.t. the weights
+(creste/utils/loss_utils.py:1208-1217).  torch.autograd is used here as the tape engine only:
+every node is a `torch.autograd.Function` whose forward is one C-ABI kernel and whose backward is
+written *in terms of the other Functions in this file*, so the set is closed under
+differentiation and `torch.autograd.grad(..., create_graph=True)` works to any order:
+
+    Conv2dFn    <-> Conv2dFn with flipped-transposed weights (dgrad), WGradFn
+    WGradFn     <-> Conv2dFn (both arguments)
+    ChanAffineFn (+ReLU) <-> ReluBwdFn, ChanDotFn ;  ChanDotFn <-> ChanAffineFn
+    MaxPool2Fn  <-> MaxPoolBwdFn <-> MaxPoolGatherFn
+    Up2Fn       <-> Up2AdjFn ;  ToNHWC <-> ToNCHW ;  RowDotFn <-> RowScaleFn
+    GradPenaltyFn (first order only: it is the last node before the loss)
+
+Tensors are channels-last fp32.  The only torch-native differentiable ops in the graph are
+views / permutations / pads of tiny tensors (weights, per-channel vectors) and `torch.cat`.
+"""
+import torch
+from torch.autograd import Function
+
+from . import engine, ops
+
+
+def _pad_last(t, mult=4):
+    c = t.shape[-1]
+    r = (-c) % mult
+    if r == 0:
+        return t.contiguous()
+    return torch.cat([t, t.new_zeros(*t.shape[:-1], r)], dim=-1).contiguous()
+
+
+def _conv_raw(x, w, ph, pw):
+    """Stride-1 conv of NHWC x with torch-layout weights w [K,C,R,S]; no epilogue.  Channel
+    counts that are not multiples of 4 are zero-padded (exact)."""
+    K, Cc, R, S = w.shape
+    xp = _pad_last(x)
+    Cp = xp.shape[-1]
+    Kp = K + ((-K) % 4)
+    wp = w
+    if Cp != Cc or Kp != K:
+        wp = w.new_zeros(Kp, Cp, R, S)
+        wp[:K, :Cc] = w
+    pad = (ph, ph, pw, pw)
+    mode = engine.get_precision()
+    if mode != "fp32" and not ops.tc_supported(tuple(xp.shape), Kp, R, S, 1, pad, mode):
+        mode = "fp32"
+    if mode == "fp32":
+        packed = ops.pack_conv_weight(wp.detach().float())
+    else:
+        packed = ops.pack_conv_weight_tc(wp.detach().float(), split=(mode == "3xtf32"))
+    y = ops.conv2d(xp, packed, Kp, R, S, 1, pad, precision=mode)
+    return y if Kp == K else y[..., :K].contiguous()
+
+
+def _wgrad_raw(x, g, R, S, ph, pw):
+    Cc, K = x.shape[-1], g.shape[-1]
+    dw = ops.conv2d_wgrad(_pad_last(x), _pad_last(g), R, S, (ph, ph, pw, pw))
+    return dw[:K, :Cc].contiguous()
+
+
+def _flip_t(w):
+    """[K,C,R,S] -> [C,K,R,S] rotated by 180 degrees: the weights of the data-gradient conv."""
+    return w.flip(2, 3).transpose(0, 1)
+
+
+class Conv2dFn(Function):
+    @staticmethod
+    def forward(ctx, x, w, ph, pw):
+        ctx.save_for_backward(x, w)
+        ctx.pad = (ph, pw)
+        return _conv_raw(x, w, ph, pw)
+
+    @staticmethod
+    def backward(ctx, g):
+        x, w = ctx.saved_tensors
+        ph, pw = ctx.pad
+        R, S = w.shape[2], w.shape[3]
+        dx = dw = None
+        if ctx.needs_input_grad[0]:
+            dx = Conv2dFn.apply(g, _flip_t(w), R - 1 - ph, S - 1 - pw)
+        if ctx.needs_input_grad[1]:
+            dw = WGradFn.apply(x, g, R, S, ph, pw)
+        return dx, dw, None, None
+
+
+class WGradFn(Function):
+    @staticmethod
+    def forward(ctx, x, g, R, S, ph, pw):
+        ctx.save_for_backward(x, g)
+        ctx.geom = (R, S, ph, pw)
+        return _wgrad_raw(x, g, R, S, ph, pw)
+
+    @staticmethod
+    def backward(ctx, ggw):
+        x, g = ctx.saved_tensors
+        R, S, ph, pw = ctx.geom
+        dx = dg = None
+        if ctx.needs_input_grad[0]:
+            dx = Conv2dFn.apply(g, _flip_t(ggw), R - 1 - ph, S - 1 - pw)
+        if ctx.needs_input_grad[1]:
+            dg = Conv2dFn.apply(x, ggw, ph, pw)
+        return dx, dg, None, None, None, None
+
+
+class ChanAffineFn(Function):
+    """y = act(x * a[c] + b[c]); a / b may be None (1 / 0)."""
+
+    @staticmethod
+    def forward(ctx, x, a, b, relu):
+        y = ops.chan_affine(x, a, b, relu)
+        ctx.relu = relu
+        ctx.has_a = a is not None
+        ctx.save_for_backward(x, a, y if relu else None)
+        return y
+
+    @staticmethod
+    def backward(ctx, g):
+        x, a, y = ctx.saved_tensors
+        gm = ReluBwdFn.apply(g, y) if ctx.relu else g
+        dx = da = db = None
+        if ctx.needs_input_grad[0]:
+            dx = ChanAffineFn.apply(gm, a, None, False) if ctx.has_a else gm
+        if ctx.has_a and ctx.needs_input_grad[1]:
+            da = ChanDotFn.apply(gm, x)
+        if ctx.needs_input_grad[2]:
+            db = ChanDotFn.apply(gm, None)
+        return dx, da, db, None
+
+
+class ReluBwdFn(Function):
+    """g * (y > 0); y carries no gradient."""
+
+    @staticmethod
+    def forward(ctx, g, y):
+        ctx.save_for_backward(y)
+        return ops.relu_bwd(g, y)
+
+    @staticmethod
+    def backward(ctx, gg):
+        (y,) = ctx.saved_tensors
+        return ReluBwdFn.apply(gg, y), None
+
+
+class ChanDotFn(Function):
+    """out[c] = sum_pix x[pix,c] * y[pix,c]   (y None: channel sum)."""
+
+    @staticmethod
+    def forward(ctx, x, y):
+        ctx.save_for_backward(x, y)
+        return ops.chan_dot(x, y)
+
+    @staticmethod
+    def backward(ctx, gc):
+        x, y = ctx.saved_tensors
+        dx = dy = None
+        if y is None:
+            if ctx.needs_input_grad[0]:   # broadcast gc over the pixels
+                zero = torch.zeros_like(gc)
+                dx = ChanAffineFn.apply(x.detach(), zero, gc, False)
+            return dx, None
+        if ctx.needs_input_grad[0]:
+            dx = ChanAffineFn.apply(y, gc, None, False)
+        if ctx.needs_input_grad[1]:
+            dy = ChanAffineFn.apply(x, gc, None, False)
+        return dx, dy
+
+
+class MaxPool2Fn(Function):
+    @staticmethod
+    def forward(ctx, x):
+        ctx.save_for_backward(x)
+        return ops.maxpool2(x)
+
+    @staticmethod
+    def backward(ctx, g):
+        (x,) = ctx.saved_tensors
+        return MaxPoolBwdFn.apply(g, x)
+
+
+class MaxPoolBwdFn(Function):
+    @staticmethod
+    def forward(ctx, g, x):
+        ctx.save_for_backward(x)
+        return ops.maxpool2_bwd(x, g)
+
+    @staticmethod
+    def backward(ctx, gg):
+        (x,) = ctx.saved_tensors
+        return MaxPoolGatherFn.apply(gg, x), None
+
+
+class MaxPoolGatherFn(Function):
+    @staticmethod
+    def forward(ctx, gg, x):
+        ctx.save_for_backward(x)
+        return ops.maxpool2_gather(x, gg)
+
+    @staticmethod
+    def backward(ctx, g):
+        (x,) = ctx.saved_tensors
+        return MaxPoolBwdFn.apply(g, x), None
+
+
+class Up2Fn(Function):
+    @staticmethod
+    def forward(ctx, x):
+        return ops.upsample2(x)
+
+    @staticmethod
+    def backward(ctx, g):
+        return Up2AdjFn.apply(g)
+
+
+class Up2AdjFn(Function):
+    @staticmethod
+    def forward(ctx, g):
+        return ops.upsample2_adjoint(g)
+
+    @staticmethod
+    def backward(ctx, gg):
+        return Up2Fn.apply(gg)
+
+
+class ToNHWC(Function):
+    @staticmethod
+    def forward(ctx, x):
+        return ops.nchw_to_nhwc(x)
+
+    @staticmethod
+    def backward(ctx, g):
+        return ToNCHW.apply(g)
+
+
+class ToNCHW(Function):
+    @staticmethod
+    def forward(ctx, x):
+        return ops.nhwc_to_nchw(x)
+
+    @staticmethod
+    def backward(ctx, g):
+        return ToNHWC.apply(g)
+
+
+class RowDotFn(Function):
+    """out[b] = sum_i x[b,i] * w[b,i] * mask[b,i]   (mask uint8 or None)."""
+
+    @staticmethod
+    def forward(ctx, x, w, mask):
+        ctx.save_for_backward(x, w, mask)
+        return ops.row_dot(x, w, mask)
+
+    @staticmethod
+    def backward(ctx, gb):
+        x, w, mask = ctx.saved_tensors
+        dx = dw = None
+        if ctx.needs_input_grad[0]:
+            dx = RowScaleFn.apply(w, gb, mask)
+        if ctx.needs_input_grad[1]:
+            dw = RowScaleFn.apply(x, gb, mask)
+        return dx, dw, None
+
+
+class RowScaleFn(Function):
+    """out[b,i] = x[b,i] * s[b] * mask[b,i]."""
+
+    @staticmethod
+    def forward(ctx, x, s, mask):
+        ctx.save_for_backward(x, s, mask)
+        return ops.row_scale(x, s, mask)
+
+    @staticmethod
+    def backward(ctx, gg):
+        x, s, mask = ctx.saved_tensors
+        dx = ds = None
+        if ctx.needs_input_grad[0]:
+            dx = RowScaleFn.apply(gg, s, mask)
+        if ctx.needs_input_grad[1]:
+            ds = RowDotFn.apply(gg, x, mask)
+        return dx, ds, None
+
+
+class GradPenaltyFn(Function):
+    """mean_{b,pixel} (||G[b,:,pixel]||_2 - 1)^2 for G NCHW (loss_utils.py:1216-1217)."""
+
+    @staticmethod
+    def forward(ctx, G):
+        ctx.save_for_backward(G)
+        return ops.grad_penalty(G)
+
+    @staticmethod
+    @torch.autograd.function.once_differentiable
+    def backward(ctx, g):
+        (G,) = ctx.saved_tensors
+        return ops.grad_penalty_bwd(G, g)
+
+
+# ----------------------------------------------------------------------------- composed layers
+def conv2d(x, conv):
+    """nn.Conv2d parameters -> differentiable stride-1 NHWC conv (+ bias)."""
+    stride = conv.stride[0] if isinstance(conv.stride, tuple) else conv.stride
+    if stride != 1:
+        raise NotImplementedError("differentiable conv path: stride 1 only (reward FCN)")
+    ph, pw = conv.padding if isinstance(conv.padding, tuple) else (conv.padding,) * 2
+    y = Conv2dFn.apply(x, conv.weight, int(ph), int(pw))
+    if conv.bias is not None:
+        y = ChanAffineFn.apply(y, None, conv.bias, False)
+    return y
+
+
+def relu(x):
+    return ChanAffineFn.apply(x, None, None, True)
+
+
+def batch_norm(x, bn, relu=False):
+    """nn.BatchNorm2d over channels-last x, honouring bn.training exactly like F.batch_norm:
+    batch statistics (biased variance) + running-stat update in training mode, running statistics
+    in eval mode.  Composed of ChanDotFn / ChanAffineFn so it is differentiable to any order."""
+    Cc = x.shape[-1]
+    M = x.numel() // Cc
+    use_batch = bn.training or bn.running_mean is None
+    if use_batch:
+        mean = ChanDotFn.apply(x, None) / M
+        xc = ChanAffineFn.apply(x, None, -mean, False)
+        var = ChanDotFn.apply(xc, xc) / M
+        if bn.training and bn.track_running_stats and bn.running_mean is not None:
+            with torch.no_grad():
+                if bn.num_batches_tracked is not None:
+                    bn.num_batches_tracked += 1
+                mom = bn.momentum if bn.momentum is not None else 1.0 / float(bn.num_batches_tracked)
+                bn.running_mean.mul_(1 - mom).add_(mean.detach(), alpha=mom)
+                bn.running_var.mul_(1 - mom).add_(var.detach() * (M / max(M - 1, 1)), alpha=mom)
+        inv = torch.rsqrt(var + bn.eps)
+        scale = inv * bn.weight if bn.affine else inv
+        return ChanAffineFn.apply(xc, scale, bn.bias if bn.affine else None, relu)
+    inv = torch.rsqrt(bn.running_var + bn.eps)
+    scale = inv * bn.weight if bn.affine else inv
+    shift = (bn.bias if bn.affine else 0) - bn.running_mean * scale
+    return ChanAffineFn.apply(x, scale, shift, relu)

@@ -96,9 +96,31 @@ class ConvLayer(nn.Sequential):
     def forward_nhwc(self, x):
         return self.fused()(x, act="relu" if hasattr(self, "relu") else "none")
 
+    def forward_autograd_nhwc(self, x):
+        """Differentiable path (training / loss evaluation): conv -> BN (batch statistics when
+        self.norm.training, as F.batch_norm) -> ReLU, composed of creste_public_b200.autograd
+        Functions so that first- and second-order gradients flow."""
+        from creste_public_b200 import autograd as ag
+        y = ag.conv2d(x, self.conv)
+        has_relu = hasattr(self, "relu")
+        if hasattr(self, "norm"):
+            return ag.batch_norm(y, self.norm, relu=has_relu)
+        return ag.relu(y) if has_relu else y
+
     def forward(self, x):
+        if _wants_grad(self, x):
+            from creste_public_b200 import autograd as ag
+            return ag.ToNCHW.apply(self.forward_autograd_nhwc(ag.ToNHWC.apply(x.float())))
         require_eval(self)
         return ops.nhwc_to_nchw(self.forward_nhwc(ops.nchw_to_nhwc(x.float())))
+
+
+def _wants_grad(module, x):
+    """True when the reference's autograd would record this call: grad mode on and either the
+    input or a parameter of the module requires grad."""
+    if not torch.is_grad_enabled():
+        return False
+    return bool(x.requires_grad) or any(p.requires_grad for p in module.parameters())
 
 
 class MultiScaleFCN(nn.Module):
@@ -183,6 +205,38 @@ class MultiScaleFCN(nn.Module):
             cat = l.forward_nhwc(cat)
         return cat
 
+    def forward_autograd_nhwc(self, x):
+        """Differentiable (to second order) evaluation of the reward FCN; BatchNorm layers honour
+        their own .training flag like the reference (batch statistics + running-stat update in
+        train mode).  Reference graph: conv.py:148-161."""
+        from creste_public_b200 import autograd as ag
+        for l in self.prepool:
+            x = l.forward_autograd_nhwc(x)
+        skip = x
+        for l in self.skip:
+            skip = l.forward_autograd_nhwc(skip)
+        t = x
+        for m in self.trunk:
+            if isinstance(m, nn.MaxPool2d):
+                t = ag.MaxPool2Fn.apply(t)
+            elif isinstance(m, ConvLayer):
+                t = m.forward_autograd_nhwc(t)
+            elif isinstance(m, nn.BatchNorm2d):
+                t = ag.batch_norm(t, m, relu=False)
+            elif isinstance(m, nn.ReLU):
+                t = ag.relu(t)
+            elif isinstance(m, nn.Upsample):
+                t = ag.Up2Fn.apply(t)
+            else:
+                raise NotImplementedError(type(m).__name__)
+        cat = torch.cat([t, skip], dim=-1)
+        for l in self.postpool:
+            cat = l.forward_autograd_nhwc(cat)
+        return cat
+
     def forward(self, x):
         """Expects input of shape [B, C, H, W] (NCHW), returns [B, 1, H, W]."""
+        if _wants_grad(self, x):
+            from creste_public_b200 import autograd as ag
+            return ag.ToNCHW.apply(self.forward_autograd_nhwc(ag.ToNHWC.apply(x.float())))
         return ops.nhwc_to_nchw(self.forward_nhwc(ops.nchw_to_nhwc(x.float())))

@@ -40,26 +40,41 @@ class VIN(nn.Module):
 
     def forward_nhwc(self, preds_nhwc, S, solve_mdp=False):
         """preds_nhwc: the head predictions in NHWC, ordered as reward_cfg.input_keys."""
-        require_eval(self)
         ds = self.reward_cfg.ds
         if ds != 2:
             raise NotImplementedError("reward_cfg.ds must be 2 (2x2 max-pool kernel)")
         N, Ho, Wo, _ = preds_nhwc[0].shape
         rows = (Ho // ds) // 2
-        iv_nhwc, iv_nchw = ops.maxpool2_concat(preds_nhwc, rows_out=rows, want_nchw=True)
-        r_nhwc = self.r.forward_nhwc(iv_nhwc)                       # [N, rows, Wo/2, 1]
-        r = r_nhwc.view(N, 1, rows, Wo // ds)
+        with torch.no_grad():
+            iv_nhwc, iv_nchw = ops.maxpool2_concat([p.detach() for p in preds_nhwc], rows_out=rows,
+                                                   want_nchw=True)
+        train_graph = torch.is_grad_enabled() and any(p.requires_grad for p in self.r.parameters())
+        if train_graph:
+            # reference vin.py:116-119: input_view is a detached leaf that requires grad, so the
+            # loss can take d(sum r)/d(input_view) (and differentiate it again w.r.t. the weights)
+            from creste_public_b200 import autograd as ag
+            iv_nchw.requires_grad_(True)
+            r_nhwc = self.r.forward_autograd_nhwc(ag.ToNHWC.apply(iv_nchw))
+            r = r_nhwc.view(N, 1, rows, Wo // ds)                   # C == 1: same memory as NCHW
+            r_graph, r_nhwc = r, r_nhwc.detach()
+        else:
+            require_eval(self)
+            r_nhwc = self.r.forward_nhwc(iv_nhwc)                   # [N, rows, Wo/2, 1]
+            r = r_nhwc.view(N, 1, rows, Wo // ds)
+            r_graph = r
         # full-resolution copy: bilinear resize to (Ho//2, Wo) placed in the top half (:121-125)
-        full = torch.zeros(N, 1, Ho, Wo, device=r.device)
-        up = ops.upsample_concat(None, _pad4(r_nhwc), (Ho // 2, Wo), None)   # C padded to 4
-        full[:, 0, : Ho // 2, :] = up[..., 0]
+        with torch.no_grad():
+            full = torch.zeros(N, 1, Ho, Wo, device=r.device)
+            up = ops.upsample_concat(None, _pad4(r_nhwc), (Ho // 2, Wo), None)   # C padded to 4
+            full[:, 0, : Ho // 2, :] = up[..., 0]
         prefix = self.reward_cfg["output_prefix"][0]
-        outputs = {prefix: r, f"{prefix}_full": full, "input_view": iv_nchw}
+        outputs = {prefix: r_graph, f"{prefix}_full": full, "input_view": iv_nchw}
         if not solve_mdp:
             return outputs
         assert S is not None, "No expert demonstrations given but solve mdp is True"
-        v, policy, q = self.value_iteration_manual(r, S[:, -1, :], threshold=0.001,
-                                                   discount=self.discount)
+        with torch.no_grad():   # vin.py:134: no gradients through value iteration
+            v, policy, q = self.value_iteration_manual(r_graph.detach(), S[:, -1, :], threshold=0.001,
+                                                       discount=self.discount)
         outputs.update({"policy": policy, "q_estimate": q, "value_estimate": v})
         return outputs
 

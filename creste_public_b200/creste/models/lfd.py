@@ -100,9 +100,13 @@ class MaxEntIRL(nn.Module):
         return {"exp_svf": svf, "state_preds_grid": grid, "state_preds": states}
 
     def forward(self, inputs):
-        require_eval(self)
+        # The frozen backbone runs the fused inference engine (eval-mode BatchNorm).  The
+        # reference leaves the frozen backbone's BatchNorm layers in train mode unless a stage-3
+        # weights file was loaded (lfd.py:141-145); that quirk is refused loudly, not emulated.
+        require_eval(self.backbone)
         image, p2p = inputs[0], inputs[1]
-        outputs, preds_nhwc = self.backbone.forward_full((image, p2p))
+        with torch.no_grad():
+            outputs, preds_nhwc = self.backbone.forward_full((image, p2p))
         keys = self.traversability_head.reward_cfg.input_keys
         prefixes = [k[: -len("_preds")] for k in keys]
         preds = [preds_nhwc[p] for p in prefixes]
@@ -119,5 +123,6 @@ class MaxEntIRL(nn.Module):
         if "method" in self.goal_cfg:
             raise NotImplementedError("goal_kwargs is unused by the shipped configs")
         outputs.update(self.traversability_head.forward_nhwc(preds, S, solve_mdp=True))
-        outputs.update(self.expected_state_visitation_frequency(outputs["policy"], expert))
+        with torch.no_grad():
+            outputs.update(self.expected_state_visitation_frequency(outputs["policy"], expert))
         return outputs

@@ -1,0 +1,610 @@
+// train.cu -- kernels of the stage-3 (MaxEnt / counterfactual IRL) training step.
+//
+// The reference trains the reward FCN (creste/models/blocks/conv.py:88-161) with PyTorch autograd,
+// including the double backward of the SMODICE gradient penalty
+// (creste/utils/loss_utils.py:1208-1217).  Here every primitive of that graph -- and of the graph
+// of its backward -- is a CUDA kernel; the host side (creste_public_b200/autograd.py) wraps them in
+// torch.autograd.Functions whose backward passes are written in terms of the same set, so the set
+// is closed under differentiation:
+//
+//   conv2d (conv_simt.cu / conv_tc.cu)  <->  conv2d with flipped-transposed weights (dgrad)
+//                                       <->  conv2d_wgrad (below)
+//   chan_affine (+ReLU)  <->  relu_bwd, chan_dot          (BatchNorm batch statistics are
+//   chan_dot             <->  chan_affine                  composed from these two)
+//   maxpool2 (layout.cu) <->  maxpool2_bwd <-> maxpool2_gather
+//   bilinear upsample (layout.cu) <-> upsample_adjoint
+//   row_dot <-> row_scale ; grad_penalty fwd/bwd ; adam_step
+//
+// All activations NHWC fp32.  Reductions are two-stage with a fixed order (no atomics).
+#include "common.cuh"
+
+namespace creste {
+
+static inline int grid_cap(long long total, int threads, int cap) {
+  long long b = (total + threads - 1) / threads;
+  if (b < 1) b = 1;
+  return (int)(b > cap ? cap : b);
+}
+
+// ------------------------------------------------------------------------- chan_affine / relu
+// y[pix,c] = act(x[pix,c] * a[c] + b[c]);  a == NULL -> 1, b == NULL -> 0
+template <int V>
+__global__ void __launch_bounds__(256) chan_affine_kernel(const float* __restrict__ x,
+                                                          const float* __restrict__ a,
+                                                          const float* __restrict__ b, int C,
+                                                          long long n, int relu, float* __restrict__ y) {
+  const long long nv = n / V;
+  const int CV = C / V;
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < nv;
+       i += (long long)gridDim.x * blockDim.x) {
+    const int c = (int)(i % CV) * V;
+    if (V == 4) {
+      float4 v = __ldg(reinterpret_cast<const float4*>(x) + i);
+      const float4 aa = a ? __ldg(reinterpret_cast<const float4*>(a + c)) : make_float4(1.f, 1.f, 1.f, 1.f);
+      const float4 bb = b ? __ldg(reinterpret_cast<const float4*>(b + c)) : make_float4(0.f, 0.f, 0.f, 0.f);
+      v.x = fmaf(v.x, aa.x, bb.x); v.y = fmaf(v.y, aa.y, bb.y);
+      v.z = fmaf(v.z, aa.z, bb.z); v.w = fmaf(v.w, aa.w, bb.w);
+      if (relu) { v.x = fmaxf(v.x, 0.f); v.y = fmaxf(v.y, 0.f); v.z = fmaxf(v.z, 0.f); v.w = fmaxf(v.w, 0.f); }
+      reinterpret_cast<float4*>(y)[i] = v;
+    } else {
+      float v = fmaf(__ldg(x + i), a ? __ldg(a + c) : 1.0f, b ? __ldg(b + c) : 0.0f);
+      if (relu) v = fmaxf(v, 0.f);
+      y[i] = v;
+    }
+  }
+}
+
+// out = g * (y > 0)
+__global__ void __launch_bounds__(256) relu_bwd_kernel(const float* __restrict__ g,
+                                                       const float* __restrict__ y, long long n,
+                                                       float* __restrict__ out) {
+  const long long n4 = n / 4;
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n4;
+       i += (long long)gridDim.x * blockDim.x) {
+    float4 gv = __ldg(reinterpret_cast<const float4*>(g) + i);
+    const float4 yv = __ldg(reinterpret_cast<const float4*>(y) + i);
+    gv.x = yv.x > 0.f ? gv.x : 0.f; gv.y = yv.y > 0.f ? gv.y : 0.f;
+    gv.z = yv.z > 0.f ? gv.z : 0.f; gv.w = yv.w > 0.f ? gv.w : 0.f;
+    reinterpret_cast<float4*>(out)[i] = gv;
+  }
+  for (long long i = n4 * 4 + (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n;
+       i += (long long)gridDim.x * blockDim.x)
+    out[i] = __ldg(y + i) > 0.f ? __ldg(g + i) : 0.f;
+}
+
+// ------------------------------------------------------------------------------------ chan_dot
+// part[blk][c] = sum over the block's pixel range of x[pix,c] * (y ? y[pix,c] : 1)
+// thread -> (pixel lane, channel group); per-thread sequential sum, then lanes in order.
+// Accumulation is in DOUBLE, as PyTorch's CPU batch-norm kernels do (acc_type<float> = double):
+// BatchNorm's backward subtracts channel means of the gradient, so the weight gradients upstream
+// are differences of nearly cancelling sums and fp32 partial sums cost 3 digits there (measured).
+template <int V>
+__global__ void __launch_bounds__(256) chan_dot_kernel(const float* __restrict__ x,
+                                                       const float* __restrict__ y, int C,
+                                                       long long npix, double* __restrict__ part) {
+  __shared__ double s_part[256 * V];
+  const int CV = C / V;                       // channel groups (<= 256 by the host check)
+  const int lanes = 256 / CV;
+  const int cg = threadIdx.x % CV, pl = threadIdx.x / CV;
+  const long long per = (npix + gridDim.x - 1) / gridDim.x;
+  const long long p0 = (long long)blockIdx.x * per;
+  const long long p1 = p0 + per < npix ? p0 + per : npix;
+  double acc[V];
+#pragma unroll
+  for (int j = 0; j < V; ++j) acc[j] = 0.0;
+  if (pl < lanes) {
+    for (long long p = p0 + pl; p < p1; p += lanes) {
+      if (V == 4) {
+        const float4 xv = __ldg(reinterpret_cast<const float4*>(x + p * C) + cg);
+        if (y) {
+          const float4 yv = __ldg(reinterpret_cast<const float4*>(y + p * C) + cg);
+          acc[0] += (double)xv.x * (double)yv.x; acc[1] += (double)xv.y * (double)yv.y;
+          acc[2] += (double)xv.z * (double)yv.z; acc[3] += (double)xv.w * (double)yv.w;
+        } else {
+          acc[0] += (double)xv.x; acc[1] += (double)xv.y; acc[2] += (double)xv.z; acc[3] += (double)xv.w;
+        }
+      } else {
+        const double xv = (double)__ldg(x + p * C + cg);
+        acc[0] += y ? xv * (double)__ldg(y + p * C + cg) : xv;
+      }
+    }
+  }
+#pragma unroll
+  for (int j = 0; j < V; ++j) s_part[threadIdx.x * V + j] = acc[j];
+  __syncthreads();
+  if (pl == 0) {
+#pragma unroll
+    for (int j = 0; j < V; ++j) {
+      double tot = s_part[threadIdx.x * V + j];
+      for (int l = 1; l < lanes; ++l) tot += s_part[(l * CV + threadIdx.x) * V + j];
+      part[(size_t)blockIdx.x * C + cg * V + j] = tot;
+    }
+  }
+}
+
+__global__ void __launch_bounds__(256) reduce_rows_f64_kernel(const double* __restrict__ part, int rows,
+                                                              int n, float* __restrict__ out) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  double tot = 0.0;
+  for (int j = 0; j < rows; ++j) tot += part[(size_t)j * n + i];
+  out[i] = (float)tot;
+}
+
+// out[i] = sum_j part[j][i] in order (double accumulator: the second stage is tiny)
+__global__ void __launch_bounds__(256) reduce_rows_kernel(const float* __restrict__ part, int rows,
+                                                          int n, float scale, float* __restrict__ out) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  double tot = 0.0;
+  for (int j = 0; j < rows; ++j) tot += (double)__ldg(part + (size_t)j * n + i);
+  out[i] = (float)tot * scale;
+}
+
+// ------------------------------------------------------------------------------------ maxpool2
+// first maximum in (0,0),(0,1),(1,0),(1,1) order, strict '>' (PyTorch max_pool2d tie rule)
+__device__ __forceinline__ int argmax4(float a, float b, float c, float d) {
+  int k = 0; float m = a;
+  if (b > m || isnan(b)) { m = b; k = 1; }
+  if (c > m || isnan(c)) { m = c; k = 2; }
+  if (d > m || isnan(d)) { m = d; k = 3; }
+  return k;
+}
+
+// mode 0: dx[argmax] = g (others 0)   (x [N,H,W,C], g [N,H/2,W/2,C], out = dx [N,H,W,C])
+// mode 1: out[pooled] = gg[argmax]    (gg [N,H,W,C], out [N,H/2,W/2,C])
+__global__ void __launch_bounds__(256) maxpool2_route_kernel(const float* __restrict__ x,
+                                                             const float* __restrict__ g, int N, int H,
+                                                             int W, int C, int mode,
+                                                             float* __restrict__ out) {
+  const int Ho = H / 2, Wo = W / 2;
+  const long long total = (long long)N * Ho * Wo * C;
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total;
+       i += (long long)gridDim.x * blockDim.x) {
+    const int c = (int)(i % C);
+    const long long pix = i / C;
+    const int ox = (int)(pix % Wo);
+    const int oy = (int)((pix / Wo) % Ho);
+    const int n = (int)(pix / ((long long)Wo * Ho));
+    const size_t base = (((size_t)n * H + 2 * oy) * W + 2 * ox) * C + c;
+    const size_t o[4] = {base, base + C, base + (size_t)W * C, base + (size_t)W * C + C};
+    const int k = argmax4(__ldg(x + o[0]), __ldg(x + o[1]), __ldg(x + o[2]), __ldg(x + o[3]));
+    if (mode == 0) {
+      const float gv = __ldg(g + i);
+#pragma unroll
+      for (int j = 0; j < 4; ++j) out[o[j]] = (j == k) ? gv : 0.f;
+    } else {
+      out[i] = __ldg(g + o[k]);
+    }
+  }
+}
+
+// ---------------------------------------------------------------------------- upsample adjoint
+// dx[n,iy,ix,c] = sum over output pixels (oy,ox) of wy(oy->iy) * wx(ox->ix) * g[n,oy,ox,c],
+// with the weights of creste_upsample_concat (PyTorch bilinear, align_corners=False).
+__device__ __forceinline__ float up_weight(int o, float ratio, int isz, int i) {
+  const float s = fmaxf(__fsub_rn(__fmul_rn(ratio, __fadd_rn((float)o, 0.5f)), 0.5f), 0.0f);
+  const int i0 = (int)s;
+  const int i1 = i0 + (i0 < isz - 1 ? 1 : 0);
+  const float l1 = __fsub_rn(s, (float)i0), l0 = __fsub_rn(1.0f, l1);
+  float w = 0.f;
+  if (i0 == i) w += l0;
+  if (i1 == i) w += l1;
+  return w;
+}
+
+__global__ void __launch_bounds__(256) upsample_adjoint_kernel(const float* __restrict__ g, int N, int Hi,
+                                                               int Wi, int C, int Ho, int Wo, float rh,
+                                                               float rw, float* __restrict__ dx) {
+  const long long total = (long long)N * Hi * Wi * C;
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total;
+       i += (long long)gridDim.x * blockDim.x) {
+    const int c = (int)(i % C);
+    const long long pix = i / C;
+    const int ix = (int)(pix % Wi);
+    const int iy = (int)((pix / Wi) % Hi);
+    const int n = (int)(pix / ((long long)Wi * Hi));
+    int oy0 = (int)floorf(((float)iy - 1.0f + 0.5f) / rh - 0.5f) - 1;
+    int oy1 = (int)ceilf(((float)iy + 1.0f + 0.5f) / rh - 0.5f) + 1;
+    int ox0 = (int)floorf(((float)ix - 1.0f + 0.5f) / rw - 0.5f) - 1;
+    int ox1 = (int)ceilf(((float)ix + 1.0f + 0.5f) / rw - 0.5f) + 1;
+    // the last input row / column also receives every clamped (i1 == isz-1) output
+    oy0 = max(oy0, 0); ox0 = max(ox0, 0);
+    oy1 = (iy == Hi - 1) ? Ho - 1 : min(oy1, Ho - 1);
+    ox1 = (ix == Wi - 1) ? Wo - 1 : min(ox1, Wo - 1);
+    float acc = 0.f;
+    for (int oy = oy0; oy <= oy1; ++oy) {
+      const float wy = up_weight(oy, rh, Hi, iy);
+      if (wy == 0.f) continue;
+      float row = 0.f;
+      for (int ox = ox0; ox <= ox1; ++ox) {
+        const float wx = up_weight(ox, rw, Wi, ix);
+        if (wx != 0.f) row = fmaf(wx, __ldg(g + (((size_t)n * Ho + oy) * Wo + ox) * C + c), row);
+      }
+      acc = fmaf(wy, row, acc);
+    }
+    dx[i] = acc;
+  }
+}
+
+// --------------------------------------------------------------------------------------- wgrad
+// dw[(r*S+s)][c][k] = sum_{n,p,q} x[n, p+r-pad_t, q+s-pad_l, c] * g[n,p,q,k]      (stride 1)
+// grid (chunks, R*S): one CTA = one filter tap x one contiguous range of output pixels; it
+// accumulates the [C x K] tile of that tap (C, K <= 64) from 64-pixel slabs staged in shared
+// memory.  Thread = (pixel lane, 4-channel group of x, 4-channel group of g): 16 FMAs per two
+// LDS.128.  part[chunk][tap][C][K] is then reduced in chunk order by reduce_rows_kernel.
+constexpr int WG_PIX = 64;
+__global__ void __launch_bounds__(256) wgrad_kernel(const float* __restrict__ x,
+                                                    const float* __restrict__ g, int N, int H, int W,
+                                                    int C, int K, int R, int S, int pad_t, int pad_l,
+                                                    int P, int Q, float* __restrict__ part) {
+  __shared__ __align__(16) float s_all[2 * WG_PIX * 64];
+  float (*s_x)[64] = reinterpret_cast<float (*)[64]>(s_all);
+  float (*s_g)[64] = reinterpret_cast<float (*)[64]>(s_all + WG_PIX * 64);
+  float (*s_red)[16] = reinterpret_cast<float (*)[16]>(s_all);   // reused after the main loop
+  const int tap = blockIdx.y;
+  const int r = tap / S, s = tap - r * S;
+  const int tcn = C / 4, tkn = K / 4;
+  const int per = tcn * tkn;
+  const int lanes = 256 / per;
+  const int t = threadIdx.x % per;
+  const int tc = t % tcn, tk = t / tcn;
+  const int pl = threadIdx.x / per;
+  const long long npix = (long long)N * P * Q;
+  const long long chunk = (npix + gridDim.x - 1) / gridDim.x;
+  const long long p0 = (long long)blockIdx.x * chunk;
+  const long long p1 = p0 + chunk < npix ? p0 + chunk : npix;
+  float acc[4][4];
+#pragma unroll
+  for (int i = 0; i < 4; ++i)
+#pragma unroll
+    for (int j = 0; j < 4; ++j) acc[i][j] = 0.f;
+
+  for (long long base = p0; base < p1; base += WG_PIX) {
+    const int cnt = (int)((p1 - base) < WG_PIX ? (p1 - base) : WG_PIX);
+    // stage x (shifted by the tap, zero outside the image) and g
+    for (int i = threadIdx.x; i < WG_PIX * tcn; i += 256) {
+      const int pp = i / tcn, c4 = i - pp * tcn;
+      float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+      if (pp < cnt) {
+        const long long pix = base + pp;
+        const int q = (int)(pix % Q);
+        const int p = (int)((pix / Q) % P);
+        const int n = (int)(pix / ((long long)Q * P));
+        const int iy = p + r - pad_t, ix = q + s - pad_l;
+        if (iy >= 0 && iy < H && ix >= 0 && ix < W)
+          v = __ldg(reinterpret_cast<const float4*>(x + (((size_t)n * H + iy) * W + ix) * C) + c4);
+      }
+      *reinterpret_cast<float4*>(&s_x[pp][c4 * 4]) = v;
+    }
+    for (int i = threadIdx.x; i < WG_PIX * tkn; i += 256) {
+      const int pp = i / tkn, k4 = i - pp * tkn;
+      float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+      if (pp < cnt) v = __ldg(reinterpret_cast<const float4*>(g + (size_t)(base + pp) * K) + k4);
+      *reinterpret_cast<float4*>(&s_g[pp][k4 * 4]) = v;
+    }
+    __syncthreads();
+    if (pl < lanes) {
+      for (int pp = pl; pp < WG_PIX; pp += lanes) {
+        const float4 xv = *reinterpret_cast<const float4*>(&s_x[pp][tc * 4]);
+        const float4 gv = *reinterpret_cast<const float4*>(&s_g[pp][tk * 4]);
+        const float xa[4] = {xv.x, xv.y, xv.z, xv.w};
+        const float ga[4] = {gv.x, gv.y, gv.z, gv.w};
+#pragma unroll
+        for (int i = 0; i < 4; ++i)
+#pragma unroll
+          for (int j = 0; j < 4; ++j) acc[i][j] = fmaf(xa[i], ga[j], acc[i][j]);
+      }
+    }
+    __syncthreads();
+  }
+#pragma unroll
+  for (int i = 0; i < 4; ++i)
+#pragma unroll
+    for (int j = 0; j < 4; ++j) s_red[threadIdx.x][i * 4 + j] = acc[i][j];
+  __syncthreads();
+  if (pl == 0) {
+    float* dst = part + (((size_t)blockIdx.x * gridDim.y + tap) * C) * K;
+#pragma unroll
+    for (int i = 0; i < 4; ++i)
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        float tot = s_red[threadIdx.x][i * 4 + j];
+        for (int l = 1; l < lanes; ++l) tot += s_red[l * per + threadIdx.x][i * 4 + j];
+        dst[(size_t)(tc * 4 + i) * K + tk * 4 + j] = tot;
+      }
+  }
+}
+
+// ---------------------------------------------------------------------------- row_dot / row_scale
+// out[b] = sum_i x[b,i] * y[b,i] * (m ? m[b,i] : 1)      one CTA per row, fixed order
+__global__ void __launch_bounds__(1024) row_dot_kernel(const float* __restrict__ x,
+                                                       const float* __restrict__ y,
+                                                       const uint8_t* __restrict__ m, long long n,
+                                                       float* __restrict__ out) {
+  __shared__ float s_red[32];
+  const size_t off = (size_t)blockIdx.x * n;
+  float acc = 0.f;
+  for (long long i = threadIdx.x; i < n; i += blockDim.x) {
+    float v = __ldg(x + off + i) * (y ? __ldg(y + off + i) : 1.0f);
+    if (m && !m[off + i]) v = 0.f;
+    acc += v;
+  }
+  acc = warp_sum(acc);
+  if ((threadIdx.x & 31) == 0) s_red[threadIdx.x >> 5] = acc;
+  __syncthreads();
+  if (threadIdx.x < 32) {
+    float v = threadIdx.x < (blockDim.x >> 5) ? s_red[threadIdx.x] : 0.f;
+    v = warp_sum(v);
+    if (threadIdx.x == 0) out[blockIdx.x] = v;
+  }
+}
+
+// out[b,i] = x[b,i] * s[b] * (m ? m[b,i] : 1)
+__global__ void __launch_bounds__(256) row_scale_kernel(const float* __restrict__ x,
+                                                        const float* __restrict__ s,
+                                                        const uint8_t* __restrict__ m, long long n,
+                                                        long long total, float* __restrict__ out) {
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total;
+       i += (long long)gridDim.x * blockDim.x) {
+    float v = __ldg(x + i) * __ldg(s + i / n);
+    if (m && !m[i]) v = 0.f;
+    out[i] = v;
+  }
+}
+
+// out[b,i] = x[b,i] * (m ? m[b,i] : 1) / (sum_i x[b,i]*m[b,i] + eps)   (loss_utils.py:1142-1146)
+__global__ void __launch_bounds__(1024) row_normalize_kernel(const float* __restrict__ x,
+                                                             const uint8_t* __restrict__ m, long long n,
+                                                             float eps, float* __restrict__ out) {
+  __shared__ float s_red[32];
+  __shared__ float s_tot;
+  const size_t off = (size_t)blockIdx.x * n;
+  float acc = 0.f;
+  for (long long i = threadIdx.x; i < n; i += blockDim.x)
+    acc += (m && !m[off + i]) ? 0.f : __ldg(x + off + i);
+  acc = warp_sum(acc);
+  if ((threadIdx.x & 31) == 0) s_red[threadIdx.x >> 5] = acc;
+  __syncthreads();
+  if (threadIdx.x < 32) {
+    float v = threadIdx.x < (blockDim.x >> 5) ? s_red[threadIdx.x] : 0.f;
+    v = warp_sum(v);
+    if (threadIdx.x == 0) s_tot = v + eps;
+  }
+  __syncthreads();
+  const float d = s_tot;
+  for (long long i = threadIdx.x; i < n; i += blockDim.x)
+    out[off + i] = (m && !m[off + i]) ? 0.f : __fdiv_rn(__ldg(x + off + i), d);
+}
+
+// ------------------------------------------------------------------------------- grad penalty
+// G NCHW [B,C,HW]: per pixel nrm = ||G[b,:,p]||_2 ; fwd: part[blk] = sum (nrm-1)^2 ;
+// bwd: dG[b,c,p] = gs * 2 (nrm-1)/nrm * G[b,c,p]  (0 where nrm == 0), gs = g_scalar / (B*HW)
+__global__ void __launch_bounds__(256) grad_penalty_kernel(const float* __restrict__ G, int B, int C,
+                                                           long long HW, const float* __restrict__ gs,
+                                                           float inv_count, float* __restrict__ part,
+                                                           float* __restrict__ dG) {
+  __shared__ float s_red[8];
+  const long long total = (long long)B * HW;
+  float acc = 0.f;
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total;
+       i += (long long)gridDim.x * blockDim.x) {
+    const long long b = i / HW, p = i - b * HW;
+    const float* src = G + (size_t)b * C * HW + p;
+    float ss = 0.f;
+    for (int c = 0; c < C; ++c) { const float v = __ldg(src + (size_t)c * HW); ss = fmaf(v, v, ss); }
+    const float nrm = sqrtf(ss);
+    acc += (nrm - 1.0f) * (nrm - 1.0f);
+    if (dG) {
+      const float k = nrm > 0.f ? __ldg(gs) * inv_count * 2.0f * (nrm - 1.0f) / nrm : 0.f;
+      float* dst = dG + (size_t)b * C * HW + p;
+      for (int c = 0; c < C; ++c) dst[(size_t)c * HW] = k * __ldg(src + (size_t)c * HW);
+    }
+  }
+  if (part) {
+    acc = warp_sum(acc);
+    if ((threadIdx.x & 31) == 0) s_red[threadIdx.x >> 5] = acc;
+    __syncthreads();
+    if (threadIdx.x == 0) {
+      float t = 0.f;
+      for (int w = 0; w < 8; ++w) t += s_red[w];
+      part[blockIdx.x] = t;
+    }
+  }
+}
+
+// --------------------------------------------------------------------------------------- Adam
+// torch.optim.Adam (no amsgrad, no weight decay): m = b1 m + (1-b1) g ; v = b2 v + (1-b2) g^2 ;
+// p -= step_size * m / (sqrt(v)/sqrt(bc2) + eps), step_size = lr / bc1
+__global__ void __launch_bounds__(256) adam_kernel(float* __restrict__ p, const float* __restrict__ g,
+                                                   float* __restrict__ m, float* __restrict__ v,
+                                                   long long n, float b1, float b2, float eps,
+                                                   float step_size, float inv_sqrt_bc2, float gscale) {
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n;
+       i += (long long)gridDim.x * blockDim.x) {
+    const float gi = g[i] * gscale;
+    const float mi = m[i] + (gi - m[i]) * (1.0f - b1);            // lerp form used by torch
+    const float vi = b2 * v[i] + (1.0f - b2) * gi * gi;
+    m[i] = mi;
+    v[i] = vi;
+    const float denom = sqrtf(vi) * inv_sqrt_bc2 + eps;
+    p[i] = p[i] - step_size * (mi / denom);
+  }
+}
+
+}  // namespace creste
+
+using namespace creste;
+
+extern "C" int creste_chan_affine(const float* x, const float* a, const float* b, long long npix, int C,
+                                  int relu, float* y, void* stream) {
+  CRESTE_CHECK_ARG(x && y && npix > 0 && C > 0, "creste_chan_affine: bad args");
+  const long long n = npix * C;
+  cudaStream_t st = (cudaStream_t)stream;
+  if (C % 4 == 0)
+    chan_affine_kernel<4><<<grid_cap(n / 4, 256, 148 * 16), 256, 0, st>>>(x, a, b, C, n, relu, y);
+  else
+    chan_affine_kernel<1><<<grid_cap(n, 256, 148 * 16), 256, 0, st>>>(x, a, b, C, n, relu, y);
+  return launch_check("chan_affine_kernel");
+}
+
+extern "C" int creste_relu_bwd(const float* g, const float* y, long long n, float* out, void* stream) {
+  CRESTE_CHECK_ARG(g && y && out && n > 0, "creste_relu_bwd: bad args");
+  relu_bwd_kernel<<<grid_cap(n / 4 + 1, 256, 148 * 16), 256, 0, (cudaStream_t)stream>>>(g, y, n, out);
+  return launch_check("relu_bwd_kernel");
+}
+
+static int chan_dot_blocks(long long npix) {
+  long long b = npix / 256;
+  if (b < 1) b = 1;
+  return (int)(b > 592 ? 592 : b);
+}
+
+extern "C" size_t creste_chan_dot_workspace_bytes(long long npix, int C) {
+  return (size_t)chan_dot_blocks(npix) * C * sizeof(double);
+}
+
+extern "C" int creste_chan_dot(const float* x, const float* y, long long npix, int C, float* out, void* ws,
+                               size_t ws_bytes, void* stream) {
+  CRESTE_CHECK_ARG(x && out && ws && npix > 0 && C > 0 && C <= 1024, "creste_chan_dot: bad args");
+  CRESTE_CHECK_ARG(ws_bytes >= creste_chan_dot_workspace_bytes(npix, C), "creste_chan_dot: workspace");
+  cudaStream_t st = (cudaStream_t)stream;
+  const int blocks = chan_dot_blocks(npix);
+  if (C % 4 == 0 && C / 4 <= 256)
+    chan_dot_kernel<4><<<blocks, 256, 0, st>>>(x, y, C, npix, (double*)ws);
+  else {
+    CRESTE_CHECK_ARG(C <= 256, "creste_chan_dot: C %% 4 != 0 needs C <= 256");
+    chan_dot_kernel<1><<<blocks, 256, 0, st>>>(x, y, C, npix, (double*)ws);
+  }
+  int rc = launch_check("chan_dot_kernel");
+  if (rc) return rc;
+  reduce_rows_f64_kernel<<<ceil_div(C, 256), 256, 0, st>>>((const double*)ws, blocks, C, out);
+  return launch_check("reduce_rows_f64_kernel");
+}
+
+extern "C" int creste_maxpool2_bwd(const float* x, const float* g, int N, int H, int W, int C, float* dx,
+                                   void* stream) {
+  CRESTE_CHECK_ARG(x && g && dx && N > 0 && H >= 2 && W >= 2 && C > 0, "creste_maxpool2_bwd: bad args");
+  cudaStream_t st = (cudaStream_t)stream;
+  if ((H & 1) || (W & 1)) CRESTE_CUDA(cudaMemsetAsync(dx, 0, (size_t)N * H * W * C * sizeof(float), st));
+  const long long total = (long long)N * (H / 2) * (W / 2) * C;
+  maxpool2_route_kernel<<<grid_cap(total, 256, 148 * 16), 256, 0, st>>>(x, g, N, H, W, C, 0, dx);
+  return launch_check("maxpool2_route_kernel");
+}
+
+extern "C" int creste_maxpool2_gather(const float* x, const float* gg, int N, int H, int W, int C,
+                                      float* out, void* stream) {
+  CRESTE_CHECK_ARG(x && gg && out && N > 0 && H >= 2 && W >= 2 && C > 0, "creste_maxpool2_gather: bad args");
+  const long long total = (long long)N * (H / 2) * (W / 2) * C;
+  maxpool2_route_kernel<<<grid_cap(total, 256, 148 * 16), 256, 0, (cudaStream_t)stream>>>(x, gg, N, H, W, C,
+                                                                                        1, out);
+  return launch_check("maxpool2_route_kernel");
+}
+
+extern "C" int creste_upsample_adjoint(const float* g, int N, int Hi, int Wi, int C, int Ho, int Wo, float rh,
+                                       float rw, float* dx, void* stream) {
+  CRESTE_CHECK_ARG(g && dx && N > 0 && Hi > 0 && Wi > 0 && C > 0 && Ho > 0 && Wo > 0 && rh > 0 && rw > 0,
+                   "creste_upsample_adjoint: bad args");
+  const long long total = (long long)N * Hi * Wi * C;
+  upsample_adjoint_kernel<<<grid_cap(total, 256, 148 * 16), 256, 0, (cudaStream_t)stream>>>(g, N, Hi, Wi, C, Ho,
+                                                                                          Wo, rh, rw, dx);
+  return launch_check("upsample_adjoint_kernel");
+}
+
+static int wgrad_chunks(const creste_conv_desc* d) {
+  const long long npix = (long long)d->N * d->P * d->Q;
+  long long chunks = 592 / (d->R * d->S);
+  if (chunks < 1) chunks = 1;
+  const long long maxc = (npix + 255) / 256;       // >= 256 pixels per chunk
+  if (chunks > maxc) chunks = maxc;
+  return (int)(chunks < 1 ? 1 : chunks);
+}
+
+extern "C" size_t creste_conv2d_wgrad_workspace_bytes(const creste_conv_desc* d) {
+  if (!d) return 0;
+  return (size_t)wgrad_chunks(d) * d->R * d->S * d->C * d->K * sizeof(float);
+}
+
+/* dw_packed [R*S*C, K] (the creste_conv2d fp32 weight layout with ldw = K) */
+extern "C" int creste_conv2d_wgrad(const creste_conv_desc* d, const float* x, const float* g, float* dw_packed,
+                                   void* ws, size_t ws_bytes, void* stream) {
+  CRESTE_CHECK_ARG(d && x && g && dw_packed && ws, "creste_conv2d_wgrad: null pointer");
+  CRESTE_CHECK_ARG(d->stride == 1, "creste_conv2d_wgrad: stride 1 only");
+  CRESTE_CHECK_ARG(d->C % 4 == 0 && d->K % 4 == 0 && d->C <= 64 && d->K <= 64 && d->C > 0 && d->K > 0,
+                   "creste_conv2d_wgrad: C, K must be multiples of 4 and <= 64 (got %d, %d)", d->C, d->K);
+  CRESTE_CHECK_ARG(ws_bytes >= creste_conv2d_wgrad_workspace_bytes(d), "creste_conv2d_wgrad: workspace");
+  cudaStream_t st = (cudaStream_t)stream;
+  const int chunks = wgrad_chunks(d);
+  dim3 grid(chunks, d->R * d->S);
+  wgrad_kernel<<<grid, 256, 0, st>>>(x, g, d->N, d->H, d->W, d->C, d->K, d->R, d->S, d->pad_t, d->pad_l,
+                                     d->P, d->Q, (float*)ws);
+  int rc = launch_check("wgrad_kernel");
+  if (rc) return rc;
+  const int n = d->R * d->S * d->C * d->K;
+  reduce_rows_kernel<<<ceil_div(n, 256), 256, 0, st>>>((const float*)ws, chunks, n, 1.0f, dw_packed);
+  return launch_check("reduce_rows_kernel");
+}
+
+extern "C" int creste_row_dot(const float* x, const float* y, const uint8_t* mask, int B, long long n,
+                              float* out, void* stream) {
+  CRESTE_CHECK_ARG(x && out && B > 0 && n > 0, "creste_row_dot: bad args");
+  row_dot_kernel<<<B, 1024, 0, (cudaStream_t)stream>>>(x, y, mask, n, out);
+  return launch_check("row_dot_kernel");
+}
+
+extern "C" int creste_row_scale(const float* x, const float* s, const uint8_t* mask, int B, long long n,
+                                float* out, void* stream) {
+  CRESTE_CHECK_ARG(x && s && out && B > 0 && n > 0, "creste_row_scale: bad args");
+  const long long total = (long long)B * n;
+  row_scale_kernel<<<grid_cap(total, 256, 148 * 8), 256, 0, (cudaStream_t)stream>>>(x, s, mask, n, total, out);
+  return launch_check("row_scale_kernel");
+}
+
+extern "C" int creste_row_normalize(const float* x, const uint8_t* mask, int B, long long n, float eps,
+                                    float* out, void* stream) {
+  CRESTE_CHECK_ARG(x && out && B > 0 && n > 0, "creste_row_normalize: bad args");
+  row_normalize_kernel<<<B, 1024, 0, (cudaStream_t)stream>>>(x, mask, n, eps, out);
+  return launch_check("row_normalize_kernel");
+}
+
+static int gp_blocks(long long total) { return grid_cap(total, 256, 592); }
+
+extern "C" size_t creste_grad_penalty_workspace_bytes(int B, long long HW) {
+  return (size_t)gp_blocks((long long)B * HW) * sizeof(float);
+}
+
+/* penalty_out (device scalar) = mean over (b,pixel) of (||G[b,:,pixel]||_2 - 1)^2, G NCHW */
+extern "C" int creste_grad_penalty(const float* G, int B, int C, long long HW, float* penalty_out, void* ws,
+                                   size_t ws_bytes, void* stream) {
+  CRESTE_CHECK_ARG(G && penalty_out && ws && B > 0 && C > 0 && HW > 0, "creste_grad_penalty: bad args");
+  CRESTE_CHECK_ARG(ws_bytes >= creste_grad_penalty_workspace_bytes(B, HW), "creste_grad_penalty: workspace");
+  cudaStream_t st = (cudaStream_t)stream;
+  const int blocks = gp_blocks((long long)B * HW);
+  grad_penalty_kernel<<<blocks, 256, 0, st>>>(G, B, C, HW, nullptr, 0.f, (float*)ws, nullptr);
+  int rc = launch_check("grad_penalty_kernel");
+  if (rc) return rc;
+  // sum of the block partials in order, then / count
+  reduce_rows_kernel<<<1, 256, 0, st>>>((const float*)ws, blocks, 1, 1.0f / (float)((long long)B * HW),
+                                        penalty_out);
+  return launch_check("reduce_rows_kernel");
+}
+
+/* dG = g_scalar * d penalty / dG   (g_scalar: device scalar) */
+extern "C" int creste_grad_penalty_bwd(const float* G, const float* g_scalar, int B, int C, long long HW,
+                                       float* dG, void* stream) {
+  CRESTE_CHECK_ARG(G && g_scalar && dG && B > 0 && C > 0 && HW > 0, "creste_grad_penalty_bwd: bad args");
+  const float inv = 1.0f / (float)((long long)B * HW);
+  grad_penalty_kernel<<<gp_blocks((long long)B * HW), 256, 0, (cudaStream_t)stream>>>(G, B, C, HW, g_scalar,
+                                                                                    inv, nullptr, dG);
+  return launch_check("grad_penalty_kernel");
+}
+
+extern "C" int creste_adam_step(float* p, const float* g, float* m, float* v, long long n, float lr, float b1,
+                                float b2, float eps, int step, float grad_scale, void* stream) {
+  CRESTE_CHECK_ARG(p && g && m && v && n > 0 && step >= 1, "creste_adam_step: bad args");
+  const double bc1 = 1.0 - pow((double)b1, (double)step);
+  const double bc2 = 1.0 - pow((double)b2, (double)step);
+  adam_kernel<<<grid_cap(n, 256, 148 * 8), 256, 0, (cudaStream_t)stream>>>(
+      p, g, m, v, n, b1, b2, eps, (float)((double)lr / bc1), (float)(1.0 / sqrt(bc2)), grad_scale);
+  return launch_check("adam_kernel");
+}

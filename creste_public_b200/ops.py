@@ -302,3 +302,154 @@ def expert_visitation(traj_rc, map_ds, max_steps, H, W):
                                          C.c_double(float(map_ds)), int(max_steps), H, W,
                                          ptr(counts), stream()), "creste_expert_visitation")
     return counts
+
+
+# ------------------------------------------------------------------ stage-3 training primitives
+def chan_affine(x, a=None, b=None, relu=False):
+    """y[..., c] = act(x[..., c] * a[c] + b[c]) over a channels-last tensor (a/b None = 1/0)."""
+    x = x.contiguous()
+    Cc = x.shape[-1]
+    y = torch.empty_like(x)
+    check(lib().creste_chan_affine(ptr(x), ptr(a), ptr(b), C.c_longlong(x.numel() // Cc), Cc,
+                                   int(bool(relu)), ptr(y), stream()), "creste_chan_affine")
+    return y
+
+
+def relu_bwd(g, y):
+    g, y = g.contiguous(), y.contiguous()
+    out = torch.empty_like(g)
+    check(lib().creste_relu_bwd(ptr(g), ptr(y), C.c_longlong(g.numel()), ptr(out), stream()),
+          "creste_relu_bwd")
+    return out
+
+
+def chan_dot(x, y=None):
+    """out[c] = sum over all leading dims of x[..., c] * y[..., c]  (y None: plain channel sum)."""
+    x = x.contiguous()
+    y = None if y is None else y.contiguous()
+    Cc = x.shape[-1]
+    npix = x.numel() // Cc
+    out = torch.empty(Cc, device=x.device)
+    lib().creste_chan_dot_workspace_bytes.restype = C.c_size_t
+    n = lib().creste_chan_dot_workspace_bytes(C.c_longlong(npix), Cc)
+    ws = _ws(n, x.device)
+    check(lib().creste_chan_dot(ptr(x), ptr(y), C.c_longlong(npix), Cc, ptr(out), ptr(ws),
+                                C.c_size_t(n), stream()), "creste_chan_dot")
+    return out
+
+
+def maxpool2(x_nhwc):
+    return maxpool2_concat([x_nhwc.contiguous()])
+
+
+def maxpool2_bwd(x_nhwc, g):
+    N, H, W, Cc = x_nhwc.shape
+    dx = torch.empty_like(x_nhwc)
+    check(lib().creste_maxpool2_bwd(ptr(x_nhwc.contiguous()), ptr(g.contiguous()), N, H, W, Cc,
+                                    ptr(dx), stream()), "creste_maxpool2_bwd")
+    return dx
+
+
+def maxpool2_gather(x_nhwc, gg):
+    N, H, W, Cc = x_nhwc.shape
+    out = torch.empty(N, H // 2, W // 2, Cc, device=x_nhwc.device)
+    check(lib().creste_maxpool2_gather(ptr(x_nhwc.contiguous()), ptr(gg.contiguous()), N, H, W, Cc,
+                                       ptr(out), stream()), "creste_maxpool2_gather")
+    return out
+
+
+def upsample2(x_nhwc):
+    """Bilinear x2 (align_corners=False), NHWC, C % 4 == 0."""
+    N, H, W, _ = x_nhwc.shape
+    return upsample_concat(None, x_nhwc.contiguous(), (2 * H, 2 * W), 2)
+
+
+def upsample2_adjoint(g_nhwc):
+    N, Ho, Wo, Cc = g_nhwc.shape
+    Hi, Wi = Ho // 2, Wo // 2
+    dx = torch.empty(N, Hi, Wi, Cc, device=g_nhwc.device)
+    check(lib().creste_upsample_adjoint(ptr(g_nhwc.contiguous()), N, Hi, Wi, Cc, Ho, Wo,
+                                        C.c_float(0.5), C.c_float(0.5), ptr(dx), stream()),
+          "creste_upsample_adjoint")
+    return dx
+
+
+def conv2d_wgrad(x_nhwc, g_nhwc, R, S, pad):
+    """dw [K,C,R,S] (torch layout) of a stride-1 conv: x [N,H,W,C], g [N,P,Q,K]."""
+    x_nhwc, g_nhwc = x_nhwc.contiguous(), g_nhwc.contiguous()
+    N, H, W, Cc = x_nhwc.shape
+    _, P, Q, K = g_nhwc.shape
+    pt, pb, pl, pr = pad
+    assert P == H + pt + pb - R + 1 and Q == W + pl + pr - S + 1
+    d = ConvDesc(N, H, W, Cc, K, R, S, 1, pt, pl, P, Q, 0, 0, 0)
+    lib().creste_conv2d_wgrad_workspace_bytes.restype = C.c_size_t
+    n = lib().creste_conv2d_wgrad_workspace_bytes(C.byref(d))
+    ws = _ws(n, x_nhwc.device)
+    dw = torch.empty(R * S * Cc, K, device=x_nhwc.device)
+    check(lib().creste_conv2d_wgrad(C.byref(d), ptr(x_nhwc), ptr(g_nhwc), ptr(dw), ptr(ws),
+                                    C.c_size_t(n), stream()), "creste_conv2d_wgrad")
+    return dw.view(R, S, Cc, K).permute(3, 2, 0, 1).contiguous()
+
+
+def row_dot(x, y=None, mask=None):
+    """out[b] = sum_i x[b,i] * y[b,i] * mask[b,i] over all trailing dims."""
+    x = x.contiguous()
+    B = x.shape[0]
+    n = x.numel() // B
+    out = torch.empty(B, device=x.device)
+    check(lib().creste_row_dot(ptr(x), ptr(None if y is None else y.contiguous()),
+                               ptr(None if mask is None else mask.contiguous()), B,
+                               C.c_longlong(n), ptr(out), stream()), "creste_row_dot")
+    return out
+
+
+def row_scale(x, s, mask=None):
+    x = x.contiguous()
+    B = x.shape[0]
+    out = torch.empty_like(x)
+    check(lib().creste_row_scale(ptr(x), ptr(s.contiguous()),
+                                 ptr(None if mask is None else mask.contiguous()), B,
+                                 C.c_longlong(x.numel() // B), ptr(out), stream()), "creste_row_scale")
+    return out
+
+
+def row_normalize(x, mask=None, eps=1e-5):
+    x = x.contiguous()
+    B = x.shape[0]
+    out = torch.empty_like(x)
+    check(lib().creste_row_normalize(ptr(x), ptr(None if mask is None else mask.contiguous()), B,
+                                     C.c_longlong(x.numel() // B), C.c_float(eps), ptr(out),
+                                     stream()), "creste_row_normalize")
+    return out
+
+
+def grad_penalty(G_nchw):
+    """mean over (b, pixel) of (||G[b,:,pixel]||_2 - 1)^2 -> 0-dim tensor."""
+    G = G_nchw.contiguous()
+    B, Cc = G.shape[0], G.shape[1]
+    HW = G.numel() // (B * Cc)
+    lib().creste_grad_penalty_workspace_bytes.restype = C.c_size_t
+    n = lib().creste_grad_penalty_workspace_bytes(B, C.c_longlong(HW))
+    ws = _ws(n, G.device)
+    out = torch.empty((), device=G.device)
+    check(lib().creste_grad_penalty(ptr(G), B, Cc, C.c_longlong(HW), ptr(out), ptr(ws),
+                                    C.c_size_t(n), stream()), "creste_grad_penalty")
+    return out
+
+
+def grad_penalty_bwd(G_nchw, g_scalar):
+    G = G_nchw.contiguous()
+    B, Cc = G.shape[0], G.shape[1]
+    HW = G.numel() // (B * Cc)
+    dG = torch.empty_like(G)
+    check(lib().creste_grad_penalty_bwd(ptr(G), ptr(g_scalar.contiguous().float()), B, Cc,
+                                        C.c_longlong(HW), ptr(dG), stream()),
+          "creste_grad_penalty_bwd")
+    return dG
+
+
+def adam_step(p, g, m, v, lr, beta1, beta2, eps, step, grad_scale=1.0):
+    """In-place torch.optim.Adam update of the flat fp32 buffers p, m, v from the flat gradient g."""
+    check(lib().creste_adam_step(ptr(p), ptr(g), ptr(m), ptr(v), C.c_longlong(p.numel()),
+                                 C.c_float(lr), C.c_float(beta1), C.c_float(beta2), C.c_float(eps),
+                                 int(step), C.c_float(grad_scale), stream()), "creste_adam_step")

@@ -195,6 +195,61 @@ int creste_nhwc_to_nchw(const float* in, int N, int H, int W, int C, float* out,
 int creste_expert_visitation(const void* traj, int is_f64, int B, int T, double map_ds,
                              int max_steps, int H, int W, float* counts, void* stream);
 
+/* ---------------------------------------------------------------------------------------------
+ * Stage-3 (MaxEnt / counterfactual IRL) training step.  The reference trains the reward FCN
+ * (creste/models/blocks/conv.py:88-161, train-mode BatchNorm) through PyTorch autograd, with a
+ * double backward for the SMODICE gradient penalty (creste/utils/loss_utils.py:1208-1217), inside
+ * MaxEntIRLModel.training_step (creste/train_traversability.py:62-103).  The entries below are the
+ * primitives of that graph and of the graph of its backward (a set closed under differentiation;
+ * creste_public_b200/autograd.py composes them).  Channels-last fp32 throughout. */
+
+/* y[pix,c] = act(x[pix,c]*a[c] + b[c]); a/b NULL = 1/0; relu: 0/1.  Replaces the elementwise part
+ * of F.batch_norm (train) and nn.ReLU in conv.py:63-85,117-126. */
+int creste_chan_affine(const float* x, const float* a, const float* b, long long npix, int C,
+                       int relu, float* y, void* stream);
+/* out = g * (y > 0): ReLU backward (autograd's threshold_backward). */
+int creste_relu_bwd(const float* g, const float* y, long long n, float* out, void* stream);
+/* out[c] = sum_pix x[pix,c] * (y ? y[pix,c] : 1): BatchNorm batch statistics and the channel
+ * reductions of its backward; two-stage fixed-order reduction.  ws >= the _workspace_bytes. */
+size_t creste_chan_dot_workspace_bytes(long long npix, int C);
+int creste_chan_dot(const float* x, const float* y, long long npix, int C, float* out, void* ws,
+                    size_t ws_bytes, void* stream);
+/* 2x2/2 max-pool backward (dx[argmax] = g; first maximum wins, the PyTorch tie rule) and its
+ * adjoint (out[pooled] = gg[argmax]) -- conv.py:117 under autograd.  x [N,H,W,C]. */
+int creste_maxpool2_bwd(const float* x, const float* g, int N, int H, int W, int C, float* dx,
+                        void* stream);
+int creste_maxpool2_gather(const float* x, const float* gg, int N, int H, int W, int C, float* out,
+                           void* stream);
+/* adjoint of the bilinear upsample of creste_upsample_concat (conv.py:128 under autograd):
+ * g [N,Ho,Wo,C] -> dx [N,Hi,Wi,C]; rh, rw = source-per-destination ratios. */
+int creste_upsample_adjoint(const float* g, int N, int Hi, int Wi, int C, int Ho, int Wo, float rh,
+                            float rw, float* dx, void* stream);
+/* weight gradient of a stride-1 conv (autograd's convolution_backward, weight part):
+ * x [N,H,W,C], g [N,P,Q,K] -> dw_packed [R*S*C, K]; C, K multiples of 4, <= 64. */
+size_t creste_conv2d_wgrad_workspace_bytes(const creste_conv_desc* d);
+int creste_conv2d_wgrad(const creste_conv_desc* d, const float* x, const float* g, float* dw_packed,
+                        void* ws, size_t ws_bytes, void* stream);
+/* per-sample reductions / scalings of the loss (loss_utils.py:1142-1146, 1195-1203):
+ * row_dot: out[b] = sum_i x[b,i]*y[b,i]*mask[b,i] (y, mask may be NULL);
+ * row_scale: out[b,i] = x[b,i]*s[b]*mask[b,i]; row_normalize: x*mask / (sum(x*mask) + eps). */
+int creste_row_dot(const float* x, const float* y, const uint8_t* mask, int B, long long n,
+                   float* out, void* stream);
+int creste_row_scale(const float* x, const float* s, const uint8_t* mask, int B, long long n,
+                     float* out, void* stream);
+int creste_row_normalize(const float* x, const uint8_t* mask, int B, long long n, float eps,
+                         float* out, void* stream);
+/* SMODICE gradient penalty (loss_utils.py:1216-1217): G NCHW [B,C,HW];
+ * penalty = mean_{b,pixel} (||G[b,:,pixel]||_2 - 1)^2 (device scalar); _bwd: dG = g_scalar * dP/dG. */
+size_t creste_grad_penalty_workspace_bytes(int B, long long HW);
+int creste_grad_penalty(const float* G, int B, int C, long long HW, float* penalty_out, void* ws,
+                        size_t ws_bytes, void* stream);
+int creste_grad_penalty_bwd(const float* G, const float* g_scalar, int B, int C, long long HW,
+                            float* dG, void* stream);
+/* torch.optim.Adam step (train_traversability.py optimizer; no amsgrad / weight decay) on flat
+ * buffers; g is multiplied by grad_scale first (1/world after the NCCL sum all-reduce). */
+int creste_adam_step(float* p, const float* g, float* m, float* v, long long n, float lr, float b1,
+                     float b2, float eps, int step, float grad_scale, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -23,6 +23,18 @@ from oracle import synth  # noqa: E402
 OUT = os.path.join(ROOT, "tests", "golden")
 
 
+def irl_step_golden():
+    from oracle import irl_oracle
+    case = irl_oracle.make_case(seed=3, B=2, H=8, W=16)
+    ref = irl_oracle.reference_step(case, steps=2)
+    d = {"loss": ref["loss"][0], "loss2": ref["loss"][1], "reward_penalty": ref["reward_penalty"][0],
+         "mean_exp": ref["mean_expected_svf_rewards"][0], "mean_svf": ref["mean_svf_rewards"][0],
+         "sum_cf": ref["sum_cf_rewards"][0], "sum_opt": ref["sum_opt_rewards"][0], "r": ref["r"]}
+    d.update({"grad/" + k: v for k, v in ref["grads"].items()})
+    d.update({"param2/" + k: v for k, v in ref["params"].items()})
+    np.savez_compressed(os.path.join(OUT, "irl_step.npz"), **d)
+
+
 def main():
     os.makedirs(OUT, exist_ok=True)
     mods = rh.ref_modules()
@@ -122,6 +134,10 @@ def main():
                         loss=np.float32(ld["maxentirl_loss"].item()),
                         mean_exp=np.float32(md["mean_expected_svf_rewards"].item()),
                         mean_svf=np.float32(md["mean_svf_rewards"].item()))
+
+    # ---- stage-3 training step: reward FCN (train-mode BN) + MaxEntIRLLoss incl. the double
+    # backward of the gradient penalty + Adam (train_traversability.py:62-103)
+    irl_step_golden()
 
     # ---- full forward, tiny image, both depth profiles (lfd.py:314-330)
     for prof in ("peaky", "soft"):

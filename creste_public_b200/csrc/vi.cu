@@ -525,6 +525,386 @@ static int vi_try_cluster(ViClusterParams& p, int c, int threads, size_t smem, c
   return 1;
 }
 
+// ---------------------------------------------------------------------------------------------
+// Cluster-resident kernel, second generation ("strip" kernel): same data placement as above
+// (one cluster per sample, r / v in registers, X tiles in shared memory, DSMEM halo exchange, no
+// grid barrier) with the three costs measured on the first generation removed:
+//   * register-blocked cells: a thread owns 4 adjacent columns x RT adjacent rows and reads each X
+//     row with one LDS.128 + 2 scalar loads (1.5-2 smem loads per cell instead of 9);
+//   * halo rows travel as st.async.v4 stores that complete transaction bytes on the NEIGHBOUR's
+//     mbarrier (one 16-byte store per 4 cells, no per-cell remote arrive);
+//   * the batch-global stop decision trails the computation by exactly LAGCHK sweeps (the ~2 us L2
+//     round trip of the max-reduction is off the critical path) and bit-exactness of K and v is
+//     kept by CHECKPOINT + REPLAY instead of rotating LAG+2 generations of v through registers:
+//     v is snapshotted every CKPT sweeps (two snapshots live); once sweep K is known to be the
+//     reference's last, every CTA restores the snapshot at floor(K/CKPT)*CKPT and replays
+//     K - that many sweeps (same arithmetic, same order => same bits).  All CTAs observe the
+//     decision at the same sweep index, so the whole grid stays in lock step without a barrier.
+// Cluster size is any 1..16 (largest that is co-resident for the whole batch).
+constexpr int VI2_RING = 32;     // per-sweep block-max slots in flight (one comm-warp lane each)
+// The decision for sweep s is consumed at sweep s + lag, and v is snapshotted every `lag` sweeps
+// (ViStripParams::lag, <= RING - 1): 8 for large strips (a sweep takes > 1 us, the decision ~4 us),
+// 24 for small ones, where the sweep rate would otherwise be decision-latency / lag.
+constexpr unsigned VI2_SPIN_LIMIT = 1u << 27;   // bail out instead of hanging the GPU
+
+struct ViStripParams {
+  const float* r; float* v_out; float* q_out; float* pi_out;
+  unsigned long long* gword;   // [max_sweeps + 2] : low 32 = max|dv| bits, high 32 = arrival count
+  int* sweeps_out;
+  int B, H, W, R, c, max_sweeps, G, nt, lag;   // nt = compute threads (multiple of 32)
+  float gamma, thr;
+};
+
+__device__ __forceinline__ uint32_t vi_mapa(uint32_t addr, uint32_t rank) {
+  uint32_t ra;
+  asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(ra) : "r"(addr), "r"(rank));
+  return ra;
+}
+__device__ __forceinline__ void vi_st_async_v4(uint32_t raddr, float4 v, uint32_t rbar) {
+  asm volatile("st.async.weak.shared::cluster.mbarrier::complete_tx::bytes.v4.b32 [%0], {%1, %2, %3, %4}, [%5];"
+               ::"r"(raddr), "r"(__float_as_uint(v.x)), "r"(__float_as_uint(v.y)), "r"(__float_as_uint(v.z)),
+                 "r"(__float_as_uint(v.w)), "r"(rbar)
+               : "memory");
+}
+// CTA-scope semantics on purpose: the tile is read only by this CTA's threads, and the neighbours'
+// halo rows arrive through the async proxy (st.async ... complete_tx), whose data is visible to
+// whoever observes the phase completion -- the TMA-multicast pattern.  Cluster-scope release /
+// acquire compiled to MEMBAR.ALL.GPU + CCTL.IVALL per thread per sweep (measured: 2x slower).
+__device__ __forceinline__ void vi_mbar_arrive_expect(uint64_t* bar, uint32_t bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(vi_smem_u32(bar)), "r"(bytes)
+               : "memory");
+}
+__device__ __forceinline__ void vi_mbar_arrive_cta(uint64_t* bar) {
+  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(vi_smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ bool vi_mbar_test(uint64_t* bar, uint32_t parity) {
+  uint32_t ok;
+  asm volatile(
+      "{\n\t"
+      ".reg .pred P1;\n\t"
+      "mbarrier.try_wait.parity.shared::cta.b64 P1, [%1], %2;\n\t"
+      "selp.b32 %0, 1, 0, P1;\n\t"
+      "}"
+      : "=r"(ok)
+      : "r"(vi_smem_u32(bar)), "r"(parity)
+      : "memory");
+  return ok != 0;
+}
+
+template <int RT>
+__global__ void __launch_bounds__(RT <= 2 ? 640 : 544, 1) vi_strip_kernel(ViStripParams p) {
+  // two X tiles [(R+2)][W+8] (interior col x at 4+x), then two v snapshots [R][W]
+  extern __shared__ __align__(16) float sm[];
+  __shared__ uint64_t s_mbar[2];
+  __shared__ uint64_t s_postbar[VI2_RING];   // per-sweep "all warps posted their max|dv|" barriers
+  __shared__ unsigned s_wmax[VI2_RING][32];  // per-sweep, per-warp max|dv| (float bits)
+  __shared__ volatile int s_dec[VI2_RING];   // (sweep << 1) | stop, published by the comm warp
+  __shared__ volatile int s_stopK;           // smallest sweep decided as the last one
+  __shared__ volatile int s_fail;
+  cg::cluster_group cluster = cg::this_cluster();
+  const int cr = (int)cluster.block_rank();
+  const int b = blockIdx.x / p.c;
+  const int W = p.W, H = p.H;
+  const int P = W + 8;
+  const int tile = (p.R + 2) * P;
+  const int row0 = cr * p.R;
+  const int n = min(p.R, H - row0);
+  const int tid = threadIdx.x;
+  const int nt = p.nt;
+  const int nwarps = nt >> 5;
+  const bool is_comm = tid >= nt;
+  const bool has_up = cr > 0;
+  const bool has_dn = (cr < p.c - 1) && (row0 + n < H);
+  const float gamma = p.gamma;
+
+  // halos / sample borders stay 0; snapshot slot 0 starts as v_0 = 0
+  for (int i = tid; i < 2 * tile + 2 * p.R * W; i += blockDim.x) sm[i] = 0.0f;
+  if (tid < VI2_RING) s_dec[tid] = -2;
+  if (tid == 0) {
+    s_stopK = 0x7fffffff;
+    s_fail = 0;
+    for (int i = 0; i < VI2_RING; ++i)
+      asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(vi_smem_u32(&s_postbar[i])), "r"(nwarps) : "memory");
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(vi_smem_u32(&s_mbar[0])), "r"(nt) : "memory");
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(vi_smem_u32(&s_mbar[1])), "r"(nt) : "memory");
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  cluster.sync();
+
+  if (is_comm) {
+    // ===== communication warp: lane l serves sweeps l+1, l+1+RING, ... (non-blocking state machine)
+    const int lane = tid - nt;
+    int s = lane + 1;
+    int state = (lane < VI2_RING && s <= p.max_sweeps) ? 0 : 2;   // 0 wait local, 1 wait global, 2 done
+    unsigned spins = 0;
+    while (__any_sync(0xffffffffu, state != 2)) {
+      if (state != 2 && (s > s_stopK || s_fail)) state = 2;
+      if (state == 0) {
+        const int slot = (s - 1) % VI2_RING;
+        if (vi_mbar_test(&s_postbar[slot], (uint32_t)(((s - 1) / VI2_RING) & 1))) {
+          unsigned d = 0u;
+          for (int wi = 0; wi < nwarps; ++wi) d = max(d, *((volatile unsigned*)&s_wmax[slot][wi]));
+          unsigned* w = reinterpret_cast<unsigned*>(p.gword + s);
+          asm volatile("red.relaxed.gpu.global.max.u32 [%0], %1;" ::"l"(w), "r"(d) : "memory");
+          asm volatile("red.release.gpu.global.add.u32 [%0], %1;" ::"l"(w + 1), "r"(1u) : "memory");
+          state = 1;
+        }
+      } else if (state == 1) {
+        unsigned long long word;
+        asm volatile("ld.acquire.gpu.global.b64 %0, [%1];" : "=l"(word) : "l"(p.gword + s) : "memory");
+        if ((unsigned)(word >> 32) >= (unsigned)p.G) {
+          const float dk = __uint_as_float((unsigned)(word & 0xffffffffu));
+          const int stop = !(dk > p.thr);
+          if (stop) atomicMin((int*)&s_stopK, s);
+          __threadfence_block();
+          s_dec[s % VI2_RING] = (s << 1) | stop;
+          s += VI2_RING;
+          state = (stop || s > p.max_sweeps) ? 2 : 0;
+        }
+      }
+      if (++spins > VI2_SPIN_LIMIT) { s_fail = 1; break; }
+      __nanosleep(40);      // leave the issue slots of this scheduler to the compute warps
+    }
+    __syncwarp();
+  } else {
+    // ===== compute threads: 4 columns x RT rows each.  The hot loop is branch-free: every thread
+    // loads and evaluates its RT rows unconditionally (rows past the strip read in-bounds junk) and
+    // only the stores / the running maximum are predicated by the per-row `on` mask.
+    const int cgn = W >> 2;
+    const int rgn = (p.R + RT - 1) / RT;
+    const bool thread_on = tid < cgn * rgn;
+    const int cgi = thread_on ? tid % cgn : 0, rg = thread_on ? tid / cgn : 0;
+    const int lr0 = rg * RT;
+    const int x0 = cgi << 2;
+    bool on[RT];
+    float4 rr[RT], v[RT];
+    float* ckpt = sm + 2 * tile;                 // snapshot slot q at ckpt + q * R * W (zero = v_0)
+    const int ck_stride = p.R * W;
+    const size_t base = ((size_t)b * H + row0) * W;
+#pragma unroll
+    for (int i = 0; i < RT; ++i) {
+      on[i] = thread_on && (lr0 + i < n);
+      rr[i] = on[i] ? __ldg(reinterpret_cast<const float4*>(p.r + base + (size_t)(lr0 + i) * W + x0))
+                    : make_float4(0.f, 0.f, 0.f, 0.f);
+      v[i] = make_float4(0.f, 0.f, 0.f, 0.f);
+    }
+    const uint32_t sm_base = vi_smem_u32(sm);
+    const bool push_up = has_up && thread_on && lr0 == 0;                       // owns strip row 0
+    const int dn_i = (has_dn && thread_on && n - 1 >= lr0 && n - 1 < lr0 + RT) ? n - 1 - lr0 : -1;
+    // remote byte addresses (tile 0): my top row -> bottom halo (row R+1) of the strip above; my
+    // bottom row -> top halo (row 0) of the strip below
+    const uint32_t up_dst = push_up ? vi_mapa(sm_base, (uint32_t)(cr - 1)) + (uint32_t)(((p.R + 1) * P + 4 + x0) * 4) : 0u;
+    const uint32_t dn_dst = dn_i >= 0 ? vi_mapa(sm_base, (uint32_t)(cr + 1)) + (uint32_t)((4 + x0) * 4) : 0u;
+    const uint32_t up_bar0 = push_up ? vi_mapa(vi_smem_u32(&s_mbar[0]), (uint32_t)(cr - 1)) : 0u;
+    const uint32_t dn_bar0 = dn_i >= 0 ? vi_mapa(vi_smem_u32(&s_mbar[0]), (uint32_t)(cr + 1)) : 0u;
+    const uint32_t halo_bytes = (uint32_t)(4 * W) * ((has_up ? 1u : 0u) + (has_dn ? 1u : 0u));
+    const bool expecter = tid == 0 && halo_bytes != 0;
+    float* const own0 = sm + (lr0 + 1) * P + 4 + x0;      // my first cell, tile 0
+    const float* const win0 = sm + lr0 * P + 4 + x0;      // row above my first cell, tile 0
+    bool failed = false;
+
+    // X = r + gamma*v of the own cells into tile ph&1 (+ halo pushes), arrive, wait for the phase
+    auto exchange = [&](int ph) {
+      const int buf = ph & 1;
+      float* mine = own0 + (buf ? tile : 0);
+      const uint32_t boff = buf ? (uint32_t)(tile * 4) : 0u;
+#pragma unroll
+      for (int i = 0; i < RT; ++i) {
+        float4 X;
+        X.x = __fadd_rn(rr[i].x, __fmul_rn(v[i].x, gamma));
+        X.y = __fadd_rn(rr[i].y, __fmul_rn(v[i].y, gamma));
+        X.z = __fadd_rn(rr[i].z, __fmul_rn(v[i].z, gamma));
+        X.w = __fadd_rn(rr[i].w, __fmul_rn(v[i].w, gamma));
+        if (on[i]) *reinterpret_cast<float4*>(mine + i * P) = X;
+        if (i == 0 && push_up) vi_st_async_v4(up_dst + boff, X, up_bar0 + (uint32_t)(buf * 8));
+        if (i == dn_i) vi_st_async_v4(dn_dst + boff, X, dn_bar0 + (uint32_t)(buf * 8));
+      }
+      uint64_t* bar = &s_mbar[buf];
+      if (expecter) vi_mbar_arrive_expect(bar, halo_bytes);
+      else vi_mbar_arrive_cta(bar);
+      const uint32_t parity = (uint32_t)((ph >> 1) & 1);
+      if (!vi_mbar_test(bar, parity)) {
+        unsigned spins = 0;
+        while (!vi_mbar_test(bar, parity)) {
+          if (++spins > VI2_SPIN_LIMIT) { failed = true; s_fail = 1; break; }
+        }
+      }
+    };
+
+    // one Bellman sweep on tile ph&1: v <- max_a q ; returns max |dv| over the own cells
+    auto sweep = [&](int ph) -> float {
+      const float* X = win0 + ((ph & 1) ? tile : 0);
+      float a[RT + 2][6];
+#pragma unroll
+      for (int i = 0; i < RT + 2; ++i) {
+        const float* row = X + i * P;
+        const float4 m = *reinterpret_cast<const float4*>(row);
+        a[i][0] = row[-1]; a[i][1] = m.x; a[i][2] = m.y; a[i][3] = m.z; a[i][4] = m.w; a[i][5] = row[4];
+      }
+      float dmax = 0.f;
+#pragma unroll
+      for (int i = 0; i < RT; ++i) {
+        float nv[4];
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+          float win[3][3], q[8];
+#pragma unroll
+          for (int dy = 0; dy < 3; ++dy)
+#pragma unroll
+            for (int dx = 0; dx < 3; ++dx) win[dy][dx] = a[i + dy][j + dx];
+          eval_q(win, q);
+          nv[j] = fmaxf(fmaxf(fmaxf(q[0], q[1]), fmaxf(q[2], q[3])), fmaxf(fmaxf(q[4], q[5]), fmaxf(q[6], q[7])));
+        }
+        const float d = fmaxf(fmaxf(fabsf(__fsub_rn(nv[0], v[i].x)), fabsf(__fsub_rn(nv[1], v[i].y))),
+                              fmaxf(fabsf(__fsub_rn(nv[2], v[i].z)), fabsf(__fsub_rn(nv[3], v[i].w))));
+        dmax = fmaxf(dmax, on[i] ? d : 0.0f);
+        v[i].x = on[i] ? nv[0] : v[i].x; v[i].y = on[i] ? nv[1] : v[i].y;
+        v[i].z = on[i] ? nv[2] : v[i].z; v[i].w = on[i] ? nv[3] : v[i].w;
+      }
+      return dmax;
+    };
+
+    int K = p.max_sweeps, hit_max = 1, ph = 0;
+    for (int s = 1; !failed; ++s) {
+      exchange(ph);
+      float dmax = sweep(ph);
+      ++ph;
+      if (s <= p.max_sweeps) {
+        // warp max in ONE instruction (non-negative floats order like their bit patterns), then a
+        // plain store + mbarrier arrive: nothing on this path returns a value to wait for
+        const unsigned wm = __reduce_max_sync(0xffffffffu, __float_as_uint(dmax));
+        if ((tid & 31) == 0) {
+          const int slot = (s - 1) % VI2_RING;
+          s_wmax[slot][tid >> 5] = wm;
+          vi_mbar_arrive_cta(&s_postbar[slot]);
+        }
+      }
+      if (s % p.lag == 0) {      // snapshot v_s into slot (s / lag) & 1 (own cells only)
+        float* dst = ckpt + ((s / p.lag) & 1) * ck_stride;
+#pragma unroll
+        for (int i = 0; i < RT; ++i)
+          if (on[i]) *reinterpret_cast<float4*>(dst + (lr0 + i) * W + x0) = v[i];
+      }
+      const int j = s - p.lag;
+      if (j >= 1) {
+        int dj;
+        unsigned spins = 0;
+        while (((dj = s_dec[j % VI2_RING]) >> 1) != j) {
+          if (s_fail || ++spins > VI2_SPIN_LIMIT) { failed = true; s_fail = 1; break; }
+        }
+        if (failed) break;
+        if (dj & 1) { K = j; hit_max = 0; break; }
+        if (j == p.max_sweeps) { K = j; hit_max = 1; break; }
+      }
+    }
+    if (!failed) {
+      // restore the snapshot at c0 = floor(K / CKPT) * CKPT and replay up to sweep K.  The stop is
+      // observed at sweep K + LAGCHK <= c0 + 2 * CKPT - 1, so slot (c0 / CKPT) & 1 still holds v_c0
+      // (slot 0 starts as zeros = v_0).
+      const int c0 = (K / p.lag) * p.lag;
+      const float* src = ckpt + ((c0 / p.lag) & 1) * ck_stride;
+#pragma unroll
+      for (int i = 0; i < RT; ++i)
+        if (on[i]) v[i] = *reinterpret_cast<const float4*>(src + (lr0 + i) * W + x0);
+      for (int s = c0; s < K && !failed; ++s) {
+        exchange(ph);
+        (void)sweep(ph);
+        ++ph;
+      }
+    }
+    if (!failed) {
+      // final pass (vin.py:76-80): q = conv(r + gamma*v_K), pi = softmax_a(q)
+      exchange(ph);
+      const float* X = sm + (ph & 1) * tile;
+      const size_t HW = (size_t)H * W;
+#pragma unroll
+      for (int i = 0; i < RT; ++i) {
+        const int lr = lr0 + i;
+        if (on[i] && !failed) {
+          const int y = row0 + lr;
+          if (p.v_out) *reinterpret_cast<float4*>(p.v_out + base + (size_t)lr * W + x0) = v[i];
+          if (p.q_out || p.pi_out) {
+            const size_t o = (size_t)b * 8 * HW + (size_t)y * W + x0;
+#pragma unroll 1
+            for (int j = 0; j < 4; ++j) {
+              float win[3][3], q[8], e[8];
+              const float* c = X + (lr + 1) * P + 4 + x0 + j;
+#pragma unroll
+              for (int dx = -1; dx <= 1; ++dx) {
+                win[0][dx + 1] = c[-P + dx];
+                win[1][dx + 1] = c[dx];
+                win[2][dx + 1] = c[P + dx];
+              }
+              eval_q(win, q);
+              float m = q[0];
+#pragma unroll
+              for (int k = 1; k < 8; ++k) m = fmaxf(m, q[k]);
+              float ssum = 0.0f;
+#pragma unroll
+              for (int k = 0; k < 8; ++k) { e[k] = expf(__fsub_rn(q[k], m)); ssum = __fadd_rn(ssum, e[k]); }
+#pragma unroll
+              for (int k = 0; k < 8; ++k) {
+                if (p.q_out) p.q_out[o + k * HW + j] = q[k];
+                if (p.pi_out) p.pi_out[o + k * HW + j] = __fdiv_rn(e[k], ssum);
+              }
+            }
+          }
+        }
+      }
+    }
+    if (blockIdx.x == 0 && tid == 0 && p.sweeps_out) {
+      p.sweeps_out[0] = failed ? -1 : K;
+      p.sweeps_out[1] = failed ? -1 : hit_max;
+    }
+  }
+  cluster.sync();   // no CTA may exit while a neighbour can still write into its shared memory
+}
+
+template <int RT>
+static int vi_try_strip(ViStripParams& p, int c, int threads, size_t smem, cudaStream_t st, int* max_clusters_out) {
+  auto kern = vi_strip_kernel<RT>;
+  if (cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) != cudaSuccess) {
+    cudaGetLastError();
+    return 0;
+  }
+  if (c > 8 && cudaFuncSetAttribute(kern, cudaFuncAttributeNonPortableClusterSizeAllowed, 1) != cudaSuccess) {
+    cudaGetLastError();
+    return 0;
+  }
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = dim3(p.B * c);
+  cfg.blockDim = dim3(threads + 32);
+  cfg.dynamicSmemBytes = smem;
+  cfg.stream = st;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeClusterDimension;
+  attr[0].val.clusterDim.x = c; attr[0].val.clusterDim.y = 1; attr[0].val.clusterDim.z = 1;
+  cfg.attrs = attr;
+  cfg.numAttrs = 1;
+  int max_clusters = 0;
+  if (cudaOccupancyMaxActiveClusters(&max_clusters, kern, &cfg) != cudaSuccess) {
+    cudaGetLastError();
+    return 0;
+  }
+  *max_clusters_out = max_clusters;
+  if (max_clusters < p.B) {              // every cluster must be co-resident (global delta exchange)
+    if (getenv("CRESTE_VI_DEBUG"))
+      fprintf(stderr, "[creste_vi strip] c=%d R=%d RT=%d: max_clusters=%d < B=%d\n", c, p.R, RT, max_clusters, p.B);
+    return 0;
+  }
+  p.c = c; p.G = p.B * c; p.nt = threads;
+  if (getenv("CRESTE_VI_DEBUG"))
+    fprintf(stderr, "[creste_vi strip] B=%d H=%d W=%d c=%d R=%d RT=%d threads=%d smem=%zu max_clusters=%d\n",
+            p.B, p.H, p.W, c, p.R, RT, threads + 32, smem, max_clusters);
+  cudaError_t e = cudaLaunchKernelEx(&cfg, kern, p);
+  if (e != cudaSuccess) {
+    cudaGetLastError();
+    return 0;
+  }
+  count_launch();
+  return 1;
+}
+
 // rows per CTA: as many CTAs as there are SMs, but never less than 2 rows per CTA, and a
 // single CTA (no grid barrier traffic) when the whole problem is tiny.
 static void vi_partition(int B, int H, int W, int* R, int* G) {
@@ -547,7 +927,7 @@ using namespace creste;
 
 extern "C" size_t creste_vi_workspace_bytes(int B, int H, int W, int max_sweeps) {
   const size_t n = (size_t)B * H * W;
-  return 2 * align_up(n * sizeof(float), 256) + 2 * align_up((size_t)(max_sweeps + 1) * 4, 256) + 256;
+  return 2 * align_up(n * sizeof(float), 256) + 2 * align_up((size_t)(max_sweeps + 64) * 4, 256) + 256;
 }
 
 extern "C" int creste_vi_solve(const float* r, float* v_out, float* q_out, float* pi_out, int B,
@@ -570,7 +950,7 @@ extern "C" int creste_vi_solve(const float* r, float* v_out, float* q_out, float
   p.vb = (float*)w;
   w += align_up(n * sizeof(float), 256);
   p.gdelta = (unsigned*)w;
-  const size_t gbytes = align_up((size_t)(max_sweeps + 1) * 4, 256);
+  const size_t gbytes = align_up((size_t)(max_sweeps + 64) * 4, 256);
   w += gbytes;
   p.counter = (unsigned*)(w + gbytes);   // after the second (arrival-count) array
   p.v_out = v_out;
@@ -581,6 +961,38 @@ extern "C" int creste_vi_solve(const float* r, float* v_out, float* q_out, float
   p.max_sweeps = max_sweeps;
   p.gamma = gamma; p.thr = thr;
   CRESTE_CUDA(cudaMemsetAsync(p.gdelta, 0, 2 * gbytes + 256, st));
+  // ---- strip kernel: largest cluster (16 .. 1 CTAs per sample) that is co-resident for the batch
+  if (!getenv("CRESTE_VI_NO_STRIP") && !getenv("CRESTE_VI_NO_CLUSTER") && (W % 4) == 0) {
+    ViStripParams sp;
+    sp.r = r; sp.v_out = v_out; sp.q_out = q_out; sp.pi_out = pi_out;
+    sp.gword = (unsigned long long*)p.gdelta;      // (max, count) pairs over the two arrays
+    sp.sweeps_out = sweeps_out;
+    sp.B = B; sp.H = H; sp.W = W; sp.max_sweeps = max_sweeps; sp.gamma = gamma; sp.thr = thr;
+    const int cgn = W / 4;
+    int last_mc = -1;
+    for (int c = 16; c >= 1; --c) {
+      if (c > H) continue;
+      const int R = ceil_div(H, c);
+      if ((c - 1) * R >= H) continue;                 // every strip needs at least one row
+      int RT = 0;
+      for (int t = 1; t <= 4; ++t)
+        if ((long long)cgn * ceil_div(R, t) <= (t <= 2 ? 608 : 512)) { RT = t; break; }
+      if (!RT) continue;
+      int threads = cgn * ceil_div(R, RT);
+      threads = (threads + 31) / 32 * 32;
+      const size_t ssmem = ((size_t)2 * (R + 2) * (W + 8) + (size_t)2 * R * W) * sizeof(float);
+      if (ssmem > 200 * 1024) continue;
+      sp.R = R;
+      sp.lag = (long long)R * W >= 2048 ? 8 : 24;
+      int mc = 0;
+      int rc = RT == 1 ? vi_try_strip<1>(sp, c, threads, ssmem, st, &mc)
+             : RT == 2 ? vi_try_strip<2>(sp, c, threads, ssmem, st, &mc)
+             : RT == 3 ? vi_try_strip<3>(sp, c, threads, ssmem, st, &mc)
+                       : vi_try_strip<4>(sp, c, threads, ssmem, st, &mc);
+      last_mc = mc;
+      if (rc == 1) return 0;
+    }
+  }
   // ---- cluster-resident path: largest cluster (16, 8, 4, 2, 1 CTAs per sample) that is
   // co-resident for the whole batch and keeps <= 16 cells per thread
   if (!getenv("CRESTE_VI_NO_CLUSTER")) {

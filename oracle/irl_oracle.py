@@ -208,3 +208,43 @@ def port_step(case, steps=1, dtype=torch.float32):
         case["input_view"] = case["input_view"].to(dtype)
         case["exp_svf"] = case["exp_svf"].to(dtype)
     return run_steps(net, PortLoss(case["map_size"]), case, steps)
+
+
+class PortHeadStep:
+    """Head-only stage-3 step on the host (primary variant), the CPU
+    counterpart of creste.train_traversability.HeadStep: cat + 2x2 max-pool + top-half crop
+    (vin.py:104-116) -> reward FCN (train mode) -> value iteration + SVF + rollout (the C oracle)
+    -> MaxEntIRLLoss -> backward -> Adam."""
+
+    def __init__(self, state_dict, map_size, action_horizon=50, lr=5e-4):
+        self.net = PortMSFCN()
+        self.net.load_state_dict(state_dict)
+        self.net.train()
+        self.loss = PortLoss(map_size)
+        self.opt = torch.optim.Adam(self.net.parameters(), lr=lr)
+        self.map_size, self.T = tuple(map_size), action_horizon
+        H, W = self.map_size
+        self.fov_model = net_oracle.trapezoid_fov_mask(2 * H, W, 70, 70, 0, 100)[:H, :W]
+
+    def __call__(self, feat_nchw, expert, fov_mask, cfs):
+        from . import c_oracle as co
+        x = torch.cat(feat_nchw, dim=1)
+        iv = F.max_pool2d(x, 2, 2)
+        iv = iv[:, :, : iv.shape[2] // 2].detach().requires_grad_(True)
+        r = self.net(iv)
+        v, q, pi, K = co.vi_solve(r.detach().numpy())
+        svf, states, grid = co.svf(pi, expert[:, :, :2, 2].numpy().copy(), self.fov_model, self.T, 2,
+                                   True, 0.005, False)
+        td = {"outputs/exp_svf": torch.from_numpy(svf), "inputs/traversability_label": expert,
+              "inputs/fov_mask": fov_mask, "inputs/counterfactuals_label": cfs,
+              "outputs/traversability_preds": r, "outputs/input_view": iv}
+        ld, md = self.loss.loss(td)
+        self.opt.zero_grad()
+        ld["maxentirl_loss"].backward()
+        self.opt.step()
+        return float(ld["maxentirl_loss"].detach()), {"r": r.detach(), "K": K, "exp_svf": svf, "v": v,
+                                             "states": states, **{k: float(v_.detach()) for k, v_ in md.items()}}
+
+
+def head_inputs(B, Hm, Wm, seed=0, T=T_EXPERT):
+    return synth.head_inputs(B, Hm, Wm, seed, T)

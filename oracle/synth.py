@@ -190,3 +190,17 @@ def loss_inputs(B=4, Hm=64, Wm=128, T=50):
 def depth_logits_inputs():
     g = np.random.default_rng(31)
     return np.maximum(g.standard_normal((2, 128, 6, 10)) * 3, 0).astype(np.float32)
+
+
+def head_inputs(B, Hm, Wm, seed=0, T=50):
+    """Synthetic BEV head predictions [B,{32,6,2},4Hm,2Wm] + expert / counterfactuals / FOV mask
+    for an Hm x Wm reward grid (un-pooled BEV 4Hm x 2Wm)."""
+    from .net_oracle import trapezoid_fov_mask   # mask generator only (input synthesis)
+    g = np.random.default_rng(7000 + seed)
+    feat = [torch.from_numpy(g.standard_normal((B, c, 4 * Hm, 2 * Wm), dtype=np.float32))
+            for c in (32, 6, 2)]
+    expert = torch.from_numpy(expert_poses(B, T, 4 * Hm, 2 * Wm, seed))
+    cfs = counterfactuals(expert.numpy(), every=2, shift=0.12 * 2 * Wm)
+    fov = trapezoid_fov_mask(4 * Hm, 2 * Wm, 70, 70, 7 * Wm / 128.0, 200 * Wm / 128.0)
+    fov = torch.from_numpy(np.ascontiguousarray(fov)).unsqueeze(0).repeat(B, 1, 1)
+    return feat, expert, fov, cfs

@@ -46,6 +46,30 @@ def test_vi_matches_oracle(cuda, B, H, W):
     np.testing.assert_allclose(pi.cpu().numpy(), pi0, atol=1e-6, rtol=0)
 
 
+@pytest.mark.parametrize("B,H,W,gamma,thr,ms", [
+    (4, 256, 256, 0.99, 1e-3, 4096),      # cluster of 16 per sample
+    (2, 100, 64, 0.99, 1e-3, 4096),       # ragged last strip
+    (16, 64, 128, 0.99, 1e-3, 4096),      # many small clusters
+    (5, 48, 256, 0.95, 1e-3, 4096),
+    (1, 256, 256, 0.99, 1e-3, 4096),
+    (3, 32, 32, 0.5, 1e-1, 4096),         # K smaller than the snapshot period
+    (3, 32, 32, 0.9, 1e-2, 4096),         # K between snapshots
+    (2, 64, 64, 0.99, 1e-3, 37),          # max_sweeps hit
+    (2, 64, 64, 0.99, 1e-3, 1),
+    (64, 64, 64, 0.99, 1e-3, 4096),       # more samples than co-resident clusters
+])
+def test_vi_strip_kernel_cases(cuda, B, H, W, gamma, thr, ms):
+    """Checkpoint + replay and the lagged stop decision must reproduce the oracle's sweep count
+    and value function bit for bit, whatever K is relative to the snapshot period."""
+    r = synth.vi_inputs(7 * B + H + W, B, H, W)
+    v0, q0, pi0, K0 = co.vi_solve(r, gamma, thr, ms)
+    v, q, pi, info = _ops().vi_solve(torch.from_numpy(r).to(cuda), gamma, thr, ms)
+    assert int(info[0]) == K0, (int(info[0]), K0)
+    assert np.array_equal(v.cpu().numpy()[:, 0].view(np.uint32), v0.view(np.uint32))
+    assert np.array_equal(q.cpu().numpy().view(np.uint32), q0.view(np.uint32))
+    np.testing.assert_allclose(pi.cpu().numpy(), pi0, atol=1e-6, rtol=0)
+
+
 def test_vi_constant_reward_known_answer(cuda):
     # interior cells of a constant-reward grid: v_k = c * sum_{i<k} gamma^i (all 8 actions equal)
     r = torch.full((1, 1, 40, 40), 0.5, device=cuda)

@@ -26,6 +26,33 @@ fov = fov.unsqueeze(0).repeat(B, 1, 1).to(dev)
 for _ in range(2):
     loss, out, meta = step(feat, expert, fov, cfs)
 torch.cuda.synchronize()
+if os.environ.get("PROFILE"):
+    import collections, types
+    from creste_public_b200 import ops
+    rec = []
+    def wrap(name, fn):
+        def w(*a, **k):
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record(); r = fn(*a, **k); e1.record()
+            tag = name
+            if name in ("conv2d", "conv2d_wgrad"):
+                tag = f"{name} {tuple(a[0].shape)}->{a[2] if name == 'conv2d' else tuple(a[1].shape)[-1]} k{a[3] if name == 'conv2d' else a[2]}"
+            rec.append((tag, name, e0, e1)); return r
+        return w
+    for n in dir(ops):
+        f = getattr(ops, n)
+        if isinstance(f, types.FunctionType) and not n.startswith("_") and n not in ("conv_desc", "tc_supported", "tc_layout", "pack_conv_weight", "pack_conv_weight_tc", "rna_tf32", "maxpool2", "upsample2"):
+            setattr(ops, n, wrap(n, f))
+    t0, t1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    t0.record(); step(feat, expert, fov, cfs); t1.record(); torch.cuda.synchronize()
+    tot = t0.elapsed_time(t1)
+    by = collections.defaultdict(lambda: [0, 0.0]); byt = collections.defaultdict(lambda: [0, 0.0])
+    for tag, name, e0, e1 in rec:
+        ms = e0.elapsed_time(e1); by[name][0] += 1; by[name][1] += ms; byt[tag][0] += 1; byt[tag][1] += ms
+    print(f"profiled step: {tot:.2f} ms, {len(rec)} op calls, sum of ops {sum(v[1] for v in by.values()):.2f} ms")
+    for k, v in sorted(by.items(), key=lambda kv: -kv[1][1])[:14]: print(f"  {k:22s} n={v[0]:4d} {v[1]:8.2f} ms")
+    for k, v in sorted(byt.items(), key=lambda kv: -kv[1][1])[:12]: print(f"    {k:60s} n={v[0]:3d} {v[1]:7.2f} ms")
+    sys.exit(0)
 n0 = _lib.lib().creste_launch_count()
 a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
 t0 = time.perf_counter(); a.record()

@@ -387,7 +387,7 @@ def run_ours(args):
             "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms / args.steps,
             "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
             "dtype": {"fp32": "f32", "3xtf32": "f32 (3xTF32 tcgen05)", "tf32": "tf32",
-                      "bf16": "bf16"}[args.precision],
+                      "3xfp16": "f32 (3xFP16 split on tcgen05 kind::f16, fp32 accumulate)"}[args.precision],
             "data": "synthetic",
             "config": {"workload": "configs[1]: RGB+LiDAR->BEV costmap forward, 3x512x960 RGB + "
                                    "131072-pt OS1 sweep per frame, full output dict",
@@ -413,7 +413,7 @@ def main():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--batch", type=int, default=8, help="frames per step per GPU")
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
-    ap.add_argument("--precision", default="3xtf32", choices=["fp32", "3xtf32", "tf32"])
+    ap.add_argument("--precision", default="3xfp16", choices=["fp32", "3xtf32", "3xfp16", "tf32"])
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
     ap.add_argument("--no-irl", action="store_true", help="skip the IRL steps/s leg")
     args = ap.parse_args()

@@ -43,11 +43,11 @@ def _conv_raw(x, w, ph, pw):
         wp = w.new_zeros(Kp, Cp, R, S)
         wp[:K, :Cc] = w
     pad = (ph, ph, pw, pw)
-    mode = engine.get_precision()
-    if mode != "fp32" and not ops.tc_supported(tuple(xp.shape), Kp, R, S, 1, pad, mode):
-        mode = "fp32"
+    mode = engine.pick_mode(tuple(xp.shape), Kp, R, S, 1, pad, engine.get_precision())
     if mode == "fp32":
         packed = ops.pack_conv_weight(wp.detach().float())
+    elif mode == "3xfp16":
+        packed = ops.pack_conv_weight_f16(wp.detach().float())
     else:
         packed = ops.pack_conv_weight_tc(wp.detach().float(), split=(mode == "3xtf32"))
     y = ops.conv2d(xp, packed, Kp, R, S, 1, pad, precision=mode)

@@ -33,6 +33,7 @@
 // lane issues tcgen05.mma; tcgen05.commit releases smem stages / signals the epilogue),
 // warps 2-5 = epilogue.  mbarrier ring of NSTAGES smem stages.
 #include <cuda.h>
+#include <cuda_fp16.h>
 
 #include "common.cuh"
 
@@ -140,6 +141,28 @@ __device__ __forceinline__ void umma_tf32_2sm(uint32_t tmem_d, uint64_t a_desc, 
       "l"(a_desc), "l"(b_desc), "r"(idesc), "r"(accumulate)
       : "memory");
 }
+__device__ __forceinline__ void umma_f16_2sm(uint32_t tmem_d, uint64_t a_desc, uint64_t b_desc,
+                                             uint32_t idesc, uint32_t accumulate) {
+  asm volatile(
+      "{\n\t"
+      ".reg .pred p;\n\t"
+      "setp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::2.kind::f16 [%0], %1, %2, %3, p;\n\t"
+      "}" ::"r"(tmem_d),
+      "l"(a_desc), "l"(b_desc), "r"(idesc), "r"(accumulate)
+      : "memory");
+}
+__device__ __forceinline__ void umma_f16(uint32_t tmem_d, uint64_t a_desc, uint64_t b_desc,
+                                         uint32_t idesc, uint32_t accumulate) {
+  asm volatile(
+      "{\n\t"
+      ".reg .pred p;\n\t"
+      "setp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t"
+      "}" ::"r"(tmem_d),
+      "l"(a_desc), "l"(b_desc), "r"(idesc), "r"(accumulate)
+      : "memory");
+}
 __device__ __forceinline__ void cluster_sync_all() {
   asm volatile("barrier.cluster.arrive.aligned;\n\tbarrier.cluster.wait.aligned;" ::: "memory");
 }
@@ -220,6 +243,11 @@ __host__ __device__ constexpr uint32_t make_idesc_tf32(int n, int m = 128) {
   return (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(n >> 3) << 17) | ((uint32_t)(m >> 4) << 24);
 }
 
+// UMMA::InstrDescriptor for kind::f16 with fp16 A/B (format 0), fp32 accumulate, K-major
+__host__ __device__ constexpr uint32_t make_idesc_f16(int n, int m = 128) {
+  return (1u << 4) | (0u << 7) | (0u << 10) | ((uint32_t)(n >> 3) << 17) | ((uint32_t)(m >> 4) << 24);
+}
+
 // ------------------------------------------------------------------------------------ kernels
 struct TcParams {
   const float* scale; const float* shift; const float* residual; float* out;
@@ -230,6 +258,10 @@ struct TcParams {
   int block_n, act, split;     // split: 1 = 3xTF32 (hi/lo operands), 0 = single TF32
   int out_nchw;
   int cl;                      // cluster size along the M tiles; the B tile is TMA-multicast in cl slices
+  // 3xFP16 mode: operands are fp16 hi / lo of (x * s_a) and (w * s_w[k]) with power-of-two scales;
+  // the epilogue undoes them: (main + cross * cross_scale) * act_inv[0] * w_inv[k]
+  const float* act_inv; const float* w_inv; float cross_scale;
+  int kelems;                  // operand elements per 128-byte swizzle row: 32 (tf32) or 64 (fp16)
 };
 
 constexpr int TC_THREADS = 192;
@@ -247,7 +279,7 @@ __device__ __forceinline__ float tc_act(float v, int act) {
 // M = 256 MMAs that read both CTAs' shared memory and write each CTA's half of D into that CTA's
 // TMEM.  Operand bytes read from shared memory per MMA-cycle halve -- the single-CTA form is bound
 // by shared-memory bandwidth ((128 + 256) rows x 32 B per 128-cycle MMA + the TMA fill).
-template <bool PAIR>
+template <bool PAIR, bool F16>
 __global__ void __launch_bounds__(TC_THREADS, 1)
 conv_tc_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_constant__ CUtensorMap map_a_lo,
                const __grid_constant__ CUtensorMap map_b_hi, const __grid_constant__ CUtensorMap map_b_lo,
@@ -317,19 +349,19 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_consta
         const int nrow = n0 + (int)rank * b_rows;
         if (PAIR) {
           if (leader) mbar_expect_tx(&full_bar[stage], (uint32_t)(2 * stage_bytes));
-          tma_load_4d_2sm(&map_a_hi, &full_bar[stage], st, cb * 32, cx, cy, img);
-          tma_load_2d_2sm(&map_b_hi, &full_bar[stage], b_hi, kb * 32, nrow);
+          tma_load_4d_2sm(&map_a_hi, &full_bar[stage], st, cb * p.kelems, cx, cy, img);
+          tma_load_2d_2sm(&map_b_hi, &full_bar[stage], b_hi, kb * p.kelems, nrow);
           if (p.split) {
-            tma_load_4d_2sm(&map_a_lo, &full_bar[stage], st + A_TILE_BYTES, cb * 32, cx, cy, img);
-            tma_load_2d_2sm(&map_b_lo, &full_bar[stage], b_lo, kb * 32, nrow);
+            tma_load_4d_2sm(&map_a_lo, &full_bar[stage], st + A_TILE_BYTES, cb * p.kelems, cx, cy, img);
+            tma_load_2d_2sm(&map_b_lo, &full_bar[stage], b_lo, kb * p.kelems, nrow);
           }
         } else {
           mbar_expect_tx(&full_bar[stage], (uint32_t)stage_bytes);
-          tma_load_4d(&map_a_hi, &full_bar[stage], st, cb * 32, cx, cy, img);
-          tma_load_2d(&map_b_hi, &full_bar[stage], b_hi, kb * 32, nrow);
+          tma_load_4d(&map_a_hi, &full_bar[stage], st, cb * p.kelems, cx, cy, img);
+          tma_load_2d(&map_b_hi, &full_bar[stage], b_hi, kb * p.kelems, nrow);
           if (p.split) {
-            tma_load_4d(&map_a_lo, &full_bar[stage], st + A_TILE_BYTES, cb * 32, cx, cy, img);
-            tma_load_2d(&map_b_lo, &full_bar[stage], b_lo, kb * 32, nrow);
+            tma_load_4d(&map_a_lo, &full_bar[stage], st + A_TILE_BYTES, cb * p.kelems, cx, cy, img);
+            tma_load_2d(&map_b_lo, &full_bar[stage], b_lo, kb * p.kelems, nrow);
           }
         }
       }
@@ -338,7 +370,8 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_consta
   } else if (warp == 1) {
     // ===== MMA issuer (leader CTA only in pair mode) =====
     if (leader) {
-      const uint32_t idesc = make_idesc_tf32(p.block_n, PAIR ? 256 : 128);
+      const uint32_t idesc = F16 ? make_idesc_f16(p.block_n, PAIR ? 256 : 128)
+                                 : make_idesc_tf32(p.block_n, PAIR ? 256 : 128);
       for (int kb = 0; kb < kblocks; ++kb) {
         const int stage = kb % nstages;
         const uint32_t parity = (kb / nstages) & 1;
@@ -352,18 +385,22 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_consta
           for (int k = 0; k < 4; ++k) {   // 4 x (K = 8 tf32 = 32 B) per 128-byte swizzle row
             const uint32_t koff = k * 32;
             const uint32_t first = (kb | k) != 0;
+            const uint64_t dah = make_sw128_desc(a_hi + koff), dal = make_sw128_desc(a_lo + koff);
+            const uint64_t dbh = make_sw128_desc(b_hi + koff), dbl = make_sw128_desc(b_lo + koff);
             if (PAIR) {
               if (p.split) {
-                umma_tf32_2sm(tmem_base + acc2, make_sw128_desc(a_lo + koff), make_sw128_desc(b_hi + koff), idesc, first);
-                umma_tf32_2sm(tmem_base + acc2, make_sw128_desc(a_hi + koff), make_sw128_desc(b_lo + koff), idesc, 1);
+                if (F16) { umma_f16_2sm(tmem_base + acc2, dal, dbh, idesc, first); umma_f16_2sm(tmem_base + acc2, dah, dbl, idesc, 1); }
+                else { umma_tf32_2sm(tmem_base + acc2, dal, dbh, idesc, first); umma_tf32_2sm(tmem_base + acc2, dah, dbl, idesc, 1); }
               }
-              umma_tf32_2sm(tmem_base, make_sw128_desc(a_hi + koff), make_sw128_desc(b_hi + koff), idesc, first);
+              if (F16) umma_f16_2sm(tmem_base, dah, dbh, idesc, first);
+              else umma_tf32_2sm(tmem_base, dah, dbh, idesc, first);
             } else {
               if (p.split) {
-                umma_tf32(tmem_base + acc2, make_sw128_desc(a_lo + koff), make_sw128_desc(b_hi + koff), idesc, first);
-                umma_tf32(tmem_base + acc2, make_sw128_desc(a_hi + koff), make_sw128_desc(b_lo + koff), idesc, 1);
+                if (F16) { umma_f16(tmem_base + acc2, dal, dbh, idesc, first); umma_f16(tmem_base + acc2, dah, dbl, idesc, 1); }
+                else { umma_tf32(tmem_base + acc2, dal, dbh, idesc, first); umma_tf32(tmem_base + acc2, dah, dbl, idesc, 1); }
               }
-              umma_tf32(tmem_base, make_sw128_desc(a_hi + koff), make_sw128_desc(b_hi + koff), idesc, first);
+              if (F16) umma_f16(tmem_base, dah, dbh, idesc, first);
+              else umma_tf32(tmem_base, dah, dbh, idesc, first);
             }
           }
           // smem stage free (in both CTAs of a pair) once these MMAs retire
@@ -385,6 +422,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_consta
     const size_t pix = ((size_t)img * p.P + oy) * p.Q + ox;
     mbar_wait(&tmem_full_bar, 0);
     tc_fence_after();
+    const float act_inv = F16 ? __ldg(p.act_inv) : 1.0f;
     for (int c0 = 0; c0 < p.block_n; c0 += 32) {
       uint32_t v[32];
       tmem_ld32(tmem_base + ((uint32_t)(quarter * 32) << 16) + (uint32_t)c0, v);
@@ -393,7 +431,9 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_consta
         tmem_ld32(tmem_base + ((uint32_t)(quarter * 32) << 16) + acc2 + (uint32_t)c0, v2);
         tmem_ld_wait();
 #pragma unroll
-        for (int j = 0; j < 32; ++j) v[j] = __float_as_uint(__uint_as_float(v[j]) + __uint_as_float(v2[j]));
+        for (int j = 0; j < 32; ++j)
+          v[j] = __float_as_uint(F16 ? fmaf(__uint_as_float(v2[j]), p.cross_scale, __uint_as_float(v[j]))
+                                     : __uint_as_float(v[j]) + __uint_as_float(v2[j]));
       } else {
         tmem_ld_wait();
       }
@@ -408,6 +448,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_consta
             const int nn = n + q;
             float val = __uint_as_float(v[j + q]);
             if (nn < p.K) {
+              if (F16) val *= act_inv * __ldg(p.w_inv + nn);      // powers of two: exact
               const float sc = p.scale ? __ldg(p.scale + nn) : 1.0f;
               const float sh = p.shift ? __ldg(p.shift + nn) : 0.0f;
               val = fmaf(val, sc, sh);
@@ -472,6 +513,68 @@ __global__ void __launch_bounds__(256) tf32_split_kernel(const float4* __restric
   }
 }
 
+// ---- 3xFP16 operand preparation.  amax over x (* gate) -> power-of-two scale s with
+// amax * s in [2^14, 2^15); hi = fp16(x*s), lo = fp16((x*s - hi) * 2^11)  (both exact scalings).
+// fp16 carries 11 significant bits like tf32, so hi*hi + (hi*lo + lo*hi) * 2^-11 has the accuracy of
+// the 3xTF32 split at twice the tensor-pipe rate; the per-tensor scale keeps everything in fp16's
+// normal range (small values go subnormal: absolute error <= 2^-25 * 2^-15 of the tensor maximum).
+__global__ void __launch_bounds__(256) f16_amax_kernel(const float4* __restrict__ x, const float* __restrict__ gate,
+                                                       int C, long long hwc4, long long n4,
+                                                       unsigned* __restrict__ amax_bits) {
+  float m = 0.f;
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n4;
+       i += (long long)gridDim.x * blockDim.x) {
+    float4 v = __ldg(x + i);
+    if (gate) {
+      const int img = (int)(i / hwc4);
+      const int c = (int)((i * 4) % C);
+      const float4 g = __ldg(reinterpret_cast<const float4*>(gate + (size_t)img * C + c));
+      v.x *= g.x; v.y *= g.y; v.z *= g.z; v.w *= g.w;
+    }
+    m = fmaxf(fmaxf(m, fmaxf(fabsf(v.x), fabsf(v.y))), fmaxf(fabsf(v.z), fabsf(v.w)));
+  }
+  m = warp_max(m);
+  if ((threadIdx.x & 31) == 0 && m > 0.f) atomicMax(amax_bits, __float_as_uint(m));
+}
+
+// scal[0] = s (power of two), scal[1] = 1/s
+__global__ void f16_scale_kernel(const unsigned* __restrict__ amax_bits, float* __restrict__ scal) {
+  const unsigned b = *amax_bits;
+  int e = (int)((b >> 23) & 0xffu) - 127;          // floor(log2(amax)) for normal amax
+  if (b == 0u || !isfinite(__uint_as_float(b))) e = 14;
+  const int k = max(-100, min(100, 14 - e));
+  scal[0] = __uint_as_float((unsigned)(127 + k) << 23);
+  scal[1] = __uint_as_float((unsigned)(127 - k) << 23);
+}
+
+__global__ void __launch_bounds__(256) f16_split_kernel(const float4* __restrict__ x, const float* __restrict__ gate,
+                                                        int C, long long hwc4, long long n4,
+                                                        const float* __restrict__ scal, uint2* __restrict__ hi,
+                                                        uint2* __restrict__ lo) {
+  const float s = __ldg(scal);
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n4;
+       i += (long long)gridDim.x * blockDim.x) {
+    float4 v = __ldg(x + i);
+    if (gate) {
+      const int img = (int)(i / hwc4);
+      const int c = (int)((i * 4) % C);
+      const float4 g = __ldg(reinterpret_cast<const float4*>(gate + (size_t)img * C + c));
+      v.x *= g.x; v.y *= g.y; v.z *= g.z; v.w *= g.w;
+    }
+    const float xs[4] = {v.x * s, v.y * s, v.z * s, v.w * s};
+    unsigned short h[4], l[4];
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      const __half hh = __float2half_rn(xs[j]);
+      const float res = (xs[j] - __half2float(hh)) * 2048.0f;
+      h[j] = __half_as_ushort(hh);
+      l[j] = __half_as_ushort(__float2half_rn(res));
+    }
+    hi[i] = make_uint2((unsigned)h[0] | ((unsigned)h[1] << 16), (unsigned)h[2] | ((unsigned)h[3] << 16));
+    lo[i] = make_uint2((unsigned)l[0] | ((unsigned)l[1] << 16), (unsigned)l[2] | ((unsigned)l[3] << 16));
+  }
+}
+
 // ------------------------------------------------------------------------------------ host
 typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
                                   const cuuint64_t*, const cuuint32_t*, const cuuint32_t*,
@@ -490,28 +593,30 @@ static EncodeTiledFn get_encode() {
   return fn;
 }
 
-static int make_map_a(CUtensorMap* m, const float* base, int N, int H, int W, int C, int wbox, int hbox) {
+static int make_map_a(CUtensorMap* m, const void* base, int N, int H, int W, int C, int wbox, int hbox,
+                      bool f16 = false) {
   EncodeTiledFn enc = get_encode();
   if (!enc) { set_error("cuTensorMapEncodeTiled unavailable"); return CRESTE_ERR_NO_DEVICE; }
+  const cuuint64_t eb = f16 ? 2 : 4;
   cuuint64_t dims[4] = {(cuuint64_t)C, (cuuint64_t)W, (cuuint64_t)H, (cuuint64_t)N};
-  cuuint64_t strides[3] = {(cuuint64_t)C * 4, (cuuint64_t)W * C * 4, (cuuint64_t)H * W * C * 4};
-  cuuint32_t box[4] = {32, (cuuint32_t)wbox, (cuuint32_t)hbox, 1};
+  cuuint64_t strides[3] = {(cuuint64_t)C * eb, (cuuint64_t)W * C * eb, (cuuint64_t)H * W * C * eb};
+  cuuint32_t box[4] = {f16 ? 64u : 32u, (cuuint32_t)wbox, (cuuint32_t)hbox, 1};
   cuuint32_t es[4] = {1, 1, 1, 1};
-  CUresult r = enc(m, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 4, (void*)base, dims, strides, box, es,
+  CUresult r = enc(m, f16 ? CU_TENSOR_MAP_DATA_TYPE_FLOAT16 : CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 4, (void*)base, dims, strides, box, es,
                    CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B,
                    CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
   if (r != CUDA_SUCCESS) { set_error("cuTensorMapEncodeTiled(A) failed: %d", (int)r); return CRESTE_ERR_ARG; }
   return 0;
 }
 
-static int make_map_b(CUtensorMap* m, const float* base, int ktot, int npad, int block_n) {
+static int make_map_b(CUtensorMap* m, const void* base, int ktot, int npad, int block_n, bool f16 = false) {
   EncodeTiledFn enc = get_encode();
   if (!enc) { set_error("cuTensorMapEncodeTiled unavailable"); return CRESTE_ERR_NO_DEVICE; }
   cuuint64_t dims[2] = {(cuuint64_t)ktot, (cuuint64_t)npad};
-  cuuint64_t strides[1] = {(cuuint64_t)ktot * 4};
-  cuuint32_t box[2] = {32, (cuuint32_t)block_n};
+  cuuint64_t strides[1] = {(cuuint64_t)ktot * (f16 ? 2 : 4)};
+  cuuint32_t box[2] = {f16 ? 64u : 32u, (cuuint32_t)block_n};
   cuuint32_t es[2] = {1, 1};
-  CUresult r = enc(m, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, (void*)base, dims, strides, box, es,
+  CUresult r = enc(m, f16 ? CU_TENSOR_MAP_DATA_TYPE_FLOAT16 : CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, (void*)base, dims, strides, box, es,
                    CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B,
                    CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
   if (r != CUDA_SUCCESS) { set_error("cuTensorMapEncodeTiled(B) failed: %d", (int)r); return CRESTE_ERR_ARG; }
@@ -542,8 +647,9 @@ static void pick_box(int P, int Q, int* wbox, int* hbox) {
 }
 
 bool conv_tc_supported(const creste_conv_desc* d) {
-  if (d->precision != 1 && d->precision != 2) return false;
+  if (d->precision != 1 && d->precision != 2 && d->precision != 4) return false;
   if (d->stride != 1 || d->C % 4 != 0 || d->K < 8) return false;
+  if (d->precision == 4 && d->C % 8 != 0) return false;     // fp16 rows must be 16-byte multiples (TMA)
   if (d->R > 5 || d->S > 5) return false;
   if ((long long)d->N * d->P * d->Q < 128) return false;
   return true;
@@ -559,6 +665,7 @@ int conv_tc_layout(int K, int C, int R, int S, int* block_n, int* npad, int* cpa
 
 size_t conv_tc_workspace_bytes(const creste_conv_desc* d) {
   const size_t n = (size_t)d->N * d->H * d->W * d->C * sizeof(float);
+  if (d->precision == 4) return 2 * align_up(n / 2, 1024) + 1024;     // fp16 hi, lo + scale scalars
   return d->precision == 1 ? 2 * align_up(n, 1024) : align_up(n, 1024);
 }
 
@@ -569,14 +676,35 @@ int conv_tc_launch(const creste_conv_desc* d, const float* x, const float* w_pac
     set_error("creste_conv2d(tc): workspace %zu < %zu", ws_bytes, conv_tc_workspace_bytes(d));
     return CRESTE_ERR_WORKSPACE;
   }
-  const int split = d->precision == 1;
+  const bool f16 = d->precision == 4;
+  const int split = d->precision == 1 || f16;
   int block_n, npad, cpad;
   conv_tc_layout(d->K, d->C, d->R, d->S, &block_n, &npad, &cpad);
+  if (f16) cpad = (d->C + 63) / 64 * 64;
   const int ktot = d->R * d->S * cpad;
   const size_t numel = (size_t)d->N * d->H * d->W * d->C;
   float* x_hi = (float*)ws;
-  float* x_lo = split ? (float*)((char*)ws + align_up(numel * 4, 1024)) : nullptr;
-  {
+  float* x_lo = split ? (float*)((char*)ws + align_up(numel * (f16 ? 2 : 4), 1024)) : nullptr;
+  float* scal = nullptr;
+  if (f16) {
+    scal = (float*)((char*)ws + 2 * align_up(numel * 2, 1024));       // [s, 1/s, amax bits, -]
+    unsigned* amax = (unsigned*)(scal + 2);
+    CRESTE_CUDA(cudaMemsetAsync(amax, 0, 4, st));
+    const long long n4 = (long long)(numel / 4);
+    long long blocks = (n4 + 255) / 256;
+    if (blocks > 148 * 16) blocks = 148 * 16;
+    const long long hwc4 = (long long)d->H * d->W * d->C / 4;
+    f16_amax_kernel<<<(int)blocks, 256, 0, st>>>((const float4*)x, gate, d->C, hwc4, n4, amax);
+    int rc = launch_check("f16_amax_kernel");
+    if (rc) return rc;
+    f16_scale_kernel<<<1, 1, 0, st>>>(amax, scal);
+    rc = launch_check("f16_scale_kernel");
+    if (rc) return rc;
+    f16_split_kernel<<<(int)blocks, 256, 0, st>>>((const float4*)x, gate, d->C, hwc4, n4, scal, (uint2*)x_hi,
+                                                  (uint2*)x_lo);
+    rc = launch_check("f16_split_kernel");
+    if (rc) return rc;
+  } else {
     const long long n4 = (long long)(numel / 4);
     long long blocks = (n4 + 255) / 256;
     if (blocks > 148 * 16) blocks = 148 * 16;
@@ -602,12 +730,19 @@ int conv_tc_launch(const creste_conv_desc* d, const float* x, const float* w_pac
   p.cl = cl;
   CUtensorMap ma_hi, ma_lo, mb_hi, mb_lo;
   int rc;
-  if ((rc = make_map_a(&ma_hi, x_hi, d->N, d->H, d->W, d->C, p.wbox, p.hbox))) return rc;
-  if ((rc = make_map_a(&ma_lo, split ? x_lo : x_hi, d->N, d->H, d->W, d->C, p.wbox, p.hbox))) return rc;
-  const float* w_hi = w_packed;
-  const float* w_lo = w_packed + (size_t)npad * ktot;
-  if ((rc = make_map_b(&mb_hi, w_hi, ktot, npad, block_n / cl))) return rc;
-  if ((rc = make_map_b(&mb_lo, split ? w_lo : w_hi, ktot, npad, block_n / cl))) return rc;
+  if ((rc = make_map_a(&ma_hi, x_hi, d->N, d->H, d->W, d->C, p.wbox, p.hbox, f16))) return rc;
+  if ((rc = make_map_a(&ma_lo, split ? x_lo : x_hi, d->N, d->H, d->W, d->C, p.wbox, p.hbox, f16))) return rc;
+  // packed weights: [hi][lo] (fp32 words for tf32; fp16 halves for 3xFP16, followed by w_inv[npad] fp32)
+  const size_t wel = (size_t)npad * ktot;
+  const void* w_hi = w_packed;
+  const void* w_lo = f16 ? (const void*)((const char*)w_packed + wel * 2) : (const void*)(w_packed + wel);
+  if ((rc = make_map_b(&mb_hi, w_hi, ktot, npad, block_n / cl, f16))) return rc;
+  if ((rc = make_map_b(&mb_lo, split ? w_lo : w_hi, ktot, npad, block_n / cl, f16))) return rc;
+  p.kelems = f16 ? 64 : 32;
+  p.cblocks = cpad / p.kelems;
+  p.act_inv = f16 ? scal + 1 : nullptr;
+  p.w_inv = f16 ? (const float*)((const char*)w_packed + wel * 4) : nullptr;
+  p.cross_scale = f16 ? (1.0f / 2048.0f) : 1.0f;
 
   const int nops = split ? 2 : 1;
   const size_t stage_bytes = (size_t)nops * (A_TILE_BYTES + (block_n / cl) * 128);
@@ -615,7 +750,8 @@ int conv_tc_launch(const creste_conv_desc* d, const float* x, const float* w_pac
   if (nstages > 8) nstages = 8;
   if (nstages < 2) { set_error("creste_conv2d(tc): stage too large"); return CRESTE_ERR_ARG; }
   const size_t smem = (size_t)nstages * stage_bytes + 1024;
-  auto kern = cl == 2 ? conv_tc_kernel<true> : conv_tc_kernel<false>;
+  auto kern = f16 ? (cl == 2 ? conv_tc_kernel<true, true> : conv_tc_kernel<false, true>)
+                  : (cl == 2 ? conv_tc_kernel<true, false> : conv_tc_kernel<false, false>);
   CRESTE_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
   dim3 grid(ceil_div(m_tiles, cl) * cl, npad / block_n);
   cudaLaunchConfig_t cfg = {};

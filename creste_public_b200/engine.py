@@ -12,8 +12,10 @@ _PRECISION = "fp32"
 
 
 def set_precision(mode):
-    """Conv-family arithmetic: 'fp32' (FFMA, exact products), '3xtf32' (tcgen05, fp32-faithful
-    split), 'tf32' / 'bf16' (tcgen05 single pass; measured error is reported, never asserted)."""
+    """Conv-family arithmetic: 'fp32' (FFMA, exact products), '3xtf32' (tcgen05 kind::tf32,
+    fp32-faithful split), '3xfp16' (tcgen05 kind::f16 on power-of-two-scaled fp16 hi/lo operands:
+    the same 11-bit significands as tf32 at twice the tensor-pipe rate), 'tf32' (single pass;
+    measured error is reported, never asserted)."""
     global _PRECISION
     assert mode in ops.PRECISION, mode
     _PRECISION = mode
@@ -30,6 +32,21 @@ def require_eval(module):
             "drop-connect, autograd) is not implemented in creste_public_b200 yet; call "
             ".eval() -- the reference semantics for inference (running statistics) are what "
             "the sm_100a engine implements.  No PyTorch fallback is provided on purpose.")
+
+
+def pick_mode(x_shape, K, R, S, stride, pad, mode):
+    """Requested precision, or the next stricter one the shape is served by:
+    3xfp16 -> 3xtf32 -> fp32 (never a looser one)."""
+    chain = {"3xfp16": ["3xfp16", "3xtf32"], "3xtf32": ["3xtf32"], "tf32": ["tf32"], "fp32": []}[mode]
+    # short reductions (1x1 convs with C <= 192: the MBConv expand / project and head convs) are
+    # HBM-bound; measured per shape, the exact-fp32 FFMA kernel beats the tensor-core kernel there
+    # (no operand pre-pass, no per-CTA TMEM / barrier set-up): 0.79 vs 1.32 ms at C16->K96 @256x480
+    if R * S * x_shape[3] <= 192:
+        return "fp32"
+    for m in chain:
+        if ops.tc_supported(x_shape, K, R, S, stride, pad, m):
+            return m
+    return "fp32"
 
 
 def _ver(*tensors):
@@ -78,6 +95,8 @@ class FusedConv:
         def build():
             if mode == "fp32":
                 w = ops.pack_conv_weight(conv.weight.detach().float())
+            elif mode == "3xfp16":
+                w = ops.pack_conv_weight_f16(conv.weight.detach().float())
             else:
                 w = ops.pack_conv_weight_tc(conv.weight.detach().float(), split=(mode == "3xtf32"))
             if bn is not None:
@@ -99,8 +118,7 @@ class FusedConv:
         mode = precision or _PRECISION
         # shapes the tensor-core kernel does not serve (strided, C = 4 stem, K < 8 heads) run on
         # the exact-fp32 CUDA-core kernel -- a stricter precision, never a looser one
-        if mode != "fp32" and not ops.tc_supported(tuple(x_nhwc.shape), K, R, S, stride, pad, mode):
-            mode = "fp32"
+        mode = pick_mode(tuple(x_nhwc.shape), K, R, S, stride, pad, mode)
         w, scale, shift = self.packed(mode)
         return ops.conv2d(x_nhwc, w, K, R, S, stride, pad, scale, shift, gate, residual, act,
                           out_nchw, mode)

@@ -12,7 +12,7 @@ from . import _lib
 from ._lib import ConvDesc, check, lib, ptr, stream
 
 ACT = {"none": 0, None: 0, "relu": 1, "swish": 2, "sigmoid": 3}
-PRECISION = {"fp32": 0, "3xtf32": 1, "tf32": 2, "bf16": 3}
+PRECISION = {"fp32": 0, "3xtf32": 1, "tf32": 2, "bf16": 3, "3xfp16": 4}
 
 
 def _ws(nbytes, device):
@@ -181,6 +181,27 @@ def pack_conv_weight_tc(w, split):
         return hi.reshape(-1).contiguous()
     lo = rna_tf32(p - hi)
     return torch.cat([hi.reshape(-1), lo.reshape(-1)]).contiguous()
+
+
+def pack_conv_weight_f16(w):
+    """[K,C,R,S] -> the 3xFP16 operand of creste_conv2d (precision 4): per-output-channel
+    power-of-two scale s_k with max_c|w_k| * s_k in [2^14, 2^15); hi = fp16(w * s_k),
+    lo = fp16((w * s_k - hi) * 2^11); layout [Npad][R*S*Cpad64] hi halves, then lo halves, then
+    1/s_k as fp32 [Npad] -- returned as one flat float32 buffer."""
+    K, Cc, R, S = w.shape
+    _, npad, _ = tc_layout(K, Cc, R, S)
+    cpad = (Cc + 63) // 64 * 64
+    p = w.new_zeros(npad, R * S, cpad)
+    p[:K, :, :Cc] = w.permute(0, 2, 3, 1).reshape(K, R * S, Cc)
+    amax = p.abs().amax(dim=(1, 2))
+    e = torch.floor(torch.log2(torch.where(amax > 0, amax, torch.ones_like(amax))))
+    k = (14 - e).clamp(-100, 100)
+    sc = torch.exp2(k).view(npad, 1, 1)
+    ps = p * sc
+    hi = ps.half()
+    lo = ((ps - hi.float()) * 2048.0).half()
+    halves = torch.cat([hi.reshape(-1), lo.reshape(-1)])
+    return torch.cat([halves.view(torch.float32), torch.exp2(-k).float()]).contiguous()
 
 
 def conv_desc(x_shape, K, R, S, stride, pad, act="none", out_nchw=False, precision="fp32"):

@@ -44,7 +44,7 @@ def _ref(case, g):
 
 
 @pytest.mark.parametrize("case", CASES)
-@pytest.mark.parametrize("mode,tol", [("3xtf32", 3e-5), ("tf32", 2e-3)])
+@pytest.mark.parametrize("mode,tol", [("3xtf32", 3e-5), ("tf32", 2e-3), ("3xfp16", 3e-5)])
 def test_conv_tc_matches_torch(cuda, case, mode, tol):
     from creste_public_b200 import ops
     N, C, H, W, K, R, act, use_gate, use_res = case
@@ -52,7 +52,8 @@ def test_conv_tc_matches_torch(cuda, case, mode, tol):
     x, w, scale, shift, gate, res, ref = _ref(case, g)
     pad = (R // 2,) * 4
     assert ops.tc_supported((N, H, W, C), K, R, R, 1, pad, mode)
-    wp = ops.pack_conv_weight_tc(w.to(cuda), split=(mode == "3xtf32"))
+    wp = ops.pack_conv_weight_f16(w.to(cuda)) if mode == "3xfp16" else \
+        ops.pack_conv_weight_tc(w.to(cuda), split=(mode == "3xtf32"))
     out = ops.conv2d(x.to(cuda).permute(0, 2, 3, 1).contiguous(), wp, K, R, R, 1, pad, scale.to(cuda),
                      shift.to(cuda), gate.to(cuda) if use_gate else None,
                      res.to(cuda).permute(0, 2, 3, 1).contiguous() if use_res else None, act,
@@ -61,6 +62,35 @@ def test_conv_tc_matches_torch(cuda, case, mode, tol):
     out = out.cpu().permute(0, 3, 1, 2)
     err = float((out - ref).abs().max())
     assert err <= tol * float(ref.abs().max()), f"err {err:.3e} vs max {float(ref.abs().max()):.3e}"
+
+
+@pytest.mark.parametrize("xs,ws", [(1e-4, 1.0), (3e3, 1e-3), (1.0, 50.0)])
+def test_conv_3xfp16_dynamic_range(cuda, xs, ws):
+    """3xFP16 (precision 4): fp16 hi/lo operands under power-of-two scales (per tensor for the
+    activations, per output channel for the weights).  Inputs far outside fp16's range, a wide
+    spread inside one tensor and per-channel weight magnitudes over 6 decades must still give
+    the 3xTF32 accuracy (both carry 11-bit significands)."""
+    from creste_public_b200 import ops
+    g = torch.Generator().manual_seed(7)
+    N, C, H, W, K, R = 1, 128, 16, 24, 64, 3
+    x = torch.randn(N, C, H, W, generator=g) * xs
+    x[:, ::7] *= 1e-3                                   # small-magnitude channels next to large ones
+    w = torch.randn(K, C, R, R, generator=g) * ws / (C * R * R) ** 0.5
+    w *= torch.logspace(-3, 3, K).view(K, 1, 1, 1)      # per-output-channel scale over 6 decades
+    ref = F.conv2d(x.double(), w.double(), padding=1)
+    out = ops.conv2d(x.to(cuda).permute(0, 2, 3, 1).contiguous(), ops.pack_conv_weight_f16(w.to(cuda)), K, R, R,
+                     1, (1, 1, 1, 1), precision="3xfp16").cpu().permute(0, 3, 1, 2).double()
+    # per output channel (each has its own magnitude)
+    err = (out - ref).abs().amax(dim=(0, 2, 3)) / ref.abs().amax(dim=(0, 2, 3))
+    assert float(err.max()) <= 3e-5, err
+
+
+def test_conv_3xfp16_zero_input(cuda):
+    from creste_public_b200 import ops
+    x = torch.zeros(1, 16, 16, 64, device=cuda)
+    w = torch.randn(32, 64, 1, 1, device=cuda)
+    out = ops.conv2d(x, ops.pack_conv_weight_f16(w), 32, 1, 1, 1, (0, 0, 0, 0), precision="3xfp16")
+    assert float(out.abs().max()) == 0.0
 
 
 def test_tc_unsupported_shapes_are_refused(cuda):

@@ -108,3 +108,26 @@ def test_data_parallel_sharding_gloo_world2(tmp_path):
     res = subprocess.run(cmd, capture_output=True, text=True, timeout=300)
     assert res.returncode == 0, res.stdout + res.stderr
     assert "OK" in res.stdout
+
+
+def test_projection_transforms_match_reference_math():
+    """get_pixel2pts_transform / get_pts2pixel_transform (projection.py:11-61): inverse pair, and
+    equal to the synthetic p2p used by every test (oracle/synth.py) for the same calibration."""
+    import numpy as np
+    from creste_public_b200.creste.utils import projection as pj
+    from oracle import synth
+    H, W = 512, 960
+    K = synth.intrinsics(H, W)
+    P = np.zeros((3, 4)); P[:, :3] = K
+    calib = {"lidar2cam": np.linalg.inv(synth.T_CAM_TO_LIDAR), "R": np.eye(3), "P": P}
+    a, b = pj.get_pixel2pts_transform(calib), pj.get_pts2pixel_transform(calib)
+    np.testing.assert_allclose(a @ b, np.eye(4), atol=1e-9)
+    P4 = P.copy(); P4[:2, :] /= 4          # quarter-resolution intrinsics (ds_gt_depth)
+    np.testing.assert_allclose(pj.get_pixel2pts_transform({**calib, "P": P4}).astype(np.float32),
+                               synth.make_p2p(H, W), atol=1e-6)
+    from oracle import ref_shims
+    if ref_shims.reference_available():
+        from oracle import ref_harness as rh
+        ref = rh.ref_modules()["projection"]
+        np.testing.assert_allclose(a, ref.get_pixel2pts_transform(calib), atol=1e-12)
+        np.testing.assert_allclose(b, ref.get_pts2pixel_transform(calib), atol=1e-12)

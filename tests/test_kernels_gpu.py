@@ -239,3 +239,17 @@ def test_expert_visitation_matches_reference_golden(cuda, golden):
         ms = int(np.ceil(np.linalg.norm((t[:, 1:] - t[:, :-1]) / 2.0, axis=-1)).max())
         c = _ops().expert_visitation(torch.from_numpy(t).to(cuda), 2, ms, 64, 128)
         assert np.array_equal(c.cpu().numpy(), co.expert_visitation(t, 2, 64, 128, True))
+
+
+def test_projection_mirror_pixels_to_depth(cuda, golden):
+    """creste.utils.projection.pixels_to_depth mirror (reference signature) vs the golden raster."""
+    from creste_public_b200.creste.utils import projection as pj
+    g = golden("lidar.npz")
+    H, W = 128, 240
+    pc = synth.os1_scan(seed=3)[::8]
+    pts, dep = pj.pixels_to_depth(pc, {"lidar2camrect": synth.lidar2camrect(H, W)}, H, W)
+    img = np.zeros((H, W), np.float32)
+    img[pts[:, 1], pts[:, 0]] = dep
+    assert np.array_equal(img, g["depth_m"])
+    rgbd = pj.make_rgbd(torch.zeros(3, H, W), pc, synth.lidar2camrect(H, W))
+    assert np.array_equal(rgbd[3].cpu().numpy(), g["depth_mm"].astype(np.float32))

@@ -56,7 +56,7 @@ def _conv_raw(x, w, ph, pw):
 
 def _wgrad_raw(x, g, R, S, ph, pw):
     Cc, K = x.shape[-1], g.shape[-1]
-    dw = ops.conv2d_wgrad(_pad_last(x), _pad_last(g), R, S, (ph, ph, pw, pw))
+    dw = ops.conv2d_wgrad(_pad_last(x, 8), _pad_last(g, 8), R, S, (ph, ph, pw, pw))
     return dw[:K, :Cc].contiguous()
 
 

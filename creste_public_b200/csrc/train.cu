@@ -229,42 +229,40 @@ __global__ void __launch_bounds__(256) upsample_adjoint_kernel(const float* __re
 
 // --------------------------------------------------------------------------------------- wgrad
 // dw[(r*S+s)][c][k] = sum_{n,p,q} x[n, p+r-pad_t, q+s-pad_l, c] * g[n,p,q,k]      (stride 1)
-// grid (chunks, R*S): one CTA = one filter tap x one contiguous range of output pixels; it
-// accumulates the [C x K] tile of that tap (C, K <= 64) from 64-pixel slabs staged in shared
-// memory.  Thread = (pixel lane, 4-channel group of x, 4-channel group of g): 16 FMAs per two
-// LDS.128.  part[chunk][tap][C][K] is then reduced in chunk order by reduce_rows_kernel.
+// grid (chunks, R*S): one CTA = one filter tap x one contiguous range of output pixels.  64-pixel
+// slabs of x (shifted by the tap, zero outside the image) and g are staged in shared memory; a
+// thread owns an 8(c) x 8(k) register tile (64 FMAs per 4 LDS.128 -- FMA-bound, not LDS-bound
+// like a 4x4 tile) and one of `lanes` pixel lanes.  Every (chunk, lane) writes its own partial
+// [C x K] tile; reduce_rows_kernel adds them in a fixed order.   C, K multiples of 8, <= 64.
 constexpr int WG_PIX = 64;
 __global__ void __launch_bounds__(256) wgrad_kernel(const float* __restrict__ x,
                                                     const float* __restrict__ g, int N, int H, int W,
                                                     int C, int K, int R, int S, int pad_t, int pad_l,
-                                                    int P, int Q, float* __restrict__ part) {
-  __shared__ __align__(16) float s_all[2 * WG_PIX * 64];
-  float (*s_x)[64] = reinterpret_cast<float (*)[64]>(s_all);
-  float (*s_g)[64] = reinterpret_cast<float (*)[64]>(s_all + WG_PIX * 64);
-  float (*s_red)[16] = reinterpret_cast<float (*)[16]>(s_all);   // reused after the main loop
+                                                    int P, int Q, int lanes, float* __restrict__ part) {
+  __shared__ __align__(16) float s_x[WG_PIX][64];
+  __shared__ __align__(16) float s_g[WG_PIX][64];
   const int tap = blockIdx.y;
   const int r = tap / S, s = tap - r * S;
-  const int tcn = C / 4, tkn = K / 4;
+  const int tcn = C >> 3, tkn = K >> 3;
   const int per = tcn * tkn;
-  const int lanes = 256 / per;
   const int t = threadIdx.x % per;
   const int tc = t % tcn, tk = t / tcn;
   const int pl = threadIdx.x / per;
+  const int c4n = C >> 2, k4n = K >> 2;
   const long long npix = (long long)N * P * Q;
   const long long chunk = (npix + gridDim.x - 1) / gridDim.x;
   const long long p0 = (long long)blockIdx.x * chunk;
   const long long p1 = p0 + chunk < npix ? p0 + chunk : npix;
-  float acc[4][4];
+  float acc[8][8];
 #pragma unroll
-  for (int i = 0; i < 4; ++i)
+  for (int i = 0; i < 8; ++i)
 #pragma unroll
-    for (int j = 0; j < 4; ++j) acc[i][j] = 0.f;
+    for (int j = 0; j < 8; ++j) acc[i][j] = 0.f;
 
   for (long long base = p0; base < p1; base += WG_PIX) {
     const int cnt = (int)((p1 - base) < WG_PIX ? (p1 - base) : WG_PIX);
-    // stage x (shifted by the tap, zero outside the image) and g
-    for (int i = threadIdx.x; i < WG_PIX * tcn; i += 256) {
-      const int pp = i / tcn, c4 = i - pp * tcn;
+    for (int i = threadIdx.x; i < WG_PIX * c4n; i += 256) {
+      const int pp = i / c4n, c4 = i - pp * c4n;
       float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
       if (pp < cnt) {
         const long long pix = base + pp;
@@ -277,8 +275,8 @@ __global__ void __launch_bounds__(256) wgrad_kernel(const float* __restrict__ x,
       }
       *reinterpret_cast<float4*>(&s_x[pp][c4 * 4]) = v;
     }
-    for (int i = threadIdx.x; i < WG_PIX * tkn; i += 256) {
-      const int pp = i / tkn, k4 = i - pp * tkn;
+    for (int i = threadIdx.x; i < WG_PIX * k4n; i += 256) {
+      const int pp = i / k4n, k4 = i - pp * k4n;
       float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
       if (pp < cnt) v = __ldg(reinterpret_cast<const float4*>(g + (size_t)(base + pp) * K) + k4);
       *reinterpret_cast<float4*>(&s_g[pp][k4 * 4]) = v;
@@ -286,33 +284,44 @@ __global__ void __launch_bounds__(256) wgrad_kernel(const float* __restrict__ x,
     __syncthreads();
     if (pl < lanes) {
       for (int pp = pl; pp < WG_PIX; pp += lanes) {
-        const float4 xv = *reinterpret_cast<const float4*>(&s_x[pp][tc * 4]);
-        const float4 gv = *reinterpret_cast<const float4*>(&s_g[pp][tk * 4]);
-        const float xa[4] = {xv.x, xv.y, xv.z, xv.w};
-        const float ga[4] = {gv.x, gv.y, gv.z, gv.w};
+        const float4 x0 = *reinterpret_cast<const float4*>(&s_x[pp][tc * 8]);
+        const float4 x1 = *reinterpret_cast<const float4*>(&s_x[pp][tc * 8 + 4]);
+        const float4 g0 = *reinterpret_cast<const float4*>(&s_g[pp][tk * 8]);
+        const float4 g1 = *reinterpret_cast<const float4*>(&s_g[pp][tk * 8 + 4]);
+        const float xa[8] = {x0.x, x0.y, x0.z, x0.w, x1.x, x1.y, x1.z, x1.w};
+        const float ga[8] = {g0.x, g0.y, g0.z, g0.w, g1.x, g1.y, g1.z, g1.w};
 #pragma unroll
-        for (int i = 0; i < 4; ++i)
+        for (int i = 0; i < 8; ++i)
 #pragma unroll
-          for (int j = 0; j < 4; ++j) acc[i][j] = fmaf(xa[i], ga[j], acc[i][j]);
+          for (int j = 0; j < 8; ++j) acc[i][j] = fmaf(xa[i], ga[j], acc[i][j]);
       }
     }
     __syncthreads();
   }
+  // reduce the pixel lanes through shared memory (8 accumulators per round, fixed lane order) and
+  // write ONE partial [C x K] tile per CTA: part[chunk][tap][C][K]
+  float* red = &s_x[0][0];                       // 4096 floats >= lanes * per * 8
+  float* dst = part + (((size_t)blockIdx.x * gridDim.y + tap) * C) * K;
 #pragma unroll
-  for (int i = 0; i < 4; ++i)
+  for (int i = 0; i < 8; ++i) {
+    __syncthreads();
+    if (pl < lanes) {
+      float* w = red + ((size_t)pl * per + t) * 8;
+      *reinterpret_cast<float4*>(w) = make_float4(acc[i][0], acc[i][1], acc[i][2], acc[i][3]);
+      *reinterpret_cast<float4*>(w + 4) = make_float4(acc[i][4], acc[i][5], acc[i][6], acc[i][7]);
+    }
+    __syncthreads();
+    if (pl == 0) {
+      float tot[8];
 #pragma unroll
-    for (int j = 0; j < 4; ++j) s_red[threadIdx.x][i * 4 + j] = acc[i][j];
-  __syncthreads();
-  if (pl == 0) {
-    float* dst = part + (((size_t)blockIdx.x * gridDim.y + tap) * C) * K;
+      for (int j = 0; j < 8; ++j) tot[j] = red[(size_t)t * 8 + j];
+      for (int l = 1; l < lanes; ++l)
 #pragma unroll
-    for (int i = 0; i < 4; ++i)
-#pragma unroll
-      for (int j = 0; j < 4; ++j) {
-        float tot = s_red[threadIdx.x][i * 4 + j];
-        for (int l = 1; l < lanes; ++l) tot += s_red[l * per + threadIdx.x][i * 4 + j];
-        dst[(size_t)(tc * 4 + i) * K + tk * 4 + j] = tot;
-      }
+        for (int j = 0; j < 8; ++j) tot[j] += red[((size_t)l * per + t) * 8 + j];
+      float* row = dst + (size_t)(tc * 8 + i) * K + tk * 8;
+      *reinterpret_cast<float4*>(row) = make_float4(tot[0], tot[1], tot[2], tot[3]);
+      *reinterpret_cast<float4*>(row + 4) = make_float4(tot[4], tot[5], tot[6], tot[7]);
+    }
   }
 }
 
@@ -519,9 +528,14 @@ static int wgrad_chunks(const creste_conv_desc* d) {
   if (chunks > maxc) chunks = maxc;
   return (int)(chunks < 1 ? 1 : chunks);
 }
+static int wgrad_lanes(const creste_conv_desc* d) {
+  const int per = (d->C / 8) * (d->K / 8);
+  const int lanes = 256 / per;
+  return lanes > 64 ? 64 : lanes;                  // one pixel of the 64-pixel slab per lane at most
+}
 
 extern "C" size_t creste_conv2d_wgrad_workspace_bytes(const creste_conv_desc* d) {
-  if (!d) return 0;
+  if (!d || d->C < 8 || d->K < 8) return 0;
   return (size_t)wgrad_chunks(d) * d->R * d->S * d->C * d->K * sizeof(float);
 }
 
@@ -530,14 +544,14 @@ extern "C" int creste_conv2d_wgrad(const creste_conv_desc* d, const float* x, co
                                    void* ws, size_t ws_bytes, void* stream) {
   CRESTE_CHECK_ARG(d && x && g && dw_packed && ws, "creste_conv2d_wgrad: null pointer");
   CRESTE_CHECK_ARG(d->stride == 1, "creste_conv2d_wgrad: stride 1 only");
-  CRESTE_CHECK_ARG(d->C % 4 == 0 && d->K % 4 == 0 && d->C <= 64 && d->K <= 64 && d->C > 0 && d->K > 0,
-                   "creste_conv2d_wgrad: C, K must be multiples of 4 and <= 64 (got %d, %d)", d->C, d->K);
+  CRESTE_CHECK_ARG(d->C % 8 == 0 && d->K % 8 == 0 && d->C <= 64 && d->K <= 64 && d->C > 0 && d->K > 0,
+                   "creste_conv2d_wgrad: C, K must be multiples of 8 and <= 64 (got %d, %d)", d->C, d->K);
   CRESTE_CHECK_ARG(ws_bytes >= creste_conv2d_wgrad_workspace_bytes(d), "creste_conv2d_wgrad: workspace");
   cudaStream_t st = (cudaStream_t)stream;
-  const int chunks = wgrad_chunks(d);
+  const int chunks = wgrad_chunks(d), lanes = wgrad_lanes(d);
   dim3 grid(chunks, d->R * d->S);
   wgrad_kernel<<<grid, 256, 0, st>>>(x, g, d->N, d->H, d->W, d->C, d->K, d->R, d->S, d->pad_t, d->pad_l,
-                                     d->P, d->Q, (float*)ws);
+                                     d->P, d->Q, lanes, (float*)ws);
   int rc = launch_check("wgrad_kernel");
   if (rc) return rc;
   const int n = d->R * d->S * d->C * d->K;

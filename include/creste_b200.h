@@ -128,7 +128,11 @@ typedef struct {
   int out_nchw;         /* 0: out is NHWC [N,P,Q,K]; 1: out is NCHW [N,K,P,Q] */
   int precision;        /* 0: fp32 FFMA (exact fp32 products, CUDA cores);
                            1: 3xTF32 split on tcgen05 (fp32-faithful);
-                           2: single-pass TF32 on tcgen05; 3: single-pass BF16 on tcgen05 */
+                           2: single-pass TF32 on tcgen05; 3: reserved;
+                           4: 3xFP16 split on tcgen05 kind::f16 (fp32-faithful, default): fp16
+                              hi/lo operands under exact power-of-two scales (per tensor for the
+                              activations -- computed on the device --, per output channel for
+                              the weights) */
 } creste_conv_desc;
 
 /* w_packed: [R*S*C, K] row-major (k index = (r*S+s)*C + c); scale/shift [K] (folded BN / bias;
@@ -225,7 +229,7 @@ int creste_maxpool2_gather(const float* x, const float* gg, int N, int H, int W,
 int creste_upsample_adjoint(const float* g, int N, int Hi, int Wi, int C, int Ho, int Wo, float rh,
                             float rw, float* dx, void* stream);
 /* weight gradient of a stride-1 conv (autograd's convolution_backward, weight part):
- * x [N,H,W,C], g [N,P,Q,K] -> dw_packed [R*S*C, K]; C, K multiples of 4, <= 64. */
+ * x [N,H,W,C], g [N,P,Q,K] -> dw_packed [R*S*C, K]; C, K multiples of 8, <= 64. */
 size_t creste_conv2d_wgrad_workspace_bytes(const creste_conv_desc* d);
 int creste_conv2d_wgrad(const creste_conv_desc* d, const float* x, const float* g, float* dw_packed,
                         void* ws, size_t ws_bytes, void* stream);

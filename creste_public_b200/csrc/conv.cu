@@ -89,6 +89,90 @@ __global__ void __launch_bounds__(256) dwconv_kernel(const float* __restrict__ x
   }
 }
 
+// ---- x-blocked variant: a thread produces XB adjacent outputs of one row for its 4 channels and
+// loads each input column once per filter row ((XB-1)*STRIDE + R float4 loads for XB*R FMAs-by-4
+// instead of XB*R): the previous kernel issued 25 loads per 5x5 output and measured ~6x its HBM floor.
+// Same FMA order per output (taps in (r,s) raster order; out-of-image taps add an exact 0), same
+// fixed-order SE partial sums (per-thread sequential -> lanes in order -> one row per block).
+template <int R, int STRIDE, int XB>
+__global__ void __launch_bounds__(256) dwconv_xb_kernel(const float* __restrict__ x, const float* __restrict__ w,
+                                                        const float* __restrict__ scale,
+                                                        const float* __restrict__ shift, int N, int H, int W,
+                                                        int C, int pad_t, int pad_l, int P, int Q,
+                                                        float* __restrict__ out, float* __restrict__ chan_part) {
+  constexpr int NC = (XB - 1) * STRIDE + R;
+  __shared__ float4 s_part[256];
+  const int C4 = C / 4;
+  const int n = blockIdx.y;
+  const int Qb = (Q + XB - 1) / XB;
+  const int units = P * Qb;
+  const int per_block = ceil_div(units, (int)gridDim.x);
+  const int u0 = blockIdx.x * per_block;
+  const int u1 = min(u0 + per_block, units);
+  const int cg0 = blockIdx.z * 256;
+  const int cgs = min(C4 - cg0, 256);
+  const int lanes = 256 / cgs;
+  const int cg = cg0 + (threadIdx.x % cgs);
+  const int pl = threadIdx.x / cgs;
+  float4 sum = make_float4(0.f, 0.f, 0.f, 0.f);
+  if (pl < lanes) {
+    const float4 sc = __ldg(reinterpret_cast<const float4*>(scale) + cg);
+    const float4 sh = __ldg(reinterpret_cast<const float4*>(shift) + cg);
+    const float4* wv = reinterpret_cast<const float4*>(w) + cg;
+    const float4* xn = reinterpret_cast<const float4*>(x + (size_t)n * H * W * C) + cg;
+    for (int u = u0 + pl; u < u1; u += lanes) {
+      const int oy = u / Qb, ox0 = (u - oy * Qb) * XB;
+      const int iy0 = oy * STRIDE - pad_t, ix0 = ox0 * STRIDE - pad_l;
+      float4 acc[XB];
+#pragma unroll
+      for (int b = 0; b < XB; ++b) acc[b] = make_float4(0.f, 0.f, 0.f, 0.f);
+#pragma unroll
+      for (int r = 0; r < R; ++r) {
+        const int iy = iy0 + r;
+        if (iy < 0 || iy >= H) continue;
+        float4 col[NC];
+#pragma unroll
+        for (int c = 0; c < NC; ++c) {
+          const int ix = ix0 + c;
+          col[c] = (ix >= 0 && ix < W) ? __ldg(xn + ((size_t)iy * W + ix) * C4) : make_float4(0.f, 0.f, 0.f, 0.f);
+        }
+#pragma unroll
+        for (int s = 0; s < R; ++s) {
+          const float4 k = __ldg(wv + (size_t)(r * R + s) * C4);
+#pragma unroll
+          for (int b = 0; b < XB; ++b) {
+            const float4 v = col[b * STRIDE + s];
+            acc[b].x = fmaf(v.x, k.x, acc[b].x); acc[b].y = fmaf(v.y, k.y, acc[b].y);
+            acc[b].z = fmaf(v.z, k.z, acc[b].z); acc[b].w = fmaf(v.w, k.w, acc[b].w);
+          }
+        }
+      }
+#pragma unroll
+      for (int b = 0; b < XB; ++b) {
+        if (ox0 + b < Q) {
+          float4 o;
+          o.x = fmaf(acc[b].x, sc.x, sh.x); o.y = fmaf(acc[b].y, sc.y, sh.y);
+          o.z = fmaf(acc[b].z, sc.z, sh.z); o.w = fmaf(acc[b].w, sc.w, sh.w);
+          o.x = o.x / (1.0f + expf(-o.x)); o.y = o.y / (1.0f + expf(-o.y));
+          o.z = o.z / (1.0f + expf(-o.z)); o.w = o.w / (1.0f + expf(-o.w));
+          reinterpret_cast<float4*>(out + (((size_t)n * P + oy) * Q + ox0 + b) * C)[cg] = o;
+          sum.x += o.x; sum.y += o.y; sum.z += o.z; sum.w += o.w;
+        }
+      }
+    }
+  }
+  s_part[threadIdx.x] = sum;
+  __syncthreads();
+  if (pl == 0 && threadIdx.x < cgs) {
+    float4 tot = s_part[threadIdx.x];
+    for (int l = 1; l < lanes; ++l) {
+      const float4 o = s_part[l * cgs + threadIdx.x];
+      tot.x += o.x; tot.y += o.y; tot.z += o.z; tot.w += o.w;
+    }
+    reinterpret_cast<float4*>(chan_part + ((size_t)n * gridDim.x + blockIdx.x) * C)[cg] = tot;
+  }
+}
+
 // ---- SE gate: one block per image
 __global__ void __launch_bounds__(1024) se_gate_kernel(const float* __restrict__ chan_part, int nparts,
                                                       float inv_hw, int C, int Csq,
@@ -187,7 +271,15 @@ extern "C" int creste_dwconv_bn_swish(const float* x, const float* w, const floa
   CRESTE_CHECK_ARG(nparts == creste_dwconv_num_parts(N, P, Q), "creste_dwconv_bn_swish: nparts");
   cudaStream_t st = (cudaStream_t)stream;
   dim3 grid(nparts, N, ceil_div(C / 4, 256));
-  if (R == 3)
+  if (stride == 1 && R == 3)
+    dwconv_xb_kernel<3, 1, 4><<<grid, 256, 0, st>>>(x, w, scale, shift, N, H, W, C, pad_t, pad_l, P, Q, out, chan_part);
+  else if (stride == 1 && R == 5)
+    dwconv_xb_kernel<5, 1, 4><<<grid, 256, 0, st>>>(x, w, scale, shift, N, H, W, C, pad_t, pad_l, P, Q, out, chan_part);
+  else if (stride == 2 && R == 3)
+    dwconv_xb_kernel<3, 2, 4><<<grid, 256, 0, st>>>(x, w, scale, shift, N, H, W, C, pad_t, pad_l, P, Q, out, chan_part);
+  else if (stride == 2 && R == 5)
+    dwconv_xb_kernel<5, 2, 4><<<grid, 256, 0, st>>>(x, w, scale, shift, N, H, W, C, pad_t, pad_l, P, Q, out, chan_part);
+  else if (R == 3)
     dwconv_kernel<3><<<grid, 256, 0, st>>>(x, w, scale, shift, N, H, W, C, stride, pad_t, pad_l, P, Q, out, chan_part);
   else
     dwconv_kernel<5><<<grid, 256, 0, st>>>(x, w, scale, shift, N, H, W, C, stride, pad_t, pad_l, P, Q, out, chan_part);

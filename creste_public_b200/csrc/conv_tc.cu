@@ -252,7 +252,7 @@ __host__ __device__ constexpr uint32_t make_idesc_f16(int n, int m = 128) {
 struct TcParams {
   const float* scale; const float* shift; const float* residual; float* out;
   int N, P, Q, K;              // output NHWC [N,P,Q,K]
-  int R, S, pad_t, pad_l;
+  int R, S, pad_t, pad_l, stride;
   int cblocks;                 // ceil(C / 32)
   int wbox, hbox, tiles_x, tiles_y;
   int block_n, act, split;     // split: 1 = 3xTF32 (hi/lo operands), 0 = single TF32
@@ -343,7 +343,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_consta
         const int tap = kb / p.cblocks;
         const int r = tap / p.S, s = tap - r * p.S;
         uint8_t* st = smem + (size_t)stage * stage_bytes;
-        const int cx = x0 + s - p.pad_l, cy = y0 + r - p.pad_t;
+        const int cx = x0 * p.stride + s - p.pad_l, cy = y0 * p.stride + r - p.pad_t;
         uint8_t* b_hi = st + nops * A_TILE_BYTES;
         uint8_t* b_lo = b_hi + b_tile_bytes;
         const int nrow = n0 + (int)rank * b_rows;
@@ -593,15 +593,17 @@ static EncodeTiledFn get_encode() {
   return fn;
 }
 
+// stride > 1: the box spans (wbox-1)*stride+1 input columns and TMA's element strides pick every
+// stride-th pixel, so the tile still lands as wbox x hbox rows of 128 bytes
 static int make_map_a(CUtensorMap* m, const void* base, int N, int H, int W, int C, int wbox, int hbox,
-                      bool f16 = false) {
+                      bool f16 = false, int stride = 1) {
   EncodeTiledFn enc = get_encode();
   if (!enc) { set_error("cuTensorMapEncodeTiled unavailable"); return CRESTE_ERR_NO_DEVICE; }
   const cuuint64_t eb = f16 ? 2 : 4;
   cuuint64_t dims[4] = {(cuuint64_t)C, (cuuint64_t)W, (cuuint64_t)H, (cuuint64_t)N};
   cuuint64_t strides[3] = {(cuuint64_t)C * eb, (cuuint64_t)W * C * eb, (cuuint64_t)H * W * C * eb};
-  cuuint32_t box[4] = {f16 ? 64u : 32u, (cuuint32_t)wbox, (cuuint32_t)hbox, 1};
-  cuuint32_t es[4] = {1, 1, 1, 1};
+  cuuint32_t box[4] = {f16 ? 64u : 32u, (cuuint32_t)((wbox - 1) * stride + 1), (cuuint32_t)((hbox - 1) * stride + 1), 1};
+  cuuint32_t es[4] = {1, (cuuint32_t)stride, (cuuint32_t)stride, 1};
   CUresult r = enc(m, f16 ? CU_TENSOR_MAP_DATA_TYPE_FLOAT16 : CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 4, (void*)base, dims, strides, box, es,
                    CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B,
                    CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
@@ -648,9 +650,9 @@ static void pick_box(int P, int Q, int* wbox, int* hbox) {
 
 bool conv_tc_supported(const creste_conv_desc* d) {
   if (d->precision != 1 && d->precision != 2 && d->precision != 4) return false;
-  if (d->stride != 1 || d->C % 4 != 0 || d->K < 8) return false;
+  if ((d->stride != 1 && d->stride != 2) || d->C % 4 != 0 || d->K < 8) return false;
   if (d->precision == 4 && d->C % 8 != 0) return false;     // fp16 rows must be 16-byte multiples (TMA)
-  if (d->R > 5 || d->S > 5) return false;
+  if (d->R > 7 || d->S > 7) return false;
   if ((long long)d->N * d->P * d->Q < 128) return false;
   return true;
 }
@@ -717,7 +719,7 @@ int conv_tc_launch(const creste_conv_desc* d, const float* x, const float* w_pac
   TcParams p;
   p.scale = scale; p.shift = shift; p.residual = residual; p.out = out;
   p.N = d->N; p.P = d->P; p.Q = d->Q; p.K = d->K;
-  p.R = d->R; p.S = d->S; p.pad_t = d->pad_t; p.pad_l = d->pad_l;
+  p.R = d->R; p.S = d->S; p.pad_t = d->pad_t; p.pad_l = d->pad_l; p.stride = d->stride;
   p.cblocks = cpad / 32;
   pick_box(d->P, d->Q, &p.wbox, &p.hbox);
   p.tiles_x = ceil_div(d->Q, p.wbox);
@@ -730,8 +732,8 @@ int conv_tc_launch(const creste_conv_desc* d, const float* x, const float* w_pac
   p.cl = cl;
   CUtensorMap ma_hi, ma_lo, mb_hi, mb_lo;
   int rc;
-  if ((rc = make_map_a(&ma_hi, x_hi, d->N, d->H, d->W, d->C, p.wbox, p.hbox, f16))) return rc;
-  if ((rc = make_map_a(&ma_lo, split ? x_lo : x_hi, d->N, d->H, d->W, d->C, p.wbox, p.hbox, f16))) return rc;
+  if ((rc = make_map_a(&ma_hi, x_hi, d->N, d->H, d->W, d->C, p.wbox, p.hbox, f16, d->stride))) return rc;
+  if ((rc = make_map_a(&ma_lo, split ? x_lo : x_hi, d->N, d->H, d->W, d->C, p.wbox, p.hbox, f16, d->stride))) return rc;
   // packed weights: [hi][lo] (fp32 words for tf32; fp16 halves for 3xFP16, followed by w_inv[npad] fp32)
   const size_t wel = (size_t)npad * ktot;
   const void* w_hi = w_packed;

@@ -592,7 +592,7 @@ __device__ __forceinline__ bool vi_mbar_test(uint64_t* bar, uint32_t parity) {
 }
 
 template <int RT>
-__global__ void __launch_bounds__(RT <= 3 ? 640 : 544, 1) vi_strip_kernel(ViStripParams p) {
+__global__ void __launch_bounds__(RT <= 2 ? 640 : 544, 1) vi_strip_kernel(ViStripParams p) {
   // two X tiles [(R+2)][W+8] (interior col x at 4+x), then two v snapshots [R][W]
   extern __shared__ __align__(16) float sm[];
   __shared__ uint64_t s_mbar[2];
@@ -976,7 +976,7 @@ extern "C" int creste_vi_solve(const float* r, float* v_out, float* q_out, float
       if ((c - 1) * R >= H) continue;                 // every strip needs at least one row
       int RT = 0;
       for (int t = 1; t <= 4; ++t)
-        if ((long long)cgn * ceil_div(R, t) <= (t <= 3 ? 608 : 512)) { RT = t; break; }
+        if ((long long)cgn * ceil_div(R, t) <= (t <= 2 ? 608 : 512)) { RT = t; break; }
       if (!RT) continue;
       int threads = cgn * ceil_div(R, RT);
       threads = (threads + 31) / 32 * 32;

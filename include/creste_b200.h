@@ -142,7 +142,7 @@ int creste_conv2d(const creste_conv_desc* d, const float* x, const float* w_pack
                   const float* scale, const float* shift, const float* gate, const float* residual,
                   float* out, void* ws, size_t ws_bytes, void* stream);
 size_t creste_conv2d_workspace_bytes(const creste_conv_desc* d);
-/* tcgen05 path (precision 1, 2): 1 if the shape is served by the tensor-core kernel (stride 1,
+/* tcgen05 path (precision 1, 2): 1 if the shape is served by the tensor-core kernel (stride 1 or 2, R, S <= 7,
  * C % 4 == 0, K >= 8, >= 128 output pixels), else the caller must use precision 0.  For those
  * modes w_packed is [Npad][R*S*Cpad] fp32 pre-rounded to tf32 ("hi"), followed for precision 1
  * by the same-shaped "lo" = rna_tf32(w - hi); creste_conv2d_tc_layout reports Npad (K rounded up

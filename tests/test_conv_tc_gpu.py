@@ -64,6 +64,29 @@ def test_conv_tc_matches_torch(cuda, case, mode, tol):
     assert err <= tol * float(ref.abs().max()), f"err {err:.3e} vs max {float(ref.abs().max()):.3e}"
 
 
+@pytest.mark.parametrize("mode", ["3xtf32", "3xfp16"])
+@pytest.mark.parametrize("case", [
+    # N, C, H, W, K, R, pad (t, b, l, r)
+    (2, 96, 32, 48, 64, 7, (3, 3, 3, 3)),       # BEV stem: conv7x7 s2 p3 (inpainting.py:80-90)
+    (1, 64, 33, 41, 32, 3, (0, 1, 0, 1)),       # TF-"SAME" static padding, odd size
+    (1, 128, 32, 32, 128, 1, (0, 0, 0, 0)),     # 1x1 s2 (ResNet downsample)
+])
+def test_conv_tc_stride2(cuda, case, mode):
+    """stride-2 convs on the tensor-core kernel: TMA element strides pick every 2nd pixel of the box"""
+    from creste_public_b200 import ops
+    N, C, H, W, K, R, pad = case
+    g = torch.Generator().manual_seed(R + C)
+    x = torch.randn(N, C, H, W, generator=g)
+    w = torch.randn(K, C, R, R, generator=g) / (C * R * R) ** 0.5
+    ref = F.conv2d(F.pad(x, (pad[2], pad[3], pad[0], pad[1])), w, stride=2)
+    assert ops.tc_supported((N, H, W, C), K, R, R, 2, pad, mode)
+    wp = ops.pack_conv_weight_f16(w.to(cuda)) if mode == "3xfp16" else ops.pack_conv_weight_tc(w.to(cuda), split=True)
+    out = ops.conv2d(x.to(cuda).permute(0, 2, 3, 1).contiguous(), wp, K, R, R, 2, pad, precision=mode)
+    out = out.cpu().permute(0, 3, 1, 2)
+    assert out.shape == ref.shape
+    assert float((out - ref).abs().max()) <= 3e-5 * float(ref.abs().max())
+
+
 @pytest.mark.parametrize("xs,ws", [(1e-4, 1.0), (3e3, 1e-3), (1.0, 50.0)])
 def test_conv_3xfp16_dynamic_range(cuda, xs, ws):
     """3xFP16 (precision 4): fp16 hi/lo operands under power-of-two scales (per tensor for the
@@ -95,7 +118,7 @@ def test_conv_3xfp16_zero_input(cuda):
 
 def test_tc_unsupported_shapes_are_refused(cuda):
     from creste_public_b200 import ops
-    assert not ops.tc_supported((1, 32, 32, 4), 32, 3, 3, 2, (0, 1, 0, 1), "3xtf32")   # strided stem
+    assert not ops.tc_supported((1, 32, 32, 4), 32, 3, 3, 2, (0, 1, 0, 1), "3xfp16")   # C = 4 stem
     assert not ops.tc_supported((1, 32, 32, 128), 6, 1, 1, 1, (0, 0, 0, 0), "3xtf32")   # K = 6 head
     x = torch.randn(1, 16, 16, 64, device=cuda)
     w = ops.pack_conv_weight(torch.randn(6, 64, 1, 1, device=cuda))

@@ -335,7 +335,11 @@ def run_ours(args):
         ach = flops / (kms / 1e3) / 1e12
         roof = {"kernel": "conv3x3 496->496 @128x240 (effnet up3.conv.3), precision=" + args.precision,
                 "bound": "tensor", "achieved": ach, "peak": peaks["bf16_sustained"], "unit": "TFLOP/s",
-                "frac": ach / peaks["bf16_sustained"], "traffic": None,
+                "frac": ach / peaks["bf16_sustained"],
+                # dram__bytes_read.sum + dram__bytes_write.sum of this launch from the committed
+                # `ncu --set full` capture (profiles/r1b_up3_conv_f16_full.md: B = 8, 3xfp16)
+                "traffic": 1.452e9 if (B == 8 and args.precision == "3xfp16") else None,
+                "algorithmic_bytes": B * 128 * 240 * 496 * (2 * 2 + 4),
                 "peak_source": peaks["src"] + " bf16 sustained (cuBLAS)", "kernel_ms": kms,
                 "step_flop_share": round(136.04 / GFLOP_PER_FRAME, 3)}
         del xin
@@ -375,6 +379,36 @@ def run_ours(args):
                                  "reward FCN + double backward, C-oracle VI/SVF), all host threads",
                        "ms_per_sample": ms_irl_cpu}
 
+    # ---- B = 1 latency (the robot's operating point): eager launches vs one CUDA-graph replay
+    latency = None
+    if rank == 0:
+        from creste_public_b200.engine import GraphedForward
+        x1 = dev_rgbd[0][:1].contiguous()
+        p1 = dev_p2p[:1].contiguous()
+        with torch.no_grad():
+            for _ in range(3):
+                model((x1, p1))
+        def _time(fn, n=20):
+            a, b_ = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            torch.cuda.synchronize()
+            t0 = time.perf_counter()
+            a.record()
+            for _ in range(n):
+                fn()
+            b_.record()
+            torch.cuda.synchronize()
+            return a.elapsed_time(b_) / n, (time.perf_counter() - t0) / n * 1e3
+        with torch.no_grad():
+            eager_ms, eager_wall = _time(lambda: model((x1, p1)))
+        try:
+            gf = GraphedForward(lambda x, p: model((x, p)), (x1, p1))
+            graph_ms, graph_wall = _time(lambda: gf(x1, p1))
+        except Exception as e:  # noqa: BLE001
+            graph_ms, graph_wall = None, repr(e)[:200]
+        latency = {"workload": "one 512x960 frame, full output dict, inputs resident",
+                   "eager_ms": eager_ms, "eager_wall_ms": eager_wall,
+                   "cuda_graph_ms": graph_ms, "cuda_graph_wall_ms": graph_wall}
+
     # ---- second headline metric: counterfactual-IRL head-only training steps/s at 256x256,
     # B = 8 per GPU (configs[3] shard; the step all-reduces the flat gradient over NCCL when N > 1)
     irl = run_irl_steps(args, dev, rank, world, barrier)
@@ -399,6 +433,7 @@ def run_ours(args):
                     "d2h_bytes_per_step": d2h, "ms_per_step": ms_e2e / args.steps},
             "gpu_launches": int(launches),
             "clocks": clocks, "roofline": roof, "cpu_baseline": cpu, "irl": irl,
+            "latency_b1": latency,
             "achieved_tflops_whole_step": GFLOP_PER_FRAME * 1e9 * value / world / 1e12,
         }
         print(json.dumps(line))

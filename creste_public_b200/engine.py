@@ -122,3 +122,35 @@ class FusedConv:
         w, scale, shift = self.packed(mode)
         return ops.conv2d(x_nhwc, w, K, R, S, stride, pad, scale, shift, gate, residual, act,
                           out_nchw, mode)
+
+
+class GraphedForward:
+    """CUDA-graph replay of an eval-mode forward with static input shapes.
+
+    The per-frame path is ~230 kernel launches (+ the ctypes / allocator work around each); at
+    B = 1 that host work, not the GPU, bounds the latency.  Capturing the whole forward once and
+    replaying it removes it: every launch of libcreste_b200 goes to torch's current stream, all
+    scratch comes from torch's capture-aware allocator, packed weights / tensor maps are captured
+    by value, and the forward contains no host synchronisation (solve_mdp=False).
+
+        g = GraphedForward(lambda rgbd, p2p: model((rgbd, p2p)), (rgbd, p2p))
+        out = g(rgbd_next, p2p_next)        # dict of tensors, overwritten by the next call
+    """
+
+    def __init__(self, fn, example_inputs, warmup=3):
+        self.static_in = [t.clone() for t in example_inputs]
+        side = torch.cuda.Stream()
+        side.wait_stream(torch.cuda.current_stream())
+        with torch.cuda.stream(side), torch.no_grad():
+            for _ in range(warmup):                       # fills the pack caches, sets kernel attributes
+                fn(*self.static_in)
+        torch.cuda.current_stream().wait_stream(side)
+        self.graph = torch.cuda.CUDAGraph()
+        with torch.no_grad(), torch.cuda.graph(self.graph):
+            self.static_out = fn(*self.static_in)
+
+    def __call__(self, *inputs):
+        for dst, src in zip(self.static_in, inputs):
+            dst.copy_(src, non_blocking=True)
+        self.graph.replay()
+        return self.static_out

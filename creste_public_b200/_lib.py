@@ -30,7 +30,7 @@ EXPORTS = [
     "creste_conv2d_wgrad_workspace_bytes", "creste_conv2d_wgrad",
     "creste_row_dot", "creste_row_scale", "creste_row_normalize",
     "creste_grad_penalty_workspace_bytes", "creste_grad_penalty", "creste_grad_penalty_bwd",
-    "creste_adam_step",
+    "creste_adam_step", "creste_stage1_depth_losses", "creste_masked_mse",
 ]
 
 

@@ -5,7 +5,8 @@ The per-sample reductions, normalisations, the visitation rasters and the SMODIC
 penalty run on the sm_100a kernels (creste_row_*, creste_expert_visitation,
 creste_grad_penalty); the differentiable pieces are creste_public_b200.autograd Functions, so
 `loss.backward()` reaches the reward-FCN weights through the first- and second-order graph
-exactly as in the reference.  Other reference losses (stage 1 / stage 2) are not mirrored here.
+exactly as in the reference.  The stage-1 losses (CrossEntropyDepth, SmoothL1Depth, MSELoss) are
+mirrored as validation-time VALUES only (one fused kernel pass); stage-2 losses are not mirrored.
 """
 import numpy as np
 import torch
@@ -66,6 +67,73 @@ class LossManager(nn.Module):
         if config["name"] not in globals():
             raise NotImplementedError(f"loss {config['name']} is outside the stage-3 hot path")
         return globals()[config["name"]](config)
+
+
+class _Stage1DepthValues:
+    """CrossEntropyDepth and SmoothL1Depth share one kernel pass; the result is cached per
+    (logits, label) pair so that the two Loss objects of the shipped config cost one launch."""
+    _key, _val = None, None
+
+    @classmethod
+    def get(cls, tensor_dict, discretize, beta):
+        logits = tensor_dict["outputs/depth_preds_logits"]
+        bins = tensor_dict["outputs/depth_preds_bins"]
+        label = tensor_dict["inputs/depth_label"]
+        key = (logits.data_ptr(), label.data_ptr(), logits._version, float(beta))
+        if cls._key != key:
+            if discretize["mode"] != "UD":
+                raise NotImplementedError("bin_depths modes other than 'UD' are unused by the shipped configs")
+            B, S, H, W = label.shape
+            if logits.shape[0] != B * S or tuple(logits.shape[-2:]) != (H, W):
+                raise NotImplementedError("multi-frame / resized depth labels are outside the hot path")
+            cls._val = ops.stage1_depth_losses(logits, bins.reshape(B * S, H * W),
+                                               label.reshape(B * S, H * W).to(logits.device),
+                                               discretize["depth_min"], discretize["depth_max"], beta)
+            cls._key = key
+        return cls._val
+
+
+class CrossEntropyDepth(Loss):
+    """Validation-time VALUE of reference loss_utils.py:477-527 (no gradient: training the backbone
+    is not implemented).  Returns depth/cls_loss and the depth/acc meta value."""
+
+    def __init__(self, config):
+        super().__init__(config.name if hasattr(config, "name") else config["name"], config)
+
+    def loss(self, tensor_dict):
+        acc = _Stage1DepthValues.get(tensor_dict, self.config["discretize"], 0.5)
+        return {"depth/cls_loss": (acc[0] / acc[1]).float()}, {"depth/acc": (acc[2] / acc[1]).float()}
+
+
+class SmoothL1Depth(Loss):
+    """Validation-time value of reference loss_utils.py:530-573; pred_key is depth_preds_bins in
+    the shipped config (class indices compared with metres, as the reference does)."""
+
+    def __init__(self, config):
+        super().__init__(config.name if hasattr(config, "name") else config["name"], config)
+        self.beta = config["beta"]
+
+    def loss(self, tensor_dict):
+        if self.config["pred_key"] != "outputs/depth_preds_bins":
+            raise NotImplementedError("SmoothL1Depth is wired to depth_preds_bins in the shipped configs")
+        acc = _Stage1DepthValues.get(tensor_dict, self.config["discretize"], self.beta)
+        return {"depth/reg_loss": (acc[3] / acc[1]).float()}, {}
+
+
+class MSELoss(Loss):
+    """Validation-time value of reference loss_utils.py:606-647 (overlap_only = False)."""
+
+    def __init__(self, config):
+        super().__init__(config.name if hasattr(config, "name") else config["name"], config)
+        self.pred_key, self.lab_key = config["pred_key"], config["lab_key"]
+        if config.get("overlap_only", False):
+            raise NotImplementedError("MSELoss(overlap_only=True) is unused by the shipped configs")
+
+    def loss(self, tensor_dict):
+        pred, gt = tensor_dict[self.pred_key], tensor_dict[self.lab_key]
+        assert pred.shape == gt.shape, (pred.shape, gt.shape)
+        acc = ops.masked_mse(pred, gt.to(pred.device))
+        return {"loss": (acc[0] / acc[1]).float()}, {}
 
 
 class MaxEntIRLLoss(Loss):

@@ -622,3 +622,109 @@ extern "C" int creste_adam_step(float* p, const float* g, float* m, float* v, lo
       p, g, m, v, n, b1, b2, eps, (float)((double)lr / bc1), (float)(1.0 / sqrt(bc2)), grad_scale);
   return launch_check("adam_kernel");
 }
+
+// ------------------------------------------------------------------ stage-1 loss values (eval)
+// CrossEntropyDepth + SmoothL1Depth forward values in ONE pass over the depth logits
+// (reference creste/utils/loss_utils.py:477-573, bin_depths creste/utils/depth_utils.py:346-383,
+// mode "UD").  One thread per pixel, coalesced across pixels for every class plane of the NCHW
+// logits.  acc[0] = sum of -log_softmax(logits)[gt_bin] over valid pixels, acc[1] = #valid,
+// acc[2] = #(argmax == gt_bin), acc[3] = sum of smooth_l1(pred_bins - label_m) over valid pixels.
+namespace creste {
+__global__ void __launch_bounds__(256) stage1_depth_loss_kernel(const float* __restrict__ logits,
+                                                                const long long* __restrict__ pred_bins,
+                                                                const float* __restrict__ label_mm, int N,
+                                                                int D, long long HW, float dmin, float bin_size,
+                                                                float beta, double* __restrict__ acc) {
+  __shared__ double s_red[4][8];
+  double ce = 0.0, nv = 0.0, nc = 0.0, sl = 0.0;
+  const long long total = (long long)N * HW;
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total;
+       i += (long long)gridDim.x * blockDim.x) {
+    const long long n = i / HW, p = i - n * HW;
+    const float d = __ldg(label_mm + i);
+    const float idxf = __fdiv_rn(__fsub_rn(d, dmin), bin_size);
+    const bool bad = (idxf < 0.0f) || (idxf > (float)D) || !isfinite(idxf);
+    const long long bin = bad ? (long long)D : (long long)idxf;        // truncation, as .type(int64)
+    if (bin == D) continue;
+    const float* src = logits + (size_t)n * D * HW + p;
+    float m = -INFINITY;
+    int am = 0;
+    for (int k = 0; k < D; ++k) {
+      const float v = __ldg(src + (size_t)k * HW);
+      if (v > m) { m = v; am = k; }
+    }
+    float ssum = 0.f;
+    for (int k = 0; k < D; ++k) ssum += expf(__ldg(src + (size_t)k * HW) - m);
+    ce += (double)(logf(ssum) + m - __ldg(src + (size_t)bin * HW));
+    nv += 1.0;
+    nc += (am == (int)bin) ? 1.0 : 0.0;
+    const float diff = fabsf((float)__ldg(pred_bins + i) - d / 1000.0f);
+    sl += (double)(diff < beta ? 0.5f * diff * diff / beta : diff - 0.5f * beta);
+  }
+  double vals[4] = {ce, nv, nc, sl};
+#pragma unroll
+  for (int j = 0; j < 4; ++j) {
+    double v = vals[j];
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+    if ((threadIdx.x & 31) == 0) s_red[j][threadIdx.x >> 5] = v;
+  }
+  __syncthreads();
+  if (threadIdx.x < 4) {
+    double t = 0.0;
+    for (int w = 0; w < 8; ++w) t += s_red[threadIdx.x][w];
+    atomicAdd(acc + threadIdx.x, t);
+  }
+}
+
+// acc[0] = sum (pred - gt)^2 over elements with !isinf(gt), acc[1] = their count (MSELoss, :606-647)
+__global__ void __launch_bounds__(256) masked_mse_kernel(const float* __restrict__ pred,
+                                                         const float* __restrict__ gt, long long n,
+                                                         double* __restrict__ acc) {
+  __shared__ double s_red[2][8];
+  double ss = 0.0, cnt = 0.0;
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n;
+       i += (long long)gridDim.x * blockDim.x) {
+    const float g = __ldg(gt + i);
+    if (isinf(g)) continue;
+    const float d = __ldg(pred + i) - g;
+    ss += (double)d * (double)d;
+    cnt += 1.0;
+  }
+  double vals[2] = {ss, cnt};
+#pragma unroll
+  for (int j = 0; j < 2; ++j) {
+    double v = vals[j];
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+    if ((threadIdx.x & 31) == 0) s_red[j][threadIdx.x >> 5] = v;
+  }
+  __syncthreads();
+  if (threadIdx.x < 2) {
+    double t = 0.0;
+    for (int w = 0; w < 8; ++w) t += s_red[threadIdx.x][w];
+    atomicAdd(acc + threadIdx.x, t);
+  }
+}
+}  // namespace creste
+
+extern "C" int creste_stage1_depth_losses(const float* logits_nchw, const long long* pred_bins,
+                                          const float* label_mm, int N, int D, long long HW, float depth_min,
+                                          float depth_max, float beta, double* acc4, void* stream) {
+  CRESTE_CHECK_ARG(logits_nchw && pred_bins && label_mm && acc4 && N > 0 && D > 0 && HW > 0 && beta > 0,
+                   "creste_stage1_depth_losses: bad args");
+  cudaStream_t st = (cudaStream_t)stream;
+  CRESTE_CUDA(cudaMemsetAsync(acc4, 0, 4 * sizeof(double), st));
+  const float bin_size = (float)(((double)depth_max - (double)depth_min) / (double)D);
+  stage1_depth_loss_kernel<<<grid_cap((long long)N * HW, 256, 148 * 8), 256, 0, st>>>(
+      logits_nchw, pred_bins, label_mm, N, D, HW, depth_min, bin_size, beta, acc4);
+  return launch_check("stage1_depth_loss_kernel");
+}
+
+extern "C" int creste_masked_mse(const float* pred, const float* gt, long long n, double* acc2, void* stream) {
+  CRESTE_CHECK_ARG(pred && gt && acc2 && n > 0, "creste_masked_mse: bad args");
+  cudaStream_t st = (cudaStream_t)stream;
+  CRESTE_CUDA(cudaMemsetAsync(acc2, 0, 2 * sizeof(double), st));
+  masked_mse_kernel<<<grid_cap(n, 256, 148 * 8), 256, 0, st>>>(pred, gt, n, acc2);
+  return launch_check("masked_mse_kernel");
+}

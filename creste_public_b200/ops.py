@@ -474,3 +474,28 @@ def adam_step(p, g, m, v, lr, beta1, beta2, eps, step, grad_scale=1.0):
     check(lib().creste_adam_step(ptr(p), ptr(g), ptr(m), ptr(v), C.c_longlong(p.numel()),
                                  C.c_float(lr), C.c_float(beta1), C.c_float(beta2), C.c_float(eps),
                                  int(step), C.c_float(grad_scale), stream()), "creste_adam_step")
+
+
+def stage1_depth_losses(logits_nchw, pred_bins, label_mm, depth_min, depth_max, beta):
+    """-> float64[4] device tensor {sum CE, #valid, #correct, sum smooth-L1} (stage-1 validation)."""
+    logits = logits_nchw.contiguous().float()
+    N, D = logits.shape[0], logits.shape[1]
+    HW = logits.numel() // (N * D)
+    bins = pred_bins.contiguous().to(torch.int64)
+    lab = label_mm.contiguous().float()
+    assert bins.numel() == N * HW and lab.numel() == N * HW
+    acc = torch.empty(4, dtype=torch.float64, device=logits.device)
+    check(lib().creste_stage1_depth_losses(ptr(logits), ptr(bins), ptr(lab), N, D, C.c_longlong(HW),
+                                           C.c_float(depth_min), C.c_float(depth_max), C.c_float(beta),
+                                           ptr(acc), stream()), "creste_stage1_depth_losses")
+    return acc
+
+
+def masked_mse(pred, gt):
+    """-> float64[2] device tensor {sum of squared differences where gt is not +-inf, count}."""
+    pred, gt = pred.contiguous().float(), gt.contiguous().float()
+    assert pred.numel() == gt.numel()
+    acc = torch.empty(2, dtype=torch.float64, device=pred.device)
+    check(lib().creste_masked_mse(ptr(pred), ptr(gt), C.c_longlong(pred.numel()), ptr(acc), stream()),
+          "creste_masked_mse")
+    return acc

@@ -254,6 +254,19 @@ int creste_grad_penalty_bwd(const float* G, const float* g_scalar, int B, int C,
 int creste_adam_step(float* p, const float* g, float* m, float* v, long long n, float lr, float b1,
                      float b2, float eps, int step, float grad_scale, void* stream);
 
+/* Stage-1 loss VALUES for validation (forward only; backbone training is not implemented):
+ * CrossEntropyDepth + SmoothL1Depth (creste/utils/loss_utils.py:477-573 with bin_depths mode "UD",
+ * creste/utils/depth_utils.py:346-383) in one pass over the NCHW depth logits.
+ *   logits [N,D,HW]; pred_bins int64 [N,HW] (depth_preds_bins: what the shipped config feeds the
+ *   Smooth-L1 term); label_mm [N,HW]; acc4 DEVICE double[4] = {sum CE over valid pixels, #valid,
+ *   #(argmax == gt bin), sum smooth_l1(pred_bins - label/1000)}. */
+int creste_stage1_depth_losses(const float* logits_nchw, const long long* pred_bins,
+                               const float* label_mm, int N, int D, long long HW, float depth_min,
+                               float depth_max, float beta, double* acc4, void* stream);
+/* MSELoss on the DINO feature targets (loss_utils.py:606-647, overlap_only = False):
+ * acc2 DEVICE double[2] = {sum (pred-gt)^2 over elements with !isinf(gt), their count}. */
+int creste_masked_mse(const float* pred, const float* gt, long long n, double* acc2, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -35,6 +35,24 @@ def irl_step_golden():
     np.savez_compressed(os.path.join(OUT, "irl_step.npz"), **d)
 
 
+def stage1_loss_golden():
+    mods = rh.ref_modules()
+    from omegaconf import OmegaConf
+    cfgs = rh.compose_cfgs()
+    lu = mods["loss_utils"]
+    logits, label, pred, gt = [torch.from_numpy(a) for a in synth.stage1_loss_inputs()]
+    td = {"outputs/depth_preds_logits": logits, "outputs/depth_preds_bins": logits.argmax(1),
+          "inputs/depth_label": label, "outputs/dino_pe_feats": pred, "inputs/fimg_label": gt}
+    out = {}
+    for lc in cfgs["distill"]["loss"]:
+        L = getattr(lu, lc["name"])(OmegaConf.create(lc))
+        ld, md = L.loss(td)
+        out.update({f"{lc['name']}/{k}": np.float32(v.item()) for k, v in ld.items()})
+        out.update({f"{lc['name']}/{k}": np.float32(v.item()) for k, v in md.items()})
+    np.savez_compressed(os.path.join(OUT, "stage1_losses.npz"), **out)
+    return out
+
+
 def main():
     os.makedirs(OUT, exist_ok=True)
     mods = rh.ref_modules()
@@ -138,6 +156,7 @@ def main():
     # ---- stage-3 training step: reward FCN (train-mode BN) + MaxEntIRLLoss incl. the double
     # backward of the gradient penalty + Adam (train_traversability.py:62-103)
     irl_step_golden()
+    stage1_loss_golden()
 
     # ---- full forward, tiny image, both depth profiles (lfd.py:314-330)
     for prof in ("peaky", "soft"):

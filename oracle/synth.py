@@ -204,3 +204,22 @@ def head_inputs(B, Hm, Wm, seed=0, T=50):
     fov = trapezoid_fov_mask(4 * Hm, 2 * Wm, 70, 70, 7 * Wm / 128.0, 200 * Wm / 128.0)
     fov = torch.from_numpy(np.ascontiguousarray(fov)).unsqueeze(0).repeat(B, 1, 1)
     return feat, expert, fov, cfs
+
+
+def stage1_loss_inputs(seed=51, B=2, H=16, W=24, D=128, Z=8):
+    """Inputs of the stage-1 validation losses: depth logits, their arg-max bins, a depth label in
+    millimetres (20 % invalid zeros, some beyond the range), DINO predictions / targets with
+    non-finite targets (pixels without a feature)."""
+    g = np.random.default_rng(seed)
+    logits = np.maximum(g.standard_normal((B, D, H, W)) * 3, 0).astype(np.float32)
+    label = g.uniform(300, 25600, (B, 1, H, W)).astype(np.float32)
+    label[g.random((B, 1, H, W)) < 0.2] = 0
+    label[0, 0, 0, :4] = [25600.0, 25599.9, 300.0, 26000.0]
+    # put some labels next to the arg-max bin so that the accuracy is not ~0
+    am = logits.argmax(1)
+    near = g.random((B, H, W)) < 0.3
+    label[:, 0][near] = (300 + (am[near] + 0.5) * (25300.0 / D)).astype(np.float32)
+    pred = g.standard_normal((B, 1, Z, H, W)).astype(np.float32)
+    gt = g.standard_normal((B, 1, Z, H, W)).astype(np.float32)
+    gt[g.random(gt.shape) < 0.1] = np.inf
+    return logits, label, pred, gt

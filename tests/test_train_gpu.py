@@ -239,3 +239,72 @@ def test_head_step_end_to_end(cuda):
     assert float((step.opt.flat_p - p_before).abs().max()) <= 5e-4 * 1.001
     loss2, _, _ = step(feat, expert, fov, cfs)
     assert torch.isfinite(loss2)
+
+
+def test_maxentirl_model_training_and_validation_step(cuda):
+    """creste.train_traversability.MaxEntIRLModel (the LightningModule mirror): a full stage-3
+    training_step from RGB-D through the frozen backbone (fused inference engine, no graph) and the
+    trainable head (autograd over the CUDA kernels) to the Adam update, then a validation_step in
+    eval mode (running BatchNorm statistics, loss incl. the gradient penalty still evaluated)."""
+    import creste_public_b200 as cb
+    from creste_public_b200 import configs
+    from creste_public_b200.creste.train_traversability import MaxEntIRLModel
+    from oracle import net_oracle
+    H, W = 64, 96
+    cfg = configs.irl_cfg(image_size=(H, W), solve_mdp=True)
+    cfg["batch_size"] = 2
+    cfg["optimizer"] = {"name": "Adam", "beta1": 0.9, "beta2": 0.999, "lr": 5e-4}
+    cfg["lr_scheduler"] = {"name": "ExponentialLR", "gamma": 0.96}
+    pl = MaxEntIRLModel(cfg)
+    pl.model.load_state_dict(synth.seeded_state_dict(pl.model.state_dict(), 0, "soft"))
+    pl = pl.to(cuda)
+    pl.configure_optimizers()
+    pl.model.traversability_head.train()
+    rgbd, p2p = synth.net_inputs(H, W, 2)
+    expert = torch.from_numpy(synth.expert_poses(2, 50, 256, 256, seed=5))
+    fov = torch.from_numpy(np.ascontiguousarray(net_oracle.trapezoid_fov_mask(256, 256, 70, 70, 7, 200)))
+    data = {"image": rgbd.to(cuda), "p2p": p2p.to(cuda), "traversability_label": expert.to(cuda),
+            "fov_mask": fov.unsqueeze(0).repeat(2, 1, 1).to(cuda),
+            "counterfactuals_label": synth.counterfactuals(expert.numpy())}
+    head = pl.model.traversability_head
+    before = {k: v.detach().clone() for k, v in head.state_dict().items()}
+    bb_before = {k: v.detach().clone() for k, v in pl.model.backbone.state_dict().items()}
+    out = pl.training_step(({"3d_sam": data}, 0, 0))
+    assert torch.isfinite(out["loss"]) and "train/MaxEntIRLLoss/maxentirl_loss" in pl.logged
+    after = head.state_dict()
+    moved = [k for k in before if k.endswith("conv.weight") and not torch.equal(before[k], after[k])]
+    assert len(moved) == 7, moved                                      # every head conv was updated
+    assert int(after["r.prepool.0.norm.num_batches_tracked"]) == int(before["r.prepool.0.norm.num_batches_tracked"]) + 1
+    for k, v in pl.model.backbone.state_dict().items():                # frozen backbone untouched
+        assert torch.equal(v, bb_before[k]), k
+    pl.model.eval()
+    val = pl.validation_step(({"3d_sam": data}, 0, 0))
+    assert torch.isfinite(val["loss"])
+    pl.on_train_epoch_end()
+    assert abs(pl.optimizers().lr - 5e-4 * 0.96) < 1e-12
+
+
+def test_stage1_validation_losses_match_reference_golden(cuda, golden):
+    """CrossEntropyDepth / SmoothL1Depth / MSELoss values (validation_step of train_pefree.py) from
+    the fused kernels vs the unmodified reference losses (tests/golden/stage1_losses.npz)."""
+    from creste_public_b200 import configs
+    from creste_public_b200.config import as_cfg
+    from creste_public_b200.creste.utils import loss_utils as lu
+    g = golden("stage1_losses.npz")
+    logits, label, pred, gt = [torch.from_numpy(a).to(cuda) for a in synth.stage1_loss_inputs()]
+    td = {"outputs/depth_preds_logits": logits, "outputs/depth_preds_bins": logits.argmax(1),
+          "inputs/depth_label": label, "outputs/dino_pe_feats": pred, "inputs/fimg_label": gt}
+    disc = dict(configs.DISCRETIZE)
+    cfgs = [{"name": "CrossEntropyDepth", "weight": 0.5, "pred_key": "outputs/depth_preds_logits",
+             "lab_key": "inputs/depth_label", "discretize": disc},
+            {"name": "SmoothL1Depth", "weight": 0.1, "pred_key": "outputs/depth_preds_bins",
+             "lab_key": "inputs/depth_label", "beta": 0.5, "discretize": disc},
+            {"name": "MSELoss", "weight": 1.0, "pred_key": "outputs/dino_pe_feats",
+             "lab_key": "inputs/fimg_label", "overlap_only": False}]
+    got = {}
+    for lc in cfgs:
+        ld, md = getattr(lu, lc["name"])(as_cfg(lc)).loss(td)
+        got.update({f"{lc['name']}/{k}": float(v) for k, v in {**ld, **md}.items()})
+    assert set(got) == set(g.files), (set(got), set(g.files))
+    for k in g.files:
+        np.testing.assert_allclose(got[k], float(g[k]), rtol=5e-6, atol=1e-7, err_msg=k)

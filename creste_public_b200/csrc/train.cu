@@ -325,6 +325,95 @@ __global__ void __launch_bounds__(256) wgrad_kernel(const float* __restrict__ x,
   }
 }
 
+// ---- wgrad for R*S > 1: all taps per CTA.  The per-tap kernel above re-reads x and g from L2 once
+// per tap (25x for the 5x5 layer).  Here a CTA owns a K slice of 16 output channels and walks
+// 8x8-pixel slabs: the x halo tile ((8+R-1) x (8+S-1) pixels x C) and the g tile (64 x 16) are
+// staged once per slab and EVERY tap is accumulated from them.  Thread = (tap, 8-channel group of
+// x) with an [8 c][16 k] register tile: 128 FMAs per 2 LDS.128 of x + 4 broadcast LDS.128 of g.
+// part[chunk][tap][C][K] as above (each CTA fills its 16 columns).
+constexpr int WGH_T = 8;           // slab edge (output pixels)
+constexpr int WGH_KS = 16;         // output channels per CTA
+__global__ void __launch_bounds__(256) wgrad_halo_kernel(const float* __restrict__ x,
+                                                         const float* __restrict__ g, int N, int H, int W,
+                                                         int C, int K, int R, int S, int pad_t, int pad_l,
+                                                         int P, int Q, float* __restrict__ part) {
+  extern __shared__ __align__(16) float wsm[];
+  const int HT = WGH_T + R - 1, WT = WGH_T + S - 1;     // halo tile
+  float* s_x = wsm;                                      // [HT*WT][C]
+  float* s_g = wsm + (size_t)HT * WT * C;                // [64][16]
+  const int c8n = C >> 3;
+  const int nthr = R * S * c8n;                          // active threads
+  const int tid = threadIdx.x;
+  const bool on = tid < nthr;
+  const int tap = on ? tid / c8n : 0, c8 = on ? tid % c8n : 0;
+  const int r = tap / S, sft = tap - r * S;
+  const int k0 = blockIdx.y * WGH_KS;
+  const int tiles_x = (Q + WGH_T - 1) / WGH_T, tiles_y = (P + WGH_T - 1) / WGH_T;
+  const int slabs = N * tiles_y * tiles_x;
+  const int per = (slabs + gridDim.x - 1) / gridDim.x;
+  const int sl0 = blockIdx.x * per, sl1 = min(sl0 + per, slabs);
+  const int c4n = C >> 2;
+  float acc[8][WGH_KS];
+#pragma unroll
+  for (int i = 0; i < 8; ++i)
+#pragma unroll
+    for (int j = 0; j < WGH_KS; ++j) acc[i][j] = 0.f;
+
+  for (int sl = sl0; sl < sl1; ++sl) {
+    const int tx = sl % tiles_x, ty = (sl / tiles_x) % tiles_y, n = sl / (tiles_x * tiles_y);
+    const int p0 = ty * WGH_T, q0 = tx * WGH_T;
+    __syncthreads();
+    for (int i = tid; i < HT * WT * c4n; i += blockDim.x) {
+      const int pix = i / c4n, c4 = i - pix * c4n;
+      const int hy = pix / WT, wx = pix - hy * WT;
+      const int iy = p0 + hy - pad_t, ix = q0 + wx - pad_l;
+      float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+      if (iy >= 0 && iy < H && ix >= 0 && ix < W)
+        v = __ldg(reinterpret_cast<const float4*>(x + (((size_t)n * H + iy) * W + ix) * C) + c4);
+      *reinterpret_cast<float4*>(s_x + (size_t)pix * C + c4 * 4) = v;
+    }
+    for (int i = tid; i < WGH_T * WGH_T * (WGH_KS / 4); i += blockDim.x) {
+      const int pix = i / (WGH_KS / 4), k4 = i - pix * (WGH_KS / 4);
+      const int py = pix / WGH_T, px = pix - py * WGH_T;
+      const int p = p0 + py, q = q0 + px;
+      float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+      if (p < P && q < Q && k0 + k4 * 4 < K)
+        v = __ldg(reinterpret_cast<const float4*>(g + (((size_t)n * P + p) * Q + q) * K + k0) + k4);
+      *reinterpret_cast<float4*>(s_g + pix * WGH_KS + k4 * 4) = v;
+    }
+    __syncthreads();
+    if (on) {
+#pragma unroll 2
+      for (int pix = 0; pix < WGH_T * WGH_T; ++pix) {
+        const int py = pix >> 3, px = pix & 7;
+        const float* xp = s_x + ((size_t)(py + r) * WT + px + sft) * C + c8 * 8;
+        const float4 x0 = *reinterpret_cast<const float4*>(xp);
+        const float4 x1 = *reinterpret_cast<const float4*>(xp + 4);
+        const float xa[8] = {x0.x, x0.y, x0.z, x0.w, x1.x, x1.y, x1.z, x1.w};
+        float ga[WGH_KS];
+#pragma unroll
+        for (int j = 0; j < WGH_KS / 4; ++j) {
+          const float4 gv = *reinterpret_cast<const float4*>(s_g + pix * WGH_KS + j * 4);
+          ga[j * 4] = gv.x; ga[j * 4 + 1] = gv.y; ga[j * 4 + 2] = gv.z; ga[j * 4 + 3] = gv.w;
+        }
+#pragma unroll
+        for (int i = 0; i < 8; ++i)
+#pragma unroll
+          for (int j = 0; j < WGH_KS; ++j) acc[i][j] = fmaf(xa[i], ga[j], acc[i][j]);
+      }
+    }
+  }
+  if (on) {
+    float* dst = part + (((size_t)blockIdx.x * (R * S) + tap) * C + c8 * 8) * K + k0;
+#pragma unroll
+    for (int i = 0; i < 8; ++i)
+#pragma unroll
+      for (int j = 0; j < WGH_KS; j += 4)
+        if (k0 + j < K)
+          *reinterpret_cast<float4*>(dst + (size_t)i * K + j) = make_float4(acc[i][j], acc[i][j + 1], acc[i][j + 2], acc[i][j + 3]);
+  }
+}
+
 // ---------------------------------------------------------------------------- row_dot / row_scale
 // out[b] = sum_i x[b,i] * y[b,i] * (m ? m[b,i] : 1)      one CTA per row, fixed order
 __global__ void __launch_bounds__(1024) row_dot_kernel(const float* __restrict__ x,
@@ -520,7 +609,17 @@ extern "C" int creste_upsample_adjoint(const float* g, int N, int Hi, int Wi, in
   return launch_check("upsample_adjoint_kernel");
 }
 
+static bool wgrad_use_halo(const creste_conv_desc* d) {
+  return d->R * d->S > 1 && d->R * d->S * (d->C / 8) <= 256 && !getenv("CRESTE_WGRAD_PER_TAP");
+}
+static int wgrad_halo_chunks(const creste_conv_desc* d) {
+  const int slabs = d->N * ceil_div(d->P, WGH_T) * ceil_div(d->Q, WGH_T);
+  int chunks = 592 / ceil_div(d->K, WGH_KS);
+  if (chunks > slabs) chunks = slabs;
+  return chunks < 1 ? 1 : chunks;
+}
 static int wgrad_chunks(const creste_conv_desc* d) {
+  if (wgrad_use_halo(d)) return wgrad_halo_chunks(d);
   const long long npix = (long long)d->N * d->P * d->Q;
   long long chunks = 592 / (d->R * d->S);
   if (chunks < 1) chunks = 1;
@@ -549,10 +648,22 @@ extern "C" int creste_conv2d_wgrad(const creste_conv_desc* d, const float* x, co
   CRESTE_CHECK_ARG(ws_bytes >= creste_conv2d_wgrad_workspace_bytes(d), "creste_conv2d_wgrad: workspace");
   cudaStream_t st = (cudaStream_t)stream;
   const int chunks = wgrad_chunks(d), lanes = wgrad_lanes(d);
-  dim3 grid(chunks, d->R * d->S);
-  wgrad_kernel<<<grid, 256, 0, st>>>(x, g, d->N, d->H, d->W, d->C, d->K, d->R, d->S, d->pad_t, d->pad_l,
-                                     d->P, d->Q, lanes, (float*)ws);
-  int rc = launch_check("wgrad_kernel");
+  int rc;
+  if (wgrad_use_halo(d)) {
+    const size_t smem = ((size_t)(WGH_T + d->R - 1) * (WGH_T + d->S - 1) * d->C + WGH_T * WGH_T * WGH_KS) * sizeof(float);
+    CRESTE_CUDA(cudaFuncSetAttribute(wgrad_halo_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    int threads = (d->R * d->S * (d->C / 8) + 31) / 32 * 32;
+    if (threads < 64) threads = 64;
+    dim3 grid(chunks, ceil_div(d->K, WGH_KS));
+    wgrad_halo_kernel<<<grid, threads, smem, st>>>(x, g, d->N, d->H, d->W, d->C, d->K, d->R, d->S, d->pad_t,
+                                                   d->pad_l, d->P, d->Q, (float*)ws);
+    rc = launch_check("wgrad_halo_kernel");
+  } else {
+    dim3 grid(chunks, d->R * d->S);
+    wgrad_kernel<<<grid, 256, 0, st>>>(x, g, d->N, d->H, d->W, d->C, d->K, d->R, d->S, d->pad_t, d->pad_l,
+                                       d->P, d->Q, lanes, (float*)ws);
+    rc = launch_check("wgrad_kernel");
+  }
   if (rc) return rc;
   const int n = d->R * d->S * d->C * d->K;
   reduce_rows_kernel<<<ceil_div(n, 256), 256, 0, st>>>((const float*)ws, chunks, n, 1.0f, dw_packed);

@@ -114,6 +114,16 @@ __device__ __forceinline__ void tma_load_2d_2sm(const CUtensorMap* map, uint64_t
       "l"((uint64_t)map), "r"(smem_u32(bar) & PEER_BIT_MASK), "r"(c0), "r"(c1)
       : "memory");
 }
+// 2-SM load multicast to the CTAs in `mask`: the tile lands at the same offset in every destination
+// CTA and the transaction bytes are signalled on each destination's pair-leader barrier
+__device__ __forceinline__ void tma_load_2d_2sm_mc(const CUtensorMap* map, uint64_t* bar, void* dst, int c0,
+                                                   int c1, uint16_t mask) {
+  asm volatile(
+      "cp.async.bulk.tensor.2d.cta_group::2.shared::cluster.global.mbarrier::complete_tx::bytes.multicast::cluster"
+      " [%0], [%1, {%4, %5}], [%2], %3;" ::"r"(smem_u32(dst)),
+      "l"((uint64_t)map), "r"(smem_u32(bar) & PEER_BIT_MASK), "h"(mask), "r"(c0), "r"(c1)
+      : "memory");
+}
 __device__ __forceinline__ void tmem_alloc_2sm(uint32_t* dst_smem, uint32_t ncols) {
   asm volatile("tcgen05.alloc.cta_group::2.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(dst_smem)),
                "r"(ncols)
@@ -123,11 +133,11 @@ __device__ __forceinline__ void tmem_alloc_2sm(uint32_t* dst_smem, uint32_t ncol
 __device__ __forceinline__ void tmem_dealloc_2sm(uint32_t addr, uint32_t ncols) {
   asm volatile("tcgen05.dealloc.cta_group::2.sync.aligned.b32 %0, %1;" ::"r"(addr), "r"(ncols) : "memory");
 }
-__device__ __forceinline__ void umma_commit_2sm(uint64_t* bar) {
+__device__ __forceinline__ void umma_commit_2sm(uint64_t* bar, uint16_t mask) {
   asm volatile(
       "tcgen05.commit.cta_group::2.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;" ::"r"(
           smem_u32(bar)),
-      "h"((uint16_t)3)
+      "h"(mask)
       : "memory");
 }
 __device__ __forceinline__ void umma_tf32_2sm(uint32_t tmem_d, uint64_t a_desc, uint64_t b_desc,
@@ -292,8 +302,15 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_consta
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int nops = p.split ? 2 : 1;
-  const uint32_t rank = PAIR ? cluster_ctarank() : 0;
+  // cluster of p.cl CTAs = p.cl / 2 CTA pairs on consecutive M tiles, all on the same N tile
+  const uint32_t crank = PAIR ? cluster_ctarank() : 0;
+  const uint32_t rank = crank & 1u;                        // rank inside the CTA pair
   const bool leader = rank == 0;
+  const int npairs = PAIR ? p.cl / 2 : 1;
+  const uint16_t pair_mask = (uint16_t)(3u << (crank & ~1u));          // this pair's two CTAs
+  const uint16_t all_mask = (uint16_t)((1u << p.cl) - 1u);
+  uint16_t bcast_mask = 0;                                 // CTAs that stage the same weight half
+  for (int j = 0; j < npairs; ++j) bcast_mask |= (uint16_t)(1u << (rank + 2 * j));
   const int b_rows = PAIR ? p.block_n / 2 : p.block_n;     // weight rows staged by THIS CTA
   const int b_tile_bytes = b_rows * 128;
   const int stage_bytes = nops * (A_TILE_BYTES + b_tile_bytes);
@@ -301,7 +318,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_consta
   // tile coordinates.  The N tiles of one M tile (pair) are adjacent in launch order, so the
   // activation tile they share is read from DRAM once and from L2 afterwards (measured: with the
   // N tile on blockIdx.y the 487 MB up3 input was fetched twice).
-  const int cls = PAIR ? 2 : 1;
+  const int cls = PAIR ? p.cl : 1;
   const int grp = blockIdx.x / cls;                       // (m tile group, n tile) in launch order
   const int n_tile = grp % p.n_tiles;
   int t = (grp / p.n_tiles) * cls + (int)(blockIdx.x % cls);
@@ -324,7 +341,9 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_consta
     prefetch_tmap(&map_a_hi);
     prefetch_tmap(&map_b_hi);
     if (p.split) { prefetch_tmap(&map_a_lo); prefetch_tmap(&map_b_lo); }
-    for (int i = 0; i < nstages; ++i) { mbar_init(&full_bar[i], 1); mbar_init(&empty_bar[i], 1); }
+    // a stage is free again once EVERY pair of the cluster has consumed it (its weight slices are
+    // written by the other pairs' multicast loads)
+    for (int i = 0; i < nstages; ++i) { mbar_init(&full_bar[i], 1); mbar_init(&empty_bar[i], npairs); }
     mbar_init(&tmem_full_bar, 1);
     fence_barrier_init();
   }
@@ -356,10 +375,19 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_consta
         if (PAIR) {
           if (leader) mbar_expect_tx(&full_bar[stage], (uint32_t)(2 * stage_bytes));
           tma_load_4d_2sm(&map_a_hi, &full_bar[stage], st, cb * p.kelems, cx, cy, img);
-          tma_load_2d_2sm(&map_b_hi, &full_bar[stage], b_hi, kb * p.kelems, nrow);
-          if (p.split) {
-            tma_load_4d_2sm(&map_a_lo, &full_bar[stage], st + A_TILE_BYTES, cb * p.kelems, cx, cy, img);
-            tma_load_2d_2sm(&map_b_lo, &full_bar[stage], b_lo, kb * p.kelems, nrow);
+          if (p.split) tma_load_4d_2sm(&map_a_lo, &full_bar[stage], st + A_TILE_BYTES, cb * p.kelems, cx, cy, img);
+          // weights: this CTA fetches slice (crank / 2) of its pair-half and multicasts it to the
+          // same-parity CTA of every pair -- each weight byte crosses L2 -> SM once per cluster
+          const int srows = b_rows / npairs;
+          const int slice = (int)(crank >> 1);
+          const int soff = slice * srows * 128;
+          if (npairs == 1) {
+            tma_load_2d_2sm(&map_b_hi, &full_bar[stage], b_hi, kb * p.kelems, nrow);
+            if (p.split) tma_load_2d_2sm(&map_b_lo, &full_bar[stage], b_lo, kb * p.kelems, nrow);
+          } else {
+            tma_load_2d_2sm_mc(&map_b_hi, &full_bar[stage], b_hi + soff, kb * p.kelems, nrow + slice * srows, bcast_mask);
+            if (p.split)
+              tma_load_2d_2sm_mc(&map_b_lo, &full_bar[stage], b_lo + soff, kb * p.kelems, nrow + slice * srows, bcast_mask);
           }
         } else {
           mbar_expect_tx(&full_bar[stage], (uint32_t)stage_bytes);
@@ -410,9 +438,9 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_consta
             }
           }
           // smem stage free (in both CTAs of a pair) once these MMAs retire
-          if (PAIR) umma_commit_2sm(&empty_bar[stage]); else umma_commit(&empty_bar[stage]);
+          if (PAIR) umma_commit_2sm(&empty_bar[stage], all_mask); else umma_commit(&empty_bar[stage]);
           if (kb == kblocks - 1) {
-            if (PAIR) umma_commit_2sm(&tmem_full_bar); else umma_commit(&tmem_full_bar);
+            if (PAIR) umma_commit_2sm(&tmem_full_bar, pair_mask); else umma_commit(&tmem_full_bar);
           }
         }
         __syncwarp();
@@ -734,7 +762,18 @@ int conv_tc_launch(const creste_conv_desc* d, const float* x, const float* w_pac
 
   // two CTAs on adjacent M tiles form a tcgen05 CTA pair (cta_group::2, M = 256)
   const int m_tiles = d->N * p.tiles_y * p.tiles_x;
-  const int cl = (m_tiles >= 2 && (block_n % 16) == 0 && !getenv("CRESTE_TC_NO_PAIR")) ? 2 : 1;
+  // cluster = 1 (no pairing), 2 (one CTA pair, the default) or 4 / 8 (CRESTE_TC_CLUSTER: 2 / 4 pairs
+  // sharing the weight tile by TMA multicast; each slice keeps whole 8-row swizzle atoms).
+  // Measured on the up3 conv: multicast cuts the L2->SM weight traffic by 25 % / 37 % but the
+  // per-SM rate does not move, and 4- / 8-CTA clusters only fill 132 / 120 of the 148 SMs
+  // (3.24 -> 3.62 / 3.95 ms) -- the kernel is not L2-bandwidth bound, so pairs stay the default.
+  int cl = (m_tiles >= 2 && (block_n % 16) == 0 && !getenv("CRESTE_TC_NO_PAIR")) ? 2 : 1;
+  if (cl == 2) {
+    int want = 2;
+    if (const char* e = getenv("CRESTE_TC_CLUSTER")) want = atoi(e);
+    while (want > 2 && !(m_tiles >= 2 * want && (block_n / want) % 8 == 0)) want >>= 1;
+    if (want == 4 || want == 8) cl = want;
+  }
   p.cl = cl;
   CUtensorMap ma_hi, ma_lo, mb_hi, mb_lo;
   int rc;
@@ -753,13 +792,13 @@ int conv_tc_launch(const creste_conv_desc* d, const float* x, const float* w_pac
   p.cross_scale = f16 ? (1.0f / 2048.0f) : 1.0f;
 
   const int nops = split ? 2 : 1;
-  const size_t stage_bytes = (size_t)nops * (A_TILE_BYTES + (block_n / cl) * 128);
+  const size_t stage_bytes = (size_t)nops * (A_TILE_BYTES + (block_n / (cl >= 2 ? 2 : 1)) * 128);
   int nstages = (int)((200 * 1024) / stage_bytes);
   if (nstages > 8) nstages = 8;
   if (nstages < 2) { set_error("creste_conv2d(tc): stage too large"); return CRESTE_ERR_ARG; }
   const size_t smem = (size_t)nstages * stage_bytes + 1024;
-  auto kern = f16 ? (cl == 2 ? conv_tc_kernel<true, true> : conv_tc_kernel<false, true>)
-                  : (cl == 2 ? conv_tc_kernel<true, false> : conv_tc_kernel<false, false>);
+  auto kern = f16 ? (cl >= 2 ? conv_tc_kernel<true, true> : conv_tc_kernel<false, true>)
+                  : (cl >= 2 ? conv_tc_kernel<true, false> : conv_tc_kernel<false, false>);
   CRESTE_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
   p.n_tiles = npad / block_n;
   dim3 grid(ceil_div(m_tiles, cl) * cl * p.n_tiles, 1);

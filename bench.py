@@ -16,8 +16,11 @@ launched by torchrun, one rank per GPU, frames sharded across ranks with no data
 collective (weak scaling); time = max over ranks, measured with CUDA events.
 
 Extra objects in the JSON line: `roofline` (dominant conv kernel, tensor bound), `cpu_baseline`
-(oracle port on the host cores, rank 0, N = 1 only), `irl` (VI + SVF at 256x256, HBM bound),
-`clocks`, `gpu_launches`.
+(oracle port on the host cores, rank 0, N = 1 only), `irl` (second headline metric: counterfactual
+IRL head-only training steps/s at 256x256 with its own CPU baseline, plus the value-iteration
+kernel's HBM-equivalent roofline), `latency_b1` (one frame, eager vs CUDA-graph replay), `clocks`,
+`gpu_launches`.  Only the cpu_baseline legs and `--impl reference` touch `oracle/`; the synthetic
+inputs come from the top-level `synth_data` module.
 """
 import argparse
 import json
@@ -176,7 +179,7 @@ def run_irl_steps(args, dev, rank, world, barrier, Bi=8, Hm=256, Wm=256, steps=5
     from creste_public_b200.config import as_cfg
     from creste_public_b200.creste.train_traversability import HeadStep
     from creste_public_b200.creste.utils.loss_utils import LossManager
-    from oracle import synth   # seeded synthetic inputs only
+    import synth_data as synth   # seeded synthetic inputs (pure generators, not the oracle)
     if args.no_irl:
         return None
     cfg = configs.irl_cfg(image_size=(64, 96), map_size=(Hm, Wm), solve_mdp=True, action_horizon=50)
@@ -221,7 +224,7 @@ def run_ours(args):
     import torch.distributed as dist
     import creste_public_b200 as cb
     from creste_public_b200 import _lib, ops
-    from oracle import synth   # seeded synthetic inputs / weights only (no oracle compute here)
+    import synth_data as synth   # seeded synthetic inputs / weights (pure generators, not the oracle)
 
     rank, local, world = dist_env()
     assert torch.cuda.is_available(), "bench.py needs a CUDA device (no CPU fallback)"

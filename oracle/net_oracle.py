@@ -262,18 +262,7 @@ def forward(sd, rgbd, p2p, encoder_fp64=False):
     return out
 
 
-def trapezoid_fov_mask(H, W, top=70, bottom=70, near=0, far=100):
-    """creste/utils/train_utils.py:511-557 restated in numpy float32."""
-    y, x = np.meshgrid(np.arange(H), np.arange(W), indexing="ij")
-    cx, cy = W / 2, H / 2
-    dx = (x - cx).astype(np.float32)
-    dy = (y - cy).astype(np.float32)
-    dist = np.sqrt(dx ** 2 + dy ** 2).astype(np.float32)
-    ang = (np.arctan2(dx, -dy).astype(np.float32) * np.float32(180) / np.float32(math.pi))
-    t, b = np.float32(top / 2), np.float32(bottom / 2)
-    spread = np.where(dist <= near, t, np.where(dist >= far, b,
-                      t + (b - t) * ((dist - near) / np.float32(far - near))))
-    return (dist >= near) & (dist <= far) & (np.abs(ang) <= spread)
+from synth_data import trapezoid_fov_mask  # noqa: E402,F401  (shared synthetic-input generator)
 
 
 def maxent_irl_loss_value(exp_svf, expert_rc, fov_mask_full, reward, cf_list, map_ds=2,

@@ -126,7 +126,7 @@ def _rel_l2(a, b):
     return float(np.linalg.norm((a - b).ravel()) / max(np.linalg.norm(b.ravel()), 1e-30))
 
 
-@pytest.mark.parametrize("precision", ["fp32", "3xtf32"])
+@pytest.mark.parametrize("precision", ["fp32", "3xtf32", "3xfp16"])
 @pytest.mark.parametrize("size", [(2, 8, 16), (1, 16, 32), (2, 64, 128)])
 def test_irl_step_matches_oracle(cuda, precision, size):
     """Loss, reward map and every parameter gradient (incl. the double-backward penalty term) of

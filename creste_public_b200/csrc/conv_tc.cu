@@ -258,6 +258,18 @@ __host__ __device__ constexpr uint32_t make_idesc_f16(int n, int m = 128) {
   return (1u << 4) | (0u << 7) | (0u << 10) | ((uint32_t)(n >> 3) << 17) | ((uint32_t)(m >> 4) << 24);
 }
 
+__device__ unsigned long long* g_tc_dbg = nullptr;      // optional per-CTA timeline (tools/conv_timeline.py)
+__device__ __forceinline__ unsigned long long gtimer() {
+  unsigned long long t;
+  asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+  return t;
+}
+#define TC_STAMP(slot)                                                                  \
+  do {                                                                                  \
+    if (g_tc_dbg && threadIdx.x == (slot == 3 || slot == 4 ? 64 : (slot == 2 ? 32 : 0))) \
+      g_tc_dbg[(size_t)blockIdx.x * 8 + slot] = gtimer();                               \
+  } while (0)
+
 // ------------------------------------------------------------------------------------ kernels
 struct TcParams {
   const float* scale; const float* shift; const float* residual; float* out;
@@ -303,6 +315,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_consta
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int nops = p.split ? 2 : 1;
+  TC_STAMP(0);
   // cluster of p.cl CTAs = p.cl / 2 CTA pairs on consecutive M tiles, all on the same N tile
   const uint32_t crank = PAIR ? cluster_ctarank() : 0;
   const uint32_t rank = crank & 1u;                        // rank inside the CTA pair
@@ -357,6 +370,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_consta
   if (PAIR) cluster_sync_all();       // barrier inits + TMEM allocation of both CTAs in place
   tc_fence_after();
   const uint32_t tmem_base = tmem_base_smem;
+  TC_STAMP(1);
 
   if (warp == 0) {
     // ===== TMA producer (both CTAs of a pair; completion bytes land on the leader's barrier) =====
@@ -412,6 +426,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_consta
         const uint32_t parity = (kb / nstages) & 1;
         mbar_wait(&full_bar[stage], parity);
         tc_fence_after();
+        if (kb == 0) TC_STAMP(2);
         if (elect_one()) {
           const uint32_t st = smem_u32(smem + (size_t)stage * stage_bytes);
           const uint32_t a_hi = st, a_lo = st + A_TILE_BYTES;
@@ -476,6 +491,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_consta
     const size_t pix = ((size_t)img * p.P + oy) * p.Q + ox;
     mbar_wait(&tmem_full_bar, 0);
     tc_fence_after();
+    TC_STAMP(3);
     for (int c0 = egroup * 32; c0 < p.block_n; c0 += 64) {
       uint32_t v[32];
       tmem_ld32(tmem_base + ((uint32_t)(quarter * 32) << 16) + (uint32_t)c0, v);
@@ -548,8 +564,10 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_consta
       }
     }
   }
+  TC_STAMP(4);
   tc_fence_before();
   __syncthreads();
+  TC_STAMP(5);
   if (PAIR) cluster_sync_all();       // no CTA exits while its peer's MMAs / TMA can still touch it
   if (warp == 1) {
     tc_fence_after();
@@ -857,6 +875,12 @@ int conv_tc_launch(const creste_conv_desc* d, const float* x, const float* w_pac
 }
 
 }  // namespace creste
+
+/* development aid: per-CTA globaltimer stamps of the next tensor-core conv launches (8 u64 per CTA) */
+extern "C" int creste_conv2d_tc_debug(void* dev_buf) {
+  unsigned long long* p = (unsigned long long*)dev_buf;
+  return (int)cudaMemcpyToSymbol(creste::g_tc_dbg, &p, sizeof(p));
+}
 
 extern "C" int creste_conv2d_tc_supported(const creste_conv_desc* d) {
   return d && creste::conv_tc_supported(d) ? 1 : 0;

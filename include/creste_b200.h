@@ -148,6 +148,10 @@ size_t creste_conv2d_workspace_bytes(const creste_conv_desc* d);
  * by the same-shaped "lo" = rna_tf32(w - hi); creste_conv2d_tc_layout reports Npad (K rounded up
  * to a multiple of the N tile block_n) and Cpad (C rounded up to 32). */
 int creste_conv2d_tc_supported(const creste_conv_desc* d);
+/* development aid (tools/conv_timeline.py): while dev_buf != NULL every tensor-core conv CTA writes
+ * 6 globaltimer stamps (start, prologue done, first operands, main loop done, epilogue done, end)
+ * to dev_buf[blockIdx.x * 8 ...] (uint64); pass NULL to switch it off. */
+int creste_conv2d_tc_debug(void* dev_buf);
 int creste_conv2d_tc_layout(int K, int C, int R, int S, int* block_n, int* npad, int* cpad);
 
 /* Depthwise conv + folded BN + swish, also producing the per-(n,c) spatial partial sums that the

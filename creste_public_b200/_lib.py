@@ -25,7 +25,7 @@ EXPORTS = [
     "creste_upsample_concat", "creste_maxpool2_concat",
     "creste_nchw_to_nhwc", "creste_nhwc_to_nchw",
     "creste_expert_visitation",
-    "creste_chan_affine", "creste_relu_bwd", "creste_chan_dot_workspace_bytes", "creste_chan_dot",
+    "creste_chan_affine", "creste_relu_bwd", "creste_chan_dot_workspace_bytes", "creste_chan_dot", "creste_chan_stats",
     "creste_maxpool2_bwd", "creste_maxpool2_gather", "creste_upsample_adjoint",
     "creste_conv2d_wgrad_workspace_bytes", "creste_conv2d_wgrad",
     "creste_row_dot", "creste_row_scale", "creste_row_normalize",

@@ -172,6 +172,21 @@ class ChanDotFn(Function):
         return dx, dy
 
 
+class ChanStatsFn(Function):
+    """(sum x, sum x^2) per channel in one pass, float64 [2, C].  Backward: d/dx = g1[c] + 2 g2[c] x,
+    i.e. ONE ChanAffineFn -- so the Function set stays closed under differentiation."""
+
+    @staticmethod
+    def forward(ctx, x):
+        ctx.save_for_backward(x)
+        return ops.chan_stats(x)
+
+    @staticmethod
+    def backward(ctx, g):
+        (x,) = ctx.saved_tensors
+        return ChanAffineFn.apply(x, (2.0 * g[1]).float(), g[0].float(), False)
+
+
 class MaxPool2Fn(Function):
     @staticmethod
     def forward(ctx, x):
@@ -326,19 +341,23 @@ def batch_norm(x, bn, relu=False):
     M = x.numel() // Cc
     use_batch = bn.training or bn.running_mean is None
     if use_batch:
-        mean = ChanDotFn.apply(x, None) / M
-        xc = ChanAffineFn.apply(x, None, -mean, False)
-        var = ChanDotFn.apply(xc, xc) / M
+        # one pass for both moments (double accumulators, so E[x^2] - mean^2 is safe), then ONE
+        # affine pass: y = x * (gamma * inv) + (beta - mean * gamma * inv).  The [C]-sized algebra in
+        # between is float64 torch arithmetic on <= 64 numbers.
+        st = ChanStatsFn.apply(x)
+        mean = st[0] / M
+        var = (st[1] / M - mean * mean).clamp_min(0.0)
         if bn.training and bn.track_running_stats and bn.running_mean is not None:
             with torch.no_grad():
                 if bn.num_batches_tracked is not None:
                     bn.num_batches_tracked += 1
                 mom = bn.momentum if bn.momentum is not None else 1.0 / float(bn.num_batches_tracked)
-                bn.running_mean.mul_(1 - mom).add_(mean.detach(), alpha=mom)
-                bn.running_var.mul_(1 - mom).add_(var.detach() * (M / max(M - 1, 1)), alpha=mom)
+                bn.running_mean.mul_(1 - mom).add_(mean.detach().float(), alpha=mom)
+                bn.running_var.mul_(1 - mom).add_((var.detach() * (M / max(M - 1, 1))).float(), alpha=mom)
         inv = torch.rsqrt(var + bn.eps)
-        scale = inv * bn.weight if bn.affine else inv
-        return ChanAffineFn.apply(xc, scale, bn.bias if bn.affine else None, relu)
+        scale = inv * bn.weight.double() if bn.affine else inv
+        shift = (bn.bias.double() if bn.affine else 0.0) - mean * scale
+        return ChanAffineFn.apply(x, scale.float(), shift.float(), relu)
     inv = torch.rsqrt(bn.running_var + bn.eps)
     scale = inv * bn.weight if bn.affine else inv
     shift = (bn.bias if bn.affine else 0) - bn.running_mean * scale

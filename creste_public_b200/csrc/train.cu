@@ -122,6 +122,59 @@ __global__ void __launch_bounds__(256) chan_dot_kernel(const float* __restrict__
   }
 }
 
+// BatchNorm batch statistics in ONE pass: part[blk][0][c] = sum x, part[blk][1][c] = sum x^2 (double)
+template <int V>
+__global__ void __launch_bounds__(256) chan_stats_kernel(const float* __restrict__ x, int C, long long npix,
+                                                         double* __restrict__ part) {
+  __shared__ double s_part[2 * 256 * V];
+  const int CV = C / V;
+  const int lanes = 256 / CV;
+  const int cg = threadIdx.x % CV, pl = threadIdx.x / CV;
+  const long long per = (npix + gridDim.x - 1) / gridDim.x;
+  const long long p0 = (long long)blockIdx.x * per;
+  const long long p1 = p0 + per < npix ? p0 + per : npix;
+  double a1[V], a2[V];
+#pragma unroll
+  for (int j = 0; j < V; ++j) { a1[j] = 0.0; a2[j] = 0.0; }
+  if (pl < lanes) {
+    for (long long p = p0 + pl; p < p1; p += lanes) {
+      float v[V];
+      if (V == 4) {
+        const float4 xv = __ldg(reinterpret_cast<const float4*>(x + p * C) + cg);
+        v[0] = xv.x; v[1 % V] = xv.y; v[2 % V] = xv.z; v[3 % V] = xv.w;
+      } else {
+        v[0] = __ldg(x + p * C + cg);
+      }
+#pragma unroll
+      for (int j = 0; j < V; ++j) { const double d = (double)v[j]; a1[j] += d; a2[j] += d * d; }
+    }
+  }
+#pragma unroll
+  for (int j = 0; j < V; ++j) { s_part[threadIdx.x * V + j] = a1[j]; s_part[256 * V + threadIdx.x * V + j] = a2[j]; }
+  __syncthreads();
+  if (pl == 0) {
+#pragma unroll
+    for (int j = 0; j < V; ++j) {
+      double t1 = s_part[threadIdx.x * V + j], t2 = s_part[256 * V + threadIdx.x * V + j];
+      for (int l = 1; l < lanes; ++l) {
+        t1 += s_part[(l * CV + threadIdx.x) * V + j];
+        t2 += s_part[256 * V + (l * CV + threadIdx.x) * V + j];
+      }
+      part[((size_t)blockIdx.x * 2) * C + cg * V + j] = t1;
+      part[((size_t)blockIdx.x * 2 + 1) * C + cg * V + j] = t2;
+    }
+  }
+}
+
+__global__ void __launch_bounds__(256) reduce_rows_f64_to_f64_kernel(const double* __restrict__ part, int rows,
+                                                                     int n, double* __restrict__ out) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  double tot = 0.0;
+  for (int j = 0; j < rows; ++j) tot += part[(size_t)j * n + i];
+  out[i] = tot;
+}
+
 __global__ void __launch_bounds__(256) reduce_rows_f64_kernel(const double* __restrict__ part, int rows,
                                                               int n, float* __restrict__ out) {
   const int i = blockIdx.x * blockDim.x + threadIdx.x;
@@ -578,6 +631,26 @@ extern "C" int creste_chan_dot(const float* x, const float* y, long long npix, i
   if (rc) return rc;
   reduce_rows_f64_kernel<<<ceil_div(C, 256), 256, 0, st>>>((const double*)ws, blocks, C, out);
   return launch_check("reduce_rows_f64_kernel");
+}
+
+/* out2 DEVICE double[2*C] = {sum_pix x[pix,c]}, {sum_pix x[pix,c]^2}: BatchNorm batch statistics in one
+ * pass (double accumulation).  ws >= 2 * creste_chan_dot_workspace_bytes(npix, C). */
+extern "C" int creste_chan_stats(const float* x, long long npix, int C, double* out2, void* ws, size_t ws_bytes,
+                                 void* stream) {
+  CRESTE_CHECK_ARG(x && out2 && ws && npix > 0 && C > 0 && C <= 1024, "creste_chan_stats: bad args");
+  CRESTE_CHECK_ARG(ws_bytes >= 2 * creste_chan_dot_workspace_bytes(npix, C), "creste_chan_stats: workspace");
+  cudaStream_t st = (cudaStream_t)stream;
+  const int blocks = chan_dot_blocks(npix);
+  if (C % 4 == 0 && C / 4 <= 256)
+    chan_stats_kernel<4><<<blocks, 256, 0, st>>>(x, C, npix, (double*)ws);
+  else {
+    CRESTE_CHECK_ARG(C <= 256, "creste_chan_stats: C %% 4 != 0 needs C <= 256");
+    chan_stats_kernel<1><<<blocks, 256, 0, st>>>(x, C, npix, (double*)ws);
+  }
+  int rc = launch_check("chan_stats_kernel");
+  if (rc) return rc;
+  reduce_rows_f64_to_f64_kernel<<<ceil_div(2 * C, 256), 256, 0, st>>>((const double*)ws, blocks, 2 * C, out2);
+  return launch_check("reduce_rows_f64_to_f64_kernel");
 }
 
 extern "C" int creste_maxpool2_bwd(const float* x, const float* g, int N, int H, int W, int C, float* dx,

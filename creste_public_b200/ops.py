@@ -359,6 +359,20 @@ def chan_dot(x, y=None):
     return out
 
 
+def chan_stats(x):
+    """-> float64 [2, C]: per-channel sum and sum of squares over all leading dims (one pass)."""
+    x = x.contiguous()
+    Cc = x.shape[-1]
+    npix = x.numel() // Cc
+    out = torch.empty(2, Cc, dtype=torch.float64, device=x.device)
+    lib().creste_chan_dot_workspace_bytes.restype = C.c_size_t
+    n = 2 * lib().creste_chan_dot_workspace_bytes(C.c_longlong(npix), Cc)
+    ws = _ws(n, x.device)
+    check(lib().creste_chan_stats(ptr(x), C.c_longlong(npix), Cc, ptr(out), ptr(ws), C.c_size_t(n), stream()),
+          "creste_chan_stats")
+    return out
+
+
 def maxpool2(x_nhwc):
     return maxpool2_concat([x_nhwc.contiguous()])
 

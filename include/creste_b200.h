@@ -222,6 +222,10 @@ int creste_relu_bwd(const float* g, const float* y, long long n, float* out, voi
 size_t creste_chan_dot_workspace_bytes(long long npix, int C);
 int creste_chan_dot(const float* x, const float* y, long long npix, int C, float* out, void* ws,
                     size_t ws_bytes, void* stream);
+/* out2 DEVICE double[2*C] = {sum_pix x}, {sum_pix x^2}: F.batch_norm's batch statistics in one pass.
+ * ws >= 2 * creste_chan_dot_workspace_bytes(npix, C). */
+int creste_chan_stats(const float* x, long long npix, int C, double* out2, void* ws, size_t ws_bytes,
+                      void* stream);
 /* 2x2/2 max-pool backward (dx[argmax] = g; first maximum wins, the PyTorch tie rule) and its
  * adjoint (out[pooled] = gg[argmax]) -- conv.py:117 under autograd.  x [N,H,W,C]. */
 int creste_maxpool2_bwd(const float* x, const float* g, int N, int H, int W, int C, float* dx,

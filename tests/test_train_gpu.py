@@ -44,6 +44,16 @@ def test_chan_affine_dot_relu(cuda, C):
     _close(o.chan_dot(x.to(cuda)), tb.chan_dot(x.double()), rtol=1e-5, atol=1e-4)
 
 
+@pytest.mark.parametrize("shape", [(2, 64, 128, 64), (3, 17, 23, 6), (1, 40, 40, 1), (2, 256, 256, 32)])
+def test_chan_stats(cuda, shape):
+    torch.manual_seed(9)
+    x = torch.randn(*shape) * 2 + 5.0
+    got = _ops().chan_stats(x.to(cuda))
+    ref = tb.chan_stats(x)
+    assert got.dtype == torch.float64
+    _close(got, ref, rtol=1e-12, atol=0)
+
+
 def test_chan_dot_large(cuda):
     torch.manual_seed(1)
     x = torch.randn(2, 256, 256, 32) + 3.0

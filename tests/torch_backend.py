@@ -35,6 +35,12 @@ def chan_dot(x, y=None):
     return v.reshape(-1, Cc).sum(0)
 
 
+def chan_stats(x):
+    Cc = x.shape[-1]
+    v = x.reshape(-1, Cc).double()
+    return torch.stack([v.sum(0), (v * v).sum(0)])
+
+
 def maxpool2(x):
     return _nhwc(F.max_pool2d(_nchw(x), 2, 2))
 
@@ -152,7 +158,7 @@ def patched():
     """Swap the kernel wrappers for the torch stand-ins (CPU graph-structure tests only)."""
     from creste_public_b200 import autograd as ag
     from creste_public_b200 import ops
-    names = ["chan_affine", "relu_bwd", "chan_dot", "maxpool2", "maxpool2_bwd", "maxpool2_gather",
+    names = ["chan_affine", "relu_bwd", "chan_dot", "chan_stats", "maxpool2", "maxpool2_bwd", "maxpool2_gather",
              "upsample2", "upsample2_adjoint", "nchw_to_nhwc", "nhwc_to_nchw", "row_dot",
              "row_scale", "row_normalize", "grad_penalty", "grad_penalty_bwd", "expert_visitation",
              "adam_step"]

@@ -31,6 +31,12 @@ EXPORTS = [
     "creste_row_dot", "creste_row_scale", "creste_row_normalize",
     "creste_grad_penalty_workspace_bytes", "creste_grad_penalty", "creste_grad_penalty_bwd",
     "creste_adam_step", "creste_stage1_depth_losses", "creste_masked_mse",
+    "creste_chan_reduce_workspace_bytes", "creste_chan_moments", "creste_chan_affine_act",
+    "creste_bn_act_bwd", "creste_chan_axpby", "creste_dwconv_fwd", "creste_dwconv_dgrad",
+    "creste_dwconv_wgrad_workspace_bytes", "creste_dwconv_wgrad", "creste_sample_dot",
+    "creste_sample_affine", "creste_act", "creste_act_bwd", "creste_add_scaled", "creste_chan_slice",
+    "creste_wgrad_strided_workspace_bytes", "creste_wgrad_strided", "creste_ce_depth_bwd",
+    "creste_masked_mse_bwd",
 ]
 
 
@@ -67,7 +73,8 @@ def lib():
         for name in ("creste_vi_workspace_bytes", "creste_svf_workspace_bytes",
                      "creste_splat_workspace_bytes", "creste_conv2d_workspace_bytes",
                      "creste_chan_dot_workspace_bytes", "creste_conv2d_wgrad_workspace_bytes",
-                     "creste_grad_penalty_workspace_bytes"):
+                     "creste_grad_penalty_workspace_bytes", "creste_chan_reduce_workspace_bytes",
+                     "creste_dwconv_wgrad_workspace_bytes", "creste_wgrad_strided_workspace_bytes"):
             getattr(L, name).restype = C.c_size_t
         _lib = L
     return _lib

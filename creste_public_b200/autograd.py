@@ -44,6 +44,8 @@ def _conv_raw(x, w, ph, pw):
         wp[:K, :Cc] = w
     pad = (ph, ph, pw, pw)
     mode = engine.pick_mode(tuple(xp.shape), Kp, R, S, 1, pad, engine.get_precision())
+    if xp.shape[1] * xp.shape[2] < 16:
+        mode = "fp32"      # squeeze-excite vectors [B,1,1,C]: a handful of rows, no tensor-core tile
     if mode == "fp32":
         packed = ops.pack_conv_weight(wp.detach().float())
     elif mode == "3xfp16":
@@ -362,3 +364,233 @@ def batch_norm(x, bn, relu=False):
     scale = inv * bn.weight if bn.affine else inv
     shift = (bn.bias if bn.affine else 0) - bn.running_mean * scale
     return ChanAffineFn.apply(x, scale, shift, relu)
+
+
+# ===================================================================== stage-1 backbone training
+# Train-mode graph of DistillationBackbone (reference creste/models/distillation.py:145-207 driven by
+# creste/train_pefree.py:76-106).  The reference needs first-order gradients only here, so the
+# fused nodes below are `once_differentiable`; dense convs reuse Conv2dFn / WGradFn above.
+once = torch.autograd.function.once_differentiable
+
+
+def _update_running(bn, mean, var, M):
+    """F.batch_norm(training=True) bookkeeping: momentum update with the UNBIASED variance."""
+    if not (bn.track_running_stats and bn.running_mean is not None):
+        return
+    with torch.no_grad():
+        if bn.num_batches_tracked is not None:
+            bn.num_batches_tracked += 1
+        mom = bn.momentum if bn.momentum is not None else 1.0 / float(bn.num_batches_tracked)
+        bn.running_mean.mul_(1 - mom).add_(mean.float(), alpha=mom)
+        bn.running_var.mul_(1 - mom).add_((var * (M / max(M - 1, 1))).float(), alpha=mom)
+
+
+class BNActFn(Function):
+    """BatchNorm2d with batch statistics + activation ('none' | 'relu' | 'swish') as ONE node:
+    forward = one moments pass + one affine/act pass; backward = one pass producing
+    gu = g*act'(u) with (sum gu, sum gu*x), then dx = gu*p + x*q + r in one more pass."""
+
+    @staticmethod
+    def forward(ctx, x, weight, bias, bn, act):
+        Cc = x.shape[-1]
+        M = x.numel() // Cc
+        st = ops.chan_moments(x)
+        mean = st[0] / M
+        var = (st[1] / M - mean * mean).clamp_min(0.0)
+        _update_running(bn, mean, var, M)
+        inv = torch.rsqrt(var + bn.eps)
+        a = inv * weight.detach().double()
+        b = bias.detach().double() - mean * a
+        a32, b32 = a.float().contiguous(), b.float().contiguous()
+        ctx.save_for_backward(x, a32, b32, mean, inv)
+        ctx.act, ctx.M = act, M
+        return ops.chan_affine_act(x, a32, b32, act)
+
+    @staticmethod
+    @once
+    def backward(ctx, g):
+        x, a32, b32, mean, inv = ctx.saved_tensors
+        M = ctx.M
+        gu, sums = ops.bn_act_bwd(g, x, a32, b32, ctx.act)
+        s1, s2 = sums[0], sums[1]
+        dgamma = inv * (s2 - mean * s1)
+        a = a32.double()
+        q = -a * inv * dgamma / M
+        r = -a * s1 / M - q * mean
+        dx = ops.chan_axpby(gu, x, a32, q.float(), r.float()) if ctx.needs_input_grad[0] else None
+        return dx, dgamma.float(), s1.float(), None, None
+
+
+def bn_act(x, bn, act="none"):
+    """nn.BatchNorm2d (+ activation) over channels-last x inside the stage-1 training graph."""
+    if bn.training or bn.running_mean is None:
+        return BNActFn.apply(x, bn.weight, bn.bias, bn, act)
+    if act == "swish":
+        raise NotImplementedError("eval-mode BatchNorm + swish inside a training graph (frozen trunk) is unused")
+    return batch_norm(x, bn, relu=(act == "relu"))
+
+
+class DwConvFn(Function):
+    """Depthwise k x k conv, weights [C,1,k,k] (torch layout), pad = (top, bottom, left, right)."""
+
+    @staticmethod
+    def forward(ctx, x, w, k, stride, pad):
+        w_rsc = w.detach().permute(2, 3, 1, 0).reshape(k * k, w.shape[0]).contiguous()
+        ctx.save_for_backward(x, w_rsc)
+        ctx.geom = (k, stride, pad)
+        return ops.dwconv_fwd(x, w_rsc, k, stride, pad)
+
+    @staticmethod
+    @once
+    def backward(ctx, g):
+        x, w_rsc = ctx.saved_tensors
+        k, stride, pad = ctx.geom
+        dx = dw = None
+        if ctx.needs_input_grad[0]:
+            dx = ops.dwconv_dgrad(g, w_rsc, tuple(x.shape), k, stride, pad)
+        if ctx.needs_input_grad[1]:
+            dw = ops.dwconv_wgrad(x, g, k, stride, pad).view(k, k, 1, -1).permute(3, 2, 0, 1).contiguous()
+        return dx, dw, None, None, None
+
+
+class StemConvFn(Function):
+    """The strided C=4 stem conv (efficientnet `_conv_stem`): exact-fp32 forward, weight gradient
+    only (its input is the image)."""
+
+    @staticmethod
+    def forward(ctx, x, w, stride, pad):
+        K, Cc, R, S = w.shape
+        ctx.save_for_backward(x)
+        ctx.geom = (R, S, stride, pad)
+        return ops.conv2d(x, ops.pack_conv_weight(w.detach().float()), K, R, S, stride, pad, precision="fp32")
+
+    @staticmethod
+    @once
+    def backward(ctx, g):
+        (x,) = ctx.saved_tensors
+        R, S, stride, pad = ctx.geom
+        if ctx.needs_input_grad[0]:
+            raise NotImplementedError("StemConvFn: the data gradient of the strided stem is never needed")
+        return None, ops.wgrad_strided(x, g, R, S, stride, pad), None, None
+
+
+class SamplePoolFn(Function):
+    """adaptive_avg_pool2d(x, 1) over NHWC -> [B,1,1,C]."""
+
+    @staticmethod
+    def forward(ctx, x):
+        ctx.shape = tuple(x.shape)
+        HW = x.numel() // (x.shape[0] * x.shape[-1])
+        return ops.sample_dot(x, None, 1.0 / HW)
+
+    @staticmethod
+    @once
+    def backward(ctx, g):
+        shape = ctx.shape
+        HW = 1
+        for d in shape[1:-1]:
+            HW *= d
+        return ops.sample_affine(None, None, (g / HW).contiguous(), shape=shape)
+
+
+class SampleScaleFn(Function):
+    """x * gate[b,c] (squeeze-excite)."""
+
+    @staticmethod
+    def forward(ctx, x, gate):
+        ctx.save_for_backward(x, gate)
+        return ops.sample_affine(x, gate)
+
+    @staticmethod
+    @once
+    def backward(ctx, g):
+        x, gate = ctx.saved_tensors
+        dx = ops.sample_affine(g, gate) if ctx.needs_input_grad[0] else None
+        dgate = ops.sample_dot(g, x).view_as(gate) if ctx.needs_input_grad[1] else None
+        return dx, dgate
+
+
+class ActFn(Function):
+    """swish / sigmoid on the small squeeze-excite tensors."""
+
+    @staticmethod
+    def forward(ctx, x, kind):
+        ctx.save_for_backward(x)
+        ctx.kind = kind
+        return ops.act(x, kind)
+
+    @staticmethod
+    @once
+    def backward(ctx, g):
+        (x,) = ctx.saved_tensors
+        return ops.act_bwd(g, x, ctx.kind), None
+
+
+class AddScaledFn(Function):
+    """inp + x * s[b]: identity skip with drop-connect (s None: plain residual sum)."""
+
+    @staticmethod
+    def forward(ctx, x, inp, s):
+        ctx.save_for_backward(s)
+        return ops.add_scaled(inp, x, s)
+
+    @staticmethod
+    @once
+    def backward(ctx, g):
+        (s,) = ctx.saved_tensors
+        dx = g if s is None else ops.row_scale(g, s)
+        return dx, g, None
+
+
+class UpCatFn(Function):
+    """cat([skip, bilinear_x2(x)], C) (reference effnet.py:22-25) and its adjoint."""
+
+    @staticmethod
+    def forward(ctx, x, skip, sf):
+        if sf != 2:
+            raise NotImplementedError("training path: the decoder up-samples by exactly 2 at every stage")
+        ctx.cs = skip.shape[-1]
+        ctx.cx = x.shape[-1]
+        return ops.upsample_concat(skip, x, (2 * x.shape[1], 2 * x.shape[2]), 2)
+
+    @staticmethod
+    @once
+    def backward(ctx, g):
+        dskip = ops.chan_slice(g, 0, ctx.cs) if ctx.needs_input_grad[1] else None
+        dx = ops.upsample2_adjoint(ops.chan_slice(g, ctx.cs, ctx.cx)) if ctx.needs_input_grad[0] else None
+        return dx, dskip, None
+
+
+class CEDepthFn(Function):
+    """mean cross-entropy over the valid pixels (CrossEntropyDepth, loss_utils.py:477-527); `acc` is
+    the device float64[>=2] {sum CE, #valid} from creste_stage1_depth_losses."""
+
+    @staticmethod
+    def forward(ctx, logits_nchw, label_mm, acc, dmin, dmax):
+        ctx.save_for_backward(logits_nchw, label_mm, acc)
+        ctx.rng = (dmin, dmax)
+        return (acc[0] / acc[1]).float()
+
+    @staticmethod
+    @once
+    def backward(ctx, g):
+        logits, label, acc = ctx.saved_tensors
+        scale = (g.double() / acc[1]).float()
+        return ops.ce_depth_bwd(logits, label, ctx.rng[0], ctx.rng[1], scale), None, None, None, None
+
+
+class MaskedMSEFn(Function):
+    """mean((pred - gt)^2) over the elements whose target is finite (MSELoss, loss_utils.py:606-647)."""
+
+    @staticmethod
+    def forward(ctx, pred, gt):
+        acc = ops.masked_mse(pred, gt)
+        ctx.save_for_backward(pred, gt, acc)
+        return (acc[0] / acc[1]).float()
+
+    @staticmethod
+    @once
+    def backward(ctx, g):
+        pred, gt, acc = ctx.saved_tensors
+        scale = (2.0 * g.double() / acc[1]).float()
+        return ops.masked_mse_bwd(pred, gt, scale), None

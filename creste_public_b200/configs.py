@@ -78,3 +78,29 @@ def irl_cfg(image_size=(512, 612), map_size=(64, 128), solve_mdp=True, action_ho
                   "lab_key": "inputs/traversability_label",
                   "cf_key": "inputs/counterfactuals_label"}],
     }
+
+
+def distill_cfg(image_size=(512, 960)):
+    """configs/model/distillation/effnet_ds2_dinov2_128.yaml (stage 1, train_pefree.py): model
+    sections + optimizer / scheduler / loss lists."""
+    disc = copy.deepcopy(DISCRETIZE)
+    base = ssc_cfg(image_size)
+    return {
+        "project_name": "Distillation", "run_name": "effnet_ds2_dinov2_128",
+        "multiview_distillation": False, "weights_path": "", "ckpt_path": "",
+        "discretize": disc,
+        "vision_backbone": copy.deepcopy(base["vision_backbone"]),
+        "depth_head": copy.deepcopy(base["depth_head"]),
+        "distillation_head": copy.deepcopy(base["distillation_head"]),
+        "batch_size": 4,
+        "optimizer": {"name": "Adam", "beta1": 0.9, "beta2": 0.999, "lr": 0.0005, "eps": 1e-7},
+        "lr_scheduler": {"name": "ExponentialLR", "gamma": 0.98},
+        "loss": [
+            {"name": "CrossEntropyDepth", "weight": 0.5, "pred_key": "outputs/depth_preds_logits",
+             "lab_key": "inputs/depth_label", "discretize": copy.deepcopy(disc)},
+            {"name": "SmoothL1Depth", "weight": 0.1, "pred_key": "outputs/depth_preds_bins",
+             "lab_key": "inputs/depth_label", "beta": 0.5, "discretize": copy.deepcopy(disc)},
+            {"name": "MSELoss", "weight": 1.0, "pred_key": "outputs/dino_pe_feats",
+             "lab_key": "inputs/fimg_label", "overlap_only": False},
+        ],
+    }

@@ -38,8 +38,23 @@ class _ConvStack(nn.Module):
             object.__setattr__(self, "_fc", fc)
         return self._fc
 
+    def forward_train(self, x):
+        """Train-mode stack as an autograd graph: conv (+bias) -> BatchNorm with batch statistics ->
+        ReLU per layer (reference conv.py:5-32 under nn.Module.train())."""
+        from creste_public_b200 import autograd as ag
+        layers = list(self._seq())
+        i = 0
+        while i < len(layers):
+            conv = layers[i]
+            bn = layers[i + 1] if isinstance(layers[i + 1], nn.BatchNorm2d) else None
+            y = ag.conv2d(x, conv)
+            x = ag.bn_act(y, bn, "relu") if bn is not None else ag.relu(y)
+            i += 3 if bn is not None else 2
+        return x
+
     def forward_nhwc(self, x):
-        require_eval(self)
+        if self.training:
+            return self.forward_train(x)
         for f in self._fused(self._seq()):
             x = f(x, act="relu")
         return x

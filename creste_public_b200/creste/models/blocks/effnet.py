@@ -20,7 +20,8 @@ import math
 import torch
 from torch import nn
 
-from creste_public_b200 import ops
+from creste_public_b200 import autograd as ag
+from creste_public_b200 import engine, ops
 from creste_public_b200.engine import FusedConv, PackCache, bn_scale_shift, require_eval
 
 # (repeats, kernel, stride, expand, in, out) -- EfficientNet-B0, SE ratio 0.25
@@ -55,6 +56,27 @@ class MBConv(nn.Module):
         if e != 1:
             object.__setattr__(self, "_f_expand", FusedConv(self._expand_conv, self._bn0))
         object.__setattr__(self, "_f_project", FusedConv(self._project_conv, self._bn2))
+
+    def forward_train(self, x, drop_rate):
+        """Train-mode MBConv as an autograd graph of sm_100a kernels (BatchNorm batch statistics,
+        squeeze-excite, drop-connect on the identity skip): efficientnet_pytorch MBConvBlock.forward."""
+        inp = x
+        if self.e != 1:
+            x = ag.bn_act(ag.conv2d(x, self._expand_conv), self._bn0, "swish")
+        lo, hi = same_pad(self.k, self.s)
+        x = ag.DwConvFn.apply(x, self._depthwise_conv.weight, self.k, self.s, (lo, hi, lo, hi))
+        x = ag.bn_act(x, self._bn1, "swish")
+        sq = ag.SamplePoolFn.apply(x)
+        sq = ag.ActFn.apply(ag.conv2d(sq, self._se_reduce), "swish")
+        gate = ag.ActFn.apply(ag.conv2d(sq, self._se_expand), "sigmoid")
+        x = ag.SampleScaleFn.apply(x, gate)
+        x = ag.bn_act(ag.conv2d(x, self._project_conv), self._bn2, "none")
+        if self.s == 1 and self.cin == self.cout:
+            scale = None
+            if drop_rate and self.training:
+                scale = engine.drop_connect_scale(x.shape[0], drop_rate, x.device)
+            x = ag.AddScaledFn.apply(x, inp, scale)
+        return x
 
     def forward_nhwc(self, x):
         inp = x
@@ -108,6 +130,34 @@ class EfficientNetB0(nn.Module):
             object.__setattr__(self, "_f_stem", FusedConv(self._conv_stem, self._bn0))
         return self.__dict__["_f_stem"]
 
+    DROP_CONNECT = 0.2      # efficientnet-b0 global drop_connect_rate
+
+    def extract_endpoints_train(self, x):
+        """extract_endpoints in training mode: drop-connect rate 0.2 * idx / n per block, and the
+        1280-channel head runs (without gradient) only because the reference's BatchNorm `_bn1`
+        updates its running statistics from it."""
+        lo, hi = same_pad(3, 2)
+        x = ag.StemConvFn.apply(x, self._conv_stem.weight, 2, (lo, hi, lo, hi))
+        x = ag.bn_act(x, self._bn0, "swish")
+        endpoints = {}
+        prev = x
+        n = len(self._blocks)
+        for idx, blk in enumerate(self._blocks):
+            x = blk.forward_train(x, self.DROP_CONNECT * float(idx) / n)
+            if prev.shape[1] > x.shape[1]:
+                endpoints[f"reduction_{len(endpoints) + 1}"] = prev
+            elif idx == n - 1:
+                endpoints[f"reduction_{len(endpoints) + 1}"] = x
+            prev = x
+        if self._bn1.training:
+            with torch.no_grad():
+                h = ag.conv2d(x.detach(), self._conv_head)
+                M = h.numel() // h.shape[-1]
+                st = ops.chan_moments(h)
+                mean = st[0] / M
+                ag._update_running(self._bn1, mean, (st[1] / M - mean * mean).clamp_min(0.0), M)
+        return endpoints
+
     def extract_endpoints_nhwc(self, x):
         """Endpoint rule of efficientnet_pytorch.extract_endpoints: the activation *before* every
         resolution drop, plus the last block's output (reduction_1..5); the 1280-ch head
@@ -141,7 +191,14 @@ class Up(nn.Module):
         object.__setattr__(self, "_f0", FusedConv(self.conv[0], self.conv[1]))
         object.__setattr__(self, "_f1", FusedConv(self.conv[3], self.conv[4]))
 
+    def forward_train(self, x1, x2):
+        x = ag.UpCatFn.apply(x1, x2, self.up.scale_factor)
+        x = ag.bn_act(ag.conv2d(x, self.conv[0]), self.conv[1], "relu")
+        return ag.bn_act(ag.conv2d(x, self.conv[3]), self.conv[4], "relu")
+
     def forward_nhwc(self, x1, x2):
+        if self.training:
+            return self.forward_train(x1, x2)
         sf = self.up.scale_factor
         sh, sw = (sf, sf) if not isinstance(sf, (tuple, list)) else sf
         Ho, Wo = int(math.floor(x1.shape[1] * sh)), int(math.floor(x1.shape[2] * sw))
@@ -149,7 +206,6 @@ class Up(nn.Module):
         return self._f1(self._f0(x, act="relu"), act="relu")
 
     def forward(self, x1, x2):
-        require_eval(self)
         y = self.forward_nhwc(ops.nchw_to_nhwc(x1.float()), ops.nchw_to_nhwc(x2.float()))
         return ops.nhwc_to_nchw(y)
 
@@ -186,8 +242,19 @@ class EffNet(nn.Module):
         object.__setattr__(self, "_f_out", FusedConv(self.conv, self.bn if apply_final_batch_norm
                                                      else None))
 
+    def forward_train(self, x):
+        ep = self.trunk.extract_endpoints_train(x)
+        y = ep["reduction_5"]
+        for i in range(1, self.n_ups + 1):
+            y = getattr(self, f"up{i}").forward_train(y, ep[f"reduction_{5 - i}"])
+        out = ag.conv2d(y, self.conv)
+        if self.apply_final_batch_norm:
+            out = ag.bn_act(out, self.bn, "relu")
+        return (out, y) if self.return_2nd_last_layer_output else out
+
     def forward_nhwc(self, x):
-        require_eval(self)
+        if self.training:
+            return self.forward_train(x)
         ep = self.trunk.extract_endpoints_nhwc(x)
         n = 5
         y = ep[f"reduction_{n}"]

@@ -4,6 +4,7 @@ import os
 import torch
 from torch import nn
 
+from creste_public_b200 import autograd as ag
 from creste_public_b200 import ops
 from creste_public_b200.engine import require_eval
 from .blocks.conv import MultiLayerConv
@@ -41,16 +42,18 @@ class DepthCompletion(nn.Module):
 
     def forward_nhwc(self, x_nhwc, want_nchw=True):
         """Returns (outputs dict in the reference's NCHW layouts, nhwc dict for the parents)."""
-        require_eval(self)
         feats = self.vision_backbone.forward_nhwc(x_nhwc)
         logits = self.depth_head.forward_nhwc(feats)
-        metric, bins = ops.depth_expectation(logits, float(self.discretize_cfg.depth_min),
+        # the soft-argmax depth and the arg-max bins are value-only outputs: no stage-1 loss of the
+        # shipped config differentiates them (SmoothL1Depth reads the int64 bins, loss_utils.py:530-573)
+        metric, bins = ops.depth_expectation(logits.detach(), float(self.discretize_cfg.depth_min),
                                              float(self.discretize_cfg.depth_max))
         out = {"depth_preds_metric": metric, "depth_preds_bins": bins}
         if want_nchw:
-            out["depth_preds_logits"] = ops.nhwc_to_nchw(logits)
+            to_nchw = ag.ToNCHW.apply if logits.requires_grad else ops.nhwc_to_nchw
+            out["depth_preds_logits"] = to_nchw(logits)
             if self.return_feats:
-                out["depth_preds_feats"] = ops.nhwc_to_nchw(feats)
+                out["depth_preds_feats"] = to_nchw(feats)
         return out, {"feats": feats, "logits": logits}
 
     def forward(self, x):

@@ -4,6 +4,7 @@ import os
 import torch
 from torch import nn
 
+from creste_public_b200 import autograd as ag
 from creste_public_b200 import ops
 from creste_public_b200.engine import require_eval
 from .blocks.conv import MultiLayerConv  # noqa: F401  (resolved by name through globals())
@@ -59,12 +60,12 @@ class DistillationBackbone(nn.Module):
             p.requires_grad = True
 
     def forward_nhwc(self, x_nhwc, B, V, want_nchw=True, want_dino=True):
-        require_eval(self)
         out, nh = self.depthcomp.forward_nhwc(x_nhwc, want_nchw)
         if want_dino:
             d = self.dino_head.forward_nhwc(nh["feats"])
             BV, Hs, Ws, D = d.shape
-            out["dino_pe_feats"] = ops.nhwc_to_nchw(d).view(B, 1, D, Hs, Ws)
+            to_nchw = ag.ToNCHW.apply if d.requires_grad else ops.nhwc_to_nchw
+            out["dino_pe_feats"] = to_nchw(d).view(B, 1, D, Hs, Ws)
         return out, nh
 
     def forward(self, x):

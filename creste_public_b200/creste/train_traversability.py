@@ -27,8 +27,11 @@ class FlatAdam:
         self.params = [p for p in params if p.requires_grad]
         assert self.params, "no trainable parameters"
         dev = self.params[0].device
-        n = sum(p.numel() for p in self.params)
-        self.flat_p = torch.empty(n, device=dev)
+        # every parameter starts on a 128-byte boundary of the flat buffers: kernels read parameters
+        # (biases, BatchNorm vectors) with 16-byte vector loads straight from these views
+        al = lambda k: (k + 31) // 32 * 32
+        n = sum(al(p.numel()) for p in self.params)
+        self.flat_p = torch.zeros(n, device=dev)
         self.flat_g = torch.zeros(n, device=dev)
         self.m = torch.zeros(n, device=dev)
         self.v = torch.zeros(n, device=dev)
@@ -42,7 +45,7 @@ class FlatAdam:
                 gv = self.flat_g[o:o + k].view_as(p)
                 p.grad = gv
                 self.views.append(gv)
-                o += k
+                o += al(k)
         self.lr, self.betas, self.eps = float(lr), betas, float(eps)
         self.steps = 0
         self.group = process_group

@@ -5,9 +5,12 @@ The per-sample reductions, normalisations, the visitation rasters and the SMODIC
 penalty run on the sm_100a kernels (creste_row_*, creste_expert_visitation,
 creste_grad_penalty); the differentiable pieces are creste_public_b200.autograd Functions, so
 `loss.backward()` reaches the reward-FCN weights through the first- and second-order graph
-exactly as in the reference.  The stage-1 losses (CrossEntropyDepth, SmoothL1Depth, MSELoss) are
-mirrored as validation-time VALUES only (one fused kernel pass); stage-2 losses are not mirrored.
+exactly as in the reference.  The stage-1 losses (CrossEntropyDepth, SmoothL1Depth, MSELoss) are one
+fused kernel pass for the values and creste_ce_depth_bwd / creste_masked_mse_bwd for the gradients
+(the Smooth-L1 term reads int64 bins and has none, as in the reference); stage-2 losses are not mirrored.
 """
+import weakref
+
 import numpy as np
 import torch
 from torch import nn
@@ -72,7 +75,7 @@ class LossManager(nn.Module):
 class _Stage1DepthValues:
     """CrossEntropyDepth and SmoothL1Depth share one kernel pass; the result is cached per
     (logits, label) pair so that the two Loss objects of the shipped config cost one launch."""
-    _key, _val = None, None
+    _key, _val, _ref = None, None, None
 
     @classmethod
     def get(cls, tensor_dict, discretize, beta):
@@ -80,7 +83,9 @@ class _Stage1DepthValues:
         bins = tensor_dict["outputs/depth_preds_bins"]
         label = tensor_dict["inputs/depth_label"]
         key = (logits.data_ptr(), label.data_ptr(), logits._version, float(beta))
-        if cls._key != key:
+        # the cache is tied to the logits OBJECT (weak reference): a later step's logits may reuse the
+        # address of a freed tensor with the same version counter
+        if cls._key != key or cls._ref is None or cls._ref() is not logits:
             if discretize["mode"] != "UD":
                 raise NotImplementedError("bin_depths modes other than 'UD' are unused by the shipped configs")
             B, S, H, W = label.shape
@@ -90,24 +95,35 @@ class _Stage1DepthValues:
                                                label.reshape(B * S, H * W).to(logits.device),
                                                discretize["depth_min"], discretize["depth_max"], beta)
             cls._key = key
+            cls._ref = weakref.ref(logits)
         return cls._val
 
 
 class CrossEntropyDepth(Loss):
-    """Validation-time VALUE of reference loss_utils.py:477-527 (no gradient: training the backbone
-    is not implemented).  Returns depth/cls_loss and the depth/acc meta value."""
+    """Reference loss_utils.py:477-527: mean cross-entropy of the depth logits against the UD-binned
+    LiDAR depth over the valid pixels (+ the depth/acc meta value); one fused kernel pass for the
+    value, creste_ce_depth_bwd for the gradient (autograd.CEDepthFn) when the logits carry one."""
 
     def __init__(self, config):
         super().__init__(config.name if hasattr(config, "name") else config["name"], config)
 
     def loss(self, tensor_dict):
-        acc = _Stage1DepthValues.get(tensor_dict, self.config["discretize"], 0.5)
-        return {"depth/cls_loss": (acc[0] / acc[1]).float()}, {"depth/acc": (acc[2] / acc[1]).float()}
+        disc = self.config["discretize"]
+        acc = _Stage1DepthValues.get(tensor_dict, disc, 0.5)
+        logits = tensor_dict["outputs/depth_preds_logits"]
+        if logits.requires_grad and torch.is_grad_enabled():
+            label = tensor_dict["inputs/depth_label"]
+            label = label.reshape(logits.shape[0], -1).to(logits.device).float().contiguous()
+            val = ag.CEDepthFn.apply(logits, label, acc, float(disc["depth_min"]), float(disc["depth_max"]))
+        else:
+            val = (acc[0] / acc[1]).float()
+        return {"depth/cls_loss": val}, {"depth/acc": (acc[2] / acc[1]).float()}
 
 
 class SmoothL1Depth(Loss):
-    """Validation-time value of reference loss_utils.py:530-573; pred_key is depth_preds_bins in
-    the shipped config (class indices compared with metres, as the reference does)."""
+    """Reference loss_utils.py:530-573; pred_key is depth_preds_bins in the shipped config (int64
+    class indices compared with metres), so -- exactly as in the reference -- this term has a value
+    but contributes no gradient."""
 
     def __init__(self, config):
         super().__init__(config.name if hasattr(config, "name") else config["name"], config)
@@ -121,7 +137,7 @@ class SmoothL1Depth(Loss):
 
 
 class MSELoss(Loss):
-    """Validation-time value of reference loss_utils.py:606-647 (overlap_only = False)."""
+    """Reference loss_utils.py:606-647 (overlap_only = False); differentiable via MaskedMSEFn."""
 
     def __init__(self, config):
         super().__init__(config.name if hasattr(config, "name") else config["name"], config)
@@ -132,7 +148,10 @@ class MSELoss(Loss):
     def loss(self, tensor_dict):
         pred, gt = tensor_dict[self.pred_key], tensor_dict[self.lab_key]
         assert pred.shape == gt.shape, (pred.shape, gt.shape)
-        acc = ops.masked_mse(pred, gt.to(pred.device))
+        gt = gt.to(pred.device).float().contiguous()
+        if pred.requires_grad and torch.is_grad_enabled():
+            return {"loss": ag.MaskedMSEFn.apply(pred.contiguous(), gt)}, {}
+        acc = ops.masked_mse(pred, gt)
         return {"loss": (acc[0] / acc[1]).float()}, {}
 
 

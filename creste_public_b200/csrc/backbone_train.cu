@@ -1,0 +1,656 @@
+// backbone_train.cu -- kernels of the stage-1 (distillation) training step of the RGB-D backbone.
+//
+// The reference trains DistillationBackbone (creste/models/distillation.py:145-207: EfficientNet-B0
+// trunk + U-Net decoder, creste/models/blocks/effnet.py:8-98, depth head and dino head,
+// creste/models/blocks/conv.py:5-32) with PyTorch autograd against CrossEntropyDepth + MSELoss
+// (creste/utils/loss_utils.py:477-527, 606-647) in creste/train_pefree.py:76-106.  The dense convs
+// of that graph reuse conv2d / conv2d_wgrad (conv_tc.cu, conv_simt.cu, train.cu); this file holds
+// everything else the train-mode graph and its backward need:
+//
+//   chan_moments               BatchNorm batch statistics, any C % 4 == 0 (double accumulators)
+//   chan_affine_act            y = act(x * a[c] + b[c]), act in {none, relu, swish}
+//   bn_act_bwd                 gu = g * act'(x*a+b)  +  (sum gu, sum gu*x) per channel, one pass
+//   chan_axpby                 dx = gu*p[c] + x*q[c] + r[c]      (BatchNorm backward, one pass)
+//   dwconv_fwd / dgrad / wgrad depthwise k x k conv with TF-'SAME' (asymmetric) padding, stride 1/2
+//   sample_dot / sample_affine squeeze-excite pooling / gating and their adjoints ([B,C] vectors)
+//   act / act_bwd              swish, sigmoid on the tiny SE tensors
+//   add_scaled                 identity skip + drop-connect:  out = inp + x * s[b]
+//   chan_slice                 channel range copy (adjoint of the decoder's concat)
+//   wgrad_strided              weight gradient of the strided C=4 stem conv
+//   ce_depth_bwd, masked_mse_bwd   loss gradients
+//
+// All activations NHWC fp32.  The reductions of this file are two-stage with a fixed order (no atomics).
+#include "common.cuh"
+
+namespace creste {
+
+enum { ACT_NONE = 0, ACT_RELU = 1, ACT_SWISH = 2, ACT_SIGMOID = 3 };
+
+static inline int grid_cap2(long long total, int threads, int cap) {
+  long long b = (total + threads - 1) / threads;
+  if (b < 1) b = 1;
+  return (int)(b > cap ? cap : b);
+}
+
+__device__ __forceinline__ float sigmoid_f(float u) { return 1.0f / (1.0f + expf(-u)); }
+__device__ __forceinline__ float act_fwd(float u, int act) {
+  if (act == ACT_RELU) return fmaxf(u, 0.f);
+  if (act == ACT_SWISH) return u * sigmoid_f(u);
+  if (act == ACT_SIGMOID) return sigmoid_f(u);
+  return u;
+}
+// d act(u) / du
+__device__ __forceinline__ float act_grad(float u, int act) {
+  if (act == ACT_RELU) return u > 0.f ? 1.f : 0.f;
+  if (act == ACT_SWISH) { const float s = sigmoid_f(u); return s * (1.f + u * (1.f - s)); }
+  if (act == ACT_SIGMOID) { const float s = sigmoid_f(u); return s * (1.f - s); }
+  return 1.f;
+}
+
+// -------------------------------------------------------------------------------- elementwise
+__global__ void __launch_bounds__(256) chan_affine_act_kernel(const float* __restrict__ x,
+                                                              const float* __restrict__ a,
+                                                              const float* __restrict__ b, int C, long long n,
+                                                              int act, float* __restrict__ y) {
+  const long long nv = n / 4;
+  const int CV = C / 4;
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < nv;
+       i += (long long)gridDim.x * blockDim.x) {
+    const int c = (int)(i % CV) * 4;
+    float4 v = __ldg(reinterpret_cast<const float4*>(x) + i);
+    const float4 aa = a ? __ldg(reinterpret_cast<const float4*>(a + c)) : make_float4(1.f, 1.f, 1.f, 1.f);
+    const float4 bb = b ? __ldg(reinterpret_cast<const float4*>(b + c)) : make_float4(0.f, 0.f, 0.f, 0.f);
+    v.x = act_fwd(fmaf(v.x, aa.x, bb.x), act); v.y = act_fwd(fmaf(v.y, aa.y, bb.y), act);
+    v.z = act_fwd(fmaf(v.z, aa.z, bb.z), act); v.w = act_fwd(fmaf(v.w, aa.w, bb.w), act);
+    reinterpret_cast<float4*>(y)[i] = v;
+  }
+}
+
+// out = u*p[c] + x*q[c] + r[c]
+__global__ void __launch_bounds__(256) chan_axpby_kernel(const float* __restrict__ u, const float* __restrict__ x,
+                                                         const float* __restrict__ p, const float* __restrict__ q,
+                                                         const float* __restrict__ r, int C, long long n,
+                                                         float* __restrict__ out) {
+  const long long nv = n / 4;
+  const int CV = C / 4;
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < nv;
+       i += (long long)gridDim.x * blockDim.x) {
+    const int c = (int)(i % CV) * 4;
+    const float4 uv = __ldg(reinterpret_cast<const float4*>(u) + i);
+    const float4 xv = __ldg(reinterpret_cast<const float4*>(x) + i);
+    const float4 pp = __ldg(reinterpret_cast<const float4*>(p + c));
+    const float4 qq = __ldg(reinterpret_cast<const float4*>(q + c));
+    const float4 rr = __ldg(reinterpret_cast<const float4*>(r + c));
+    float4 o;
+    o.x = fmaf(uv.x, pp.x, fmaf(xv.x, qq.x, rr.x)); o.y = fmaf(uv.y, pp.y, fmaf(xv.y, qq.y, rr.y));
+    o.z = fmaf(uv.z, pp.z, fmaf(xv.z, qq.z, rr.z)); o.w = fmaf(uv.w, pp.w, fmaf(xv.w, qq.w, rr.w));
+    reinterpret_cast<float4*>(out)[i] = o;
+  }
+}
+
+// out[b,pix,c] = (x ? x[b,pix,c] * (a ? a[b,c] : 1) : 0) + (bb ? bb[b,c] : 0)
+__global__ void __launch_bounds__(256) sample_affine_kernel(const float* __restrict__ x,
+                                                            const float* __restrict__ a,
+                                                            const float* __restrict__ bb, long long HW, int C,
+                                                            long long n, float* __restrict__ out) {
+  const long long nv = n / 4;
+  const int CV = C / 4;
+  const long long per = HW * CV;
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < nv;
+       i += (long long)gridDim.x * blockDim.x) {
+    const int c = (int)(i % CV) * 4;
+    const long long s = i / per;
+    float4 v = x ? __ldg(reinterpret_cast<const float4*>(x) + i) : make_float4(0.f, 0.f, 0.f, 0.f);
+    if (a) {
+      const float4 av = __ldg(reinterpret_cast<const float4*>(a + s * C + c));
+      v.x *= av.x; v.y *= av.y; v.z *= av.z; v.w *= av.w;
+    }
+    if (bb) {
+      const float4 bv = __ldg(reinterpret_cast<const float4*>(bb + s * C + c));
+      v.x += bv.x; v.y += bv.y; v.z += bv.z; v.w += bv.w;
+    }
+    reinterpret_cast<float4*>(out)[i] = v;
+  }
+}
+
+__global__ void __launch_bounds__(256) act_kernel(const float* __restrict__ x, long long n, int act,
+                                                  float* __restrict__ y) {
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x)
+    y[i] = act_fwd(__ldg(x + i), act);
+}
+__global__ void __launch_bounds__(256) act_bwd_kernel(const float* __restrict__ g, const float* __restrict__ x,
+                                                      long long n, int act, float* __restrict__ dx) {
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x)
+    dx[i] = __ldg(g + i) * act_grad(__ldg(x + i), act);
+}
+
+// out[b, i] = inp[b, i] + x[b, i] * (s ? s[b] : 1)
+__global__ void __launch_bounds__(256) add_scaled_kernel(const float* __restrict__ inp, const float* __restrict__ x,
+                                                         const float* __restrict__ s, long long per, long long n,
+                                                         float* __restrict__ out) {
+  const long long nv = n / 4, perv = per / 4;
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < nv;
+       i += (long long)gridDim.x * blockDim.x) {
+    const float sc = s ? __ldg(s + i / perv) : 1.0f;
+    const float4 a = __ldg(reinterpret_cast<const float4*>(inp) + i);
+    const float4 v = __ldg(reinterpret_cast<const float4*>(x) + i);
+    float4 o;
+    o.x = fmaf(v.x, sc, a.x); o.y = fmaf(v.y, sc, a.y); o.z = fmaf(v.z, sc, a.z); o.w = fmaf(v.w, sc, a.w);
+    reinterpret_cast<float4*>(out)[i] = o;
+  }
+}
+
+// out[pix, 0:Cn] = x[pix, c0:c0+Cn]      (C, c0, Cn multiples of 4)
+__global__ void __launch_bounds__(256) chan_slice_kernel(const float* __restrict__ x, long long npix, int C, int c0,
+                                                         int Cn, float* __restrict__ out) {
+  const int CV = Cn / 4;
+  const long long nv = npix * CV;
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < nv;
+       i += (long long)gridDim.x * blockDim.x) {
+    const long long p = i / CV;
+    const int c = (int)(i - p * CV) * 4;
+    reinterpret_cast<float4*>(out)[i] = __ldg(reinterpret_cast<const float4*>(x + p * C + c0 + c));
+  }
+}
+
+// ------------------------------------------------------------------------- channel reductions
+// grid (PB pixel blocks, ceil(C/128) channel tiles, Z samples); block = 32 channel groups (float4)
+// x 8 pixel lanes.  part[((z*PB + bx)*NACC + a)*C + c] = this block's sum (double) of term a.
+struct MomentsOp {   // (x, x^2), squared in double
+  const float* x;
+  __device__ __forceinline__ void operator()(long long off, int c, double acc[2][4]) const {
+    const float4 xv = __ldg(reinterpret_cast<const float4*>(x + off));
+    const double d[4] = {(double)xv.x, (double)xv.y, (double)xv.z, (double)xv.w};
+#pragma unroll
+    for (int j = 0; j < 4; ++j) { acc[0][j] += d[j]; acc[1][j] += d[j] * d[j]; }
+  }
+};
+struct DotOp {       // x * y (y NULL: x)
+  const float* x; const float* y;
+  __device__ __forceinline__ void operator()(long long off, int c, double acc[1][4]) const {
+    const float4 xv = __ldg(reinterpret_cast<const float4*>(x + off));
+    if (y) {
+      const float4 yv = __ldg(reinterpret_cast<const float4*>(y + off));
+      acc[0][0] += (double)xv.x * (double)yv.x; acc[0][1] += (double)xv.y * (double)yv.y;
+      acc[0][2] += (double)xv.z * (double)yv.z; acc[0][3] += (double)xv.w * (double)yv.w;
+    } else {
+      acc[0][0] += (double)xv.x; acc[0][1] += (double)xv.y; acc[0][2] += (double)xv.z; acc[0][3] += (double)xv.w;
+    }
+  }
+};
+struct BnActBwdOp {  // gu = g * act'(x*a+b) (stored if gu != NULL); terms (gu, gu*x)
+  const float* g; const float* x; const float* a; const float* b; float* gu; int act;
+  __device__ __forceinline__ void operator()(long long off, int c, double acc[2][4]) const {
+    float4 gv = __ldg(reinterpret_cast<const float4*>(g + off));
+    const float4 xv = __ldg(reinterpret_cast<const float4*>(x + off));
+    if (act != ACT_NONE) {
+      const float4 aa = __ldg(reinterpret_cast<const float4*>(a + c));
+      const float4 bb = __ldg(reinterpret_cast<const float4*>(b + c));
+      gv.x *= act_grad(fmaf(xv.x, aa.x, bb.x), act); gv.y *= act_grad(fmaf(xv.y, aa.y, bb.y), act);
+      gv.z *= act_grad(fmaf(xv.z, aa.z, bb.z), act); gv.w *= act_grad(fmaf(xv.w, aa.w, bb.w), act);
+      if (gu) *reinterpret_cast<float4*>(gu + off) = gv;
+    }
+    acc[0][0] += (double)gv.x; acc[0][1] += (double)gv.y; acc[0][2] += (double)gv.z; acc[0][3] += (double)gv.w;
+    acc[1][0] += (double)gv.x * (double)xv.x; acc[1][1] += (double)gv.y * (double)xv.y;
+    acc[1][2] += (double)gv.z * (double)xv.z; acc[1][3] += (double)gv.w * (double)xv.w;
+  }
+};
+
+template <int NACC, class Op>
+__global__ void __launch_bounds__(256) chan_reduce_kernel(Op op, int C, long long npix, double* __restrict__ part) {
+  __shared__ double s_part[8][32][NACC * 4 + 1];
+  const int cg = threadIdx.x & 31, pl = threadIdx.x >> 5;
+  const int c = blockIdx.y * 128 + cg * 4;
+  const long long per = (npix + gridDim.x - 1) / gridDim.x;
+  const long long p0 = (long long)blockIdx.x * per;
+  const long long p1 = p0 + per < npix ? p0 + per : npix;
+  const long long zoff = (long long)blockIdx.z * npix;
+  double acc[NACC][4];
+#pragma unroll
+  for (int a = 0; a < NACC; ++a)
+#pragma unroll
+    for (int j = 0; j < 4; ++j) acc[a][j] = 0.0;
+  if (c < C)
+    for (long long p = p0 + pl; p < p1; p += 8) op((zoff + p) * C + c, c, acc);
+#pragma unroll
+  for (int a = 0; a < NACC; ++a)
+#pragma unroll
+    for (int j = 0; j < 4; ++j) s_part[pl][cg][a * 4 + j] = acc[a][j];
+  __syncthreads();
+  if (pl == 0 && c < C) {
+    const size_t base = ((size_t)blockIdx.z * gridDim.x + blockIdx.x) * NACC;
+#pragma unroll
+    for (int a = 0; a < NACC; ++a)
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        double t = s_part[0][cg][a * 4 + j];
+        for (int l = 1; l < 8; ++l) t += s_part[l][cg][a * 4 + j];
+        part[(base + a) * C + c + j] = t;
+      }
+  }
+}
+
+// out[z*n + i] = scale * sum_bx part[(z*PB + bx)*n + i]
+template <class T>
+__global__ void __launch_bounds__(256) reduce_parts_kernel(const double* __restrict__ part, int PB, int n, int Z,
+                                                           double scale, T* __restrict__ out) {
+  const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= (long long)n * Z) return;
+  const int z = (int)(i / n), k = (int)(i - (long long)z * n);
+  double t = 0.0;
+  for (int b = 0; b < PB; ++b) t += part[((size_t)z * PB + b) * n + k];
+  out[i] = (T)(t * scale);
+}
+
+static int reduce_pb(long long npix, int Z) {
+  long long b = npix / 64;
+  if (b < 1) b = 1;
+  long long cap = 1184 / (Z > 0 ? Z : 1);
+  if (cap < 4) cap = 4;
+  return (int)(b > cap ? cap : b);
+}
+
+// ------------------------------------------------------------------------------- depthwise conv
+// w [R*R][C] (tap-major), x [N,H,W,C], y [N,P,Q,C]; pad (pt, pl) low, the high side is implied.
+template <int R>
+__global__ void __launch_bounds__(256) dwconv_fwd_kernel(const float* __restrict__ x, const float* __restrict__ w,
+                                                         int N, int H, int W, int C, int st, int pt, int pl, int P,
+                                                         int Q, float* __restrict__ y) {
+  const int CV = C / 4;
+  const long long nv = (long long)N * P * Q * CV;
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < nv;
+       i += (long long)gridDim.x * blockDim.x) {
+    const int c = (int)(i % CV) * 4;
+    long long pix = i / CV;
+    const int q = (int)(pix % Q); pix /= Q;
+    const int p = (int)(pix % P);
+    const int n = (int)(pix / P);
+    float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
+#pragma unroll
+    for (int r = 0; r < R; ++r) {
+      const int iy = p * st + r - pt;
+      if (iy < 0 || iy >= H) continue;
+#pragma unroll
+      for (int s = 0; s < R; ++s) {
+        const int ix = q * st + s - pl;
+        if (ix < 0 || ix >= W) continue;
+        const float4 xv = __ldg(reinterpret_cast<const float4*>(x + (((size_t)n * H + iy) * W + ix) * C + c));
+        const float4 wv = __ldg(reinterpret_cast<const float4*>(w + (size_t)(r * R + s) * C + c));
+        acc.x = fmaf(xv.x, wv.x, acc.x); acc.y = fmaf(xv.y, wv.y, acc.y);
+        acc.z = fmaf(xv.z, wv.z, acc.z); acc.w = fmaf(xv.w, wv.w, acc.w);
+      }
+    }
+    reinterpret_cast<float4*>(y)[i] = acc;
+  }
+}
+
+// dx[n,iy,ix,c] = sum over taps (r,s) with (iy+pt-r) = p*st, (ix+pl-s) = q*st of w[r,s,c] * g[n,p,q,c]
+template <int R>
+__global__ void __launch_bounds__(256) dwconv_dgrad_kernel(const float* __restrict__ g, const float* __restrict__ w,
+                                                           int N, int H, int W, int C, int st, int pt, int pl, int P,
+                                                           int Q, float* __restrict__ dx) {
+  const int CV = C / 4;
+  const long long nv = (long long)N * H * W * CV;
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < nv;
+       i += (long long)gridDim.x * blockDim.x) {
+    const int c = (int)(i % CV) * 4;
+    long long pix = i / CV;
+    const int ix = (int)(pix % W); pix /= W;
+    const int iy = (int)(pix % H);
+    const int n = (int)(pix / H);
+    float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
+#pragma unroll
+    for (int r = 0; r < R; ++r) {
+      const int ty = iy + pt - r;
+      if (ty < 0 || (ty % st) != 0) continue;
+      const int p = ty / st;
+      if (p >= P) continue;
+#pragma unroll
+      for (int s = 0; s < R; ++s) {
+        const int tx = ix + pl - s;
+        if (tx < 0 || (tx % st) != 0) continue;
+        const int q = tx / st;
+        if (q >= Q) continue;
+        const float4 gv = __ldg(reinterpret_cast<const float4*>(g + (((size_t)n * P + p) * Q + q) * C + c));
+        const float4 wv = __ldg(reinterpret_cast<const float4*>(w + (size_t)(r * R + s) * C + c));
+        acc.x = fmaf(gv.x, wv.x, acc.x); acc.y = fmaf(gv.y, wv.y, acc.y);
+        acc.z = fmaf(gv.z, wv.z, acc.z); acc.w = fmaf(gv.w, wv.w, acc.w);
+      }
+    }
+    reinterpret_cast<float4*>(dx)[i] = acc;
+  }
+}
+
+// part[bx][tap][c] = sum over the block's output pixels of g[pix,c] * x[shifted pix,c]; per-thread
+// fp32 partial sums over <= a few hundred pixels, the cross-lane / cross-block stages in double.
+template <int R>
+__global__ void __launch_bounds__(256) dwconv_wgrad_kernel(const float* __restrict__ x, const float* __restrict__ g,
+                                                           int N, int H, int W, int C, int st, int pt, int pl, int P,
+                                                           int Q, double* __restrict__ part) {
+  __shared__ float s_red[8][32][4];
+  const int cg = threadIdx.x & 31, pl_ = threadIdx.x >> 5;
+  const int c = blockIdx.y * 128 + cg * 4;
+  const long long npix = (long long)N * P * Q;
+  const long long per = (npix + gridDim.x - 1) / gridDim.x;
+  const long long p0 = (long long)blockIdx.x * per;
+  const long long p1 = p0 + per < npix ? p0 + per : npix;
+  float4 acc[R * R];
+#pragma unroll
+  for (int t = 0; t < R * R; ++t) acc[t] = make_float4(0.f, 0.f, 0.f, 0.f);
+  if (c < C) {
+    for (long long pix = p0 + pl_; pix < p1; pix += 8) {
+      const int q = (int)(pix % Q);
+      const long long t2 = pix / Q;
+      const int p = (int)(t2 % P);
+      const int n = (int)(t2 / P);
+      const float4 gv = __ldg(reinterpret_cast<const float4*>(g + (size_t)pix * C + c));
+#pragma unroll
+      for (int r = 0; r < R; ++r) {
+        const int iy = p * st + r - pt;
+        if (iy < 0 || iy >= H) continue;
+#pragma unroll
+        for (int s = 0; s < R; ++s) {
+          const int ix = q * st + s - pl;
+          if (ix < 0 || ix >= W) continue;
+          const float4 xv = __ldg(reinterpret_cast<const float4*>(x + (((size_t)n * H + iy) * W + ix) * C + c));
+          float4& a = acc[r * R + s];
+          a.x = fmaf(gv.x, xv.x, a.x); a.y = fmaf(gv.y, xv.y, a.y);
+          a.z = fmaf(gv.z, xv.z, a.z); a.w = fmaf(gv.w, xv.w, a.w);
+        }
+      }
+    }
+  }
+#pragma unroll 1
+  for (int t = 0; t < R * R; ++t) {
+    float4 a = make_float4(0.f, 0.f, 0.f, 0.f);
+    // static indexing of acc[] (registers): select by an unrolled compare chain
+#pragma unroll
+    for (int u = 0; u < R * R; ++u)
+      if (u == t) a = acc[u];
+    s_red[pl_][cg][0] = a.x; s_red[pl_][cg][1] = a.y; s_red[pl_][cg][2] = a.z; s_red[pl_][cg][3] = a.w;
+    __syncthreads();
+    if (pl_ == 0 && c < C) {
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        double tot = (double)s_red[0][cg][j];
+        for (int l = 1; l < 8; ++l) tot += (double)s_red[l][cg][j];
+        part[((size_t)blockIdx.x * (R * R) + t) * C + c + j] = tot;
+      }
+    }
+    __syncthreads();
+  }
+}
+
+// ------------------------------------------------------------------- strided dense wgrad (C == 4)
+// thread -> (tap, k); part[bx][(tap*4 + c)*K + k] = sum over the block's output pixels.
+__global__ void __launch_bounds__(1024) wgrad_strided_c4_kernel(const float* __restrict__ x,
+                                                                const float* __restrict__ g, int N, int H, int W,
+                                                                int K, int R, int S, int st, int pt, int pl, int P,
+                                                                int Q, double* __restrict__ part) {
+  const int t = threadIdx.x;
+  const int tap = t / K, k = t - tap * K;
+  if (tap >= R * S) return;
+  const int r = tap / S, s = tap - r * S;
+  const long long npix = (long long)N * P * Q;
+  const long long per = (npix + gridDim.x - 1) / gridDim.x;
+  const long long p0 = (long long)blockIdx.x * per;
+  const long long p1 = p0 + per < npix ? p0 + per : npix;
+  float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
+  for (long long pix = p0; pix < p1; ++pix) {
+    const int q = (int)(pix % Q);
+    const long long t2 = pix / Q;
+    const int p = (int)(t2 % P);
+    const int n = (int)(t2 / P);
+    const int iy = p * st + r - pt, ix = q * st + s - pl;
+    if (iy < 0 || iy >= H || ix < 0 || ix >= W) continue;
+    const float gv = __ldg(g + (size_t)pix * K + k);
+    const float4 xv = __ldg(reinterpret_cast<const float4*>(x + (((size_t)n * H + iy) * W + ix) * 4));
+    acc.x = fmaf(gv, xv.x, acc.x); acc.y = fmaf(gv, xv.y, acc.y);
+    acc.z = fmaf(gv, xv.z, acc.z); acc.w = fmaf(gv, xv.w, acc.w);
+  }
+  double* dst = part + (size_t)blockIdx.x * (R * S * 4 * K);
+  dst[(tap * 4 + 0) * K + k] = (double)acc.x; dst[(tap * 4 + 1) * K + k] = (double)acc.y;
+  dst[(tap * 4 + 2) * K + k] = (double)acc.z; dst[(tap * 4 + 3) * K + k] = (double)acc.w;
+}
+
+// ----------------------------------------------------------------------------- loss gradients
+// dlogits[n,k,p] = scale * (softmax_k(logits[n,:,p]) - [k == bin]) on valid pixels, 0 elsewhere
+// (CrossEntropyDepth, loss_utils.py:477-527; bin_depths 'UD', depth_utils.py:346-383).  NCHW.
+__global__ void __launch_bounds__(256) ce_depth_bwd_kernel(const float* __restrict__ logits,
+                                                           const float* __restrict__ label_mm, int N, int D,
+                                                           long long HW, float dmin, float bin_size,
+                                                           const float* __restrict__ scale_dev,
+                                                           float* __restrict__ dlogits) {
+  const float scale = __ldg(scale_dev);
+  const long long total = (long long)N * HW;
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total;
+       i += (long long)gridDim.x * blockDim.x) {
+    const long long n = i / HW, p = i - n * HW;
+    const float d = __ldg(label_mm + i);
+    const float idxf = __fdiv_rn(__fsub_rn(d, dmin), bin_size);
+    const bool bad = (idxf < 0.0f) || (idxf > (float)D) || !isfinite(idxf);
+    const int bin = bad ? D : (int)idxf;
+    const float* src = logits + (size_t)n * D * HW + p;
+    float* dst = dlogits + (size_t)n * D * HW + p;
+    if (bin == D) {
+      for (int k = 0; k < D; ++k) dst[(size_t)k * HW] = 0.f;
+      continue;
+    }
+    float m = -INFINITY;
+    for (int k = 0; k < D; ++k) m = fmaxf(m, __ldg(src + (size_t)k * HW));
+    float ssum = 0.f;
+    for (int k = 0; k < D; ++k) ssum += expf(__ldg(src + (size_t)k * HW) - m);
+    const float inv = 1.0f / ssum;
+    for (int k = 0; k < D; ++k) {
+      const float pk = expf(__ldg(src + (size_t)k * HW) - m) * inv;
+      dst[(size_t)k * HW] = scale * (pk - (k == bin ? 1.0f : 0.0f));
+    }
+  }
+}
+
+// dpred = scale * (pred - gt) where gt is not +-inf, 0 elsewhere   (MSELoss, loss_utils.py:606-647)
+__global__ void __launch_bounds__(256) masked_mse_bwd_kernel(const float* __restrict__ pred,
+                                                             const float* __restrict__ gt, long long n,
+                                                             const float* __restrict__ scale_dev,
+                                                             float* __restrict__ dpred) {
+  const float scale = __ldg(scale_dev);
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n;
+       i += (long long)gridDim.x * blockDim.x) {
+    const float t = __ldg(gt + i);
+    dpred[i] = isinf(t) ? 0.f : scale * (__ldg(pred + i) - t);
+  }
+}
+
+}  // namespace creste
+
+using namespace creste;
+
+#define ELT_GRID(nvec) grid_cap2((nvec), 256, 148 * 16)
+
+extern "C" size_t creste_chan_reduce_workspace_bytes(long long npix, int C, int nacc, int Z) {
+  return (size_t)reduce_pb(npix, Z) * (Z > 0 ? Z : 1) * nacc * C * sizeof(double);
+}
+
+extern "C" int creste_chan_moments(const float* x, long long npix, int C, double* out2, void* ws, size_t ws_bytes,
+                                   void* stream) {
+  CRESTE_CHECK_ARG(x && out2 && ws && npix > 0 && C > 0 && C % 4 == 0, "creste_chan_moments: bad args");
+  CRESTE_CHECK_ARG(ws_bytes >= creste_chan_reduce_workspace_bytes(npix, C, 2, 1), "creste_chan_moments: workspace");
+  cudaStream_t st = (cudaStream_t)stream;
+  const int PB = reduce_pb(npix, 1);
+  chan_reduce_kernel<2, MomentsOp><<<dim3(PB, ceil_div(C, 128), 1), 256, 0, st>>>(MomentsOp{x}, C, npix, (double*)ws);
+  int rc = launch_check("chan_reduce_kernel<moments>");
+  if (rc) return rc;
+  reduce_parts_kernel<double><<<ceil_div(2 * C, 256), 256, 0, st>>>((const double*)ws, PB, 2 * C, 1, 1.0, out2);
+  return launch_check("reduce_parts_kernel");
+}
+
+extern "C" int creste_chan_affine_act(const float* x, const float* a, const float* b, long long npix, int C, int act,
+                                      float* y, void* stream) {
+  CRESTE_CHECK_ARG(x && y && npix > 0 && C > 0 && C % 4 == 0 && act >= 0 && act <= 2, "creste_chan_affine_act: bad args");
+  const long long n = npix * C;
+  chan_affine_act_kernel<<<ELT_GRID(n / 4), 256, 0, (cudaStream_t)stream>>>(x, a, b, C, n, act, y);
+  return launch_check("chan_affine_act_kernel");
+}
+
+extern "C" int creste_bn_act_bwd(const float* g, const float* x, const float* a, const float* b, long long npix, int C,
+                                 int act, float* gu, double* sums2, void* ws, size_t ws_bytes, void* stream) {
+  CRESTE_CHECK_ARG(g && x && sums2 && ws && npix > 0 && C > 0 && C % 4 == 0 && act >= 0 && act <= 2,
+                   "creste_bn_act_bwd: bad args");
+  CRESTE_CHECK_ARG(act == ACT_NONE || (a && b && gu), "creste_bn_act_bwd: act needs a, b and gu");
+  CRESTE_CHECK_ARG(ws_bytes >= creste_chan_reduce_workspace_bytes(npix, C, 2, 1), "creste_bn_act_bwd: workspace");
+  cudaStream_t st = (cudaStream_t)stream;
+  const int PB = reduce_pb(npix, 1);
+  chan_reduce_kernel<2, BnActBwdOp><<<dim3(PB, ceil_div(C, 128), 1), 256, 0, st>>>(BnActBwdOp{g, x, a, b, gu, act}, C,
+                                                                                 npix, (double*)ws);
+  int rc = launch_check("chan_reduce_kernel<bn_act_bwd>");
+  if (rc) return rc;
+  reduce_parts_kernel<double><<<ceil_div(2 * C, 256), 256, 0, st>>>((const double*)ws, PB, 2 * C, 1, 1.0, sums2);
+  return launch_check("reduce_parts_kernel");
+}
+
+extern "C" int creste_chan_axpby(const float* u, const float* x, const float* p, const float* q, const float* r,
+                                 long long npix, int C, float* out, void* stream) {
+  CRESTE_CHECK_ARG(u && x && p && q && r && out && npix > 0 && C > 0 && C % 4 == 0, "creste_chan_axpby: bad args");
+  const long long n = npix * C;
+  chan_axpby_kernel<<<ELT_GRID(n / 4), 256, 0, (cudaStream_t)stream>>>(u, x, p, q, r, C, n, out);
+  return launch_check("chan_axpby_kernel");
+}
+
+static int dw_geom_ok(int N, int H, int W, int C, int R, int st, int P, int Q) {
+  return N > 0 && H > 0 && W > 0 && C > 0 && C % 4 == 0 && (R == 3 || R == 5) && (st == 1 || st == 2) && P > 0 && Q > 0;
+}
+
+extern "C" int creste_dwconv_fwd(const float* x, const float* w, int N, int H, int W, int C, int R, int stride,
+                                 int pad_t, int pad_l, int P, int Q, float* y, void* stream) {
+  CRESTE_CHECK_ARG(x && w && y && dw_geom_ok(N, H, W, C, R, stride, P, Q), "creste_dwconv_fwd: bad args");
+  cudaStream_t st = (cudaStream_t)stream;
+  const int grid = ELT_GRID((long long)N * P * Q * (C / 4));
+  if (R == 3) dwconv_fwd_kernel<3><<<grid, 256, 0, st>>>(x, w, N, H, W, C, stride, pad_t, pad_l, P, Q, y);
+  else dwconv_fwd_kernel<5><<<grid, 256, 0, st>>>(x, w, N, H, W, C, stride, pad_t, pad_l, P, Q, y);
+  return launch_check("dwconv_fwd_kernel");
+}
+
+extern "C" int creste_dwconv_dgrad(const float* g, const float* w, int N, int H, int W, int C, int R, int stride,
+                                   int pad_t, int pad_l, int P, int Q, float* dx, void* stream) {
+  CRESTE_CHECK_ARG(g && w && dx && dw_geom_ok(N, H, W, C, R, stride, P, Q), "creste_dwconv_dgrad: bad args");
+  cudaStream_t st = (cudaStream_t)stream;
+  const int grid = ELT_GRID((long long)N * H * W * (C / 4));
+  if (R == 3) dwconv_dgrad_kernel<3><<<grid, 256, 0, st>>>(g, w, N, H, W, C, stride, pad_t, pad_l, P, Q, dx);
+  else dwconv_dgrad_kernel<5><<<grid, 256, 0, st>>>(g, w, N, H, W, C, stride, pad_t, pad_l, P, Q, dx);
+  return launch_check("dwconv_dgrad_kernel");
+}
+
+extern "C" size_t creste_dwconv_wgrad_workspace_bytes(int N, int C, int R, int P, int Q) {
+  return (size_t)reduce_pb((long long)N * P * Q, 1) * R * R * C * sizeof(double);
+}
+
+extern "C" int creste_dwconv_wgrad(const float* x, const float* g, int N, int H, int W, int C, int R, int stride,
+                                   int pad_t, int pad_l, int P, int Q, float* dw, void* ws, size_t ws_bytes,
+                                   void* stream) {
+  CRESTE_CHECK_ARG(x && g && dw && ws && dw_geom_ok(N, H, W, C, R, stride, P, Q), "creste_dwconv_wgrad: bad args");
+  CRESTE_CHECK_ARG(ws_bytes >= creste_dwconv_wgrad_workspace_bytes(N, C, R, P, Q), "creste_dwconv_wgrad: workspace");
+  cudaStream_t st = (cudaStream_t)stream;
+  const int PB = reduce_pb((long long)N * P * Q, 1);
+  const dim3 grid(PB, ceil_div(C, 128), 1);
+  if (R == 3) dwconv_wgrad_kernel<3><<<grid, 256, 0, st>>>(x, g, N, H, W, C, stride, pad_t, pad_l, P, Q, (double*)ws);
+  else dwconv_wgrad_kernel<5><<<grid, 256, 0, st>>>(x, g, N, H, W, C, stride, pad_t, pad_l, P, Q, (double*)ws);
+  int rc = launch_check("dwconv_wgrad_kernel");
+  if (rc) return rc;
+  reduce_parts_kernel<float><<<ceil_div(R * R * C, 256), 256, 0, st>>>((const double*)ws, PB, R * R * C, 1, 1.0, dw);
+  return launch_check("reduce_parts_kernel");
+}
+
+extern "C" int creste_sample_dot(const float* x, const float* y, int B, long long HW, int C, float scale, float* out,
+                                 void* ws, size_t ws_bytes, void* stream) {
+  CRESTE_CHECK_ARG(x && out && ws && B > 0 && HW > 0 && C > 0 && C % 4 == 0, "creste_sample_dot: bad args");
+  CRESTE_CHECK_ARG(ws_bytes >= creste_chan_reduce_workspace_bytes(HW, C, 1, B), "creste_sample_dot: workspace");
+  cudaStream_t st = (cudaStream_t)stream;
+  const int PB = reduce_pb(HW, B);
+  chan_reduce_kernel<1, DotOp><<<dim3(PB, ceil_div(C, 128), B), 256, 0, st>>>(DotOp{x, y}, C, HW, (double*)ws);
+  int rc = launch_check("chan_reduce_kernel<sample_dot>");
+  if (rc) return rc;
+  reduce_parts_kernel<float><<<ceil_div(B * C, 256), 256, 0, st>>>((const double*)ws, PB, C, B, (double)scale, out);
+  return launch_check("reduce_parts_kernel");
+}
+
+extern "C" int creste_sample_affine(const float* x, const float* a, const float* b, int B, long long HW, int C,
+                                    float* out, void* stream) {
+  CRESTE_CHECK_ARG(out && (x || b) && B > 0 && HW > 0 && C > 0 && C % 4 == 0, "creste_sample_affine: bad args");
+  const long long n = (long long)B * HW * C;
+  sample_affine_kernel<<<ELT_GRID(n / 4), 256, 0, (cudaStream_t)stream>>>(x, a, b, HW, C, n, out);
+  return launch_check("sample_affine_kernel");
+}
+
+extern "C" int creste_act(const float* x, long long n, int act, float* y, void* stream) {
+  CRESTE_CHECK_ARG(x && y && n > 0 && act >= 0 && act <= 3, "creste_act: bad args");
+  act_kernel<<<ELT_GRID(n), 256, 0, (cudaStream_t)stream>>>(x, n, act, y);
+  return launch_check("act_kernel");
+}
+
+extern "C" int creste_act_bwd(const float* g, const float* x, long long n, int act, float* dx, void* stream) {
+  CRESTE_CHECK_ARG(g && x && dx && n > 0 && act >= 0 && act <= 3, "creste_act_bwd: bad args");
+  act_bwd_kernel<<<ELT_GRID(n), 256, 0, (cudaStream_t)stream>>>(g, x, n, act, dx);
+  return launch_check("act_bwd_kernel");
+}
+
+extern "C" int creste_add_scaled(const float* inp, const float* x, const float* s, int B, long long per, float* out,
+                                 void* stream) {
+  CRESTE_CHECK_ARG(inp && x && out && B > 0 && per > 0 && per % 4 == 0, "creste_add_scaled: bad args");
+  const long long n = (long long)B * per;
+  add_scaled_kernel<<<ELT_GRID(n / 4), 256, 0, (cudaStream_t)stream>>>(inp, x, s, per, n, out);
+  return launch_check("add_scaled_kernel");
+}
+
+extern "C" int creste_chan_slice(const float* x, long long npix, int C, int c0, int Cn, float* out, void* stream) {
+  CRESTE_CHECK_ARG(x && out && npix > 0 && C % 4 == 0 && c0 % 4 == 0 && Cn % 4 == 0 && c0 >= 0 && Cn > 0 &&
+                       c0 + Cn <= C, "creste_chan_slice: bad args");
+  chan_slice_kernel<<<ELT_GRID(npix * (Cn / 4)), 256, 0, (cudaStream_t)stream>>>(x, npix, C, c0, Cn, out);
+  return launch_check("chan_slice_kernel");
+}
+
+static int wgrad_strided_pb(long long npix) {
+  long long b = npix / 256;
+  if (b < 1) b = 1;
+  return (int)(b > 592 ? 592 : b);
+}
+
+extern "C" size_t creste_wgrad_strided_workspace_bytes(int N, int P, int Q, int C, int K, int R, int S) {
+  return (size_t)wgrad_strided_pb((long long)N * P * Q) * R * S * C * K * sizeof(double);
+}
+
+/* dw [R*S*C][K] of a strided dense conv with C == 4 input channels (the EfficientNet stem). */
+extern "C" int creste_wgrad_strided(const float* x, const float* g, int N, int H, int W, int C, int K, int R, int S,
+                                    int stride, int pad_t, int pad_l, int P, int Q, float* dw, void* ws,
+                                    size_t ws_bytes, void* stream) {
+  CRESTE_CHECK_ARG(x && g && dw && ws && N > 0 && H > 0 && W > 0 && K > 0 && R > 0 && S > 0 && stride > 0 && P > 0 &&
+                       Q > 0, "creste_wgrad_strided: bad args");
+  CRESTE_CHECK_ARG(C == 4 && R * S * K <= 1024, "creste_wgrad_strided: serves C == 4 and R*S*K <= 1024 only");
+  CRESTE_CHECK_ARG(ws_bytes >= creste_wgrad_strided_workspace_bytes(N, P, Q, C, K, R, S), "creste_wgrad_strided: workspace");
+  cudaStream_t st = (cudaStream_t)stream;
+  const int PB = wgrad_strided_pb((long long)N * P * Q);
+  const int threads = (R * S * K + 31) / 32 * 32;
+  wgrad_strided_c4_kernel<<<PB, threads, 0, st>>>(x, g, N, H, W, K, R, S, stride, pad_t, pad_l, P, Q, (double*)ws);
+  int rc = launch_check("wgrad_strided_c4_kernel");
+  if (rc) return rc;
+  const int n = R * S * C * K;
+  reduce_parts_kernel<float><<<ceil_div(n, 256), 256, 0, st>>>((const double*)ws, PB, n, 1, 1.0, dw);
+  return launch_check("reduce_parts_kernel");
+}
+
+extern "C" int creste_ce_depth_bwd(const float* logits_nchw, const float* label_mm, int N, int D, long long HW,
+                                   float depth_min, float depth_max, const float* scale_dev, float* dlogits,
+                                   void* stream) {
+  CRESTE_CHECK_ARG(logits_nchw && label_mm && scale_dev && dlogits && N > 0 && D > 0 && HW > 0,
+                   "creste_ce_depth_bwd: bad args");
+  const float bin_size = (float)(((double)depth_max - (double)depth_min) / (double)D);
+  ce_depth_bwd_kernel<<<grid_cap2((long long)N * HW, 256, 148 * 8), 256, 0, (cudaStream_t)stream>>>(
+      logits_nchw, label_mm, N, D, HW, depth_min, bin_size, scale_dev, dlogits);
+  return launch_check("ce_depth_bwd_kernel");
+}
+
+extern "C" int creste_masked_mse_bwd(const float* pred, const float* gt, long long n, const float* scale_dev,
+                                     float* dpred, void* stream) {
+  CRESTE_CHECK_ARG(pred && gt && scale_dev && dpred && n > 0, "creste_masked_mse_bwd: bad args");
+  masked_mse_bwd_kernel<<<ELT_GRID(n), 256, 0, (cudaStream_t)stream>>>(pred, gt, n, scale_dev, dpred);
+  return launch_check("masked_mse_bwd_kernel");
+}

@@ -34,6 +34,19 @@ def require_eval(module):
             "the sm_100a engine implements.  No PyTorch fallback is provided on purpose.")
 
 
+# Source of the drop-connect uniforms (efficientnet_pytorch.utils.drop_connect draws
+# torch.rand([B,1,1,1]) per residual block).  Tests replace it with a CPU-generator-backed sampler so
+# that the masks equal the reference's on the same seed; the default draws on the device.
+drop_connect_rand = None
+
+
+def drop_connect_scale(B, rate, device):
+    """Per-sample multiplier floor(keep + U[0,1)) / keep of efficientnet_pytorch's drop_connect."""
+    keep = 1.0 - rate
+    u = drop_connect_rand(B, device) if drop_connect_rand is not None else torch.rand(B, device=device)
+    return (torch.floor(keep + u.float()) / keep).contiguous()
+
+
 def pick_mode(x_shape, K, R, S, stride, pad, mode):
     """Requested precision, or the next stricter one the shape is served by:
     3xfp16 -> 3xtf32 -> fp32 (never a looser one)."""

@@ -513,3 +513,192 @@ def masked_mse(pred, gt):
     check(lib().creste_masked_mse(ptr(pred), ptr(gt), C.c_longlong(pred.numel()), ptr(acc), stream()),
           "creste_masked_mse")
     return acc
+
+
+# ------------------------------------------------------- stage-1 backbone training primitives
+def _npix_c(x):
+    Cc = x.shape[-1]
+    return x.numel() // Cc, Cc
+
+
+def chan_moments(x):
+    """-> float64 [2, C]: per-channel (sum x, sum x^2) over all leading dims; any C % 4 == 0."""
+    x = x.contiguous()
+    npix, Cc = _npix_c(x)
+    out = torch.empty(2, Cc, dtype=torch.float64, device=x.device)
+    n = lib().creste_chan_reduce_workspace_bytes(C.c_longlong(npix), Cc, 2, 1)
+    ws = _ws(n, x.device)
+    check(lib().creste_chan_moments(ptr(x), C.c_longlong(npix), Cc, ptr(out), ptr(ws), C.c_size_t(n),
+                                    stream()), "creste_chan_moments")
+    return out
+
+
+def chan_affine_act(x, a, b, act):
+    """y = act(x * a[c] + b[c]), act in {'none', 'relu', 'swish'}."""
+    x = x.contiguous()
+    npix, Cc = _npix_c(x)
+    y = torch.empty_like(x)
+    check(lib().creste_chan_affine_act(ptr(x), ptr(a), ptr(b), C.c_longlong(npix), Cc, ACT[act], ptr(y),
+                                       stream()), "creste_chan_affine_act")
+    return y
+
+
+def bn_act_bwd(g, x, a, b, act):
+    """-> (gu, sums float64 [2, C]) with gu = g * act'(x*a+b) (gu is g itself for act 'none') and
+    sums = (sum gu, sum gu*x) per channel."""
+    g, x = g.contiguous(), x.contiguous()
+    npix, Cc = _npix_c(x)
+    gu = torch.empty_like(g) if ACT[act] != 0 else None
+    sums = torch.empty(2, Cc, dtype=torch.float64, device=x.device)
+    n = lib().creste_chan_reduce_workspace_bytes(C.c_longlong(npix), Cc, 2, 1)
+    ws = _ws(n, x.device)
+    check(lib().creste_bn_act_bwd(ptr(g), ptr(x), ptr(a), ptr(b), C.c_longlong(npix), Cc, ACT[act], ptr(gu),
+                                  ptr(sums), ptr(ws), C.c_size_t(n), stream()), "creste_bn_act_bwd")
+    return (gu if gu is not None else g), sums
+
+
+def chan_axpby(u, x, p, q, r):
+    """out = u*p[c] + x*q[c] + r[c]."""
+    u, x = u.contiguous(), x.contiguous()
+    npix, Cc = _npix_c(x)
+    out = torch.empty_like(x)
+    check(lib().creste_chan_axpby(ptr(u), ptr(x), ptr(p.contiguous()), ptr(q.contiguous()), ptr(r.contiguous()),
+                                  C.c_longlong(npix), Cc, ptr(out), stream()), "creste_chan_axpby")
+    return out
+
+
+def _dw_out(H, W, R, stride, pad):
+    pt, pb, pl, pr = pad
+    return (H + pt + pb - R) // stride + 1, (W + pl + pr - R) // stride + 1
+
+
+def dwconv_fwd(x_nhwc, w_rsc, R, stride, pad):
+    """Raw depthwise conv: x [N,H,W,C], w [R*R, C], pad = (top, bottom, left, right)."""
+    x_nhwc = x_nhwc.contiguous()
+    N, H, W, Cc = x_nhwc.shape
+    P, Q = _dw_out(H, W, R, stride, pad)
+    y = torch.empty(N, P, Q, Cc, device=x_nhwc.device)
+    check(lib().creste_dwconv_fwd(ptr(x_nhwc), ptr(w_rsc.contiguous()), N, H, W, Cc, R, stride, pad[0], pad[2],
+                                  P, Q, ptr(y), stream()), "creste_dwconv_fwd")
+    return y
+
+
+def dwconv_dgrad(g_nhwc, w_rsc, x_shape, R, stride, pad):
+    g_nhwc = g_nhwc.contiguous()
+    N, H, W, Cc = x_shape
+    _, P, Q, _ = g_nhwc.shape
+    dx = torch.empty(N, H, W, Cc, device=g_nhwc.device)
+    check(lib().creste_dwconv_dgrad(ptr(g_nhwc), ptr(w_rsc.contiguous()), N, H, W, Cc, R, stride, pad[0],
+                                    pad[2], P, Q, ptr(dx), stream()), "creste_dwconv_dgrad")
+    return dx
+
+
+def dwconv_wgrad(x_nhwc, g_nhwc, R, stride, pad):
+    """-> dw [R*R, C]."""
+    x_nhwc, g_nhwc = x_nhwc.contiguous(), g_nhwc.contiguous()
+    N, H, W, Cc = x_nhwc.shape
+    _, P, Q, _ = g_nhwc.shape
+    dw = torch.empty(R * R, Cc, device=x_nhwc.device)
+    n = lib().creste_dwconv_wgrad_workspace_bytes(N, Cc, R, P, Q)
+    ws = _ws(n, x_nhwc.device)
+    check(lib().creste_dwconv_wgrad(ptr(x_nhwc), ptr(g_nhwc), N, H, W, Cc, R, stride, pad[0], pad[2], P, Q,
+                                    ptr(dw), ptr(ws), C.c_size_t(n), stream()), "creste_dwconv_wgrad")
+    return dw
+
+
+def sample_dot(x, y=None, scale=1.0):
+    """out[b, c] = scale * sum_pix x[b,pix,c] * y[b,pix,c]  (y None: plain sum) -> [B,1,1,C]."""
+    x = x.contiguous()
+    y = None if y is None else y.contiguous()
+    B, Cc = x.shape[0], x.shape[-1]
+    HW = x.numel() // (B * Cc)
+    out = torch.empty(B, 1, 1, Cc, device=x.device)
+    n = lib().creste_chan_reduce_workspace_bytes(C.c_longlong(HW), Cc, 1, B)
+    ws = _ws(n, x.device)
+    check(lib().creste_sample_dot(ptr(x), ptr(y), B, C.c_longlong(HW), Cc, C.c_float(scale), ptr(out), ptr(ws),
+                                  C.c_size_t(n), stream()), "creste_sample_dot")
+    return out
+
+
+def sample_affine(x, a=None, b=None, shape=None):
+    """out[b,pix,c] = (x * a[b,c] if x is not None else 0) + b[b,c]; `shape` when x is None."""
+    shape = tuple(x.shape) if x is not None else tuple(shape)
+    B, Cc = shape[0], shape[-1]
+    HW = 1
+    for d in shape[1:-1]:
+        HW *= d
+    dev = (x if x is not None else b).device
+    out = torch.empty(shape, device=dev)
+    check(lib().creste_sample_affine(ptr(None if x is None else x.contiguous()),
+                                     ptr(None if a is None else a.contiguous()),
+                                     ptr(None if b is None else b.contiguous()), B, C.c_longlong(HW), Cc,
+                                     ptr(out), stream()), "creste_sample_affine")
+    return out
+
+
+def act(x, kind):
+    x = x.contiguous()
+    y = torch.empty_like(x)
+    check(lib().creste_act(ptr(x), C.c_longlong(x.numel()), ACT[kind], ptr(y), stream()), "creste_act")
+    return y
+
+
+def act_bwd(g, x, kind):
+    g, x = g.contiguous(), x.contiguous()
+    dx = torch.empty_like(x)
+    check(lib().creste_act_bwd(ptr(g), ptr(x), C.c_longlong(x.numel()), ACT[kind], ptr(dx), stream()),
+          "creste_act_bwd")
+    return dx
+
+
+def add_scaled(inp, x, s=None):
+    """out = inp + x * s[b]  (s None: plain sum) -- identity skip with drop-connect."""
+    inp, x = inp.contiguous(), x.contiguous()
+    B = x.shape[0]
+    out = torch.empty_like(x)
+    check(lib().creste_add_scaled(ptr(inp), ptr(x), ptr(None if s is None else s.contiguous()), B,
+                                  C.c_longlong(x.numel() // B), ptr(out), stream()), "creste_add_scaled")
+    return out
+
+
+def chan_slice(x, c0, cn):
+    x = x.contiguous()
+    npix, Cc = _npix_c(x)
+    out = torch.empty(*x.shape[:-1], cn, device=x.device)
+    check(lib().creste_chan_slice(ptr(x), C.c_longlong(npix), Cc, int(c0), int(cn), ptr(out), stream()),
+          "creste_chan_slice")
+    return out
+
+
+def wgrad_strided(x_nhwc, g_nhwc, R, S, stride, pad):
+    """dw [K,C,R,S] (torch layout) of a strided dense conv with C == 4 (the EfficientNet stem)."""
+    x_nhwc, g_nhwc = x_nhwc.contiguous(), g_nhwc.contiguous()
+    N, H, W, Cc = x_nhwc.shape
+    _, P, Q, K = g_nhwc.shape
+    n = lib().creste_wgrad_strided_workspace_bytes(N, P, Q, Cc, K, R, S)
+    ws = _ws(n, x_nhwc.device)
+    dw = torch.empty(R * S * Cc, K, device=x_nhwc.device)
+    check(lib().creste_wgrad_strided(ptr(x_nhwc), ptr(g_nhwc), N, H, W, Cc, K, R, S, stride, pad[0], pad[2],
+                                     P, Q, ptr(dw), ptr(ws), C.c_size_t(n), stream()), "creste_wgrad_strided")
+    return dw.view(R, S, Cc, K).permute(3, 2, 0, 1).contiguous()
+
+
+def ce_depth_bwd(logits_nchw, label_mm, depth_min, depth_max, scale_dev):
+    logits = logits_nchw.contiguous()
+    N, D = logits.shape[0], logits.shape[1]
+    HW = logits.numel() // (N * D)
+    out = torch.empty_like(logits)
+    check(lib().creste_ce_depth_bwd(ptr(logits), ptr(label_mm.contiguous().float()), N, D, C.c_longlong(HW),
+                                    C.c_float(depth_min), C.c_float(depth_max),
+                                    ptr(scale_dev.reshape(1).float().contiguous()), ptr(out), stream()),
+          "creste_ce_depth_bwd")
+    return out
+
+
+def masked_mse_bwd(pred, gt, scale_dev):
+    pred, gt = pred.contiguous(), gt.contiguous().float()
+    out = torch.empty_like(pred)
+    check(lib().creste_masked_mse_bwd(ptr(pred), ptr(gt), C.c_longlong(pred.numel()),
+                                      ptr(scale_dev.reshape(1).float().contiguous()), ptr(out), stream()),
+          "creste_masked_mse_bwd")
+    return out

@@ -262,7 +262,7 @@ int creste_grad_penalty_bwd(const float* G, const float* g_scalar, int B, int C,
 int creste_adam_step(float* p, const float* g, float* m, float* v, long long n, float lr, float b1,
                      float b2, float eps, int step, float grad_scale, void* stream);
 
-/* Stage-1 loss VALUES for validation (forward only; backbone training is not implemented):
+/* Stage-1 loss VALUES (forward; the gradients are creste_ce_depth_bwd / creste_masked_mse_bwd below):
  * CrossEntropyDepth + SmoothL1Depth (creste/utils/loss_utils.py:477-573 with bin_depths mode "UD",
  * creste/utils/depth_utils.py:346-383) in one pass over the NCHW depth logits.
  *   logits [N,D,HW]; pred_bins int64 [N,HW] (depth_preds_bins: what the shipped config feeds the
@@ -274,6 +274,67 @@ int creste_stage1_depth_losses(const float* logits_nchw, const long long* pred_b
 /* MSELoss on the DINO feature targets (loss_utils.py:606-647, overlap_only = False):
  * acc2 DEVICE double[2] = {sum (pred-gt)^2 over elements with !isinf(gt), their count}. */
 int creste_masked_mse(const float* pred, const float* gt, long long n, double* acc2, void* stream);
+
+/* ---------------------------------------------------------------------------------------------
+ * Stage-1 (distillation) backbone TRAINING step: the train-mode graph of DistillationBackbone
+ * (creste/models/distillation.py:145-207; EfficientNet-B0 trunk + U-Net decoder,
+ * creste/models/blocks/effnet.py:8-98; heads creste/models/blocks/conv.py:5-32) and its backward,
+ * as driven by creste/train_pefree.py:76-106.  Dense convs reuse creste_conv2d /
+ * creste_conv2d_wgrad; everything else is below (csrc/backbone_train.cu).  NHWC fp32, C % 4 == 0.
+ * act codes: 0 none, 1 relu, 2 swish (x*sigmoid(x)), 3 sigmoid. */
+/* workspace of the two-stage channel reductions: nacc terms, Z samples (Z = 1: whole batch) */
+size_t creste_chan_reduce_workspace_bytes(long long npix, int C, int nacc, int Z);
+/* BatchNorm batch statistics (F.batch_norm training=True): out2 DEVICE double[2*C] = {sum x},
+ * {sum x^2}; any C % 4 == 0 (the EfficientNet mid tensors reach 1152 channels). */
+int creste_chan_moments(const float* x, long long npix, int C, double* out2, void* ws, size_t ws_bytes,
+                        void* stream);
+/* y = act(x*a[c] + b[c])  (BatchNorm affine + ReLU / swish in one pass) */
+int creste_chan_affine_act(const float* x, const float* a, const float* b, long long npix, int C, int act,
+                           float* y, void* stream);
+/* first half of the BatchNorm(+act) backward: gu = g * act'(x*a[c]+b[c]) (written when act != 0) and
+ * sums2 DEVICE double[2*C] = {sum gu}, {sum gu*x}; ws >= creste_chan_reduce_workspace_bytes(npix,C,2,1) */
+int creste_bn_act_bwd(const float* g, const float* x, const float* a, const float* b, long long npix, int C,
+                      int act, float* gu, double* sums2, void* ws, size_t ws_bytes, void* stream);
+/* second half: out = u*p[c] + x*q[c] + r[c] */
+int creste_chan_axpby(const float* u, const float* x, const float* p, const float* q, const float* r,
+                      long long npix, int C, float* out, void* stream);
+/* depthwise R x R conv (R in {3,5}, stride in {1,2}) with the static TF-'SAME' padding of
+ * efficientnet_pytorch (low pads given, high implied by P, Q): w [R*R][C]; x [N,H,W,C]; y [N,P,Q,C];
+ * _dgrad: dx from g [N,P,Q,C]; _wgrad: dw [R*R][C]. */
+int creste_dwconv_fwd(const float* x, const float* w, int N, int H, int W, int C, int R, int stride,
+                      int pad_t, int pad_l, int P, int Q, float* y, void* stream);
+int creste_dwconv_dgrad(const float* g, const float* w, int N, int H, int W, int C, int R, int stride,
+                        int pad_t, int pad_l, int P, int Q, float* dx, void* stream);
+size_t creste_dwconv_wgrad_workspace_bytes(int N, int C, int R, int P, int Q);
+int creste_dwconv_wgrad(const float* x, const float* g, int N, int H, int W, int C, int R, int stride,
+                        int pad_t, int pad_l, int P, int Q, float* dw, void* ws, size_t ws_bytes,
+                        void* stream);
+/* squeeze-excite: out[b,c] = scale * sum_pix x[b,pix,c] * (y ? y[b,pix,c] : 1)   (adaptive_avg_pool2d
+ * with scale = 1/HW, and the gate gradient); ws >= creste_chan_reduce_workspace_bytes(HW,C,1,B) */
+int creste_sample_dot(const float* x, const float* y, int B, long long HW, int C, float scale, float* out,
+                      void* ws, size_t ws_bytes, void* stream);
+/* out[b,pix,c] = (x ? x*(a ? a[b,c] : 1) : 0) + (b ? b[b,c] : 0): the gate multiply and the pool adjoint */
+int creste_sample_affine(const float* x, const float* a, const float* b, int B, long long HW, int C,
+                         float* out, void* stream);
+int creste_act(const float* x, long long n, int act, float* y, void* stream);
+int creste_act_bwd(const float* g, const float* x, long long n, int act, float* dx, void* stream);
+/* identity skip + drop-connect (efficientnet_pytorch drop_connect): out = inp + x*s[b] (s NULL: 1) */
+int creste_add_scaled(const float* inp, const float* x, const float* s, int B, long long per, float* out,
+                      void* stream);
+/* out[pix,0:Cn] = x[pix,c0:c0+Cn]: adjoint of torch.cat([skip, up], 1) (effnet.py:24) */
+int creste_chan_slice(const float* x, long long npix, int C, int c0, int Cn, float* out, void* stream);
+/* weight gradient of the strided stem conv (C == 4): dw [R*S*C][K] */
+size_t creste_wgrad_strided_workspace_bytes(int N, int P, int Q, int C, int K, int R, int S);
+int creste_wgrad_strided(const float* x, const float* g, int N, int H, int W, int C, int K, int R, int S,
+                         int stride, int pad_t, int pad_l, int P, int Q, float* dw, void* ws,
+                         size_t ws_bytes, void* stream);
+/* gradients of CrossEntropyDepth (loss_utils.py:477-527) w.r.t. the NCHW logits and of MSELoss
+ * (:606-647); scale_dev is a DEVICE float (upstream gradient / #valid), so no host sync. */
+int creste_ce_depth_bwd(const float* logits_nchw, const float* label_mm, int N, int D, long long HW,
+                        float depth_min, float depth_max, const float* scale_dev, float* dlogits,
+                        void* stream);
+int creste_masked_mse_bwd(const float* pred, const float* gt, long long n, const float* scale_dev,
+                          float* dpred, void* stream);
 
 #ifdef __cplusplus
 }

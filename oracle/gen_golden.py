@@ -157,6 +157,7 @@ def main():
     # backward of the gradient penalty + Adam (train_traversability.py:62-103)
     irl_step_golden()
     stage1_loss_golden()
+    distill_step_golden()
 
     # ---- full forward, tiny image, both depth profiles (lfd.py:314-330)
     for prof in ("peaky", "soft"):
@@ -186,6 +187,27 @@ def main():
     print("golden fixtures written to", OUT)
     for f in sorted(os.listdir(OUT)):
         print(f"  {f}: {os.path.getsize(os.path.join(OUT, f)) / 1024:.1f} KB")
+
+
+def distill_step_golden():
+    """Stage-1 training step of the UNMODIFIED reference (DistillationBackbone in train mode + the three
+    losses of effnet_ds2_dinov2_128.yaml + Adam, train_pefree.py:76-106, 176-181) on the seeded 64x96
+    case of oracle/distill_oracle.make_case: loss values, the L2 norm of every parameter gradient, three
+    full gradient tensors (stem, depth-head BN, last dino conv), samples of the outputs."""
+    from . import distill_oracle as do
+    ref = do.reference_step(do.make_case())
+    names = sorted(ref["grads"])
+    full = ["dino_head.model.6.weight", "depthcomp.depth_head.model.1.weight",
+            "depthcomp.vision_backbone.model.trunk._conv_stem.weight"]
+    np.savez_compressed(
+        os.path.join(OUT, "distill_step.npz"),
+        loss=ref["loss"], ce=ref["CrossEntropyDepth/depth/cls_loss"], sl1=ref["SmoothL1Depth/depth/reg_loss"],
+        mse=ref["MSELoss/loss"], acc=ref["CrossEntropyDepth/depth/acc"],
+        grad_names=np.array(names),
+        grad_l2=np.array([np.sqrt((ref["grads"][n].astype(np.float64) ** 2).sum()) for n in names]),
+        logits_sample=ref["logits"][:, ::16], dino_sample=ref["dino"][:, :, ::16],
+        bn_running_mean=ref["params"]["depthcomp.vision_backbone.model.trunk._bn1.running_mean"],
+        **{"grad::" + n: ref["grads"][n] for n in full})
 
 
 if __name__ == "__main__":

@@ -226,3 +226,17 @@ def trapezoid_fov_mask(H, W, top=70, bottom=70, near=0, far=100):
     spread = np.where(dist <= near, t, np.where(dist >= far, b,
                       t + (b - t) * ((dist - near) / np.float32(far - near))))
     return (dist >= near) & (dist <= far) & (np.abs(ang) <= spread)
+
+
+def distill_batch(B, H, W, seed=0, Z=128):
+    """One synthetic stage-1 batch: `image` [B,1,4,H,W] (RGB in [0,1) +
+    ~4 % filled LiDAR depth in mm), `depth_label` [B,1,H/4,W/4] mm in [300, 25600) with 20 % invalid
+    zeros, `fimg_label` [B,1,Z,H/4,W/4] ~ N(0,1) DINO targets."""
+    g = torch.Generator().manual_seed(4000 + seed)
+    rgb = torch.rand(B, 1, 3, H, W, generator=g)
+    depth = torch.rand(B, 1, 1, H, W, generator=g) * 25300.0 + 300.0
+    depth = depth * (torch.rand(B, 1, 1, H, W, generator=g) < 0.04)
+    lab = torch.rand(B, 1, H // 4, W // 4, generator=g) * 25300.0 + 300.0
+    lab = lab * (torch.rand(B, 1, H // 4, W // 4, generator=g) >= 0.2)
+    fimg = torch.randn(B, 1, Z, H // 4, W // 4, generator=g)
+    return {"image": torch.cat([rgb, depth], dim=2), "depth_label": lab, "fimg_label": fimg}

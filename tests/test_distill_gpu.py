@@ -1,0 +1,142 @@
+"""GPU parity tests of the stage-1 (distillation) training path (-m gpu).
+
+Kernel level: every entry point of csrc/backbone_train.cu against its plain-PyTorch fp32 statement
+(tests/torch_backend.py, evaluated on the CPU).  Step level: one DistillationModel.training_step
+through the C ABI against the oracle port (oracle/distill_oracle.py, pinned bit-for-bit to the
+reference) and against the golden fixture minted from the unmodified reference."""
+import numpy as np
+import pytest
+import torch
+
+from oracle import distill_oracle as do
+import torch_backend as tb
+from test_distill_cpu import check_golden, compare, ours_step
+
+pytestmark = pytest.mark.gpu
+
+
+def _t(g, *shape, scale=1.0):
+    return torch.from_numpy((g.standard_normal(shape) * scale).astype(np.float32))
+
+
+def _close(a, b, rtol=1e-5, what=""):
+    a, b = a.detach().cpu().double(), b.detach().cpu().double()
+    err = (a - b).abs().max().item()
+    ref = b.abs().max().item()
+    assert err <= rtol * max(ref, 1e-6), (what, err, ref)
+
+
+@pytest.mark.parametrize("C", [32, 144, 1152])
+@pytest.mark.parametrize("act", ["none", "relu", "swish"])
+def test_bn_kernels(cuda, C, act):
+    from creste_public_b200 import ops
+    g = np.random.default_rng(C)
+    x, gy = _t(g, 3, 9, 7, C), _t(g, 3, 9, 7, C)
+    a, b = _t(g, C), _t(g, C)
+    p, q, r = _t(g, C), _t(g, C), _t(g, C)
+    _close(ops.chan_moments(x.to(cuda)), tb.chan_moments(x), 1e-12, "moments")
+    _close(ops.chan_affine_act(x.to(cuda), a.to(cuda), b.to(cuda), act), tb.chan_affine_act(x, a, b, act), 2e-6, "affine_act")
+    gu, sums = ops.bn_act_bwd(gy.to(cuda), x.to(cuda), a.to(cuda), b.to(cuda), act)
+    gu0, sums0 = tb.bn_act_bwd(gy, x, a, b, act)
+    _close(gu, gu0, 5e-6, "gu")
+    _close(sums, sums0, 1e-5, "sums")
+    _close(ops.chan_axpby(gy.to(cuda), x.to(cuda), p.to(cuda), q.to(cuda), r.to(cuda)), tb.chan_axpby(gy, x, p, q, r), 2e-6, "axpby")
+
+
+@pytest.mark.parametrize("R,stride,H,W", [(3, 1, 10, 14), (3, 2, 10, 14), (5, 1, 8, 12), (5, 2, 8, 12), (5, 2, 4, 6),
+                                          (3, 1, 2, 3), (5, 1, 2, 3)])
+def test_dwconv_family(cuda, R, stride, H, W):
+    from creste_public_b200 import ops
+    from creste_public_b200.creste.models.blocks.effnet import same_pad
+    g = np.random.default_rng(R * 10 + stride)
+    C = 40
+    lo, hi = same_pad(R, stride)
+    pad = (lo, hi, lo, hi)
+    x, w = _t(g, 2, H, W, C), _t(g, R * R, C)
+    y0 = tb.dwconv_fwd(x, w, R, stride, pad)
+    y = ops.dwconv_fwd(x.to(cuda), w.to(cuda), R, stride, pad)
+    assert tuple(y.shape) == tuple(y0.shape)
+    _close(y, y0, 2e-6, "fwd")
+    gy = _t(g, *y0.shape)
+    _close(ops.dwconv_dgrad(gy.to(cuda), w.to(cuda), tuple(x.shape), R, stride, pad),
+           tb.dwconv_dgrad(gy, w, tuple(x.shape), R, stride, pad), 2e-6, "dgrad")
+    _close(ops.dwconv_wgrad(x.to(cuda), gy.to(cuda), R, stride, pad), tb.dwconv_wgrad(x, gy, R, stride, pad), 1e-5, "wgrad")
+
+
+def test_se_and_small_kernels(cuda):
+    from creste_public_b200 import ops
+    g = np.random.default_rng(11)
+    B, H, W, C = 3, 6, 5, 672
+    x, y = _t(g, B, H, W, C), _t(g, B, H, W, C)
+    gate, bvec = _t(g, B, 1, 1, C), _t(g, B, 1, 1, C)
+    _close(ops.sample_dot(x.to(cuda), None, 1.0 / (H * W)), tb.sample_dot(x, None, 1.0 / (H * W)), 1e-6, "pool")
+    _close(ops.sample_dot(x.to(cuda), y.to(cuda)), tb.sample_dot(x, y), 1e-6, "dot")
+    _close(ops.sample_affine(x.to(cuda), gate.to(cuda)), tb.sample_affine(x, gate), 1e-6, "gate")
+    _close(ops.sample_affine(None, None, bvec.to(cuda), shape=x.shape), tb.sample_affine(None, None, bvec, shape=x.shape), 0, "bcast")
+    for kind in ("swish", "sigmoid"):
+        v, gv = _t(g, B, 1, 1, 10), _t(g, B, 1, 1, 10)
+        _close(ops.act(v.to(cuda), kind), tb.act(v, kind), 2e-6, kind)
+        _close(ops.act_bwd(gv.to(cuda), v.to(cuda), kind), tb.act_bwd(gv, v, kind), 5e-6, kind + "_bwd")
+    s = torch.tensor([0.0, 1.25, 1.25])
+    _close(ops.add_scaled(x.to(cuda), y.to(cuda), s.to(cuda)), tb.add_scaled(x, y, s), 1e-6, "add_scaled")
+    _close(ops.add_scaled(x.to(cuda), y.to(cuda), None), tb.add_scaled(x, y, None), 1e-6, "add")
+    _close(ops.chan_slice(x.to(cuda), 112, 320), tb.chan_slice(x, 112, 320), 0, "slice")
+
+
+def test_stem_wgrad(cuda):
+    from creste_public_b200 import ops
+    g = np.random.default_rng(12)
+    x, gy = _t(g, 2, 32, 48, 4), _t(g, 2, 16, 24, 32)
+    pad = (0, 1, 0, 1)
+    _close(ops.wgrad_strided(x.to(cuda), gy.to(cuda), 3, 3, 2, pad), tb.wgrad_strided(x, gy, 3, 3, 2, pad), 1e-5, "stem wgrad")
+
+
+def test_loss_gradients(cuda):
+    from creste_public_b200 import ops
+    g = np.random.default_rng(13)
+    N, D, H, W = 2, 128, 6, 10
+    logits = _t(g, N, D, H, W, scale=3.0)
+    lab = torch.from_numpy(g.uniform(300, 25600, (N, H * W)).astype(np.float32))
+    lab[0, :7] = 0.0
+    lab[1, 3] = 25600.0
+    lab[1, 4] = 300.0
+    lab[1, 5] = float("nan")
+    scale = torch.tensor(0.37)
+    _close(ops.ce_depth_bwd(logits.to(cuda), lab.to(cuda), 300.0, 25600.0, scale.to(cuda)),
+           tb.ce_depth_bwd(logits, lab, 300.0, 25600.0, scale), 5e-6, "ce bwd")
+    pred, gt = _t(g, 2, 1, 16, 6, 10), _t(g, 2, 1, 16, 6, 10)
+    gt[0, 0, 3] = float("inf")
+    gt[1, 0, 5, 2, 2] = float("-inf")
+    _close(ops.masked_mse_bwd(pred.to(cuda), gt.to(cuda), scale.to(cuda)), tb.masked_mse_bwd(pred, gt, scale), 1e-6, "mse bwd")
+
+
+@pytest.mark.parametrize("precision", ["fp32", "3xfp16"])
+def test_training_step_matches_port_and_golden(cuda, golden, precision):
+    """One full stage-1 step (forward in train mode, three losses, backward, Adam) on the GPU against the
+    oracle port (== the reference bit for bit) on the same seeded case, drop-connect masks included."""
+    from creste_public_b200 import engine
+    case = do.make_case()
+    port = do.port_step(case)
+    old = engine.get_precision()
+    engine.set_precision(precision)
+    try:
+        ours = ours_step(case, device=cuda)
+    finally:
+        engine.set_precision(old)
+    compare(ours, port)
+    check_golden(ours, golden("distill_step.npz"), rtol=2e-4)
+
+
+def test_training_loss_decreases(cuda):
+    """Five steps on one batch: the loss goes down and every parameter stays finite."""
+    from creste_public_b200 import configs
+    from creste_public_b200.creste.train_pefree import DistillationModel
+    case = do.make_case(seed=6, B=2, image_size=(64, 96))
+    m = DistillationModel(configs.distill_cfg(case["image_size"]))
+    m.model.load_state_dict(case["state_dict"])
+    m = m.to(cuda).train()
+    inputs = {k: case[k].to(cuda) for k in ("image", "depth_label", "fimg_label")}
+    torch.manual_seed(0)
+    losses = [float(m.training_step({k: v.clone() for k, v in inputs.items()})["loss"]) for _ in range(5)]
+    assert losses[-1] < losses[0], losses
+    assert all(torch.isfinite(p).all() for p in m.model.parameters())

@@ -153,6 +153,190 @@ def adam_step(p, g, m, v, lr, b1, b2, eps, step, grad_scale=1.0):
     p.addcdiv_(m, (v.sqrt() / np.sqrt(bc2)).add_(eps), value=-lr / bc1)
 
 
+# ------------------------------------------------------------ stage-1 backbone training stand-ins
+def _act(u, kind):
+    if kind == "relu":
+        return torch.relu(u)
+    if kind == "swish":
+        return u * torch.sigmoid(u)
+    if kind == "sigmoid":
+        return torch.sigmoid(u)
+    return u
+
+
+def _act_grad(u, kind):
+    if kind == "relu":
+        return (u > 0).to(u.dtype)
+    s = torch.sigmoid(u)
+    if kind == "swish":
+        return s * (1 + u * (1 - s))
+    if kind == "sigmoid":
+        return s * (1 - s)
+    return torch.ones_like(u)
+
+
+def chan_moments(x):
+    return chan_stats(x)
+
+
+def chan_affine_act(x, a, b, act):
+    return _act(x * a + b, act)
+
+
+def bn_act_bwd(g, x, a, b, act):
+    gu = g if act in ("none", None) else g * _act_grad(x * a + b, act)
+    Cc = x.shape[-1]
+    gd, xd = gu.reshape(-1, Cc).double(), x.reshape(-1, Cc).double()
+    return gu, torch.stack([gd.sum(0), (gd * xd).sum(0)])
+
+
+def chan_axpby(u, x, p, q, r):
+    return u * p + x * q + r
+
+
+def _dw_w(w_rsc, R):
+    return w_rsc.view(R, R, 1, -1).permute(3, 2, 0, 1).contiguous()
+
+
+def dwconv_fwd(x, w_rsc, R, stride, pad):
+    pt, pb, pl, pr = pad
+    xn = F.pad(_nchw(x), (pl, pr, pt, pb))
+    return _nhwc(F.conv2d(xn, _dw_w(w_rsc, R), stride=stride, groups=x.shape[-1]))
+
+
+def dwconv_dgrad(g, w_rsc, x_shape, R, stride, pad):
+    N, H, W, Cc = x_shape
+    x = torch.zeros(N, H, W, Cc, dtype=g.dtype, requires_grad=True)
+    with torch.enable_grad():
+        y = dwconv_fwd(x, w_rsc, R, stride, pad)
+        (dx,) = torch.autograd.grad(y, x, g)
+    return dx
+
+
+def dwconv_wgrad(x, g, R, stride, pad):
+    w = torch.zeros(R * R, x.shape[-1], dtype=x.dtype, requires_grad=True)
+    with torch.enable_grad():
+        y = dwconv_fwd(x, w, R, stride, pad)
+        (dw,) = torch.autograd.grad(y, w, g)
+    return dw
+
+
+def sample_dot(x, y=None, scale=1.0):
+    B, Cc = x.shape[0], x.shape[-1]
+    v = x if y is None else x * y
+    return (v.reshape(B, -1, Cc).double().sum(1) * scale).float().view(B, 1, 1, Cc)
+
+
+def sample_affine(x, a=None, b=None, shape=None):
+    shape = tuple(x.shape) if x is not None else tuple(shape)
+    B, Cc = shape[0], shape[-1]
+    out = torch.zeros(shape) if x is None else x.clone()
+    bc = (B,) + (1,) * (len(shape) - 2) + (Cc,)
+    if a is not None and x is not None:
+        out = out * a.reshape(bc)
+    if b is not None:
+        out = out + b.reshape(bc)
+    return out
+
+
+def act(x, kind):
+    return _act(x, kind)
+
+
+def act_bwd(g, x, kind):
+    return g * _act_grad(x, kind)
+
+
+def add_scaled(inp, x, s=None):
+    if s is None:
+        return inp + x
+    return inp + x * s.view(-1, *([1] * (x.ndim - 1)))
+
+
+def chan_slice(x, c0, cn):
+    return x[..., c0:c0 + cn].contiguous()
+
+
+def wgrad_strided(x, g, R, S, stride, pad):
+    pt, pb, pl, pr = pad
+    K, Cc = g.shape[-1], x.shape[-1]
+    w = torch.zeros(K, Cc, R, S, dtype=x.dtype, requires_grad=True)
+    with torch.enable_grad():
+        y = F.conv2d(F.pad(_nchw(x), (pl, pr, pt, pb)), w, stride=stride)
+        (dw,) = torch.autograd.grad(y, w, _nchw(g))
+    return dw
+
+
+def conv2d(x, w_packed, K, R, S, stride=1, pad=(0, 0, 0, 0), scale=None, shift=None, gate=None,
+           residual=None, act="none", out_nchw=False, precision="fp32"):
+    """Only the raw strided stem call of StemConvFn reaches this stand-in (w_packed = torch weights)."""
+    pt, pb, pl, pr = pad
+    return _nhwc(F.conv2d(F.pad(_nchw(x), (pl, pr, pt, pb)), w_packed, stride=stride))
+
+
+def pack_conv_weight(w):
+    return w
+
+
+def upsample_concat(skip, x, out_hw, scale_factor=None, x_first=False):
+    up = upsample2(x)
+    return up if skip is None else torch.cat([skip, up], dim=-1)
+
+
+def _bins(label_mm, D, dmin, dmax):
+    bin_size = (dmax - dmin) / D
+    idx = (label_mm - dmin) / bin_size
+    bad = (idx < 0) | (idx > D) | ~torch.isfinite(idx)
+    idx = torch.where(bad, torch.full_like(idx, float(D)), idx)
+    return idx.long()
+
+
+def stage1_depth_losses(logits_nchw, pred_bins, label_mm, depth_min, depth_max, beta):
+    N, D = logits_nchw.shape[0], logits_nchw.shape[1]
+    flat = logits_nchw.reshape(N, D, -1).permute(0, 2, 1)
+    gt = _bins(label_mm.reshape(N, -1).float(), D, depth_min, depth_max)
+    valid = gt != D
+    ce = F.cross_entropy(flat[valid], gt[valid], reduction="sum")
+    correct = (flat[valid].argmax(1) == gt[valid]).sum()
+    sl = F.smooth_l1_loss(pred_bins.reshape(N, -1)[valid].float(), label_mm.reshape(N, -1)[valid] / 1000.0,
+                          beta=beta, reduction="sum")
+    return torch.stack([ce.double(), valid.sum().double(), correct.double(), sl.double()])
+
+
+def ce_depth_bwd(logits_nchw, label_mm, depth_min, depth_max, scale_dev):
+    N, D = logits_nchw.shape[0], logits_nchw.shape[1]
+    gt = _bins(label_mm.reshape(N, -1).float(), D, depth_min, depth_max)
+    valid = (gt != D)
+    p = torch.softmax(logits_nchw.reshape(N, D, -1), dim=1)
+    onehot = F.one_hot(gt.clamp(max=D - 1), D).permute(0, 2, 1).to(p.dtype)
+    d = (p - onehot) * valid.unsqueeze(1).to(p.dtype) * scale_dev.reshape(())
+    return d.view_as(logits_nchw)
+
+
+def masked_mse(pred, gt):
+    valid = ~torch.isinf(gt)
+    d = (pred - gt)[valid].double()
+    return torch.stack([(d * d).sum(), valid.sum().double()])
+
+
+def masked_mse_bwd(pred, gt, scale_dev):
+    valid = ~torch.isinf(gt)
+    return torch.where(valid, (pred - gt) * scale_dev.reshape(()), torch.zeros_like(pred))
+
+
+def depth_expectation(logits_nhwc, dmin=300.0, dmax=25600.0):
+    D = logits_nhwc.shape[-1]
+    p = torch.softmax(logits_nhwc, dim=-1)
+    vals = torch.linspace(dmin, dmax, D)
+    return (p * vals).sum(-1) / 1000.0, logits_nhwc.argmax(-1)
+
+
+STAGE1_NAMES = ["chan_moments", "chan_affine_act", "bn_act_bwd", "chan_axpby", "dwconv_fwd", "dwconv_dgrad",
+                "dwconv_wgrad", "sample_dot", "sample_affine", "act", "act_bwd", "add_scaled", "chan_slice",
+                "wgrad_strided", "conv2d", "pack_conv_weight", "upsample_concat", "stage1_depth_losses",
+                "ce_depth_bwd", "masked_mse", "masked_mse_bwd", "depth_expectation"]
+
+
 @contextlib.contextmanager
 def patched():
     """Swap the kernel wrappers for the torch stand-ins (CPU graph-structure tests only)."""
@@ -161,7 +345,7 @@ def patched():
     names = ["chan_affine", "relu_bwd", "chan_dot", "chan_stats", "maxpool2", "maxpool2_bwd", "maxpool2_gather",
              "upsample2", "upsample2_adjoint", "nchw_to_nhwc", "nhwc_to_nchw", "row_dot",
              "row_scale", "row_normalize", "grad_penalty", "grad_penalty_bwd", "expert_visitation",
-             "adam_step"]
+             "adam_step"] + STAGE1_NAMES
     saved = {n: getattr(ops, n) for n in names}
     saved_ag = (ag._conv_raw, ag._wgrad_raw)
     try:

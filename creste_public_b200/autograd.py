@@ -56,10 +56,29 @@ def _conv_raw(x, w, ph, pw):
     return y if Kp == K else y[..., :K].contiguous()
 
 
+WGRAD_TILE = 64      # the CUDA-core wgrad kernels hold one [C x K] tile of at most 64 x 64 per CTA
+
+
 def _wgrad_raw(x, g, R, S, ph, pw):
+    """dw [K,C,R,S] of a stride-1 conv.  Layers wider than 64 channels (the backbone's) are cut into
+    64-channel slices of x and g (one extra pass over each tensor) and every (c, k) tile pair goes
+    through the same kernel."""
     Cc, K = x.shape[-1], g.shape[-1]
-    dw = ops.conv2d_wgrad(_pad_last(x, 8), _pad_last(g, 8), R, S, (ph, ph, pw, pw))
-    return dw[:K, :Cc].contiguous()
+    pad = (ph, ph, pw, pw)
+    if Cc <= WGRAD_TILE and K <= WGRAD_TILE:
+        dw = ops.conv2d_wgrad(_pad_last(x, 8), _pad_last(g, 8), R, S, pad)
+        return dw[:K, :Cc].contiguous()
+    T = WGRAD_TILE
+    xp, gp = _pad_last(x), _pad_last(g)
+    xs = [(c0, min(T, Cc - c0), _pad_last(ops.chan_slice(xp, c0, min(T, xp.shape[-1] - c0)), 8))
+          for c0 in range(0, Cc, T)] if Cc > T else [(0, Cc, _pad_last(x, 8))]
+    gs = [(k0, min(T, K - k0), _pad_last(ops.chan_slice(gp, k0, min(T, gp.shape[-1] - k0)), 8))
+          for k0 in range(0, K, T)] if K > T else [(0, K, _pad_last(g, 8))]
+    dw = torch.empty(K, Cc, R, S, device=x.device)
+    for c0, cn, xt in xs:
+        for k0, kn, gt in gs:
+            dw[k0:k0 + kn, c0:c0 + cn] = ops.conv2d_wgrad(xt, gt, R, S, pad)[:kn, :cn]
+    return dw
 
 
 def _flip_t(w):

@@ -189,6 +189,33 @@ def port_step(case, lr=5e-4):
     return _finish(model, out)
 
 
+def port_grads_fp64(case):
+    """The same step evaluated in float64 (same drop-connect masks): the yardstick that separates an
+    implementation's error from the fp32 rounding noise of the reference itself.  -> (grads, loss)"""
+    model = PortDistillation(case["image_size"])
+    model.load_state_dict(case["state_dict"])
+    model.double().train()
+    orig = effs.drop_connect
+
+    def drop_connect32(inputs, p, training):          # the fp32 run's uniforms, whatever the dtype
+        if not training:
+            return inputs
+        keep = 1 - p
+        r = keep + torch.rand([inputs.shape[0], 1, 1, 1], dtype=torch.float32).to(inputs.dtype)
+        return inputs / keep * torch.floor(r)
+    effs.drop_connect = drop_connect32
+    try:
+        torch.manual_seed(case["seed"])
+        outputs = model(case["image"].double())
+        total, _ = port_losses(outputs, {"depth_label": case["depth_label"].double(),
+                                         "fimg_label": case["fimg_label"].double()})
+        total.backward()
+    finally:
+        effs.drop_connect = orig
+    return ({k: p.grad.numpy().copy() for k, p in model.named_parameters() if p.grad is not None},
+            float(total.detach()))
+
+
 def reference_step(case, lr=5e-4):
     """The unmodified reference modules (build container only)."""
     from . import ref_harness as rh

@@ -49,23 +49,45 @@ def ours_step(case, device=None):
     return out
 
 
-def compare(ours, ref, tol_out=2e-4, tol_grad=2e-3, tol_par=2e-3):
-    """Parity bars of the stage-1 step (fp32; reductions are ordered differently from oneDNN's):
-    losses <= 2e-4 relative, outputs <= tol_out of their max, every gradient tensor <= tol_grad of
-    its own max (+ a 1e-6 floor: bias gradients in front of a train-mode BatchNorm are exact zeros up to
-    rounding), post-Adam parameters / running statistics <= tol_par absolute-relative."""
+def compare(ours, ref, truth, tol_out=2e-4, tol_grad=5e-4, strict=True):
+    """Parity bars of the stage-1 step.  `ref` is the fp32 oracle port (== the reference bit for bit),
+    `truth` the same step in float64.  Losses <= 2e-4 relative, outputs <= tol_out of their max.
+
+    Gradients.  The reference's own fp32 rounding noise is large on some tensors (measured against
+    float64: up to 2.4e-2 of the tensor's max on the dino-head BatchNorm vectors), because the noise is
+    DISCRETE: a pre-activation within ~1e-6 of zero lands on the other side of a ReLU, and in this
+    768-pixel case one flipped element moves a row of the downstream weight gradient by up to 3 % and
+    everything upstream by ~1e-3 (profiles/r1c_distill_parity.md).  Two criteria:
+      strict   |ours - truth|_max <= 3 * |ref - truth|_max + tol_grad * |truth|_max + 1e-6  per tensor:
+               as close to the exact gradient as the reference is, up to a factor 3.  Asserted for every
+               tensor when `strict` (an implementation that flips the same elements as the reference
+               does), else for at least half of the tensors.
+      robust   per-tensor relative L2 error against float64 <= max(3 x the reference's, 3e-2): no single
+               ReLU flip reaches it, any wrong backward formula exceeds it by an order of magnitude."""
     for k in ("loss", "CrossEntropyDepth/depth/cls_loss", "SmoothL1Depth/depth/reg_loss", "MSELoss/loss"):
         np.testing.assert_allclose(ours[k], ref[k], rtol=2e-4, err_msg=k)
     np.testing.assert_allclose(ours["CrossEntropyDepth/depth/acc"], ref["CrossEntropyDepth/depth/acc"], atol=2e-3)
     for k in ("logits", "dino"):
         assert np.abs(ours[k] - ref[k]).max() <= tol_out * np.abs(ref[k]).max(), k
-    live = 0
+    assert len(ref["grads"]) >= 240
+    bad, bad_l2 = [], []
     for k, g0 in ref["grads"].items():
-        g1 = ours["grads"][k]
-        err = np.abs(g0 - g1).max()
-        assert err <= tol_grad * np.abs(g0).max() + 1e-6, (k, err, np.abs(g0).max())
-        live += 1
-    assert live >= 240
+        t = truth[k]
+        d = ours["grads"][k] - t
+        err, yard, tmax = np.abs(d).max(), np.abs(g0 - t).max(), np.abs(t).max()
+        lim = 3 * yard + tol_grad * tmax + 1e-6
+        if not err <= lim:
+            bad.append((float(err / lim), k, float(err), float(yard), float(tmax)))
+        tn = np.sqrt((t ** 2).sum())
+        if tn > 1e-5:                                # exact-zero gradients (biases in front of a BatchNorm) aside
+            rel, rel_ref = np.sqrt((d ** 2).sum()) / tn, np.sqrt(((g0 - t) ** 2).sum()) / tn
+            if not rel <= max(3 * rel_ref, 3e-2):
+                bad_l2.append((float(rel), k, float(rel_ref)))
+    assert not bad_l2, sorted(bad_l2, reverse=True)[:10]
+    if strict:
+        assert not bad, sorted(bad, reverse=True)[:10]
+    else:
+        assert len(bad) <= len(ref["grads"]) // 2, (len(bad), sorted(bad, reverse=True)[:10])
     for k, g1 in ours["grads"].items():          # parameters the reference leaves without a gradient
         if k not in ref["grads"]:
             assert np.abs(g1).max() == 0.0, k
@@ -76,7 +98,7 @@ def compare(ours, ref, tol_out=2e-4, tol_grad=2e-3, tol_par=2e-3):
             continue
         # Adam normalises the step to +-lr whatever the gradient's size: a parameter whose gradient is
         # rounding noise (exact zero in exact arithmetic) may move by up to lr either way
-        np.testing.assert_allclose(p1, p0, rtol=tol_par, atol=1.1e-3, err_msg=k)
+        np.testing.assert_allclose(p1, p0, rtol=2e-3, atol=1.1e-3, err_msg=k)
 
 
 @pytest.mark.skipif(not HAVE_REF, reason="reference tree not present")
@@ -118,7 +140,7 @@ def test_graph_matches_port():
     port = do.port_step(case)
     with tb.patched():
         ours = ours_step(case)
-    compare(ours, port)
+    compare(ours, port, do.port_grads_fp64(case)[0])
 
 
 def test_graph_matches_golden(golden):

@@ -123,7 +123,9 @@ def test_training_step_matches_port_and_golden(cuda, golden, precision):
         ours = ours_step(case, device=cuda)
     finally:
         engine.set_precision(old)
-    compare(ours, port)
+    # 3xfp16 (the default mode) reproduces the reference's ReLU masks on this case; the exact-fp32 FFMA path
+    # flips one element of up3's last ReLU (tools/distill_diag.py), so it is held to the robust criterion
+    compare(ours, port, do.port_grads_fp64(case)[0], strict=(precision == "3xfp16"))
     check_golden(ours, golden("distill_step.npz"), rtol=2e-4)
 
 

@@ -150,6 +150,26 @@ def cpu_irl_baseline(Hm=256, Wm=256, steps=1):
     return 1.0 / dt, dt * 1e3, torch.get_num_threads()
 
 
+def cpu_stage1_baseline(H=512, W=960):
+    """The reference's stage-1 training step on the host cores (oracle port: torch CPU modules in train
+    mode + autograd + Adam), bounded sample: ONE 512x960 frame per step, one step."""
+    import torch
+    from oracle import distill_oracle as do
+    import synth_data as synth
+    torch.set_num_threads(os.cpu_count() or 1)
+    model = do.PortDistillation((H, W)).train()
+    opt = torch.optim.Adam(model.parameters(), lr=5e-4)
+    batch = synth.distill_batch(1, H, W, seed=0)
+    t0 = time.perf_counter()
+    out = model(batch["image"])
+    total, _ = do.port_losses(out, batch)
+    opt.zero_grad()
+    total.backward()
+    opt.step()
+    dt = time.perf_counter() - t0
+    return 1.0 / dt, dt * 1e3, torch.get_num_threads()
+
+
 def run_reference(args):
     rank, local, world = dist_env()
     if rank != 0:
@@ -217,6 +237,50 @@ def run_irl_steps(args, dev, rank, world, barrier, Bi=8, Hm=256, Wm=256, steps=5
             "vi_sweeps": int(model.traversability_head.last_vi_info[0]),
             "loss": float(loss), "gpu_launches_per_step": launches,
             "precision": args.precision}
+
+
+def run_stage1_steps(args, dev, rank, world, barrier, Bi=4, H=512, W=960, steps=3):
+    """configs[2] shard: stage-1 (distillation) backbone training step, Bi frames per GPU -- train-mode
+    forward (BatchNorm batch statistics, drop-connect), CrossEntropyDepth + SmoothL1Depth + MSELoss,
+    backward through the whole encoder, ONE flat gradient all-reduce (N > 1), fused Adam."""
+    import torch
+    import torch.distributed as dist
+    from creste_public_b200 import _lib, configs
+    from creste_public_b200.creste.train_pefree import DistillationModel
+    import synth_data as synth
+    if args.no_stage1:
+        return None
+    torch.manual_seed(1234 + rank)
+    m = DistillationModel(configs.distill_cfg((H, W))).to(dev).train()
+    batch = {k: v.to(dev) for k, v in synth.distill_batch(Bi, H, W, seed=rank).items()}
+    for _ in range(2):
+        out = m.training_step(batch)
+    barrier()
+    n0 = _lib.lib().creste_launch_count()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(steps):
+        out = m.training_step(batch)
+    e1.record()
+    barrier()
+    ms = e0.elapsed_time(e1) / steps
+    launches = (_lib.lib().creste_launch_count() - n0) / steps
+    if world > 1:
+        t = torch.tensor([ms], device=dev)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        ms = float(t)
+    flop = 3.0 * GFLOP_PER_FRAME * 1e9 * Bi
+    res = {"metric": "stage-1 training frames/sec @ 512x960", "value": Bi * world * 1e3 / ms, "unit": "frames/s",
+           "ms_per_step": ms, "frames_per_step_per_gpu": Bi,
+           "workload": f"configs[2] shard: distillation.yaml RGB-D backbone training step, B={Bi}/GPU "
+                       f"(global {Bi * world}), {H}x{W}: train-mode EfficientNet-B0 + U-Net + depth/dino heads -> "
+                       "3 losses -> backward -> flat gradient all-reduce -> Adam",
+           "loss": float(out["loss"]), "gpu_launches_per_step": launches, "precision": args.precision,
+           "achieved_tflops": flop / (ms * 1e-3) / 1e12,
+           "peak_mem_gib": torch.cuda.max_memory_allocated() / 2 ** 30}
+    del m, batch
+    torch.cuda.empty_cache()
+    return res
 
 
 def run_ours(args):
@@ -418,6 +482,17 @@ def run_ours(args):
     if rank == 0 and irl is not None:
         irl["vi_roofline"] = vi_roof
         irl["cpu_baseline"] = irl_cpu
+    # ---- third leg: stage-1 backbone training frames/s (configs[2] shard, B = 4 per GPU)
+    stage1 = run_stage1_steps(args, dev, rank, world, barrier)
+    if rank == 0 and stage1 is not None and not args.no_cpu and world == 1:
+        try:
+            fps1, ms1, cores1 = cpu_stage1_baseline()
+            stage1["cpu_baseline"] = {"value": fps1, "unit": "frames/s", "cores": cores1, "kind": "port",
+                                      "sample": "1 step x 1 frame of the same 512x960 stage-1 step (torch CPU oracle "
+                                                "port of the reference, train mode, autograd, Adam), all host threads",
+                                      "ms_per_frame": ms1}
+        except Exception as e:                                  # noqa: BLE001
+            stage1["cpu_baseline"] = {"error": repr(e)[:200]}
     if rank == 0:
         line = {
             "metric": METRIC, "value": value, "unit": "frames/s", "n_gpus": world,
@@ -435,7 +510,7 @@ def run_ours(args):
             "e2e": {"value": e2e_value, "unit": "frames/s", "h2d_bytes_per_step": h2d,
                     "d2h_bytes_per_step": d2h, "ms_per_step": ms_e2e / args.steps},
             "gpu_launches": int(launches),
-            "clocks": clocks, "roofline": roof, "cpu_baseline": cpu, "irl": irl,
+            "clocks": clocks, "roofline": roof, "cpu_baseline": cpu, "irl": irl, "stage1": stage1,
             "latency_b1": latency,
             "achieved_tflops_whole_step": GFLOP_PER_FRAME * 1e9 * value / world / 1e12,
         }
@@ -454,6 +529,7 @@ def main():
     ap.add_argument("--precision", default="3xfp16", choices=["fp32", "3xtf32", "3xfp16", "tf32"])
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
     ap.add_argument("--no-irl", action="store_true", help="skip the IRL steps/s leg")
+    ap.add_argument("--no-stage1", action="store_true", help="skip the stage-1 training frames/s leg")
     args = ap.parse_args()
     if args.warmup < 3 and args.impl == "ours":
         args.warmup = 3

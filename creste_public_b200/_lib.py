@@ -37,6 +37,7 @@ EXPORTS = [
     "creste_sample_affine", "creste_act", "creste_act_bwd", "creste_add_scaled", "creste_chan_slice",
     "creste_wgrad_strided_workspace_bytes", "creste_wgrad_strided", "creste_ce_depth_bwd",
     "creste_masked_mse_bwd",
+    "creste_conv2d_wgrad_tc_supported", "creste_conv2d_wgrad_tc_workspace_bytes", "creste_conv2d_wgrad_tc",
 ]
 
 
@@ -74,7 +75,8 @@ def lib():
                      "creste_splat_workspace_bytes", "creste_conv2d_workspace_bytes",
                      "creste_chan_dot_workspace_bytes", "creste_conv2d_wgrad_workspace_bytes",
                      "creste_grad_penalty_workspace_bytes", "creste_chan_reduce_workspace_bytes",
-                     "creste_dwconv_wgrad_workspace_bytes", "creste_wgrad_strided_workspace_bytes"):
+                     "creste_dwconv_wgrad_workspace_bytes", "creste_wgrad_strided_workspace_bytes",
+                     "creste_conv2d_wgrad_tc_workspace_bytes"):
             getattr(L, name).restype = C.c_size_t
         _lib = L
     return _lib

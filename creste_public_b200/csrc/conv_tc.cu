@@ -874,6 +874,284 @@ int conv_tc_launch(const creste_conv_desc* d, const float* x, const float* w_pac
   return launch_check("conv_tc_kernel");
 }
 
+
+// =====================================================================================================
+// Weight gradient of the stride-1 dense convolutions on the tensor cores (stage-1 / stage-3 training).
+//
+//   dw[tap][c][k] = sum over output pixels of  g[pix][k] * x[pix shifted by the tap][c]
+//
+// GEMM view per filter tap: D[M = 128 output channels][N = BN input channels] accumulated over the
+// PIXELS.  Both operands are therefore "MN-major": the reduction index (pixel) is the slow axis of the
+// NHWC tensors.  A TMA box {64 channels, wbox, hbox, 1} lands as 64 pixel rows x 128 bytes with the
+// 128-byte swizzle -- the canonical MN-major SWIZZLE_128B UMMA layout ((T,8,m),(8,k)) with
+// SBO = 1024 B between 8-pixel groups and LBO = one box (8192 B) between 64-channel groups; the
+// instruction descriptor carries the a_major / b_major transpose bits.  The shifted x box (tap offset,
+// zero padding, ragged edges, channel tails) is TMA out-of-bounds zero fill, exactly as in the forward.
+// Precision: 3xFP16 split of both operands (same pre-pass as the forward), main and cross terms in
+// separate TMEM accumulators.  One CTA = (128-k tile, BN-c tile, tap, pixel split); partial tiles
+// part[split][tap][C][K] are summed in a fixed order by wg_reduce_kernel.
+// Warps: 0 = TMA producer, 1 = MMA issuer, 2..5 = epilogue (one TMEM lane quarter each).
+struct WgParams {
+  float* part;                 // [splits][R*S][C][K]
+  const float* sx; const float* sg;     // operand scale records {s, 1/s}
+  int N, P, Q, C, K, R, S, pad_t, pad_l;
+  int wbox, hbox, tiles_x, tiles_y, ntiles;
+  int bn, nb;                  // input-channel tile (multiple of 64) and its 64-channel box count
+  int m_tiles, n_tiles, splits;
+  uint32_t lbo, sbo;           // descriptor offsets in bytes
+};
+constexpr int WG_THREADS = 192;
+constexpr int WG_BOX_BYTES = 64 * 128;       // 64 pixels x 64 fp16 channels
+
+__device__ __forceinline__ uint64_t make_mn_sw128_desc(uint32_t saddr, uint32_t lbo, uint32_t sbo) {
+  return (uint64_t)((saddr >> 4) & 0x3FFFu) | ((uint64_t)((lbo >> 4) & 0x3FFFu) << 16) |
+         ((uint64_t)((sbo >> 4) & 0x3FFFu) << 32) | (1ull << 46) | (2ull << 61);
+}
+
+__global__ void __launch_bounds__(WG_THREADS, 1)
+wgrad_tc_kernel(const __grid_constant__ CUtensorMap map_g_hi, const __grid_constant__ CUtensorMap map_g_lo,
+                const __grid_constant__ CUtensorMap map_x_hi, const __grid_constant__ CUtensorMap map_x_lo,
+                WgParams p, int nstages) {
+  extern __shared__ uint8_t smem_raw[];
+  __shared__ uint64_t full_bar[8], empty_bar[8], tmem_full_bar;
+  __shared__ uint32_t tmem_base_smem;
+  uint8_t* smem = (uint8_t*)(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+
+  int t = blockIdx.x;
+  const int split = t % p.splits; t /= p.splits;
+  const int tap = t % (p.R * p.S); t /= (p.R * p.S);
+  const int n_tile = t % p.n_tiles;
+  const int m_tile = t / p.n_tiles;
+  const int r = tap / p.S, s = tap - r * p.S;
+  const int m0 = m_tile * 128, n0 = n_tile * p.bn;
+  const int per = (p.ntiles + p.splits - 1) / p.splits;
+  const int t0 = split * per, t1 = min(t0 + per, p.ntiles);
+  const int iters = max(t1 - t0, 0);
+  const int a_bytes = 2 * WG_BOX_BYTES, b_bytes = p.nb * WG_BOX_BYTES;
+  const int stage_bytes = 2 * (a_bytes + b_bytes);
+  const uint32_t acc_cols = p.bn <= 64 ? 64 : (p.bn <= 128 ? 128 : 256);
+  const uint32_t tmem_cols = 2 * acc_cols;
+
+  if (warp == 0 && lane == 0) {
+    prefetch_tmap(&map_g_hi); prefetch_tmap(&map_g_lo); prefetch_tmap(&map_x_hi); prefetch_tmap(&map_x_lo);
+    for (int i = 0; i < nstages; ++i) { mbar_init(&full_bar[i], 1); mbar_init(&empty_bar[i], 1); }
+    mbar_init(&tmem_full_bar, 1);
+    fence_barrier_init();
+  }
+  if (warp == 1) tmem_alloc(&tmem_base_smem, tmem_cols);
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = tmem_base_smem;
+
+  if (warp == 0) {
+    if (elect_one()) {
+      for (int it = 0; it < iters; ++it) {
+        const int stage = it % nstages;
+        mbar_wait(&empty_bar[stage], ((it / nstages) & 1) ^ 1);
+        int tt = t0 + it;
+        const int tx = tt % p.tiles_x; tt /= p.tiles_x;
+        const int ty = tt % p.tiles_y;
+        const int img = tt / p.tiles_y;
+        const int q0 = tx * p.wbox, p0 = ty * p.hbox;
+        uint8_t* st = smem + (size_t)stage * stage_bytes;
+        uint8_t* a_hi = st; uint8_t* a_lo = st + a_bytes;
+        uint8_t* b_hi = st + 2 * a_bytes; uint8_t* b_lo = b_hi + b_bytes;
+        mbar_expect_tx(&full_bar[stage], (uint32_t)stage_bytes);
+#pragma unroll
+        for (int j = 0; j < 2; ++j) {
+          tma_load_4d(&map_g_hi, &full_bar[stage], a_hi + j * WG_BOX_BYTES, m0 + j * 64, q0, p0, img);
+          tma_load_4d(&map_g_lo, &full_bar[stage], a_lo + j * WG_BOX_BYTES, m0 + j * 64, q0, p0, img);
+        }
+        const int cx = q0 + s - p.pad_l, cy = p0 + r - p.pad_t;
+        for (int j = 0; j < p.nb; ++j) {
+          tma_load_4d(&map_x_hi, &full_bar[stage], b_hi + j * WG_BOX_BYTES, n0 + j * 64, cx, cy, img);
+          tma_load_4d(&map_x_lo, &full_bar[stage], b_lo + j * WG_BOX_BYTES, n0 + j * 64, cx, cy, img);
+        }
+      }
+    }
+    __syncwarp();
+  } else if (warp == 1) {
+    // fp16 A/B, fp32 accumulate, M = 128, N = bn, A and B MN-major (transpose bits 15 / 16)
+    const uint32_t idesc = make_idesc_f16(p.bn, 128) | (1u << 15) | (1u << 16);
+    for (int it = 0; it < iters; ++it) {
+      const int stage = it % nstages;
+      mbar_wait(&full_bar[stage], (it / nstages) & 1);
+      tc_fence_after();
+      if (elect_one()) {
+        const uint32_t st = smem_u32(smem + (size_t)stage * stage_bytes);
+        const uint32_t a_hi = st, a_lo = st + a_bytes, b_hi = st + 2 * a_bytes, b_lo = b_hi + b_bytes;
+#pragma unroll
+        for (int k = 0; k < 4; ++k) {          // 4 x 16 pixels per 64-pixel box
+          const uint32_t koff = k * 16 * 128;
+          const uint32_t first = (it | k) != 0;
+          const uint64_t dah = make_mn_sw128_desc(a_hi + koff, p.lbo, p.sbo), dal = make_mn_sw128_desc(a_lo + koff, p.lbo, p.sbo);
+          const uint64_t dbh = make_mn_sw128_desc(b_hi + koff, p.lbo, p.sbo), dbl = make_mn_sw128_desc(b_lo + koff, p.lbo, p.sbo);
+          umma_f16(tmem_base + acc_cols, dal, dbh, idesc, first);
+          umma_f16(tmem_base + acc_cols, dah, dbl, idesc, 1);
+          umma_f16(tmem_base, dah, dbh, idesc, first);
+        }
+        umma_commit(&empty_bar[stage]);
+        if (it == iters - 1) umma_commit(&tmem_full_bar);
+      }
+      __syncwarp();
+    }
+  } else {
+    // epilogue warps 2..5: TMEM lane quarter = warp % 4; lane = output channel k, columns = input channel c
+    const int quarter = warp & 3;
+    const int k = m0 + quarter * 32 + lane;
+    float* dst = p.part + ((size_t)split * (p.R * p.S) + tap) * (size_t)p.C * p.K;
+    if (iters > 0) {
+      mbar_wait(&tmem_full_bar, 0);
+      tc_fence_after();
+    }
+    const float inv = __ldg(p.sx + 1) * __ldg(p.sg + 1);
+    const float cross = 1.0f / 2048.0f;
+    for (int c0 = 0; c0 < p.bn; c0 += 32) {
+      uint32_t vm[32], vc[32];
+      if (iters > 0) {
+        const uint32_t taddr = tmem_base + ((uint32_t)(quarter * 32) << 16) + (uint32_t)c0;
+        tmem_ld32(taddr, vm);
+        tmem_ld32(taddr + acc_cols, vc);
+        tmem_ld_wait();
+      }
+#pragma unroll
+      for (int j = 0; j < 32; ++j) {
+        const int c = n0 + c0 + j;
+        if (c < p.C && k < p.K) {
+          const float v = iters > 0 ? (__uint_as_float(vm[j]) + __uint_as_float(vc[j]) * cross) * inv : 0.0f;
+          dst[(size_t)c * p.K + k] = v;
+        }
+      }
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 1) {
+    tc_fence_after();
+    tmem_dealloc(tmem_base, tmem_cols);
+  }
+}
+
+__global__ void __launch_bounds__(256) wg_reduce_kernel(const float* __restrict__ part, int rows, long long n,
+                                                        float* __restrict__ out) {
+  const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  float tot = 0.f;
+  for (int j = 0; j < rows; ++j) tot += __ldg(part + (size_t)j * n + i);
+  out[i] = tot;
+}
+
+// fp32 NHWC tensor -> fp16 hi / lo halves + {s, 1/s} (the forward's 3xFP16 operand pre-pass)
+static int wg_split(const float* x, size_t numel, int C, void* hi, void* lo, float* scal, cudaStream_t st) {
+  unsigned* amax = (unsigned*)(scal + 2);
+  CRESTE_CUDA(cudaMemsetAsync(amax, 0, 4, st));
+  const long long n4 = (long long)(numel / 4);
+  long long blocks = (n4 + 255) / 256;
+  if (blocks > 148 * 16) blocks = 148 * 16;
+  f16_amax_kernel<<<(int)blocks, 256, 0, st>>>((const float4*)x, nullptr, C, 1, n4, amax);
+  int rc = launch_check("f16_amax_kernel");
+  if (rc) return rc;
+  f16_scale_kernel<<<1, 1, 0, st>>>(amax, scal);
+  if ((rc = launch_check("f16_scale_kernel"))) return rc;
+  f16_split_kernel<<<(int)blocks, 256, 0, st>>>((const float4*)x, nullptr, C, 1, n4, scal, (uint2*)hi, (uint2*)lo);
+  return launch_check("f16_split_kernel");
+}
+
+static void wg_pick_box(int P, int Q, int* wbox, int* hbox) {
+  int best_w = 8;
+  double best = -1.0;
+  for (int w = 64; w >= 1; w >>= 1) {
+    const int h = 64 / w;
+    const double util = ((double)P * Q) / ((double)ceil_div(Q, w) * w * ceil_div(P, h) * h);
+    const double score = util - 1e-3 * fabs(log2((double)w / h));
+    if (score > best) { best = score; best_w = w; }
+  }
+  *wbox = best_w;
+  *hbox = 64 / best_w;
+}
+
+struct WgPlan { int bn, nb, m_tiles, n_tiles, wbox, hbox, tiles_x, tiles_y, ntiles, splits; size_t nx, ng; };
+
+static WgPlan wg_plan(const creste_conv_desc* d) {
+  WgPlan w;
+  const int c64 = (d->C + 63) / 64 * 64;
+  const int nt = (c64 + 255) / 256;
+  w.bn = ((c64 / 64 + nt - 1) / nt) * 64;          // <= 256, balanced over the N tiles
+  w.nb = w.bn / 64;
+  w.n_tiles = ceil_div(d->C, w.bn);
+  w.m_tiles = ceil_div(d->K, 128);
+  wg_pick_box(d->P, d->Q, &w.wbox, &w.hbox);
+  w.tiles_x = ceil_div(d->Q, w.wbox);
+  w.tiles_y = ceil_div(d->P, w.hbox);
+  w.ntiles = d->N * w.tiles_y * w.tiles_x;
+  const int base = w.m_tiles * w.n_tiles * d->R * d->S;
+  int splits = ceil_div(2 * 148, base);
+  const int max_splits = w.ntiles / 8 > 1 ? w.ntiles / 8 : 1;
+  if (splits > max_splits) splits = max_splits;
+  if (splits < 1) splits = 1;
+  w.splits = splits;
+  w.nx = (size_t)d->N * d->H * d->W * d->C;
+  w.ng = (size_t)d->N * d->P * d->Q * d->K;
+  return w;
+}
+
+bool wgrad_tc_supported(const creste_conv_desc* d) {
+  if (d->stride != 1 || d->C % 8 != 0 || d->K % 8 != 0 || d->C < 64 || d->K < 64) return false;
+  if (d->R > 7 || d->S > 7) return false;
+  if ((long long)d->N * d->P * d->Q < 512) return false;
+  return true;
+}
+
+size_t wgrad_tc_workspace_bytes(const creste_conv_desc* d) {
+  const WgPlan w = wg_plan(d);
+  return 2 * align_up(w.nx * 2, 1024) + 2 * align_up(w.ng * 2, 1024) + 1024 +
+         (size_t)w.splits * d->R * d->S * d->C * d->K * sizeof(float);
+}
+
+int wgrad_tc_launch(const creste_conv_desc* d, const float* x, const float* g, float* dw, void* ws, size_t ws_bytes,
+                    cudaStream_t st) {
+  if (!wgrad_tc_supported(d)) { set_error("creste_conv2d_wgrad_tc: shape not served (C, K >= 64, multiples of 8, stride 1)"); return CRESTE_ERR_ARG; }
+  if (!ws || ws_bytes < wgrad_tc_workspace_bytes(d)) { set_error("creste_conv2d_wgrad_tc: workspace"); return CRESTE_ERR_WORKSPACE; }
+  const WgPlan w = wg_plan(d);
+  char* base = (char*)ws;
+  void* x_hi = base; void* x_lo = base + align_up(w.nx * 2, 1024);
+  char* gb = base + 2 * align_up(w.nx * 2, 1024);
+  void* g_hi = gb; void* g_lo = gb + align_up(w.ng * 2, 1024);
+  float* scal = (float*)(gb + 2 * align_up(w.ng * 2, 1024));      // x: [0..3], g: [4..7]
+  float* part = (float*)((char*)scal + 1024);
+  int rc;
+  if ((rc = wg_split(x, w.nx, d->C, x_hi, x_lo, scal, st))) return rc;
+  if ((rc = wg_split(g, w.ng, d->K, g_hi, g_lo, scal + 4, st))) return rc;
+  CUtensorMap mg_hi, mg_lo, mx_hi, mx_lo;
+  // box {64 channels, wbox, hbox, 1}: make_map_a's f16 form with a 64-pixel box
+  if ((rc = make_map_a(&mg_hi, g_hi, d->N, d->P, d->Q, d->K, w.wbox, w.hbox, true, 1))) return rc;
+  if ((rc = make_map_a(&mg_lo, g_lo, d->N, d->P, d->Q, d->K, w.wbox, w.hbox, true, 1))) return rc;
+  if ((rc = make_map_a(&mx_hi, x_hi, d->N, d->H, d->W, d->C, w.wbox, w.hbox, true, 1))) return rc;
+  if ((rc = make_map_a(&mx_lo, x_lo, d->N, d->H, d->W, d->C, w.wbox, w.hbox, true, 1))) return rc;
+  WgParams p;
+  p.part = part; p.sx = scal; p.sg = scal + 4;
+  p.N = d->N; p.P = d->P; p.Q = d->Q; p.C = d->C; p.K = d->K; p.R = d->R; p.S = d->S;
+  p.pad_t = d->pad_t; p.pad_l = d->pad_l;
+  p.wbox = w.wbox; p.hbox = w.hbox; p.tiles_x = w.tiles_x; p.tiles_y = w.tiles_y; p.ntiles = w.ntiles;
+  p.bn = w.bn; p.nb = w.nb; p.m_tiles = w.m_tiles; p.n_tiles = w.n_tiles; p.splits = w.splits;
+  p.lbo = WG_BOX_BYTES; p.sbo = 1024;
+  if (const char* e = getenv("CRESTE_WGRAD_SWAP")) if (atoi(e)) { p.lbo = 1024; p.sbo = WG_BOX_BYTES; }
+  const size_t stage_bytes = (size_t)2 * (2 + w.nb) * WG_BOX_BYTES;
+  int nstages = (int)((200 * 1024) / stage_bytes);
+  if (nstages > 8) nstages = 8;
+  if (nstages < 2) { set_error("creste_conv2d_wgrad_tc: stage too large"); return CRESTE_ERR_ARG; }
+  const size_t smem = (size_t)nstages * stage_bytes + 1024;
+  CRESTE_CUDA(cudaFuncSetAttribute(wgrad_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  const int grid = w.m_tiles * w.n_tiles * d->R * d->S * w.splits;
+  wgrad_tc_kernel<<<grid, WG_THREADS, smem, st>>>(mg_hi, mg_lo, mx_hi, mx_lo, p, nstages);
+  if ((rc = launch_check("wgrad_tc_kernel"))) return rc;
+  const long long n = (long long)d->R * d->S * d->C * d->K;
+  wg_reduce_kernel<<<(int)((n + 255) / 256), 256, 0, st>>>(part, w.splits, n, dw);
+  return launch_check("wg_reduce_kernel");
+}
+
 }  // namespace creste
 
 /* development aid: per-CTA globaltimer stamps of the next tensor-core conv launches (8 u64 per CTA) */
@@ -889,4 +1167,17 @@ extern "C" int creste_conv2d_tc_supported(const creste_conv_desc* d) {
 // weight layout helper for the host side (Python packs on the GPU with torch; this reports sizes)
 extern "C" int creste_conv2d_tc_layout(int K, int C, int R, int S, int* block_n, int* npad, int* cpad) {
   return creste::conv_tc_layout(K, C, R, S, block_n, npad, cpad);
+}
+
+/* tcgen05 weight gradient (3xFP16): dw [R*S*C][K] like creste_conv2d_wgrad, for C, K >= 64. */
+extern "C" int creste_conv2d_wgrad_tc_supported(const creste_conv_desc* d) {
+  return d && creste::wgrad_tc_supported(d) ? 1 : 0;
+}
+extern "C" size_t creste_conv2d_wgrad_tc_workspace_bytes(const creste_conv_desc* d) {
+  return d ? creste::wgrad_tc_workspace_bytes(d) : 0;
+}
+extern "C" int creste_conv2d_wgrad_tc(const creste_conv_desc* d, const float* x, const float* g, float* dw, void* ws,
+                                      size_t ws_bytes, void* stream) {
+  if (!d || !x || !g || !dw) { creste::set_error("creste_conv2d_wgrad_tc: bad args"); return CRESTE_ERR_ARG; }
+  return creste::wgrad_tc_launch(d, x, g, dw, ws, ws_bytes, (cudaStream_t)stream);
 }

@@ -704,3 +704,26 @@ def masked_mse_bwd(pred, gt, scale_dev):
                                       ptr(scale_dev.reshape(1).float().contiguous()), ptr(out), stream()),
           "creste_masked_mse_bwd")
     return out
+
+
+def wgrad_tc_supported(x_shape, K, R, S, pad):
+    N, H, W, Cc = x_shape
+    pt, pb, pl, pr = pad
+    d = ConvDesc(N, H, W, Cc, K, R, S, 1, pt, pl, H + pt + pb - R + 1, W + pl + pr - S + 1, 0, 0, 4)
+    return bool(lib().creste_conv2d_wgrad_tc_supported(C.byref(d)))
+
+
+def conv2d_wgrad_tc(x_nhwc, g_nhwc, R, S, pad):
+    """dw [K,C,R,S] of a stride-1 conv on the tcgen05 tensor cores (3xFP16 split); C, K >= 64."""
+    x_nhwc, g_nhwc = x_nhwc.contiguous(), g_nhwc.contiguous()
+    N, H, W, Cc = x_nhwc.shape
+    _, P, Q, K = g_nhwc.shape
+    pt, pb, pl, pr = pad
+    assert P == H + pt + pb - R + 1 and Q == W + pl + pr - S + 1
+    d = ConvDesc(N, H, W, Cc, K, R, S, 1, pt, pl, P, Q, 0, 0, 4)
+    n = lib().creste_conv2d_wgrad_tc_workspace_bytes(C.byref(d))
+    ws = _ws(n, x_nhwc.device)
+    dw = torch.empty(R * S * Cc, K, device=x_nhwc.device)
+    check(lib().creste_conv2d_wgrad_tc(C.byref(d), ptr(x_nhwc), ptr(g_nhwc), ptr(dw), ptr(ws), C.c_size_t(n),
+                                       stream()), "creste_conv2d_wgrad_tc")
+    return dw.view(R, S, Cc, K).permute(3, 2, 0, 1).contiguous()

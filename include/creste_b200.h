@@ -336,6 +336,15 @@ int creste_ce_depth_bwd(const float* logits_nchw, const float* label_mm, int N, 
 int creste_masked_mse_bwd(const float* pred, const float* gt, long long n, const float* scale_dev,
                           float* dpred, void* stream);
 
+/* Weight gradient of a stride-1 dense conv on the tcgen05 tensor cores (3xFP16 split, fp32 accumulate):
+ * same contract as creste_conv2d_wgrad (dw [R*S*C][K]) for the wide layers of the backbone
+ * (C, K >= 64 and multiples of 8, N*P*Q >= 512).  GEMM over the PIXELS with MN-major operands staged by
+ * TMA straight from the NHWC tensors (csrc/conv_tc.cu, wgrad_tc_kernel). */
+int creste_conv2d_wgrad_tc_supported(const creste_conv_desc* d);
+size_t creste_conv2d_wgrad_tc_workspace_bytes(const creste_conv_desc* d);
+int creste_conv2d_wgrad_tc(const creste_conv_desc* d, const float* x, const float* g, float* dw, void* ws,
+                           size_t ws_bytes, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -110,6 +110,25 @@ def test_loss_gradients(cuda):
     _close(ops.masked_mse_bwd(pred.to(cuda), gt.to(cuda), scale.to(cuda)), tb.masked_mse_bwd(pred, gt, scale), 1e-6, "mse bwd")
 
 
+@pytest.mark.parametrize("N,H,W,C,K,R", [(2, 16, 24, 64, 64, 1), (2, 16, 24, 128, 256, 3), (2, 16, 30, 496, 496, 3),
+                                         (2, 20, 28, 112, 72, 3), (3, 17, 23, 72, 200, 1), (1, 32, 60, 432, 432, 3),
+                                         (2, 16, 24, 1152, 192, 1), (1, 24, 40, 64, 64, 5)])
+def test_wgrad_tcgen05(cuda, N, H, W, C, K, R):
+    """Weight gradient on the tensor cores (MN-major tcgen05 operands, 3xFP16 split) against torch CPU
+    float64: ragged pixel boxes, channel tails (C, K not multiples of 64 / 128), 1x1 / 3x3 / 5x5 taps."""
+    import torch.nn.functional as F
+    from creste_public_b200 import ops
+    g = np.random.default_rng(C + K + R)
+    pad = (R // 2,) * 4
+    x, gy = _t(g, N, H, W, C), _t(g, N, H, W, K, scale=1e-3)
+    assert ops.wgrad_tc_supported(tuple(x.shape), K, R, R, pad)
+    dw = ops.conv2d_wgrad_tc(x.to(cuda), gy.to(cuda), R, R, pad)
+    w = torch.zeros(K, C, R, R, dtype=torch.float64, requires_grad=True)
+    y = F.conv2d(x.permute(0, 3, 1, 2).double(), w, padding=R // 2)
+    (ref,) = torch.autograd.grad(y, w, gy.permute(0, 3, 1, 2).double())
+    _close(dw, ref, 1e-5, "wgrad_tc")
+
+
 @pytest.mark.parametrize("precision", ["fp32", "3xfp16"])
 def test_training_step_matches_port_and_golden(cuda, golden, precision):
     """One full stage-1 step (forward in train mode, three losses, backward, Adam) on the GPU against the

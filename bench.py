@@ -239,7 +239,7 @@ def run_irl_steps(args, dev, rank, world, barrier, Bi=8, Hm=256, Wm=256, steps=5
             "precision": args.precision}
 
 
-def run_stage1_steps(args, dev, rank, world, barrier, Bi=4, H=512, W=960, steps=3):
+def run_stage1_steps(args, dev, rank, world, barrier, Bi=16, H=512, W=960, steps=3):
     """configs[2] shard: stage-1 (distillation) backbone training step, Bi frames per GPU -- train-mode
     forward (BatchNorm batch statistics, drop-connect), CrossEntropyDepth + SmoothL1Depth + MSELoss,
     backward through the whole encoder, ONE flat gradient all-reduce (N > 1), fused Adam."""
@@ -482,7 +482,7 @@ def run_ours(args):
     if rank == 0 and irl is not None:
         irl["vi_roofline"] = vi_roof
         irl["cpu_baseline"] = irl_cpu
-    # ---- third leg: stage-1 backbone training frames/s (configs[2] shard, B = 4 per GPU)
+    # ---- third leg: stage-1 backbone training frames/s (configs[2]: batch 16 per GPU)
     stage1 = run_stage1_steps(args, dev, rank, world, barrier)
     if rank == 0 and stage1 is not None and not args.no_cpu and world == 1:
         try:

@@ -56,7 +56,7 @@ def _conv_raw(x, w, ph, pw):
     return y if Kp == K else y[..., :K].contiguous()
 
 
-WGRAD_TC = True      # tcgen05 weight gradient for the wide layers (C, K >= 64) in the tensor-core modes
+WGRAD_TC = True      # tcgen05 weight gradient (>= 512 output pixels) in the tensor-core precision modes
 WGRAD_TILE = 64      # the CUDA-core wgrad kernels hold one [C x K] tile of at most 64 x 64 per CTA
 
 
@@ -66,9 +66,13 @@ def _wgrad_raw(x, g, R, S, ph, pw):
     through the same kernel."""
     Cc, K = x.shape[-1], g.shape[-1]
     pad = (ph, ph, pw, pw)
-    if WGRAD_TC and engine.get_precision() != "fp32" and x.dim() == 4 and \
-            ops.wgrad_tc_supported(tuple(x.shape), K, R, S, pad):
-        return ops.conv2d_wgrad_tc(x, g, R, S, pad)        # tcgen05, 3xFP16 split
+    if R == 1 and S == 1 and x.numel() // Cc <= 64 and max(Cc, K) > WGRAD_TILE:
+        return ops.wgrad_rows(x, g)          # squeeze-excite convs: [B,1,1,C] vectors, one launch
+    if WGRAD_TC and engine.get_precision() != "fp32" and x.dim() == 4:
+        Cp, Kp = Cc + (-Cc) % 8, K + (-K) % 8
+        if ops.wgrad_tc_supported(tuple(x.shape[:3]) + (Cp,), Kp, R, S, pad):      # tcgen05, 3xFP16 split
+            dw = ops.conv2d_wgrad_tc(_pad_last(x, 8), _pad_last(g, 8), R, S, pad)
+            return dw if (Cp == Cc and Kp == K) else dw[:K, :Cc].contiguous()
     if Cc <= WGRAD_TILE and K <= WGRAD_TILE:
         dw = ops.conv2d_wgrad(_pad_last(x, 8), _pad_last(g, 8), R, S, pad)
         return dw[:K, :Cc].contiguous()

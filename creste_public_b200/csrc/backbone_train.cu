@@ -413,6 +413,19 @@ __global__ void __launch_bounds__(1024) wgrad_strided_c4_kernel(const float* __r
   dst[(tap * 4 + 2) * K + k] = (double)acc.z; dst[(tap * 4 + 3) * K + k] = (double)acc.w;
 }
 
+// ------------------------------------------------- 1x1 wgrad over a handful of rows (squeeze-excite)
+// dw[c][k] = sum_p x[p][c] * g[p][k], p < npix (= batch size: the SE convs act on [B,1,1,C] vectors)
+__global__ void __launch_bounds__(256) wgrad_rows_kernel(const float* __restrict__ x, const float* __restrict__ g,
+                                                         int npix, int C, int K, float* __restrict__ dw) {
+  const long long n = (long long)C * K;
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) {
+    const int c = (int)(i / K), k = (int)(i - (long long)c * K);
+    float acc = 0.f;
+    for (int p = 0; p < npix; ++p) acc = fmaf(__ldg(x + (size_t)p * C + c), __ldg(g + (size_t)p * K + k), acc);
+    dw[i] = acc;
+  }
+}
+
 // ----------------------------------------------------------------------------- loss gradients
 // dlogits[n,k,p] = scale * (softmax_k(logits[n,:,p]) - [k == bin]) on valid pixels, 0 elsewhere
 // (CrossEntropyDepth, loss_utils.py:477-527; bin_depths 'UD', depth_utils.py:346-383).  NCHW.
@@ -635,6 +648,12 @@ extern "C" int creste_wgrad_strided(const float* x, const float* g, int N, int H
   const int n = R * S * C * K;
   reduce_parts_kernel<float><<<ceil_div(n, 256), 256, 0, st>>>((const double*)ws, PB, n, 1, 1.0, dw);
   return launch_check("reduce_parts_kernel");
+}
+
+extern "C" int creste_wgrad_rows(const float* x, const float* g, int npix, int C, int K, float* dw, void* stream) {
+  CRESTE_CHECK_ARG(x && g && dw && npix > 0 && npix <= 4096 && C > 0 && K > 0, "creste_wgrad_rows: bad args");
+  wgrad_rows_kernel<<<ELT_GRID((long long)C * K), 256, 0, (cudaStream_t)stream>>>(x, g, npix, C, K, dw);
+  return launch_check("wgrad_rows_kernel");
 }
 
 extern "C" int creste_ce_depth_bwd(const float* logits_nchw, const float* label_mm, int N, int D, long long HW,

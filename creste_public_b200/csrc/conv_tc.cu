@@ -930,6 +930,11 @@ wgrad_tc_kernel(const __grid_constant__ CUtensorMap map_g_hi, const __grid_const
   const int iters = max(t1 - t0, 0);
   const int a_bytes = 2 * WG_BOX_BYTES, b_bytes = p.nb * WG_BOX_BYTES;
   const int stage_bytes = 2 * (a_bytes + b_bytes);
+  // 64-channel boxes that lie entirely beyond K / C are not fetched: their accumulator rows / columns hold
+  // garbage that the epilogue never stores (rows and columns of D are independent)
+  const int a_boxes = (p.K - m0 > 64) ? 2 : 1;
+  const int b_boxes = min(p.nb, (p.C - n0 + 63) / 64);
+  const uint32_t tx_bytes = (uint32_t)(2 * (a_boxes + b_boxes) * WG_BOX_BYTES);
   const uint32_t acc_cols = p.bn <= 64 ? 64 : (p.bn <= 128 ? 128 : 256);
   const uint32_t tmem_cols = 2 * acc_cols;
 
@@ -958,14 +963,13 @@ wgrad_tc_kernel(const __grid_constant__ CUtensorMap map_g_hi, const __grid_const
         uint8_t* st = smem + (size_t)stage * stage_bytes;
         uint8_t* a_hi = st; uint8_t* a_lo = st + a_bytes;
         uint8_t* b_hi = st + 2 * a_bytes; uint8_t* b_lo = b_hi + b_bytes;
-        mbar_expect_tx(&full_bar[stage], (uint32_t)stage_bytes);
-#pragma unroll
-        for (int j = 0; j < 2; ++j) {
+        mbar_expect_tx(&full_bar[stage], tx_bytes);
+        for (int j = 0; j < a_boxes; ++j) {
           tma_load_4d(&map_g_hi, &full_bar[stage], a_hi + j * WG_BOX_BYTES, m0 + j * 64, q0, p0, img);
           tma_load_4d(&map_g_lo, &full_bar[stage], a_lo + j * WG_BOX_BYTES, m0 + j * 64, q0, p0, img);
         }
         const int cx = q0 + s - p.pad_l, cy = p0 + r - p.pad_t;
-        for (int j = 0; j < p.nb; ++j) {
+        for (int j = 0; j < b_boxes; ++j) {
           tma_load_4d(&map_x_hi, &full_bar[stage], b_hi + j * WG_BOX_BYTES, n0 + j * 64, cx, cy, img);
           tma_load_4d(&map_x_lo, &full_bar[stage], b_lo + j * WG_BOX_BYTES, n0 + j * 64, cx, cy, img);
         }
@@ -1098,7 +1102,7 @@ static WgPlan wg_plan(const creste_conv_desc* d) {
 }
 
 bool wgrad_tc_supported(const creste_conv_desc* d) {
-  if (d->stride != 1 || d->C % 8 != 0 || d->K % 8 != 0 || d->C < 64 || d->K < 64) return false;
+  if (d->stride != 1 || d->C % 8 != 0 || d->K % 8 != 0 || d->C < 8 || d->K < 8) return false;
   if (d->R > 7 || d->S > 7) return false;
   if ((long long)d->N * d->P * d->Q < 512) return false;
   return true;
@@ -1112,7 +1116,7 @@ size_t wgrad_tc_workspace_bytes(const creste_conv_desc* d) {
 
 int wgrad_tc_launch(const creste_conv_desc* d, const float* x, const float* g, float* dw, void* ws, size_t ws_bytes,
                     cudaStream_t st) {
-  if (!wgrad_tc_supported(d)) { set_error("creste_conv2d_wgrad_tc: shape not served (C, K >= 64, multiples of 8, stride 1)"); return CRESTE_ERR_ARG; }
+  if (!wgrad_tc_supported(d)) { set_error("creste_conv2d_wgrad_tc: shape not served (C, K multiples of 8, stride 1, >= 512 output pixels)"); return CRESTE_ERR_ARG; }
   if (!ws || ws_bytes < wgrad_tc_workspace_bytes(d)) { set_error("creste_conv2d_wgrad_tc: workspace"); return CRESTE_ERR_WORKSPACE; }
   const WgPlan w = wg_plan(d);
   char* base = (char*)ws;

@@ -727,3 +727,13 @@ def conv2d_wgrad_tc(x_nhwc, g_nhwc, R, S, pad):
     check(lib().creste_conv2d_wgrad_tc(C.byref(d), ptr(x_nhwc), ptr(g_nhwc), ptr(dw), ptr(ws), C.c_size_t(n),
                                        stream()), "creste_conv2d_wgrad_tc")
     return dw.view(R, S, Cc, K).permute(3, 2, 0, 1).contiguous()
+
+
+def wgrad_rows(x, g):
+    """dw [K,C,1,1] of a 1x1 conv over a handful of rows: x [...,C], g [...,K] with <= 4096 rows."""
+    x, g = x.contiguous(), g.contiguous()
+    Cc, K = x.shape[-1], g.shape[-1]
+    npix = x.numel() // Cc
+    dw = torch.empty(Cc, K, device=x.device)
+    check(lib().creste_wgrad_rows(ptr(x), ptr(g), npix, Cc, K, ptr(dw), stream()), "creste_wgrad_rows")
+    return dw.t().contiguous().view(K, Cc, 1, 1)

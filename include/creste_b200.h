@@ -328,6 +328,9 @@ size_t creste_wgrad_strided_workspace_bytes(int N, int P, int Q, int C, int K, i
 int creste_wgrad_strided(const float* x, const float* g, int N, int H, int W, int C, int K, int R, int S,
                          int stride, int pad_t, int pad_l, int P, int Q, float* dw, void* ws,
                          size_t ws_bytes, void* stream);
+/* 1x1 weight gradient over a handful of rows (the squeeze-excite convs act on [B,1,1,C] vectors):
+ * dw [C][K] = x^T g with x [npix,C], g [npix,K], npix <= 4096 */
+int creste_wgrad_rows(const float* x, const float* g, int npix, int C, int K, float* dw, void* stream);
 /* gradients of CrossEntropyDepth (loss_utils.py:477-527) w.r.t. the NCHW logits and of MSELoss
  * (:606-647); scale_dev is a DEVICE float (upstream gradient / #valid), so no host sync. */
 int creste_ce_depth_bwd(const float* logits_nchw, const float* label_mm, int N, int D, long long HW,

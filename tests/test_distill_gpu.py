@@ -91,6 +91,13 @@ def test_stem_wgrad(cuda):
     _close(ops.wgrad_strided(x.to(cuda), gy.to(cuda), 3, 3, 2, pad), tb.wgrad_strided(x, gy, 3, 3, 2, pad), 1e-5, "stem wgrad")
 
 
+def test_wgrad_rows(cuda):
+    from creste_public_b200 import ops
+    g = np.random.default_rng(14)
+    x, gy = _t(g, 4, 1, 1, 1152), _t(g, 4, 1, 1, 48)
+    _close(ops.wgrad_rows(x.to(cuda), gy.to(cuda)), tb.wgrad_rows(x, gy), 2e-6, "wgrad_rows")
+
+
 def test_loss_gradients(cuda):
     from creste_public_b200 import ops
     g = np.random.default_rng(13)
@@ -112,7 +119,8 @@ def test_loss_gradients(cuda):
 
 @pytest.mark.parametrize("N,H,W,C,K,R", [(2, 16, 24, 64, 64, 1), (2, 16, 24, 128, 256, 3), (2, 16, 30, 496, 496, 3),
                                          (2, 20, 28, 112, 72, 3), (3, 17, 23, 72, 200, 1), (1, 32, 60, 432, 432, 3),
-                                         (2, 16, 24, 1152, 192, 1), (1, 24, 40, 64, 64, 5)])
+                                         (2, 16, 24, 1152, 192, 1), (1, 24, 40, 64, 64, 5), (2, 32, 32, 40, 64, 5),
+                                         (2, 32, 32, 32, 16, 1), (2, 32, 32, 48, 8, 1), (2, 24, 24, 16, 96, 1), (1, 32, 32, 144, 24, 1)])
 def test_wgrad_tcgen05(cuda, N, H, W, C, K, R):
     """Weight gradient on the tensor cores (MN-major tcgen05 operands, 3xFP16 split) against torch CPU
     float64: ragged pixel boxes, channel tails (C, K not multiples of 64 / 128), 1x1 / 3x3 / 5x5 taps."""

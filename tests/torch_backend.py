@@ -267,6 +267,11 @@ def wgrad_strided(x, g, R, S, stride, pad):
     return dw
 
 
+def wgrad_rows(x, g):
+    Cc, K = x.shape[-1], g.shape[-1]
+    return (g.reshape(-1, K).t() @ x.reshape(-1, Cc)).view(K, Cc, 1, 1)
+
+
 def conv2d(x, w_packed, K, R, S, stride=1, pad=(0, 0, 0, 0), scale=None, shift=None, gate=None,
            residual=None, act="none", out_nchw=False, precision="fp32"):
     """Only the raw strided stem call of StemConvFn reaches this stand-in (w_packed = torch weights)."""
@@ -333,7 +338,7 @@ def depth_expectation(logits_nhwc, dmin=300.0, dmax=25600.0):
 
 STAGE1_NAMES = ["chan_moments", "chan_affine_act", "bn_act_bwd", "chan_axpby", "dwconv_fwd", "dwconv_dgrad",
                 "dwconv_wgrad", "sample_dot", "sample_affine", "act", "act_bwd", "add_scaled", "chan_slice",
-                "wgrad_strided", "conv2d", "pack_conv_weight", "upsample_concat", "stage1_depth_losses",
+                "wgrad_strided", "wgrad_rows", "conv2d", "pack_conv_weight", "upsample_concat", "stage1_depth_losses",
                 "ce_depth_bwd", "masked_mse", "masked_mse_bwd", "depth_expectation"]
 
 

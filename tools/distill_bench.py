@@ -32,7 +32,7 @@ if os.environ.get("PROFILE"):
             rec.append((tag, name, e0, e1)); return r
         return w
     skip = ("conv_desc", "tc_supported", "tc_layout", "pack_conv_weight", "pack_conv_weight_tc", "pack_conv_weight_f16",
-            "rna_tf32", "maxpool2", "upsample2")
+            "rna_tf32", "maxpool2", "upsample2", "ptr", "lib", "stream", "check", "wgrad_tc_supported")
     for n in dir(ops):
         f = getattr(ops, n)
         if isinstance(f, types.FunctionType) and not n.startswith("_") and n not in skip:

@@ -414,38 +414,35 @@ def _update_running(bn, mean, var, M):
 
 class BNActFn(Function):
     """BatchNorm2d with batch statistics + activation ('none' | 'relu' | 'swish') as ONE node:
-    forward = one moments pass + one affine/act pass; backward = one pass producing
-    gu = g*act'(u) with (sum gu, sum gu*x), then dx = gu*p + x*q + r in one more pass."""
+    forward = one moments pass + one [C]-sized finalize launch + one affine/act pass; backward = one pass
+    producing gu = g*act'(u) with (sum gu, sum gu*x), one finalize launch, then dx = gu*a + x*q + r."""
 
     @staticmethod
     def forward(ctx, x, weight, bias, bn, act):
         Cc = x.shape[-1]
         M = x.numel() // Cc
         st = ops.chan_moments(x)
-        mean = st[0] / M
-        var = (st[1] / M - mean * mean).clamp_min(0.0)
-        _update_running(bn, mean, var, M)
-        inv = torch.rsqrt(var + bn.eps)
-        a = inv * weight.detach().double()
-        b = bias.detach().double() - mean * a
-        a32, b32 = a.float().contiguous(), b.float().contiguous()
-        ctx.save_for_backward(x, a32, b32, mean, inv)
+        track = bn.training and bn.track_running_stats and bn.running_mean is not None
+        if track and bn.num_batches_tracked is not None:
+            bn.num_batches_tracked += 1
+        mom = bn.momentum
+        if track and mom is None:
+            mom = 1.0 / float(bn.num_batches_tracked)        # cumulative average (one host sync, as torch)
+        ab, mi = ops.bn_fwd_finalize(st, weight.detach() if weight is not None else None,
+                                     bias.detach() if bias is not None else None, M, bn.eps, mom,
+                                     bn.running_mean if track else None, bn.running_var if track else None)
+        ctx.save_for_backward(x, ab, mi)
         ctx.act, ctx.M = act, M
-        return ops.chan_affine_act(x, a32, b32, act)
+        return ops.chan_affine_act(x, ab[0], ab[1], act)
 
     @staticmethod
     @once
     def backward(ctx, g):
-        x, a32, b32, mean, inv = ctx.saved_tensors
-        M = ctx.M
-        gu, sums = ops.bn_act_bwd(g, x, a32, b32, ctx.act)
-        s1, s2 = sums[0], sums[1]
-        dgamma = inv * (s2 - mean * s1)
-        a = a32.double()
-        q = -a * inv * dgamma / M
-        r = -a * s1 / M - q * mean
-        dx = ops.chan_axpby(gu, x, a32, q.float(), r.float()) if ctx.needs_input_grad[0] else None
-        return dx, dgamma.float(), s1.float(), None, None
+        x, ab, mi = ctx.saved_tensors
+        gu, sums = ops.bn_act_bwd(g, x, ab[0], ab[1], ctx.act)
+        out4 = ops.bn_bwd_finalize(sums, ab, mi, ctx.M)
+        dx = ops.chan_axpby(gu, x, ab[0], out4[2], out4[3]) if ctx.needs_input_grad[0] else None
+        return dx, out4[0], out4[1], None, None
 
 
 def bn_act(x, bn, act="none"):

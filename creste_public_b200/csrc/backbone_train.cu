@@ -230,22 +230,35 @@ __global__ void __launch_bounds__(256) chan_reduce_kernel(Op op, int C, long lon
   }
 }
 
-// out[z*n + i] = scale * sum_bx part[(z*PB + bx)*n + i]
+// out[z*n + i] = scale * sum_bx part[(z*PB + bx)*n + i].  32 outputs per block; 8 row lanes per output sum
+// rows lane, lane + 8, ... in order, then the 8 lane sums are added in lane order (fixed order => reproducible).
 template <class T>
 __global__ void __launch_bounds__(256) reduce_parts_kernel(const double* __restrict__ part, int PB, int n, int Z,
                                                            double scale, T* __restrict__ out) {
-  const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
-  if (i >= (long long)n * Z) return;
-  const int z = (int)(i / n), k = (int)(i - (long long)z * n);
+  __shared__ double s_sum[8][32];
+  const int o = threadIdx.x & 31, rl = threadIdx.x >> 5;
+  const long long i = (long long)blockIdx.x * 32 + o;
+  const bool ok = i < (long long)n * Z;
   double t = 0.0;
-  for (int b = 0; b < PB; ++b) t += part[((size_t)z * PB + b) * n + k];
-  out[i] = (T)(t * scale);
+  if (ok) {
+    const int z = (int)(i / n), k = (int)(i - (long long)z * n);
+    const double* src = part + (size_t)z * PB * n + k;
+    for (int b = rl; b < PB; b += 8) t += src[(size_t)b * n];
+  }
+  s_sum[rl][o] = t;
+  __syncthreads();
+  if (rl == 0 && ok) {
+    double tot = s_sum[0][o];
+#pragma unroll
+    for (int l = 1; l < 8; ++l) tot += s_sum[l][o];
+    out[i] = (T)(tot * scale);
+  }
 }
 
 static int reduce_pb(long long npix, int Z) {
   long long b = npix / 64;
   if (b < 1) b = 1;
-  long long cap = 1184 / (Z > 0 ? Z : 1);
+  long long cap = 592 / (Z > 0 ? Z : 1);          // x ceil(C/128) channel tiles: >= 4 CTAs per SM at C >= 128
   if (cap < 4) cap = 4;
   return (int)(b > cap ? cap : b);
 }
@@ -413,6 +426,49 @@ __global__ void __launch_bounds__(1024) wgrad_strided_c4_kernel(const float* __r
   dst[(tap * 4 + 2) * K + k] = (double)acc.z; dst[(tap * 4 + 3) * K + k] = (double)acc.w;
 }
 
+// ---------------------------------------------------------------- BatchNorm per-channel algebra
+// forward: batch moments -> (a, b) of y = x*a + b, saved (mean, inv) and the running-stat update of
+// F.batch_norm(training=True) (momentum form; unbiased variance).  One launch instead of ~15 [C]-sized ops.
+__global__ void __launch_bounds__(256) bn_fwd_finalize_kernel(const double* __restrict__ st, const float* __restrict__ weight,
+                                                              const float* __restrict__ bias, int C, double M, double eps,
+                                                              float momentum, float* __restrict__ running_mean,
+                                                              float* __restrict__ running_var, float* __restrict__ ab,
+                                                              double* __restrict__ mi) {
+  const int c = blockIdx.x * blockDim.x + threadIdx.x;
+  if (c >= C) return;
+  const double mean = st[c] / M;
+  double var = st[C + c] / M - mean * mean;
+  var = var > 0.0 ? var : 0.0;
+  if (running_mean) {
+    const double unb = var * (M / (M > 1.0 ? M - 1.0 : 1.0));
+    running_mean[c] = running_mean[c] * (1.0f - momentum) + momentum * (float)mean;
+    running_var[c] = running_var[c] * (1.0f - momentum) + momentum * (float)unb;
+  }
+  const double inv = 1.0 / sqrt(var + eps);
+  const double a = inv * (weight ? (double)weight[c] : 1.0);
+  const double b = (bias ? (double)bias[c] : 0.0) - mean * a;
+  ab[c] = (float)a;
+  ab[C + c] = (float)b;
+  mi[c] = mean;
+  mi[C + c] = inv;
+}
+
+// backward: (sum gu, sum gu*x) -> dgamma, dbeta and the (q, r) of dx = gu*a + x*q + r
+__global__ void __launch_bounds__(256) bn_bwd_finalize_kernel(const double* __restrict__ sums, const float* __restrict__ ab,
+                                                              const double* __restrict__ mi, int C, double M,
+                                                              float* __restrict__ out4) {
+  const int c = blockIdx.x * blockDim.x + threadIdx.x;
+  if (c >= C) return;
+  const double s1 = sums[c], s2 = sums[C + c], mean = mi[c], inv = mi[C + c], a = (double)ab[c];
+  const double dgamma = inv * (s2 - mean * s1);
+  const double q = -a * inv * dgamma / M;
+  const double r = -a * s1 / M - q * mean;
+  out4[c] = (float)dgamma;
+  out4[C + c] = (float)s1;
+  out4[2 * C + c] = (float)q;
+  out4[3 * C + c] = (float)r;
+}
+
 // ------------------------------------------------- 1x1 wgrad over a handful of rows (squeeze-excite)
 // dw[c][k] = sum_p x[p][c] * g[p][k], p < npix (= batch size: the SE convs act on [B,1,1,C] vectors)
 __global__ void __launch_bounds__(256) wgrad_rows_kernel(const float* __restrict__ x, const float* __restrict__ g,
@@ -493,7 +549,7 @@ extern "C" int creste_chan_moments(const float* x, long long npix, int C, double
   chan_reduce_kernel<2, MomentsOp><<<dim3(PB, ceil_div(C, 128), 1), 256, 0, st>>>(MomentsOp{x}, C, npix, (double*)ws);
   int rc = launch_check("chan_reduce_kernel<moments>");
   if (rc) return rc;
-  reduce_parts_kernel<double><<<ceil_div(2 * C, 256), 256, 0, st>>>((const double*)ws, PB, 2 * C, 1, 1.0, out2);
+  reduce_parts_kernel<double><<<ceil_div(2 * C, 32), 256, 0, st>>>((const double*)ws, PB, 2 * C, 1, 1.0, out2);
   return launch_check("reduce_parts_kernel");
 }
 
@@ -517,7 +573,7 @@ extern "C" int creste_bn_act_bwd(const float* g, const float* x, const float* a,
                                                                                  npix, (double*)ws);
   int rc = launch_check("chan_reduce_kernel<bn_act_bwd>");
   if (rc) return rc;
-  reduce_parts_kernel<double><<<ceil_div(2 * C, 256), 256, 0, st>>>((const double*)ws, PB, 2 * C, 1, 1.0, sums2);
+  reduce_parts_kernel<double><<<ceil_div(2 * C, 32), 256, 0, st>>>((const double*)ws, PB, 2 * C, 1, 1.0, sums2);
   return launch_check("reduce_parts_kernel");
 }
 
@@ -569,7 +625,7 @@ extern "C" int creste_dwconv_wgrad(const float* x, const float* g, int N, int H,
   else dwconv_wgrad_kernel<5><<<grid, 256, 0, st>>>(x, g, N, H, W, C, stride, pad_t, pad_l, P, Q, (double*)ws);
   int rc = launch_check("dwconv_wgrad_kernel");
   if (rc) return rc;
-  reduce_parts_kernel<float><<<ceil_div(R * R * C, 256), 256, 0, st>>>((const double*)ws, PB, R * R * C, 1, 1.0, dw);
+  reduce_parts_kernel<float><<<ceil_div(R * R * C, 32), 256, 0, st>>>((const double*)ws, PB, R * R * C, 1, 1.0, dw);
   return launch_check("reduce_parts_kernel");
 }
 
@@ -582,7 +638,7 @@ extern "C" int creste_sample_dot(const float* x, const float* y, int B, long lon
   chan_reduce_kernel<1, DotOp><<<dim3(PB, ceil_div(C, 128), B), 256, 0, st>>>(DotOp{x, y}, C, HW, (double*)ws);
   int rc = launch_check("chan_reduce_kernel<sample_dot>");
   if (rc) return rc;
-  reduce_parts_kernel<float><<<ceil_div(B * C, 256), 256, 0, st>>>((const double*)ws, PB, C, B, (double)scale, out);
+  reduce_parts_kernel<float><<<ceil_div(B * C, 32), 256, 0, st>>>((const double*)ws, PB, C, B, (double)scale, out);
   return launch_check("reduce_parts_kernel");
 }
 
@@ -646,8 +702,25 @@ extern "C" int creste_wgrad_strided(const float* x, const float* g, int N, int H
   int rc = launch_check("wgrad_strided_c4_kernel");
   if (rc) return rc;
   const int n = R * S * C * K;
-  reduce_parts_kernel<float><<<ceil_div(n, 256), 256, 0, st>>>((const double*)ws, PB, n, 1, 1.0, dw);
+  reduce_parts_kernel<float><<<ceil_div(n, 32), 256, 0, st>>>((const double*)ws, PB, n, 1, 1.0, dw);
   return launch_check("reduce_parts_kernel");
+}
+
+extern "C" int creste_bn_fwd_finalize(const double* stats2, const float* weight, const float* bias, int C, double M,
+                                      double eps, float momentum, float* running_mean, float* running_var, float* ab,
+                                      double* mean_inv, void* stream) {
+  CRESTE_CHECK_ARG(stats2 && ab && mean_inv && C > 0 && M > 0 && (!running_mean == !running_var),
+                   "creste_bn_fwd_finalize: bad args");
+  bn_fwd_finalize_kernel<<<ceil_div(C, 256), 256, 0, (cudaStream_t)stream>>>(stats2, weight, bias, C, M, eps, momentum,
+                                                                             running_mean, running_var, ab, mean_inv);
+  return launch_check("bn_fwd_finalize_kernel");
+}
+
+extern "C" int creste_bn_bwd_finalize(const double* sums2, const float* ab, const double* mean_inv, int C, double M,
+                                      float* out4, void* stream) {
+  CRESTE_CHECK_ARG(sums2 && ab && mean_inv && out4 && C > 0 && M > 0, "creste_bn_bwd_finalize: bad args");
+  bn_bwd_finalize_kernel<<<ceil_div(C, 256), 256, 0, (cudaStream_t)stream>>>(sums2, ab, mean_inv, C, M, out4);
+  return launch_check("bn_bwd_finalize_kernel");
 }
 
 extern "C" int creste_wgrad_rows(const float* x, const float* g, int npix, int C, int K, float* dw, void* stream) {

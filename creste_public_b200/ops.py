@@ -737,3 +737,25 @@ def wgrad_rows(x, g):
     dw = torch.empty(Cc, K, device=x.device)
     check(lib().creste_wgrad_rows(ptr(x), ptr(g), npix, Cc, K, ptr(dw), stream()), "creste_wgrad_rows")
     return dw.t().contiguous().view(K, Cc, 1, 1)
+
+
+def bn_fwd_finalize(stats, weight, bias, M, eps, momentum, running_mean, running_var):
+    """moments [2,C] float64 -> (ab [2,C] float = scale / shift of the normalisation, mean_inv [2,C] float64);
+    updates running_mean / running_var in place when given (momentum form of F.batch_norm)."""
+    Cc = stats.shape[1]
+    ab = torch.empty(2, Cc, device=stats.device)
+    mi = torch.empty(2, Cc, dtype=torch.float64, device=stats.device)
+    check(lib().creste_bn_fwd_finalize(ptr(stats.contiguous(), torch.float64), ptr(weight), ptr(bias), Cc,
+                                       C.c_double(float(M)), C.c_double(float(eps)), C.c_float(float(momentum or 0.0)),
+                                       ptr(running_mean), ptr(running_var), ptr(ab), ptr(mi), stream()),
+          "creste_bn_fwd_finalize")
+    return ab, mi
+
+
+def bn_bwd_finalize(sums, ab, mean_inv, M):
+    """(sum gu, sum gu*x) -> [4,C] float = (dgamma, dbeta, q, r) with dx = gu*a + x*q + r."""
+    Cc = sums.shape[1]
+    out = torch.empty(4, Cc, device=sums.device)
+    check(lib().creste_bn_bwd_finalize(ptr(sums.contiguous(), torch.float64), ptr(ab), ptr(mean_inv), Cc,
+                                       C.c_double(float(M)), ptr(out), stream()), "creste_bn_bwd_finalize")
+    return out

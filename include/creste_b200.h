@@ -288,6 +288,15 @@ size_t creste_chan_reduce_workspace_bytes(long long npix, int C, int nacc, int Z
  * {sum x^2}; any C % 4 == 0 (the EfficientNet mid tensors reach 1152 channels). */
 int creste_chan_moments(const float* x, long long npix, int C, double* out2, void* ws, size_t ws_bytes,
                         void* stream);
+/* per-channel algebra of BatchNorm(training=True) in one launch each.  _fwd_: moments -> ab [2*C] float = (a, b) of
+ * y = x*a + b, mean_inv [2*C] double = (mean, 1/sqrt(var+eps)), and -- when running_mean/var are given -- the
+ * momentum update with the unbiased variance.  _bwd_: sums2 = (sum gu, sum gu*x) -> out4 [4*C] float =
+ * (dgamma, dbeta, q, r) with dx = gu*a + x*q + r. */
+int creste_bn_fwd_finalize(const double* stats2, const float* weight, const float* bias, int C, double M, double eps,
+                           float momentum, float* running_mean, float* running_var, float* ab, double* mean_inv,
+                           void* stream);
+int creste_bn_bwd_finalize(const double* sums2, const float* ab, const double* mean_inv, int C, double M, float* out4,
+                           void* stream);
 /* y = act(x*a[c] + b[c])  (BatchNorm affine + ReLU / swish in one pass) */
 int creste_chan_affine_act(const float* x, const float* a, const float* b, long long npix, int C, int act,
                            float* y, void* stream);

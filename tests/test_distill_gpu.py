@@ -41,6 +41,15 @@ def test_bn_kernels(cuda, C, act):
     _close(gu, gu0, 5e-6, "gu")
     _close(sums, sums0, 1e-5, "sums")
     _close(ops.chan_axpby(gy.to(cuda), x.to(cuda), p.to(cuda), q.to(cuda), r.to(cuda)), tb.chan_axpby(gy, x, p, q, r), 2e-6, "axpby")
+    # the [C]-sized BatchNorm algebra (one launch each way), running statistics included
+    M = x.numel() // C
+    w, bb = _t(g, C).abs() + 0.5, _t(g, C)
+    rm0, rv0 = _t(g, C), _t(g, C).abs() + 0.5
+    rm1, rv1 = rm0.clone().to(cuda), rv0.clone().to(cuda)
+    ab0, mi0 = tb.bn_fwd_finalize(tb.chan_moments(x), w, bb, M, 1e-3, 0.01, rm0, rv0)
+    ab1, mi1 = ops.bn_fwd_finalize(ops.chan_moments(x.to(cuda)), w.to(cuda), bb.to(cuda), M, 1e-3, 0.01, rm1, rv1)
+    _close(ab1, ab0, 1e-6, "ab"); _close(mi1, mi0, 1e-12, "mean_inv"); _close(rm1, rm0, 1e-6, "rm"); _close(rv1, rv0, 1e-6, "rv")
+    _close(ops.bn_bwd_finalize(sums, ab1, mi1, M), tb.bn_bwd_finalize(sums0, ab0, mi0, M), 1e-5, "bwd finalize")
 
 
 @pytest.mark.parametrize("R,stride,H,W", [(3, 1, 10, 14), (3, 2, 10, 14), (5, 1, 8, 12), (5, 2, 8, 12), (5, 2, 4, 6),

@@ -179,6 +179,26 @@ def chan_moments(x):
     return chan_stats(x)
 
 
+def bn_fwd_finalize(stats, weight, bias, M, eps, momentum, running_mean, running_var):
+    mean = stats[0] / M
+    var = (stats[1] / M - mean * mean).clamp_min(0.0)
+    if running_mean is not None:
+        running_mean.mul_(1 - momentum).add_(mean.float(), alpha=momentum)
+        running_var.mul_(1 - momentum).add_((var * (M / max(M - 1, 1))).float(), alpha=momentum)
+    inv = torch.rsqrt(var + eps)
+    a = inv * (weight.double() if weight is not None else 1.0)
+    b = (bias.double() if bias is not None else 0.0) - mean * a
+    return torch.stack([a.float(), b.float()]), torch.stack([mean, inv])
+
+
+def bn_bwd_finalize(sums, ab, mean_inv, M):
+    s1, s2, mean, inv, a = sums[0], sums[1], mean_inv[0], mean_inv[1], ab[0].double()
+    dgamma = inv * (s2 - mean * s1)
+    q = -a * inv * dgamma / M
+    r = -a * s1 / M - q * mean
+    return torch.stack([dgamma.float(), s1.float(), q.float(), r.float()])
+
+
 def chan_affine_act(x, a, b, act):
     return _act(x * a + b, act)
 
@@ -336,7 +356,7 @@ def depth_expectation(logits_nhwc, dmin=300.0, dmax=25600.0):
     return (p * vals).sum(-1) / 1000.0, logits_nhwc.argmax(-1)
 
 
-STAGE1_NAMES = ["chan_moments", "chan_affine_act", "bn_act_bwd", "chan_axpby", "dwconv_fwd", "dwconv_dgrad",
+STAGE1_NAMES = ["bn_fwd_finalize", "bn_bwd_finalize", "chan_moments", "chan_affine_act", "bn_act_bwd", "chan_axpby", "dwconv_fwd", "dwconv_dgrad",
                 "dwconv_wgrad", "sample_dot", "sample_affine", "act", "act_bwd", "add_scaled", "chan_slice",
                 "wgrad_strided", "wgrad_rows", "conv2d", "pack_conv_weight", "upsample_concat", "stage1_depth_losses",
                 "ce_depth_bwd", "masked_mse", "masked_mse_bwd", "depth_expectation"]

@@ -166,6 +166,28 @@ __global__ void __launch_bounds__(256) chan_stats_kernel(const float* __restrict
   }
 }
 
+// second stage of the two-stage reductions, 32 outputs per block: 8 row lanes per output add rows
+// lane, lane + 8, ... in order, then the lane sums are added in lane order (fixed order => reproducible).
+// A single thread walking all <= 592 rows was 15 % of the IRL step in the round-1 launch list.
+template <class Tin, class Tout>
+__global__ void __launch_bounds__(256) reduce_rows8_kernel(const Tin* __restrict__ part, int rows, int n, double scale,
+                                                           Tout* __restrict__ out) {
+  __shared__ double s_sum[8][32];
+  const int o = threadIdx.x & 31, rl = threadIdx.x >> 5;
+  const int i = blockIdx.x * 32 + o;
+  double t = 0.0;
+  if (i < n)
+    for (int j = rl; j < rows; j += 8) t += (double)part[(size_t)j * n + i];
+  s_sum[rl][o] = t;
+  __syncthreads();
+  if (rl == 0 && i < n) {
+    double tot = s_sum[0][o];
+#pragma unroll
+    for (int l = 1; l < 8; ++l) tot += s_sum[l][o];
+    out[i] = (Tout)(tot * scale);
+  }
+}
+
 __global__ void __launch_bounds__(256) reduce_rows_f64_to_f64_kernel(const double* __restrict__ part, int rows,
                                                                      int n, double* __restrict__ out) {
   const int i = blockIdx.x * blockDim.x + threadIdx.x;
@@ -629,8 +651,8 @@ extern "C" int creste_chan_dot(const float* x, const float* y, long long npix, i
   }
   int rc = launch_check("chan_dot_kernel");
   if (rc) return rc;
-  reduce_rows_f64_kernel<<<ceil_div(C, 256), 256, 0, st>>>((const double*)ws, blocks, C, out);
-  return launch_check("reduce_rows_f64_kernel");
+  reduce_rows8_kernel<double, float><<<ceil_div(C, 32), 256, 0, st>>>((const double*)ws, blocks, C, 1.0, out);
+  return launch_check("reduce_rows8_kernel");
 }
 
 /* out2 DEVICE double[2*C] = {sum_pix x[pix,c]}, {sum_pix x[pix,c]^2}: BatchNorm batch statistics in one
@@ -649,8 +671,8 @@ extern "C" int creste_chan_stats(const float* x, long long npix, int C, double* 
   }
   int rc = launch_check("chan_stats_kernel");
   if (rc) return rc;
-  reduce_rows_f64_to_f64_kernel<<<ceil_div(2 * C, 256), 256, 0, st>>>((const double*)ws, blocks, 2 * C, out2);
-  return launch_check("reduce_rows_f64_to_f64_kernel");
+  reduce_rows8_kernel<double, double><<<ceil_div(2 * C, 32), 256, 0, st>>>((const double*)ws, blocks, 2 * C, 1.0, out2);
+  return launch_check("reduce_rows8_kernel");
 }
 
 extern "C" int creste_maxpool2_bwd(const float* x, const float* g, int N, int H, int W, int C, float* dx,
@@ -739,7 +761,7 @@ extern "C" int creste_conv2d_wgrad(const creste_conv_desc* d, const float* x, co
   }
   if (rc) return rc;
   const int n = d->R * d->S * d->C * d->K;
-  reduce_rows_kernel<<<ceil_div(n, 256), 256, 0, st>>>((const float*)ws, chunks, n, 1.0f, dw_packed);
+  reduce_rows8_kernel<float, float><<<ceil_div(n, 32), 256, 0, st>>>((const float*)ws, chunks, n, 1.0, dw_packed);
   return launch_check("reduce_rows_kernel");
 }
 

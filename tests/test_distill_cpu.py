@@ -154,3 +154,72 @@ def test_train_mode_no_longer_refused_but_eval_swish_frozen_is():
     bn = torch.nn.BatchNorm2d(8).eval()
     with pytest.raises(NotImplementedError):
         ag.bn_act(torch.zeros(1, 2, 2, 8), bn, "swish")
+
+
+DDP_STEP = r'''
+import os, sys
+import numpy as np, torch, torch.distributed as dist
+root = sys.argv[1]
+sys.path.insert(0, root); sys.path.insert(0, os.path.join(root, "tests"))
+import torch_backend as tb
+from oracle import distill_oracle as do
+from test_distill_cpu import ours_step
+dist.init_process_group("gloo")
+rank, world = dist.get_rank(), dist.get_world_size()
+# global batch of 4 frames, rank r owns frames r::world (DistributedSampler semantics); BatchNorm statistics
+# and drop-connect masks stay per-rank, the product's FlatAdam all-reduces ONE flat gradient buffer.
+full = do.make_case(seed=7, B=4)
+mine = dict(full)
+for k in ("image", "depth_label", "fimg_label"):
+    mine[k] = full[k][rank::world].contiguous()
+mine["seed"] = full["seed"] + rank
+with tb.patched():
+    out = ours_step(mine)
+gs, ps = [None] * world, [None] * world
+dist.all_gather_object(gs, {k: out["grads"][k] for k in ("dino_head.model.6.weight", "depthcomp.depth_head.model.0.weight")})
+dist.all_gather_object(ps, out["params"])
+if rank == 0:
+    for k in ps[0]:
+        if "running" in k or "num_batches" in k:
+            continue            # per-rank BatchNorm statistics (no SyncBN in the reference)
+        assert np.array_equal(ps[0][k], ps[1][k]), k          # replicas stay in lock step
+    # each rank's local gradient equals the port's on its shard; the update used their mean
+    ports = []
+    for r in range(world):
+        c = dict(full)
+        for k in ("image", "depth_label", "fimg_label"):
+            c[k] = full[k][r::world].contiguous()
+        c["seed"] = full["seed"] + r
+        ports.append(do.port_step(c))
+    for k in gs[0]:
+        for r in range(world):
+            ref = ports[r]["grads"][k]       # robust (relative L2) criterion: see compare() on ReLU flips
+            assert np.sqrt(((gs[r][k] - ref) ** 2).sum()) <= 3e-2 * np.sqrt((ref ** 2).sum()), (k, r)
+        gmean = sum(p["grads"][k] for p in ports) / world
+        p0 = full["state_dict"][k].clone().requires_grad_(True)
+        opt = torch.optim.Adam([p0], lr=5e-4)
+        p0.grad = torch.from_numpy(gmean)
+        opt.step()
+        d_ref = (p0.detach() - full["state_dict"][k]).numpy()
+        d_ours = ps[0][k] - full["state_dict"][k].numpy()
+        agree = np.mean(np.sign(d_ref) == np.sign(d_ours))
+        assert agree > 0.97, (k, agree)
+    print("OK")
+dist.destroy_process_group()
+'''
+
+
+def test_stage1_data_parallel_gloo_world2(tmp_path):
+    """World-size-2 stage-1 step over gloo: per-rank shards / BatchNorm statistics / drop-connect, ONE flat
+    gradient all-reduce, replicas bit-identical after Adam and moving along the mean gradient."""
+    import os
+    import subprocess
+    import sys
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    script = tmp_path / "ddp_distill.py"
+    script.write_text(DDP_STEP)
+    cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node=2",
+           "--master-addr", "127.0.0.1", "--master-port", "29617", str(script), root]
+    res = subprocess.run(cmd, capture_output=True, text=True, timeout=900)
+    assert res.returncode == 0, res.stdout[-3000:] + res.stderr[-3000:]
+    assert "OK" in res.stdout

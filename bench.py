@@ -250,7 +250,7 @@ def run_stage1_steps(args, dev, rank, world, barrier, Bi=16, H=512, W=960, steps
     import synth_data as synth
     if args.no_stage1:
         return None
-    torch.manual_seed(1234 + rank)
+    torch.manual_seed(1234)          # identical initial replicas on every rank (DDP); the data is per-rank
     m = DistillationModel(configs.distill_cfg((H, W))).to(dev).train()
     batch = {k: v.to(dev) for k, v in synth.distill_batch(Bi, H, W, seed=rank).items()}
     for _ in range(2):

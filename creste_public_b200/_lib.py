@@ -39,6 +39,7 @@ EXPORTS = [
     "creste_masked_mse_bwd",
     "creste_conv2d_wgrad_tc_supported", "creste_conv2d_wgrad_tc_workspace_bytes", "creste_conv2d_wgrad_tc",
     "creste_wgrad_rows", "creste_bn_fwd_finalize", "creste_bn_bwd_finalize",
+    "creste_pack_weight_f16",
 ]
 
 

@@ -49,7 +49,7 @@ def _conv_raw(x, w, ph, pw):
     if mode == "fp32":
         packed = ops.pack_conv_weight(wp.detach().float())
     elif mode == "3xfp16":
-        packed = ops.pack_conv_weight_f16(wp.detach().float())
+        packed = ops.pack_conv_weight_f16_strided(wp.detach().float())      # one launch, strided read
     else:
         packed = ops.pack_conv_weight_tc(wp.detach().float(), split=(mode == "3xtf32"))
     y = ops.conv2d(xp, packed, Kp, R, S, 1, pad, precision=mode)

@@ -181,23 +181,26 @@ __global__ void __launch_bounds__(1024) se_gate_kernel(const float* __restrict__
                                                       const float* __restrict__ w_exp,
                                                       const float* __restrict__ b_exp,
                                                       float* __restrict__ gate) {
-  extern __shared__ float sm[];  // mean[C], sq[Csq]
+  extern __shared__ float sm[];  // mean[C], sq[Csq], lane sums [8][C]
   float* mean = sm;
   float* sq = sm + C;
+  float* lsum = sm + C + Csq;
   const int n = blockIdx.x;
-  for (int c = threadIdx.x; c < C; c += blockDim.x) {
-    // fixed summation order (row 0, 1, 2, ...) with 8 independent loads in flight
+  // fixed summation order, independent of the batch size: 8 row lanes per channel add rows lane, lane + 8,
+  // ... in order, then the lane sums are added in lane order (a single thread per channel walking all the
+  // partial rows made this kernel 7 % of the forward in the round-1 launch list)
+  for (int idx = threadIdx.x; idx < 8 * C; idx += blockDim.x) {
+    const int l = idx / C, c = idx - l * C;
     const float* src = chan_part + (size_t)n * nparts * C + c;
     float tot = 0.0f;
-    int j = 0;
-    for (; j + 8 <= nparts; j += 8) {
-      float v[8];
+    for (int j = l; j < nparts; j += 8) tot += __ldg(src + (size_t)j * C);
+    lsum[idx] = tot;
+  }
+  __syncthreads();
+  for (int c = threadIdx.x; c < C; c += blockDim.x) {
+    float tot = lsum[c];
 #pragma unroll
-      for (int u = 0; u < 8; ++u) v[u] = __ldg(src + (size_t)(j + u) * C);
-#pragma unroll
-      for (int u = 0; u < 8; ++u) tot += v[u];
-    }
-    for (; j < nparts; ++j) tot += __ldg(src + (size_t)j * C);
+    for (int l = 1; l < 8; ++l) tot += lsum[l * C + c];
     mean[c] = tot * inv_hw;
   }
   __syncthreads();
@@ -290,7 +293,7 @@ extern "C" int creste_se_gate(const float* chan_part, int nparts, float inv_hw, 
                               const float* w_red, const float* b_red, const float* w_exp,
                               const float* b_exp, float* gate, void* stream) {
   CRESTE_CHECK_ARG(chan_part && w_red && b_red && w_exp && b_exp && gate && nparts > 0, "creste_se_gate: null pointer");
-  const size_t smem = (size_t)(C + Csq) * sizeof(float);
+  const size_t smem = (size_t)(9 * C + Csq) * sizeof(float);
   se_gate_kernel<<<N, 1024, smem, (cudaStream_t)stream>>>(chan_part, nparts, inv_hw, C, Csq, w_red, b_red, w_exp,
                                                         b_exp, gate);
   return launch_check("se_gate_kernel");

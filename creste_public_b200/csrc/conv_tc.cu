@@ -1156,6 +1156,70 @@ int wgrad_tc_launch(const creste_conv_desc* d, const float* x, const float* g, f
   return launch_check("wg_reduce_kernel");
 }
 
+
+// ---- 3xFP16 weight operand in ONE launch (training: the weights change every step, so the ~20 small
+// torch kernels of the cached inference pack would be paid per conv per step).  Logical weights
+// w[k][c][r][s] are read through element strides (the data-gradient conv passes the transposed view of the
+// flipped filter); block = one output channel: amax -> power-of-two scale (amax * s in [2^14, 2^15)) ->
+// hi = fp16(w*s), lo = fp16((w*s - hi) * 2^11) in the [npad][R*S][cpad] layout, inv[k] = 1/s.
+__global__ void __launch_bounds__(256) pack_weight_f16_kernel(const float* __restrict__ w, long long sK, long long sC,
+                                                              long long sR, long long sS, int K, int C, int R, int S,
+                                                              int cpad, __half* __restrict__ hi, __half* __restrict__ lo,
+                                                              float* __restrict__ inv) {
+  __shared__ float s_red[8];
+  __shared__ float s_scale;
+  const int k = blockIdx.x;
+  const int RS = R * S;
+  const int n = RS * C;
+  float m = 0.f;
+  if (k < K)
+    for (int i = threadIdx.x; i < n; i += blockDim.x) {
+      const int c = i % C, t = i / C;
+      const int r = t / S, s = t - r * S;
+      m = fmaxf(m, fabsf(__ldg(w + k * sK + c * sC + r * sR + s * sS)));
+    }
+  m = warp_max(m);
+  if ((threadIdx.x & 31) == 0) s_red[threadIdx.x >> 5] = m;
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    float a = s_red[0];
+    for (int i = 1; i < 8; ++i) a = fmaxf(a, s_red[i]);
+    const unsigned b = __float_as_uint(a);
+    int e = (int)((b >> 23) & 0xffu) - 127;
+    if (b == 0u || !isfinite(a)) e = 0;
+    const int kk = max(-100, min(100, 14 - e));
+    s_scale = __uint_as_float((unsigned)(127 + kk) << 23);
+    inv[k] = __uint_as_float((unsigned)(127 - kk) << 23);
+  }
+  __syncthreads();
+  const float sc = s_scale;
+  const size_t row = (size_t)k * RS * cpad;
+  for (int i = threadIdx.x; i < RS * cpad; i += blockDim.x) {
+    const int c = i % cpad, t = i / cpad;
+    float v = 0.f;
+    if (k < K && c < C) {
+      const int r = t / S, s = t - r * S;
+      v = __ldg(w + k * sK + c * sC + r * sR + s * sS) * sc;
+    }
+    const __half h = __float2half_rn(v);
+    hi[row + i] = h;
+    lo[row + i] = __float2half_rn((v - __half2float(h)) * 2048.0f);
+  }
+}
+
+int pack_weight_f16_launch(const float* w, long long sK, long long sC, long long sR, long long sS, int K, int C, int R,
+                           int S, float* out, cudaStream_t st) {
+  int block_n, npad, cpad32;
+  conv_tc_layout(K, C, R, S, &block_n, &npad, &cpad32);
+  const int cpad = (C + 63) / 64 * 64;
+  const size_t wel = (size_t)npad * R * S * cpad;
+  __half* hi = (__half*)out;
+  __half* lo = hi + wel;
+  float* inv = (float*)((char*)out + wel * 4);
+  pack_weight_f16_kernel<<<npad, 256, 0, st>>>(w, sK, sC, sR, sS, K, C, R, S, cpad, hi, lo, inv);
+  return launch_check("pack_weight_f16_kernel");
+}
+
 }  // namespace creste
 
 /* development aid: per-CTA globaltimer stamps of the next tensor-core conv launches (8 u64 per CTA) */
@@ -1184,4 +1248,13 @@ extern "C" int creste_conv2d_wgrad_tc(const creste_conv_desc* d, const float* x,
                                       size_t ws_bytes, void* stream) {
   if (!d || !x || !g || !dw) { creste::set_error("creste_conv2d_wgrad_tc: bad args"); return CRESTE_ERR_ARG; }
   return creste::wgrad_tc_launch(d, x, g, dw, ws, ws_bytes, (cudaStream_t)stream);
+}
+
+/* 3xFP16 weight operand of creste_conv2d (precision 4) in one launch: logical w[k][c][r][s] read through element
+ * strides; out = npad*R*S*cpad64 fp16 hi, the same count of lo, then npad fp32 inverse scales
+ * (creste_conv2d_tc_layout gives npad; cpad64 = C rounded up to 64). */
+extern "C" int creste_pack_weight_f16(const float* w, long long sK, long long sC, long long sR, long long sS, int K,
+                                      int C, int R, int S, float* out, void* stream) {
+  if (!w || !out || K <= 0 || C <= 0 || R <= 0 || S <= 0) { creste::set_error("creste_pack_weight_f16: bad args"); return CRESTE_ERR_ARG; }
+  return creste::pack_weight_f16_launch(w, sK, sC, sR, sS, K, C, R, S, out, (cudaStream_t)stream);
 }

@@ -759,3 +759,17 @@ def bn_bwd_finalize(sums, ab, mean_inv, M):
     check(lib().creste_bn_bwd_finalize(ptr(sums.contiguous(), torch.float64), ptr(ab), ptr(mean_inv), Cc,
                                        C.c_double(float(M)), ptr(out), stream()), "creste_bn_bwd_finalize")
     return out
+
+
+def pack_conv_weight_f16_strided(w):
+    """pack_conv_weight_f16 in one kernel launch, reading w [K,C,R,S] through its strides (no copy for the
+    transposed view the data-gradient conv passes).  Same layout; the scale is taken from the exponent bits."""
+    assert w.dtype == torch.float32 and w.is_cuda
+    K, Cc, R, S = w.shape
+    _, npad, _ = tc_layout(K, Cc, R, S)
+    cpad = (Cc + 63) // 64 * 64
+    out = torch.empty(npad * R * S * cpad + npad, device=w.device)
+    sK, sC, sR, sS = w.stride()
+    check(lib().creste_pack_weight_f16(C.c_void_p(w.data_ptr()), C.c_longlong(sK), C.c_longlong(sC), C.c_longlong(sR),
+                                       C.c_longlong(sS), K, Cc, R, S, ptr(out), stream()), "creste_pack_weight_f16")
+    return out

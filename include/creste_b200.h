@@ -357,6 +357,13 @@ size_t creste_conv2d_wgrad_tc_workspace_bytes(const creste_conv_desc* d);
 int creste_conv2d_wgrad_tc(const creste_conv_desc* d, const float* x, const float* g, float* dw, void* ws,
                            size_t ws_bytes, void* stream);
 
+/* The 3xFP16 weight operand of creste_conv2d (precision 4) packed in ONE launch (training re-packs every step):
+ * logical w[k][c][r][s] is read through element strides (sK, sC, sR, sS) -- the data-gradient conv passes the
+ * transposed view of the flipped filter; out (floats) = npad*R*S*cpad64 fp16 hi halves, as many lo halves, then
+ * npad fp32 inverse scales (npad from creste_conv2d_tc_layout, cpad64 = C rounded up to 64). */
+int creste_pack_weight_f16(const float* w, long long sK, long long sC, long long sR, long long sS, int K, int C,
+                           int R, int S, float* out, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -100,6 +100,18 @@ def test_stem_wgrad(cuda):
     _close(ops.wgrad_strided(x.to(cuda), gy.to(cuda), 3, 3, 2, pad), tb.wgrad_strided(x, gy, 3, 3, 2, pad), 1e-5, "stem wgrad")
 
 
+@pytest.mark.parametrize("K,C,R", [(496, 496, 3), (40, 240, 1), (64, 40, 5), (8, 48, 1)])
+def test_pack_weight_f16_kernel(cuda, K, C, R):
+    """The one-launch 3xFP16 weight pack against the torch pack the inference path caches: same bytes for the
+    contiguous filter, and -- through strides -- for the transposed view of the flipped filter (dgrad)."""
+    from creste_public_b200 import ops
+    g = np.random.default_rng(K + C)
+    w = (_t(g, K, C, R, R) * torch.from_numpy(np.exp(g.uniform(-6, 6, (K, 1, 1, 1))).astype(np.float32))).to(cuda)
+    assert torch.equal(ops.pack_conv_weight_f16_strided(w), ops.pack_conv_weight_f16(w))
+    wt = w.flip(2, 3).transpose(0, 1)
+    assert torch.equal(ops.pack_conv_weight_f16_strided(wt), ops.pack_conv_weight_f16(wt.contiguous()))
+
+
 def test_wgrad_rows(cuda):
     from creste_public_b200 import ops
     g = np.random.default_rng(14)

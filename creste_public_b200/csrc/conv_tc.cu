@@ -1090,12 +1090,19 @@ static WgPlan wg_plan(const creste_conv_desc* d) {
   w.tiles_x = ceil_div(d->Q, w.wbox);
   w.tiles_y = ceil_div(d->P, w.hbox);
   w.ntiles = d->N * w.tiles_y * w.tiles_x;
+  // pixel splits: minimise (waves over the 148 SMs) x (pixel tiles per CTA + a fixed per-CTA cost of ~6 tiles for
+  // the prologue / epilogue), so that the grid does not spill a nearly empty last wave (25 taps x 12 splits = 300
+  // CTAs ran as three waves on the reward FCN's 5x5 layers)
   const int base = w.m_tiles * w.n_tiles * d->R * d->S;
-  int splits = ceil_div(2 * 148, base);
   const int max_splits = w.ntiles / 8 > 1 ? w.ntiles / 8 : 1;
-  if (splits > max_splits) splits = max_splits;
-  if (splits < 1) splits = 1;
-  w.splits = splits;
+  int best_s = 1;
+  long long best_cost = -1;
+  for (int sp = 1; sp <= max_splits && (long long)base * sp <= 4 * 148 + base; ++sp) {
+    const long long waves = ceil_div(base * sp, 148);
+    const long long cost = waves * (ceil_div(w.ntiles, sp) + 6);
+    if (best_cost < 0 || cost < best_cost) { best_cost = cost; best_s = sp; }
+  }
+  w.splits = best_s;
   w.nx = (size_t)d->N * d->H * d->W * d->C;
   w.ng = (size_t)d->N * d->P * d->Q * d->K;
   return w;

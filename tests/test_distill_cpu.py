@@ -223,3 +223,53 @@ def test_stage1_data_parallel_gloo_world2(tmp_path):
     res = subprocess.run(cmd, capture_output=True, text=True, timeout=900)
     assert res.returncode == 0, res.stdout[-3000:] + res.stderr[-3000:]
     assert "OK" in res.stdout
+
+
+def test_drop_connect_scale_matches_efficientnet():
+    """engine.drop_connect_scale == efficientnet_pytorch.utils.drop_connect's per-sample multiplier."""
+    from creste_public_b200 import engine
+    from oracle.ref_shims import efficientnet_shim as effs
+    x = torch.ones(6, 3, 2, 2)
+    torch.manual_seed(11)
+    ref = effs.drop_connect(x, 0.2, True)[:, 0, 0, 0]
+    torch.manual_seed(11)
+    engine.drop_connect_rand = lambda B, d: torch.rand([B, 1, 1, 1]).reshape(B)
+    try:
+        ours = engine.drop_connect_scale(6, 0.2, torch.device("cpu"))
+    finally:
+        engine.drop_connect_rand = None
+    torch.testing.assert_close(ours, ref)
+    assert set(ours.tolist()) <= {0.0, 1.25}
+
+
+def test_flat_adam_views_are_128_byte_aligned():
+    """Kernels read parameters (biases, BatchNorm vectors) with 16-byte vector loads straight from the flat
+    buffer views: every view must start on a 128-byte boundary whatever the sizes before it."""
+    from creste_public_b200.creste.train_traversability import FlatAdam
+    ps = [torch.nn.Parameter(torch.randn(n)) for n in (6, 10, 1152, 3, 48)]
+    vals = [p.detach().clone() for p in ps]
+    with tb.patched():
+        opt = FlatAdam(ps)
+    base = opt.flat_p.data_ptr()
+    for p, v, g in zip(ps, vals, opt.views):
+        assert (p.data_ptr() - base) % 128 == 0 and (g.data_ptr() - opt.flat_g.data_ptr()) % 128 == 0
+        assert torch.equal(p.detach(), v)
+
+
+@pytest.mark.parametrize("C,K,R", [(112, 40, 1), (144, 200, 3), (64, 70, 1), (30, 130, 3), (6, 96, 1)])
+def test_wgrad_channel_tiling(C, K, R):
+    """autograd._wgrad_raw cuts wide layers into 64-channel slices for the CUDA-core kernel: the assembled
+    gradient equals the one-shot torch weight gradient (kernel stand-ins; the tiling logic is what runs)."""
+    from creste_public_b200 import autograd as ag
+    from creste_public_b200 import ops
+    saved = (ops.conv2d_wgrad, ops.chan_slice, ag.WGRAD_TC)
+    ops.conv2d_wgrad = lambda x, g, R_, S_, pad: tb.wgrad_raw(x, g, R_, S_, pad[0], pad[2])
+    ops.chan_slice = tb.chan_slice
+    ag.WGRAD_TC = False
+    try:
+        g = torch.Generator().manual_seed(C + K)
+        x, gy = torch.randn(2, 9, 8, C, generator=g), torch.randn(2, 9, 8, K, generator=g)   # > 64 rows: not the SE path
+        got = ag._wgrad_raw(x, gy, R, R, R // 2, R // 2)
+        torch.testing.assert_close(got, tb.wgrad_raw(x, gy, R, R, R // 2, R // 2), rtol=1e-5, atol=1e-5)
+    finally:
+        ops.conv2d_wgrad, ops.chan_slice, ag.WGRAD_TC = saved

@@ -11,6 +11,8 @@
 // Tile 128 x BN x 16, 256 threads, 8 x TN register micro-tiles, double-buffered shared memory
 // with register prefetch (one __syncthreads per k-chunk).  Epilogue fuses folded BatchNorm /
 // bias (scale, shift), residual add, ReLU / swish / sigmoid, and writes NHWC or NCHW.
+#include <stdlib.h>
+
 #include "common.cuh"
 
 namespace creste {
@@ -20,6 +22,7 @@ struct ConvP {
   const float* residual; float* out;
   int N, H, W, C, K, R, S, stride, pad_t, pad_l, P, Q, act, out_nchw;
   int M, Kdim, ldw;
+  int vec;      // NHWC output, K % 4 == 0 and 16-byte aligned pointers: 128-bit epilogue loads / stores
 };
 
 __device__ __forceinline__ float apply_act(float v, int act) {
@@ -185,6 +188,53 @@ __global__ void __launch_bounds__(256, 2) conv_simt_kernel(ConvP p) {
   }
 
   // ---- epilogue
+  // vector path: a thread's output columns come in groups of 4 (2 for TN == 2) contiguous channels, so the
+  // folded BN factors, the residual and the store are one 128-bit access per group -- 16 lanes write 256
+  // contiguous bytes of a pixel row.  (The scalar form below wrote 4 bytes per lane at a 16-byte stride: a
+  // quarter of every 32-byte sector, and 4x the store instructions; it was 23 % of the forward.)
+  if (p.vec) {
+    constexpr int G = TN >= 4 ? 4 : 2;            // channels per group
+#pragma unroll
+    for (int jg = 0; jg < TN / G; ++jg) {
+      const int n = n0 + ((TN == 8) ? (jg ? BN / 2 + tx * 4 : tx * 4) : tx * TN);
+      if (n >= p.K) continue;
+      float sc[G], sh[G];
+      if (G == 4) {
+        const float4 s4 = p.scale ? __ldg(reinterpret_cast<const float4*>(p.scale + n)) : make_float4(1.f, 1.f, 1.f, 1.f);
+        const float4 h4 = p.shift ? __ldg(reinterpret_cast<const float4*>(p.shift + n)) : make_float4(0.f, 0.f, 0.f, 0.f);
+        sc[0] = s4.x; sc[1] = s4.y; sc[2 % G] = s4.z; sc[3 % G] = s4.w;
+        sh[0] = h4.x; sh[1] = h4.y; sh[2 % G] = h4.z; sh[3 % G] = h4.w;
+      } else {
+        const float2 s2 = p.scale ? __ldg(reinterpret_cast<const float2*>(p.scale + n)) : make_float2(1.f, 1.f);
+        const float2 h2 = p.shift ? __ldg(reinterpret_cast<const float2*>(p.shift + n)) : make_float2(0.f, 0.f);
+        sc[0] = s2.x; sc[1] = s2.y; sh[0] = h2.x; sh[1] = h2.y;
+      }
+#pragma unroll
+      for (int i = 0; i < TM; ++i) {
+        const int m = m0 + ty * TM + i;
+        if (m >= p.M) continue;
+        float v[G];
+#pragma unroll
+        for (int u = 0; u < G; ++u) v[u] = fmaf(acc[i][jg * G + u], sc[u], sh[u]);
+        float* dst = p.out + (size_t)m * p.K + n;
+        if (G == 4) {
+          if (p.residual) {
+            const float4 r4 = __ldg(reinterpret_cast<const float4*>(p.residual + (size_t)m * p.K + n));
+            v[0] += r4.x; v[1] += r4.y; v[2 % G] += r4.z; v[3 % G] += r4.w;
+          }
+          *reinterpret_cast<float4*>(dst) = make_float4(apply_act(v[0], p.act), apply_act(v[1], p.act),
+                                                        apply_act(v[2 % G], p.act), apply_act(v[3 % G], p.act));
+        } else {
+          if (p.residual) {
+            const float2 r2 = __ldg(reinterpret_cast<const float2*>(p.residual + (size_t)m * p.K + n));
+            v[0] += r2.x; v[1] += r2.y;
+          }
+          *reinterpret_cast<float2*>(dst) = make_float2(apply_act(v[0], p.act), apply_act(v[1], p.act));
+        }
+      }
+    }
+    return;
+  }
   const int PQ = p.P * p.Q;
 #pragma unroll
   for (int j = 0; j < TN; ++j) {
@@ -221,6 +271,9 @@ int conv_simt_launch(const creste_conv_desc* d, const float* x, const float* w, 
   p.M = d->N * d->P * d->Q;
   p.Kdim = d->R * d->S * d->C;
   p.ldw = ldw;
+  auto al16 = [](const void* q) { return q == nullptr || ((uintptr_t)q & 15u) == 0; };
+  p.vec = (!d->out_nchw && d->K % 4 == 0 && al16(out) && al16(residual) && al16(scale) && al16(shift)) ? 1 : 0;
+  if (getenv("CRESTE_SIMT_SCALAR_EPILOGUE")) p.vec = 0;
   const int gm = ceil_div(p.M, BM);
   if (d->K > 64) {
     dim3 grid(gm, ceil_div(d->K, 128));

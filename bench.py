@@ -484,6 +484,33 @@ def run_ours(args):
         irl["cpu_baseline"] = irl_cpu
     # ---- third leg: stage-1 backbone training frames/s (configs[2]: batch 16 per GPU)
     stage1 = run_stage1_steps(args, dev, rank, world, barrier)
+    if rank == 0 and stage1 is not None and args.precision != "fp32":
+        # the stage-1 step's dominant backward kernel alone: tcgen05 weight gradient of the up3 conv (B = 8 frames),
+        # timed with CUDA events around the C-ABI call (operand split + wgrad_tc_kernel + split-K reduction)
+        from creste_public_b200 import ops as _ops
+        Bw = 8
+        xw = torch.randn(Bw, 128, 240, 496, device=dev)
+        gw = torch.randn(Bw, 128, 240, 496, device=dev) * 1e-3
+        for _ in range(2):
+            _ops.conv2d_wgrad_tc(xw, gw, 3, 3, (1, 1, 1, 1))
+        evw = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(5)]
+        for a, b_ in evw:
+            a.record()
+            _ops.conv2d_wgrad_tc(xw, gw, 3, 3, (1, 1, 1, 1))
+            b_.record()
+        torch.cuda.synchronize()
+        wms = statistics.median(a.elapsed_time(b_) for a, b_ in evw)
+        wfl = 2.0 * Bw * 128 * 240 * 496 * (9 * 496)
+        wach = wfl / (wms / 1e3) / 1e12
+        stage1["wgrad_roofline"] = {
+            "kernel": "wgrad_tc_kernel (creste_conv2d_wgrad_tc): up3 conv 496->496 3x3 @128x240, B=8, 3xfp16, incl. the "
+                      "operand split pre-pass and the split-K reduction",
+            "bound": "tensor", "achieved": wach, "peak": peaks["bf16_sustained"], "unit": "TFLOP/s",
+            "frac": wach / peaks["bf16_sustained"], "kernel_ms": wms,
+            # dram bytes of one launch from profiles/r1c_wgrad_tc_full.md (B = 4 capture), per launch
+            "traffic": None, "algorithmic_bytes": 2 * Bw * 128 * 240 * 496 * (2 * 2),
+            "note": "3 MMAs per k-step (3xFP16 split): a split mode can reach at most 1/3 of the fp16 peak"}
+        del xw, gw
     if rank == 0 and stage1 is not None and not args.no_cpu and world == 1:
         try:
             fps1, ms1, cores1 = cpu_stage1_baseline()

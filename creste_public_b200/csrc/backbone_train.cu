@@ -680,7 +680,7 @@ extern "C" int creste_chan_slice(const float* x, long long npix, int C, int c0, 
 static int wgrad_strided_pb(long long npix) {
   long long b = npix / 256;
   if (b < 1) b = 1;
-  return (int)(b > 592 ? 592 : b);
+  return (int)(b > 1776 ? 1776 : b);        // 12 CTAs per SM: the per-thread pixel loop is latency-bound
 }
 
 extern "C" size_t creste_wgrad_strided_workspace_bytes(int N, int P, int Q, int C, int K, int R, int S) {

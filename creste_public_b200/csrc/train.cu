@@ -268,14 +268,18 @@ __device__ __forceinline__ float up_weight(int o, float ratio, int isz, int i) {
   return w;
 }
 
+// V = 4: one thread = one input pixel x 4 channels (the tap weights depend on the pixel only, so they are
+// computed once per 4 channels and every access is 128 bits); per-channel arithmetic order is that of V = 1.
+template <int V>
 __global__ void __launch_bounds__(256) upsample_adjoint_kernel(const float* __restrict__ g, int N, int Hi,
                                                                int Wi, int C, int Ho, int Wo, float rh,
                                                                float rw, float* __restrict__ dx) {
-  const long long total = (long long)N * Hi * Wi * C;
+  const int CV = C / V;
+  const long long total = (long long)N * Hi * Wi * CV;
   for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total;
        i += (long long)gridDim.x * blockDim.x) {
-    const int c = (int)(i % C);
-    const long long pix = i / C;
+    const int c = (int)(i % CV) * V;
+    const long long pix = i / CV;
     const int ix = (int)(pix % Wi);
     const int iy = (int)((pix / Wi) % Hi);
     const int n = (int)(pix / ((long long)Wi * Hi));
@@ -287,18 +291,32 @@ __global__ void __launch_bounds__(256) upsample_adjoint_kernel(const float* __re
     oy0 = max(oy0, 0); ox0 = max(ox0, 0);
     oy1 = (iy == Hi - 1) ? Ho - 1 : min(oy1, Ho - 1);
     ox1 = (ix == Wi - 1) ? Wo - 1 : min(ox1, Wo - 1);
-    float acc = 0.f;
+    float acc[V];
+#pragma unroll
+    for (int u = 0; u < V; ++u) acc[u] = 0.f;
     for (int oy = oy0; oy <= oy1; ++oy) {
       const float wy = up_weight(oy, rh, Hi, iy);
       if (wy == 0.f) continue;
-      float row = 0.f;
+      float row[V];
+#pragma unroll
+      for (int u = 0; u < V; ++u) row[u] = 0.f;
       for (int ox = ox0; ox <= ox1; ++ox) {
         const float wx = up_weight(ox, rw, Wi, ix);
-        if (wx != 0.f) row = fmaf(wx, __ldg(g + (((size_t)n * Ho + oy) * Wo + ox) * C + c), row);
+        if (wx == 0.f) continue;
+        const float* src = g + (((size_t)n * Ho + oy) * Wo + ox) * C + c;
+        if (V == 4) {
+          const float4 gv = __ldg(reinterpret_cast<const float4*>(src));
+          row[0] = fmaf(wx, gv.x, row[0]); row[1 % V] = fmaf(wx, gv.y, row[1 % V]);
+          row[2 % V] = fmaf(wx, gv.z, row[2 % V]); row[3 % V] = fmaf(wx, gv.w, row[3 % V]);
+        } else {
+          row[0] = fmaf(wx, __ldg(src), row[0]);
+        }
       }
-      acc = fmaf(wy, row, acc);
+#pragma unroll
+      for (int u = 0; u < V; ++u) acc[u] = fmaf(wy, row[u], acc[u]);
     }
-    dx[i] = acc;
+    if (V == 4) reinterpret_cast<float4*>(dx)[i] = make_float4(acc[0], acc[1 % V], acc[2 % V], acc[3 % V]);
+    else dx[i] = acc[0];
   }
 }
 
@@ -699,8 +717,12 @@ extern "C" int creste_upsample_adjoint(const float* g, int N, int Hi, int Wi, in
   CRESTE_CHECK_ARG(g && dx && N > 0 && Hi > 0 && Wi > 0 && C > 0 && Ho > 0 && Wo > 0 && rh > 0 && rw > 0,
                    "creste_upsample_adjoint: bad args");
   const long long total = (long long)N * Hi * Wi * C;
-  upsample_adjoint_kernel<<<grid_cap(total, 256, 148 * 16), 256, 0, (cudaStream_t)stream>>>(g, N, Hi, Wi, C, Ho,
-                                                                                          Wo, rh, rw, dx);
+  if (C % 4 == 0 && (((uintptr_t)g | (uintptr_t)dx) & 15u) == 0)
+    upsample_adjoint_kernel<4><<<grid_cap(total / 4, 256, 148 * 16), 256, 0, (cudaStream_t)stream>>>(g, N, Hi, Wi, C, Ho,
+                                                                                                   Wo, rh, rw, dx);
+  else
+    upsample_adjoint_kernel<1><<<grid_cap(total, 256, 148 * 16), 256, 0, (cudaStream_t)stream>>>(g, N, Hi, Wi, C, Ho,
+                                                                                               Wo, rh, rw, dx);
   return launch_check("upsample_adjoint_kernel");
 }
 

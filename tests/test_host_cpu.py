@@ -31,6 +31,26 @@ def test_no_cpu_fallback():
         ops.vi_solve(torch.rand(1, 1, 8, 8))
     with pytest.raises(RuntimeError, match="CUDA"):
         ops.nchw_to_nhwc(torch.rand(1, 4, 8, 8))
+    # the stage-1 training primitives and the tcgen05 weight gradient: same rule
+    x = torch.rand(2, 8, 8, 64)
+    for call in (lambda: ops.chan_moments(x), lambda: ops.chan_affine_act(x, torch.ones(64), torch.zeros(64), "swish"),
+                 lambda: ops.dwconv_fwd(x, torch.rand(9, 64), 3, 1, (1, 1, 1, 1)),
+                 lambda: ops.conv2d_wgrad_tc(torch.rand(2, 16, 16, 64), torch.rand(2, 16, 16, 64), 3, 3, (1, 1, 1, 1)),
+                 lambda: ops.pack_conv_weight_f16_strided(torch.rand(64, 64, 3, 3)) if False else ops.wgrad_rows(x[:, :1, :1], x[:, :1, :1]),
+                 lambda: ops.sample_dot(x), lambda: ops.masked_mse_bwd(x, x, torch.ones(1))):
+        with pytest.raises(RuntimeError, match="CUDA"):
+            call()
+
+
+def test_training_mode_modules_without_gpu_fail_loudly():
+    """DistillationBackbone.train() no longer refuses (stage 1 is implemented) -- on a CPU box it must reach the
+    kernels and fail there, not fall back to eager PyTorch."""
+    from creste_public_b200 import configs
+    from creste_public_b200.creste.train_pefree import DistillationModel
+    m = DistillationModel(configs.distill_cfg((64, 96))).train()
+    with pytest.raises(RuntimeError, match="CUDA"):
+        m.training_step({"image": torch.rand(1, 1, 4, 64, 96), "depth_label": torch.rand(1, 1, 16, 24) * 9000,
+                         "fimg_label": torch.randn(1, 1, 128, 16, 24)})
 
 
 def test_product_never_imports_the_oracle():

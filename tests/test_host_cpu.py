@@ -151,3 +151,24 @@ def test_projection_transforms_match_reference_math():
         ref = rh.ref_modules()["projection"]
         np.testing.assert_allclose(a, ref.get_pixel2pts_transform(calib), atol=1e-12)
         np.testing.assert_allclose(b, ref.get_pts2pixel_transform(calib), atol=1e-12)
+
+
+def test_wgrad_tc_host_planning_without_gpu():
+    """The shape gate and the workspace size of the tcgen05 weight gradient are host-only functions of the C ABI:
+    callable on the CPU box (no launch).  Workspace = fp16 hi+lo copies of x and g + scalars + split-K partials."""
+    import ctypes as C
+    from creste_public_b200 import _lib
+    L = _lib.lib()
+
+    def desc(N, H, W, Cc, K, R, stride=1):
+        return _lib.ConvDesc(N, H, W, Cc, K, R, R, stride, R // 2, R // 2, H, W, 0, 0, 4)
+    ok = lambda *a, **k: bool(L.creste_conv2d_wgrad_tc_supported(C.byref(desc(*a, **k))))
+    assert ok(4, 128, 240, 496, 496, 3) and ok(8, 256, 256, 40, 64, 5) and ok(2, 16, 24, 1152, 192, 1)
+    assert not ok(4, 1, 1, 1152, 48, 1)            # squeeze-excite vectors: a handful of rows
+    assert not ok(4, 128, 240, 4, 32, 3)           # C = 4 stem
+    assert not ok(4, 128, 240, 64, 64, 3, stride=2)
+    assert not ok(4, 128, 240, 60, 64, 3)          # fp16 rows must be 16-byte multiples (TMA)
+    d = desc(4, 128, 240, 496, 496, 3)
+    n = L.creste_conv2d_wgrad_tc_workspace_bytes(C.byref(d))
+    operands = 2 * (4 * 128 * 240 * 496 * 2) * 2
+    assert operands < n < operands + 64 * 9 * 496 * 496 * 4 + 4096

@@ -61,7 +61,7 @@ def compare(ours, ref, truth, tol_out=2e-4, tol_grad=5e-4, strict=True):
       strict   |ours - truth|_max <= 3 * |ref - truth|_max + tol_grad * |truth|_max + 1e-6  per tensor:
                as close to the exact gradient as the reference is, up to a factor 3.  Asserted for every
                tensor when `strict` (an implementation that flips the same elements as the reference
-               does), else for at least half of the tensors.
+               does); otherwise the median relative L2 error over the tensors must stay <= 5e-3.
       robust   per-tensor relative L2 error against float64 <= max(3 x the reference's, 3e-2): no single
                ReLU flip reaches it, any wrong backward formula exceeds it by an order of magnitude."""
     for k in ("loss", "CrossEntropyDepth/depth/cls_loss", "SmoothL1Depth/depth/reg_loss", "MSELoss/loss"):
@@ -70,7 +70,7 @@ def compare(ours, ref, truth, tol_out=2e-4, tol_grad=5e-4, strict=True):
     for k in ("logits", "dino"):
         assert np.abs(ours[k] - ref[k]).max() <= tol_out * np.abs(ref[k]).max(), k
     assert len(ref["grads"]) >= 240
-    bad, bad_l2 = [], []
+    bad, bad_l2, rels = [], [], []
     for k, g0 in ref["grads"].items():
         t = truth[k]
         d = ours["grads"][k] - t
@@ -81,13 +81,16 @@ def compare(ours, ref, truth, tol_out=2e-4, tol_grad=5e-4, strict=True):
         tn = np.sqrt((t ** 2).sum())
         if tn > 1e-5:                                # exact-zero gradients (biases in front of a BatchNorm) aside
             rel, rel_ref = np.sqrt((d ** 2).sum()) / tn, np.sqrt(((g0 - t) ** 2).sum()) / tn
+            rels.append(rel)
             if not rel <= max(3 * rel_ref, 3e-2):
                 bad_l2.append((float(rel), k, float(rel_ref)))
     assert not bad_l2, sorted(bad_l2, reverse=True)[:10]
     if strict:
         assert not bad, sorted(bad, reverse=True)[:10]
     else:
-        assert len(bad) <= len(ref["grads"]) // 2, (len(bad), sorted(bad, reverse=True)[:10])
+        # one flipped element near the loss shifts EVERY upstream gradient by ~1e-3 of its size (117 of 244 tensors
+        # were over the strict limit in the measured fp32-mode run), so the aggregate bar is on the typical tensor
+        assert float(np.median(rels)) <= 5e-3, (float(np.median(rels)), len(bad), sorted(bad, reverse=True)[:5])
     for k, g1 in ours["grads"].items():          # parameters the reference leaves without a gradient
         if k not in ref["grads"]:
             assert np.abs(g1).max() == 0.0, k

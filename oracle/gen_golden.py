@@ -118,6 +118,20 @@ def main():
                         dens=dens[:, :, 0].numpy(), vol_nz=vol.permute(0, 2, 1)[nz].numpy(),
                         nz=nz.numpy())
 
+    # ---- splat backward (stage-2 groundwork): the reference's own autograd through splat_soft on the same case
+    gq = np.random.default_rng(77)
+    G = gq.standard_normal(tuple(vol.shape)).astype(np.float32)
+    Gd = gq.standard_normal(tuple(dens.shape)).astype(np.float32)
+    xy_g = xy.detach().clone().requires_grad_(True)
+    fm_g = fm.detach().clone().requires_grad_(True)
+    torch.manual_seed(0)             # splat_soft draws random indices for its weight-0 out-of-bounds votes
+    vol_g, dens_g = c2m.splat_soft((xy_g, fm_g, c2m.grid_size[:2]))
+    ((vol_g * torch.from_numpy(G)).sum() + (dens_g * torch.from_numpy(Gd)).sum()).backward()
+    # G / Gd are regenerated from the seed by the test (default_rng(77): G [N,C,HW] then Gd [N,HW,1], float32)
+    np.savez_compressed(os.path.join(OUT, "splat_bwd.npz"), xy=xy.numpy(), feats=fm.numpy(), g_seed=np.array(77),
+                        grid=np.array([int(c2m.grid_size[0]), int(c2m.grid_size[1])]),
+                        dfeats=fm_g.grad.numpy(), dxy=xy_g.grad.numpy())
+
     # ---- LiDAR raster (projection.py:64-134, build_dense_depth.py:461-463)
     H, W = 128, 240
     pc = synth.os1_scan(seed=3)[::8]

@@ -140,3 +140,23 @@ def test_net_oracle_equals_live_reference_forward():
         assert torch.equal(a[k], b[k].view_as(a[k])), k
     assert torch.equal(a["depth_preds_bins"], b["depth_preds_bins"])
     assert float((a["traversability_preds"] - b["traversability_preds"]).abs().max()) < 1e-4
+
+
+def test_splat_backward_restatement_matches_reference_golden(golden):
+    """Stage-2 groundwork: the numpy restatement of splat_soft's backward -- the formulas a
+    future creste_splat_soft_bwd kernel implements -- against the reference's own autograd (golden minted by
+    oracle/gen_golden.py from splat_projection.py:262-354 on the seeded splat case)."""
+    from oracle import splat_bwd_oracle as sb
+    g = golden("splat_bwd.npz")
+    H, W = int(g["grid"][0]), int(g["grid"][1])
+    N, Cc, _ = g["feats"].shape
+    rng = np.random.default_rng(int(g["g_seed"]))
+    G = rng.standard_normal((N, Cc, H * W)).astype(np.float32)
+    Gd = rng.standard_normal((N, H * W, 1)).astype(np.float32)[:, :, 0]
+    dfe, dxy = sb.splat_backward(g["xy"], g["feats"], G, Gd, H, W)
+    assert np.abs(dfe - g["dfeats"]).max() <= 1e-5 * np.abs(g["dfeats"]).max()
+    assert np.abs(dxy - g["dxy"]).max() <= 1e-5 * np.abs(g["dxy"]).max()
+    # and the forward half of the restatement against the forward golden of the same case
+    f = golden("splat.npz")
+    out, dens, _ = sb.splat_forward(g["xy"], g["feats"], H, W)
+    np.testing.assert_allclose(dens, f["dens"], rtol=1e-5, atol=1e-6)

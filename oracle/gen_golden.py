@@ -172,6 +172,7 @@ def main():
     irl_step_golden()
     stage1_loss_golden()
     distill_step_golden()
+    bev_step_golden()
 
     # ---- full forward, tiny image, both depth profiles (lfd.py:314-330)
     for prof in ("peaky", "soft"):
@@ -221,6 +222,22 @@ def distill_step_golden():
         grad_l2=np.array([np.sqrt((ref["grads"][n].astype(np.float64) ** 2).sum()) for n in names]),
         logits_sample=ref["logits"][:, ::16], dino_sample=ref["dino"][:, :, ::16],
         bn_running_mean=ref["params"]["depthcomp.vision_backbone.model.trunk._bn1.running_mean"],
+        **{"grad::" + n: ref["grads"][n] for n in full})
+
+
+def bev_step_golden():
+    """Stage-2 groundwork: train-mode forward + backward of the UNMODIFIED reference BEV decoder
+    (inpainting.py:70-109) on the seeded case of oracle/bev_oracle.make_case: loss, the L2 norm of every
+    gradient, two full gradient tensors (the strided layer2 conv and its 1x1 downsample) and an output sample."""
+    from . import bev_oracle as bo
+    ref = bo.reference_step(bo.make_case())
+    names = sorted(ref["grads"])
+    full = ["layer2.0.conv1.weight", "layer2.0.downsample.0.weight"]
+    np.savez_compressed(
+        os.path.join(OUT, "bev_step.npz"), loss=ref["loss"], grad_names=np.array(names),
+        grad_l2=np.array([np.sqrt((ref["grads"][n].astype(np.float64) ** 2).sum()) for n in names]),
+        preds0_sample=ref["preds0"][:, ::4, ::4, ::4],
+        bn1_running_mean=ref["buffers"]["bn1.running_mean"],
         **{"grad::" + n: ref["grads"][n] for n in full})
 
 

@@ -160,3 +160,31 @@ def test_splat_backward_restatement_matches_reference_golden(golden):
     f = golden("splat.npz")
     out, dens, _ = sb.splat_forward(g["xy"], g["feats"], H, W)
     np.testing.assert_allclose(dens, f["dens"], rtol=1e-5, atol=1e-6)
+
+
+@pytest.mark.skipif(not HAVE_REF, reason="reference tree not present")
+def test_bev_port_matches_reference():
+    """Stage-2 groundwork: the train-mode BEV decoder port (torchvision ResNet-18 layers + DeconvHeads) equals the
+    unmodified reference bit for bit on loss, all 78 gradients and the BatchNorm running statistics."""
+    from oracle import bev_oracle as bo
+    case = bo.make_case()
+    ref, port = bo.reference_step(case), bo.port_step(case)
+    assert ref["loss"] == port["loss"] and set(ref["grads"]) == set(port["grads"]) and len(ref["grads"]) == 78
+    for k in ref["grads"]:
+        assert np.array_equal(ref["grads"][k], port["grads"][k]), k
+    for k in ref["buffers"]:
+        assert np.array_equal(ref["buffers"][k], port["buffers"][k]), k
+
+
+def test_bev_port_matches_golden(golden):
+    from oracle import bev_oracle as bo
+    g = golden("bev_step.npz")
+    port = bo.port_step(bo.make_case())
+    np.testing.assert_allclose(port["loss"], g["loss"], rtol=1e-5)
+    names = [str(n) for n in g["grad_names"]]
+    l2 = np.array([np.sqrt((port["grads"][n].astype(np.float64) ** 2).sum()) for n in names])
+    np.testing.assert_allclose(l2, g["grad_l2"], rtol=1e-4)
+    for n in ("layer2.0.conv1.weight", "layer2.0.downsample.0.weight"):
+        ref = g["grad::" + n]
+        assert np.abs(port["grads"][n] - ref).max() <= 1e-4 * np.abs(ref).max(), n
+    np.testing.assert_allclose(port["buffers"]["bn1.running_mean"], g["bn1_running_mean"], rtol=1e-5, atol=1e-7)

@@ -431,6 +431,8 @@ class BNActFn(Function):
         ab, mi = ops.bn_fwd_finalize(st, weight.detach() if weight is not None else None,
                                      bias.detach() if bias is not None else None, M, bn.eps, mom,
                                      bn.running_mean if track else None, bn.running_var if track else None)
+        if track:       # updated in place through raw pointers by the finalize kernel
+            engine.mark_written([bn.running_mean, bn.running_var])
         ctx.save_for_backward(x, ab, mi)
         ctx.act, ctx.M = act, M
         return ops.chan_affine_act(x, ab[0], ab[1], act)

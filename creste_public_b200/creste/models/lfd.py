@@ -51,8 +51,14 @@ class MaxEntIRL(nn.Module):
             raise ValueError(f"Policy method {self.policy_method} not found.")
         if "TerrainNet" not in self.backbone_cfg["project_name"]:
             raise ValueError(f"Model {self.backbone_cfg['project_name']} not found.")
+        if self.backbone_cfg["load_setting"] == "strict_unfreezesplat":
+            # the reference leaves cam2map trainable in this mode and optimises it in stage 3; here the
+            # backbone runs without a graph inside MaxEntIRL.forward, so the splat layer would silently
+            # never train -- refused until the stage-3 step differentiates the splat
+            raise NotImplementedError("load_setting='strict_unfreezesplat' (trainable splat layer in stage 3) "
+                                      "is not implemented; use 'strict_freeze' (the shipped stage-3 configs)")
         with open_dict(self.backbone_cfg):
-            if self.backbone_cfg["load_setting"] not in ("strict_freeze", "strict_unfreezesplat"):
+            if self.backbone_cfg["load_setting"] != "strict_freeze":
                 self.backbone_cfg["load_setting"] = "strict_freeze"
         self.backbone = TerrainNet(OmegaConf.create(self.backbone_cfg))
         if os.path.exists(self.backbone_cfg["weights_path"]):

@@ -71,23 +71,40 @@ class TerrainNet(nn.Module):
             fixed[k] = v
         assert len(fixed) == n0
         sd = fixed
-        own = self.state_dict()
         setting = self.load_setting
+
+        def trainable_iff(pred):
+            for name, p in self.named_parameters():
+                p.requires_grad = bool(pred(name))
+
+        heads = "bevclassifier.out_heads"
         if setting in ("strict", "strict_freeze", "strict_unfreezesplat"):
-            self.load_state_dict(sd, strict=True)
-            if setting != "strict":
-                for n, p in self.named_parameters():
-                    p.requires_grad = False
-                if setting == "strict_unfreezesplat":
-                    for p in self.cam2map.parameters():
+            # Lightning stage-2 checkpoints carry the LossManager's tensors under `loss.`: dropped in all
+            # three strict modes (terrainnet.py:236-257); only strict_unfreezesplat loads non-strictly
+            sd = {k: v for k, v in sd.items() if not k.startswith("loss.")}
+            self.load_state_dict(sd, strict=(setting != "strict_unfreezesplat"))
+            if setting == "strict_freeze":
+                trainable_iff(lambda n: False)
+            elif setting == "strict_unfreezesplat":
+                trainable_iff(lambda n: "cam2map." in n)
+        elif setting == "ft_semantic_head":
+            # everything loads non-strictly; only a (future) semantic head and the 1-channel decoder
+            # heads train (terrainnet.py:151-166)
+            self.load_state_dict(sd, strict=False)
+            trainable_iff(lambda n: "bev_semantic_head" in n)
+            for head in self.bevclassifier.out_heads:
+                if head.proj.out_channels == 1:
+                    for p in head.parameters():
                         p.requires_grad = True
-        elif setting in ("ft_semantic_head", "ft_decoders_all", "ft_decoders_partial"):
-            keep = {k: v for k, v in sd.items() if k in own and own[k].shape == v.shape}
-            if setting == "ft_decoders_all":
-                keep = {k: v for k, v in keep.items() if not k.startswith("bevclassifier.out_heads")}
-            self.load_state_dict(keep, strict=False)
-            for n, p in self.named_parameters():
-                p.requires_grad = n not in keep
+        elif setting == "ft_decoders_all":
+            sd = {k: v for k, v in sd.items() if heads not in k}
+            self.load_state_dict(sd, strict=False)
+            trainable_iff(lambda n: heads in n)
+        elif setting == "ft_decoders_partial":
+            last = lambda n: heads in n and ("up2" in n or "proj" in n)   # noqa: E731
+            sd = {k: v for k, v in sd.items() if not last(k)}
+            self.load_state_dict(sd, strict=False)
+            trainable_iff(last)
         else:
             raise ValueError(f"Invalid load_setting {self.load_setting}")
 

@@ -13,7 +13,7 @@ from torch import nn
 
 from creste_public_b200.config import as_cfg
 from .models.distillation import DistillationBackbone  # noqa: F401  (resolved by name)
-from .train_traversability import ExponentialLR, FlatAdam
+from .train_traversability import ExponentialLR, FlatAdam, broadcast_buffers
 from .utils import loss_utils as lu
 from .utils import train_utils as tu
 
@@ -69,6 +69,7 @@ class DistillationModel(nn.Module):
     def training_step(self, inputs):
         opt = self.optimizers()
         opt.zero_grad()
+        broadcast_buffers(self.model, opt.group)
         _, loss_dict, meta, loss = self._losses(inputs)
         loss.backward()
         opt.step()

@@ -11,11 +11,42 @@ averaged over ranks once per step.  Here that exchange is ONE flat NCCL all-redu
 import torch
 from torch import nn
 
-from creste_public_b200 import ops
+from creste_public_b200 import engine, ops
 from creste_public_b200.config import as_cfg
 from .models.lfd import MaxEntIRL
 from .utils import loss_utils as lu
 from .utils import train_utils as tu
+
+
+def _world(group=None):
+    import torch.distributed as dist
+    if not (dist.is_available() and dist.is_initialized()):
+        return 1
+    return dist.get_world_size(group)
+
+
+def broadcast_buffers(module, group=None):
+    """DDP's `broadcast_buffers=True` (the default Lightning's DDPStrategy keeps): before every forward
+    rank 0's buffers -- the BatchNorm running statistics and step counters -- overwrite the other
+    ranks'.  The batch statistics used for normalisation stay per-rank (no SyncBN), as in the reference.
+    One coalesced broadcast of the floating-point buffers + one of the integer ones; no-op at world 1."""
+    if _world(group) <= 1:
+        return
+    import torch.distributed as dist
+    from torch._utils import _flatten_dense_tensors, _unflatten_dense_tensors
+    src = dist.get_global_rank(group, 0) if group else 0
+    bufs = [b for b in module.buffers() if b is not None and b.numel() > 0]
+    for sel in (lambda b: b.is_floating_point(), lambda b: not b.is_floating_point()):
+        by_dtype = {}
+        for b in bufs:
+            if sel(b):
+                by_dtype.setdefault(b.dtype, []).append(b)
+        for group_bufs in by_dtype.values():
+            flat = _flatten_dense_tensors(group_bufs)
+            dist.broadcast(flat, src=src, group=group)
+            with torch.no_grad():
+                for b, f in zip(group_bufs, _unflatten_dense_tensors(flat, group_bufs)):
+                    b.copy_(f)
 
 
 class FlatAdam:
@@ -49,6 +80,13 @@ class FlatAdam:
         self.lr, self.betas, self.eps = float(lr), betas, float(eps)
         self.steps = 0
         self.group = process_group
+        # DistributedDataParallel broadcasts rank 0's parameters when it wraps the module (the reference
+        # trains under Lightning's DDPStrategy): without it replicas initialised from per-rank RNG
+        # streams would average gradients of DIFFERENT weights and drift apart silently
+        if _world(self.group) > 1:
+            import torch.distributed as dist
+            dist.broadcast(self.flat_p, src=dist.get_global_rank(self.group, 0) if self.group else 0,
+                           group=self.group)
 
     def zero_grad(self):
         self.flat_g.zero_()
@@ -67,12 +105,15 @@ class FlatAdam:
         import torch.distributed as dist
         self._gather_grads()
         scale = 1.0
-        if dist.is_available() and dist.is_initialized() and dist.get_world_size(self.group) > 1:
+        if _world(self.group) > 1:
             dist.all_reduce(self.flat_g, op=dist.ReduceOp.SUM, group=self.group)
             scale = 1.0 / dist.get_world_size(self.group)
         self.steps += 1
         ops.adam_step(self.flat_p, self.flat_g, self.m, self.v, self.lr, self.betas[0],
                       self.betas[1], self.eps, self.steps, scale)
+        # the kernel wrote the parameters through the flat buffer's raw pointer: advance their version
+        # counters so the eval-path pack caches (engine.PackCache) see the new values
+        engine.mark_written(self.params)
 
     def grad_norm(self):
         """train_traversability.py:110-118 without the per-parameter .item() loop."""
@@ -140,6 +181,7 @@ class MaxEntIRLModel(nn.Module):
         for task, data in batch.items():
             opt = self.optimizers()
             opt.zero_grad()
+            broadcast_buffers(self.model, opt.group)
             _, merged = self._run(data, task)
             loss_dict, meta = self.loss(merged)
             loss = loss + sum(w * v for w, v in loss_dict.values())
@@ -151,11 +193,14 @@ class MaxEntIRLModel(nn.Module):
         return {"loss": loss}
 
     def validation_step(self, inputs):
+        """Lightning runs validation under torch.no_grad(): the reward map carries no graph there, so the
+        SMODICE gradient penalty is 0 and `val/loss` is the visitation term alone (loss_utils.py:1208)."""
         batch, _, _ = inputs
         loss = 0.0
         for task, data in batch.items():
-            _, merged = self._run(data, task)
-            loss_dict, meta = self.loss(merged)
+            with torch.no_grad():
+                _, merged = self._run(data, task)
+                loss_dict, meta = self.loss(merged)
             loss = sum(w * v for w, v in loss_dict.values())
             self.logged.update({f"val/{k}": w * v.detach() for k, (w, v) in loss_dict.items()})
             self.logged.update({f"val/{k}": v.detach() for k, v in meta.items()})
@@ -180,6 +225,7 @@ class HeadStep:
     def __call__(self, feat_map, expert, fov_mask, counterfactuals):
         m = self.model
         self.opt.zero_grad()
+        broadcast_buffers(m.traversability_head, self.opt.group)
         keys = m.traversability_head.reward_cfg.input_keys
         Wo = feat_map[keys[0]].shape[-1]
         map_ds = Wo // m.map_size[1]

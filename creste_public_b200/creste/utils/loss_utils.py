@@ -88,6 +88,9 @@ class _Stage1DepthValues:
         if cls._key != key or cls._ref is None or cls._ref() is not logits:
             if discretize["mode"] != "UD":
                 raise NotImplementedError("bin_depths modes other than 'UD' are unused by the shipped configs")
+            if int(logits.shape[1]) != int(discretize["num_bins"]):
+                raise ValueError(f"depth head emits {int(logits.shape[1])} bins, discretize.num_bins is "
+                                 f"{discretize['num_bins']}")
             B, S, H, W = label.shape
             if logits.shape[0] != B * S or tuple(logits.shape[-2:]) != (H, W):
                 raise NotImplementedError("multi-frame / resized depth labels are outside the hot path")

@@ -66,6 +66,17 @@ def _ver(*tensors):
     return tuple((t.data_ptr(), t._version, str(t.device)) for t in tensors if t is not None)
 
 
+def mark_written(tensors):
+    """Tell the pack caches that `tensors` were updated through a raw device pointer (the fused Adam
+    step on the flat parameter buffer, the BatchNorm running-statistics update inside
+    creste_bn_fwd_finalize): a kernel writing through data_ptr() does not advance torch's version
+    counter, and PackCache keys on (data_ptr, _version) -- without this an eval forward after a
+    training step would reuse the packed weights / folded BatchNorm factors of the old parameters."""
+    ts = [t for t in tensors if t is not None]
+    if ts:
+        torch._C._increment_version(ts)
+
+
 class PackCache:
     """Per-module cache of device-side packed tensors, invalidated by parameter version."""
 

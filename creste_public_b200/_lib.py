@@ -16,9 +16,9 @@ EXPORTS = [
     "creste_version", "creste_last_error", "creste_num_sms", "creste_launch_count",
     "creste_vi_workspace_bytes", "creste_vi_solve",
     "creste_svf_workspace_bytes", "creste_svf",
-    "creste_frustum_to_bev", "creste_zmlp_concat",
+    "creste_frustum_to_bev", "creste_camera_to_world", "creste_points_to_voxels", "creste_zmlp_concat",
     "creste_splat_workspace_bytes", "creste_splat_soft",
-    "creste_lidar_raster", "creste_depth_expectation",
+    "creste_lidar_raster", "creste_depth_expectation", "creste_bin_depths",
     "creste_conv2d", "creste_conv2d_workspace_bytes", "creste_conv2d_tc_supported",
     "creste_conv2d_tc_layout", "creste_conv2d_tc_debug",
     "creste_dwconv_num_parts", "creste_dwconv_bn_swish", "creste_se_gate",

@@ -17,9 +17,13 @@ class Camera2World(nn.Module):
     """depth [B,N,H,W] + p2p [B,N,4,4] -> xyz [B,N,3,H,W] in the LiDAR frame."""
 
     def forward(self, x):
-        raise NotImplementedError(
-            "Camera2World is fused into creste_frustum_to_bev (xyz is never materialised); "
-            "use Camera2MapMulti.frustum(depth, p2p) for xy / z / mask")
+        """(depth [B,N,H,W], p2p [B,N,4,4]) -> xyz [B,N,3,H,W] (reference :19-51).  The fused hot path
+        (Camera2MapMulti.forward_nhwc -> creste_frustum_to_bev) never materialises xyz; this is the
+        stand-alone module call, one launch of creste_camera_to_world."""
+        depth, p2p = x
+        B, N, H, W = depth.shape
+        xyz = ops.camera_to_world(depth.reshape(B * N, H, W).float(), p2p.reshape(B * N, 4, 4).float())
+        return xyz.view(B, N, 3, H, W)
 
 
 class Camera2MapMulti(nn.Module):
@@ -77,11 +81,7 @@ class Camera2MapMulti(nn.Module):
         _, _, grid = self._geom()
         xy, z, mask = self.frustum(depth, p2p)
         l0, l2 = self.z_proj[0], self.z_proj[2]
-        w1, b1, w2, b2 = self._cache.get(
-            "z", [l0.weight, l0.bias, l2.weight, l2.bias],
-            lambda: (l0.weight.detach().float().reshape(-1).contiguous(),
-                     l0.bias.detach().float().contiguous(),
-                     l2.weight.detach().float().contiguous(), l2.bias.detach().float().contiguous()))
+        w1, b1, w2, b2 = self._zmlp_weights(l0, l2)
         cat = ops.zmlp_concat(feats_nhwc, z, w1, b1, w2, b2)
         fused = self.vision_fusion.forward_nhwc(cat)                     # [M,Hs,Ws,96]
         Cf = fused.shape[-1]
@@ -92,6 +92,49 @@ class Camera2MapMulti(nn.Module):
         if want_nchw:
             ret["bev_features"] = out["bev_nchw"]
         return ret, out["bev_nhwc"]
+
+    # ---- the reference's helper methods as callable entry points (same signatures and layouts) ----
+    def _prepare_features_and_coords(self, x):
+        """(depth [B,N,H,W], feats [B,N,F,H,W], p2p [B,N,4,4]) -> xyz [B,N,3,H,W], xyz_mask [B,N,1,H,W]
+        bool, fused feats [B,N,C,H,W] (reference :131-173)."""
+        require_eval(self)
+        depth, feats, p2p = x
+        B, N, F, H, W = feats.shape
+        d = depth.reshape(B * N, H, W).float()
+        m = p2p.reshape(B * N, 4, 4).float()
+        xyz = ops.camera_to_world(d, m)                                       # [BN,3,H,W]
+        _, z, mask = self.frustum(d, m)
+        l0, l2 = self.z_proj[0], self.z_proj[2]
+        w1, b1, w2, b2 = self._zmlp_weights(l0, l2)
+        cat = ops.zmlp_concat(ops.nchw_to_nhwc(feats.reshape(B * N, F, H, W).float()), z, w1, b1, w2, b2)
+        fused = ops.nhwc_to_nchw(self.vision_fusion.forward_nhwc(cat))
+        return (xyz.view(B, N, 3, H, W), mask.view(B, N, 1, H, W).bool(),
+                fused.view(B, N, fused.shape[1], H, W))
+
+    def _points_to_voxels(self, points):
+        """points [B,P,3] (LiDAR frame) -> fractional voxel coordinates [B,P,2] (reference :175-189)."""
+        vox = [float(v) for v in self.voxel_size.tolist()]
+        return ops.points_to_voxels(points, self.lidar2map.tolist(), vox[:2])
+
+    def splat_soft(self, x):
+        """(points_2d [B,P,2], points_features [B,F,P], grid_size (H, W)) -> (volume_features [B,F,H*W],
+        volume_densities [B,H*W,1]) (reference :262-354, scatter_mode='mean')."""
+        xy, feats, grid = x
+        H, W = int(grid[0]), int(grid[1])
+        B, F, P = feats.shape
+        f = ops.nchw_to_nhwc(feats.reshape(B, F, 1, P).float()).view(B, P, F)
+        Fp = F + (-F) % 4
+        if Fp != F:
+            f = torch.cat([f, f.new_zeros(B, P, Fp - F)], dim=-1).contiguous()
+        out = ops.splat_soft(xy, f, None, H, W, self.min_weight, want_nhwc=False, want_nchw=True)
+        return out["bev_nchw"][:, :F].reshape(B, F, H * W), out["dens"].view(B, H * W, 1)
+
+    def _zmlp_weights(self, l0, l2):
+        return self._cache.get(
+            "z", [l0.weight, l0.bias, l2.weight, l2.bias],
+            lambda: (l0.weight.detach().float().reshape(-1).contiguous(),
+                     l0.bias.detach().float().contiguous(),
+                     l2.weight.detach().float().contiguous(), l2.bias.detach().float().contiguous()))
 
     def forward(self, x):
         assert len(x) >= 3, "Input must contain depth, features and camera projection matrix."

@@ -56,7 +56,7 @@ __global__ void lidar_finish_kernel(const unsigned long long* __restrict__ zbuf,
 
 // one warp per pixel, D == 128
 __global__ void __launch_bounds__(256) depth_expectation_kernel(const float* __restrict__ logits,
-                                                                int NP, float dmin, float dmax,
+                                                                int NP, float dmin, float dmax, float out_div,
                                                                 float* __restrict__ metric,
                                                                 long long* __restrict__ bins) {
   const int lane = threadIdx.x & 31;
@@ -91,15 +91,53 @@ __global__ void __launch_bounds__(256) depth_expectation_kernel(const float* __r
     }
     acc = warp_sum(acc);
     if (lane == 0) {
-      metric[p] = __fdiv_rn(acc, 1000.0f);
+      metric[p] = __fdiv_rn(acc, out_div);      // 1000: metres (depth.py:100); 1: the bin units (mm)
       if (bins) bins[p] = arg;
     }
   }
 }
 
+// bin_depths (depth_utils.py:346-383): same fp32 operation order as the tensor expression
+__global__ void bin_depths_kernel(const float* __restrict__ d, long long n, int mode, float dmin, float bin_size,
+                                  float log_lo, float log_span, int num_bins, int target,
+                                  float* __restrict__ out_f, long long* __restrict__ out_i) {
+  const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  const float x = d[i];
+  float idx;
+  if (mode == 0) {
+    idx = __fdiv_rn(__fsub_rn(x, dmin), bin_size);
+  } else if (mode == 1) {
+    const float t = __fadd_rn(1.0f, __fdiv_rn(__fmul_rn(8.0f, __fsub_rn(x, dmin)), bin_size));
+    idx = __fadd_rn(-0.5f, __fmul_rn(0.5f, sqrtf(t)));
+  } else {
+    idx = __fdiv_rn(__fmul_rn((float)num_bins, __fsub_rn(logf(__fadd_rn(1.0f, x)), log_lo)), log_span);
+  }
+  if (!target) { out_f[i] = idx; return; }
+  const bool bad = (idx < 0.0f) || (idx > (float)num_bins) || !isfinite(idx);
+  out_i[i] = bad ? (long long)num_bins : (long long)idx;
+}
+
 }  // namespace creste
 
 using namespace creste;
+
+extern "C" int creste_bin_depths(const float* depth, long long n, int mode, float depth_min, float depth_max,
+                                 int num_bins, int target, float* out_f, int64_t* out_i, void* stream) {
+  CRESTE_CHECK_ARG(depth && n > 0 && num_bins > 0 && mode >= 0 && mode <= 2, "creste_bin_depths: bad args");
+  CRESTE_CHECK_ARG(target ? (out_i != nullptr) : (out_f != nullptr), "creste_bin_depths: output pointer");
+  // python-float (double) constants rounded once to fp32 when they meet the fp32 tensor, as in torch
+  float bin_size = 1.0f, log_lo = 0.0f, log_span = 1.0f;
+  if (mode == 0) bin_size = (float)(((double)depth_max - (double)depth_min) / (double)num_bins);
+  if (mode == 1) bin_size = (float)(2.0 * ((double)depth_max - (double)depth_min) / ((double)num_bins * (1.0 + num_bins)));
+  if (mode == 2) {
+    log_lo = (float)log(1.0 + (double)depth_min);
+    log_span = (float)(log(1.0 + (double)depth_max) - log(1.0 + (double)depth_min));
+  }
+  bin_depths_kernel<<<(unsigned)((n + 255) / 256), 256, 0, (cudaStream_t)stream>>>(
+      depth, n, mode, depth_min, bin_size, log_lo, log_span, num_bins, target, out_f, (long long*)out_i);
+  return launch_check("bin_depths_kernel");
+}
 
 extern "C" int creste_lidar_raster(const float* pc, int npts, int stride, const double* P34_host,
                                    int H, int W, float* depth_m, float* depth_mm, void* ws,
@@ -127,13 +165,13 @@ extern "C" int creste_lidar_raster(const float* pc, int npts, int stride, const 
 }
 
 extern "C" int creste_depth_expectation(const float* logits, int NP, int D, float depth_min_mm,
-                                        float depth_max_mm, float* metric, int64_t* bins,
+                                        float depth_max_mm, float out_div, float* metric, int64_t* bins,
                                         void* stream) {
   CRESTE_CHECK_ARG(logits && metric, "creste_depth_expectation: null pointer");
   CRESTE_CHECK_ARG(D == 128, "creste_depth_expectation: only D = 128 bins is implemented (got %d)", D);
   CRESTE_CHECK_ARG(NP > 0, "creste_depth_expectation: bad shape");
   const int blocks = min(ceil_div(NP, 8), 148 * 8);
   depth_expectation_kernel<<<blocks, 256, 0, (cudaStream_t)stream>>>(
-      logits, NP, depth_min_mm, depth_max_mm, metric, (long long*)bins);
+      logits, NP, depth_min_mm, depth_max_mm, out_div, metric, (long long*)bins);
   return launch_check("depth_expectation_kernel");
 }

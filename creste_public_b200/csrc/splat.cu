@@ -55,6 +55,42 @@ __global__ void frustum_kernel(const float* __restrict__ depth, const float* __r
   xy[(size_t)i * 2 + 1] = __fdiv_rn(ym, vy);
 }
 
+// Camera2World.forward as a stand-alone op (the fused path never materialises xyz): xyz [N,3,Hs,Ws]
+__global__ void camera_to_world_kernel(const float* __restrict__ depth, const float* __restrict__ p2p, int N,
+                                       int Hs, int Ws, float* __restrict__ xyz) {
+  const int P = Hs * Ws;
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= N * P) return;
+  const int n = i / P, p = i - n * P;
+  const int v = p / Ws, u = p - v * Ws;
+  const float* M = p2p + n * 16;
+  const float d = depth[i];
+  const float c0 = __fmul_rn((float)u, d), c1 = __fmul_rn((float)v, d), c2 = d;
+#pragma unroll
+  for (int r = 0; r < 3; ++r) {
+    float acc = __fmul_rn(M[r * 4 + 0], c0);
+    acc = __fmaf_rn(M[r * 4 + 1], c1, acc);
+    acc = __fmaf_rn(M[r * 4 + 2], c2, acc);
+    acc = __fmaf_rn(M[r * 4 + 3], 1.0f, acc);
+    xyz[((size_t)n * 3 + r) * P + p] = acc;
+  }
+}
+
+// Camera2MapMulti._points_to_voxels: rows 0..1 of (lidar2map @ [x,y,z,1]) / voxel_size[:2]
+__global__ void points_to_voxels_kernel(const float* __restrict__ pts, long long NP, float l00, float l01,
+                                        float l02, float l03, float l10, float l11, float l12, float l13,
+                                        float vx, float vy, float* __restrict__ xy) {
+  const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= NP) return;
+  const float x = pts[i * 3 + 0], y = pts[i * 3 + 1], z = pts[i * 3 + 2];
+  float a = __fmul_rn(l00, x);
+  a = __fmaf_rn(l01, y, a); a = __fmaf_rn(l02, z, a); a = __fmaf_rn(l03, 1.0f, a);
+  float b = __fmul_rn(l10, x);
+  b = __fmaf_rn(l11, y, b); b = __fmaf_rn(l12, z, b); b = __fmaf_rn(l13, 1.0f, b);
+  xy[i * 2 + 0] = __fdiv_rn(a, vx);
+  xy[i * 2 + 1] = __fdiv_rn(b, vy);
+}
+
 // one warp per point; C % 4 == 0
 __global__ void __launch_bounds__(256) zmlp_concat_kernel(const float* __restrict__ feats,
                                                           const float* __restrict__ z, int NP, int C,
@@ -189,6 +225,24 @@ extern "C" int creste_frustum_to_bev(const float* depth, const float* p2p, int N
       depth, p2p, N, Hs, Ws, range[0], range[1], range[2], range[3], range[4], range[5], voxel[0],
       voxel[1], xy, z, mask);
   return launch_check("frustum_kernel");
+}
+
+extern "C" int creste_camera_to_world(const float* depth, const float* p2p, int N, int Hs, int Ws, float* xyz,
+                                      void* stream) {
+  CRESTE_CHECK_ARG(depth && p2p && xyz, "creste_camera_to_world: null pointer");
+  CRESTE_CHECK_ARG(N > 0 && Hs > 0 && Ws > 0, "creste_camera_to_world: bad shape");
+  const int total = N * Hs * Ws;
+  camera_to_world_kernel<<<ceil_div(total, 256), 256, 0, (cudaStream_t)stream>>>(depth, p2p, N, Hs, Ws, xyz);
+  return launch_check("camera_to_world_kernel");
+}
+
+extern "C" int creste_points_to_voxels(const float* pts, long long NP, const float* lidar2map, const float* voxel,
+                                       float* xy, void* stream) {
+  CRESTE_CHECK_ARG(pts && lidar2map && voxel && xy && NP > 0, "creste_points_to_voxels: null pointer");
+  const float* L = lidar2map;   // HOST 4x4 row-major
+  points_to_voxels_kernel<<<(unsigned)((NP + 255) / 256), 256, 0, (cudaStream_t)stream>>>(
+      pts, NP, L[0], L[1], L[2], L[3], L[4], L[5], L[6], L[7], voxel[0], voxel[1], xy);
+  return launch_check("points_to_voxels_kernel");
 }
 
 extern "C" int creste_zmlp_concat(const float* feats, const float* z, int NP, int C, const float* w1,

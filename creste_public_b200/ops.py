@@ -78,6 +78,30 @@ def frustum_to_bev(depth, p2p, pc_range, voxel):
     return xy, z, mask
 
 
+def camera_to_world(depth, p2p):
+    """depth [N,Hs,Ws], p2p [N,4,4] -> xyz [N,3,Hs,Ws] (reference splat_projection.py:19-51)."""
+    depth = depth.contiguous().float()
+    p2p = p2p.contiguous().float()
+    N, Hs, Ws = depth.shape
+    xyz = torch.empty(N, 3, Hs, Ws, device=depth.device)
+    check(lib().creste_camera_to_world(ptr(depth), ptr(p2p), N, Hs, Ws, ptr(xyz), stream()),
+          "creste_camera_to_world")
+    return xyz
+
+
+def points_to_voxels(points, lidar2map, voxel):
+    """points [B,P,3] CUDA; lidar2map 4x4 / voxel (x, y) python floats -> voxels [B,P,2]
+    (reference splat_projection.py:175-189)."""
+    points = points.contiguous().float()
+    B, P, _ = points.shape
+    xy = torch.empty(B, P, 2, device=points.device)
+    L = (C.c_float * 16)(*[float(v) for row in lidar2map for v in row])
+    vox = (C.c_float * 2)(float(voxel[0]), float(voxel[1]))
+    check(lib().creste_points_to_voxels(ptr(points), C.c_longlong(B * P), L, vox, ptr(xy), stream()),
+          "creste_points_to_voxels")
+    return xy
+
+
 def zmlp_concat(feats_nhwc, z, w1, b1, w2, b2):
     """feats NHWC [...,C] + MLP(z) -> NHWC [...,C+32] (reference splat_projection.py:152-158)."""
     Cc = feats_nhwc.shape[-1]
@@ -133,18 +157,32 @@ def lidar_raster(pc, P34, H, W, out_mm=None, want_m=True):
     return dm, dmm
 
 
-def depth_expectation(logits_nhwc, dmin=300.0, dmax=25600.0):
-    """logits NHWC [N,Hs,Ws,128] -> metric [N,Hs,Ws] (m), bins [N,Hs,Ws] int64
-    (reference depth_utils.py:300-313, depth.py:60-100)."""
+def depth_expectation(logits_nhwc, dmin=300.0, dmax=25600.0, out_div=1000.0):
+    """logits NHWC [N,Hs,Ws,128] -> metric [N,Hs,Ws] (expectation / out_div: metres by default),
+    bins [N,Hs,Ws] int64 (reference depth_utils.py:300-313, depth.py:60-100)."""
     D = logits_nhwc.shape[-1]
     shp = logits_nhwc.shape[:-1]
     NP = logits_nhwc.numel() // D
     metric = torch.empty(shp, device=logits_nhwc.device)
     bins = torch.empty(shp, dtype=torch.int64, device=logits_nhwc.device)
     check(lib().creste_depth_expectation(ptr(logits_nhwc), NP, D, C.c_float(dmin), C.c_float(dmax),
-                                         ptr(metric), ptr(bins), stream()),
+                                         C.c_float(out_div), ptr(metric), ptr(bins), stream()),
           "creste_depth_expectation")
     return metric, bins
+
+
+BIN_MODES = {"UD": 0, "LID": 1, "SID": 2}
+
+
+def bin_depths(depth, mode, depth_min, depth_max, num_bins, target=False):
+    """Depth map -> (float | int64) bin indices, reference depth_utils.py:346-383."""
+    d = depth.contiguous().float()
+    out = torch.empty(d.shape, dtype=torch.int64 if target else torch.float32, device=d.device)
+    check(lib().creste_bin_depths(ptr(d), C.c_longlong(d.numel()), BIN_MODES[mode], C.c_float(depth_min),
+                                  C.c_float(depth_max), int(num_bins), int(bool(target)),
+                                  ptr(None if target else out), ptr(out if target else None), stream()),
+          "creste_bin_depths")
+    return out
 
 
 # ---------------------------------------------------------------------------------- conv family

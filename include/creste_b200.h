@@ -82,6 +82,18 @@ int creste_frustum_to_bev(const float* depth, const float* p2p, int N, int Hs, i
 int creste_zmlp_concat(const float* feats, const float* z, int NP, int C, const float* w1,
                        const float* b1, const float* w2, const float* b2, float* out, void* stream);
 
+/* Camera2World.forward as a stand-alone op, creste/models/blocks/splat_projection.py:19-51:
+ * xyz[n, :, v, u] = (p2p[n] @ [u*d, v*d, d, 1])[:3] (K = 4 in-order FMA chain, the CPU bmm order).
+ *   depth [N,Hs,Ws]; p2p [N,4,4]; xyz [N,3,Hs,Ws].  The fused path (creste_frustum_to_bev) never
+ *   materialises xyz; this entry exists for callers of the reference's Camera2World module. */
+int creste_camera_to_world(const float* depth, const float* p2p, int N, int Hs, int Ws, float* xyz,
+                           void* stream);
+/* Camera2MapMulti._points_to_voxels, splat_projection.py:175-189:
+ * xy = (lidar2map @ [x,y,z,1])[:2] / voxel_size[:2].
+ *   pts [NP,3] device; lidar2map HOST float[16] row-major; voxel HOST float[2]; xy [NP,2] device. */
+int creste_points_to_voxels(const float* pts, long long NP, const float* lidar2map, const float* voxel,
+                            float* xy, void* stream);
+
 /* Bilinear 4-tap scatter-add splat with mean normalisation.  Replaces
  * Camera2MapMulti.splat_soft, creste/models/blocks/splat_projection.py:262-354
  * (scatter_mode='mean') and the `feats * xyz_mask` at :219.
@@ -108,9 +120,18 @@ int creste_lidar_raster(const float* pc, int npts, int stride, const double* P34
 /* Softmax-expectation metric depth + arg-max bin.  Replaces
  * convert_to_metric_depth_differentiable, creste/utils/depth_utils.py:300-313 and
  * DepthCompletion._convert_to_metric_depth, creste/models/depth.py:60-100.
- *   logits NHWC [NP, D] (D = 128); metric [NP] metres; bins [NP] int64. */
+ *   logits NHWC [NP, D] (D = 128); metric [NP] = expectation / out_div (out_div = 1000: metres as
+ *   depth.py:100 returns; 1: the units of depth_min / depth_max as depth_utils.py:300-313 returns);
+ *   bins [NP] int64 (may be NULL). */
 int creste_depth_expectation(const float* logits, int NP, int D, float depth_min_mm,
-                             float depth_max_mm, float* metric, int64_t* bins, void* stream);
+                             float depth_max_mm, float out_div, float* metric, int64_t* bins,
+                             void* stream);
+
+/* bin_depths, creste/utils/depth_utils.py:346-383.  mode 0 = UD, 1 = LID, 2 = SID.
+ *   depth [n]; out_f [n] float indices (target == 0) or out_i [n] int64 with out-of-range / non-finite
+ *   indices set to num_bins (target != 0).  Exactly one of out_f / out_i is written. */
+int creste_bin_depths(const float* depth, long long n, int mode, float depth_min, float depth_max,
+                      int num_bins, int target, float* out_f, int64_t* out_i, void* stream);
 
 /* ---------------------------------------------------------------------------------------------
  * Convolution family (NHWC, fp32 storage).  One descriptor covers every dense conv / linear on

@@ -181,11 +181,21 @@ def test_batch_split_invariance(cuda):
 def test_forward_tensor_core_modes(cuda, mode):
     """Whole forward in the fp32-faithful tensor-core modes (tcgen05 3xTF32 / 3xFP16 splits):
     encoder features within 5e-5 * max of the fp32 oracle, depth bins identical on the soft
-    profile, costmap within the conditioning yardstick used by the fp32 end-to-end test."""
+    profile, costmap within the conditioning yardstick used by the fp32 end-to-end test
+    (|cuda - ref32| <= 3 * yardstick + 1e-4; the full-size stage-wise checks of the benchmarked mode are in
+    tests/test_forward_full_gpu.py)."""
     import creste_public_b200 as cb
     model, sd = _model("soft")
     rgbd, p2p = synth.net_inputs(H, W, 1)
     ref = no.forward(sd, rgbd, p2p)
+    ens = [no.forward(sd, rgbd, p2p, encoder_fp64=True)]
+    g = torch.Generator().manual_seed(0)
+    kw = "backbone.depthcomp.depthcomp.vision_backbone.model.conv.weight"
+    for _ in range(4):
+        sd2 = dict(sd)
+        sd2[kw] = sd[kw] * (1 + 1e-6 * torch.randn(sd[kw].shape, generator=g))
+        ens.append(no.forward(sd2, rgbd, p2p))
+    yard = max(float((e["traversability_preds"] - ref["traversability_preds"]).abs().max()) for e in ens)
     cb.set_precision(mode)
     try:
         with torch.no_grad():
@@ -197,9 +207,9 @@ def test_forward_tensor_core_modes(cuda, mode):
     agree = float((out["depth_preds_bins"].cpu() == ref["depth_preds_bins"]).float().mean())
     assert agree >= 0.999, agree
     # the costmap is conditioning-limited (perturbing one encoder layer by 1e-6 moves it
-    # by 2e-3..2e-2); it is held to the same order as that yardstick, not to 1e-4
+    # by 2e-3..2e-2): held to the yardstick measured above, exactly as the fp32 end-to-end test
     err = float((out["traversability_preds"].cpu() - ref["traversability_preds"]).abs().max())
-    assert err <= 1e-1, err
+    assert err <= 3 * yard + 1e-4, (err, yard)
 
 
 def test_training_mode_is_refused_loudly(cuda):

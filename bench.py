@@ -16,11 +16,15 @@ launched by torchrun, one rank per GPU, frames sharded across ranks with no data
 collective (weak scaling); time = max over ranks, measured with CUDA events.
 
 Extra objects in the JSON line: `roofline` (dominant conv kernel, tensor bound), `cpu_baseline`
-(oracle port on the host cores, rank 0, N = 1 only), `irl` (second headline metric: counterfactual
-IRL head-only training steps/s at 256x256 with its own CPU baseline, plus the value-iteration
-kernel's HBM-equivalent roofline), `latency_b1` (one frame, eager vs CUDA-graph replay), `clocks`,
-`gpu_launches`.  Only the cpu_baseline legs and `--impl reference` touch `oracle/`; the synthetic
-inputs come from the top-level `synth_data` module.
+(oracle port on the host cores, rank 0, N = 1 only), `gpu_eager_baseline` (the reference's PyTorch-eager
+GPU path restated in oracle/eager_oracle.py, on cuda:0 under three flag sets -- the denominator of the
+north_star's ">= 20x" target), `irl` (second headline metric: counterfactual IRL head-only training
+steps/s at 256x256 with its own CPU baseline, plus the value-iteration kernel's HBM-equivalent roofline),
+`hbm_kernels` (achieved GB/s of the splat / SVF / LiDAR-raster kernels), `vi_64x64` (configs[0]),
+`latency_b1` (one frame, eager vs CUDA-graph replay), `clocks`, `gpu_launches`.  The second and third
+metrics are repeated as TOP-LEVEL scalars (`irl_steps_per_s`, `irl_samples_per_s`, `stage1_fps`,
+`vi_hbm_frac`) so that they survive a truncated line.  Only the baseline legs and `--impl reference`
+touch `oracle/`; the synthetic inputs come from the top-level `synth_data` module.
 """
 import argparse
 import json
@@ -170,6 +174,164 @@ def cpu_stage1_baseline(H=512, W=960):
     return 1.0 / dt, dt * 1e3, torch.get_num_threads()
 
 
+def gpu_eager_baseline(dev, B=8, steps=3):
+    """The reference's single-GPU PyTorch-eager path (cuDNN / cuBLAS / ATen scatter_add_, restated in
+    oracle/eager_oracle.py because the reference itself cannot travel) on the SAME frames, inputs resident:
+    (a) default flags (cudnn.allow_tf32 = True, what the reference runs with), (b) cudnn.allow_tf32 = False,
+    (c) use_deterministic_algorithms(True, warn_only=True) as train_ssc.py / train_traversability.py set."""
+    import torch
+    from oracle import eager_oracle
+    import creste_public_b200 as cb
+    import synth_data as synth
+    model = cb.build_maxentirl(image_size=(H, W)).eval()
+    sd = {k: v.to(dev) for k, v in synth.seeded_state_dict(model.state_dict(), 0, "peaky").items()}
+    del model
+    out = {}
+    saved = (torch.backends.cudnn.allow_tf32, torch.backends.cudnn.benchmark)
+    for name, tf32, det in (("default_flags", True, False), ("cudnn_tf32_off", False, False),
+                            ("deterministic", True, True)):
+        res = {}
+        for b in (B, 1):
+            x = torch.rand(b, 1, 4, H, W, device=dev)
+            x[:, :, 3] *= 20000.0
+            p2p = torch.from_numpy(synth.make_p2p(H, W)).view(1, 1, 4, 4).repeat(b, 1, 1, 1).to(dev)
+            try:
+                torch.backends.cudnn.allow_tf32 = tf32
+                torch.use_deterministic_algorithms(det, warn_only=True)
+                for _ in range(2):
+                    eager_oracle.forward(sd, x, p2p)
+                torch.cuda.synchronize()
+                e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+                e0.record()
+                for _ in range(steps):
+                    eager_oracle.forward(sd, x, p2p)
+                e1.record()
+                torch.cuda.synchronize()
+                ms = e0.elapsed_time(e1) / steps
+                res[f"b{b}"] = {"fps": b * 1e3 / ms, "ms_per_step": ms}
+            except Exception as e:  # noqa: BLE001
+                res[f"b{b}"] = {"error": repr(e)[:160]}
+            finally:
+                torch.use_deterministic_algorithms(False)
+                torch.backends.cudnn.allow_tf32 = saved[0]
+            del x
+        out[name] = res
+    torch.cuda.empty_cache()
+    out["kind"] = "port"
+    out["what"] = ("oracle/eager_oracle.py: the reference's eager GPU forward (same library calls: cuDNN conv/BN, "
+                   "bmm un-projection, scatter_add_ splat) on cuda:0, inputs resident, full output dict")
+    return out
+
+
+def hbm_kernel_rooflines(dev, peaks, B=8):
+    """Achieved HBM GB/s of the three small memory-side kernels on the path (algorithmic bytes per unit from
+    SURVEY.md section 8(d)), each timed alone with CUDA events (median of 10 launches after 3 warm-ups)."""
+    import statistics as st
+    import torch
+    from creste_public_b200 import ops
+    import synth_data as synth
+
+    def med(fn, n=10):
+        for _ in range(3):
+            fn()
+        ts = []
+        for _ in range(n):
+            a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            a.record()
+            fn()
+            b.record()
+            torch.cuda.synchronize()
+            ts.append(a.elapsed_time(b))
+        return st.median(ts)
+
+    def obj(kernel, nbytes, ms, note=None):
+        gbs = nbytes / (ms * 1e-3) / 1e9
+        o = {"kernel": kernel, "bound": "hbm", "achieved": gbs, "peak": peaks["hbm_gbs"], "unit": "GB/s",
+             "frac": gbs / peaks["hbm_gbs"], "kernel_ms": ms, "algorithmic_bytes": nbytes, "traffic": None}
+        if note:
+            o["note"] = note
+        return o
+    res = {}
+    # splat: B frames x 30720 points x 96 channels -> 256x256 (37.6 MB / frame)
+    P, F, G = 128 * 240, 96, 256 * 256
+    g = torch.Generator(device="cpu").manual_seed(0)
+    xy = (torch.rand(B, P, 2, generator=g) * 255.0).to(dev)
+    feats = torch.randn(B, P, F, generator=g).to(dev)
+    mask = torch.ones(B, P, dtype=torch.uint8, device=dev)
+    ms = med(lambda: ops.splat_soft(xy, feats, mask, 256, 256))
+    res["splat"] = obj(f"splat_kernel + splat_normalize_kernel (creste_splat_soft), B={B}", B * 37.6e6, ms,
+                       "zero fill + red.global.add.v4.f32 accumulate + normalise to NHWC and NCHW")
+    del xy, feats, mask
+    # SVF: B=8, 256x256, T=50: pi read once (32 B/cell) + 40 B/cell/step in the reference formulation
+    Hm = Wm = 256
+    pol = torch.softmax(torch.randn(B, 8, Hm, Wm, generator=g), 1).to(dev)
+    exp_rc = torch.from_numpy(synth.expert_poses(B, 50, 2 * Hm, 2 * Wm, seed=1))[:, :, :2, 2].float().to(dev)
+    fov = torch.from_numpy(synth.trapezoid_fov_mask(2 * Hm, Wm)[:Hm, :Wm].copy()).to(dev)
+    ms = med(lambda: ops.svf(pol, exp_rc, fov, 50, 2, True, 0.005, False))
+    res["svf"] = obj(f"svf_kernel (creste_svf), B={B}, 256x256, T=50", B * Hm * Wm * (40.0 * 49 + 64.0), ms,
+                     "reference-formulation bytes (40 B/cell/step x 49 + sharpen 64 B/cell); the kernel keeps the "
+                     "(2T-1)^2 window in shared memory, so this is an equivalent rate")
+    del pol
+    # LiDAR raster: 131072 points -> 512x960 (3.5 MB)
+    pc = torch.from_numpy(synth.os1_scan(0)).to(dev)
+    P34 = synth.lidar2camrect(H, W)
+    ms = med(lambda: ops.lidar_raster(pc, P34, H, W, want_m=False))
+    res["lidar_raster"] = obj("lidar_project_kernel + lidar_finish_kernel (creste_lidar_raster), 131072 pts -> 512x960",
+                              131072 * 12.0 + H * W * 4.0, ms, "3 launches + a memset for 3.5 MB: launch-latency bound")
+    return res
+
+
+def vi_config0(dev):
+    """configs[0]: value iteration on ONE 64x64 grid, batch 1 -- GPU kernel next to the reference algorithm on the host
+    cores (C oracle), sweeps/s."""
+    import statistics as st
+    import numpy as np
+    import torch
+    from creste_public_b200 import ops
+    import synth_data as synth
+    r = synth.vi_inputs(0, 1, 64, 64)
+    rd = torch.from_numpy(r).to(dev)
+    for _ in range(3):
+        v, q, pi, info = ops.vi_solve(rd, 0.99, 1e-3)
+    ts = []
+    for _ in range(10):
+        a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        a.record()
+        v, q, pi, info = ops.vi_solve(rd, 0.99, 1e-3)
+        b.record()
+        torch.cuda.synchronize()
+        ts.append(a.elapsed_time(b))
+    K = int(info[0])
+    ms = st.median(ts)
+    out = {"workload": "configs[0]: VI on one 64x64 grid, B=1, gamma 0.99, thr 1e-3", "sweeps": K, "gpu_ms": ms,
+           "gpu_sweeps_per_s": K / (ms * 1e-3)}
+    try:
+        from oracle import c_oracle
+        c_oracle.vi_solve(r)
+        t0 = time.perf_counter()
+        v0, _, _, K0 = c_oracle.vi_solve(r)
+        dt = time.perf_counter() - t0
+        out.update({"cpu_ms": dt * 1e3, "cpu_sweeps_per_s": K0 / dt, "cpu_kind": "port (C oracle, %d thread(s))" % c_oracle.num_threads(),
+                    "bit_exact_vs_cpu": bool(K0 == K and np.array_equal(v.cpu().numpy()[:, 0].view(np.uint32), v0.view(np.uint32)))})
+    except Exception as e:  # noqa: BLE001
+        out["cpu_error"] = repr(e)[:120]
+    return out
+
+
+def captured_traffic(kernel_key, B, precision):
+    """DRAM bytes per launch of the roofline kernel from the committed `ncu --set full` capture of THIS kernel
+    version (profiles/roofline_traffic.json, written next to the capture's summary); None when the capture does not
+    match the benchmarked batch / precision."""
+    try:
+        with open(os.path.join(ROOT, "profiles", "roofline_traffic.json")) as f:
+            rec = json.load(f)[kernel_key]
+        if rec["batch"] == B and rec["precision"] == precision:
+            return rec["dram_bytes"], rec["source"]
+    except Exception:  # noqa: BLE001
+        pass
+    return None, None
+
+
 def run_reference(args):
     rank, local, world = dist_env()
     if rank != 0:
@@ -229,11 +391,8 @@ def run_irl_steps(args, dev, rank, world, barrier, Bi=8, Hm=256, Wm=256, steps=5
         ms = float(t)
     return {"metric": "IRL steps/sec @ 256x256", "value": 1e3 / ms, "unit": "steps/s",
             "samples_per_s": Bi * world * 1e3 / ms, "ms_per_step": ms,
-            "workload": f"configs[3] shard: counterfactual MaxEnt IRL head-only training step, "
-                        f"B={Bi}/GPU (global {Bi * world}), {Hm}x{Wm} reward grid: max-pool/crop -> "
-                        "reward FCN (train-mode BN, autograd) -> value iteration -> SVF + rollout -> "
-                        "MaxEntIRLLoss (double-backward gradient penalty) -> backward -> flat "
-                        "gradient all-reduce -> Adam",
+            "workload": f"configs[3] shard: counterfactual IRL head-only training step, B={Bi}/GPU "
+                        f"(global {Bi * world}), {Hm}x{Wm} grid (reward FCN fwd/bwd + VI + SVF + loss + all-reduce + Adam)",
             "vi_sweeps": int(model.traversability_head.last_vi_info[0]),
             "loss": float(loss), "gpu_launches_per_step": launches,
             "precision": args.precision}
@@ -272,9 +431,8 @@ def run_stage1_steps(args, dev, rank, world, barrier, Bi=16, H=512, W=960, steps
     flop = 3.0 * GFLOP_PER_FRAME * 1e9 * Bi
     res = {"metric": "stage-1 training frames/sec @ 512x960", "value": Bi * world * 1e3 / ms, "unit": "frames/s",
            "ms_per_step": ms, "frames_per_step_per_gpu": Bi,
-           "workload": f"configs[2] shard: distillation.yaml RGB-D backbone training step, B={Bi}/GPU "
-                       f"(global {Bi * world}), {H}x{W}: train-mode EfficientNet-B0 + U-Net + depth/dino heads -> "
-                       "3 losses -> backward -> flat gradient all-reduce -> Adam",
+           "workload": f"configs[2] shard: distillation.yaml backbone training step, B={Bi}/GPU (global {Bi * world}), "
+                       f"{H}x{W} (fwd + 3 losses + bwd + all-reduce + Adam)",
            "loss": float(out["loss"]), "gpu_launches_per_step": launches, "precision": args.precision,
            "achieved_tflops": flop / (ms * 1e-3) / 1e12,
            "peak_mem_gib": torch.cuda.max_memory_allocated() / 2 ** 30}
@@ -400,12 +558,12 @@ def run_ours(args):
         kms = statistics.median(a.elapsed_time(b_) for a, b_ in ev)
         flops = 2.0 * B * 128 * 240 * 496 * (9 * 496)
         ach = flops / (kms / 1e3) / 1e12
+        traffic, traffic_src = captured_traffic("up3_conv", B, args.precision)
         roof = {"kernel": "conv3x3 496->496 @128x240 (effnet up3.conv.3), precision=" + args.precision,
                 "bound": "tensor", "achieved": ach, "peak": peaks["bf16_sustained"], "unit": "TFLOP/s",
                 "frac": ach / peaks["bf16_sustained"],
-                # dram__bytes_read.sum + dram__bytes_write.sum of this launch from the committed
-                # `ncu --set full` capture (profiles/r1b_up3_conv_f16_full.md: B = 8, 3xfp16)
-                "traffic": 1.452e9 if (B == 8 and args.precision == "3xfp16") else None,
+                # dram__bytes_read.sum + dram__bytes_write.sum per launch, from the committed ncu capture
+                "traffic": traffic, "traffic_source": traffic_src,
                 "algorithmic_bytes": B * 128 * 240 * 496 * (2 * 2 + 4),
                 "peak_source": peaks["src"] + " bf16 sustained (cuBLAS)", "kernel_ms": kms,
                 "step_flop_share": round(136.04 / GFLOP_PER_FRAME, 3)}
@@ -445,6 +603,16 @@ def run_ours(args):
                        "sample": "1 step x 1 sample of the same 256x256 head-only IRL step (torch CPU "
                                  "reward FCN + double backward, C-oracle VI/SVF), all host threads",
                        "ms_per_sample": ms_irl_cpu}
+
+    gpu_eager = hbm = vi0 = None
+    if rank == 0:
+        hbm = hbm_kernel_rooflines(dev, peaks)
+        vi0 = vi_config0(dev)
+        if world == 1 and not args.no_eager:
+            try:
+                gpu_eager = gpu_eager_baseline(dev, B)
+            except Exception as e:  # noqa: BLE001
+                gpu_eager = {"error": repr(e)[:200]}
 
     # ---- B = 1 latency (the robot's operating point): eager launches vs one CUDA-graph replay
     latency = None
@@ -537,9 +705,16 @@ def run_ours(args):
             "e2e": {"value": e2e_value, "unit": "frames/s", "h2d_bytes_per_step": h2d,
                     "d2h_bytes_per_step": d2h, "ms_per_step": ms_e2e / args.steps},
             "gpu_launches": int(launches),
-            "clocks": clocks, "roofline": roof, "cpu_baseline": cpu, "irl": irl, "stage1": stage1,
-            "latency_b1": latency,
+            "clocks": clocks, "roofline": roof, "cpu_baseline": cpu,
+            # second / third metrics as top-level scalars (whole-job aggregates over all ranks)
+            "irl_steps_per_s": irl["value"] if irl else None,
+            "irl_samples_per_s": irl["samples_per_s"] if irl else None,
+            "stage1_fps": stage1["value"] if stage1 else None,
+            "vi_hbm_frac": vi_roof["frac"] if vi_roof else None,
+            "gpu_eager_fps": (gpu_eager or {}).get("default_flags", {}).get(f"b{B}", {}).get("fps"),
             "achieved_tflops_whole_step": GFLOP_PER_FRAME * 1e9 * value / world / 1e12,
+            "gpu_eager_baseline": gpu_eager, "irl": irl, "stage1": stage1, "hbm_kernels": hbm, "vi_64x64": vi0,
+            "latency_b1": latency,
         }
         print(json.dumps(line))
     if world > 1:
@@ -555,6 +730,7 @@ def main():
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--precision", default="3xfp16", choices=["fp32", "3xtf32", "3xfp16", "tf32"])
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
+    ap.add_argument("--no-eager", action="store_true", help="skip the gpu_eager_baseline leg")
     ap.add_argument("--no-irl", action="store_true", help="skip the IRL steps/s leg")
     ap.add_argument("--no-stage1", action="store_true", help="skip the stage-1 training frames/s leg")
     args = ap.parse_args()

@@ -17,7 +17,8 @@ EXPORTS = [
     "creste_vi_workspace_bytes", "creste_vi_solve",
     "creste_svf_workspace_bytes", "creste_svf",
     "creste_frustum_to_bev", "creste_camera_to_world", "creste_points_to_voxels", "creste_zmlp_concat",
-    "creste_splat_workspace_bytes", "creste_splat_soft",
+    "creste_splat_workspace_bytes", "creste_splat_soft", "creste_splat_bwd_workspace_bytes", "creste_splat_soft_bwd",
+    "creste_frustum_bwd", "creste_depth_expectation_bwd", "creste_dilate", "creste_phase_slice",
     "creste_lidar_raster", "creste_depth_expectation", "creste_bin_depths",
     "creste_conv2d", "creste_conv2d_workspace_bytes", "creste_conv2d_tc_supported",
     "creste_conv2d_tc_layout", "creste_conv2d_tc_debug",
@@ -74,7 +75,7 @@ def lib():
         L.creste_last_error.restype = C.c_char_p
         L.creste_launch_count.restype = C.c_ulonglong
         for name in ("creste_vi_workspace_bytes", "creste_svf_workspace_bytes",
-                     "creste_splat_workspace_bytes", "creste_conv2d_workspace_bytes",
+                     "creste_splat_workspace_bytes", "creste_splat_bwd_workspace_bytes", "creste_conv2d_workspace_bytes",
                      "creste_chan_dot_workspace_bytes", "creste_conv2d_wgrad_workspace_bytes",
                      "creste_grad_penalty_workspace_bytes", "creste_chan_reduce_workspace_bytes",
                      "creste_dwconv_wgrad_workspace_bytes", "creste_wgrad_strided_workspace_bytes",

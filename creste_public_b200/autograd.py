@@ -31,9 +31,16 @@ def _pad_last(t, mult=4):
     return torch.cat([t, t.new_zeros(*t.shape[:-1], r)], dim=-1).contiguous()
 
 
-def _conv_raw(x, w, ph, pw):
-    """Stride-1 conv of NHWC x with torch-layout weights w [K,C,R,S]; no epilogue.  Channel
-    counts that are not multiples of 4 are zero-padded (exact)."""
+def _pad4(ph, pw):
+    """(ph, pw) with each an int or a (low, high) pair -> (top, bottom, left, right)."""
+    t, b = (ph, ph) if isinstance(ph, int) else ph
+    l, r = (pw, pw) if isinstance(pw, int) else pw
+    return (int(t), int(b), int(l), int(r))
+
+
+def _conv_raw(x, w, ph, pw, stride=1):
+    """Conv of NHWC x with torch-layout weights w [K,C,R,S]; no epilogue.  Channel counts that are not
+    multiples of 4 are zero-padded (exact).  ph / pw: symmetric int or (low, high) pair."""
     K, Cc, R, S = w.shape
     xp = _pad_last(x)
     Cp = xp.shape[-1]
@@ -42,8 +49,8 @@ def _conv_raw(x, w, ph, pw):
     if Cp != Cc or Kp != K:
         wp = w.new_zeros(Kp, Cp, R, S)
         wp[:K, :Cc] = w
-    pad = (ph, ph, pw, pw)
-    mode = engine.pick_mode(tuple(xp.shape), Kp, R, S, 1, pad, engine.get_precision())
+    pad = _pad4(ph, pw)
+    mode = engine.pick_mode(tuple(xp.shape), Kp, R, S, stride, pad, engine.get_precision())
     if xp.shape[1] * xp.shape[2] < 16:
         mode = "fp32"      # squeeze-excite vectors [B,1,1,C]: a handful of rows, no tensor-core tile
     if mode == "fp32":
@@ -52,7 +59,7 @@ def _conv_raw(x, w, ph, pw):
         packed = ops.pack_conv_weight_f16_strided(wp.detach().float())      # one launch, strided read
     else:
         packed = ops.pack_conv_weight_tc(wp.detach().float(), split=(mode == "3xtf32"))
-    y = ops.conv2d(xp, packed, Kp, R, S, 1, pad, precision=mode)
+    y = ops.conv2d(xp, packed, Kp, R, S, stride, pad, precision=mode)
     return y if Kp == K else y[..., :K].contiguous()
 
 
@@ -65,7 +72,7 @@ def _wgrad_raw(x, g, R, S, ph, pw):
     64-channel slices of x and g (one extra pass over each tensor) and every (c, k) tile pair goes
     through the same kernel."""
     Cc, K = x.shape[-1], g.shape[-1]
-    pad = (ph, ph, pw, pw)
+    pad = _pad4(ph, pw)
     if R == 1 and S == 1 and x.numel() // Cc <= 64 and max(Cc, K) > WGRAD_TILE:
         return ops.wgrad_rows(x, g)          # squeeze-excite convs: [B,1,1,C] vectors, one launch
     if WGRAD_TC and engine.get_precision() != "fp32" and x.dim() == 4:
@@ -131,6 +138,126 @@ class WGradFn(Function):
         if ctx.needs_input_grad[1]:
             dg = Conv2dFn.apply(x, ggw, ph, pw)
         return dx, dg, None, None, None, None
+
+
+def _strided_dgrad(g, w, x_shape, stride, ph, pw):
+    """Data gradient of a strided conv: stride-1 conv of the zero-inserted output gradient with the flipped
+    weights (low pad R-1-pad, high pad chosen so that the result has the input's size)."""
+    N, H, W, _ = x_shape
+    _, P, Q, _ = g.shape
+    R, S = w.shape[2], w.shape[3]
+    Hz, Wz = stride * (P - 1) + 1, stride * (Q - 1) + 1
+    z = ops.dilate(g, stride, Hz, Wz)
+    return _conv_raw(z, _flip_t(w), (R - 1 - ph, H - Hz + ph), (S - 1 - pw, W - Wz + pw))
+
+
+def _strided_wgrad(x, g, R, S, stride, ph, pw):
+    """Weight gradient of a strided conv as stride-1 weight gradients over the stride^2 phase images:
+    tap r with r - pad = stride * i + a (0 <= a < stride) is tap i of the phase image x[a::stride]."""
+    N, H, W, Cc = x.shape
+    _, P, Q, K = g.shape
+    dw = torch.zeros(K, Cc, R, S, device=x.device, dtype=x.dtype)
+
+    def taps(n, pad, a):
+        rs = [r for r in range(n) if (r - pad) % stride == a]
+        return rs, [(r - pad - a) // stride for r in rs]
+    for a in range(stride):
+        rs, iis = taps(R, ph, a)
+        if not rs:
+            continue
+        for b in range(stride):
+            ss, jjs = taps(S, pw, b)
+            if not ss:
+                continue
+            Ri, Sj = iis[-1] - iis[0] + 1, jjs[-1] - jjs[0] + 1
+            pt, pl = -iis[0], -jjs[0]
+            xa = ops.phase_slice(x, stride, a, b, P + Ri - 1 - pt, Q + Sj - 1 - pl)
+            dwa = _wgrad_raw(xa, g, Ri, Sj, (pt, 0), (pl, 0))               # [K,C,Ri,Sj]
+            for r, i in zip(rs, iis):
+                for s_, j in zip(ss, jjs):
+                    dw[:, :, r, s_] = dwa[:, :, i - iis[0], j - jjs[0]]
+    return dw
+
+
+class StridedConvFn(Function):
+    """Dense conv with stride > 1 (the ResNet-18 BEV trunk's 7x7 / 3x3 / 1x1 stride-2 layers, reference
+    inpainting.py:80-90); first-order gradients only."""
+
+    @staticmethod
+    def forward(ctx, x, w, stride, ph, pw):
+        ctx.save_for_backward(x, w)
+        ctx.geom = (stride, ph, pw)
+        return _conv_raw(x, w, ph, pw, stride)
+
+    @staticmethod
+    @torch.autograd.function.once_differentiable
+    def backward(ctx, g):
+        x, w = ctx.saved_tensors
+        stride, ph, pw = ctx.geom
+        g = g.contiguous()
+        dx = _strided_dgrad(g, w, tuple(x.shape), stride, ph, pw) if ctx.needs_input_grad[0] else None
+        dw = _strided_wgrad(x, g, w.shape[2], w.shape[3], stride, ph, pw) if ctx.needs_input_grad[1] else None
+        return dx, dw, None, None, None
+
+
+class FrustumFn(Function):
+    """depth [M,Hs,Ws] (m) -> voxel coordinates xy [M,P,2], height z [M,P], bounds mask [M,P] (uint8, no
+    gradient): Camera2World + the bounds test + _points_to_voxels (splat_projection.py:19-51, :169, :175-189).
+    xy and z are affine in the depth, so the backward is one elementwise kernel."""
+
+    @staticmethod
+    def forward(ctx, depth, p2p, rng, vox):
+        xy, z, mask = ops.frustum_to_bev(depth, p2p, rng, vox)
+        ctx.save_for_backward(p2p)
+        ctx.geom = (tuple(depth.shape), vox)
+        ctx.mark_non_differentiable(mask)
+        return xy, z, mask
+
+    @staticmethod
+    @torch.autograd.function.once_differentiable
+    def backward(ctx, gxy, gz, _gmask):
+        (p2p,) = ctx.saved_tensors
+        shape, vox = ctx.geom
+        return ops.frustum_bwd(gxy, gz, p2p, shape, vox), None, None, None
+
+
+class SplatFn(Function):
+    """Bilinear BEV splat with mean normalisation (splat_projection.py:262-354) -> (bev NHWC [M,H,W,F],
+    densities [M,1,H,W]); differentiable w.r.t. the point features and the voxel coordinates."""
+
+    @staticmethod
+    def forward(ctx, xy, feats, mask, H, W, min_weight):
+        out = ops.splat_soft(xy, feats, mask, H, W, min_weight, want_nhwc=True, want_nchw=False)
+        ctx.save_for_backward(xy, feats, mask, out["bev_nhwc"], out["dens"])
+        ctx.min_weight = min_weight
+        return out["bev_nhwc"], out["dens"]
+
+    @staticmethod
+    @torch.autograd.function.once_differentiable
+    def backward(ctx, g_bev, g_dens):
+        xy, feats, mask, bev, dens = ctx.saved_tensors
+        dfeats, dxy = ops.splat_soft_bwd(xy, feats, mask, bev, dens, g_bev, g_dens, ctx.min_weight)
+        return dxy, dfeats.view_as(feats), None, None, None, None
+
+
+class DepthExpectFn(Function):
+    """Softmax expectation over the depth bins (depth_utils.py:300-313), logits NHWC [..., 128] -> [...]."""
+
+    @staticmethod
+    def forward(ctx, logits, dmin, dmax, out_div):
+        ctx.save_for_backward(logits)
+        ctx.cfg = (dmin, dmax, out_div)
+        return ops.depth_expectation(logits, dmin, dmax, out_div)[0]
+
+    @staticmethod
+    @torch.autograd.function.once_differentiable
+    def backward(ctx, g):
+        (logits,) = ctx.saved_tensors
+        return ops.depth_expectation_bwd(logits, g, *ctx.cfg), None, None, None
+
+
+def depth_expectation_nchw(logits_nchw, dmin, dmax, out_div=1000.0):
+    return DepthExpectFn.apply(ToNHWC.apply(logits_nchw.float()), dmin, dmax, out_div)
 
 
 class ChanAffineFn(Function):
@@ -349,10 +476,11 @@ class GradPenaltyFn(Function):
 def conv2d(x, conv):
     """nn.Conv2d parameters -> differentiable stride-1 NHWC conv (+ bias)."""
     stride = conv.stride[0] if isinstance(conv.stride, tuple) else conv.stride
-    if stride != 1:
-        raise NotImplementedError("differentiable conv path: stride 1 only (reward FCN)")
     ph, pw = conv.padding if isinstance(conv.padding, tuple) else (conv.padding,) * 2
-    y = Conv2dFn.apply(x, conv.weight, int(ph), int(pw))
+    if stride != 1:
+        y = StridedConvFn.apply(x, conv.weight, int(stride), int(ph), int(pw))     # first-order only
+    else:
+        y = Conv2dFn.apply(x, conv.weight, int(ph), int(pw))
     if conv.bias is not None:
         y = ChanAffineFn.apply(y, None, conv.bias, False)
     return y
@@ -573,17 +701,21 @@ class UpCatFn(Function):
 
     @staticmethod
     def forward(ctx, x, skip, sf):
-        if sf != 2:
-            raise NotImplementedError("training path: the decoder up-samples by exactly 2 at every stage")
-        ctx.cs = skip.shape[-1]
-        ctx.cx = x.shape[-1]
-        return ops.upsample_concat(skip, x, (2 * x.shape[1], 2 * x.shape[2]), 2)
+        if isinstance(sf, (tuple, list)) or int(sf) != sf:
+            raise NotImplementedError("training path: integer up-sampling factors only (2 in the RGB-D decoder, "
+                                      "4 in the BEV DeconvHeads)")
+        sf = int(sf)
+        ctx.cs, ctx.cx, ctx.sf = skip.shape[-1], x.shape[-1], sf
+        ctx.hw = (x.shape[1], x.shape[2])
+        return ops.upsample_concat(skip, x, (sf * x.shape[1], sf * x.shape[2]), sf)
 
     @staticmethod
     @once
     def backward(ctx, g):
         dskip = ops.chan_slice(g, 0, ctx.cs) if ctx.needs_input_grad[1] else None
-        dx = ops.upsample2_adjoint(ops.chan_slice(g, ctx.cs, ctx.cx)) if ctx.needs_input_grad[0] else None
+        dx = None
+        if ctx.needs_input_grad[0]:
+            dx = ops.upsample_adjoint(ops.chan_slice(g, ctx.cs, ctx.cx), ctx.hw[0], ctx.hw[1], 1.0 / ctx.sf)
         return dx, dskip, None
 
 

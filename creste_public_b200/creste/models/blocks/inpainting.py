@@ -35,7 +35,17 @@ class BasicBlock(nn.Module):
         if self.downsample is not None:
             object.__setattr__(self, "_fd", FusedConv(self.downsample[0], self.downsample[1]))
 
+    def forward_train(self, x):
+        """torchvision BasicBlock.forward in train mode (BatchNorm batch statistics) as an autograd graph."""
+        from creste_public_b200 import autograd as ag
+        out = ag.bn_act(ag.conv2d(x, self.conv1), self.bn1, "relu")
+        out = ag.bn_act(ag.conv2d(out, self.conv2), self.bn2, "none")
+        idt = x if self.downsample is None else ag.bn_act(ag.conv2d(x, self.downsample[0]), self.downsample[1], "none")
+        return ag.relu(ag.AddScaledFn.apply(out, idt, None))
+
     def forward_nhwc(self, x):
+        if self.training:
+            return self.forward_train(x)
         idt = self._fd(x) if self.downsample is not None else x
         return self._f2(self._f1(x, act="relu"), act="relu", residual=idt)
 
@@ -84,7 +94,15 @@ class DeconvHead(nn.Module):
         object.__setattr__(self, "_f_up2", FusedConv(self.up2[1], self.up2[2]))
         object.__setattr__(self, "_f_proj", FusedConv(self.proj, None))
 
+    def forward_train(self, x1, x2):
+        from creste_public_b200 import autograd as ag
+        x = self.up1.forward_train(x1, x2)
+        x = ag.bn_act(ag.conv2d(ag.Up2Fn.apply(x), self.up2[1]), self.up2[2], "relu")
+        return ag.conv2d(x, self.proj), x
+
     def forward_nhwc(self, x1, x2):
+        if self.training:
+            return self.forward_train(x1, x2)
         x = self.up1.forward_nhwc(x1, x2)
         N, H, W, _ = x.shape
         x = ops.upsample_concat(None, x, (2 * H, 2 * W), 2)
@@ -119,9 +137,13 @@ class InpaintingResNet18MultiHead(Inpainting):
         object.__setattr__(self, "_f_conv1", FusedConv(self.conv1, self.bn1))
 
     def forward_nhwc(self, bev_nhwc, want_nchw=True):
-        """Returns (reference-layout dict, {prefix: preds NHWC})."""
-        require_eval(self)
-        x = self._f_conv1(bev_nhwc, act="relu")
+        """Returns (reference-layout dict, {prefix: preds NHWC}).  In train mode every node is an autograd
+        Function over the sm_100a kernels (BatchNorm batch statistics, strided-conv gradients)."""
+        from creste_public_b200 import autograd as ag
+        if self.training:
+            x = ag.bn_act(ag.conv2d(bev_nhwc, self.conv1), self.bn1, "relu")
+        else:
+            x = self._f_conv1(bev_nhwc, act="relu")
         x1 = x
         for blk in self.layer1:
             x1 = blk.forward_nhwc(x1)
@@ -133,11 +155,14 @@ class InpaintingResNet18MultiHead(Inpainting):
             pred, fea = head.forward_nhwc(x, x1)
             preds_nhwc[prefix] = pred
             if want_nchw:
-                ret[f"{prefix}_preds"] = ops.nhwc_to_nchw(pred)
-                ret[f"{prefix}_features"] = ops.nhwc_to_nchw(fea)
+                to_nchw = ag.ToNCHW.apply if (pred.requires_grad or fea.requires_grad) else ops.nhwc_to_nchw
+                ret[f"{prefix}_preds"] = to_nchw(pred)
+                ret[f"{prefix}_features"] = to_nchw(fea)
         return ret, preds_nhwc
 
     def _forward(self, x):
-        ret, _ = self.forward_nhwc(ops.nchw_to_nhwc(x.float()))
+        from creste_public_b200 import autograd as ag
+        to_nhwc = ag.ToNHWC.apply if (x.requires_grad and torch.is_grad_enabled()) else ops.nchw_to_nhwc
+        ret, _ = self.forward_nhwc(to_nhwc(x.float()))
         return [dict(preds=ret[f"{p}_preds"], features=ret[f"{p}_features"])
                 for p in self.output_prefix]

@@ -72,9 +72,10 @@ class Camera2MapMulti(nn.Module):
     def forward_nhwc(self, depth, feats_nhwc, p2p, want_nchw=True):
         """depth [M,Hs,Ws] (m), feats NHWC [M,Hs,Ws,F], p2p [M,4,4]; NC == 1 (one camera per
         BEV map, `num_cams: 1` in the shipped configs)."""
-        require_eval(self)
         if self.NC != 1:
             raise NotImplementedError("num_cams != 1 is not used by the shipped configs")
+        if self.training:
+            return self.forward_train(depth, feats_nhwc, p2p, want_nchw)
         if self.z_proj[0].out_features != 64 or self.z_proj[2].out_features != 32:
             raise NotImplementedError("creste_zmlp_concat is specialised for z_embed_dim = 32")
         M, Hs, Ws, F = feats_nhwc.shape
@@ -135,6 +136,29 @@ class Camera2MapMulti(nn.Module):
             lambda: (l0.weight.detach().float().reshape(-1).contiguous(),
                      l0.bias.detach().float().contiguous(),
                      l2.weight.detach().float().contiguous(), l2.bias.detach().float().contiguous()))
+
+    def forward_train(self, depth, feats_nhwc, p2p, want_nchw=True):
+        """Train-mode splat as an autograd graph (reference :131-173, :191-260 under nn.Module.train(), stage 2):
+        frustum -> z-MLP (two 1x1 convs over the height channel) -> concat -> fusion conv + BatchNorm (batch
+        statistics) + ReLU -> bounds mask -> bilinear splat.  Gradients reach the image features, the z-MLP /
+        fusion parameters and -- through the voxel coordinates and z -- the predicted depth."""
+        from creste_public_b200 import autograd as ag
+        M, Hs, Ws, F = feats_nhwc.shape
+        rng, vox, grid = self._geom()
+        xy, z, mask = ag.FrustumFn.apply(depth.contiguous().float(), p2p.contiguous().float(), rng, vox)
+        l0, l2 = self.z_proj[0], self.z_proj[2]
+        zf = z.view(M, Hs, Ws, 1)
+        zf = ag.ChanAffineFn.apply(ag.Conv2dFn.apply(zf, l0.weight.view(l0.out_features, 1, 1, 1), 0, 0), None,
+                                   l0.bias, True)
+        zf = ag.ChanAffineFn.apply(ag.Conv2dFn.apply(zf, l2.weight.view(l2.out_features, l2.in_features, 1, 1), 0, 0),
+                                   None, l2.bias, True)
+        fused = self.vision_fusion.forward_nhwc(torch.cat([feats_nhwc, zf], dim=-1))       # BN batch statistics
+        Cf = fused.shape[-1]
+        bev_nhwc, dens = ag.SplatFn.apply(xy, fused.reshape(M, Hs * Ws, Cf), mask, grid[0], grid[1], self.min_weight)
+        ret = {"bev_densities": dens, "bev_coords": xy}
+        if want_nchw:
+            ret["bev_features"] = ag.ToNCHW.apply(bev_nhwc)
+        return ret, bev_nhwc
 
     def forward(self, x):
         assert len(x) >= 3, "Input must contain depth, features and camera projection matrix."

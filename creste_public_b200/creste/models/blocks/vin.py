@@ -49,16 +49,18 @@ class VIN(nn.Module):
             iv_nhwc, iv_nchw = ops.maxpool2_concat([p.detach() for p in preds_nhwc], rows_out=rows,
                                                    want_nchw=True)
         train_graph = torch.is_grad_enabled() and any(p.requires_grad for p in self.r.parameters())
-        if train_graph:
+        if train_graph or self.r.training:
             # reference vin.py:116-119: input_view is a detached leaf that requires grad, so the
-            # loss can take d(sum r)/d(input_view) (and differentiate it again w.r.t. the weights)
+            # loss can take d(sum r)/d(input_view) (and differentiate it again w.r.t. the weights).
+            # A train-mode head under no_grad (Lightning validation never does this, a user may) takes the
+            # same path without a graph: BatchNorm batch statistics, as nn.Module.train() implies.
             from creste_public_b200 import autograd as ag
-            iv_nchw.requires_grad_(True)
+            if train_graph:
+                iv_nchw.requires_grad_(True)
             r_nhwc = self.r.forward_autograd_nhwc(ag.ToNHWC.apply(iv_nchw))
             r = r_nhwc.view(N, 1, rows, Wo // ds)                   # C == 1: same memory as NCHW
             r_graph, r_nhwc = r, r_nhwc.detach()
         else:
-            require_eval(self)
             r_nhwc = self.r.forward_nhwc(iv_nhwc)                   # [N, rows, Wo/2, 1]
             r = r_nhwc.view(N, 1, rows, Wo // ds)
             r_graph = r

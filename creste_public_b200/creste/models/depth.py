@@ -44,10 +44,12 @@ class DepthCompletion(nn.Module):
         """Returns (outputs dict in the reference's NCHW layouts, nhwc dict for the parents)."""
         feats = self.vision_backbone.forward_nhwc(x_nhwc)
         logits = self.depth_head.forward_nhwc(feats)
-        # the soft-argmax depth and the arg-max bins are value-only outputs: no stage-1 loss of the
-        # shipped config differentiates them (SmoothL1Depth reads the int64 bins, loss_utils.py:530-573)
-        metric, bins = ops.depth_expectation(logits.detach(), float(self.discretize_cfg.depth_min),
-                                             float(self.discretize_cfg.depth_max))
+        dmin, dmax = float(self.discretize_cfg.depth_min), float(self.discretize_cfg.depth_max)
+        metric, bins = ops.depth_expectation(logits.detach(), dmin, dmax)
+        if logits.requires_grad and torch.is_grad_enabled():
+            # stage 2 differentiates the soft-argmax depth (SmoothL1Depth on depth_preds_metric and the splat's
+            # voxel coordinates, train_ssc.py:92-129); the arg-max bins stay a value
+            metric = ag.DepthExpectFn.apply(logits, dmin, dmax, 1000.0)
         out = {"depth_preds_metric": metric, "depth_preds_bins": bins}
         if want_nchw:
             to_nchw = ag.ToNCHW.apply if logits.requires_grad else ops.nhwc_to_nchw

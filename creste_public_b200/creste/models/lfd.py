@@ -106,10 +106,9 @@ class MaxEntIRL(nn.Module):
         return {"exp_svf": svf, "state_preds_grid": grid, "state_preds": states}
 
     def forward(self, inputs):
-        # The frozen backbone runs the fused inference engine (eval-mode BatchNorm).  The
-        # reference leaves the frozen backbone's BatchNorm layers in train mode unless a stage-3
-        # weights file was loaded (lfd.py:141-145); that quirk is refused loudly, not emulated.
-        require_eval(self.backbone)
+        # The frozen backbone follows its own .training flag like the reference: eval = the fused inference
+        # engine; train = batch-statistics BatchNorm + running-stat updates (what the reference does when no
+        # stage-3 weights file froze it, lfd.py:141-145) -- never with a graph (frozen: no_grad).
         image, p2p = inputs[0], inputs[1]
         with torch.no_grad():
             outputs, preds_nhwc = self.backbone.forward_full((image, p2p))

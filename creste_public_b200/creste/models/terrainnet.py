@@ -110,8 +110,12 @@ class TerrainNet(nn.Module):
 
     # ------------------------------------------------------------------ forward (terrainnet.py:272-350)
     def forward_full(self, x, want_nchw=True, want_dino=True):
-        """Returns (reference-layout dict, preds NHWC per head prefix)."""
-        require_eval(self)
+        """Returns (reference-layout dict, preds NHWC per head prefix).  Follows self.training like the
+        reference: eval = the fused inference engine (running statistics); train = the autograd graph over the
+        same kernels (BatchNorm batch statistics through backbone, splat and BEV decoder; stage 2)."""
+        if self.training and self.use_movability:
+            raise NotImplementedError("use_movability (double splat with movability masks) is False in every "
+                                      "shipped config")
         rgbd, p2p = x[:2]
         B, N, Cc, H, W = rgbd.shape
         x_nhwc = ops.nchw_to_nhwc(rgbd.reshape(B * N, Cc, H, W).float())

@@ -138,6 +138,67 @@ def splat_soft(xy, feats_nhwc, mask, H, W, min_weight=1.0, want_nhwc=True, want_
     return {"bev_nhwc": nhwc, "bev_nchw": nchw, "dens": dens, "idx": idx}
 
 
+def splat_soft_bwd(xy, feats_nhwc, mask, bev_nhwc, dens, g_bev_nhwc, g_dens, min_weight=1.0):
+    """Backward of splat_soft: -> (dfeats [N,P,F], dxy [N,P,2]).  bev_nhwc [N,H,W,F] / dens [N,1,H,W] are the
+    forward outputs, g_bev_nhwc / g_dens (None = 0) their gradients (reference autograd of :262-354)."""
+    xy, feats_nhwc = xy.contiguous().float(), feats_nhwc.contiguous().float()
+    N, P, _ = xy.shape
+    F = feats_nhwc.shape[-1]
+    _, H, W, _ = bev_nhwc.shape
+    dfeats = torch.empty(N, P, F, device=xy.device)
+    dxy = torch.empty(N, P, 2, device=xy.device)
+    n = lib().creste_splat_bwd_workspace_bytes(N, H, W)
+    ws = _ws(n, xy.device)
+    check(lib().creste_splat_soft_bwd(ptr(xy), ptr(feats_nhwc), ptr(mask), ptr(bev_nhwc.contiguous()),
+                                      ptr(dens.contiguous()), ptr(g_bev_nhwc.contiguous().float()),
+                                      ptr(None if g_dens is None else g_dens.contiguous().float()), N, P, F, H, W,
+                                      C.c_float(min_weight), ptr(dfeats), ptr(dxy), ptr(ws), C.c_size_t(n), stream()),
+          "creste_splat_soft_bwd")
+    return dfeats, dxy
+
+
+def frustum_bwd(dxy, dz, p2p, shape, voxel):
+    """-> d depth [N,Hs,Ws] from d xy [N,P,2] and / or d z [N,P] (either may be None)."""
+    N, Hs, Ws = shape
+    p2p = p2p.contiguous().float()
+    out = torch.empty(N, Hs, Ws, device=p2p.device)
+    vox = (C.c_float * 2)(float(voxel[0]), float(voxel[1]))
+    check(lib().creste_frustum_bwd(ptr(None if dxy is None else dxy.contiguous().float()),
+                                   ptr(None if dz is None else dz.contiguous().float()), ptr(p2p), N, Hs, Ws, vox,
+                                   ptr(out), stream()), "creste_frustum_bwd")
+    return out
+
+
+def depth_expectation_bwd(logits_nhwc, g_metric, dmin=300.0, dmax=25600.0, out_div=1000.0):
+    logits_nhwc = logits_nhwc.contiguous()
+    D = logits_nhwc.shape[-1]
+    NP = logits_nhwc.numel() // D
+    out = torch.empty_like(logits_nhwc)
+    check(lib().creste_depth_expectation_bwd(ptr(logits_nhwc), ptr(g_metric.contiguous().float()), NP, D,
+                                             C.c_float(dmin), C.c_float(dmax), C.c_float(out_div), ptr(out), stream()),
+          "creste_depth_expectation_bwd")
+    return out
+
+
+def dilate(g_nhwc, stride, Hz, Wz):
+    """Zero insertion: z[n, p*stride, q*stride, :] = g[n,p,q,:] on an [N,Hz,Wz,C] zero canvas."""
+    g_nhwc = g_nhwc.contiguous()
+    N, P, Q, Cc = g_nhwc.shape
+    z = torch.empty(N, Hz, Wz, Cc, device=g_nhwc.device)
+    check(lib().creste_dilate(ptr(g_nhwc), N, P, Q, Cc, int(stride), int(Hz), int(Wz), ptr(z), stream()), "creste_dilate")
+    return z
+
+
+def phase_slice(x_nhwc, stride, a, b, Ha, Wa):
+    """x[:, a::stride, b::stride, :] padded / cropped to [N,Ha,Wa,C] (zeros outside the image)."""
+    x_nhwc = x_nhwc.contiguous()
+    N, H, W, Cc = x_nhwc.shape
+    out = torch.empty(N, Ha, Wa, Cc, device=x_nhwc.device)
+    check(lib().creste_phase_slice(ptr(x_nhwc), N, H, W, Cc, int(stride), int(a), int(b), int(Ha), int(Wa), ptr(out),
+                                   stream()), "creste_phase_slice")
+    return out
+
+
 # --------------------------------------------------------------------------------------- LiDAR
 def lidar_raster(pc, P34, H, W, out_mm=None, want_m=True):
     """pc [n,>=3] fp32 CUDA; P34 [3,4] float64 (host array-like) -> depth_m [H,W], depth_mm [H,W]
@@ -446,6 +507,15 @@ def upsample2_adjoint(g_nhwc):
     check(lib().creste_upsample_adjoint(ptr(g_nhwc.contiguous()), N, Hi, Wi, Cc, Ho, Wo,
                                         C.c_float(0.5), C.c_float(0.5), ptr(dx), stream()),
           "creste_upsample_adjoint")
+    return dx
+
+
+def upsample_adjoint(g_nhwc, Hi, Wi, ratio):
+    """Adjoint of the bilinear up-sampling [N,Hi,Wi,C] -> [N,Ho,Wo,C] with sampling ratio `ratio` = 1 / scale."""
+    N, Ho, Wo, Cc = g_nhwc.shape
+    dx = torch.empty(N, Hi, Wi, Cc, device=g_nhwc.device)
+    check(lib().creste_upsample_adjoint(ptr(g_nhwc.contiguous()), N, Hi, Wi, Cc, Ho, Wo, C.c_float(ratio),
+                                        C.c_float(ratio), ptr(dx), stream()), "creste_upsample_adjoint")
     return dx
 
 

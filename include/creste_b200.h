@@ -106,6 +106,23 @@ size_t creste_splat_workspace_bytes(int N, int H, int W, int F);
 int creste_splat_soft(const float* xy, const float* feats, const uint8_t* mask, int N, int P, int F,
                       int H, int W, float min_weight, float* bev_nhwc, float* bev_nchw, float* dens,
                       int64_t* idx_out, void* ws, size_t ws_bytes, void* stream);
+/* Backward of creste_splat_soft (autograd of Camera2MapMulti.splat_soft, splat_projection.py:262-354, which the
+ * reference's stage-2 training step differentiates into the point features AND the voxel coordinates).
+ *   xy [N,P,2], feats NHWC [N,P,F], mask [N,P] (NULL = all valid): the forward inputs;
+ *   bev_nhwc [N,H,W,F], dens [N,H*W]: the forward outputs; g_bev_nhwc / g_dens (NULL = 0): their gradients;
+ *   dfeats [N,P,F] (0 for masked points), dxy [N,P,2] (floor has no gradient);
+ *   ws: >= creste_splat_bwd_workspace_bytes(N,H,W). */
+size_t creste_splat_bwd_workspace_bytes(int N, int H, int W);
+int creste_splat_soft_bwd(const float* xy, const float* feats, const uint8_t* mask, const float* bev_nhwc,
+                          const float* dens, const float* g_bev_nhwc, const float* g_dens, int N, int P, int F,
+                          int H, int W, float min_weight, float* dfeats, float* dxy, void* ws, size_t ws_bytes,
+                          void* stream);
+/* Backward of creste_frustum_to_bev w.r.t. the depth (xy and z are affine in it): autograd of
+ * Camera2World.forward + _points_to_voxels (splat_projection.py:19-51, :175-189).
+ *   dxy [N,P,2] and / or dz [N,P] (either may be NULL); voxel HOST float[2]; ddepth [N,Hs,Ws]. */
+int creste_frustum_bwd(const float* dxy, const float* dz, const float* p2p, int N, int Hs, int Ws,
+                       const float* voxel, float* ddepth, void* stream);
+
 
 /* ---------------------------------------------------------------------------------------------
  * LiDAR -> sparse depth raster.  Replaces pixels_to_depth, creste/utils/projection.py:64-134
@@ -132,6 +149,11 @@ int creste_depth_expectation(const float* logits, int NP, int D, float depth_min
  *   indices set to num_bins (target != 0).  Exactly one of out_f / out_i is written. */
 int creste_bin_depths(const float* depth, long long n, int mode, float depth_min, float depth_max,
                       int num_bins, int target, float* out_f, int64_t* out_i, void* stream);
+/* Backward of creste_depth_expectation w.r.t. the logits: d logit_k = g * softmax_k * (val_k - E) / out_div
+ * (autograd of convert_to_metric_depth_differentiable, depth_utils.py:300-313).  logits NHWC [NP,128]. */
+int creste_depth_expectation_bwd(const float* logits, const float* g_metric, int NP, int D, float depth_min_mm,
+                                 float depth_max_mm, float out_div, float* dlogits, void* stream);
+
 
 /* ---------------------------------------------------------------------------------------------
  * Convolution family (NHWC, fp32 storage).  One descriptor covers every dense conv / linear on
@@ -215,6 +237,15 @@ int creste_maxpool2_concat(const float* const* srcs_host, const int* chans_host,
 /* layout shuffles used at the module boundary (the reference's tensors are NCHW) */
 int creste_nchw_to_nhwc(const float* in, int N, int C, int H, int W, float* out, void* stream);
 int creste_nhwc_to_nchw(const float* in, int N, int H, int W, int C, float* out, void* stream);
+/* Layout helpers of the strided-convolution gradients (the stride-2 7x7 / 3x3 / 1x1 convs of the ResNet-18 BEV
+ * trunk, creste/models/blocks/inpainting.py:80-90, differentiated by the reference's stage-2 step):
+ *   creste_dilate       z [N,Hz,Wz,C] = 0 except z[n, p*stride, q*stride, :] = g[n,p,q,:]   (data gradient =
+ *                       stride-1 conv of the dilated output gradient with the flipped weights)
+ *   creste_phase_slice  out [N,Ha,Wa,C] = x[n, a + stride*i, b + stride*j, :], zero outside the image (weight
+ *                       gradient = stride-1 weight gradients over the stride^2 phase images).  C % 4 == 0. */
+int creste_dilate(const float* g, int N, int P, int Q, int C, int stride, int Hz, int Wz, float* z, void* stream);
+int creste_phase_slice(const float* x, int N, int H, int W, int C, int stride, int a, int b, int Ha, int Wa,
+                       float* out, void* stream);
 
 /* Expert / counterfactual visitation raster.  Replaces MaxEntIRLLoss.compute_expert_visitation,
  * creste/utils/loss_utils.py:1055-1116 (second definition).

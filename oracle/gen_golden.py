@@ -173,6 +173,7 @@ def main():
     stage1_loss_golden()
     distill_step_golden()
     bev_step_golden()
+    ssc_step_golden()
 
     # ---- full forward, tiny image, both depth profiles (lfd.py:314-330)
     for prof in ("peaky", "soft"):
@@ -238,6 +239,25 @@ def bev_step_golden():
         grad_l2=np.array([np.sqrt((ref["grads"][n].astype(np.float64) ** 2).sum()) for n in names]),
         preds0_sample=ref["preds0"][:, ::4, ::4, ::4],
         bn1_running_mean=ref["buffers"]["bn1.running_mean"],
+        **{"grad::" + n: ref["grads"][n] for n in full})
+
+
+def ssc_step_golden():
+    """Stage-2 graph: train-mode forward + backward of the UNMODIFIED reference TerrainNet (terrainnet.py:272-350)
+    on the seeded case of oracle/ssc_oracle.make_case: the scalar, the L2 norm of every gradient, three full
+    gradient tensors (z-MLP, fusion conv, the strided layer2 conv), the soft-argmax depth and a BEV sample."""
+    from . import ref_harness as rh
+    from . import ssc_oracle as so
+    model, _ = rh.build_ref_maxentirl(image_size=(64, 96))
+    template = {k[len("backbone."):]: v for k, v in model.state_dict().items() if k.startswith("backbone.")}
+    ref = so.reference_step(so.make_case(template))
+    names = sorted(ref["grads"])
+    full = ["cam2map.z_proj.2.weight", "cam2map.vision_fusion.convs.0.weight", "bevclassifier.layer2.0.conv1.weight"]
+    np.savez_compressed(
+        os.path.join(OUT, "ssc_step.npz"), loss=ref["loss"], grad_names=np.array(names),
+        grad_l2=np.array([np.sqrt((ref["grads"][n].astype(np.float64) ** 2).sum()) for n in names]),
+        depth_metric=ref["outputs"]["depth_preds_metric"], bev_sample=ref["samples"]["bev_features"][:, ::8],
+        bn_running_mean=ref["buffers"]["cam2map.vision_fusion.convs.1.running_mean"],
         **{"grad::" + n: ref["grads"][n] for n in full})
 
 

@@ -212,12 +212,24 @@ def test_forward_tensor_core_modes(cuda, mode):
     assert err <= 3 * yard + 1e-4, (err, yard)
 
 
-def test_training_mode_is_refused_loudly(cuda):
+def test_training_mode_follows_module_flag(cuda):
+    """model.train() switches the whole forward to batch-statistics BatchNorm (+ running-stat updates) like the
+    reference's modules do; model.eval() afterwards restores the inference engine and sees the updated statistics."""
     model, _ = _model("peaky")
+    rgbd, p2p = synth.net_inputs(H, W, 2)
+    with torch.no_grad():
+        ev = model((rgbd.cuda(), p2p.cuda()))["traversability_preds"].clone()
     model.train()
-    rgbd, p2p = synth.net_inputs(H, W, 1)
-    with pytest.raises(NotImplementedError):
-        model((rgbd.cuda(), p2p.cuda()))
+    bn = model.backbone.bevclassifier.bn1
+    before = bn.running_mean.clone()
+    with torch.no_grad():
+        tr = model((rgbd.cuda(), p2p.cuda()))["traversability_preds"].clone()
+    assert not torch.equal(before, bn.running_mean) and int(bn.num_batches_tracked) == 1
+    assert float((tr - ev).abs().max()) > 1e-4                      # batch statistics != running statistics
+    model.eval()
+    with torch.no_grad():
+        ev2 = model((rgbd.cuda(), p2p.cuda()))["traversability_preds"]
+    assert float((ev2 - ev).abs().max()) > 1e-6                     # the folded BatchNorm factors were rebuilt
 
 
 def test_irl_forward_solve_mdp(cuda):

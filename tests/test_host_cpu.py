@@ -75,7 +75,9 @@ def test_config_standin_and_model_surface():
     assert "backbone.depthcomp.depthcomp.vision_backbone.model.trunk._blocks.3._depthwise_conv.weight" in names
     assert "backbone.bevclassifier.out_heads.2.up2.1.weight" in names
     assert "traversability_head.r.trunk.4.conv.weight" in names
-    with pytest.raises(NotImplementedError):
+    # train mode is implemented (stage 2 / stage 3 semantics): on a CPU box it must reach the kernels and fail
+    # there -- never fall back to eager PyTorch
+    with pytest.raises(RuntimeError, match="CUDA"):
         m.train()
         m((torch.zeros(1, 1, 4, 64, 96), torch.eye(4).view(1, 1, 4, 4)))
 

@@ -1,0 +1,158 @@
+"""CPU tests of the stage-2 (train_ssc.py) training graph (-m "not gpu").
+
+The kernels only run on a GPU; here their torch stand-ins (tests/torch_backend.py) are patched in and the GRAPH --
+TerrainNet in train mode: RGB-D backbone, soft-argmax depth, frustum -> z-MLP -> fusion conv -> bilinear splat,
+ResNet-18 BEV decoder with its stride-2 convolutions and three DeconvHeads, every hand-written backward -- is
+checked against the oracle port (oracle/ssc_oracle.py), which is itself pinned bit for bit to the unmodified
+reference run in the build container, and against tests/golden/ssc_step.npz."""
+import numpy as np
+import pytest
+import torch
+
+from oracle import ref_shims
+from oracle import ssc_oracle as so
+import torch_backend as tb
+
+HAVE_REF = ref_shims.reference_available()
+
+
+def _template():
+    import creste_public_b200 as cb
+    return cb.build_terrainnet(image_size=(64, 96)).state_dict()
+
+
+@pytest.fixture(scope="module")
+def case():
+    return so.make_case(_template())
+
+
+@pytest.fixture(scope="module")
+def port(case):
+    return so.port_step(case)
+
+
+def ours_step(case, device=None):
+    """Train-mode forward + backward of the mirror TerrainNet on the oracle's scalar; same dict as port_step."""
+    import creste_public_b200 as cb
+    from creste_public_b200 import engine
+    m = cb.build_terrainnet(image_size=case["image_size"])
+    m.load_state_dict(case["state_dict"])
+    dev = torch.device(device) if device is not None else torch.device("cpu")
+    m = m.to(dev).train()
+    torch.manual_seed(case["seed"])
+    engine.drop_connect_rand = lambda B, d: torch.rand([B, 1, 1, 1]).reshape(B).to(d)      # the reference's CPU stream
+    try:
+        out = m((case["image"].clone().to(dev), case["p2p"].clone().to(dev), None))
+        total = so.scalar(out, case)
+        total.backward()
+    finally:
+        engine.drop_connect_rand = None
+    return {"loss": np.float64(total.detach().double().cpu()),
+            "grads": {k: p.grad.detach().cpu().numpy().copy() for k, p in m.named_parameters() if p.grad is not None},
+            "buffers": {k: v.detach().cpu().numpy().copy() for k, v in m.state_dict().items() if "running" in k},
+            "outputs": {k: out[k].detach().cpu().numpy().copy() for k in ("depth_preds_metric", "bev_densities")},
+            "keys": sorted(out.keys())}
+
+
+def compare(ours, ref, truth, loss_rtol=5e-3):
+    """The splat makes the graph ill-conditioned (a 1e-6 change of a depth moves a tap weight discontinuously past a
+    cell boundary; measured: the fp32 REFERENCE is 3 % (median relative L2) from the float64 evaluation of its own
+    graph), so gradients are held to the float64 yardstick: per tensor, relative L2 error against float64
+    <= max(3 x the reference's, 3e-2) -- any wrong backward formula exceeds that by an order of magnitude -- and the
+    median over the tensors <= 1.5 x the reference's median."""
+    np.testing.assert_allclose(ours["loss"], ref["loss"], rtol=loss_rtol)
+    assert abs(ours["loss"] - truth["loss"]) <= 3 * abs(ref["loss"] - truth["loss"]) + 1e-3 * abs(truth["loss"])
+    assert np.abs(ours["outputs"]["depth_preds_metric"] - ref["outputs"]["depth_preds_metric"]).max() <= 2e-4
+    assert set(ours["grads"]) == set(ref["grads"]) and len(ref["grads"]) == 330
+    rels, rels_ref, bad = [], [], []
+    for k, g0 in ref["grads"].items():
+        t = truth["grads"][k]
+        tn = np.sqrt((t ** 2).sum())
+        if tn < 1e-5:            # exact-zero gradients (biases in front of a BatchNorm): rounding noise only
+            assert np.abs(ours["grads"][k]).max() <= 1e-3 * max(1.0, np.abs(g0).max()) + 10 * np.abs(g0).max(), k
+            continue
+        r, r0 = np.sqrt(((ours["grads"][k] - t) ** 2).sum()) / tn, np.sqrt(((g0 - t) ** 2).sum()) / tn
+        rels.append(r)
+        rels_ref.append(r0)
+        if not r <= max(3 * r0, 3e-2):
+            bad.append((float(r), float(r0), k))
+    assert not bad, sorted(bad, reverse=True)[:10]
+    assert np.median(rels) <= 1.5 * np.median(rels_ref) + 1e-3, (np.median(rels), np.median(rels_ref))
+    for k, b0 in ref["buffers"].items():
+        np.testing.assert_allclose(ours["buffers"][k], b0, rtol=2e-3, atol=1e-4, err_msg=k)
+
+
+@pytest.mark.skipif(not HAVE_REF, reason="reference tree not present")
+def test_port_matches_reference(case, port):
+    ref = so.reference_step(case)
+    assert ref["loss"] == port["loss"]
+    assert len(ref["grads"]) == 330
+    for k, g in ref["grads"].items():
+        assert np.array_equal(g, port["grads"][k]), k
+    for k, b in ref["buffers"].items():
+        assert np.array_equal(b, port["buffers"][k]), k
+
+
+def test_port_matches_golden(port, golden):
+    """The port on THIS machine against the reference's outputs minted in the build container (oneDNN kernels differ
+    between CPUs by rounding, and the splat amplifies that: norms to 5 %, the well-conditioned part tightly)."""
+    g = golden("ssc_step.npz")
+    np.testing.assert_allclose(port["loss"], g["loss"], rtol=5e-3)
+    assert np.abs(port["outputs"]["depth_preds_metric"] - g["depth_metric"]).max() <= 2e-4
+    l2 = dict(zip(g["grad_names"].tolist(), g["grad_l2"]))
+    for k, v in port["grads"].items():
+        if l2[k] > 1e-4:
+            assert abs(np.sqrt((v.astype(np.float64) ** 2).sum()) - l2[k]) <= 0.08 * l2[k], k
+    for k in ("cam2map.z_proj.2.weight", "cam2map.vision_fusion.convs.0.weight", "bevclassifier.layer2.0.conv1.weight"):
+        ref = g["grad::" + k]
+        assert np.sqrt(((port["grads"][k] - ref) ** 2).sum()) <= 0.1 * np.sqrt((ref ** 2).sum()), k
+
+
+def test_graph_matches_port(case, port):
+    truth = so.port_step(case, torch.float64)
+    with tb.patched():
+        ours = ours_step(case)
+    compare(ours, port, truth)
+    for k in ("bev_features", "bev_densities", "bev_coords", "depth_preds_metric", "depth_preds_bins", "dino_pe_feats",
+              "inpainting_sam_preds", "inpainting_sam_dynamic_features", "elevation_preds"):
+        assert k in ours["keys"], k
+
+
+@pytest.mark.parametrize("C,K,R,stride,pad,H,W", [(8, 12, 7, 2, 3, 16, 20), (8, 16, 3, 2, 1, 16, 16),
+                                                  (8, 16, 1, 2, 0, 16, 16), (8, 8, 3, 2, 1, 15, 17),
+                                                  (8, 8, 3, 3, 1, 13, 16)])
+def test_strided_conv_gradient_decomposition(C, K, R, stride, pad, H, W):
+    """Data gradient = stride-1 conv of the zero-inserted output gradient with the flipped weights; weight gradient =
+    stride-1 weight gradients over the stride^2 phase images: exact (float64) against torch's autograd."""
+    from creste_public_b200 import autograd as ag
+    torch.manual_seed(0)
+    x = torch.randn(2, H, W, C, dtype=torch.float64, requires_grad=True)
+    w = torch.randn(K, C, R, R, dtype=torch.float64, requires_grad=True)
+    with tb.patched():
+        y = ag.StridedConvFn.apply(x, w, stride, pad, pad)
+        gy = torch.randn_like(y)
+        gx, gw = torch.autograd.grad(y, (x, w), gy)
+    xr, wr = x.detach().clone().requires_grad_(True), w.detach().clone().requires_grad_(True)
+    yr = torch.nn.functional.conv2d(xr.permute(0, 3, 1, 2), wr, stride=stride, padding=pad).permute(0, 2, 3, 1)
+    gxr, gwr = torch.autograd.grad(yr, (xr, wr), gy)
+    torch.testing.assert_close(y, yr, rtol=1e-12, atol=1e-12)
+    torch.testing.assert_close(gx, gxr, rtol=1e-12, atol=1e-12)
+    torch.testing.assert_close(gw, gwr, rtol=1e-12, atol=1e-12)
+
+
+def test_frozen_backbone_train_mode_runs_without_graph():
+    """Stage 3 with a backbone left in train mode (the reference when no stage-3 weights file froze it,
+    lfd.py:141-145): the forward uses batch statistics and updates the running statistics, without a graph."""
+    import creste_public_b200 as cb
+    from oracle import synth
+    m = cb.build_maxentirl(image_size=(64, 96))
+    m.load_state_dict(synth.seeded_state_dict(m.state_dict(), 0, "soft"))
+    m.backbone.train()
+    m.traversability_head.eval()
+    rgbd, p2p = synth.net_inputs(64, 96, 2)
+    bn = m.backbone.bevclassifier.bn1
+    before = bn.running_mean.clone()
+    with tb.patched(), torch.no_grad():
+        out = m.backbone((rgbd, p2p))
+    assert not torch.equal(before, bn.running_mean) and int(bn.num_batches_tracked) == 1
+    assert not out["inpainting_sam_preds"].requires_grad

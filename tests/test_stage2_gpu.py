@@ -1,0 +1,155 @@
+"""GPU parity of the stage-2 (train_ssc.py) surface: the splat backward kernel against the reference's autograd
+(golden splat_bwd.npz) and the float64 restatement, the frustum / soft-argmax-depth backward, strided-convolution
+gradients, the train-mode BEV decoder step (golden bev_step.npz + oracle port) and the whole train-mode TerrainNet
+graph against the oracle port with the float64 yardstick (see tests/test_stage2_cpu.py::compare)."""
+import numpy as np
+import pytest
+import torch
+
+from oracle import bev_oracle as bo
+from oracle import splat_bwd_oracle as sbo
+from oracle import ssc_oracle as so
+from test_stage2_cpu import compare, ours_step
+
+pytestmark = pytest.mark.gpu
+
+
+def _ops():
+    from creste_public_b200 import ops
+    return ops
+
+
+def test_splat_backward_matches_reference_golden(cuda, golden):
+    g = golden("splat_bwd.npz")
+    xy, feats = g["xy"], g["feats"]                                  # [N,P,2], [N,C,P]
+    H, W = int(g["grid"][0]), int(g["grid"][1])
+    N, Cc, P = feats.shape
+    rng = np.random.default_rng(int(g["g_seed"]))
+    G = rng.standard_normal((N, Cc, H * W)).astype(np.float32)
+    Gd = rng.standard_normal((N, H * W, 1)).astype(np.float32)
+    ops = _ops()
+    Cp = Cc + (-Cc) % 4
+    f = torch.zeros(N, P, Cp)
+    f[..., :Cc] = torch.from_numpy(feats).permute(0, 2, 1)
+    Gn = torch.zeros(N, H, W, Cp)
+    Gn[..., :Cc] = torch.from_numpy(G).view(N, Cc, H, W).permute(0, 2, 3, 1)
+    xyd, fd = torch.from_numpy(xy).cuda(), f.cuda()
+    fwd = ops.splat_soft(xyd, fd, None, H, W, 1.0, want_nhwc=True, want_nchw=False)
+    dfe, dxy = ops.splat_soft_bwd(xyd, fd, None, fwd["bev_nhwc"], fwd["dens"], Gn.cuda(),
+                                  torch.from_numpy(Gd).view(N, 1, H, W).cuda(), 1.0)
+    dfe = dfe.cpu()[..., :Cc].permute(0, 2, 1).numpy()
+    np.testing.assert_allclose(dfe, g["dfeats"], rtol=1e-4, atol=1e-5 * np.abs(g["dfeats"]).max())
+    np.testing.assert_allclose(dxy.cpu().numpy(), g["dxy"], rtol=1e-3, atol=2e-5 * np.abs(g["dxy"]).max())
+    d64, x64 = sbo.splat_backward(xy, feats, G, Gd[..., 0], H, W)
+    assert np.abs(dfe - d64).max() <= 1e-5 * np.abs(d64).max()
+    assert np.abs(dxy.cpu().numpy() - x64).max() <= 2e-5 * np.abs(x64).max()
+
+
+def test_splat_backward_masked_points(cuda):
+    """Masked points deposit density only: zero feature gradient, coordinate gradient from the density term."""
+    ops = _ops()
+    g = torch.Generator().manual_seed(3)
+    N, P, F, H, W = 1, 300, 8, 16, 16
+    xy = torch.rand(N, P, 2, generator=g) * 18 - 1                    # some taps fall outside the grid
+    feats = torch.randn(N, P, F, generator=g)
+    mask = (torch.rand(N, P, generator=g) > 0.3).to(torch.uint8)
+    Gb, Gd = torch.randn(N, H, W, F, generator=g), torch.randn(N, 1, H, W, generator=g)
+    fwd = ops.splat_soft(xy.cuda(), feats.cuda(), mask.cuda(), H, W, 1.0, want_nchw=False)
+    dfe, dxy = ops.splat_soft_bwd(xy.cuda(), feats.cuda(), mask.cuda(), fwd["bev_nhwc"], fwd["dens"], Gb.cuda(), Gd.cuda())
+    fm = (feats * mask.unsqueeze(-1)).permute(0, 2, 1).numpy()
+    d64, x64 = sbo.splat_backward(xy.numpy(), fm, Gb.permute(0, 3, 1, 2).reshape(N, F, -1).numpy(),
+                                  Gd.reshape(N, -1).numpy(), H, W)
+    want = torch.from_numpy(d64).permute(0, 2, 1).float() * mask.unsqueeze(-1)
+    assert float((dfe.cpu() - want).abs().max()) <= 1e-5 * float(want.abs().max())
+    assert float((dfe.cpu()[mask == 0]).abs().max()) == 0.0
+    assert np.abs(dxy.cpu().numpy() - x64).max() <= 2e-5 * np.abs(x64).max()
+
+
+def test_frustum_and_depth_expectation_backward(cuda):
+    import torch_backend as tb
+    from oracle import synth
+    ops = _ops()
+    g = torch.Generator().manual_seed(5)
+    M, Hs, Ws = 2, 16, 24
+    depth = torch.rand(M, Hs, Ws, generator=g) * 20 + 0.5
+    p2p = torch.from_numpy(synth.make_p2p(64, 96)).view(1, 4, 4).repeat(M, 1, 1)
+    dxy, dz = torch.randn(M, Hs * Ws, 2, generator=g), torch.randn(M, Hs * Ws, generator=g)
+    vox = [0.1, 0.1]
+    got = ops.frustum_bwd(dxy.cuda(), dz.cuda(), p2p.cuda(), (M, Hs, Ws), vox).cpu()
+    want = tb.frustum_bwd(dxy, dz, p2p, (M, Hs, Ws), vox)
+    assert float((got - want).abs().max()) <= 1e-5 * float(want.abs().max())
+    logits = torch.from_numpy(synth.depth_logits_inputs()).permute(0, 2, 3, 1).contiguous()
+    gm = torch.randn(logits.shape[:-1], generator=g)
+    got = ops.depth_expectation_bwd(logits.cuda(), gm.cuda()).cpu()
+    want = tb.depth_expectation_bwd(logits.double(), gm.double()).float()
+    assert float((got - want).abs().max()) <= 1e-5 * float(want.abs().max())
+
+
+@pytest.mark.parametrize("mode", ["fp32", "3xfp16"])
+@pytest.mark.parametrize("C,K,R,pad,H,W", [(96, 64, 7, 3, 64, 64), (64, 128, 3, 1, 32, 32), (64, 128, 1, 0, 32, 32),
+                                           (8, 16, 3, 1, 15, 17)])
+def test_strided_conv_gradients(cuda, mode, C, K, R, pad, H, W):
+    import creste_public_b200 as cb
+    from creste_public_b200 import autograd as ag
+    cb.set_precision(mode)
+    try:
+        torch.manual_seed(1)
+        x = torch.randn(2, H, W, C)
+        w = torch.randn(K, C, R, R) / (C * R * R) ** 0.5
+        xd, wd = x.cuda().requires_grad_(True), w.cuda().requires_grad_(True)
+        y = ag.StridedConvFn.apply(xd, wd, 2, pad, pad)
+        gy = torch.randn(y.shape)
+        gx, gw = torch.autograd.grad(y, (xd, wd), gy.cuda())
+    finally:
+        cb.set_precision("fp32")
+    xr, wr = x.double().requires_grad_(True), w.double().requires_grad_(True)
+    yr = torch.nn.functional.conv2d(xr.permute(0, 3, 1, 2), wr, stride=2, padding=pad).permute(0, 2, 3, 1)
+    gxr, gwr = torch.autograd.grad(yr, (xr, wr), gy.double())
+    tol = 2e-5 if mode == "fp32" else 5e-5
+    for a, b in ((y, yr), (gx, gxr), (gw, gwr)):
+        assert float((a.detach().cpu().double() - b).abs().max()) <= tol * float(b.abs().max())
+
+
+def test_bev_decoder_train_step_matches_port_and_golden(cuda, golden):
+    import creste_public_b200 as cb
+    from creste_public_b200.creste.models.blocks.inpainting import InpaintingResNet18MultiHead
+    cb.set_precision("fp32")
+    case = bo.make_case()
+    port = bo.port_step(case)
+    m = InpaintingResNet18MultiHead(96, list(bo.NUM_CLASSES), norm_layer="batch_norm", input_key="bev_features",
+                                    output_prefix=list(bo.PREFIXES))
+    m.load_state_dict(case["state_dict"])
+    m = m.cuda().train()
+    out = m({"bev_features": case["bev"].clone().cuda()})
+    loss = sum((out[f"{p}_preds"] * P.cuda()).sum() + 1e-2 * (out[f"{p}_features"] * Fw.cuda()).sum()
+               for p, P, Fw in zip(bo.PREFIXES, case["P"], case["F"]))
+    loss.backward()
+    g = golden("bev_step.npz")
+    np.testing.assert_allclose(float(loss), float(port["loss"]), rtol=2e-4)
+    np.testing.assert_allclose(float(loss), float(g["loss"]), rtol=2e-4)
+    l2 = dict(zip(g["grad_names"].tolist(), g["grad_l2"]))
+    grads = {k: p.grad.detach().cpu().numpy() for k, p in m.named_parameters() if p.grad is not None}
+    assert set(grads) == set(port["grads"])
+    for k, g0 in port["grads"].items():
+        n0 = np.sqrt((g0.astype(np.float64) ** 2).sum())
+        if n0 < 1e-4:
+            continue
+        err = np.sqrt(((grads[k] - g0).astype(np.float64) ** 2).sum())
+        assert err <= 2e-3 * n0, (k, err / n0)
+        assert abs(np.sqrt((grads[k].astype(np.float64) ** 2).sum()) - l2[k]) <= 5e-3 * l2[k], k
+    for k in ("layer2.0.conv1.weight", "layer2.0.downsample.0.weight"):
+        ref = g["grad::" + k]
+        assert np.abs(grads[k] - ref).max() <= 2e-3 * np.abs(ref).max(), k
+    np.testing.assert_allclose(m.bn1.running_mean.cpu().numpy(), g["bn1_running_mean"], rtol=1e-4, atol=1e-6)
+
+
+@pytest.mark.parametrize("mode", ["fp32", "3xfp16"])
+def test_terrainnet_train_graph_matches_port(cuda, mode):
+    import creste_public_b200 as cb
+    cb.set_precision(mode)
+    try:
+        case = so.make_case(cb.build_terrainnet(image_size=(64, 96)).state_dict())
+        ours = ours_step(case, "cuda")
+    finally:
+        cb.set_precision("fp32")
+    compare(ours, so.port_step(case), so.port_step(case, torch.float64))

@@ -77,17 +77,136 @@ def upsample2_adjoint(g):
     return _nhwc(dx)
 
 
-def conv_raw(x, w, ph, pw):
-    return _nhwc(F.conv2d(_nchw(x), w, padding=(ph, pw)))
+def _pad4(ph, pw):
+    t, b = (ph, ph) if isinstance(ph, int) else ph
+    l, r = (pw, pw) if isinstance(pw, int) else pw
+    return int(t), int(b), int(l), int(r)
+
+
+def _padded(xn, ph, pw):
+    t, b, l, r = _pad4(ph, pw)
+    return F.pad(xn, (l, r, t, b))
+
+
+def conv_raw(x, w, ph, pw, stride=1):
+    return _nhwc(F.conv2d(_padded(_nchw(x), ph, pw), w, stride=stride))
 
 
 def wgrad_raw(x, g, R, S, ph, pw):
     K, Cc = g.shape[-1], x.shape[-1]
     w = torch.zeros(K, Cc, R, S, dtype=x.dtype, requires_grad=True)
     with torch.enable_grad():
-        y = F.conv2d(_nchw(x), w, padding=(ph, pw))
+        y = F.conv2d(_padded(_nchw(x), ph, pw), w)
         (dw,) = torch.autograd.grad(y, w, _nchw(g))
     return dw
+
+
+# ------------------------------------------------------------ stage-2 stand-ins
+def dilate(g, stride, Hz, Wz):
+    N, P, Q, Cc = g.shape
+    z = torch.zeros(N, Hz, Wz, Cc, dtype=g.dtype)
+    z[:, : (P - 1) * stride + 1: stride, : (Q - 1) * stride + 1: stride] = g
+    return z
+
+
+def phase_slice(x, stride, a, b, Ha, Wa):
+    N, H, W, Cc = x.shape
+    out = torch.zeros(N, Ha, Wa, Cc, dtype=x.dtype)
+    src = x[:, a::stride, b::stride]
+    h, w = min(Ha, src.shape[1]), min(Wa, src.shape[2])
+    out[:, :h, :w] = src[:, :h, :w]
+    return out
+
+
+def upsample_adjoint(g, Hi, Wi, ratio):
+    N, Ho, Wo, Cc = g.shape
+    x = torch.zeros(N, Cc, Hi, Wi, dtype=g.dtype, requires_grad=True)
+    with torch.enable_grad():
+        y = F.interpolate(x, size=(Ho, Wo), mode="bilinear", align_corners=False)
+        (dx,) = torch.autograd.grad(y, x, _nchw(g))
+    return _nhwc(dx)
+
+
+def _frustum(depth, p2p, rng, vox):
+    M, Hs, Ws = depth.shape
+    u, v = torch.meshgrid(torch.arange(Ws), torch.arange(Hs), indexing="xy")
+    cam = torch.stack([u, v, torch.ones_like(u)], 0).unsqueeze(0).to(depth.dtype) * depth.view(M, 1, Hs, Ws)
+    cam = torch.cat([cam, torch.ones(M, 1, Hs, Ws, dtype=depth.dtype)], 1)
+    xyz = torch.bmm(p2p.to(depth.dtype), cam.flatten(2))[:, :3]                       # [M,3,P]
+    lo = torch.tensor(rng[:3], dtype=depth.dtype).view(1, 3, 1)
+    hi = torch.tensor(rng[3:], dtype=depth.dtype).view(1, 3, 1)
+    mask = ((xyz < hi) & (xyz >= lo)).all(dim=1)
+    xy = torch.stack([(-rng[0] - xyz[:, 1]) / vox[0], (-rng[1] - xyz[:, 0]) / vox[1]], dim=-1)
+    return xy, xyz[:, 2], mask.to(torch.uint8)
+
+
+def frustum_to_bev(depth, p2p, rng, vox):
+    xy, z, mask = _frustum(depth.detach(), p2p, rng, vox)
+    return xy.contiguous(), z.contiguous(), mask
+
+
+def frustum_bwd(dxy, dz, p2p, shape, voxel):
+    # xy / z are affine in depth: differentiate at an arbitrary point
+    d = torch.ones(shape, requires_grad=True)
+    with torch.enable_grad():
+        xy, z, _ = _frustum(d, p2p, [0.0] * 6, list(voxel) + [1.0])
+        tot = 0.0
+        if dxy is not None:
+            tot = tot + (xy * dxy).sum()
+        if dz is not None:
+            tot = tot + (z * dz).sum()
+        (g,) = torch.autograd.grad(tot, d)
+    return g
+
+
+def _splat(xy, feats, mask, H, W, min_weight):
+    """feats [N,P,F] -> (bev [N,H,W,F], dens [N,1,H,W]); masked points deposit density only."""
+    N, P, Fc = feats.shape
+    f = feats if mask is None else feats * mask.view(N, P, 1).to(feats.dtype)
+    XY = xy.detach().floor().long()
+    r = xy - XY.to(xy.dtype)
+    dens = torch.zeros(N, H * W, dtype=xy.dtype)
+    vol = torch.zeros(N, H * W, Fc, dtype=xy.dtype)
+    for dx in (0, 1):
+        wX = (1 - dx) + (2 * dx - 1) * r[..., 0]
+        for dy in (0, 1):
+            wY = (1 - dy) + (2 * dy - 1) * r[..., 1]
+            X_, Y_ = XY[..., 0] + dx, XY[..., 1] + dy
+            valid = (X_ >= 0) & (X_ < W) & (Y_ >= 0) & (Y_ < H)
+            idx = torch.where(valid, Y_ * W + X_, torch.zeros_like(X_))
+            w = wX * wY * valid.to(xy.dtype)
+            dens = dens.scatter_add(1, idx, w)
+            vol = vol.scatter_add(1, idx.unsqueeze(-1).expand(-1, -1, Fc), w.unsqueeze(-1) * f)
+    out = vol / dens.clamp(min=min_weight).unsqueeze(-1)
+    return out.view(N, H, W, Fc), dens.view(N, 1, H, W)
+
+
+def splat_soft(xy, feats_nhwc, mask, H, W, min_weight=1.0, want_nhwc=True, want_nchw=True, want_idx=False):
+    N, P, _ = xy.shape
+    bev, dens = _splat(xy, feats_nhwc.reshape(N, P, -1), mask, H, W, min_weight)
+    return {"bev_nhwc": bev.contiguous(), "bev_nchw": _nchw(bev) if want_nchw else None, "dens": dens, "idx": None}
+
+
+def splat_soft_bwd(xy, feats_nhwc, mask, bev_nhwc, dens, g_bev, g_dens, min_weight=1.0):
+    N, P, _ = xy.shape
+    _, H, W, _ = bev_nhwc.shape
+    x = xy.detach().clone().requires_grad_(True)
+    f = feats_nhwc.detach().reshape(N, P, -1).clone().requires_grad_(True)
+    with torch.enable_grad():
+        bev, d = _splat(x, f, mask, H, W, min_weight)
+        tot = (bev * g_bev).sum()
+        if g_dens is not None:
+            tot = tot + (d * g_dens).sum()
+        gx, gf = torch.autograd.grad(tot, (x, f))
+    return gf, gx
+
+
+def depth_expectation_bwd(logits_nhwc, g_metric, dmin=300.0, dmax=25600.0, out_div=1000.0):
+    l = logits_nhwc.detach().clone().requires_grad_(True)
+    with torch.enable_grad():
+        m = (torch.softmax(l, dim=-1) * torch.linspace(dmin, dmax, l.shape[-1])).sum(-1) / out_div
+        (g,) = torch.autograd.grad(m, l, g_metric)
+    return g
 
 
 def nchw_to_nhwc(x):
@@ -304,8 +423,13 @@ def pack_conv_weight(w):
 
 
 def upsample_concat(skip, x, out_hw, scale_factor=None, x_first=False):
-    up = upsample2(x)
-    return up if skip is None else torch.cat([skip, up], dim=-1)
+    if scale_factor is None:
+        up = _nhwc(F.interpolate(_nchw(x), size=tuple(out_hw), mode="bilinear", align_corners=False))
+    else:
+        up = _nhwc(F.interpolate(_nchw(x), scale_factor=scale_factor, mode="bilinear", align_corners=False))
+    if skip is None:
+        return up
+    return torch.cat([up, skip], dim=-1) if x_first else torch.cat([skip, up], dim=-1)
 
 
 def _bins(label_mm, D, dmin, dmax):
@@ -349,17 +473,19 @@ def masked_mse_bwd(pred, gt, scale_dev):
     return torch.where(valid, (pred - gt) * scale_dev.reshape(()), torch.zeros_like(pred))
 
 
-def depth_expectation(logits_nhwc, dmin=300.0, dmax=25600.0):
+def depth_expectation(logits_nhwc, dmin=300.0, dmax=25600.0, out_div=1000.0):
     D = logits_nhwc.shape[-1]
     p = torch.softmax(logits_nhwc, dim=-1)
     vals = torch.linspace(dmin, dmax, D)
-    return (p * vals).sum(-1) / 1000.0, logits_nhwc.argmax(-1)
+    return (p * vals).sum(-1) / out_div, logits_nhwc.argmax(-1)
 
 
 STAGE1_NAMES = ["bn_fwd_finalize", "bn_bwd_finalize", "chan_moments", "chan_affine_act", "bn_act_bwd", "chan_axpby", "dwconv_fwd", "dwconv_dgrad",
                 "dwconv_wgrad", "sample_dot", "sample_affine", "act", "act_bwd", "add_scaled", "chan_slice",
                 "wgrad_strided", "wgrad_rows", "conv2d", "pack_conv_weight", "upsample_concat", "stage1_depth_losses",
                 "ce_depth_bwd", "masked_mse", "masked_mse_bwd", "depth_expectation"]
+STAGE2_NAMES = ["dilate", "phase_slice", "upsample_adjoint", "frustum_to_bev", "frustum_bwd", "splat_soft",
+                "splat_soft_bwd", "depth_expectation_bwd"]
 
 
 @contextlib.contextmanager
@@ -370,7 +496,7 @@ def patched():
     names = ["chan_affine", "relu_bwd", "chan_dot", "chan_stats", "maxpool2", "maxpool2_bwd", "maxpool2_gather",
              "upsample2", "upsample2_adjoint", "nchw_to_nhwc", "nhwc_to_nchw", "row_dot",
              "row_scale", "row_normalize", "grad_penalty", "grad_penalty_bwd", "expert_visitation",
-             "adam_step"] + STAGE1_NAMES
+             "adam_step"] + STAGE1_NAMES + STAGE2_NAMES
     saved = {n: getattr(ops, n) for n in names}
     saved_ag = (ag._conv_raw, ag._wgrad_raw)
     try:

@@ -41,6 +41,8 @@ EXPORTS = [
     "creste_conv2d_wgrad_tc_supported", "creste_conv2d_wgrad_tc_workspace_bytes", "creste_conv2d_wgrad_tc",
     "creste_wgrad_rows", "creste_bn_fwd_finalize", "creste_bn_bwd_finalize",
     "creste_pack_weight_f16",
+    "creste_smooth_l1", "creste_smooth_l1_bwd", "creste_ce_weighted", "creste_ce_weighted_bwd",
+    "creste_l2norm_rows", "creste_l2norm_rows_bwd", "creste_supcon_fwd", "creste_supcon_bwd",
 ]
 
 

@@ -752,3 +752,75 @@ class MaskedMSEFn(Function):
         pred, gt, acc = ctx.saved_tensors
         scale = (2.0 * g.double() / acc[1]).float()
         return ops.masked_mse_bwd(pred, gt, scale), None
+
+
+# ============================================================================ stage-2 (train_ssc.py) losses
+class SmoothL1Fn(Function):
+    """mean Smooth-L1(pred - gt * gt_scale) over mask & isfinite(gt) (loss_utils.py:530-604)."""
+
+    @staticmethod
+    def forward(ctx, pred, gt, mask, gt_scale, beta):
+        acc = ops.smooth_l1(pred, gt, mask, gt_scale, beta)
+        ctx.save_for_backward(pred, gt, mask, acc)
+        ctx.cfg = (gt_scale, beta)
+        return (acc[0] / acc[1]).float()
+
+    @staticmethod
+    @once
+    def backward(ctx, g):
+        pred, gt, mask, acc = ctx.saved_tensors
+        scale = (g.double() / acc[1]).float()
+        return ops.smooth_l1_bwd(pred, gt, mask, ctx.cfg[0], ctx.cfg[1], scale).view_as(pred), None, None, None, None
+
+
+class WeightedCEFn(Function):
+    """torch.nn.CrossEntropyLoss(weight, ignore_index, reduction='mean') over the masked cells of NCHW logits
+    (loss_utils.py:379-474); `acc` is the float64[4] result of creste_ce_weighted."""
+
+    @staticmethod
+    def forward(ctx, logits, labels, mask, weights, ignore_index, acc):
+        ctx.save_for_backward(logits, labels, mask, weights, acc)
+        ctx.ignore_index = ignore_index
+        return (acc[0] / acc[1]).float()
+
+    @staticmethod
+    @once
+    def backward(ctx, g):
+        logits, labels, mask, weights, acc = ctx.saved_tensors
+        scale = (g.double() / acc[1]).float()
+        return ops.ce_weighted_bwd(logits, labels, mask, weights, ctx.ignore_index, scale), None, None, None, None, None
+
+
+class L2NormRowsFn(Function):
+    @staticmethod
+    def forward(ctx, x):
+        y, nrm = ops.l2norm_rows(x)
+        ctx.save_for_backward(y, nrm)
+        return y
+
+    @staticmethod
+    @once
+    def backward(ctx, g):
+        y, nrm = ctx.saved_tensors
+        return ops.l2norm_rows_bwd(y, g, nrm)
+
+
+class SupConFn(Function):
+    """Multi-positive contrastive loss (supcon_loss.py:56-115) of local rows `f` against the gathered rows `a`:
+    the N x Na similarity matrix is never materialised.  Returns the mean over the local rows; backward gives
+    d f (rows) and d a (columns) -- the caller's differentiable all-gather turns d a into a reduce-scatter."""
+
+    @staticmethod
+    def forward(ctx, f, a, lf, la, self_off, temperature, class_weights):
+        stats, acc = ops.supcon_fwd(f, a, lf, la, self_off, temperature, class_weights)
+        ctx.save_for_backward(f, a, lf, la, class_weights, stats)
+        ctx.cfg = (self_off, temperature)
+        return (acc[0] / f.shape[0]).float()
+
+    @staticmethod
+    @once
+    def backward(ctx, g):
+        f, a, lf, la, cw, stats = ctx.saved_tensors
+        scale = (g / f.shape[0]).float()
+        df, da = ops.supcon_bwd(f, a, lf, la, ctx.cfg[0], ctx.cfg[1], cw, stats, scale)
+        return df, da, None, None, None, None, None

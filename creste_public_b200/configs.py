@@ -44,6 +44,37 @@ def ssc_cfg(image_size=(512, 612)):
     }
 
 
+def ssc_train_cfg(image_size=(512, 612), class_weights=None):
+    """ssc_cfg + the training sections of terrainnet_supcon_sam2dynelev_jointdinopretrain.yaml (stage 2,
+    train_ssc.py): optimizer / scheduler / the six losses.  `class_weights`: path of the class-frequency text file
+    of the dynamic-object CrossEntropy (the reference ships it with its dataset; None = unweighted)."""
+    cfg = ssc_cfg(image_size)
+    disc = copy.deepcopy(DISCRETIZE)
+    ce = {"name": "CrossEntropy", "weight": 2.0, "pred_key": "outputs/inpainting_sam_dynamic_preds",
+          "lab_key": "inputs/3d_sam_dynamic_label", "num_class": 6, "class_dim": 1, "task": "joint"}
+    if class_weights is not None:
+        ce["class_weights"] = class_weights
+    cfg.update({
+        "batch_size": 8,
+        "optimizer": {"name": "Adam", "beta1": 0.9, "beta2": 0.999, "lr": 0.0005},
+        "lr_scheduler": {"name": "ExponentialLR", "gamma": 0.98},
+        "loss": [
+            {"name": "SupPixelConLoss", "views": 1, "weight": 1.0, "pred_key": "outputs/inpainting_sam_preds",
+             "lab_key": "inputs/3d_sam_label", "ignore_index": 0, "temperature": 0.1, "task": "joint",
+             "contrast_mode": "batch_all"},
+            ce,
+            {"name": "MSELoss", "weight": 2.0, "pred_key": "outputs/dino_pe_feats", "lab_key": "inputs/fimg_label",
+             "overlap_only": False},
+            {"name": "CrossEntropyDepth", "weight": 0.5, "pred_key": "outputs/depth_preds_logits",
+             "lab_key": "inputs/depth_label", "discretize": copy.deepcopy(disc)},
+            {"name": "SmoothL1Depth", "weight": 0.1, "pred_key": "outputs/depth_preds_metric",
+             "lab_key": "inputs/depth_label", "beta": 0.5, "discretize": copy.deepcopy(disc)},
+            {"name": "SmoothL1", "weight": 3.0, "beta": 0.2, "pred_key": "outputs/elevation_preds",
+             "lab_key": "inputs/elevation_label", "absolute": False, "task": "joint"},
+        ]})
+    return cfg
+
+
 def irl_cfg(image_size=(512, 612), map_size=(64, 128), solve_mdp=True, action_horizon=50):
     def stack(dims, kernels):
         return {"dims": dims, "kernels": kernels, "stride": [1] * len(kernels),

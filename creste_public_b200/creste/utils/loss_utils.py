@@ -7,7 +7,11 @@ creste_grad_penalty); the differentiable pieces are creste_public_b200.autograd 
 `loss.backward()` reaches the reward-FCN weights through the first- and second-order graph
 exactly as in the reference.  The stage-1 losses (CrossEntropyDepth, SmoothL1Depth, MSELoss) are one
 fused kernel pass for the values and creste_ce_depth_bwd / creste_masked_mse_bwd for the gradients
-(the Smooth-L1 term reads int64 bins and has none, as in the reference); stage-2 losses are not mirrored.
+(the Smooth-L1 term reads int64 bins and has none, as in the reference).  The stage-2 losses of
+configs/model/ssc_sam/*.yaml -- SupPixelConLoss (:203-286), CrossEntropy (:379-474), SmoothL1Depth on the
+differentiable soft-argmax depth, SmoothL1 (:576-604) -- are fused value + gradient kernels too (csrc/losses2.cu);
+the data-dependent pixel selection of SupPixelConLoss (valid-mask gather, per-class random subsampling) is index
+bookkeeping on the device, as in the reference.
 """
 import weakref
 
@@ -17,7 +21,9 @@ from torch import nn
 
 from creste_public_b200 import autograd as ag
 from creste_public_b200 import ops
+from ..models.losses.supcon_loss import MultiPosConLoss
 from . import train_utils as tu
+from . import utils
 
 
 class Loss(nn.Module):
@@ -68,7 +74,7 @@ class LossManager(nn.Module):
 
     def get_loss(self, config):
         if config["name"] not in globals():
-            raise NotImplementedError(f"loss {config['name']} is outside the stage-3 hot path")
+            raise NotImplementedError(f"loss {config['name']} is outside the hot path (SURVEY.md section 8)")
         return globals()[config["name"]](config)
 
 
@@ -80,7 +86,9 @@ class _Stage1DepthValues:
     @classmethod
     def get(cls, tensor_dict, discretize, beta):
         logits = tensor_dict["outputs/depth_preds_logits"]
-        bins = tensor_dict["outputs/depth_preds_bins"]
+        bins = tensor_dict.get("outputs/depth_preds_bins")
+        if bins is None:                       # a caller that hands over the logits alone: the bins ARE their arg-max
+            bins = logits.detach().argmax(dim=1)
         label = tensor_dict["inputs/depth_label"]
         key = (logits.data_ptr(), label.data_ptr(), logits._version, float(beta))
         # the cache is tied to the logits OBJECT (weak reference): a later step's logits may reuse the
@@ -124,19 +132,155 @@ class CrossEntropyDepth(Loss):
 
 
 class SmoothL1Depth(Loss):
-    """Reference loss_utils.py:530-573; pred_key is depth_preds_bins in the shipped config (int64
-    class indices compared with metres), so -- exactly as in the reference -- this term has a value
-    but contributes no gradient."""
+    """Reference loss_utils.py:530-573.  Stage 1 wires pred_key to depth_preds_bins (int64 class indices compared
+    with metres: a value without a gradient, exactly as in the reference); stage 2 wires it to the soft-argmax
+    depth_preds_metric, which IS differentiated (autograd.SmoothL1Fn over the valid LiDAR bins)."""
 
     def __init__(self, config):
         super().__init__(config.name if hasattr(config, "name") else config["name"], config)
         self.beta = config["beta"]
 
     def loss(self, tensor_dict):
-        if self.config["pred_key"] != "outputs/depth_preds_bins":
-            raise NotImplementedError("SmoothL1Depth is wired to depth_preds_bins in the shipped configs")
-        acc = _Stage1DepthValues.get(tensor_dict, self.config["discretize"], self.beta)
-        return {"depth/reg_loss": (acc[3] / acc[1]).float()}, {}
+        key = self.config["pred_key"]
+        if key == "outputs/depth_preds_bins":
+            acc = _Stage1DepthValues.get(tensor_dict, self.config["discretize"], self.beta)
+            return {"depth/reg_loss": (acc[3] / acc[1]).float()}, {}
+        pred = tensor_dict[key]                                         # [B*S, H, W] metres
+        gt = tensor_dict[self.config["lab_key"]]
+        B, S, H, W = gt.shape
+        if pred.shape[0] != B * S or tuple(pred.shape[-2:]) != (H, W):
+            raise NotImplementedError("multi-frame / resized depth labels are outside the hot path")
+        disc = self.config["discretize"]
+        gt = gt.reshape(B * S, H, W).to(pred.device).float().contiguous()
+        with torch.no_grad():
+            valid = ops.bin_depths(gt, disc["mode"], disc["depth_min"], disc["depth_max"], disc["num_bins"],
+                                   target=True) != int(disc["num_bins"])
+        if pred.requires_grad and torch.is_grad_enabled():
+            return {"depth/reg_loss": ag.SmoothL1Fn.apply(pred.contiguous(), gt, valid, 1e-3, float(self.beta))}, {}
+        acc = ops.smooth_l1(pred, gt, valid, 1e-3, float(self.beta))
+        return {"depth/reg_loss": (acc[0] / acc[1]).float()}, {}
+
+
+class SmoothL1(Loss):
+    """Reference loss_utils.py:576-604 (elevation regression): channel 1 of the target becomes relative to channel
+    0 IN PLACE unless `absolute` (the reference mutates its input the same way), non-finite targets are skipped."""
+
+    def __init__(self, config):
+        super().__init__(config.name if hasattr(config, "name") else config["name"], config)
+        self.beta = config["beta"]
+        self.pred_key, self.lab_key = config["pred_key"], config["lab_key"]
+        self.absolute = config.get("absolute", False)
+        if config.get("take_grad", False):
+            raise NotImplementedError("SmoothL1(take_grad=True) is unused by the shipped configs")
+
+    def loss(self, tensor_dict):
+        pred, gt = tensor_dict[self.pred_key], tensor_dict[self.lab_key]
+        if not self.absolute:
+            gt[:, 1, :, :] = gt[:, 1, :, :] - gt[:, 0, :, :]
+        g = gt.to(pred.device).float().contiguous()
+        if pred.requires_grad and torch.is_grad_enabled():
+            return {"val": ag.SmoothL1Fn.apply(pred.contiguous(), g, None, 1.0, float(self.beta))}, {}
+        acc = ops.smooth_l1(pred, g, None, 1.0, float(self.beta))
+        return {"val": (acc[0] / acc[1]).float()}, {}
+
+
+def _class_weights(config, eps=1e-5):
+    """1 / log(frequency + eps) from the text file named by config['class_weights'] (loss_utils.py:386-392)."""
+    freq = np.loadtxt(config["class_weights"])
+    return torch.from_numpy(1 / np.log(freq + eps)).float()
+
+
+class CrossEntropy(Loss):
+    """Reference loss_utils.py:379-474: class-weighted cross-entropy of the BEV logits over the FOV-masked cells
+    (+ the accuracy meta value over the cells whose label is not 0); one fused kernel pass each way."""
+
+    def __init__(self, config):
+        super().__init__(config.name if hasattr(config, "name") else config["name"], config)
+        self.num_class = config["num_class"]
+        self.epsilon_w = 1e-5
+        if "class_weights" in config:
+            self.register_buffer("class_weights", _class_weights(config, self.epsilon_w))
+            assert self.num_class == len(self.class_weights)
+        else:
+            self.class_weights = None
+        self.mask_key = config.get("mask_key", "inputs/fov_mask")
+        self.pred_key = config.get("pred_key", "outputs/inpainting_preds")
+        self.lab_key = config.get("lab_key", "inputs/sem_label")
+        self.ignore_index = config.get("ignore_index", None)
+        self.task = config.get("task", "3d_ssc")
+        self.class_dim = config.get("class_dim", -1)
+
+    def loss(self, tensor_dict):
+        pred = tensor_dict[self.pred_key]                               # [B,C,H,W]
+        gt = tensor_dict[self.lab_key]
+        with torch.no_grad():
+            if self.class_dim < 0:
+                gt_mode = torch.argmax(gt / (gt.sum(dim=1, keepdim=True) + self.epsilon_w), dim=1)
+            else:
+                gt_mode = gt[:, self.class_dim, :, :].long()
+            gt_mode = gt_mode.to(pred.device).contiguous()
+            mask = tensor_dict[self.mask_key].to(pred.device).to(torch.uint8).contiguous()
+        ign = -100 if self.ignore_index is None else int(self.ignore_index)
+        cw = None if self.class_weights is None else self.class_weights.to(pred.device)
+        acc = ops.ce_weighted(pred.detach(), gt_mode, mask, cw, ign)
+        if pred.requires_grad and torch.is_grad_enabled():
+            val = ag.WeightedCEFn.apply(pred.contiguous(), gt_mode, mask, cw, ign, acc)
+        else:
+            val = (acc[0] / acc[1]).float()
+        return {f"{self.task}/cls_loss": val}, {f"{self.task}/mIoU": (acc[2] / (acc[3] + self.epsilon_w)).float()}
+
+
+class SupPixelConLoss(Loss):
+    """Reference loss_utils.py:203-286: supervised pixel-contrastive loss on the BEV embedding head.  Labels are
+    made unique across the batch (SAM masks are per-frame ids), the valid (labelled & in-FOV) cells are gathered,
+    every class is randomly subsampled to the median class size (at most 1000), and the multi-positive contrastive
+    loss is evaluated over those embeddings (all-gathered across ranks)."""
+
+    def __init__(self, config):
+        super().__init__(config.name if hasattr(config, "name") else config["name"], config)
+        self.views = config.get("views", 1)
+        self.temperature = config.get("temperature", 0.1)
+        self.epsilon_w = 1e-5
+        if "class_weights" in config:
+            self.register_buffer("class_weights", _class_weights(config, self.epsilon_w))
+            self.num_class = config["num_class"]
+            assert self.num_class == len(self.class_weights)
+        else:
+            self.class_weights = None
+        self.supcon_loss = MultiPosConLoss(temperature=self.temperature, class_weights=self.class_weights)
+        self.ignore_index = config.get("ignore_index", -1)
+        self.mask_key = config.get("mask_key", "inputs/fov_mask")
+        self.pred_key = config.get("pred_key", "outputs/inpainting_preds")
+        self.lab_key = config.get("lab_key", "inputs/sem_label")
+        self.lab_suffix_key = self.lab_key.split("/")[-1]
+        self.task = config.get("task", "3d_ssc")
+        if self.views != 1:
+            raise NotImplementedError("views != 1 is unused by the shipped configs")
+
+    def loss(self, tensor_dict):
+        preds = tensor_dict[self.pred_key]                              # [B,Z,H,W]
+        gt_prob = tensor_dict[self.lab_key]
+        B, Z, H, W = preds.shape
+        with torch.no_grad():
+            fov = tensor_dict[self.mask_key].to(preds.device)
+            gt_label = (torch.argmax(gt_prob, dim=1) if gt_prob.shape[1] > 1 else gt_prob.squeeze(1)).to(preds.device)
+            if self.lab_key == "inputs/3d_sam_label":
+                gt_label = utils.remap_labels_in_batch(gt_label, ignore_idx=0)
+            valid = ((gt_label != self.ignore_index) & fov).view(B, H, W)
+            lab = gt_label.view(B, H, W)[valid]                         # [N]
+            counts = torch.bincount(lab)
+            nz = counts[counts.nonzero(as_tuple=True)].float()
+            median_count = min(nz.median().int(), 1000)
+            sel = tu.extract_max_per_class(lab, median_count, return_indices=True)
+            lab = lab[sel]
+            # flat cell index of every selected embedding in the [B,H,W] grid
+            cells = valid.reshape(-1).nonzero(as_tuple=False).reshape(-1)[sel]
+        # gather of the selected pixel embeddings: NCHW -> [N,Z] (torch index_select: differentiable plumbing)
+        flat = preds.permute(0, 2, 3, 1).reshape(B * H * W, Z)
+        feats = flat.index_select(0, cells)
+        out = self.supcon_loss({"feats": feats, "labels": lab})
+        base = f"{self.task}/{self.lab_suffix_key}/supcon"
+        return {f"{base}/sem_loss": out["loss"], f"{base}/img_loss": out["image_loss"]}, {}
 
 
 class MSELoss(Loss):

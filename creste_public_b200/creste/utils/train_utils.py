@@ -106,3 +106,17 @@ def get_save_paths(cfg, model_type="ssc", stage="train"):
     out = os.path.join(cfg["trainer"]["default_root_dir"], cfg["model"]["project_name"], run_name, day, clock)
     os.makedirs(out, exist_ok=True)
     return out
+
+
+def extract_max_per_class(tensor, max_per_class=100, return_indices=True):
+    """Up to `max_per_class` random members of every class of a 1-D label tensor (reference :324-352).  The random
+    subsets are drawn with torch.randperm from the DEFAULT (CPU) generator, class by class in ascending label
+    order -- the same draws as the reference's on the same seed."""
+    picked = []
+    for cls in torch.unique(tensor):
+        idx = (tensor == cls).nonzero(as_tuple=False).reshape(-1)
+        if idx.size(0) > max_per_class:
+            idx = idx[torch.randperm(idx.size(0))[:max_per_class].to(idx.device)]
+        picked.append(idx)
+    out = torch.cat(picked) if picked else torch.zeros(0, dtype=torch.long, device=tensor.device)
+    return out if return_indices else tensor[out]

@@ -1,0 +1,17 @@
+"""Hot-path helper of reference creste/utils/utils.py: remap_labels_in_batch (:59-77)."""
+import torch
+
+
+def remap_labels_in_batch(gt, ignore_idx=0):
+    """[B,H,W] integer labels -> labels that are unique ACROSS the batch: a label of sample b maps to (its rank
+    among ALL distinct labels of that sample, the ignore label included) + offset_b, where offset_b counts the
+    non-ignore labels of the earlier samples -- the reference's enumeration, ignore slot and all.  One torch.unique
+    + one bucketize per sample instead of the reference's per-label masked assignments (same result)."""
+    out = torch.full_like(gt, ignore_idx)
+    offset = 0
+    for b in range(gt.shape[0]):
+        labs = torch.unique(gt[b])
+        pos = torch.bucketize(gt[b], labs)                     # rank of each pixel's label in the sorted list
+        out[b] = torch.where(gt[b] != ignore_idx, pos + offset, out[b])
+        offset += int((labs != ignore_idx).sum())
+    return out

@@ -881,3 +881,94 @@ def pack_conv_weight_f16_strided(w):
     check(lib().creste_pack_weight_f16(C.c_void_p(w.data_ptr()), C.c_longlong(sK), C.c_longlong(sC), C.c_longlong(sR),
                                        C.c_longlong(sS), K, Cc, R, S, ptr(out), stream()), "creste_pack_weight_f16")
     return out
+
+
+# ------------------------------------------------------------------------- stage-2 loss kernels
+def _mask_ptr(mask):
+    return ptr(None if mask is None else mask.contiguous().to(torch.uint8))
+
+
+def smooth_l1(pred, gt, mask, gt_scale, beta):
+    """-> float64[2] device tensor {sum of smooth-L1(pred - gt * gt_scale), count} over mask & isfinite(gt)."""
+    pred, gt = pred.contiguous().float(), gt.contiguous().float()
+    assert pred.numel() == gt.numel()
+    acc = torch.empty(2, dtype=torch.float64, device=pred.device)
+    check(lib().creste_smooth_l1(ptr(pred), ptr(gt), _mask_ptr(mask), C.c_longlong(pred.numel()), C.c_float(gt_scale),
+                                 C.c_float(beta), ptr(acc), stream()), "creste_smooth_l1")
+    return acc
+
+
+def smooth_l1_bwd(pred, gt, mask, gt_scale, beta, scale_dev):
+    pred, gt = pred.contiguous().float(), gt.contiguous().float()
+    out = torch.empty_like(pred)
+    check(lib().creste_smooth_l1_bwd(ptr(pred), ptr(gt), _mask_ptr(mask), C.c_longlong(pred.numel()), C.c_float(gt_scale),
+                                     C.c_float(beta), ptr(scale_dev.reshape(1).float().contiguous()), ptr(out), stream()),
+          "creste_smooth_l1_bwd")
+    return out
+
+
+def ce_weighted(logits_nchw, labels, mask, class_weights, ignore_index=-100):
+    """-> float64[4] {sum w*nll, sum w, #correct over label != 0, #(label != 0)} over the masked cells."""
+    logits = logits_nchw.contiguous().float()
+    B, Cc = logits.shape[0], logits.shape[1]
+    HW = logits.numel() // (B * Cc)
+    acc = torch.empty(4, dtype=torch.float64, device=logits.device)
+    check(lib().creste_ce_weighted(ptr(logits), ptr(labels.contiguous().to(torch.int64)), _mask_ptr(mask),
+                                   ptr(None if class_weights is None else class_weights.contiguous().float()), B, Cc,
+                                   C.c_longlong(HW), C.c_longlong(int(ignore_index)), ptr(acc), stream()),
+          "creste_ce_weighted")
+    return acc
+
+
+def ce_weighted_bwd(logits_nchw, labels, mask, class_weights, ignore_index, scale_dev):
+    logits = logits_nchw.contiguous().float()
+    B, Cc = logits.shape[0], logits.shape[1]
+    HW = logits.numel() // (B * Cc)
+    out = torch.empty_like(logits)
+    check(lib().creste_ce_weighted_bwd(ptr(logits), ptr(labels.contiguous().to(torch.int64)), _mask_ptr(mask),
+                                       ptr(None if class_weights is None else class_weights.contiguous().float()), B, Cc,
+                                       C.c_longlong(HW), C.c_longlong(int(ignore_index)),
+                                       ptr(scale_dev.reshape(1).float().contiguous()), ptr(out), stream()),
+          "creste_ce_weighted_bwd")
+    return out
+
+
+def l2norm_rows(x, eps=1e-12):
+    x = x.contiguous().float()
+    N, D = x.shape
+    y, nrm = torch.empty_like(x), torch.empty(N, device=x.device)
+    check(lib().creste_l2norm_rows(ptr(x), N, D, C.c_float(eps), ptr(y), ptr(nrm), stream()), "creste_l2norm_rows")
+    return y, nrm
+
+
+def l2norm_rows_bwd(y, dy, nrm):
+    N, D = y.shape
+    dx = torch.empty_like(y)
+    check(lib().creste_l2norm_rows_bwd(ptr(y.contiguous()), ptr(dy.contiguous().float()), ptr(nrm), N, D, ptr(dx),
+                                       stream()), "creste_l2norm_rows_bwd")
+    return dx
+
+
+def supcon_fwd(f, a, lf, la, self_off, temperature, class_weights=None):
+    """-> (stats [N,4], loss_sum float64[1]); f [N,D] / a [Na,D] L2-normalised, lf / la int64 labels."""
+    f, a = f.contiguous().float(), a.contiguous().float()
+    N, D = f.shape
+    stats = torch.empty(N, 4, device=f.device)
+    acc = torch.empty(1, dtype=torch.float64, device=f.device)
+    check(lib().creste_supcon_fwd(ptr(f), ptr(a), ptr(lf.contiguous().to(torch.int64)), ptr(la.contiguous().to(torch.int64)),
+                                  N, a.shape[0], D, int(self_off), C.c_float(temperature),
+                                  ptr(None if class_weights is None else class_weights.contiguous().float()), ptr(stats),
+                                  ptr(acc), stream()), "creste_supcon_fwd")
+    return stats, acc
+
+
+def supcon_bwd(f, a, lf, la, self_off, temperature, class_weights, stats, scale_dev):
+    f, a = f.contiguous().float(), a.contiguous().float()
+    N, D = f.shape
+    df, da = torch.empty_like(f), torch.empty_like(a)
+    check(lib().creste_supcon_bwd(ptr(f), ptr(a), ptr(lf.contiguous().to(torch.int64)), ptr(la.contiguous().to(torch.int64)),
+                                  N, a.shape[0], D, int(self_off), C.c_float(temperature),
+                                  ptr(None if class_weights is None else class_weights.contiguous().float()),
+                                  ptr(stats.contiguous()), ptr(scale_dev.reshape(1).float().contiguous()), ptr(df), ptr(da),
+                                  stream()), "creste_supcon_bwd")
+    return df, da

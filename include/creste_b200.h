@@ -416,6 +416,42 @@ int creste_conv2d_wgrad_tc(const creste_conv_desc* d, const float* x, const floa
 int creste_pack_weight_f16(const float* w, long long sK, long long sC, long long sR, long long sS, int K, int C,
                            int R, int S, float* out, void* stream);
 
+/* ---------------------------------------------------------------------------------------------
+ * Stage-2 (train_ssc.py) losses: values and gradients.
+ *
+ * creste_smooth_l1: masked Smooth-L1 mean -- SmoothL1Depth on the soft-argmax depth (loss_utils.py:530-573:
+ *   mask = valid LiDAR bins, gt_scale = 1/1000) and SmoothL1 on the elevation head (:576-604: mask NULL, non-finite
+ *   targets skipped).  acc2 = DEVICE double {sum, count}; the backward writes scale * d smoothl1 / d pred.
+ * creste_ce_weighted: class-weighted cross-entropy over masked cells (CrossEntropy, :379-474).  logits NCHW
+ *   [B,C,HW], labels int64 [B,HW], mask uint8 [B,HW] (NULL = all), class_weights [C] (NULL = 1).
+ *   acc4 = DEVICE double {sum w*nll, sum w, #argmax == label over label != 0, #(label != 0)}.
+ * creste_supcon_*: multi-positive contrastive loss over L2-normalised embeddings (SupPixelConLoss :203-286 ->
+ *   MultiPosConLoss, creste/models/losses/supcon_loss.py:56-115).  f [N,D] local rows, a [Na,D] all-gathered rows
+ *   (row i of f is row i + self_off of a), labels int64; stats4 [N,4] float (row max, sum exp, #positives, sum of
+ *   positive logits) is written by the forward and read by the backward; loss_sum = DEVICE double (sum over rows;
+ *   the loss is loss_sum / N); df [N,D], da [Na,D] (the caller reduce-scatters da across ranks: the backward of
+ *   torch.distributed.nn.all_gather).  D in {4, 8, 16, 32, 64, 128}.
+ * creste_l2norm_rows: F.normalize(x, dim=-1) and its backward. */
+int creste_smooth_l1(const float* pred, const float* gt, const uint8_t* mask, long long n, float gt_scale,
+                     float beta, double* acc2, void* stream);
+int creste_smooth_l1_bwd(const float* pred, const float* gt, const uint8_t* mask, long long n, float gt_scale,
+                         float beta, const float* scale_dev, float* dpred, void* stream);
+int creste_ce_weighted(const float* logits_nchw, const int64_t* labels, const uint8_t* mask,
+                       const float* class_weights, int B, int C, long long HW, long long ignore_index, double* acc4,
+                       void* stream);
+int creste_ce_weighted_bwd(const float* logits_nchw, const int64_t* labels, const uint8_t* mask,
+                           const float* class_weights, int B, int C, long long HW, long long ignore_index,
+                           const float* scale_dev, float* dlogits, void* stream);
+int creste_l2norm_rows(const float* x, int N, int D, float eps, float* y, float* norms, void* stream);
+int creste_l2norm_rows_bwd(const float* y, const float* dy, const float* norms, int N, int D, float* dx,
+                           void* stream);
+int creste_supcon_fwd(const float* f, const float* a, const int64_t* lf, const int64_t* la, int N, int Na, int D,
+                      int self_off, float temperature, const float* class_weights, float* stats4, double* loss_sum,
+                      void* stream);
+int creste_supcon_bwd(const float* f, const float* a, const int64_t* lf, const int64_t* la, int N, int Na, int D,
+                      int self_off, float temperature, const float* class_weights, const float* stats4,
+                      const float* scale_dev, float* df, float* da, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

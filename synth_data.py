@@ -240,3 +240,28 @@ def distill_batch(B, H, W, seed=0, Z=128):
     lab = lab * (torch.rand(B, 1, H // 4, W // 4, generator=g) >= 0.2)
     fimg = torch.randn(B, 1, Z, H // 4, W // 4, generator=g)
     return {"image": torch.cat([rgb, depth], dim=2), "depth_label": lab, "fimg_label": fimg}
+
+
+def ssc_batch(B, H, W, seed=0, G=256):
+    """Synthetic stage-2 (train_ssc.py) batch, shapes of the reference's CODa loader: RGB-D image + p2p, the stage-1
+    labels (sparse LiDAR depth at 1/4 resolution, DINO feature targets) and the BEV labels on the G x G grid -- SAM
+    mask ids (blocky regions, 0 = unlabeled), dynamic-object classes in channel 1, (min, max) elevation with
+    unobserved (NaN) cells, and a trapezoidal FOV mask."""
+    import torch
+    g = np.random.default_rng(4200 + seed)
+    batch = distill_batch(B, H, W, seed)
+    batch["p2p"] = torch.from_numpy(make_p2p(H, W)).view(1, 1, 4, 4).repeat(B, 1, 1, 1)
+    cell = G // 16
+    ids = g.integers(0, 12, (B, 16, 16))
+    sam = np.repeat(np.repeat(ids, cell, axis=1), cell, axis=2)
+    batch["3d_sam_label"] = torch.from_numpy(sam[:, None].astype(np.int64))
+    dyn = np.zeros((B, 2, G, G), np.float32)
+    dyn[:, 1] = np.repeat(np.repeat(g.integers(0, 6, (B, 32, 32)), G // 32, axis=1), G // 32, axis=2)
+    batch["3d_sam_dynamic_label"] = torch.from_numpy(dyn)
+    elev = g.standard_normal((B, 2, G, G)).astype(np.float32) * 0.3
+    elev[:, 1] = elev[:, 0] + np.abs(elev[:, 1])
+    elev[g.random((B, 2, G, G)) < 0.3] = np.nan
+    batch["elevation_label"] = torch.from_numpy(elev)
+    fov = trapezoid_fov_mask(G, G, 70, 70, 7, 200)
+    batch["fov_mask"] = torch.from_numpy(np.broadcast_to(np.asarray(fov, bool), (B, G, G)).copy())
+    return batch

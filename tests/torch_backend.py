@@ -480,12 +480,112 @@ def depth_expectation(logits_nhwc, dmin=300.0, dmax=25600.0, out_div=1000.0):
     return (p * vals).sum(-1) / out_div, logits_nhwc.argmax(-1)
 
 
+# ------------------------------------------------------------ stage-2 loss stand-ins
+def bin_depths(depth, mode, depth_min, depth_max, num_bins, target=False):
+    assert mode == "UD"
+    idx = (depth - depth_min) / ((depth_max - depth_min) / num_bins)
+    if not target:
+        return idx
+    bad = (idx < 0) | (idx > num_bins) | ~torch.isfinite(idx)
+    return torch.where(bad, torch.full_like(idx, float(num_bins)), idx).long()
+
+
+def _sl1_valid(gt, mask):
+    v = torch.isfinite(gt)
+    return v if mask is None else v & mask.bool().view_as(gt)
+
+
+def smooth_l1(pred, gt, mask, gt_scale, beta):
+    v = _sl1_valid(gt, mask)
+    l = F.smooth_l1_loss(pred[v], gt[v] * gt_scale, beta=beta, reduction="sum")
+    return torch.stack([l.double(), v.sum().double()])
+
+
+def smooth_l1_bwd(pred, gt, mask, gt_scale, beta, scale_dev):
+    v = _sl1_valid(gt, mask)
+    p = pred.detach().clone().requires_grad_(True)
+    with torch.enable_grad():
+        l = F.smooth_l1_loss(p[v], gt[v] * gt_scale, beta=beta, reduction="sum")
+        (g,) = torch.autograd.grad(l, p)
+    return g * scale_dev.reshape(())
+
+
+def _ce_terms(logits, labels, mask, weights, ignore_index):
+    B, Cc = logits.shape[0], logits.shape[1]
+    flat = logits.reshape(B, Cc, -1).permute(0, 2, 1).reshape(-1, Cc)
+    lab = labels.reshape(-1)
+    m = torch.ones_like(lab, dtype=torch.bool) if mask is None else mask.reshape(-1).bool()
+    return flat, lab, m
+
+
+def ce_weighted(logits, labels, mask, weights, ignore_index=-100):
+    flat, lab, m = _ce_terms(logits, labels, mask, weights, ignore_index)
+    live = m & (lab != ignore_index)
+    w = torch.ones(flat.shape[1]) if weights is None else weights
+    nll = F.cross_entropy(flat[live], lab[live], weight=w, reduction="sum")
+    nz = m & (lab != 0)
+    ok = (flat[nz].argmax(1) == lab[nz]).sum()
+    return torch.stack([nll.double(), w[lab[live]].sum().double(), ok.double(), nz.sum().double()])
+
+
+def ce_weighted_bwd(logits, labels, mask, weights, ignore_index, scale_dev):
+    l = logits.detach().clone().requires_grad_(True)
+    with torch.enable_grad():
+        flat, lab, m = _ce_terms(l, labels, mask, weights, ignore_index)
+        live = m & (lab != ignore_index)
+        w = torch.ones(flat.shape[1]) if weights is None else weights
+        nll = F.cross_entropy(flat[live], lab[live], weight=w, reduction="sum")
+        (g,) = torch.autograd.grad(nll, l)
+    return g * scale_dev.reshape(())
+
+
+def l2norm_rows(x, eps=1e-12):
+    n = x.norm(dim=1).clamp_min(eps)
+    return x / n.unsqueeze(1), n
+
+
+def l2norm_rows_bwd(y, dy, nrm):
+    return (dy - y * (y * dy).sum(1, keepdim=True)) / nrm.unsqueeze(1)
+
+
+def _supcon_rows(f, a, lf, la, self_off, temperature, cw):
+    N, Na = f.shape[0], a.shape[0]
+    logits = f @ a.t() / temperature
+    notself = torch.ones(N, Na, dtype=torch.bool)
+    notself[torch.arange(N), torch.arange(N) + self_off] = False
+    pos = (lf.view(-1, 1) == la.view(1, -1)) & notself
+    logits = logits.masked_fill(~notself, -1e9)
+    logp = torch.log_softmax(logits, dim=1)
+    p = pos.float() / pos.sum(1, keepdim=True).clamp(min=1.0)
+    li = -(p * logp).sum(1)
+    if cw is not None:
+        li = li * cw[lf]
+    return li, logits, pos
+
+
+def supcon_fwd(f, a, lf, la, self_off, temperature, class_weights=None):
+    li, logits, pos = _supcon_rows(f, a, lf, la, self_off, temperature, class_weights)
+    m = logits.max(1).values
+    stats = torch.stack([m, torch.exp(logits - m.unsqueeze(1)).sum(1), pos.sum(1).float(),
+                         (logits * pos).sum(1)], dim=1)
+    return stats, li.sum().double().reshape(1)
+
+
+def supcon_bwd(f, a, lf, la, self_off, temperature, class_weights, stats, scale_dev):
+    ff, aa = f.detach().clone().requires_grad_(True), a.detach().clone().requires_grad_(True)
+    with torch.enable_grad():
+        li, _, _ = _supcon_rows(ff, aa, lf, la, self_off, temperature, class_weights)
+        df, da = torch.autograd.grad(li.sum(), (ff, aa))
+    return df * scale_dev.reshape(()), da * scale_dev.reshape(())
+
+
 STAGE1_NAMES = ["bn_fwd_finalize", "bn_bwd_finalize", "chan_moments", "chan_affine_act", "bn_act_bwd", "chan_axpby", "dwconv_fwd", "dwconv_dgrad",
                 "dwconv_wgrad", "sample_dot", "sample_affine", "act", "act_bwd", "add_scaled", "chan_slice",
                 "wgrad_strided", "wgrad_rows", "conv2d", "pack_conv_weight", "upsample_concat", "stage1_depth_losses",
                 "ce_depth_bwd", "masked_mse", "masked_mse_bwd", "depth_expectation"]
 STAGE2_NAMES = ["dilate", "phase_slice", "upsample_adjoint", "frustum_to_bev", "frustum_bwd", "splat_soft",
-                "splat_soft_bwd", "depth_expectation_bwd"]
+                "splat_soft_bwd", "depth_expectation_bwd", "bin_depths", "smooth_l1", "smooth_l1_bwd", "ce_weighted",
+                "ce_weighted_bwd", "l2norm_rows", "l2norm_rows_bwd", "supcon_fwd", "supcon_bwd"]
 
 
 @contextlib.contextmanager

@@ -441,6 +441,48 @@ def run_stage1_steps(args, dev, rank, world, barrier, Bi=16, H=512, W=960, steps
     return res
 
 
+def run_stage2_steps(args, dev, rank, world, barrier, Bi=8, H=512, W=960, steps=3):
+    """Stage-2 (train_ssc.py) training step, Bi frames per GPU (the yaml's batch_size): train-mode TerrainNet (backbone,
+    differentiable splat, ResNet-18 BEV decoder), the six stage-2 losses (SupPixelConLoss all-gathers the sampled
+    pixel embeddings across ranks), backward, ONE flat gradient all-reduce (N > 1), fused Adam."""
+    import torch
+    import torch.distributed as dist
+    from creste_public_b200 import _lib, configs
+    from creste_public_b200.creste.train_ssc import TerrainNetModel
+    import synth_data as synth
+    if args.no_stage2:
+        return None
+    torch.manual_seed(1234)
+    m = TerrainNetModel(configs.ssc_train_cfg((H, W))).to(dev).train()
+    batch = {"joint": {k: v.to(dev) for k, v in synth.ssc_batch(Bi, H, W, seed=rank).items()}}
+    for _ in range(2):
+        out = m.training_step((batch, 0, 0))
+    barrier()
+    n0 = _lib.lib().creste_launch_count()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(steps):
+        out = m.training_step((batch, 0, 0))
+    e1.record()
+    barrier()
+    ms = e0.elapsed_time(e1) / steps
+    launches = (_lib.lib().creste_launch_count() - n0) / steps
+    if world > 1:
+        t = torch.tensor([ms], device=dev)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        ms = float(t)
+    res = {"metric": "stage-2 training frames/sec @ 512x960", "value": Bi * world * 1e3 / ms, "unit": "frames/s",
+           "ms_per_step": ms, "frames_per_step_per_gpu": Bi,
+           "workload": f"train_ssc.py step, B={Bi}/GPU (global {Bi * world}), {H}x{W} (train-mode TerrainNet fwd + 6 "
+                       "losses + bwd + embedding all-gather + gradient all-reduce + Adam)",
+           "loss": float(out["loss"]), "gpu_launches_per_step": launches, "precision": args.precision,
+           "achieved_tflops": 3.0 * GFLOP_PER_FRAME * 1e9 * Bi / (ms * 1e-3) / 1e12,
+           "peak_mem_gib": torch.cuda.max_memory_allocated() / 2 ** 30}
+    del m, batch
+    torch.cuda.empty_cache()
+    return res
+
+
 def run_ours(args):
     import torch
     import torch.distributed as dist
@@ -679,6 +721,13 @@ def run_ours(args):
             "traffic": None, "algorithmic_bytes": 2 * Bw * 128 * 240 * 496 * (2 * 2),
             "note": "3 MMAs per k-step (3xFP16 split): a split mode can reach at most 1/3 of the fp16 peak"}
         del xw, gw
+    stage2 = None
+    try:
+        stage2 = run_stage2_steps(args, dev, rank, world, barrier)
+    except Exception as e:  # noqa: BLE001  (keep the headline line alive if this leg fails)
+        if world > 1:
+            raise
+        stage2 = {"error": repr(e)[:300]}
     if rank == 0 and stage1 is not None and not args.no_cpu and world == 1:
         try:
             fps1, ms1, cores1 = cpu_stage1_baseline()
@@ -710,10 +759,11 @@ def run_ours(args):
             "irl_steps_per_s": irl["value"] if irl else None,
             "irl_samples_per_s": irl["samples_per_s"] if irl else None,
             "stage1_fps": stage1["value"] if stage1 else None,
+            "stage2_fps": (stage2 or {}).get("value"),
             "vi_hbm_frac": vi_roof["frac"] if vi_roof else None,
             "gpu_eager_fps": (gpu_eager or {}).get("default_flags", {}).get(f"b{B}", {}).get("fps"),
             "achieved_tflops_whole_step": GFLOP_PER_FRAME * 1e9 * value / world / 1e12,
-            "gpu_eager_baseline": gpu_eager, "irl": irl, "stage1": stage1, "hbm_kernels": hbm, "vi_64x64": vi0,
+            "gpu_eager_baseline": gpu_eager, "irl": irl, "stage1": stage1, "stage2": stage2, "hbm_kernels": hbm, "vi_64x64": vi0,
             "latency_b1": latency,
         }
         print(json.dumps(line))
@@ -733,6 +783,7 @@ def main():
     ap.add_argument("--no-eager", action="store_true", help="skip the gpu_eager_baseline leg")
     ap.add_argument("--no-irl", action="store_true", help="skip the IRL steps/s leg")
     ap.add_argument("--no-stage1", action="store_true", help="skip the stage-1 training frames/s leg")
+    ap.add_argument("--no-stage2", action="store_true", help="skip the stage-2 training frames/s leg")
     args = ap.parse_args()
     if args.warmup < 3 and args.impl == "ours":
         args.warmup = 3

@@ -55,7 +55,7 @@ def _conv_raw(x, w, ph, pw, stride=1):
         mode = "fp32"      # squeeze-excite vectors [B,1,1,C]: a handful of rows, no tensor-core tile
     if mode == "fp32":
         packed = ops.pack_conv_weight(wp.detach().float())
-    elif mode == "3xfp16":
+    elif mode in ("3xfp16", "fp16"):
         packed = ops.pack_conv_weight_f16_strided(wp.detach().float())      # one launch, strided read
     else:
         packed = ops.pack_conv_weight_tc(wp.detach().float(), split=(mode == "3xtf32"))

@@ -7,7 +7,7 @@ import torch
 from torch import nn
 
 from creste_public_b200 import ops
-from creste_public_b200.engine import FusedConv, require_eval
+from creste_public_b200.engine import FusedConv, carry_amax, require_eval
 from .effnet import Up
 
 
@@ -105,7 +105,7 @@ class DeconvHead(nn.Module):
             return self.forward_train(x1, x2)
         x = self.up1.forward_nhwc(x1, x2)
         N, H, W, _ = x.shape
-        x = ops.upsample_concat(None, x, (2 * H, 2 * W), 2)
+        x = carry_amax(ops.upsample_concat(None, x, (2 * H, 2 * W), 2), x)
         x = self._f_up2(x, act="relu")
         return self._f_proj(x, act="none"), x
 

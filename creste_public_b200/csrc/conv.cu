@@ -5,10 +5,11 @@
 namespace creste {
 int conv_simt_launch(const creste_conv_desc* d, const float* x, const float* w, int ldw,
                      const float* scale, const float* shift, const float* gate,
-                     const float* residual, float* out, cudaStream_t st);
+                     const float* residual, float* out, unsigned* amax_out, cudaStream_t st);
 int conv_tc_launch(const creste_conv_desc* d, const float* x, const float* w_packed,
                    const float* scale, const float* shift, const float* gate, const float* residual,
-                   float* out, void* ws, size_t ws_bytes, cudaStream_t st);
+                   float* out, const float* amax_in, unsigned* amax_out, void* ws, size_t ws_bytes,
+                   cudaStream_t st);
 size_t conv_tc_workspace_bytes(const creste_conv_desc* d);
 bool conv_tc_supported(const creste_conv_desc* d);
 
@@ -235,6 +236,13 @@ extern "C" int creste_conv2d(const creste_conv_desc* d, const float* x, const fl
                              const float* scale, const float* shift, const float* gate,
                              const float* residual, float* out, void* ws, size_t ws_bytes,
                              void* stream) {
+  return creste_conv2d_ex(d, x, w_packed, scale, shift, gate, residual, out, nullptr, nullptr, ws, ws_bytes, stream);
+}
+
+extern "C" int creste_conv2d_ex(const creste_conv_desc* d, const float* x, const float* w_packed,
+                                const float* scale, const float* shift, const float* gate,
+                                const float* residual, float* out, const float* amax_in, float* amax_out,
+                                void* ws, size_t ws_bytes, void* stream) {
   CRESTE_CHECK_ARG(d && x && w_packed && out, "creste_conv2d: null pointer");
   CRESTE_CHECK_ARG(d->N > 0 && d->H > 0 && d->W > 0 && d->C > 0 && d->K > 0 && d->R > 0 && d->S > 0 &&
                        d->stride > 0 && d->P > 0 && d->Q > 0,
@@ -242,16 +250,17 @@ extern "C" int creste_conv2d(const creste_conv_desc* d, const float* x, const fl
   CRESTE_CHECK_ARG(d->C % 4 == 0, "creste_conv2d: C must be a multiple of 4 (got %d)", d->C);
   CRESTE_CHECK_ARG((d->P - 1) * d->stride - d->pad_t + d->R - 1 >= 0, "creste_conv2d: bad padding");
   cudaStream_t st = (cudaStream_t)stream;
+  if (amax_out) CRESTE_CUDA(cudaMemsetAsync(amax_out, 0, sizeof(float), st));
   if (d->precision == 0) {
     const int ldw = (d->K + 3) / 4 * 4;
-    return conv_simt_launch(d, x, w_packed, ldw, scale, shift, gate, residual, out, st);
+    return conv_simt_launch(d, x, w_packed, ldw, scale, shift, gate, residual, out, (unsigned*)amax_out, st);
   }
   if (!conv_tc_supported(d)) {
     set_error("creste_conv2d: precision mode %d is not available for this shape "
               "(C=%d K=%d R=%d stride=%d); use precision 0", d->precision, d->C, d->K, d->R, d->stride);
     return CRESTE_ERR_ARG;
   }
-  return conv_tc_launch(d, x, w_packed, scale, shift, gate, residual, out, ws, ws_bytes, st);
+  return conv_tc_launch(d, x, w_packed, scale, shift, gate, residual, out, amax_in, (unsigned*)amax_out, ws, ws_bytes, st);
 }
 
 extern "C" int creste_dwconv_num_parts(int N, int P, int Q) {

@@ -23,6 +23,8 @@ struct ConvP {
   int N, H, W, C, K, R, S, stride, pad_t, pad_l, P, Q, act, out_nchw;
   int M, Kdim, ldw;
   int vec;      // NHWC output, K % 4 == 0 and 16-byte aligned pointers: 128-bit epilogue loads / stores
+  unsigned* amax_out;   // optional: atomicMax of |out| (float bits) -- "amax carried with the tensor" for the
+                        // 3xFP16 operand scale of the NEXT tensor-core conv (no separate amax pass over it)
 };
 
 __device__ __forceinline__ float apply_act(float v, int act) {
@@ -188,6 +190,13 @@ __global__ void __launch_bounds__(256, 2) conv_simt_kernel(ConvP p) {
   }
 
   // ---- epilogue
+  float amx = 0.0f;
+  auto post_amax = [&]() {
+    if (p.amax_out) {
+      amx = warp_max(amx);
+      if ((t & 31) == 0 && amx > 0.0f) atomicMax(p.amax_out, __float_as_uint(amx));
+    }
+  };
   // vector path: a thread's output columns come in groups of 4 (2 for TN == 2) contiguous channels, so the
   // folded BN factors, the residual and the store are one 128-bit access per group -- 16 lanes write 256
   // contiguous bytes of a pixel row.  (The scalar form below wrote 4 bytes per lane at a 16-byte stride: a
@@ -222,17 +231,22 @@ __global__ void __launch_bounds__(256, 2) conv_simt_kernel(ConvP p) {
             const float4 r4 = __ldg(reinterpret_cast<const float4*>(p.residual + (size_t)m * p.K + n));
             v[0] += r4.x; v[1] += r4.y; v[2 % G] += r4.z; v[3 % G] += r4.w;
           }
-          *reinterpret_cast<float4*>(dst) = make_float4(apply_act(v[0], p.act), apply_act(v[1], p.act),
-                                                        apply_act(v[2 % G], p.act), apply_act(v[3 % G], p.act));
+          const float4 o4 = make_float4(apply_act(v[0], p.act), apply_act(v[1], p.act),
+                                        apply_act(v[2 % G], p.act), apply_act(v[3 % G], p.act));
+          amx = fmaxf(fmaxf(amx, fmaxf(fabsf(o4.x), fabsf(o4.y))), fmaxf(fabsf(o4.z), fabsf(o4.w)));
+          *reinterpret_cast<float4*>(dst) = o4;
         } else {
           if (p.residual) {
             const float2 r2 = __ldg(reinterpret_cast<const float2*>(p.residual + (size_t)m * p.K + n));
             v[0] += r2.x; v[1] += r2.y;
           }
-          *reinterpret_cast<float2*>(dst) = make_float2(apply_act(v[0], p.act), apply_act(v[1], p.act));
+          const float2 o2 = make_float2(apply_act(v[0], p.act), apply_act(v[1], p.act));
+          amx = fmaxf(amx, fmaxf(fabsf(o2.x), fabsf(o2.y)));
+          *reinterpret_cast<float2*>(dst) = o2;
         }
       }
     }
+    post_amax();
     return;
   }
   const int PQ = p.P * p.Q;
@@ -249,6 +263,7 @@ __global__ void __launch_bounds__(256, 2) conv_simt_kernel(ConvP p) {
       float v = fmaf(acc[i][j], sc, sh);
       if (p.residual) v += __ldg(p.residual + (size_t)m * p.K + n);
       v = apply_act(v, p.act);
+      amx = fmaxf(amx, fabsf(v));
       if (p.out_nchw) {
         const int img = m / PQ, pix = m - img * PQ;
         p.out[((size_t)img * p.K + n) * PQ + pix] = v;
@@ -257,12 +272,14 @@ __global__ void __launch_bounds__(256, 2) conv_simt_kernel(ConvP p) {
       }
     }
   }
+  post_amax();
 }
 
 int conv_simt_launch(const creste_conv_desc* d, const float* x, const float* w, int ldw,
                      const float* scale, const float* shift, const float* gate,
-                     const float* residual, float* out, cudaStream_t st) {
+                     const float* residual, float* out, unsigned* amax_out, cudaStream_t st) {
   ConvP p;
+  p.amax_out = amax_out;
   p.x = x; p.w = w; p.scale = scale; p.shift = shift; p.gate = gate; p.residual = residual;
   p.out = out;
   p.N = d->N; p.H = d->H; p.W = d->W; p.C = d->C; p.K = d->K; p.R = d->R; p.S = d->S;

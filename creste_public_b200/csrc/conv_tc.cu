@@ -285,6 +285,7 @@ struct TcParams {
   const float* act_inv; const float* w_inv; float cross_scale;
   int kelems;                  // operand elements per 128-byte swizzle row: 32 (tf32) or 64 (fp16)
   int n_tiles;                 // number of N tiles (output-channel blocks)
+  unsigned* amax_out;          // optional: atomicMax of |out| (float bits), carried with the output tensor
 };
 
 constexpr int TC_THREADS = 320;     // warp 0 TMA, warp 1 MMA, warps 2..9 epilogue (two per TMEM lane quarter)
@@ -489,6 +490,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_consta
     const int ox = x0 + wx, oy = y0 + hy;
     const bool pix_ok = (ox < p.Q) && (oy < p.P) && (img < p.N);
     const size_t pix = ((size_t)img * p.P + oy) * p.Q + ox;
+    float amx = 0.0f;
     mbar_wait(&tmem_full_bar, 0);
     tc_fence_after();
     TC_STAMP(3);
@@ -535,15 +537,18 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_consta
                 const float4 rr = __ldg(reinterpret_cast<const float4*>(p.residual + (size_t)rpix * p.K + n));
                 o[0] += rr.x; o[1] += rr.y; o[2] += rr.z; o[3] += rr.w;
               }
-              *reinterpret_cast<float4*>(dst) = make_float4(tc_act(o[0], p.act), tc_act(o[1], p.act),
-                                                            tc_act(o[2], p.act), tc_act(o[3], p.act));
+              const float4 o4 = make_float4(tc_act(o[0], p.act), tc_act(o[1], p.act), tc_act(o[2], p.act), tc_act(o[3], p.act));
+              amx = fmaxf(fmaxf(amx, fmaxf(fabsf(o4.x), fabsf(o4.y))), fmaxf(fabsf(o4.z), fabsf(o4.w)));
+              *reinterpret_cast<float4*>(dst) = o4;
             } else {
 #pragma unroll
               for (int q = 0; q < 4; ++q)
                 if (n + q < p.K) {
                   float val = o[q];
                   if (p.residual) val += __ldg(p.residual + (size_t)rpix * p.K + n + q);
-                  dst[q] = tc_act(val, p.act);
+                  val = tc_act(val, p.act);
+                  amx = fmaxf(amx, fabsf(val));
+                  dst[q] = val;
                 }
             }
           }
@@ -558,10 +563,16 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_consta
           if (nn < p.K && c0 + j < p.block_n) {
             float val = fmaf(__uint_as_float(v[j]), s_mul[c0 + j], s_add[c0 + j]);
             if (p.residual) val += __ldg(p.residual + pix * p.K + nn);
-            p.out[((size_t)img * p.K + nn) * PQ + pp] = tc_act(val, p.act);
+            val = tc_act(val, p.act);
+            amx = fmaxf(amx, fabsf(val));
+            p.out[((size_t)img * p.K + nn) * PQ + pp] = val;
           }
         }
       }
+    }
+    if (p.amax_out) {
+      amx = warp_max(amx);
+      if (lane == 0 && amx > 0.0f) atomicMax(p.amax_out, __float_as_uint(amx));
     }
   }
   TC_STAMP(4);
@@ -639,11 +650,25 @@ __global__ void f16_scale_kernel(const unsigned* __restrict__ amax_bits, float* 
   scal[1] = __uint_as_float((unsigned)(127 - k) << 23);
 }
 
+// amax_bound != nullptr: the scale comes from an upper bound of max|x * gate| that travels with the tensor (the
+// producing kernel's epilogue atomicMax, or the maximum over the inputs of an interpolation / concat): no amax pass
+// and no scale kernel.  Any power-of-two scale with amax * s in [2^-4, 2^15] keeps the hi/lo split at 22 bits
+// relative to the tensor maximum, so a loose bound costs nothing; block 0 publishes {s, 1/s} for the epilogue.
 __global__ void __launch_bounds__(256) f16_split_kernel(const float4* __restrict__ x, const float* __restrict__ gate,
                                                         int C, long long hwc4, long long n4,
-                                                        const float* __restrict__ scal, uint2* __restrict__ hi,
-                                                        uint2* __restrict__ lo) {
-  const float s = __ldg(scal);
+                                                        float* __restrict__ scal, const unsigned* __restrict__ amax_bound,
+                                                        uint2* __restrict__ hi, uint2* __restrict__ lo) {
+  float s;
+  if (amax_bound) {
+    const unsigned b = __ldg(amax_bound);
+    int e = (int)((b >> 23) & 0xffu) - 127;
+    if (b == 0u || !isfinite(__uint_as_float(b))) e = 14;
+    const int k = max(-100, min(100, 14 - e));
+    s = __uint_as_float((unsigned)(127 + k) << 23);
+    if (blockIdx.x == 0 && threadIdx.x == 0) { scal[0] = s; scal[1] = __uint_as_float((unsigned)(127 - k) << 23); }
+  } else {
+    s = __ldg(scal);
+  }
   for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n4;
        i += (long long)gridDim.x * blockDim.x) {
     float4 v = __ldg(x + i);
@@ -663,7 +688,7 @@ __global__ void __launch_bounds__(256) f16_split_kernel(const float4* __restrict
       l[j] = __half_as_ushort(__float2half_rn(res));
     }
     hi[i] = make_uint2((unsigned)h[0] | ((unsigned)h[1] << 16), (unsigned)h[2] | ((unsigned)h[3] << 16));
-    lo[i] = make_uint2((unsigned)l[0] | ((unsigned)l[1] << 16), (unsigned)l[2] | ((unsigned)l[3] << 16));
+    if (lo) lo[i] = make_uint2((unsigned)l[0] | ((unsigned)l[1] << 16), (unsigned)l[2] | ((unsigned)l[3] << 16));
   }
 }
 
@@ -741,9 +766,9 @@ static void pick_box(int P, int Q, int* wbox, int* hbox) {
 }
 
 bool conv_tc_supported(const creste_conv_desc* d) {
-  if (d->precision != 1 && d->precision != 2 && d->precision != 4) return false;
+  if (d->precision != 1 && d->precision != 2 && d->precision != 4 && d->precision != 5) return false;
   if ((d->stride != 1 && d->stride != 2) || d->C % 4 != 0 || d->K < 8) return false;
-  if (d->precision == 4 && d->C % 8 != 0) return false;     // fp16 rows must be 16-byte multiples (TMA)
+  if ((d->precision == 4 || d->precision == 5) && d->C % 8 != 0) return false;     // fp16 rows must be 16-byte multiples (TMA)
   if (d->R > 7 || d->S > 7) return false;
   if ((long long)d->N * d->P * d->Q < 128) return false;
   return true;
@@ -759,19 +784,21 @@ int conv_tc_layout(int K, int C, int R, int S, int* block_n, int* npad, int* cpa
 
 size_t conv_tc_workspace_bytes(const creste_conv_desc* d) {
   const size_t n = (size_t)d->N * d->H * d->W * d->C * sizeof(float);
-  if (d->precision == 4) return 2 * align_up(n / 2, 1024) + 1024;     // fp16 hi, lo + scale scalars
+  if (d->precision == 4 || d->precision == 5) return 2 * align_up(n / 2, 1024) + 1024;     // fp16 hi, lo + scale scalars
   return d->precision == 1 ? 2 * align_up(n, 1024) : align_up(n, 1024);
 }
 
 int conv_tc_launch(const creste_conv_desc* d, const float* x, const float* w_packed, const float* scale,
-                   const float* shift, const float* gate, const float* residual, float* out, void* ws,
-                   size_t ws_bytes, cudaStream_t st) {
+                   const float* shift, const float* gate, const float* residual, float* out, const float* amax_in,
+                   unsigned* amax_out, void* ws, size_t ws_bytes, cudaStream_t st) {
   if (ws_bytes < conv_tc_workspace_bytes(d) || !ws) {
     set_error("creste_conv2d(tc): workspace %zu < %zu", ws_bytes, conv_tc_workspace_bytes(d));
     return CRESTE_ERR_WORKSPACE;
   }
-  const bool f16 = d->precision == 4;
-  const int split = d->precision == 1 || f16;
+  // precision 4 = 3xFP16 (hi/lo split, fp32-faithful); 5 = single-pass fp16 (hi only: the arithmetic class of the
+  // reference's own default GPU run, cuDNN TF32 -- 11 significant bits per operand; reported, never asserted)
+  const bool f16 = d->precision == 4 || d->precision == 5;
+  const int split = d->precision == 1 || d->precision == 4;
   int block_n, npad, cpad;
   conv_tc_layout(d->K, d->C, d->R, d->S, &block_n, &npad, &cpad);
   if (f16) cpad = (d->C + 63) / 64 * 64;
@@ -783,19 +810,22 @@ int conv_tc_launch(const creste_conv_desc* d, const float* x, const float* w_pac
   if (f16) {
     scal = (float*)((char*)ws + 2 * align_up(numel * 2, 1024));       // [s, 1/s, amax bits, -]
     unsigned* amax = (unsigned*)(scal + 2);
-    CRESTE_CUDA(cudaMemsetAsync(amax, 0, 4, st));
     const long long n4 = (long long)(numel / 4);
     long long blocks = (n4 + 255) / 256;
     if (blocks > 148 * 16) blocks = 148 * 16;
     const long long hwc4 = (long long)d->H * d->W * d->C / 4;
-    f16_amax_kernel<<<(int)blocks, 256, 0, st>>>((const float4*)x, gate, d->C, hwc4, n4, amax);
-    int rc = launch_check("f16_amax_kernel");
-    if (rc) return rc;
-    f16_scale_kernel<<<1, 1, 0, st>>>(amax, scal);
-    rc = launch_check("f16_scale_kernel");
-    if (rc) return rc;
-    f16_split_kernel<<<(int)blocks, 256, 0, st>>>((const float4*)x, gate, d->C, hwc4, n4, scal, (uint2*)x_hi,
-                                                  (uint2*)x_lo);
+    int rc;
+    if (!amax_in) {          // no bound travels with the tensor: one extra pass over it
+      CRESTE_CUDA(cudaMemsetAsync(amax, 0, 4, st));
+      f16_amax_kernel<<<(int)blocks, 256, 0, st>>>((const float4*)x, gate, d->C, hwc4, n4, amax);
+      rc = launch_check("f16_amax_kernel");
+      if (rc) return rc;
+      f16_scale_kernel<<<1, 1, 0, st>>>(amax, scal);
+      rc = launch_check("f16_scale_kernel");
+      if (rc) return rc;
+    }
+    f16_split_kernel<<<(int)blocks, 256, 0, st>>>((const float4*)x, gate, d->C, hwc4, n4, scal,
+                                                  (const unsigned*)amax_in, (uint2*)x_hi, (uint2*)x_lo);
     rc = launch_check("f16_split_kernel");
     if (rc) return rc;
   } else {
@@ -817,6 +847,7 @@ int conv_tc_launch(const creste_conv_desc* d, const float* x, const float* w_pac
   p.tiles_x = ceil_div(d->Q, p.wbox);
   p.tiles_y = ceil_div(d->P, p.hbox);
   p.block_n = block_n; p.act = d->act; p.split = split; p.out_nchw = d->out_nchw;
+  p.amax_out = amax_out;
 
   // two CTAs on adjacent M tiles form a tcgen05 CTA pair (cta_group::2, M = 256)
   const int m_tiles = d->N * p.tiles_y * p.tiles_x;
@@ -1059,7 +1090,7 @@ static int wg_split(const float* x, size_t numel, int C, void* hi, void* lo, flo
   if (rc) return rc;
   f16_scale_kernel<<<1, 1, 0, st>>>(amax, scal);
   if ((rc = launch_check("f16_scale_kernel"))) return rc;
-  f16_split_kernel<<<(int)blocks, 256, 0, st>>>((const float4*)x, nullptr, C, 1, n4, scal, (uint2*)hi, (uint2*)lo);
+  f16_split_kernel<<<(int)blocks, 256, 0, st>>>((const float4*)x, nullptr, C, 1, n4, scal, nullptr, (uint2*)hi, (uint2*)lo);
   return launch_check("f16_split_kernel");
 }
 

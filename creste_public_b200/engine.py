@@ -14,8 +14,9 @@ _PRECISION = "fp32"
 def set_precision(mode):
     """Conv-family arithmetic: 'fp32' (FFMA, exact products), '3xtf32' (tcgen05 kind::tf32,
     fp32-faithful split), '3xfp16' (tcgen05 kind::f16 on power-of-two-scaled fp16 hi/lo operands:
-    the same 11-bit significands as tf32 at twice the tensor-pipe rate), 'tf32' (single pass;
-    measured error is reported, never asserted)."""
+    the same 11-bit significands as tf32 at twice the tensor-pipe rate), 'tf32' / 'fp16' (single pass: the
+    arithmetic class of the reference's own default GPU run, cuDNN TF32; measured error is reported, never
+    asserted)."""
     global _PRECISION
     assert mode in ops.PRECISION, mode
     _PRECISION = mode
@@ -50,7 +51,7 @@ def drop_connect_scale(B, rate, device):
 def pick_mode(x_shape, K, R, S, stride, pad, mode):
     """Requested precision, or the next stricter one the shape is served by:
     3xfp16 -> 3xtf32 -> fp32 (never a looser one)."""
-    chain = {"3xfp16": ["3xfp16", "3xtf32"], "3xtf32": ["3xtf32"], "tf32": ["tf32"], "fp32": []}[mode]
+    chain = {"3xfp16": ["3xfp16", "3xtf32"], "3xtf32": ["3xtf32"], "tf32": ["tf32"], "fp16": ["fp16"], "fp32": []}[mode]
     # short reductions (1x1 convs with C <= 192: the MBConv expand / project and head convs) are
     # HBM-bound; measured per shape, the exact-fp32 FFMA kernel beats the tensor-core kernel there
     # (no operand pre-pass, no per-CTA TMEM / barrier set-up): 0.79 vs 1.32 ms at C16->K96 @256x480
@@ -103,6 +104,20 @@ def bn_scale_shift(bn, conv_bias=None):
     return scale.float().contiguous(), shift.float().contiguous()
 
 
+def carried_amax(t):
+    """The max|t| bound that travels with an activation tensor (set by the producing op), or None."""
+    return getattr(t, "_amax", None)
+
+
+def carry_amax(out, *sources):
+    """Bound of an op whose outputs are convex combinations / copies of its inputs (bilinear up-sampling, channel
+    concat, max-pool): the maximum of the inputs' bounds.  No bound if any input has none."""
+    bounds = [carried_amax(s) for s in sources if s is not None]
+    if bounds and all(b is not None for b in bounds):
+        out._amax = bounds[0] if len(bounds) == 1 else torch.maximum(bounds[0], bounds[1])
+    return out
+
+
 class FusedConv:
     """conv (+bias) (+BN eval) packed for creste_conv2d; built lazily from live parameters."""
 
@@ -119,7 +134,7 @@ class FusedConv:
         def build():
             if mode == "fp32":
                 w = ops.pack_conv_weight(conv.weight.detach().float())
-            elif mode == "3xfp16":
+            elif mode in ("3xfp16", "fp16"):
                 w = ops.pack_conv_weight_f16(conv.weight.detach().float())
             else:
                 w = ops.pack_conv_weight_tc(conv.weight.detach().float(), split=(mode == "3xtf32"))
@@ -142,10 +157,17 @@ class FusedConv:
         mode = precision or _PRECISION
         # shapes the tensor-core kernel does not serve (strided, C = 4 stem, K < 8 heads) run on
         # the exact-fp32 CUDA-core kernel -- a stricter precision, never a looser one
+        track = (precision or _PRECISION) in ("3xfp16", "fp16")
         mode = pick_mode(tuple(x_nhwc.shape), K, R, S, stride, pad, mode)
         w, scale, shift = self.packed(mode)
-        return ops.conv2d(x_nhwc, w, K, R, S, stride, pad, scale, shift, gate, residual, act,
-                          out_nchw, mode)
+        # 3xFP16: max|out| is produced by this conv's epilogue and travels with the tensor (`_amax`), so the next
+        # tensor-core conv derives its operand scale from it instead of making an extra amax pass over its input
+        amax_out = torch.empty(1, device=x_nhwc.device) if track else None
+        out = ops.conv2d(x_nhwc, w, K, R, S, stride, pad, scale, shift, gate, residual, act, out_nchw, mode,
+                         amax_in=carried_amax(x_nhwc) if mode in ("3xfp16", "fp16") else None, amax_out=amax_out)
+        if track:
+            out._amax = amax_out
+        return out
 
 
 class GraphedForward:

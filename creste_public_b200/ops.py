@@ -12,7 +12,7 @@ from . import _lib
 from ._lib import ConvDesc, check, lib, ptr, stream
 
 ACT = {"none": 0, None: 0, "relu": 1, "swish": 2, "sigmoid": 3}
-PRECISION = {"fp32": 0, "3xtf32": 1, "tf32": 2, "bf16": 3, "3xfp16": 4}
+PRECISION = {"fp32": 0, "3xtf32": 1, "tf32": 2, "bf16": 3, "3xfp16": 4, "fp16": 5}
 
 
 def _ws(nbytes, device):
@@ -320,8 +320,10 @@ def tc_supported(x_shape, K, R, S, stride, pad, precision):
 
 
 def conv2d(x_nhwc, w_packed, K, R, S, stride=1, pad=(0, 0, 0, 0), scale=None, shift=None,
-           gate=None, residual=None, act="none", out_nchw=False, precision="fp32"):
-    """NHWC conv + folded BN/bias + residual + activation.  pad = (top, bottom, left, right)."""
+           gate=None, residual=None, act="none", out_nchw=False, precision="fp32", amax_in=None, amax_out=None):
+    """NHWC conv + folded BN/bias + residual + activation.  pad = (top, bottom, left, right).
+    amax_in / amax_out: optional device float[1] tensors -- an upper bound of max|x * gate| that lets the 3xFP16
+    operand pre-pass skip its amax pass, and the slot that receives max|out| from the epilogue."""
     N, H, W, Cc = x_nhwc.shape
     pt, pb, pl, pr = pad
     P = (H + pt + pb - R) // stride + 1
@@ -331,9 +333,9 @@ def conv2d(x_nhwc, w_packed, K, R, S, stride=1, pad=(0, 0, 0, 0), scale=None, sh
     out = torch.empty((N, K, P, Q) if out_nchw else (N, P, Q, K), device=x_nhwc.device)
     n = lib().creste_conv2d_workspace_bytes(C.byref(d))
     ws = _ws(n, x_nhwc.device) if n else None
-    check(lib().creste_conv2d(C.byref(d), ptr(x_nhwc), ptr(w_packed), ptr(scale), ptr(shift),
-                              ptr(gate), ptr(residual), ptr(out), ptr(ws), C.c_size_t(n), stream()),
-          "creste_conv2d")
+    check(lib().creste_conv2d_ex(C.byref(d), ptr(x_nhwc), ptr(w_packed), ptr(scale), ptr(shift),
+                                 ptr(gate), ptr(residual), ptr(out), ptr(amax_in), ptr(amax_out), ptr(ws),
+                                 C.c_size_t(n), stream()), "creste_conv2d")
     return out
 
 

@@ -184,6 +184,14 @@ typedef struct {
 int creste_conv2d(const creste_conv_desc* d, const float* x, const float* w_packed,
                   const float* scale, const float* shift, const float* gate, const float* residual,
                   float* out, void* ws, size_t ws_bytes, void* stream);
+/* creste_conv2d with the operand-scale bound carried beside the tensors (3xFP16 mode):
+ *   amax_in  DEVICE float[1] or NULL: an upper bound of max|x * gate| (e.g. the amax_out of the producing call);
+ *            given, the operand pre-pass skips its amax pass over x and derives the power-of-two scale from it;
+ *   amax_out DEVICE float[1] or NULL: receives max|out| (zeroed, then atomicMax from the epilogue). */
+int creste_conv2d_ex(const creste_conv_desc* d, const float* x, const float* w_packed, const float* scale,
+                     const float* shift, const float* gate, const float* residual, float* out,
+                     const float* amax_in, float* amax_out, void* ws, size_t ws_bytes, void* stream);
+
 size_t creste_conv2d_workspace_bytes(const creste_conv_desc* d);
 /* tcgen05 path (precision 1, 2): 1 if the shape is served by the tensor-core kernel (stride 1 or 2, R, S <= 7,
  * C % 4 == 0, K >= 8, >= 128 output pixels), else the caller must use precision 0.  For those

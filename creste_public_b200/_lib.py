@@ -24,7 +24,7 @@ EXPORTS = [
     "creste_conv2d_tc_layout", "creste_conv2d_tc_debug",
     "creste_dwconv_num_parts", "creste_dwconv_bn_swish", "creste_se_gate",
     "creste_upsample_concat", "creste_maxpool2_concat",
-    "creste_nchw_to_nhwc", "creste_nhwc_to_nchw",
+    "creste_nchw_to_nhwc", "creste_nhwc_to_nchw", "creste_proj_head",
     "creste_expert_visitation",
     "creste_chan_affine", "creste_relu_bwd", "creste_chan_dot_workspace_bytes", "creste_chan_dot", "creste_chan_stats",
     "creste_maxpool2_bwd", "creste_maxpool2_gather", "creste_upsample_adjoint",

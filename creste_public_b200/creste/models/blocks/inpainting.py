@@ -109,6 +109,24 @@ class DeconvHead(nn.Module):
         x = self._f_up2(x, act="relu")
         return self._f_proj(x, act="none"), x
 
+    def forward_fused_nhwc(self, x1, x2, want_nchw=True):
+        """Eval path with the projection head, the NCHW copy of the predictions and the NCHW copy of the 128-channel
+        features in ONE pass over the features (creste_proj_head) instead of a generic conv + two transposes.
+        -> (pred NHWC, features NHWC, pred NCHW | None, features NCHW | None)."""
+        x = self.up1.forward_nhwc(x1, x2)
+        N, H, W, _ = x.shape
+        x = carry_amax(ops.upsample_concat(None, x, (2 * H, 2 * W), 2), x)
+        x = self._f_up2(x, act="relu")
+        K, Cc = self.proj.weight.shape[0], self.proj.weight.shape[1]
+        if K > 32 or Cc % 32 or Cc > 512:
+            pred = self._f_proj(x, act="none")
+            return pred, x, (ops.nhwc_to_nchw(pred) if want_nchw else None), (ops.nhwc_to_nchw(x) if want_nchw else None)
+        w, b = self._f_proj.cache.get("proj_kc", [self.proj.weight, self.proj.bias], lambda: (
+            self.proj.weight.detach().float().reshape(K, Cc).contiguous(),
+            None if self.proj.bias is None else self.proj.bias.detach().float().contiguous()))
+        pred, pred_nchw, x_nchw = ops.proj_head(x, w, b, want_nchw, want_nchw)
+        return pred, x, pred_nchw, x_nchw
+
 
 class InpaintingResNet18MultiHead(Inpainting):
     def __init__(self, num_input_features, num_classes, norm_layer="batch_norm", **kwargs):
@@ -152,6 +170,12 @@ class InpaintingResNet18MultiHead(Inpainting):
             x = blk.forward_nhwc(x)
         ret, preds_nhwc = {}, {}
         for head, prefix in zip(self.out_heads, self.output_prefix):
+            if not self.training:
+                pred, fea, pred_nchw, fea_nchw = head.forward_fused_nhwc(x, x1, want_nchw)
+                preds_nhwc[prefix] = pred
+                if want_nchw:
+                    ret[f"{prefix}_preds"], ret[f"{prefix}_features"] = pred_nchw, fea_nchw
+                continue
             pred, fea = head.forward_nhwc(x, x1)
             preds_nhwc[prefix] = pred
             if want_nchw:

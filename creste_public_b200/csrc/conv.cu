@@ -223,6 +223,69 @@ __global__ void __launch_bounds__(1024) se_gate_kernel(const float* __restrict__
   }
 }
 
+// ---- SE gate across a thread-block cluster: 8 CTAs per image, CTA r owns channels [r*Cs, (r+1)*Cs).  The
+// one-CTA form above is latency-bound on its first phase (one SM pulling up to 592 x 1152 partial sums out of L2:
+// 37-48 us per call, 10 % of the B = 1 frame); here that phase and the excite phase run 8-wide, the per-channel
+// means are exchanged through distributed shared memory, and every CTA evaluates the (tiny) squeeze layer itself.
+// Same summation order per channel as se_gate_kernel (rows lane, lane + 8, ... then the lanes in order), so the
+// gate is bit-identical.
+constexpr int SE_CL = 8;
+__global__ void __cluster_dims__(SE_CL, 1, 1) __launch_bounds__(512)
+se_gate_cluster_kernel(const float* __restrict__ chan_part, int nparts, float inv_hw, int C, int Csq,
+                       const float* __restrict__ w_red, const float* __restrict__ b_red,
+                       const float* __restrict__ w_exp, const float* __restrict__ b_exp, float* __restrict__ gate) {
+  extern __shared__ float sm[];  // mean[C] (all channels, filled by every CTA of the cluster), sq[Csq], lsum[8][Cs]
+  const int Cs = (C + SE_CL - 1) / SE_CL;
+  float* mean = sm;
+  float* sq = sm + C;
+  float* lsum = sm + C + Csq;
+  unsigned rank;
+  asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(rank));
+  const int n = blockIdx.x / SE_CL;
+  const int c0 = (int)rank * Cs, cn = max(0, min(Cs, C - c0));
+  for (int idx = threadIdx.x; idx < 8 * cn; idx += blockDim.x) {
+    const int l = idx / cn, c = idx - l * cn;
+    const float* src = chan_part + (size_t)n * nparts * C + c0 + c;
+    float tot = 0.0f;
+    for (int j = l; j < nparts; j += 8) tot += __ldg(src + (size_t)j * C);
+    lsum[l * Cs + c] = tot;
+  }
+  __syncthreads();
+  // own means -> every CTA's `mean` array (distributed shared memory stores)
+  const unsigned mean_addr = (unsigned)__cvta_generic_to_shared(mean);
+  for (int c = threadIdx.x; c < cn; c += blockDim.x) {
+    float tot = lsum[c];
+#pragma unroll
+    for (int l = 1; l < 8; ++l) tot += lsum[l * Cs + c];
+    const float m = tot * inv_hw;
+#pragma unroll
+    for (unsigned r = 0; r < SE_CL; ++r) {
+      unsigned ra;
+      asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(ra) : "r"(mean_addr + (unsigned)(c0 + c) * 4u), "r"(r));
+      asm volatile("st.shared::cluster.f32 [%0], %1;" ::"r"(ra), "f"(m) : "memory");
+    }
+  }
+  asm volatile("barrier.cluster.arrive.release.aligned;\n\tbarrier.cluster.wait.acquire.aligned;" ::: "memory");
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nw = blockDim.x >> 5;
+  for (int j = warp; j < Csq; j += nw) {
+    float a = 0.0f;
+    for (int c = lane; c < C; c += 32) a = fmaf(w_red[(size_t)j * C + c], mean[c], a);
+    a = warp_sum(a);
+    if (lane == 0) {
+      a += b_red[j];
+      sq[j] = a / (1.0f + expf(-a));  // swish
+    }
+  }
+  __syncthreads();
+  for (int c = threadIdx.x; c < cn; c += blockDim.x) {
+    float a = b_exp[c0 + c];
+    for (int j = 0; j < Csq; ++j) a = fmaf(w_exp[(size_t)(c0 + c) * Csq + j], sq[j], a);
+    gate[(size_t)n * C + c0 + c] = 1.0f / (1.0f + expf(-a));
+  }
+  // no CTA may exit while a peer can still store into its shared memory
+  asm volatile("barrier.cluster.arrive.release.aligned;\n\tbarrier.cluster.wait.acquire.aligned;" ::: "memory");
+}
+
 }  // namespace creste
 
 using namespace creste;
@@ -302,6 +365,13 @@ extern "C" int creste_se_gate(const float* chan_part, int nparts, float inv_hw, 
                               const float* w_red, const float* b_red, const float* w_exp,
                               const float* b_exp, float* gate, void* stream) {
   CRESTE_CHECK_ARG(chan_part && w_red && b_red && w_exp && b_exp && gate && nparts > 0, "creste_se_gate: null pointer");
+  if (!getenv("CRESTE_SE_ONE_CTA")) {
+    const int Cs = (C + SE_CL - 1) / SE_CL;
+    const size_t smem = (size_t)(C + Csq + 8 * Cs) * sizeof(float);
+    se_gate_cluster_kernel<<<N * SE_CL, 512, smem, (cudaStream_t)stream>>>(chan_part, nparts, inv_hw, C, Csq, w_red,
+                                                                          b_red, w_exp, b_exp, gate);
+    return launch_check("se_gate_cluster_kernel");
+  }
   const size_t smem = (size_t)(9 * C + Csq) * sizeof(float);
   se_gate_kernel<<<N, 1024, smem, (cudaStream_t)stream>>>(chan_part, nparts, inv_hw, C, Csq, w_red, b_red, w_exp,
                                                         b_exp, gate);

@@ -24,6 +24,59 @@ __global__ void __launch_bounds__(256) transpose_kernel(const float* __restrict_
   }
 }
 
+// ---- projection head: 1x1 conv with a handful of output channels (the DeconvHead `proj`, K = 32 / 6 / 2 over
+// C = 128 features at 256 x 256) fused with the layout change of its INPUT.  The generic conv kernels tile the
+// output channels by >= 32 and waste 5-16x of their FFMA work here, and the reference's output dict wants both the
+// predictions and the 128-channel features in NCHW -- another full read + write of the feature tensor.  One pass:
+// a warp stages 32 pixels x 32 channels through a padded shared tile (coalesced NHWC read), lane = pixel then
+// accumulates its K dot products in registers (weights broadcast from shared memory, channels in ascending order:
+// the same fp32 FFMA chain as conv_simt_kernel) and writes the tile back transposed as 32 coalesced NCHW rows.
+// HBM traffic: read x once, write x^T once, write the predictions -- the floor for the two outputs.
+template <int KO>
+__global__ void __launch_bounds__(256) proj_head_kernel(const float* __restrict__ x, const float* __restrict__ w,
+                                                        const float* __restrict__ bias, long long M, int C,
+                                                        long long PQ, float* __restrict__ pred_nhwc,
+                                                        float* __restrict__ pred_nchw, float* __restrict__ x_nchw,
+                                                        int K) {
+  extern __shared__ float s_w[];                       // [KO][C]
+  __shared__ float tile[8][32][33];
+  for (int i = threadIdx.x; i < KO * C; i += blockDim.x) s_w[i] = (i / C < K) ? w[i] : 0.0f;
+  __syncthreads();
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  for (long long p0 = ((long long)blockIdx.x * 8 + warp) * 32; p0 < M; p0 += (long long)gridDim.x * 256) {
+    const long long pix = p0 + lane;                   // this lane's pixel in the compute / store phases
+    const bool ok = pix < M;
+    const long long img = ok ? pix / PQ : 0, pp = ok ? pix - img * PQ : 0;
+    float acc[KO];
+#pragma unroll
+    for (int k = 0; k < KO; ++k) acc[k] = 0.0f;
+    for (int c0 = 0; c0 < C; c0 += 32) {
+#pragma unroll 8
+      for (int r = 0; r < 32; ++r)                     // row r of the tile = pixel p0 + r: one 128-byte line
+        tile[warp][r][lane] = (p0 + r < M) ? __ldg(x + (size_t)(p0 + r) * C + c0 + lane) : 0.0f;
+      __syncwarp();
+#pragma unroll 8
+      for (int c = 0; c < 32; ++c) {
+        const float xv = tile[warp][lane][c];
+#pragma unroll
+        for (int k = 0; k < KO; ++k) acc[k] = fmaf(xv, s_w[k * C + c0 + c], acc[k]);
+        if (x_nchw && ok) x_nchw[((size_t)img * C + c0 + c) * PQ + pp] = xv;
+      }
+      __syncwarp();
+    }
+    if (ok) {
+#pragma unroll
+      for (int k = 0; k < KO; ++k) {
+        if (k < K) {
+          const float v = acc[k] + (bias ? __ldg(bias + k) : 0.0f);
+          if (pred_nhwc) pred_nhwc[(size_t)pix * K + k] = v;
+          if (pred_nchw) pred_nchw[((size_t)img * K + k) * PQ + pp] = v;
+        }
+      }
+    }
+  }
+}
+
 // ---- cat([skip, bilinear(x)], C) in NHWC; Cs % 4 == 0, Cx % 4 == 0.
 // PyTorch upsample_bilinear2d (align_corners=False): src = max(r*(dst+0.5)-0.5, 0); i0 = (int)src;
 // i1 = i0 + (i0 < in-1); l1 = src - i0; l0 = 1 - l1;
@@ -161,6 +214,28 @@ extern "C" int creste_nhwc_to_nchw(const float* in, int N, int H, int W, int C, 
   dim3 grid(ceil_div(C, 32), ceil_div(H * W, 32), N);
   transpose_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(in, H * W, C, out);
   return launch_check("transpose_kernel");
+}
+
+extern "C" int creste_proj_head(const float* x, const float* w, const float* bias, int N, int H, int W, int C, int K,
+                                float* pred_nhwc, float* pred_nchw, float* x_nchw, void* stream) {
+  CRESTE_CHECK_ARG(x && w && (pred_nhwc || pred_nchw) && N > 0 && H > 0 && W > 0, "creste_proj_head: null pointer");
+  CRESTE_CHECK_ARG(C % 32 == 0 && C <= 512 && K >= 1 && K <= 32, "creste_proj_head: C %% 32 == 0, C <= 512, K <= 32");
+  const long long PQ = (long long)H * W, M = (long long)N * PQ;
+  long long blocks = (M + 255) / 256;
+  if (blocks > 148 * 8) blocks = 148 * 8;
+  cudaStream_t st = (cudaStream_t)stream;
+#define CRESTE_PROJ(KO)                                                                                         \
+  proj_head_kernel<KO><<<(int)blocks, 256, (size_t)KO * C * sizeof(float), st>>>(x, w, bias, M, C, PQ, pred_nhwc, \
+                                                                                pred_nchw, x_nchw, K)
+  if (K <= 2) CRESTE_PROJ(2);
+  else if (K <= 8) CRESTE_PROJ(8);
+  else if (K <= 16) CRESTE_PROJ(16);
+  else { 
+    CRESTE_CUDA(cudaFuncSetAttribute(proj_head_kernel<32>, cudaFuncAttributeMaxDynamicSharedMemorySize, 32 * 512 * 4));
+    CRESTE_PROJ(32);
+  }
+#undef CRESTE_PROJ
+  return launch_check("proj_head_kernel");
 }
 
 extern "C" int creste_upsample_concat(const float* skip, int Cs, const float* x, int N, int Hi,

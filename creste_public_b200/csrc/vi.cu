@@ -553,6 +553,7 @@ struct ViStripParams {
   int* sweeps_out;
   int B, H, W, R, c, max_sweeps, G, nt, lag;   // nt = compute threads (multiple of 32)
   float gamma, thr;
+  int warp_arrive;             // 1: one mbarrier arrival per WARP per sweep (after __syncwarp) instead of one per thread
 };
 
 __device__ __forceinline__ uint32_t vi_mapa(uint32_t addr, uint32_t rank) {
@@ -592,7 +593,7 @@ __device__ __forceinline__ bool vi_mbar_test(uint64_t* bar, uint32_t parity) {
 }
 
 template <int RT>
-__global__ void __launch_bounds__(RT <= 2 ? 640 : 544, 1) vi_strip_kernel(ViStripParams p) {
+__global__ void __launch_bounds__(RT <= 3 ? 640 : 544, 1) vi_strip_kernel(ViStripParams p) {
   // two X tiles [(R+2)][W+8] (interior col x at 4+x), then two v snapshots [R][W]
   extern __shared__ __align__(16) float sm[];
   __shared__ uint64_t s_mbar[2];
@@ -625,8 +626,9 @@ __global__ void __launch_bounds__(RT <= 2 ? 640 : 544, 1) vi_strip_kernel(ViStri
     s_fail = 0;
     for (int i = 0; i < VI2_RING; ++i)
       asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(vi_smem_u32(&s_postbar[i])), "r"(nwarps) : "memory");
-    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(vi_smem_u32(&s_mbar[0])), "r"(nt) : "memory");
-    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(vi_smem_u32(&s_mbar[1])), "r"(nt) : "memory");
+    const int arrivals = p.warp_arrive ? nwarps : nt;
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(vi_smem_u32(&s_mbar[0])), "r"(arrivals) : "memory");
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(vi_smem_u32(&s_mbar[1])), "r"(arrivals) : "memory");
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
   cluster.sync();
@@ -720,7 +722,15 @@ __global__ void __launch_bounds__(RT <= 2 ? 640 : 544, 1) vi_strip_kernel(ViStri
         if (i == dn_i) vi_st_async_v4(dn_dst + boff, X, dn_bar0 + (uint32_t)(buf * 8));
       }
       uint64_t* bar = &s_mbar[buf];
-      if (expecter) vi_mbar_arrive_expect(bar, halo_bytes);
+      if (p.warp_arrive) {
+        // the lanes' tile stores are ordered before lane 0's (release) arrival by the warp barrier: one shared-
+        // memory atomic per warp per sweep instead of 32 serialised ones on the same mbarrier word
+        __syncwarp();
+        if ((tid & 31) == 0) {
+          if (expecter) vi_mbar_arrive_expect(bar, halo_bytes);
+          else vi_mbar_arrive_cta(bar);
+        }
+      } else if (expecter) vi_mbar_arrive_expect(bar, halo_bytes);
       else vi_mbar_arrive_cta(bar);
       const uint32_t parity = (uint32_t)((ph >> 1) & 1);
       if (!vi_mbar_test(bar, parity)) {
@@ -976,7 +986,11 @@ extern "C" int creste_vi_solve(const float* r, float* v_out, float* q_out, float
       if ((c - 1) * R >= H) continue;                 // every strip needs at least one row
       int RT = 0;
       for (int t = 1; t <= 4; ++t)
-        if ((long long)cgn * ceil_div(R, t) <= (t <= 2 ? 608 : 512)) { RT = t; break; }
+        if ((long long)cgn * ceil_div(R, t) <= (t <= 3 ? 608 : 512)) { RT = t; break; }
+      if (const char* e = getenv("CRESTE_VI_RT")) {          // experiment knob: force the rows-per-thread blocking
+        const int t = atoi(e);
+        if (t >= 1 && t <= 4 && (long long)cgn * ceil_div(R, t) <= (t <= 3 ? 608 : 512)) RT = t;
+      }
       if (!RT) continue;
       int threads = cgn * ceil_div(R, RT);
       threads = (threads + 31) / 32 * 32;
@@ -984,6 +998,8 @@ extern "C" int creste_vi_solve(const float* r, float* v_out, float* q_out, float
       if (ssmem > 200 * 1024) continue;
       sp.R = R;
       sp.lag = (long long)R * W >= 2048 ? 8 : 24;
+      sp.warp_arrive = getenv("CRESTE_VI_THREAD_ARRIVE") ? 0 : 1;
+      if (const char* e = getenv("CRESTE_VI_LAG")) { const int l = atoi(e); if (l >= 2 && l < VI2_RING) sp.lag = l; }
       int mc = 0;
       int rc = RT == 1 ? vi_try_strip<1>(sp, c, threads, ssmem, st, &mc)
              : RT == 2 ? vi_try_strip<2>(sp, c, threads, ssmem, st, &mc)

@@ -414,6 +414,21 @@ def nhwc_to_nchw(x):
     return out
 
 
+def proj_head(x_nhwc, w_kc, bias, want_nchw=True, want_x_nchw=True):
+    """1x1 conv C -> K (K <= 32) + the NCHW copies the output dict wants, one pass over x.
+    -> (pred NHWC [N,H,W,K], pred NCHW [N,K,H,W] | None, x NCHW [N,C,H,W] | None)."""
+    x_nhwc = x_nhwc.contiguous()
+    N, H, W, Cc = x_nhwc.shape
+    K = w_kc.shape[0]
+    dev = x_nhwc.device
+    pred = torch.empty(N, H, W, K, device=dev)
+    pred_nchw = torch.empty(N, K, H, W, device=dev) if want_nchw else None
+    x_nchw = torch.empty(N, Cc, H, W, device=dev) if want_x_nchw else None
+    check(lib().creste_proj_head(ptr(x_nhwc), ptr(w_kc.contiguous()), ptr(bias), N, H, W, Cc, K, ptr(pred),
+                                 ptr(pred_nchw), ptr(x_nchw), stream()), "creste_proj_head")
+    return pred, pred_nchw, x_nchw
+
+
 def expert_visitation(traj_rc, map_ds, max_steps, H, W):
     """traj_rc [B,T,2] fp32 or fp64 CUDA -> counts [B,H,W] (reference loss_utils.py:1055-1116)."""
     traj_rc = traj_rc.contiguous()

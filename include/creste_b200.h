@@ -245,6 +245,12 @@ int creste_maxpool2_concat(const float* const* srcs_host, const int* chans_host,
 /* layout shuffles used at the module boundary (the reference's tensors are NCHW) */
 int creste_nchw_to_nhwc(const float* in, int N, int C, int H, int W, float* out, void* stream);
 int creste_nhwc_to_nchw(const float* in, int N, int H, int W, int C, float* out, void* stream);
+/* Projection head: 1x1 conv C -> K (K <= 32; the DeconvHead `proj`, creste/models/blocks/inpainting.py:52-68)
+ * fused with the NHWC -> NCHW change of its input (the `{prefix}_features` entry of the output dict).
+ *   x NHWC [N,H,W,C] (C % 32 == 0); w [K,C]; bias [K] or NULL; pred_nhwc [N,H,W,K] / pred_nchw [N,K,H,W] (either may
+ *   be NULL); x_nchw [N,C,H,W] or NULL.  Exact fp32 FFMA chain over ascending channels. */
+int creste_proj_head(const float* x, const float* w, const float* bias, int N, int H, int W, int C, int K,
+                     float* pred_nhwc, float* pred_nchw, float* x_nchw, void* stream);
 /* Layout helpers of the strided-convolution gradients (the stride-2 7x7 / 3x3 / 1x1 convs of the ResNet-18 BEV
  * trunk, creste/models/blocks/inpainting.py:80-90, differentiated by the reference's stage-2 step):
  *   creste_dilate       z [N,Hz,Wz,C] = 0 except z[n, p*stride, q*stride, :] = g[n,p,q,:]   (data gradient =

@@ -119,3 +119,23 @@ def test_maxpool_concat_and_layout(cuda):
     out, nchw = ops.maxpool2_concat(srcs, rows_out=4, want_nchw=True)
     assert torch.equal(nchw.cpu(), ref)
     assert torch.equal(ops.nhwc_to_nchw(out).cpu(), ref)
+
+
+@pytest.mark.parametrize("K,C,HW", [(32, 128, (64, 48)), (6, 128, (33, 31)), (2, 128, (16, 16)), (12, 64, (8, 40))])
+def test_proj_head_equals_generic_conv_and_transposes(cuda, K, C, HW):
+    """creste_proj_head (1x1 conv C -> K <= 32 fused with the NCHW copies) is bit-identical to the exact-fp32 generic
+    conv followed by the two layout kernels: same FFMA chain over ascending channels."""
+    from creste_public_b200 import ops
+    torch.manual_seed(K)
+    H, W = HW
+    x = torch.randn(3, H, W, C, device="cuda")
+    w = torch.randn(K, C, 1, 1, device="cuda") / C ** 0.5
+    b = torch.randn(K, device="cuda")
+    want = ops.conv2d(x, ops.pack_conv_weight(w), K, 1, 1, 1, (0, 0, 0, 0), None, b, None, None, "none", False, "fp32")
+    pred, pred_nchw, x_nchw = ops.proj_head(x, w.reshape(K, C).contiguous(), b)
+    assert torch.equal(pred, want)
+    assert torch.equal(pred_nchw, ops.nhwc_to_nchw(want))
+    assert torch.equal(x_nchw, ops.nhwc_to_nchw(x))
+    p2, n2, x2 = ops.proj_head(x, w.reshape(K, C).contiguous(), None, want_nchw=False, want_x_nchw=False)
+    assert n2 is None and x2 is None
+    assert torch.equal(p2, ops.conv2d(x, ops.pack_conv_weight(w), K, 1, 1, 1, (0, 0, 0, 0), precision="fp32"))

@@ -268,3 +268,8 @@ class EffNet(nn.Module):
         if isinstance(r, tuple):
             return tuple(ops.nhwc_to_nchw(t) for t in r)
         return ops.nhwc_to_nchw(r)
+
+
+# names this mirror does not define fall through to the reference's file when the mirror is overlaid on a checkout
+from creste_public_b200.creste import _overlay  # noqa: E402
+__getattr__ = _overlay.fallback(__name__, "models/blocks/effnet.py")

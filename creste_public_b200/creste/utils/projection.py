@@ -80,3 +80,8 @@ def make_rgbd(rgb, pc, lidar2camrect):
     ops.lidar_raster(pc if isinstance(pc, torch.Tensor) else torch.from_numpy(np.asarray(pc, np.float32)).cuda(),
                      np.asarray(lidar2camrect)[:3, :4].astype(np.float64), H, W, out_mm=out[3], want_m=False)
     return out
+
+
+# names this mirror does not define fall through to the reference's file when the mirror is overlaid on a checkout
+from creste_public_b200.creste import _overlay  # noqa: E402
+__getattr__ = _overlay.fallback(__name__, "utils/projection.py")

@@ -58,6 +58,16 @@ def reference_available() -> bool:
 _installed = False
 
 
+def install_lightning():
+    """Replace the auto-mocked pytorch_lightning by a stand-in whose LightningModule is a real nn.Module, so that the
+    reference's train scripts can be imported and their step methods driven (tests/test_dropin_cpu.py)."""
+    from . import lightning_shim
+    _MOCK_ROOTS.discard("pytorch_lightning")
+    for k in [k for k in sys.modules if k == "pytorch_lightning" or k.startswith("pytorch_lightning.")]:
+        del sys.modules[k]
+    return lightning_shim.install()
+
+
 def install():
     """Idempotently install the shim set and put the reference on sys.path."""
     global _installed

@@ -579,13 +579,39 @@ def supcon_bwd(f, a, lf, la, self_off, temperature, class_weights, stats, scale_
     return df * scale_dev.reshape(()), da * scale_dev.reshape(())
 
 
+# ------------------------------------------------------------ eval / IRL stand-ins over the C oracle
+def vi_solve(r, gamma=0.99, thr=1e-3, max_sweeps=4096, want_q=True):
+    from oracle import c_oracle
+    r3 = r.detach().reshape(r.shape[0], r.shape[-2], r.shape[-1]).float().numpy()
+    v, q, pi, K = c_oracle.vi_solve(r3, gamma, thr, max_sweeps)
+    B, H, W = r3.shape
+    return (torch.from_numpy(v).view(B, 1, H, W), torch.from_numpy(q), torch.from_numpy(pi),
+            torch.tensor([K, 0], dtype=torch.int32))
+
+
+def svf(policy, expert_rc, fov, T, ds=2, sharpen=True, temperature=0.005, zero_terminal=False):
+    from oracle import c_oracle
+    s, st, g = c_oracle.svf(policy.detach().float().numpy(), expert_rc.detach().float().numpy(),
+                            fov.detach().to(torch.uint8).numpy(), T, ds, sharpen, temperature, zero_terminal)
+    return torch.from_numpy(s), torch.from_numpy(st), torch.from_numpy(g)
+
+
+def maxpool2_concat(srcs_nhwc, rows_out=None, want_nchw=False):
+    x = torch.cat(list(srcs_nhwc), dim=-1)
+    y = _nhwc(F.max_pool2d(_nchw(x), 2, 2))
+    if rows_out is not None:
+        y = y[:, :rows_out].contiguous()
+    return (y, _nchw(y)) if want_nchw else y
+
+
 STAGE1_NAMES = ["bn_fwd_finalize", "bn_bwd_finalize", "chan_moments", "chan_affine_act", "bn_act_bwd", "chan_axpby", "dwconv_fwd", "dwconv_dgrad",
                 "dwconv_wgrad", "sample_dot", "sample_affine", "act", "act_bwd", "add_scaled", "chan_slice",
                 "wgrad_strided", "wgrad_rows", "conv2d", "pack_conv_weight", "upsample_concat", "stage1_depth_losses",
                 "ce_depth_bwd", "masked_mse", "masked_mse_bwd", "depth_expectation"]
 STAGE2_NAMES = ["dilate", "phase_slice", "upsample_adjoint", "frustum_to_bev", "frustum_bwd", "splat_soft",
                 "splat_soft_bwd", "depth_expectation_bwd", "bin_depths", "smooth_l1", "smooth_l1_bwd", "ce_weighted",
-                "ce_weighted_bwd", "l2norm_rows", "l2norm_rows_bwd", "supcon_fwd", "supcon_bwd"]
+                "ce_weighted_bwd", "l2norm_rows", "l2norm_rows_bwd", "supcon_fwd", "supcon_bwd", "vi_solve", "svf",
+                "maxpool2_concat"]
 
 
 @contextlib.contextmanager

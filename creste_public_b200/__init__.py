@@ -59,3 +59,22 @@ def install_as_creste(reference_root=None):
         m = types.ModuleType("datasets")
         m.__path__ = [ds]
         sys.modules["datasets"] = m
+
+
+def build_maxentirl(cfg=None, image_size=(512, 960), solve_mdp=False, map_size=(64, 128),
+                    action_horizon=50):
+    """MaxEntIRL (reference creste/models/lfd.py) from a composed config (DictConfig / dict) or
+    the shipped defaults."""
+    from . import configs
+    from .config import as_cfg
+    from .creste.models.lfd import MaxEntIRL
+    if cfg is None:
+        cfg = configs.irl_cfg(image_size, map_size, solve_mdp, action_horizon)
+    return MaxEntIRL(as_cfg(cfg))
+
+
+def build_terrainnet(cfg=None, image_size=(512, 960)):
+    from . import configs
+    from .config import as_cfg
+    from .creste.models.terrainnet import TerrainNet
+    return TerrainNet(as_cfg(cfg if cfg is not None else configs.ssc_cfg(image_size)))

@@ -21,7 +21,8 @@ def install_as_creste(reference_root=None):
     scripts): puts this package directory first on sys.path.
 
     reference_root: path of a ut-amrl/creste_public checkout.  Given, the mirror is OVERLAID on it: the mirror's
-    packages (`creste`, `creste.models`, `creste.models.blocks`, `creste.models.losses`, `creste.utils`) get the
+    packages (`creste`, `creste.models`, `creste.models.blocks`, `creste.models.losses`, `creste.utils`,
+    `creste.datasets`) get the
     reference's directories appended to their __path__, so every module the mirror provides shadows the
     reference's, and everything else the train scripts import (`creste.datasets.*`, `creste.utils.visualization`,
     `creste.utils.tb_utils`, ...) falls through to the reference tree unchanged.  `<reference_root>/creste` is also
@@ -39,7 +40,8 @@ def install_as_creste(reference_root=None):
     from .creste import _overlay
     _overlay.REFERENCE_ROOT = reference_root
     _overlay._loaded.clear()
-    for name in ("creste", "creste.models", "creste.models.blocks", "creste.models.losses", "creste.utils"):
+    for name in ("creste", "creste.models", "creste.models.blocks", "creste.models.losses", "creste.utils",
+                 "creste.datasets"):
         pkg = importlib.import_module(name)
         extra = os.path.join(reference_root, *name.split("."))
         if os.path.isdir(extra) and extra not in pkg.__path__:

@@ -157,7 +157,8 @@ class FusedConv:
         mode = precision or _PRECISION
         # shapes the tensor-core kernel does not serve (strided, C = 4 stem, K < 8 heads) run on
         # the exact-fp32 CUDA-core kernel -- a stricter precision, never a looser one
-        track = (precision or _PRECISION) in ("3xfp16", "fp16")
+        # (not under torch.jit.trace: the traced `creste::conv2d` op is a pure function of its inputs)
+        track = (precision or _PRECISION) in ("3xfp16", "fp16") and not torch.jit.is_tracing()
         mode = pick_mode(tuple(x_nhwc.shape), K, R, S, stride, pad, mode)
         w, scale, shift = self.packed(mode)
         # 3xFP16: max|out| is produced by this conv's epilogue and travels with the tensor (`_amax`), so the next

@@ -989,3 +989,110 @@ def supcon_bwd(f, a, lf, la, self_off, temperature, class_weights, stats, scale_
                                   ptr(stats.contiguous()), ptr(scale_dev.reshape(1).float().contiguous()), ptr(df), ptr(da),
                                   stream()), "creste_supcon_bwd")
     return df, da
+
+
+# ------------------------------------------------------------------ export path (torch.jit.trace)
+# Under torch.jit.trace the eval-forward entry points route through the `creste::` dispatcher ops of
+# creste_public_b200.torch_ops so that the tracer records them (scripts/runtime/compile.py:197 of the reference);
+# everywhere else the functions above are called directly.
+_RAW = {n: globals()[n] for n in ("conv2d", "dwconv_bn_swish", "se_gate", "upsample_concat", "maxpool2_concat",
+                                  "nchw_to_nhwc", "nhwc_to_nchw", "depth_expectation", "frustum_to_bev", "zmlp_concat",
+                                  "splat_soft", "proj_head")}
+
+
+def _tracing():
+    if not torch.jit.is_tracing():
+        return False
+    from . import torch_ops
+    return not torch_ops.inside()
+
+
+def _t_conv2d(x_nhwc, w_packed, K, R, S, stride=1, pad=(0, 0, 0, 0), scale=None, shift=None, gate=None, residual=None,
+              act="none", out_nchw=False, precision="fp32", amax_in=None, amax_out=None):
+    if _tracing():
+        return torch.ops.creste.conv2d(x_nhwc, w_packed, int(K), int(R), int(S), int(stride), [int(p) for p in pad], scale,
+                                       shift, gate, residual, act or "none", bool(out_nchw), precision)
+    return _RAW["conv2d"](x_nhwc, w_packed, K, R, S, stride, pad, scale, shift, gate, residual, act, out_nchw, precision,
+                          amax_in, amax_out)
+
+
+def _t_dwconv_bn_swish(x_nhwc, w_rsc, scale, shift, R, stride, pad):
+    if _tracing():
+        return torch.ops.creste.dwconv_bn_swish(x_nhwc, w_rsc, scale, shift, int(R), int(stride), [int(p) for p in pad])
+    return _RAW["dwconv_bn_swish"](x_nhwc, w_rsc, scale, shift, R, stride, pad)
+
+
+def _t_se_gate(chan_part, hw, w_red, b_red, w_exp, b_exp):
+    if _tracing():
+        return torch.ops.creste.se_gate(chan_part, int(hw), w_red, b_red, w_exp, b_exp)
+    return _RAW["se_gate"](chan_part, hw, w_red, b_red, w_exp, b_exp)
+
+
+def _t_upsample_concat(skip_nhwc, x_nhwc, out_hw, scale_factor=None, x_first=False):
+    if _tracing():
+        Hi, Wi = x_nhwc.shape[1], x_nhwc.shape[2]
+        if scale_factor is None:
+            rh, rw = Hi / out_hw[0], Wi / out_hw[1]
+        else:
+            sh, sw = (scale_factor, scale_factor) if not isinstance(scale_factor, (tuple, list)) else scale_factor
+            rh, rw = 1.0 / sh, 1.0 / sw
+        return torch.ops.creste.upsample_concat(skip_nhwc, x_nhwc, [int(out_hw[0]), int(out_hw[1])], float(rh), float(rw),
+                                                bool(x_first))
+    return _RAW["upsample_concat"](skip_nhwc, x_nhwc, out_hw, scale_factor, x_first)
+
+
+def _t_maxpool2_concat(srcs_nhwc, rows_out=None, want_nchw=False):
+    if _tracing():
+        rows = srcs_nhwc[0].shape[1] // 2 if rows_out is None else rows_out
+        a, b = torch.ops.creste.maxpool2_concat(list(srcs_nhwc), int(rows))
+        return (a, b) if want_nchw else a
+    return _RAW["maxpool2_concat"](srcs_nhwc, rows_out, want_nchw)
+
+
+def _t_nchw_to_nhwc(x):
+    return torch.ops.creste.nchw_to_nhwc(x.contiguous()) if _tracing() else _RAW["nchw_to_nhwc"](x)
+
+
+def _t_nhwc_to_nchw(x):
+    return torch.ops.creste.nhwc_to_nchw(x.contiguous()) if _tracing() else _RAW["nhwc_to_nchw"](x)
+
+
+def _t_depth_expectation(logits_nhwc, dmin=300.0, dmax=25600.0, out_div=1000.0):
+    if _tracing():
+        return torch.ops.creste.depth_expectation(logits_nhwc, float(dmin), float(dmax), float(out_div))
+    return _RAW["depth_expectation"](logits_nhwc, dmin, dmax, out_div)
+
+
+def _t_frustum_to_bev(depth, p2p, pc_range, voxel):
+    if _tracing():
+        return torch.ops.creste.frustum_to_bev(depth.contiguous().float(), p2p.contiguous().float(),
+                                               [float(v) for v in pc_range], [float(voxel[0]), float(voxel[1])])
+    return _RAW["frustum_to_bev"](depth, p2p, pc_range, voxel)
+
+
+def _t_zmlp_concat(feats_nhwc, z, w1, b1, w2, b2):
+    if _tracing():
+        return torch.ops.creste.zmlp_concat(feats_nhwc, z, w1, b1, w2, b2)
+    return _RAW["zmlp_concat"](feats_nhwc, z, w1, b1, w2, b2)
+
+
+def _t_splat_soft(xy, feats_nhwc, mask, H, W, min_weight=1.0, want_nhwc=True, want_nchw=True, want_idx=False):
+    if _tracing() and feats_nhwc is not None and not want_idx:
+        a, b, d = torch.ops.creste.splat_soft(xy, feats_nhwc, mask, int(H), int(W), float(min_weight))
+        return {"bev_nhwc": a if want_nhwc else None, "bev_nchw": b if want_nchw else None, "dens": d, "idx": None}
+    return _RAW["splat_soft"](xy, feats_nhwc, mask, H, W, min_weight, want_nhwc, want_nchw, want_idx)
+
+
+def _t_proj_head(x_nhwc, w_kc, bias, want_nchw=True, want_x_nchw=True):
+    if _tracing():
+        a, b, c = torch.ops.creste.proj_head(x_nhwc, w_kc, bias)
+        return a, (b if want_nchw else None), (c if want_x_nchw else None)
+    return _RAW["proj_head"](x_nhwc, w_kc, bias, want_nchw, want_x_nchw)
+
+
+for _n in list(_RAW):
+    _w = globals()["_t_" + _n]
+    _w.__doc__ = _RAW[_n].__doc__
+    _w.__name__ = _n
+    globals()[_n] = _w
+del _n, _w

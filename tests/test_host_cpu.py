@@ -174,3 +174,21 @@ def test_wgrad_tc_host_planning_without_gpu():
     n = L.creste_conv2d_wgrad_tc_workspace_bytes(C.byref(d))
     operands = 2 * (4 * 128 * 240 * 496 * 2) * 2
     assert operands < n < operands + 64 * 9 * 496 * 496 * 4 + 4096
+
+
+def test_export_ops_are_registered_with_the_dispatcher():
+    """creste_public_b200.torch_ops: every eval-forward entry point is a `creste::` dispatcher op (what torch.jit.trace
+    records, reference scripts/runtime/compile.py:197); off-trace calls bypass the dispatcher."""
+    from creste_public_b200 import ops, torch_ops
+    for name in torch_ops.NAMES:
+        op = getattr(torch.ops.creste, name)
+        assert "creste::" + name in str(op.default._schema)
+        assert name in ops._RAW and getattr(ops, name) is not ops._RAW[name]
+    # meta / fake implementation: shapes without a device
+    from torch._subclasses.fake_tensor import FakeTensorMode
+    with FakeTensorMode():
+        x = torch.empty(2, 16, 24, 32)
+        y = torch.ops.creste.conv2d(x, torch.empty(10), 64, 3, 3, 1, [1, 1, 1, 1], None, None, None, None, "relu", False, "fp32")
+        assert tuple(y.shape) == (2, 16, 24, 64)
+        a, b, d = torch.ops.creste.splat_soft(torch.empty(2, 50, 2), torch.empty(2, 50, 8), None, 16, 16, 1.0)
+        assert tuple(a.shape) == (2, 16, 16, 8) and tuple(b.shape) == (2, 8, 16, 16) and tuple(d.shape) == (2, 1, 16, 16)

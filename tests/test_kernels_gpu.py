@@ -253,3 +253,20 @@ def test_projection_mirror_pixels_to_depth(cuda, golden):
     assert np.array_equal(img, g["depth_m"])
     rgbd = pj.make_rgbd(torch.zeros(3, H, W), pc, synth.lidar2camrect(H, W))
     assert np.array_equal(rgbd[3].cpu().numpy(), g["depth_mm"].astype(np.float32))
+
+
+def test_os1_file_to_depth_png_pipeline(cuda, tmp_path):
+    """Formats either side of the raster kernel: an OS1 `.bin` sweep (5 float32 per point) -> creste_lidar_raster ->
+    the uint16-mm depth PNG the reference's preprocessing writes -> read back as the network's 4th channel: identical
+    to the C oracle of projection.py:64-134 + build_dense_depth.py:461-463."""
+    from creste_public_b200.creste.datasets import coda_formats as fmt
+    H, W = 512, 960
+    pc5 = np.concatenate([synth.os1_scan(4), np.ones((131072, 2), np.float32)], axis=1)
+    fmt.write_os1_bin(str(tmp_path / "sweep.bin"), pc5)
+    pc = torch.from_numpy(fmt.read_os1_bin(str(tmp_path / "sweep.bin"))).cuda()
+    assert tuple(pc.shape) == (131072, 5)
+    _, dmm = _ops().lidar_raster(pc, synth.lidar2camrect(H, W), H, W, want_m=False)
+    fmt.write_depth_png(str(tmp_path / "0.png"), dmm.cpu().numpy())
+    back = fmt.read_depth_png(str(tmp_path / "0.png"))
+    _, want = co.lidar_raster(pc5, synth.lidar2camrect(H, W), H, W)
+    assert np.array_equal(back, want)

@@ -202,7 +202,7 @@ class Up(nn.Module):
         sf = self.up.scale_factor
         sh, sw = (sf, sf) if not isinstance(sf, (tuple, list)) else sf
         Ho, Wo = int(math.floor(x1.shape[1] * sh)), int(math.floor(x1.shape[2] * sw))
-        x = engine.carry_amax(ops.upsample_concat(x2, x1, (Ho, Wo), sf), x2, x1)
+        x = engine.upsample_concat_for(self._f0, x2, x1, (Ho, Wo), sf)
         return self._f1(self._f0(x, act="relu"), act="relu")
 
     def forward(self, x1, x2):

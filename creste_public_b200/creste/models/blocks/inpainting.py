@@ -7,7 +7,7 @@ import torch
 from torch import nn
 
 from creste_public_b200 import ops
-from creste_public_b200.engine import FusedConv, carry_amax, require_eval
+from creste_public_b200.engine import FusedConv, carry_amax, require_eval, upsample_concat_for
 from .effnet import Up
 
 
@@ -105,7 +105,7 @@ class DeconvHead(nn.Module):
             return self.forward_train(x1, x2)
         x = self.up1.forward_nhwc(x1, x2)
         N, H, W, _ = x.shape
-        x = carry_amax(ops.upsample_concat(None, x, (2 * H, 2 * W), 2), x)
+        x = upsample_concat_for(self._f_up2, None, x, (2 * H, 2 * W), 2)
         x = self._f_up2(x, act="relu")
         return self._f_proj(x, act="none"), x
 
@@ -115,7 +115,7 @@ class DeconvHead(nn.Module):
         -> (pred NHWC, features NHWC, pred NCHW | None, features NCHW | None)."""
         x = self.up1.forward_nhwc(x1, x2)
         N, H, W, _ = x.shape
-        x = carry_amax(ops.upsample_concat(None, x, (2 * H, 2 * W), 2), x)
+        x = upsample_concat_for(self._f_up2, None, x, (2 * H, 2 * W), 2)
         x = self._f_up2(x, act="relu")
         K, Cc = self.proj.weight.shape[0], self.proj.weight.shape[1]
         if K > 32 or Cc % 32 or Cc > 512:

@@ -10,6 +10,9 @@ int conv_tc_launch(const creste_conv_desc* d, const float* x, const float* w_pac
                    const float* scale, const float* shift, const float* gate, const float* residual,
                    float* out, const float* amax_in, unsigned* amax_out, void* ws, size_t ws_bytes,
                    cudaStream_t st);
+int conv_tc_presplit_launch(const creste_conv_desc* d, const void* x_hi, const void* x_lo, const float* x_scal,
+                            const float* w_packed, const float* scale, const float* shift, const float* residual,
+                            float* out, unsigned* amax_out, cudaStream_t st);
 size_t conv_tc_workspace_bytes(const creste_conv_desc* d);
 bool conv_tc_supported(const creste_conv_desc* d);
 
@@ -324,6 +327,23 @@ extern "C" int creste_conv2d_ex(const creste_conv_desc* d, const float* x, const
     return CRESTE_ERR_ARG;
   }
   return conv_tc_launch(d, x, w_packed, scale, shift, gate, residual, out, amax_in, (unsigned*)amax_out, ws, ws_bytes, st);
+}
+
+extern "C" int creste_conv2d_presplit(const creste_conv_desc* d, const void* x_hi, const void* x_lo,
+                                      const float* x_scal, const float* w_packed, const float* scale,
+                                      const float* shift, const float* residual, float* out, float* amax_out,
+                                      void* stream) {
+  CRESTE_CHECK_ARG(d && x_hi && x_scal && w_packed && out, "creste_conv2d_presplit: null pointer");
+  CRESTE_CHECK_ARG(d->precision == 4 || d->precision == 5, "creste_conv2d_presplit: precision must be 4 (3xFP16) or 5 (fp16)");
+  CRESTE_CHECK_ARG(d->precision == 5 || x_lo, "creste_conv2d_presplit: the 3xFP16 mode needs the lo halves");
+  if (!conv_tc_supported(d)) {
+    set_error("creste_conv2d_presplit: shape not served by the tensor-core kernel (C=%d K=%d R=%d stride=%d)", d->C,
+              d->K, d->R, d->stride);
+    return CRESTE_ERR_ARG;
+  }
+  cudaStream_t st = (cudaStream_t)stream;
+  if (amax_out) CRESTE_CUDA(cudaMemsetAsync(amax_out, 0, sizeof(float), st));
+  return conv_tc_presplit_launch(d, x_hi, x_lo, x_scal, w_packed, scale, shift, residual, out, (unsigned*)amax_out, st);
 }
 
 extern "C" int creste_dwconv_num_parts(int N, int P, int Q) {

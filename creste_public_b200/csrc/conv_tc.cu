@@ -788,6 +788,10 @@ size_t conv_tc_workspace_bytes(const creste_conv_desc* d) {
   return d->precision == 1 ? 2 * align_up(n, 1024) : align_up(n, 1024);
 }
 
+static int conv_tc_main(const creste_conv_desc* d, float* x_hi, float* x_lo, float* scal, const float* w_packed,
+                        const float* scale, const float* shift, const float* residual, float* out, unsigned* amax_out,
+                        cudaStream_t st);
+
 int conv_tc_launch(const creste_conv_desc* d, const float* x, const float* w_packed, const float* scale,
                    const float* shift, const float* gate, const float* residual, float* out, const float* amax_in,
                    unsigned* amax_out, void* ws, size_t ws_bytes, cudaStream_t st) {
@@ -838,6 +842,25 @@ int conv_tc_launch(const creste_conv_desc* d, const float* x, const float* w_pac
     int rc = launch_check("tf32_split_kernel");
     if (rc) return rc;
   }
+  return conv_tc_main(d, x_hi, x_lo, scal, w_packed, scale, shift, residual, out, amax_out, st);
+}
+
+// operands already split (by the pre-pass above, or written that way by the producing kernel)
+int conv_tc_presplit_launch(const creste_conv_desc* d, const void* x_hi, const void* x_lo, const float* x_scal,
+                            const float* w_packed, const float* scale, const float* shift, const float* residual,
+                            float* out, unsigned* amax_out, cudaStream_t st) {
+  return conv_tc_main(d, (float*)x_hi, (float*)x_lo, (float*)x_scal, w_packed, scale, shift, residual, out, amax_out, st);
+}
+
+static int conv_tc_main(const creste_conv_desc* d, float* x_hi, float* x_lo, float* scal, const float* w_packed,
+                        const float* scale, const float* shift, const float* residual, float* out, unsigned* amax_out,
+                        cudaStream_t st) {
+  const bool f16 = d->precision == 4 || d->precision == 5;
+  const int split = d->precision == 1 || d->precision == 4;
+  int block_n, npad, cpad;
+  conv_tc_layout(d->K, d->C, d->R, d->S, &block_n, &npad, &cpad);
+  if (f16) cpad = (d->C + 63) / 64 * 64;
+  const int ktot = d->R * d->S * cpad;
   TcParams p;
   p.scale = scale; p.shift = shift; p.residual = residual; p.out = out;
   p.N = d->N; p.P = d->P; p.Q = d->Q; p.K = d->K;

@@ -1,6 +1,8 @@
 // layout.cu -- memory-bound glue kernels (NHWC): layout shuffles at the module boundary,
 // bilinear upsample + channel concat, 2x2 max-pool + concat + crop, expert-visitation raster.
 // All are pure HBM streaming kernels: float4-vectorised, channel-contiguous, grid-stride.
+#include <cuda_fp16.h>
+
 #include "common.cuh"
 
 namespace creste {
@@ -81,11 +83,30 @@ __global__ void __launch_bounds__(256) proj_head_kernel(const float* __restrict_
 // PyTorch upsample_bilinear2d (align_corners=False): src = max(r*(dst+0.5)-0.5, 0); i0 = (int)src;
 // i1 = i0 + (i0 < in-1); l1 = src - i0; l0 = 1 - l1;
 // out = l0h*(l0w*v00 + l1w*v01) + l1h*(l0w*v10 + l1w*v11).
+// SPLIT: instead of the fp32 tensor, write the 3xFP16 operand of the consuming tensor-core conv directly -- hi =
+// fp16(v * s), lo = fp16((v * s - hi) * 2^11) with the power-of-two scale s taken from the amax bounds that travel
+// with the two inputs (an interpolation / concat never exceeds the maximum of its inputs).  Saves the fp32 write, the
+// split pre-pass's read of it and one launch per consumer; same arithmetic per element as f16_split_kernel.
+template <bool SPLIT>
 __global__ void __launch_bounds__(256) upsample_concat_kernel(const float* __restrict__ skip, int Cs,
                                                               const float* __restrict__ x, int N,
                                                               int Hi, int Wi, int Cx, int Ho, int Wo,
                                                               float rh, float rw, int x_first,
-                                                              float* __restrict__ out) {
+                                                              float* __restrict__ out,
+                                                              const unsigned* __restrict__ amax_a,
+                                                              const unsigned* __restrict__ amax_b,
+                                                              uint2* __restrict__ hi, uint2* __restrict__ lo,
+                                                              float* __restrict__ scal) {
+  float sc = 1.0f;
+  if (SPLIT) {
+    unsigned b = __ldg(amax_a);
+    if (amax_b) b = max(b, __ldg(amax_b));
+    int e = (int)((b >> 23) & 0xffu) - 127;
+    if (b == 0u || !isfinite(__uint_as_float(b))) e = 14;
+    const int k = max(-100, min(100, 14 - e));
+    sc = __uint_as_float((unsigned)(127 + k) << 23);
+    if (blockIdx.x == 0 && threadIdx.x == 0) { scal[0] = sc; scal[1] = __uint_as_float((unsigned)(127 - k) << 23); }
+  }
   const int Ct = Cs + Cx;
   const int c4t = Ct / 4, cs4 = Cs / 4, cx4 = Cx / 4;
   const long long total = (long long)N * Ho * Wo * c4t;
@@ -117,7 +138,20 @@ __global__ void __launch_bounds__(256) upsample_concat_kernel(const float* __res
       v.x = CRESTE_LERP(x); v.y = CRESTE_LERP(y); v.z = CRESTE_LERP(z); v.w = CRESTE_LERP(w);
 #undef CRESTE_LERP
     }
-    reinterpret_cast<float4*>(out + pix * Ct)[c4] = v;
+    if (!SPLIT) {
+      reinterpret_cast<float4*>(out + pix * Ct)[c4] = v;
+    } else {
+      const float xs[4] = {v.x * sc, v.y * sc, v.z * sc, v.w * sc};
+      unsigned short h[4], l[4];
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        const __half hh = __float2half_rn(xs[j]);
+        h[j] = __half_as_ushort(hh);
+        l[j] = __half_as_ushort(__float2half_rn((xs[j] - __half2float(hh)) * 2048.0f));
+      }
+      hi[pix * c4t + c4] = make_uint2((unsigned)h[0] | ((unsigned)h[1] << 16), (unsigned)h[2] | ((unsigned)h[3] << 16));
+      if (lo) lo[pix * c4t + c4] = make_uint2((unsigned)l[0] | ((unsigned)l[1] << 16), (unsigned)l[2] | ((unsigned)l[3] << 16));
+    }
   }
 }
 
@@ -245,9 +279,22 @@ extern "C" int creste_upsample_concat(const float* skip, int Cs, const float* x,
   CRESTE_CHECK_ARG((Cs == 0 || skip) && Cs % 4 == 0 && Cx % 4 == 0 && Cx > 0,
                    "creste_upsample_concat: channel counts must be multiples of 4");
   const long long total = (long long)N * Ho * Wo * ((Cs + Cx) / 4);
-  upsample_concat_kernel<<<grid_for(total), 256, 0, (cudaStream_t)stream>>>(skip, Cs, x, N, Hi, Wi, Cx,
-                                                                           Ho, Wo, rh, rw, x_first, out);
+  upsample_concat_kernel<false><<<grid_for(total), 256, 0, (cudaStream_t)stream>>>(
+      skip, Cs, x, N, Hi, Wi, Cx, Ho, Wo, rh, rw, x_first, out, nullptr, nullptr, nullptr, nullptr, nullptr);
   return launch_check("upsample_concat_kernel");
+}
+
+extern "C" int creste_upsample_concat_split(const float* skip, int Cs, const float* x, int N, int Hi, int Wi, int Cx,
+                                            int Ho, int Wo, float rh, float rw, int x_first, const float* amax_a,
+                                            const float* amax_b, void* hi, void* lo, float* scal, void* stream) {
+  CRESTE_CHECK_ARG(x && hi && scal && amax_a, "creste_upsample_concat_split: null pointer");
+  CRESTE_CHECK_ARG((Cs == 0 || skip) && Cs % 4 == 0 && Cx % 4 == 0 && Cx > 0 && (Cs + Cx) % 8 == 0,
+                   "creste_upsample_concat_split: channel counts must be multiples of 4 (8 in total)");
+  const long long total = (long long)N * Ho * Wo * ((Cs + Cx) / 4);
+  upsample_concat_kernel<true><<<grid_for(total), 256, 0, (cudaStream_t)stream>>>(
+      skip, Cs, x, N, Hi, Wi, Cx, Ho, Wo, rh, rw, x_first, nullptr, (const unsigned*)amax_a, (const unsigned*)amax_b,
+      (uint2*)hi, (uint2*)lo, scal);
+  return launch_check("upsample_concat_kernel<split>");
 }
 
 extern "C" int creste_maxpool2_concat(const float* const* srcs, const int* chans, int nsrc, int N,

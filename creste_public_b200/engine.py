@@ -51,6 +51,7 @@ def drop_connect_scale(B, rate, device):
 def pick_mode(x_shape, K, R, S, stride, pad, mode):
     """Requested precision, or the next stricter one the shape is served by:
     3xfp16 -> 3xtf32 -> fp32 (never a looser one)."""
+    x_shape = tuple(int(v) for v in x_shape)
     chain = {"3xfp16": ["3xfp16", "3xtf32"], "3xtf32": ["3xtf32"], "tf32": ["tf32"], "fp16": ["fp16"], "fp32": []}[mode]
     # short reductions (1x1 convs with C <= 192: the MBConv expand / project and head convs) are
     # HBM-bound; measured per shape, the exact-fp32 FFMA kernel beats the tensor-core kernel there
@@ -78,6 +79,21 @@ def mark_written(tensors):
         torch._C._increment_version(ts)
 
 
+class _NoTrace:
+    """Suspend torch.jit.trace recording: pack / fold computations run as plain eager code whose RESULTS enter the
+    trace as constants -- the same graph whether a cache is cold (first trace run) or warm (the tracer's check run),
+    and shapes stay Python ints."""
+
+    def __enter__(self):
+        self.state = torch._C._get_tracing_state()
+        if self.state is not None:
+            torch._C._set_tracing_state(None)
+
+    def __exit__(self, *a):
+        if self.state is not None:
+            torch._C._set_tracing_state(self.state)
+
+
 class PackCache:
     """Per-module cache of device-side packed tensors, invalidated by parameter version."""
 
@@ -89,7 +105,7 @@ class PackCache:
         hit = self._store.get(key)
         if hit is not None and hit[0] == v:
             return hit[1]
-        with torch.no_grad():
+        with torch.no_grad(), _NoTrace():
             val = builder()
         self._store[key] = (v, val)
         return val
@@ -146,10 +162,23 @@ class FusedConv:
             return w, scale, shift
         return self.cache.get("w_" + mode, tensors, build)
 
+    def tc_mode(self, x_shape, pad=None, precision=None):
+        """The precision mode this conv would run in on an input of `x_shape` (callers that can hand over a
+        pre-split operand ask first)."""
+        conv = self.conv
+        K, _, R, S = (int(v) for v in conv.weight.shape)      # ints also under torch.jit.trace
+        if pad is None:
+            ph, pw = conv.padding if isinstance(conv.padding, tuple) else (conv.padding,) * 2
+            pad = (ph, ph, pw, pw)
+        stride = conv.stride[0] if isinstance(conv.stride, tuple) else conv.stride
+        return pick_mode(tuple(x_shape), K, R, S, stride, pad, precision or _PRECISION)
+
     def __call__(self, x_nhwc, act="none", pad=None, gate=None, residual=None, out_nchw=False,
                  precision=None):
+        if isinstance(x_nhwc, ops.SplitAct):
+            return self._call_presplit(x_nhwc, act, pad, residual, out_nchw, precision)
         conv = self.conv
-        K, _, R, S = conv.weight.shape
+        K, _, R, S = (int(v) for v in conv.weight.shape)      # ints also under torch.jit.trace
         if pad is None:
             ph, pw = conv.padding if isinstance(conv.padding, tuple) else (conv.padding,) * 2
             pad = (ph, ph, pw, pw)
@@ -169,6 +198,39 @@ class FusedConv:
         if track:
             out._amax = amax_out
         return out
+
+
+def _fused_presplit(self, xs, act, pad, residual, out_nchw, precision):
+    conv = self.conv
+    K, _, R, S = (int(v) for v in conv.weight.shape)
+    if pad is None:
+        ph, pw = conv.padding if isinstance(conv.padding, tuple) else (conv.padding,) * 2
+        pad = (ph, ph, pw, pw)
+    stride = conv.stride[0] if isinstance(conv.stride, tuple) else conv.stride
+    mode = pick_mode(tuple(xs.shape), K, R, S, stride, pad, precision or _PRECISION)
+    if mode not in ("3xfp16", "fp16"):
+        raise RuntimeError(f"pre-split operand handed to a conv that runs in mode {mode}")
+    w, scale, shift = self.packed(mode)
+    amax_out = torch.empty(1, device=xs.device)
+    out = ops.conv2d_presplit(xs, w, K, R, S, stride, pad, scale, shift, residual, act, out_nchw, mode, amax_out)
+    out._amax = amax_out
+    return out
+
+
+FusedConv._call_presplit = _fused_presplit
+
+
+def upsample_concat_for(conv, skip, x, out_hw, scale_factor):
+    """bilinear(x) (concatenated behind `skip`) as the input of FusedConv `conv`: written directly as that conv's
+    3xFP16 operand when the conv runs on the tensor cores and both inputs carry their amax bound; the plain fp32
+    tensor (with the bound attached) otherwise."""
+    Ct = x.shape[-1] + (0 if skip is None else skip.shape[-1])
+    shape = (x.shape[0], out_hw[0], out_hw[1], Ct)
+    ax, ask = carried_amax(x), (None if skip is None else carried_amax(skip))
+    if (_PRECISION in ("3xfp16", "fp16") and not torch.jit.is_tracing() and Ct % 8 == 0 and ax is not None
+            and (skip is None or ask is not None) and conv.tc_mode(shape) == _PRECISION):
+        return ops.upsample_concat_split(skip, x, out_hw, scale_factor, ask, ax, want_lo=(_PRECISION == "3xfp16"))
+    return carry_amax(ops.upsample_concat(skip, x, out_hw, scale_factor), skip, x)
 
 
 class GraphedForward:

@@ -339,6 +339,51 @@ def conv2d(x_nhwc, w_packed, K, R, S, stride=1, pad=(0, 0, 0, 0), scale=None, sh
     return out
 
 
+class SplitAct:
+    """An activation tensor held as the 3xFP16 operand of a tensor-core conv: fp16 hi / lo halves [N,H,W,C] and the
+    device scale record {s, 1/s}.  Produced by upsample_concat_split, consumed by conv2d_presplit."""
+
+    def __init__(self, hi, lo, scal, shape):
+        self.hi, self.lo, self.scal, self.shape = hi, lo, scal, tuple(shape)
+        self.device = hi.device
+
+
+def upsample_concat_split(skip_nhwc, x_nhwc, out_hw, scale_factor, amax_skip, amax_x, x_first=False, want_lo=True):
+    """upsample_concat whose output is written directly as a SplitAct (no fp32 tensor, no split pre-pass)."""
+    N, Hi, Wi, Cx = x_nhwc.shape
+    Ho, Wo = out_hw
+    if scale_factor is None:
+        rh, rw = Hi / Ho, Wi / Wo
+    else:
+        sh, sw = (scale_factor, scale_factor) if not isinstance(scale_factor, (tuple, list)) else scale_factor
+        rh, rw = 1.0 / sh, 1.0 / sw
+    Cs = 0 if skip_nhwc is None else skip_nhwc.shape[-1]
+    dev = x_nhwc.device
+    hi = torch.empty(N, Ho, Wo, Cs + Cx, dtype=torch.float16, device=dev)
+    lo = torch.empty_like(hi) if want_lo else None
+    scal = torch.empty(2, device=dev)
+    a, b = (amax_x, None) if skip_nhwc is None else (amax_skip, amax_x)
+    check(lib().creste_upsample_concat_split(ptr(skip_nhwc), Cs, ptr(x_nhwc), N, Hi, Wi, Cx, Ho, Wo, C.c_float(rh),
+                                             C.c_float(rw), int(bool(x_first)), ptr(a), ptr(b), ptr(hi), ptr(lo),
+                                             ptr(scal), stream()), "creste_upsample_concat_split")
+    return SplitAct(hi, lo, scal, (N, Ho, Wo, Cs + Cx))
+
+
+def conv2d_presplit(xs, w_packed, K, R, S, stride=1, pad=(0, 0, 0, 0), scale=None, shift=None, residual=None,
+                    act="none", out_nchw=False, precision="3xfp16", amax_out=None):
+    """Tensor-core conv on a SplitAct input (no activation pre-pass)."""
+    N, H, W, Cc = xs.shape
+    pt, pb, pl, pr = pad
+    P = (H + pt + pb - R) // stride + 1
+    Q = (W + pl + pr - S) // stride + 1
+    d = ConvDesc(N, H, W, Cc, K, R, S, stride, pt, pl, P, Q, ACT[act], int(out_nchw), PRECISION[precision])
+    out = torch.empty((N, K, P, Q) if out_nchw else (N, P, Q, K), device=xs.device)
+    check(lib().creste_conv2d_presplit(C.byref(d), ptr(xs.hi), ptr(xs.lo), ptr(xs.scal), ptr(w_packed), ptr(scale),
+                                       ptr(shift), ptr(residual), ptr(out), ptr(amax_out), stream()),
+          "creste_conv2d_presplit")
+    return out
+
+
 def dwconv_bn_swish(x_nhwc, w_rsc, scale, shift, R, stride, pad):
     """Depthwise conv + BN + swish; returns (out NHWC, chan_part [N,nparts,C] SE partial sums)."""
     N, H, W, Cc = x_nhwc.shape

@@ -191,6 +191,14 @@ int creste_conv2d(const creste_conv_desc* d, const float* x, const float* w_pack
 int creste_conv2d_ex(const creste_conv_desc* d, const float* x, const float* w_packed, const float* scale,
                      const float* shift, const float* gate, const float* residual, float* out,
                      const float* amax_in, float* amax_out, void* ws, size_t ws_bytes, void* stream);
+/* Tensor-core conv on operands that are ALREADY split (precision 4 = 3xFP16, 5 = single-pass fp16): x_hi / x_lo are
+ * dense fp16 [N,H,W,C] tensors holding fp16(x*s) and fp16((x*s - hi) * 2^11), x_scal = DEVICE float[2] {s, 1/s} --
+ * written by creste_upsample_concat_split (or any producer that knows a bound of its output).  No pre-pass over the
+ * activations; no gate operand.  x_lo may be NULL for precision 5. */
+int creste_conv2d_presplit(const creste_conv_desc* d, const void* x_hi, const void* x_lo, const float* x_scal,
+                           const float* w_packed, const float* scale, const float* shift, const float* residual,
+                           float* out, float* amax_out, void* stream);
+
 
 size_t creste_conv2d_workspace_bytes(const creste_conv_desc* d);
 /* tcgen05 path (precision 1, 2): 1 if the shape is served by the tensor-core kernel (stride 1 or 2, R, S <= 7,
@@ -233,6 +241,13 @@ int creste_se_gate(const float* chan_part, int nparts, float inv_hw, int N, int 
 int creste_upsample_concat(const float* skip, int Cs, const float* x, int N, int Hi, int Wi, int Cx,
                            int Ho, int Wo, float rh, float rw, int x_first, float* out,
                            void* stream);
+/* creste_upsample_concat writing the 3xFP16 operand of the consuming conv directly (hi / lo fp16 [N,Ho,Wo,Cs+Cx] and
+ * scal = {s, 1/s}); amax_a / amax_b: DEVICE float[1] bounds of max|skip| and max|x| (amax_b may be NULL when there is
+ * no skip).  lo may be NULL (single-pass fp16 consumer).  (Cs + Cx) % 8 == 0. */
+int creste_upsample_concat_split(const float* skip, int Cs, const float* x, int N, int Hi, int Wi, int Cx, int Ho,
+                                 int Wo, float rh, float rw, int x_first, const float* amax_a, const float* amax_b,
+                                 void* hi, void* lo, float* scal, void* stream);
+
 
 /* 2x2/2 max-pool over the channel-concatenation of up to 3 NCHW or NHWC sources, cropped to the
  * first `rows_out` output rows.  Replaces vin.py:104-115 (cat + max_pool2d + crop) and

@@ -6,7 +6,7 @@
  * --impl reference legs may load it.  The product path never calls into it.
  *
  * Parity status: PINNED -- every function here is checked bit-for-bit / to tolerance against
- * the reference's own Python code executed in the build container (tests/test_oracle_pin.py,
+ * the reference's own Python code executed in the build container (tests/test_oracle_cpu.py,
  * fixtures under tests/golden/ made by oracle/gen_golden.py).  The reference itself ships no
  * tests or golden vectors.
  *

@@ -4,7 +4,7 @@ TEST INFRASTRUCTURE ONLY (checker).  Only tests/, __graft_entry__.smoke() and be
 cpu_baseline / --impl reference legs may import this; the product package never does.
 
 Parity status: PINNED against the reference's own modules executed in the build container
-(tests/test_oracle_pin.py) and against tests/golden/*.npz (made by oracle/gen_golden.py from
+(tests/test_oracle_cpu.py) and against tests/golden/*.npz (made by oracle/gen_golden.py from
 the unmodified reference).  One boundary is UNPINNED BY THE REFERENCE ITSELF: the EfficientNet-B0
 trunk lives in the third-party `efficientnet_pytorch` package, which the reference neither
 vendors nor pins; `effnet_trunk_endpoints` restates that library's published

@@ -1,7 +1,7 @@
 """Import shims that let the UNMODIFIED reference (/root/reference) run in this container.
 
 TEST INFRASTRUCTURE ONLY.  Nothing here ships in the product path; it exists so that
-`oracle/gen_golden.py` and `tests/test_oracle_vs_reference.py` can execute the reference's
+`oracle/gen_golden.py` and `tests/test_oracle_cpu.py` / `tests/test_stage2_cpu.py` / `tests/test_dropin_cpu.py` can execute the reference's
 own Python code (creste.models.*, creste.utils.*) to pin the oracle restatement.
 
 The reference imports seven third-party packages that are not installed here (and there is

@@ -251,8 +251,11 @@ def ssc_batch(B, H, W, seed=0, G=256):
     g = np.random.default_rng(4200 + seed)
     batch = distill_batch(B, H, W, seed)
     batch["p2p"] = torch.from_numpy(make_p2p(H, W)).view(1, 1, 4, 4).repeat(B, 1, 1, 1)
+    # SAM masks: a few dozen segments per frame over a mostly unlabeled grid (the contrastive loss is O(N^2) in the
+    # number of sampled labelled cells: ~15 % coverage x 20 ids keeps N at the 2-3e4 rows of a real CODa batch
+    # rather than every cell of the map)
     cell = G // 16
-    ids = g.integers(0, 12, (B, 16, 16))
+    ids = g.integers(1, 21, (B, 16, 16)) * (g.random((B, 16, 16)) < 0.15)
     sam = np.repeat(np.repeat(ids, cell, axis=1), cell, axis=2)
     batch["3d_sam_label"] = torch.from_numpy(sam[:, None].astype(np.int64))
     dyn = np.zeros((B, 2, G, G), np.float32)

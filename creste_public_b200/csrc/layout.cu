@@ -109,48 +109,56 @@ __global__ void __launch_bounds__(256) upsample_concat_kernel(const float* __res
   }
   const int Ct = Cs + Cx;
   const int c4t = Ct / 4, cs4 = Cs / 4, cx4 = Cx / 4;
-  const long long total = (long long)N * Ho * Wo * c4t;
-  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total;
-       i += (long long)gridDim.x * blockDim.x) {
-    const int c4 = (int)(i % c4t);
-    const long long pix = i / c4t;
-    float4 v;
-    const bool is_skip = x_first ? (c4 >= cx4) : (c4 < cs4);
-    if (is_skip) {
-      v = __ldg(reinterpret_cast<const float4*>(skip + pix * Cs) + (x_first ? c4 - cx4 : c4));
-    } else {
-      const int ox = (int)(pix % Wo);
-      const int oy = (int)((pix / Wo) % Ho);
-      const int n = (int)(pix / ((long long)Wo * Ho));
-      const float sy = fmaxf(__fsub_rn(__fmul_rn(rh, __fadd_rn((float)oy, 0.5f)), 0.5f), 0.0f);
-      const float sx = fmaxf(__fsub_rn(__fmul_rn(rw, __fadd_rn((float)ox, 0.5f)), 0.5f), 0.0f);
-      const int y0 = (int)sy, x0 = (int)sx;
-      const int y1 = y0 + (y0 < Hi - 1 ? 1 : 0), x1 = x0 + (x0 < Wi - 1 ? 1 : 0);
-      const float l1h = __fsub_rn(sy, (float)y0), l0h = __fsub_rn(1.0f, l1h);
-      const float l1w = __fsub_rn(sx, (float)x0), l0w = __fsub_rn(1.0f, l1w);
-      const int cc = x_first ? c4 : c4 - cs4;
-      const float* b = x + (size_t)n * Hi * Wi * Cx;
-      const float4 v00 = __ldg(reinterpret_cast<const float4*>(b + ((size_t)y0 * Wi + x0) * Cx) + cc);
-      const float4 v01 = __ldg(reinterpret_cast<const float4*>(b + ((size_t)y0 * Wi + x1) * Cx) + cc);
-      const float4 v10 = __ldg(reinterpret_cast<const float4*>(b + ((size_t)y1 * Wi + x0) * Cx) + cc);
-      const float4 v11 = __ldg(reinterpret_cast<const float4*>(b + ((size_t)y1 * Wi + x1) * Cx) + cc);
+  // one warp per output pixel, lanes over the 4-channel groups: the pixel decode (three integer divisions), the
+  // source taps and the interpolation weights are computed once per pixel per warp instead of once per element
+  // (five 64-bit divisions per float4 made the element-per-thread form issue-bound at ~30 % of HBM rate)
+  const int lane = threadIdx.x & 31;
+  const long long npix = (long long)N * Ho * Wo;
+  const long long warp0 = ((long long)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  const long long nwarps = ((long long)gridDim.x * blockDim.x) >> 5;
+  for (long long pix = warp0; pix < npix; pix += nwarps) {
+    const int ox = (int)(pix % Wo);
+    const long long t = pix / Wo;
+    const int oy = (int)(t % Ho);
+    const int n = (int)(t / Ho);
+    const float sy = fmaxf(__fsub_rn(__fmul_rn(rh, __fadd_rn((float)oy, 0.5f)), 0.5f), 0.0f);
+    const float sx = fmaxf(__fsub_rn(__fmul_rn(rw, __fadd_rn((float)ox, 0.5f)), 0.5f), 0.0f);
+    const int y0 = (int)sy, x0 = (int)sx;
+    const int y1 = y0 + (y0 < Hi - 1 ? 1 : 0), x1 = x0 + (x0 < Wi - 1 ? 1 : 0);
+    const float l1h = __fsub_rn(sy, (float)y0), l0h = __fsub_rn(1.0f, l1h);
+    const float l1w = __fsub_rn(sx, (float)x0), l0w = __fsub_rn(1.0f, l1w);
+    const float* b = x + (size_t)n * Hi * Wi * Cx;
+    const float4* p00 = reinterpret_cast<const float4*>(b + ((size_t)y0 * Wi + x0) * Cx);
+    const float4* p01 = reinterpret_cast<const float4*>(b + ((size_t)y0 * Wi + x1) * Cx);
+    const float4* p10 = reinterpret_cast<const float4*>(b + ((size_t)y1 * Wi + x0) * Cx);
+    const float4* p11 = reinterpret_cast<const float4*>(b + ((size_t)y1 * Wi + x1) * Cx);
+    const float4* ps = Cs ? reinterpret_cast<const float4*>(skip + pix * Cs) : nullptr;
+    for (int c4 = lane; c4 < c4t; c4 += 32) {
+      float4 v;
+      const bool is_skip = x_first ? (c4 >= cx4) : (c4 < cs4);
+      if (is_skip) {
+        v = __ldg(ps + (x_first ? c4 - cx4 : c4));
+      } else {
+        const int cc = x_first ? c4 : c4 - cs4;
+        const float4 v00 = __ldg(p00 + cc), v01 = __ldg(p01 + cc), v10 = __ldg(p10 + cc), v11 = __ldg(p11 + cc);
 #define CRESTE_LERP(f) (l0h * (l0w * v00.f + l1w * v01.f) + l1h * (l0w * v10.f + l1w * v11.f))
-      v.x = CRESTE_LERP(x); v.y = CRESTE_LERP(y); v.z = CRESTE_LERP(z); v.w = CRESTE_LERP(w);
+        v.x = CRESTE_LERP(x); v.y = CRESTE_LERP(y); v.z = CRESTE_LERP(z); v.w = CRESTE_LERP(w);
 #undef CRESTE_LERP
-    }
-    if (!SPLIT) {
-      reinterpret_cast<float4*>(out + pix * Ct)[c4] = v;
-    } else {
-      const float xs[4] = {v.x * sc, v.y * sc, v.z * sc, v.w * sc};
-      unsigned short h[4], l[4];
-#pragma unroll
-      for (int j = 0; j < 4; ++j) {
-        const __half hh = __float2half_rn(xs[j]);
-        h[j] = __half_as_ushort(hh);
-        l[j] = __half_as_ushort(__float2half_rn((xs[j] - __half2float(hh)) * 2048.0f));
       }
-      hi[pix * c4t + c4] = make_uint2((unsigned)h[0] | ((unsigned)h[1] << 16), (unsigned)h[2] | ((unsigned)h[3] << 16));
-      if (lo) lo[pix * c4t + c4] = make_uint2((unsigned)l[0] | ((unsigned)l[1] << 16), (unsigned)l[2] | ((unsigned)l[3] << 16));
+      if (!SPLIT) {
+        reinterpret_cast<float4*>(out + pix * Ct)[c4] = v;
+      } else {
+        const float xs[4] = {v.x * sc, v.y * sc, v.z * sc, v.w * sc};
+        unsigned short h[4], l[4];
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+          const __half hh = __float2half_rn(xs[j]);
+          h[j] = __half_as_ushort(hh);
+          l[j] = __half_as_ushort(__float2half_rn((xs[j] - __half2float(hh)) * 2048.0f));
+        }
+        hi[pix * c4t + c4] = make_uint2((unsigned)h[0] | ((unsigned)h[1] << 16), (unsigned)h[2] | ((unsigned)h[3] << 16));
+        if (lo) lo[pix * c4t + c4] = make_uint2((unsigned)l[0] | ((unsigned)l[1] << 16), (unsigned)l[2] | ((unsigned)l[3] << 16));
+      }
     }
   }
 }
@@ -278,7 +286,7 @@ extern "C" int creste_upsample_concat(const float* skip, int Cs, const float* x,
   CRESTE_CHECK_ARG(x && out, "creste_upsample_concat: null pointer");
   CRESTE_CHECK_ARG((Cs == 0 || skip) && Cs % 4 == 0 && Cx % 4 == 0 && Cx > 0,
                    "creste_upsample_concat: channel counts must be multiples of 4");
-  const long long total = (long long)N * Ho * Wo * ((Cs + Cx) / 4);
+  const long long total = (long long)N * Ho * Wo * 32;      // one warp per output pixel
   upsample_concat_kernel<false><<<grid_for(total), 256, 0, (cudaStream_t)stream>>>(
       skip, Cs, x, N, Hi, Wi, Cx, Ho, Wo, rh, rw, x_first, out, nullptr, nullptr, nullptr, nullptr, nullptr);
   return launch_check("upsample_concat_kernel");
@@ -290,7 +298,7 @@ extern "C" int creste_upsample_concat_split(const float* skip, int Cs, const flo
   CRESTE_CHECK_ARG(x && hi && scal && amax_a, "creste_upsample_concat_split: null pointer");
   CRESTE_CHECK_ARG((Cs == 0 || skip) && Cs % 4 == 0 && Cx % 4 == 0 && Cx > 0 && (Cs + Cx) % 8 == 0,
                    "creste_upsample_concat_split: channel counts must be multiples of 4 (8 in total)");
-  const long long total = (long long)N * Ho * Wo * ((Cs + Cx) / 4);
+  const long long total = (long long)N * Ho * Wo * 32;
   upsample_concat_kernel<true><<<grid_for(total), 256, 0, (cudaStream_t)stream>>>(
       skip, Cs, x, N, Hi, Wi, Cx, Ho, Wo, rh, rw, x_first, nullptr, (const unsigned*)amax_a, (const unsigned*)amax_b,
       (uint2*)hi, (uint2*)lo, scal);

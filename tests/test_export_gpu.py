@@ -66,3 +66,52 @@ def test_trace_batch_generalises(cuda):
         after = model((a.cuda(), p2p.cuda()))["elevation_preds"]
         t = traced((a.cuda(), p2p.cuda()))["elevation_preds"]
     assert float((before - after).abs().max()) <= 1e-4 and float((t - after).abs().max()) <= 1e-4
+
+
+RUNTIME = r'''
+import sys, torch
+torch.ops.load_library(sys.argv[1])                      # C++ registration of creste:: over libcreste_b200.so
+assert "creste_public_b200" not in sys.modules
+m = torch.jit.load(sys.argv[2])
+io = torch.load(sys.argv[3])
+with torch.no_grad():
+    out = m((io["rgbd"].cuda(), io["p2p"].cuda()))
+assert "creste_public_b200" not in sys.modules            # no product Python was needed to run the traced model
+assert torch.equal(out["depth_preds_feats"].cpu(), io["feats"]) and torch.equal(out["depth_preds_bins"].cpu(), io["bins"])
+err = float((out["traversability_preds"].cpu() - io["costmap"]).abs().max())
+assert err <= 1e-4, err
+print("OK", err)
+'''
+
+
+def test_traced_model_runs_on_the_cpp_registered_ops(cuda, tmp_path):
+    """The TorchScript file the reference's compile.py would save runs in a process that never imports the Python
+    package: the `creste::` ops come from csrc_torch/libcreste_torch_ops.so (C++ TORCH_LIBRARY over the C ABI) -- the
+    library a libtorch runtime links."""
+    import os
+    import subprocess
+    import sys
+    import creste_public_b200 as cb
+    from creste_public_b200.csrc_torch import build as tb_build
+    lib = tb_build.build()
+    cb.set_precision("3xfp16")
+    try:
+        model = cb.build_maxentirl(image_size=(H, W)).eval()
+        model.load_state_dict(synth.seeded_state_dict(model.state_dict(), 0, "soft"))
+        model = model.cuda()
+        a, p2p = synth.net_inputs(H, W, 1, seed=0)
+        b, _ = synth.net_inputs(H, W, 1, seed=2)
+        with torch.no_grad():
+            traced = torch.jit.trace(model, ((a.cuda(), p2p.cuda()),), strict=False)
+            want = model((b.cuda(), p2p.cuda()))
+    finally:
+        cb.set_precision("fp32")
+    path, io = str(tmp_path / "model.pt"), str(tmp_path / "io.pt")
+    traced.save(path)
+    torch.save({"rgbd": b, "p2p": p2p, "feats": want["depth_preds_feats"].cpu(), "bins": want["depth_preds_bins"].cpu(),
+                "costmap": want["traversability_preds"].cpu()}, io)
+    script = tmp_path / "runtime.py"
+    script.write_text(RUNTIME)
+    res = subprocess.run([sys.executable, str(script), lib, path, io], capture_output=True, text=True, timeout=600,
+                         cwd=str(tmp_path), env={k: v for k, v in os.environ.items() if k != "PYTHONPATH"})
+    assert res.returncode == 0 and "OK" in res.stdout, res.stdout[-2000:] + res.stderr[-4000:]

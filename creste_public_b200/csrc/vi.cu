@@ -593,7 +593,7 @@ __device__ __forceinline__ bool vi_mbar_test(uint64_t* bar, uint32_t parity) {
 }
 
 template <int RT>
-__global__ void __launch_bounds__(RT <= 3 ? 640 : 544, 1) vi_strip_kernel(ViStripParams p) {
+__global__ void __launch_bounds__(RT <= 2 ? 896 : (RT == 3 ? 640 : 544), 1) vi_strip_kernel(ViStripParams p) {
   // two X tiles [(R+2)][W+8] (interior col x at 4+x), then two v snapshots [R][W]
   extern __shared__ __align__(16) float sm[];
   __shared__ uint64_t s_mbar[2];
@@ -870,6 +870,9 @@ __global__ void __launch_bounds__(RT <= 3 ? 640 : 544, 1) vi_strip_kernel(ViStri
   cluster.sync();   // no CTA may exit while a neighbour can still write into its shared memory
 }
 
+// threads an RT <= 2 strip may use: 864 (27 warps, <= 72 registers) when CRESTE_VI_WIDE is set, else 608
+static int vi_rt2_limit() { return getenv("CRESTE_VI_WIDE") ? 864 : 608; }
+
 template <int RT>
 static int vi_try_strip(ViStripParams& p, int c, int threads, size_t smem, cudaStream_t st, int* max_clusters_out) {
   auto kern = vi_strip_kernel<RT>;
@@ -986,10 +989,10 @@ extern "C" int creste_vi_solve(const float* r, float* v_out, float* q_out, float
       if ((c - 1) * R >= H) continue;                 // every strip needs at least one row
       int RT = 0;
       for (int t = 1; t <= 4; ++t)
-        if ((long long)cgn * ceil_div(R, t) <= (t <= 3 ? 608 : 512)) { RT = t; break; }
+        if ((long long)cgn * ceil_div(R, t) <= (t <= 2 ? vi_rt2_limit() : (t == 3 ? 608 : 512))) { RT = t; break; }
       if (const char* e = getenv("CRESTE_VI_RT")) {          // experiment knob: force the rows-per-thread blocking
         const int t = atoi(e);
-        if (t >= 1 && t <= 4 && (long long)cgn * ceil_div(R, t) <= (t <= 3 ? 608 : 512)) RT = t;
+        if (t >= 1 && t <= 4 && (long long)cgn * ceil_div(R, t) <= (t <= 2 ? 864 : (t == 3 ? 608 : 512))) RT = t;
       }
       if (!RT) continue;
       int threads = cgn * ceil_div(R, RT);

@@ -527,17 +527,39 @@ def run_ours(args):
             ops.lidar_raster(dev_pc[r][b], P34, H, W, out_mm=x[b, 0, 3], want_m=False)
         return model((x, dev_p2p))
 
-    stage = torch.zeros(B, 1, 4, H, W, device=dev)
+    # end-to-end leg: every step's inputs start in pinned HOST memory and its costmap ends there.  The copies run on a
+    # side stream into double-buffered staging tensors, one step ahead of the compute stream (what a prefetching
+    # loader does): every timed step still pays its own H2D (issued inside the timed region) and its own D2H.
+    stages = [torch.zeros(B, 1, 4, H, W, device=dev) for _ in range(2)]
+    pcs = [torch.empty(B, NPTS, 3, device=dev) for _ in range(2)]
+    p2ps = [torch.empty(B, 1, 4, 4, device=dev) for _ in range(2)]
     host_out = torch.empty(B, 1, 64, 128).pin_memory()
+    copy_stream = torch.cuda.Stream(device=dev)
+    ready = [torch.cuda.Event() for _ in range(2)]
+    consumed = [torch.cuda.Event() for _ in range(2)]
+    pending = {}
+
+    def issue_h2d(i):
+        r, slot = i % R, i % 2
+        with torch.cuda.stream(copy_stream):
+            copy_stream.wait_event(consumed[slot])              # the step that last used this slot has read it
+            stages[slot][:, :, :3].copy_(host_rgb[r], non_blocking=True)
+            pcs[slot].copy_(host_pc[r], non_blocking=True)
+            p2ps[slot].copy_(host_p2p, non_blocking=True)
+            ready[slot].record(copy_stream)
+        pending[i] = slot
 
     def step_e2e(i):
-        r = i % R
-        stage[:, :, :3].copy_(host_rgb[r], non_blocking=True)
-        pc = host_pc[r].to(dev, non_blocking=True)
-        p2p = host_p2p.to(dev, non_blocking=True)
+        if i not in pending:
+            issue_h2d(i)
+        slot = pending.pop(i)
+        issue_h2d(i + 1)                                        # next step's inputs travel under this step's compute
+        cur = torch.cuda.current_stream()
+        cur.wait_event(ready[slot])
         for b in range(B):
-            ops.lidar_raster(pc[b], P34, H, W, out_mm=stage[b, 0, 3], want_m=False)
-        out = model((stage, p2p))
+            ops.lidar_raster(pcs[slot][b], P34, H, W, out_mm=stages[slot][b, 0, 3], want_m=False)
+        out = model((stages[slot], p2ps[slot]))
+        consumed[slot].record(cur)
         host_out.copy_(out["traversability_preds"], non_blocking=True)
         return out
 

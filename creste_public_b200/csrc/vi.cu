@@ -23,6 +23,8 @@
 // final pass; HBM-bound if streamed, here served from L2/SMEM.
 #include <cooperative_groups.h>
 
+#include <type_traits>
+
 #include "common.cuh"
 
 namespace creste {
@@ -553,7 +555,6 @@ struct ViStripParams {
   int* sweeps_out;
   int B, H, W, R, c, max_sweeps, G, nt, lag;   // nt = compute threads (multiple of 32)
   float gamma, thr;
-  int warp_arrive;             // 1: one mbarrier arrival per WARP per sweep (after __syncwarp) instead of one per thread
 };
 
 __device__ __forceinline__ uint32_t vi_mapa(uint32_t addr, uint32_t rank) {
@@ -592,21 +593,78 @@ __device__ __forceinline__ bool vi_mbar_test(uint64_t* bar, uint32_t parity) {
   return ok != 0;
 }
 
-template <int RT>
-__global__ void __launch_bounds__(RT <= 2 ? 896 : (RT == 3 ? 640 : 544), 1) vi_strip_kernel(ViStripParams p) {
+// the same on 32-bit shared-window addresses held in registers (the hot loop sets every address up once)
+__device__ __forceinline__ void vi_mbar_arrive_expect_a(uint32_t bar, uint32_t bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void vi_mbar_arrive_a(uint32_t bar) {
+  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar) : "memory");
+}
+__device__ __forceinline__ bool vi_mbar_test_a(uint32_t bar, uint32_t parity) {
+  uint32_t ok;
+  asm volatile(
+      "{\n\t"
+      ".reg .pred P1;\n\t"
+      "mbarrier.try_wait.parity.shared::cta.b64 P1, [%1], %2;\n\t"
+      "selp.b32 %0, 1, 0, P1;\n\t"
+      "}"
+      : "=r"(ok)
+      : "r"(bar), "r"(parity)
+      : "memory");
+  return ok != 0;
+}
+// shared-memory accesses at [register + compile-time byte offset]: with a compile-time tile pitch every row of the
+// window is one base register plus an immediate, no address arithmetic in the loop
+template <int OFF>
+__device__ __forceinline__ void vi_sts_v4(uint32_t a, float4 v) {
+  asm volatile("st.shared.v4.f32 [%0+%5], {%1, %2, %3, %4};" ::"r"(a), "f"(v.x), "f"(v.y), "f"(v.z), "f"(v.w), "n"(OFF) : "memory");
+}
+__device__ __forceinline__ void vi_sts_u32(uint32_t a, unsigned v) {
+  asm volatile("st.shared.u32 [%0], %1;" ::"r"(a), "r"(v) : "memory");
+}
+template <int OFF>
+__device__ __forceinline__ float4 vi_lds_v4(uint32_t a) {
+  float4 v;
+  asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4+%5];" : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "r"(a), "n"(OFF) : "memory");
+  return v;
+}
+template <int OFF>
+__device__ __forceinline__ float vi_lds(uint32_t a) {
+  float v;
+  asm volatile("ld.shared.f32 %0, [%1+%2];" : "=f"(v) : "r"(a), "n"(OFF) : "memory");
+  return v;
+}
+// compile-time loop: f(std::integral_constant<int, I>) for I = 0 .. N-1
+template <int I, int N, class F>
+__device__ __forceinline__ void vi_static_for(F&& f) {
+  if constexpr (I < N) {
+    f(std::integral_constant<int, I>{});
+    vi_static_for<I + 1, N>(f);
+  }
+}
+// three-input maximum (FMNMX3): exact, so any association of a max tree gives the same bits
+__device__ __forceinline__ float vi_max3(float a, float b, float c) {
+  float d;
+  asm("max.f32 %0, %1, %2, %3;" : "=f"(d) : "f"(a), "f"(b), "f"(c));
+  return d;
+}
+
+// PW: compile-time tile pitch in floats (W + 8) for the widths that matter (64, 128, 256), 0 = run-time pitch
+template <int RT, int PW>
+__global__ void __launch_bounds__(RT <= 2 ? 896 : (RT == 3 ? 608 : 544), 1) vi_strip_kernel(ViStripParams p) {
   // two X tiles [(R+2)][W+8] (interior col x at 4+x), then two v snapshots [R][W]
   extern __shared__ __align__(16) float sm[];
   __shared__ uint64_t s_mbar[2];
   __shared__ uint64_t s_postbar[VI2_RING];   // per-sweep "all warps posted their max|dv|" barriers
   __shared__ unsigned s_wmax[VI2_RING][32];  // per-sweep, per-warp max|dv| (float bits)
-  __shared__ volatile int s_dec[VI2_RING];   // (sweep << 1) | stop, published by the comm warp
+  __shared__ volatile int s_done;            // every sweep <= s_done is decided (or lies beyond a known stop)
   __shared__ volatile int s_stopK;           // smallest sweep decided as the last one
   __shared__ volatile int s_fail;
   cg::cluster_group cluster = cg::this_cluster();
   const int cr = (int)cluster.block_rank();
   const int b = blockIdx.x / p.c;
   const int W = p.W, H = p.H;
-  const int P = W + 8;
+  const int P = PW ? PW : W + 8;
   const int tile = (p.R + 2) * P;
   const int row0 = cr * p.R;
   const int n = min(p.R, H - row0);
@@ -620,13 +678,13 @@ __global__ void __launch_bounds__(RT <= 2 ? 896 : (RT == 3 ? 640 : 544), 1) vi_s
 
   // halos / sample borders stay 0; snapshot slot 0 starts as v_0 = 0
   for (int i = tid; i < 2 * tile + 2 * p.R * W; i += blockDim.x) sm[i] = 0.0f;
-  if (tid < VI2_RING) s_dec[tid] = -2;
   if (tid == 0) {
+    s_done = 0;
     s_stopK = 0x7fffffff;
     s_fail = 0;
     for (int i = 0; i < VI2_RING; ++i)
       asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(vi_smem_u32(&s_postbar[i])), "r"(nwarps) : "memory");
-    const int arrivals = p.warp_arrive ? nwarps : nt;
+    const int arrivals = nwarps;          // one arrival per compute warp per sweep
     asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(vi_smem_u32(&s_mbar[0])), "r"(arrivals) : "memory");
     asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(vi_smem_u32(&s_mbar[1])), "r"(arrivals) : "memory");
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
@@ -639,6 +697,7 @@ __global__ void __launch_bounds__(RT <= 2 ? 896 : (RT == 3 ? 640 : 544), 1) vi_s
     int s = lane + 1;
     int state = (lane < VI2_RING && s <= p.max_sweeps) ? 0 : 2;   // 0 wait local, 1 wait global, 2 done
     unsigned spins = 0;
+    int done_pub = 0;
     while (__any_sync(0xffffffffu, state != 2)) {
       if (state != 2 && (s > s_stopK || s_fail)) state = 2;
       if (state == 0) {
@@ -658,20 +717,27 @@ __global__ void __launch_bounds__(RT <= 2 ? 896 : (RT == 3 ? 640 : 544), 1) vi_s
           const float dk = __uint_as_float((unsigned)(word & 0xffffffffu));
           const int stop = !(dk > p.thr);
           if (stop) atomicMin((int*)&s_stopK, s);
-          __threadfence_block();
-          s_dec[s % VI2_RING] = (s << 1) | stop;
           s += VI2_RING;
           state = (stop || s > p.max_sweeps) ? 2 : 0;
         }
       }
+      // watermark: every sweep below the smallest undecided one is decided.  A lane that retired (past max_sweeps,
+      // or beyond a stop that is already in s_stopK) no longer holds the watermark back.
+      __threadfence_block();
+      const int low = __reduce_min_sync(0xffffffffu, state == 2 ? 0x7fffffff : s);
+      if (lane == 0 && low - 1 > done_pub) { done_pub = low - 1; s_done = done_pub; }
       if (++spins > VI2_SPIN_LIMIT) { s_fail = 1; break; }
       __nanosleep(40);      // leave the issue slots of this scheduler to the compute warps
     }
     __syncwarp();
   } else {
-    // ===== compute threads: 4 columns x RT rows each.  The hot loop is branch-free: every thread
-    // loads and evaluates its RT rows unconditionally (rows past the strip read in-bounds junk) and
-    // only the stores / the running maximum are predicated by the per-row `on` mask.
+    // ===== compute threads: 4 columns x RT rows each.  The hot loop is branch-free apart from warp-uniform
+    // branches: every thread loads and evaluates its RT rows unconditionally (rows past the strip read in-bounds
+    // junk and keep junk in their v registers, which nothing ever stores) and only the tile stores / the running
+    // maximum are predicated by the per-row `on` mask.  Round-2 rewrite: the integer / control work of the loop
+    // (it ran on the 16-lane ALU pipe and cost more cycles than the FP work, profiles/r2_vi_experiments.md) is
+    // hoisted: shared-memory addresses are 32-bit registers set up once, the sweeps come in blocks of `lag` with
+    // a compile-time tile parity, and the stop decision is consumed once per block instead of once per sweep.
     const int cgn = W >> 2;
     const int rgn = (p.R + RT - 1) / RT;
     const bool thread_on = tid < cgn * rgn;
@@ -695,61 +761,88 @@ __global__ void __launch_bounds__(RT <= 2 ? 896 : (RT == 3 ? 640 : 544), 1) vi_s
     const int dn_i = (has_dn && thread_on && n - 1 >= lr0 && n - 1 < lr0 + RT) ? n - 1 - lr0 : -1;
     // remote byte addresses (tile 0): my top row -> bottom halo (row R+1) of the strip above; my
     // bottom row -> top halo (row 0) of the strip below
-    const uint32_t up_dst = push_up ? vi_mapa(sm_base, (uint32_t)(cr - 1)) + (uint32_t)(((p.R + 1) * P + 4 + x0) * 4) : 0u;
-    const uint32_t dn_dst = dn_i >= 0 ? vi_mapa(sm_base, (uint32_t)(cr + 1)) + (uint32_t)((4 + x0) * 4) : 0u;
-    const uint32_t up_bar0 = push_up ? vi_mapa(vi_smem_u32(&s_mbar[0]), (uint32_t)(cr - 1)) : 0u;
-    const uint32_t dn_bar0 = dn_i >= 0 ? vi_mapa(vi_smem_u32(&s_mbar[0]), (uint32_t)(cr + 1)) : 0u;
+    uint32_t up_dst = push_up ? vi_mapa(sm_base, (uint32_t)(cr - 1)) + (uint32_t)(((p.R + 1) * P + 4 + x0) * 4) : 0u;
+    uint32_t dn_dst = dn_i >= 0 ? vi_mapa(sm_base, (uint32_t)(cr + 1)) + (uint32_t)((4 + x0) * 4) : 0u;
+    uint32_t up_bar0 = push_up ? vi_mapa(vi_smem_u32(&s_mbar[0]), (uint32_t)(cr - 1)) : 0u;
+    uint32_t dn_bar0 = dn_i >= 0 ? vi_mapa(vi_smem_u32(&s_mbar[0]), (uint32_t)(cr + 1)) : 0u;
     const uint32_t halo_bytes = (uint32_t)(4 * W) * ((has_up ? 1u : 0u) + (has_dn ? 1u : 0u));
-    const bool expecter = tid == 0 && halo_bytes != 0;
-    float* const own0 = sm + (lr0 + 1) * P + 4 + x0;      // my first cell, tile 0
-    const float* const win0 = sm + lr0 * P + 4 + x0;      // row above my first cell, tile 0
+    const bool lane0 = (tid & 31) == 0;
+    uint32_t my_tx = tid == 0 ? halo_bytes : 0u;   // thread 0 also announces the halo bytes the neighbours push
+    uint32_t P4 = (uint32_t)P * 4u, tile4 = (uint32_t)tile * 4u;
+    uint32_t win_a = sm_base + (uint32_t)((lr0 * P + 4 + x0) * 4);   // row above my first cell, tile 0
+    uint32_t mbar_a = vi_smem_u32(&s_mbar[0]);
+    uint32_t wmax_a = vi_smem_u32(&s_wmax[0][tid >> 5]);
+    uint32_t post_a = vi_smem_u32(&s_postbar[0]);
+    // keep the loop-invariant addresses in registers: without this the compiler re-derives each of them from the
+    // kernel parameters and %cluster_ctaid at every use (a dozen integer instructions per shared-memory access)
+    asm volatile("" : "+r"(win_a), "+r"(P4), "+r"(tile4), "+r"(mbar_a), "+r"(wmax_a), "+r"(post_a));
+    asm volatile("" : "+r"(up_dst), "+r"(dn_dst), "+r"(up_bar0), "+r"(dn_bar0), "+r"(my_tx));
     bool failed = false;
 
-    // X = r + gamma*v of the own cells into tile ph&1 (+ halo pushes), arrive, wait for the phase
-    auto exchange = [&](int ph) {
-      const int buf = ph & 1;
-      float* mine = own0 + (buf ? tile : 0);
-      const uint32_t boff = buf ? (uint32_t)(tile * 4) : 0u;
+    // X = r + gamma*v of the own cells into tile `buf` (+ halo pushes), arrive, wait for the phase
+    auto exchange = [&](const uint32_t buf, const uint32_t parity) {
+      const uint32_t boff = buf ? tile4 : 0u;
+      const uint32_t a = win_a + boff;
+      float4 X[RT];
 #pragma unroll
       for (int i = 0; i < RT; ++i) {
-        float4 X;
-        X.x = __fadd_rn(rr[i].x, __fmul_rn(v[i].x, gamma));
-        X.y = __fadd_rn(rr[i].y, __fmul_rn(v[i].y, gamma));
-        X.z = __fadd_rn(rr[i].z, __fmul_rn(v[i].z, gamma));
-        X.w = __fadd_rn(rr[i].w, __fmul_rn(v[i].w, gamma));
-        if (on[i]) *reinterpret_cast<float4*>(mine + i * P) = X;
-        if (i == 0 && push_up) vi_st_async_v4(up_dst + boff, X, up_bar0 + (uint32_t)(buf * 8));
-        if (i == dn_i) vi_st_async_v4(dn_dst + boff, X, dn_bar0 + (uint32_t)(buf * 8));
+        X[i].x = __fadd_rn(rr[i].x, __fmul_rn(v[i].x, gamma));
+        X[i].y = __fadd_rn(rr[i].y, __fmul_rn(v[i].y, gamma));
+        X[i].z = __fadd_rn(rr[i].z, __fmul_rn(v[i].z, gamma));
+        X[i].w = __fadd_rn(rr[i].w, __fmul_rn(v[i].w, gamma));
       }
-      uint64_t* bar = &s_mbar[buf];
-      if (p.warp_arrive) {
-        // the lanes' tile stores are ordered before lane 0's (release) arrival by the warp barrier: one shared-
-        // memory atomic per warp per sweep instead of 32 serialised ones on the same mbarrier word
-        __syncwarp();
-        if ((tid & 31) == 0) {
-          if (expecter) vi_mbar_arrive_expect(bar, halo_bytes);
-          else vi_mbar_arrive_cta(bar);
+      if constexpr (PW > 0) {
+        vi_static_for<0, RT>([&](auto ic) {
+          constexpr int i = decltype(ic)::value;
+          if (on[i]) vi_sts_v4<(i + 1) * PW * 4>(a, X[i]);
+        });
+      } else {
+        uint32_t ai = a;
+#pragma unroll
+        for (int i = 0; i < RT; ++i) {
+          ai += P4;
+          if (on[i]) vi_sts_v4<0>(ai, X[i]);
         }
-      } else if (expecter) vi_mbar_arrive_expect(bar, halo_bytes);
-      else vi_mbar_arrive_cta(bar);
-      const uint32_t parity = (uint32_t)((ph >> 1) & 1);
-      if (!vi_mbar_test(bar, parity)) {
+      }
+      if (push_up) vi_st_async_v4(up_dst + boff, X[0], up_bar0 + buf * 8u);
+      if (dn_i >= 0) {
+        float4 Xd = X[0];
+#pragma unroll
+        for (int i = 1; i < RT; ++i) if (dn_i == i) Xd = X[i];
+        vi_st_async_v4(dn_dst + boff, Xd, dn_bar0 + buf * 8u);
+      }
+      const uint32_t bar = mbar_a + buf * 8u;
+      // the lanes' tile stores are ordered before lane 0's (release) arrival by the warp barrier: one shared-memory
+      // atomic per warp per sweep.  expect_tx(0) is a plain arrival, so one instruction serves every warp.
+      __syncwarp();
+      if (lane0) vi_mbar_arrive_expect_a(bar, my_tx);
+      if (!vi_mbar_test_a(bar, parity)) {
         unsigned spins = 0;
-        while (!vi_mbar_test(bar, parity)) {
+        while (!vi_mbar_test_a(bar, parity)) {
           if (++spins > VI2_SPIN_LIMIT) { failed = true; s_fail = 1; break; }
         }
       }
     };
 
-    // one Bellman sweep on tile ph&1: v <- max_a q ; returns max |dv| over the own cells
-    auto sweep = [&](int ph) -> float {
-      const float* X = win0 + ((ph & 1) ? tile : 0);
+    // one Bellman sweep on tile `buf`: v <- max_a q ; returns max |dv| over the own cells
+    auto sweep = [&](const uint32_t buf) -> float {
+      const uint32_t ra = win_a + (buf ? tile4 : 0u);
       float a[RT + 2][6];
+      if constexpr (PW > 0) {
+        vi_static_for<0, RT + 2>([&](auto ic) {
+          constexpr int i = decltype(ic)::value;
+          const float4 m = vi_lds_v4<i * PW * 4>(ra);
+          a[i][0] = vi_lds<i * PW * 4 - 4>(ra); a[i][1] = m.x; a[i][2] = m.y; a[i][3] = m.z; a[i][4] = m.w;
+          a[i][5] = vi_lds<i * PW * 4 + 16>(ra);
+        });
+      } else {
+        uint32_t ri = ra;
 #pragma unroll
-      for (int i = 0; i < RT + 2; ++i) {
-        const float* row = X + i * P;
-        const float4 m = *reinterpret_cast<const float4*>(row);
-        a[i][0] = row[-1]; a[i][1] = m.x; a[i][2] = m.y; a[i][3] = m.z; a[i][4] = m.w; a[i][5] = row[4];
+        for (int i = 0; i < RT + 2; ++i) {
+          const float4 m = vi_lds_v4<0>(ri);
+          a[i][0] = vi_lds<-4>(ri); a[i][1] = m.x; a[i][2] = m.y; a[i][3] = m.z; a[i][4] = m.w; a[i][5] = vi_lds<16>(ri);
+          ri += P4;
+        }
       }
       float dmax = 0.f;
 #pragma unroll
@@ -763,68 +856,82 @@ __global__ void __launch_bounds__(RT <= 2 ? 896 : (RT == 3 ? 640 : 544), 1) vi_s
 #pragma unroll
             for (int dx = 0; dx < 3; ++dx) win[dy][dx] = a[i + dy][j + dx];
           eval_q(win, q);
-          nv[j] = fmaxf(fmaxf(fmaxf(q[0], q[1]), fmaxf(q[2], q[3])), fmaxf(fmaxf(q[4], q[5]), fmaxf(q[6], q[7])));
+          nv[j] = fmaxf(vi_max3(q[0], q[1], q[2]), vi_max3(q[3], q[4], vi_max3(q[5], q[6], q[7])));
         }
-        const float d = fmaxf(fmaxf(fabsf(__fsub_rn(nv[0], v[i].x)), fabsf(__fsub_rn(nv[1], v[i].y))),
-                              fmaxf(fabsf(__fsub_rn(nv[2], v[i].z)), fabsf(__fsub_rn(nv[3], v[i].w))));
+        // max is exact and order-free, so the three-input form changes no bit
+        float d = vi_max3(0.0f, fabsf(__fsub_rn(nv[0], v[i].x)), fabsf(__fsub_rn(nv[1], v[i].y)));
+        d = vi_max3(d, fabsf(__fsub_rn(nv[2], v[i].z)), fabsf(__fsub_rn(nv[3], v[i].w)));
         dmax = fmaxf(dmax, on[i] ? d : 0.0f);
-        v[i].x = on[i] ? nv[0] : v[i].x; v[i].y = on[i] ? nv[1] : v[i].y;
-        v[i].z = on[i] ? nv[2] : v[i].z; v[i].w = on[i] ? nv[3] : v[i].w;
+        v[i] = make_float4(nv[0], nv[1], nv[2], nv[3]);
       }
       return dmax;
     };
 
-    int K = p.max_sweeps, hit_max = 1, ph = 0;
-    for (int s = 1; !failed; ++s) {
-      exchange(ph);
-      float dmax = sweep(ph);
-      ++ph;
-      if (s <= p.max_sweeps) {
-        // warp max in ONE instruction (non-negative floats order like their bit patterns), then a
-        // plain store + mbarrier arrive: nothing on this path returns a value to wait for
-        const unsigned wm = __reduce_max_sync(0xffffffffu, __float_as_uint(dmax));
-        if ((tid & 31) == 0) {
-          const int slot = (s - 1) % VI2_RING;
-          s_wmax[slot][tid >> 5] = wm;
-          vi_mbar_arrive_cta(&s_postbar[slot]);
-        }
+    // warp max of max|dv| in ONE instruction (non-negative floats order like their bit patterns), then a plain
+    // store + mbarrier arrive by lane 0: nothing on this path returns a value to wait for
+    auto post = [&](const int s, const float dmax) {
+      const unsigned wm = __reduce_max_sync(0xffffffffu, __float_as_uint(dmax));
+      if (lane0) {
+        const uint32_t slot = (uint32_t)(s - 1) & (uint32_t)(VI2_RING - 1);
+        vi_sts_u32(wmax_a + slot * 128u, wm);
+        vi_mbar_arrive_a(post_a + slot * 8u);
       }
-      if (s % p.lag == 0) {      // snapshot v_s into slot (s / lag) & 1 (own cells only)
-        float* dst = ckpt + ((s / p.lag) & 1) * ck_stride;
-#pragma unroll
-        for (int i = 0; i < RT; ++i)
-          if (on[i]) *reinterpret_cast<float4*>(dst + (lr0 + i) * W + x0) = v[i];
+    };
+
+    // Blocks of `lag` sweeps (lag even: the tile parity is a compile-time constant inside the block).  At the end of
+    // block m (s = m*lag sweeps done) the decisions of every sweep <= J = (m-1)*lag are awaited -- they are at least
+    // `lag` sweeps old, so the wait is normally already satisfied -- and only then v_s is snapshotted into slot m & 1:
+    // a stop at K in ((m-2)*lag, (m-1)*lag] finds both candidate snapshots, (m-2)*lag and (m-1)*lag, still alive.
+    const int lag = p.lag;
+    int K = p.max_sweeps, hit_max = 1, s = 0;
+    uint32_t par = 0;                       // mbarrier phase parity of both tiles for the current pair of sweeps
+    for (int m = 1; !failed; ++m) {
+      for (int t = 0; t < lag; t += 2) {
+        exchange(0u, par);
+        float d0 = sweep(0u);
+        ++s;
+        if (s <= p.max_sweeps) post(s, d0);
+        exchange(1u, par);
+        float d1 = sweep(1u);
+        ++s;
+        if (s <= p.max_sweeps) post(s, d1);
+        par ^= 1u;
       }
-      const int j = s - p.lag;
-      if (j >= 1) {
-        int dj;
+      if (failed) break;
+      const int J = min(s - lag, p.max_sweeps);
+      if (J >= 1) {
         unsigned spins = 0;
-        while (((dj = s_dec[j % VI2_RING]) >> 1) != j) {
+        while (s_done < J) {
           if (s_fail || ++spins > VI2_SPIN_LIMIT) { failed = true; s_fail = 1; break; }
         }
         if (failed) break;
-        if (dj & 1) { K = j; hit_max = 0; break; }
-        if (j == p.max_sweeps) { K = j; hit_max = 1; break; }
+        const int sk = s_stopK;
+        if (sk <= J) { K = sk; hit_max = 0; break; }
+        if (J == p.max_sweeps) { K = J; hit_max = 1; break; }
       }
+      float* dst = ckpt + (m & 1) * ck_stride;      // snapshot v_s, s = m * lag (own cells only)
+#pragma unroll
+      for (int i = 0; i < RT; ++i)
+        if (on[i]) *reinterpret_cast<float4*>(dst + (lr0 + i) * W + x0) = v[i];
     }
+    int ph = s;                                      // even: the next exchange uses tile 0
     if (!failed) {
-      // restore the snapshot at c0 = floor(K / CKPT) * CKPT and replay up to sweep K.  The stop is
-      // observed at sweep K + LAGCHK <= c0 + 2 * CKPT - 1, so slot (c0 / CKPT) & 1 still holds v_c0
-      // (slot 0 starts as zeros = v_0).
-      const int c0 = (K / p.lag) * p.lag;
-      const float* src = ckpt + ((c0 / p.lag) & 1) * ck_stride;
+      // restore the snapshot at c0 = floor(K / lag) * lag and replay up to sweep K (same arithmetic, same order =>
+      // same bits); slot (c0 / lag) & 1 still holds v_c0 (slot 0 starts as zeros = v_0)
+      const int c0 = (K / lag) * lag;
+      const float* src = ckpt + ((c0 / lag) & 1) * ck_stride;
 #pragma unroll
       for (int i = 0; i < RT; ++i)
         if (on[i]) v[i] = *reinterpret_cast<const float4*>(src + (lr0 + i) * W + x0);
-      for (int s = c0; s < K && !failed; ++s) {
-        exchange(ph);
-        (void)sweep(ph);
+      for (int r = c0; r < K && !failed; ++r) {
+        exchange((uint32_t)(ph & 1), (uint32_t)((ph >> 1) & 1));
+        (void)sweep((uint32_t)(ph & 1));
         ++ph;
       }
     }
     if (!failed) {
       // final pass (vin.py:76-80): q = conv(r + gamma*v_K), pi = softmax_a(q)
-      exchange(ph);
+      exchange((uint32_t)(ph & 1), (uint32_t)((ph >> 1) & 1));
       const float* X = sm + (ph & 1) * tile;
       const size_t HW = (size_t)H * W;
 #pragma unroll
@@ -873,9 +980,9 @@ __global__ void __launch_bounds__(RT <= 2 ? 896 : (RT == 3 ? 640 : 544), 1) vi_s
 // threads an RT <= 2 strip may use: 864 (27 warps, <= 72 registers) when CRESTE_VI_WIDE is set, else 608
 static int vi_rt2_limit() { return getenv("CRESTE_VI_WIDE") ? 864 : 608; }
 
-template <int RT>
+template <int RT, int PW>
 static int vi_try_strip(ViStripParams& p, int c, int threads, size_t smem, cudaStream_t st, int* max_clusters_out) {
-  auto kern = vi_strip_kernel<RT>;
+  auto kern = vi_strip_kernel<RT, PW>;
   if (cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) != cudaSuccess) {
     cudaGetLastError();
     return 0;
@@ -989,10 +1096,10 @@ extern "C" int creste_vi_solve(const float* r, float* v_out, float* q_out, float
       if ((c - 1) * R >= H) continue;                 // every strip needs at least one row
       int RT = 0;
       for (int t = 1; t <= 4; ++t)
-        if ((long long)cgn * ceil_div(R, t) <= (t <= 2 ? vi_rt2_limit() : (t == 3 ? 608 : 512))) { RT = t; break; }
+        if ((long long)cgn * ceil_div(R, t) <= (t <= 2 ? vi_rt2_limit() : (t == 3 ? 576 : 512))) { RT = t; break; }
       if (const char* e = getenv("CRESTE_VI_RT")) {          // experiment knob: force the rows-per-thread blocking
         const int t = atoi(e);
-        if (t >= 1 && t <= 4 && (long long)cgn * ceil_div(R, t) <= (t <= 2 ? 864 : (t == 3 ? 608 : 512))) RT = t;
+        if (t >= 1 && t <= 4 && (long long)cgn * ceil_div(R, t) <= (t <= 2 ? 864 : (t == 3 ? 576 : 512))) RT = t;
       }
       if (!RT) continue;
       int threads = cgn * ceil_div(R, RT);
@@ -1000,14 +1107,20 @@ extern "C" int creste_vi_solve(const float* r, float* v_out, float* q_out, float
       const size_t ssmem = ((size_t)2 * (R + 2) * (W + 8) + (size_t)2 * R * W) * sizeof(float);
       if (ssmem > 200 * 1024) continue;
       sp.R = R;
-      sp.lag = (long long)R * W >= 2048 ? 8 : 24;
-      sp.warp_arrive = getenv("CRESTE_VI_THREAD_ARRIVE") ? 0 : 1;
-      if (const char* e = getenv("CRESTE_VI_LAG")) { const int l = atoi(e); if (l >= 2 && l < VI2_RING) sp.lag = l; }
+      sp.lag = (long long)R * W >= 2048 ? 8 : 16;   // even, 2 * lag <= RING
+      if (const char* e = getenv("CRESTE_VI_LAG")) { const int l = atoi(e); if (l >= 2 && 2 * l <= VI2_RING && (l & 1) == 0) sp.lag = l; }
       int mc = 0;
-      int rc = RT == 1 ? vi_try_strip<1>(sp, c, threads, ssmem, st, &mc)
-             : RT == 2 ? vi_try_strip<2>(sp, c, threads, ssmem, st, &mc)
-             : RT == 3 ? vi_try_strip<3>(sp, c, threads, ssmem, st, &mc)
-                       : vi_try_strip<4>(sp, c, threads, ssmem, st, &mc);
+      int rc;
+#define VI_STRIP_RT(PWV)                                                        \
+      rc = RT == 1 ? vi_try_strip<1, PWV>(sp, c, threads, ssmem, st, &mc)       \
+         : RT == 2 ? vi_try_strip<2, PWV>(sp, c, threads, ssmem, st, &mc)       \
+         : RT == 3 ? vi_try_strip<3, PWV>(sp, c, threads, ssmem, st, &mc)       \
+                   : vi_try_strip<4, PWV>(sp, c, threads, ssmem, st, &mc)
+      if (W == 256) { VI_STRIP_RT(264); }
+      else if (W == 128) { VI_STRIP_RT(136); }
+      else if (W == 64) { VI_STRIP_RT(72); }
+      else { VI_STRIP_RT(0); }
+#undef VI_STRIP_RT
       last_mc = mc;
       if (rc == 1) return 0;
     }

@@ -6,6 +6,9 @@ namespace creste {
 int conv_simt_launch(const creste_conv_desc* d, const float* x, const float* w, int ldw,
                      const float* scale, const float* shift, const float* gate,
                      const float* residual, float* out, unsigned* amax_out, cudaStream_t st);
+int conv1x1_stream_launch(const creste_conv_desc* d, const float* x, const float* w, int ldw, const float* scale,
+                          const float* shift, const float* gate, const float* residual, float* out,
+                          unsigned* amax_out, cudaStream_t st);
 int conv_tc_launch(const creste_conv_desc* d, const float* x, const float* w_packed,
                    const float* scale, const float* shift, const float* gate, const float* residual,
                    float* out, const float* amax_in, unsigned* amax_out, void* ws, size_t ws_bytes,
@@ -319,6 +322,9 @@ extern "C" int creste_conv2d_ex(const creste_conv_desc* d, const float* x, const
   if (amax_out) CRESTE_CUDA(cudaMemsetAsync(amax_out, 0, sizeof(float), st));
   if (d->precision == 0) {
     const int ldw = (d->K + 3) / 4 * 4;
+    // HBM-bound 1x1 convs with short reductions: the streaming kernel (same arithmetic, bit-identical results)
+    const int rc = conv1x1_stream_launch(d, x, w_packed, ldw, scale, shift, gate, residual, out, (unsigned*)amax_out, st);
+    if (rc != 0) return rc == 1 ? 0 : rc;
     return conv_simt_launch(d, x, w_packed, ldw, scale, shift, gate, residual, out, (unsigned*)amax_out, st);
   }
   if (!conv_tc_supported(d)) {

@@ -2,6 +2,7 @@
 // bilinear upsample + channel concat, 2x2 max-pool + concat + crop, expert-visitation raster.
 // All are pure HBM streaming kernels: float4-vectorised, channel-contiguous, grid-stride.
 #include <cuda_fp16.h>
+#include <stdlib.h>
 
 #include "common.cuh"
 
@@ -26,6 +27,46 @@ __global__ void __launch_bounds__(256) transpose_kernel(const float* __restrict_
   }
 }
 
+// NCHW -> NHWC for C == 4 (the RGB-D input): one pixel per thread, four coalesced plane reads, one float4 store
+__global__ void __launch_bounds__(256) nchw4_to_nhwc_kernel(const float* __restrict__ in, long long HW, long long total,
+                                                            float4* __restrict__ out) {
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
+    const long long n = i / HW, p = i - n * HW;
+    const float* b = in + n * 4 * HW + p;
+    out[i] = make_float4(__ldg(b), __ldg(b + HW), __ldg(b + 2 * HW), __ldg(b + 3 * HW));
+  }
+}
+
+// 128-bit form of transpose_kernel for rows % 4 == 0 && cols % 4 == 0: a 64 x 64 tile, float4 loads along the
+// columns and float4 stores along the rows (the scalar form moved 4 bytes per lane per instruction and ran the
+// 126 MB layout changes at the module boundary at ~0.25 of the HBM rate)
+__global__ void __launch_bounds__(256) transpose4_kernel(const float* __restrict__ in, int rows, int cols,
+                                                         float* __restrict__ out) {
+  __shared__ float tile[64][65];
+  const size_t base = (size_t)blockIdx.z * rows * cols;
+  const int c0 = blockIdx.x * 64, r0 = blockIdx.y * 64;
+  const int t = threadIdx.x;
+#pragma unroll
+  for (int k = 0; k < 4; ++k) {
+    const int f = t + k * 256;               // 64 rows x 16 float4
+    const int r = f >> 4, c4 = f & 15;
+    float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+    if (r0 + r < rows && c0 + c4 * 4 < cols)
+      v = __ldg(reinterpret_cast<const float4*>(in + base + (size_t)(r0 + r) * cols + c0 + c4 * 4));
+    tile[r][c4 * 4 + 0] = v.x; tile[r][c4 * 4 + 1] = v.y; tile[r][c4 * 4 + 2] = v.z; tile[r][c4 * 4 + 3] = v.w;
+  }
+  __syncthreads();
+#pragma unroll
+  for (int k = 0; k < 4; ++k) {
+    const int f = t + k * 256;               // 64 cols x 16 float4 (along the rows)
+    const int c = f >> 4, r4 = f & 15;
+    if (c0 + c < cols && r0 + r4 * 4 < rows) {
+      const float4 v = make_float4(tile[r4 * 4 + 0][c], tile[r4 * 4 + 1][c], tile[r4 * 4 + 2][c], tile[r4 * 4 + 3][c]);
+      *reinterpret_cast<float4*>(out + base + (size_t)(c0 + c) * rows + r0 + r4 * 4) = v;
+    }
+  }
+}
+
 // ---- projection head: 1x1 conv with a handful of output channels (the DeconvHead `proj`, K = 32 / 6 / 2 over
 // C = 128 features at 256 x 256) fused with the layout change of its INPUT.  The generic conv kernels tile the
 // output channels by >= 32 and waste 5-16x of their FFMA work here, and the reference's output dict wants both the
@@ -40,31 +81,71 @@ __global__ void __launch_bounds__(256) proj_head_kernel(const float* __restrict_
                                                         long long PQ, float* __restrict__ pred_nhwc,
                                                         float* __restrict__ pred_nchw, float* __restrict__ x_nchw,
                                                         int K) {
-  extern __shared__ float s_w[];                       // [KO][C]
-  __shared__ float tile[8][32][33];
-  for (int i = threadIdx.x; i < KO * C; i += blockDim.x) s_w[i] = (i / C < K) ? w[i] : 0.0f;
+  // weights transposed to [C][KO]: the KO products of one input channel read their weights as float4 broadcasts
+  // (one shared-memory load per 4 FFMA; the [KO][C] form issued one load per FFMA and made the kernel LSU-bound)
+  extern __shared__ __align__(16) float s_w[];          // [C][KO], then the per-warp tiles [8][2][32][33]
+  float (*tile)[2][32][33] = reinterpret_cast<float (*)[2][32][33]>(s_w + KO * C);
+  for (int i = threadIdx.x; i < KO * C; i += blockDim.x) {
+    const int k = i / C, c = i - k * C;
+    s_w[c * KO + k] = (k < K) ? w[i] : 0.0f;
+  }
   __syncthreads();
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-  for (long long p0 = ((long long)blockIdx.x * 8 + warp) * 32; p0 < M; p0 += (long long)gridDim.x * 256) {
+  // stage one 32-pixel x 32-channel chunk into tile buffer `buf` with cp.async (no registers, no stall): the next
+  // chunk is in flight while the current one is multiplied (the synchronous form waited a full DRAM latency per
+  // batch of 8 rows with 16 warps per SM: 6.3 of 10 issue slots idle on long-scoreboard stalls, ncu round 2)
+  auto stage = [&](long long p0, int c0, int buf) {
+#pragma unroll 8
+    for (int r = 0; r < 32; ++r) {
+      float* dst = &tile[warp][buf][r][lane];
+      if (p0 + r < M) {
+        const uint32_t d = (uint32_t)__cvta_generic_to_shared(dst);
+        asm volatile("cp.async.ca.shared.global [%0], [%1], 4;" ::"r"(d), "l"(x + (size_t)(p0 + r) * C + c0 + lane) : "memory");
+      } else {
+        *dst = 0.0f;
+      }
+    }
+    asm volatile("cp.async.commit_group;" ::: "memory");
+  };
+  const long long pstep = (long long)gridDim.x * 256;
+  const int nch = C / 32;
+  long long p0 = ((long long)blockIdx.x * 8 + warp) * 32;
+  int buf = 0;
+  if (p0 < M) stage(p0, 0, 0);
+  for (; p0 < M; p0 += pstep) {
     const long long pix = p0 + lane;                   // this lane's pixel in the compute / store phases
     const bool ok = pix < M;
     const long long img = ok ? pix / PQ : 0, pp = ok ? pix - img * PQ : 0;
     float acc[KO];
 #pragma unroll
     for (int k = 0; k < KO; ++k) acc[k] = 0.0f;
-    for (int c0 = 0; c0 < C; c0 += 32) {
-#pragma unroll 8
-      for (int r = 0; r < 32; ++r)                     // row r of the tile = pixel p0 + r: one 128-byte line
-        tile[warp][r][lane] = (p0 + r < M) ? __ldg(x + (size_t)(p0 + r) * C + c0 + lane) : 0.0f;
+    for (int ch = 0; ch < nch; ++ch) {
+      const int c0 = ch * 32;
+      // prefetch the next chunk (of this pixel group, or the first chunk of the next one)
+      if (ch + 1 < nch) stage(p0, c0 + 32, buf ^ 1);
+      else if (p0 + pstep < M) stage(p0 + pstep, 0, buf ^ 1);
+      else asm volatile("cp.async.commit_group;" ::: "memory");
+      asm volatile("cp.async.wait_group 1;" ::: "memory");
       __syncwarp();
 #pragma unroll 8
       for (int c = 0; c < 32; ++c) {
-        const float xv = tile[warp][lane][c];
+        const float xv = tile[warp][buf][lane][c];
+        const float* wr = s_w + (c0 + c) * KO;
+        if constexpr (KO % 4 == 0) {
 #pragma unroll
-        for (int k = 0; k < KO; ++k) acc[k] = fmaf(xv, s_w[k * C + c0 + c], acc[k]);
+          for (int k = 0; k < KO; k += 4) {
+            const float4 w4 = *reinterpret_cast<const float4*>(wr + k);
+            acc[k] = fmaf(xv, w4.x, acc[k]); acc[k + 1] = fmaf(xv, w4.y, acc[k + 1]);
+            acc[k + 2] = fmaf(xv, w4.z, acc[k + 2]); acc[k + 3] = fmaf(xv, w4.w, acc[k + 3]);
+          }
+        } else {
+#pragma unroll
+          for (int k = 0; k < KO; ++k) acc[k] = fmaf(xv, wr[k], acc[k]);
+        }
         if (x_nchw && ok) x_nchw[((size_t)img * C + c0 + c) * PQ + pp] = xv;
       }
       __syncwarp();
+      buf ^= 1;
     }
     if (ok) {
 #pragma unroll
@@ -77,6 +158,7 @@ __global__ void __launch_bounds__(256) proj_head_kernel(const float* __restrict_
       }
     }
   }
+  asm volatile("cp.async.wait_group 0;" ::: "memory");
 }
 
 // ---- cat([skip, bilinear(x)], C) in NHWC; Cs % 4 == 0, Cx % 4 == 0.
@@ -163,6 +245,147 @@ __global__ void __launch_bounds__(256) upsample_concat_kernel(const float* __res
   }
 }
 
+// ---- the same for an integer factor F in {2, 4} (Ho = F * Hi, Wo = F * Wi, ratio 1 / F): one warp per INPUT pixel.
+// With src = (dst + 0.5) / F - 0.5 the F x F output block of input pixel (by, bx) takes its taps from the 3 x 3
+// neighbourhood only (first half of the block: (b - 1, b), second half: (b, b + 1)), so a lane loads 9 float4 once
+// and produces F * F outputs instead of 4 loads per output, and the horizontal interpolation of an input row is
+// shared by the output rows that use it.  Bit-identical to upsample_concat_kernel: the tap weights come from the
+// same float formula per output row / column, the two-level interpolation is evaluated as the same
+// fma(l0, a, l1 * b) pairs, and at the borders the clamped neighbour carries weight exactly 0 or duplicates the tap
+// (1 * a + 0 * b = a for finite b).
+template <int F, bool SPLIT>
+__global__ void __launch_bounds__(256, 2) upsample_block_kernel(const float* __restrict__ skip, int Cs,
+                                                             const float* __restrict__ x, int N, int Hi, int Wi, int Cx,
+                                                             int x_first, float* __restrict__ out,
+                                                             const unsigned* __restrict__ amax_a,
+                                                             const unsigned* __restrict__ amax_b,
+                                                             uint2* __restrict__ hi, uint2* __restrict__ lo,
+                                                             float* __restrict__ scal) {
+  float sc = 1.0f;
+  if (SPLIT) {
+    unsigned b = __ldg(amax_a);
+    if (amax_b) b = max(b, __ldg(amax_b));
+    int e = (int)((b >> 23) & 0xffu) - 127;
+    if (b == 0u || !isfinite(__uint_as_float(b))) e = 14;
+    const int k = max(-100, min(100, 14 - e));
+    sc = __uint_as_float((unsigned)(127 + k) << 23);
+    if (blockIdx.x == 0 && threadIdx.x == 0) { scal[0] = sc; scal[1] = __uint_as_float((unsigned)(127 - k) << 23); }
+  }
+  constexpr float R = 1.0f / F;
+  const int Ho = Hi * F, Wo = Wi * F;
+  const int Ct = Cs + Cx;
+  const int c4t = Ct / 4, cs4 = Cs / 4, cx4 = Cx / 4;
+  const int lane = threadIdx.x & 31;
+  const long long nin = (long long)N * Hi * Wi;
+  const long long warp0 = ((long long)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  const long long nwarps = ((long long)gridDim.x * blockDim.x) >> 5;
+  auto emit = [&](long long pix, int c4, const float4 v) {
+    if (!SPLIT) {
+      reinterpret_cast<float4*>(out + pix * Ct)[c4] = v;
+    } else {
+      const float xs[4] = {v.x * sc, v.y * sc, v.z * sc, v.w * sc};
+      unsigned short h[4], l[4];
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        const __half hh = __float2half_rn(xs[j]);
+        h[j] = __half_as_ushort(hh);
+        l[j] = __half_as_ushort(__float2half_rn((xs[j] - __half2float(hh)) * 2048.0f));
+      }
+      hi[pix * c4t + c4] = make_uint2((unsigned)h[0] | ((unsigned)h[1] << 16), (unsigned)h[2] | ((unsigned)h[3] << 16));
+      if (lo) lo[pix * c4t + c4] = make_uint2((unsigned)l[0] | ((unsigned)l[1] << 16), (unsigned)l[2] | ((unsigned)l[3] << 16));
+    }
+  };
+  for (long long item = warp0; item < nin; item += nwarps) {
+    const int bx = (int)(item % Wi);
+    const long long t = item / Wi;
+    const int by = (int)(t % Hi);
+    const int n = (int)(t / Hi);
+    const int ry[3] = {max(by - 1, 0), by, min(by + 1, Hi - 1)};
+    const int rx[3] = {max(bx - 1, 0), bx, min(bx + 1, Wi - 1)};
+    const float* b = x + (size_t)n * Hi * Wi * Cx;
+    const long long opix0 = ((long long)n * Ho + (long long)by * F) * Wo + (long long)bx * F;
+    for (int c4 = lane; c4 < c4t; c4 += 32) {
+      const bool is_skip = x_first ? (c4 >= cx4) : (c4 < cs4);
+      if (is_skip) {
+        const int sc4 = x_first ? c4 - cx4 : c4;
+#pragma unroll 1
+        for (int i = 0; i < F; ++i)
+#pragma unroll
+          for (int k = 0; k < F; ++k) {
+            const long long pix = opix0 + (long long)i * Wo + k;
+            emit(pix, c4, __ldg(reinterpret_cast<const float4*>(skip + pix * Cs) + sc4));
+          }
+        continue;
+      }
+      const int cc = x_first ? c4 : c4 - cs4;
+      float4 V[3][3];
+#pragma unroll
+      for (int r = 0; r < 3; ++r)
+#pragma unroll
+        for (int q = 0; q < 3; ++q)
+          V[r][q] = __ldg(reinterpret_cast<const float4*>(b + ((size_t)ry[r] * Wi + rx[q]) * Cx) + cc);
+      // the tap weights are recomputed per output column / row (six FP instructions) instead of being kept in
+      // 4 * F registers, and only the half index is unrolled: the fully unrolled form needed 255 registers
+      constexpr int HALF = F / 2;
+#pragma unroll
+      for (int qh = 0; qh < 2; ++qh) {
+#pragma unroll 1
+        for (int kk = 0; kk < HALF; ++kk) {
+          const int k = qh * HALF + kk;
+          const float sx = fmaxf(__fsub_rn(__fmul_rn(R, __fadd_rn((float)(bx * F + k), 0.5f)), 0.5f), 0.0f);
+          const float l1w = __fsub_rn(sx, (float)(int)sx), l0w = __fsub_rn(1.0f, l1w);
+          float4 Hr[3];
+#pragma unroll
+          for (int r = 0; r < 3; ++r) {
+            const float4 a = V[r][qh], c = V[r][qh + 1];
+            Hr[r].x = __fmaf_rn(l0w, a.x, __fmul_rn(l1w, c.x));
+            Hr[r].y = __fmaf_rn(l0w, a.y, __fmul_rn(l1w, c.y));
+            Hr[r].z = __fmaf_rn(l0w, a.z, __fmul_rn(l1w, c.z));
+            Hr[r].w = __fmaf_rn(l0w, a.w, __fmul_rn(l1w, c.w));
+          }
+#pragma unroll
+          for (int rh = 0; rh < 2; ++rh) {
+#pragma unroll 1
+            for (int ii = 0; ii < HALF; ++ii) {
+              const int i = rh * HALF + ii;
+              const float sy = fmaxf(__fsub_rn(__fmul_rn(R, __fadd_rn((float)(by * F + i), 0.5f)), 0.5f), 0.0f);
+              const float l1h = __fsub_rn(sy, (float)(int)sy), l0h = __fsub_rn(1.0f, l1h);
+              float4 v;
+              v.x = __fmaf_rn(l0h, Hr[rh].x, __fmul_rn(l1h, Hr[rh + 1].x));
+              v.y = __fmaf_rn(l0h, Hr[rh].y, __fmul_rn(l1h, Hr[rh + 1].y));
+              v.z = __fmaf_rn(l0h, Hr[rh].z, __fmul_rn(l1h, Hr[rh + 1].z));
+              v.w = __fmaf_rn(l0h, Hr[rh].w, __fmul_rn(l1h, Hr[rh + 1].w));
+              emit(opix0 + (long long)i * Wo + k, c4, v);
+            }
+          }
+        }
+      }
+    }
+  }
+}
+
+// integer-factor dispatch shared by the two entry points; returns false if the shape is not an exact x2 / x4
+template <bool SPLIT>
+static bool upsample_block_launch(const float* skip, int Cs, const float* x, int N, int Hi, int Wi, int Cx, int Ho, int Wo,
+                                  float rh, float rw, int x_first, float* out, const unsigned* amax_a,
+                                  const unsigned* amax_b, uint2* hi, uint2* lo, float* scal, cudaStream_t st) {
+  if (getenv("CRESTE_NO_UPSAMPLE_BLOCK")) return false;
+  int F = 0;
+  if (Ho == 2 * Hi && Wo == 2 * Wi && rh == 0.5f && rw == 0.5f) F = 2;
+  if (Ho == 4 * Hi && Wo == 4 * Wi && rh == 0.25f && rw == 0.25f) F = 4;
+  if (!F) return false;
+  const long long total = (long long)N * Hi * Wi * 32;      // one warp per input pixel
+  long long blocks = (total + 255) / 256;
+  if (blocks > 148LL * 64) blocks = 148LL * 64;
+  if (F == 2)
+    upsample_block_kernel<2, SPLIT><<<(int)blocks, 256, 0, st>>>(skip, Cs, x, N, Hi, Wi, Cx, x_first, out, amax_a, amax_b,
+                                                                 hi, lo, scal);
+  else
+    upsample_block_kernel<4, SPLIT><<<(int)blocks, 256, 0, st>>>(skip, Cs, x, N, Hi, Wi, Cx, x_first, out, amax_a, amax_b,
+                                                                 hi, lo, scal);
+  return true;
+}
+
 // ---- 2x2/2 max-pool of channel-concatenated NHWC sources, cropped to rows_out rows
 struct PoolSrcs { const float* p[3]; int c[3]; int n; };
 __global__ void __launch_bounds__(256) maxpool2_concat_kernel(PoolSrcs s, int N, int H, int W,
@@ -245,6 +468,18 @@ static int grid_for(long long total, int threads = 256) {
 extern "C" int creste_nchw_to_nhwc(const float* in, int N, int C, int H, int W, float* out,
                                    void* stream) {
   CRESTE_CHECK_ARG(in && out && N > 0 && C > 0 && H > 0 && W > 0, "creste_nchw_to_nhwc: bad args");
+  auto al16 = [](const void* q) { return ((uintptr_t)q & 15u) == 0; };
+  if (C == 4 && al16(out)) {
+    const long long total = (long long)N * H * W;
+    nchw4_to_nhwc_kernel<<<grid_for(total), 256, 0, (cudaStream_t)stream>>>(in, (long long)H * W, total,
+                                                                          reinterpret_cast<float4*>(out));
+    return launch_check("nchw4_to_nhwc_kernel");
+  }
+  if (C % 4 == 0 && (H * W) % 4 == 0 && al16(in) && al16(out)) {
+    dim3 grid4(ceil_div(H * W, 64), ceil_div(C, 64), N);
+    transpose4_kernel<<<grid4, 256, 0, (cudaStream_t)stream>>>(in, C, H * W, out);
+    return launch_check("transpose4_kernel");
+  }
   dim3 grid(ceil_div(H * W, 32), ceil_div(C, 32), N);
   transpose_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(in, C, H * W, out);
   return launch_check("transpose_kernel");
@@ -253,6 +488,11 @@ extern "C" int creste_nchw_to_nhwc(const float* in, int N, int C, int H, int W, 
 extern "C" int creste_nhwc_to_nchw(const float* in, int N, int H, int W, int C, float* out,
                                    void* stream) {
   CRESTE_CHECK_ARG(in && out && N > 0 && C > 0 && H > 0 && W > 0, "creste_nhwc_to_nchw: bad args");
+  if (C % 4 == 0 && (H * W) % 4 == 0 && ((uintptr_t)in & 15u) == 0 && ((uintptr_t)out & 15u) == 0) {
+    dim3 grid4(ceil_div(C, 64), ceil_div(H * W, 64), N);
+    transpose4_kernel<<<grid4, 256, 0, (cudaStream_t)stream>>>(in, H * W, C, out);
+    return launch_check("transpose4_kernel");
+  }
   dim3 grid(ceil_div(C, 32), ceil_div(H * W, 32), N);
   transpose_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(in, H * W, C, out);
   return launch_check("transpose_kernel");
@@ -267,15 +507,15 @@ extern "C" int creste_proj_head(const float* x, const float* w, const float* bia
   if (blocks > 148 * 8) blocks = 148 * 8;
   cudaStream_t st = (cudaStream_t)stream;
 #define CRESTE_PROJ(KO)                                                                                         \
-  proj_head_kernel<KO><<<(int)blocks, 256, (size_t)KO * C * sizeof(float), st>>>(x, w, bias, M, C, PQ, pred_nhwc, \
-                                                                                pred_nchw, x_nchw, K)
+  do {                                                                                                          \
+    const size_t smem = (size_t)KO * C * sizeof(float) + 8 * 2 * 32 * 33 * sizeof(float);                       \
+    CRESTE_CUDA(cudaFuncSetAttribute(proj_head_kernel<KO>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)); \
+    proj_head_kernel<KO><<<(int)blocks, 256, smem, st>>>(x, w, bias, M, C, PQ, pred_nhwc, pred_nchw, x_nchw, K); \
+  } while (0)
   if (K <= 2) CRESTE_PROJ(2);
   else if (K <= 8) CRESTE_PROJ(8);
   else if (K <= 16) CRESTE_PROJ(16);
-  else { 
-    CRESTE_CUDA(cudaFuncSetAttribute(proj_head_kernel<32>, cudaFuncAttributeMaxDynamicSharedMemorySize, 32 * 512 * 4));
-    CRESTE_PROJ(32);
-  }
+  else CRESTE_PROJ(32);
 #undef CRESTE_PROJ
   return launch_check("proj_head_kernel");
 }
@@ -286,6 +526,9 @@ extern "C" int creste_upsample_concat(const float* skip, int Cs, const float* x,
   CRESTE_CHECK_ARG(x && out, "creste_upsample_concat: null pointer");
   CRESTE_CHECK_ARG((Cs == 0 || skip) && Cs % 4 == 0 && Cx % 4 == 0 && Cx > 0,
                    "creste_upsample_concat: channel counts must be multiples of 4");
+  if (upsample_block_launch<false>(skip, Cs, x, N, Hi, Wi, Cx, Ho, Wo, rh, rw, x_first, out, nullptr, nullptr, nullptr,
+                                   nullptr, nullptr, (cudaStream_t)stream))
+    return launch_check("upsample_block_kernel");
   const long long total = (long long)N * Ho * Wo * 32;      // one warp per output pixel
   upsample_concat_kernel<false><<<grid_for(total), 256, 0, (cudaStream_t)stream>>>(
       skip, Cs, x, N, Hi, Wi, Cx, Ho, Wo, rh, rw, x_first, out, nullptr, nullptr, nullptr, nullptr, nullptr);
@@ -298,6 +541,9 @@ extern "C" int creste_upsample_concat_split(const float* skip, int Cs, const flo
   CRESTE_CHECK_ARG(x && hi && scal && amax_a, "creste_upsample_concat_split: null pointer");
   CRESTE_CHECK_ARG((Cs == 0 || skip) && Cs % 4 == 0 && Cx % 4 == 0 && Cx > 0 && (Cs + Cx) % 8 == 0,
                    "creste_upsample_concat_split: channel counts must be multiples of 4 (8 in total)");
+  if (upsample_block_launch<true>(skip, Cs, x, N, Hi, Wi, Cx, Ho, Wo, rh, rw, x_first, nullptr, (const unsigned*)amax_a,
+                                  (const unsigned*)amax_b, (uint2*)hi, (uint2*)lo, scal, (cudaStream_t)stream))
+    return launch_check("upsample_block_kernel<split>");
   const long long total = (long long)N * Ho * Wo * 32;
   upsample_concat_kernel<true><<<grid_for(total), 256, 0, (cudaStream_t)stream>>>(
       skip, Cs, x, N, Hi, Wi, Cx, Ho, Wo, rh, rw, x_first, nullptr, (const unsigned*)amax_a, (const unsigned*)amax_b,

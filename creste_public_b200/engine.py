@@ -4,6 +4,8 @@ packing caches and the global precision policy of the conv family.
 Nothing here computes on the CPU at run time: folding and packing are a handful of tiny
 tensor ops executed on the GPU once per parameter version, cached, and reused every frame.
 """
+import os
+
 import torch
 
 from . import ops
@@ -48,6 +50,10 @@ def drop_connect_scale(B, rate, device):
     return (torch.floor(keep + u.float()) / keep).contiguous()
 
 
+# reductions up to this length run on the exact-fp32 CUDA-core kernels (experiment knob: CRESTE_SIMT_MAX_REDUCTION)
+_SIMT_MAX_REDUCTION = int(os.environ.get("CRESTE_SIMT_MAX_REDUCTION", "192"))
+
+
 def pick_mode(x_shape, K, R, S, stride, pad, mode):
     """Requested precision, or the next stricter one the shape is served by:
     3xfp16 -> 3xtf32 -> fp32 (never a looser one)."""
@@ -56,7 +62,7 @@ def pick_mode(x_shape, K, R, S, stride, pad, mode):
     # short reductions (1x1 convs with C <= 192: the MBConv expand / project and head convs) are
     # HBM-bound; measured per shape, the exact-fp32 FFMA kernel beats the tensor-core kernel there
     # (no operand pre-pass, no per-CTA TMEM / barrier set-up): 0.79 vs 1.32 ms at C16->K96 @256x480
-    if R * S * x_shape[3] <= 192:
+    if R * S * x_shape[3] <= _SIMT_MAX_REDUCTION:
         return "fp32"
     for m in chain:
         if ops.tc_supported(x_shape, K, R, S, stride, pad, m):

@@ -635,13 +635,19 @@ def run_ours(args):
         up3 = model.backbone.depthcomp.depthcomp.vision_backbone.model.up3
         xin = torch.randn(B, 128, 240, 496, device=dev)
         with torch.no_grad():
+            # exactly as the forward runs it: the operand arrives pre-split from the producing conv's epilogue
+            # (up3.conv.0 -> BN -> ReLU) and the output is written as the operand of the final 1x1 conv
+            pre = args.precision in ("3xfp16", "fp16")
+            if pre:
+                xin = up3._f0(xin, act="relu", split_out="only")
+            kw = {"split_out": "only"} if pre else {}
             for _ in range(2):
-                up3._f1(xin, act="relu")
+                up3._f1(xin, act="relu", **kw)
             ev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True))
                   for _ in range(5)]
             for a, b_ in ev:
                 a.record()
-                up3._f1(xin, act="relu")
+                up3._f1(xin, act="relu", **kw)
                 b_.record()
             torch.cuda.synchronize()
         kms = statistics.median(a.elapsed_time(b_) for a, b_ in ev)

@@ -91,7 +91,14 @@ class MBConv(nn.Module):
         w, scale, shift = self._cache.get("dw", [dw.weight, bn.weight, bn.bias, bn.running_mean,
                                                  bn.running_var], build_dw)
         lo, hi = same_pad(self.k, self.s)
-        x, csum = ops.dwconv_bn_swish(x, w, scale, shift, self.k, self.s, (lo, hi, lo, hi))
+        # max|dw out| travels with the tensor when the project conv runs on the fp16 tensor-core path: it bounds
+        # max|out * gate| (sigmoid gate), so the operand pre-pass of that conv makes no amax pass
+        track = engine.get_precision() in ("3xfp16", "fp16") and not torch.jit.is_tracing()
+        amax = torch.empty(1, device=x.device) if track else None
+        x, csum = ops.dwconv_bn_swish(x, w, scale, shift, self.k, self.s, (lo, hi, lo, hi),
+                                      **({"amax_out": amax} if track else {}))
+        if track:
+            x._amax = amax
 
         def build_se():
             r, e = self._se_reduce, self._se_expand
@@ -196,14 +203,19 @@ class Up(nn.Module):
         x = ag.bn_act(ag.conv2d(x, self.conv[0]), self.conv[1], "relu")
         return ag.bn_act(ag.conv2d(x, self.conv[3]), self.conv[4], "relu")
 
-    def forward_nhwc(self, x1, x2):
+    def forward_nhwc(self, x1, x2, split_out=None):
+        """split_out ("only" | "both" | None): how the consumer wants the block's output (engine.FusedConv.__call__)."""
         if self.training:
             return self.forward_train(x1, x2)
         sf = self.up.scale_factor
         sh, sw = (sf, sf) if not isinstance(sf, (tuple, list)) else sf
         Ho, Wo = int(math.floor(x1.shape[1] * sh)), int(math.floor(x1.shape[2] * sw))
         x = engine.upsample_concat_for(self._f0, x2, x1, (Ho, Wo), sf)
-        return self._f1(self._f0(x, act="relu"), act="relu")
+        # conv -> BN -> ReLU -> conv: the intermediate has one consumer, so the first conv's epilogue writes it
+        # directly as the second conv's 3xFP16 operand (no fp32 tensor, no split pre-pass)
+        mid = (x.shape[0], Ho, Wo, self.conv[0].weight.shape[0])
+        return self._f1(self._f0(x, act="relu", split_out="only" if self._f1.split_ok(mid) else None), act="relu",
+                        split_out=split_out)
 
     def forward(self, x1, x2):
         y = self.forward_nhwc(ops.nchw_to_nhwc(x1.float()), ops.nchw_to_nhwc(x2.float()))
@@ -259,8 +271,19 @@ class EffNet(nn.Module):
         n = 5
         y = ep[f"reduction_{n}"]
         for i in range(1, self.n_ups + 1):
-            y = getattr(self, f"up{i}").forward_nhwc(y, ep[f"reduction_{n - i}"])
-        out = self._f_out(y, act="relu" if self.apply_final_batch_norm else "none")
+            skip = ep[f"reduction_{n - i}"]
+            so = None
+            if i == self.n_ups and not self.return_2nd_last_layer_output:
+                # the last block's output only feeds the final 1x1 conv
+                up = getattr(self, f"up{i}")
+                sf = up.up.scale_factor
+                sh, sw = (sf, sf) if not isinstance(sf, (tuple, list)) else sf
+                shp = (y.shape[0], int(math.floor(y.shape[1] * sh)), int(math.floor(y.shape[2] * sw)),
+                       up.conv[3].weight.shape[0])
+                so = "only" if self._f_out.split_ok(shp) else None
+            y = getattr(self, f"up{i}").forward_nhwc(y, skip, split_out=so)
+        # the features feed tensor-core convs (depth head, distillation head) AND fp32 readers: write both forms
+        out = self._f_out(y, act="relu" if self.apply_final_batch_norm else "none", split_out="both")
         return (out, y) if self.return_2nd_last_layer_output else out
 
     def forward(self, x):

@@ -47,7 +47,11 @@ class BasicBlock(nn.Module):
         if self.training:
             return self.forward_train(x)
         idt = self._fd(x) if self.downsample is not None else x
-        return self._f2(self._f1(x, act="relu"), act="relu", residual=idt)
+        # conv1's output has one consumer (conv2): its epilogue writes conv2's 3xFP16 operand directly
+        N, H, W, _ = x.shape
+        mid = (N, (H - 1) // self.stride + 1, (W - 1) // self.stride + 1, self.conv1.weight.shape[0])
+        return self._f2(self._f1(x, act="relu", split_out="only" if self._f2.split_ok(mid) else None), act="relu",
+                        residual=idt)
 
 
 def _make_layer(inplanes, planes, stride, norm_layer):

@@ -9,13 +9,14 @@ int conv_simt_launch(const creste_conv_desc* d, const float* x, const float* w, 
 int conv1x1_stream_launch(const creste_conv_desc* d, const float* x, const float* w, int ldw, const float* scale,
                           const float* shift, const float* gate, const float* residual, float* out,
                           unsigned* amax_out, cudaStream_t st);
+struct TcSplitOut { void* hi; void* lo; float* scal; float bound_mul, bound_add; };   // conv_tc.cu
 int conv_tc_launch(const creste_conv_desc* d, const float* x, const float* w_packed,
                    const float* scale, const float* shift, const float* gate, const float* residual,
                    float* out, const float* amax_in, unsigned* amax_out, void* ws, size_t ws_bytes,
-                   cudaStream_t st);
+                   cudaStream_t st, const TcSplitOut* so);
 int conv_tc_presplit_launch(const creste_conv_desc* d, const void* x_hi, const void* x_lo, const float* x_scal,
                             const float* w_packed, const float* scale, const float* shift, const float* residual,
-                            float* out, unsigned* amax_out, cudaStream_t st);
+                            float* out, unsigned* amax_out, cudaStream_t st, const TcSplitOut* so);
 size_t conv_tc_workspace_bytes(const creste_conv_desc* d);
 bool conv_tc_supported(const creste_conv_desc* d);
 
@@ -106,7 +107,8 @@ __global__ void __launch_bounds__(256) dwconv_xb_kernel(const float* __restrict_
                                                         const float* __restrict__ scale,
                                                         const float* __restrict__ shift, int N, int H, int W,
                                                         int C, int pad_t, int pad_l, int P, int Q,
-                                                        float* __restrict__ out, float* __restrict__ chan_part) {
+                                                        float* __restrict__ out, float* __restrict__ chan_part,
+                                                        unsigned* __restrict__ amax_out) {
   constexpr int NC = (XB - 1) * STRIDE + R;
   __shared__ float4 s_part[256];
   const int C4 = C / 4;
@@ -122,6 +124,7 @@ __global__ void __launch_bounds__(256) dwconv_xb_kernel(const float* __restrict_
   const int cg = cg0 + (threadIdx.x % cgs);
   const int pl = threadIdx.x / cgs;
   float4 sum = make_float4(0.f, 0.f, 0.f, 0.f);
+  float amx = 0.0f;
   if (pl < lanes) {
     const float4 sc = __ldg(reinterpret_cast<const float4*>(scale) + cg);
     const float4 sh = __ldg(reinterpret_cast<const float4*>(shift) + cg);
@@ -164,9 +167,16 @@ __global__ void __launch_bounds__(256) dwconv_xb_kernel(const float* __restrict_
           o.z = o.z / (1.0f + expf(-o.z)); o.w = o.w / (1.0f + expf(-o.w));
           reinterpret_cast<float4*>(out + (((size_t)n * P + oy) * Q + ox0 + b) * C)[cg] = o;
           sum.x += o.x; sum.y += o.y; sum.z += o.z; sum.w += o.w;
+          amx = fmaxf(fmaxf(amx, fmaxf(fabsf(o.x), fabsf(o.y))), fmaxf(fabsf(o.z), fabsf(o.w)));
         }
       }
     }
+  }
+  // max|out| travels with the tensor: the project conv derives its 3xFP16 operand scale from it (the SE gate is a
+  // sigmoid, so max|out * gate| <= max|out|) instead of making an amax pass over out * gate
+  if (amax_out) {
+    amx = warp_max(amx);
+    if ((threadIdx.x & 31) == 0 && amx > 0.0f) atomicMax(amax_out, __float_as_uint(amx));
   }
   s_part[threadIdx.x] = sum;
   __syncthreads();
@@ -308,11 +318,10 @@ extern "C" int creste_conv2d(const creste_conv_desc* d, const float* x, const fl
   return creste_conv2d_ex(d, x, w_packed, scale, shift, gate, residual, out, nullptr, nullptr, ws, ws_bytes, stream);
 }
 
-extern "C" int creste_conv2d_ex(const creste_conv_desc* d, const float* x, const float* w_packed,
-                                const float* scale, const float* shift, const float* gate,
-                                const float* residual, float* out, const float* amax_in, float* amax_out,
-                                void* ws, size_t ws_bytes, void* stream) {
-  CRESTE_CHECK_ARG(d && x && w_packed && out, "creste_conv2d: null pointer");
+static int conv2d_impl(const creste_conv_desc* d, const float* x, const float* w_packed, const float* scale,
+                       const float* shift, const float* gate, const float* residual, float* out, const float* amax_in,
+                       float* amax_out, const TcSplitOut* so, void* ws, size_t ws_bytes, void* stream) {
+  CRESTE_CHECK_ARG(d && x && w_packed && (out || (so && so->hi)), "creste_conv2d: null pointer");
   CRESTE_CHECK_ARG(d->N > 0 && d->H > 0 && d->W > 0 && d->C > 0 && d->K > 0 && d->R > 0 && d->S > 0 &&
                        d->stride > 0 && d->P > 0 && d->Q > 0,
                    "creste_conv2d: bad shape");
@@ -321,6 +330,7 @@ extern "C" int creste_conv2d_ex(const creste_conv_desc* d, const float* x, const
   cudaStream_t st = (cudaStream_t)stream;
   if (amax_out) CRESTE_CUDA(cudaMemsetAsync(amax_out, 0, sizeof(float), st));
   if (d->precision == 0) {
+    CRESTE_CHECK_ARG(!(so && so->hi), "creste_conv2d: the split output needs a tensor-core precision mode");
     const int ldw = (d->K + 3) / 4 * 4;
     // HBM-bound 1x1 convs with short reductions: the streaming kernel (same arithmetic, bit-identical results)
     const int rc = conv1x1_stream_launch(d, x, w_packed, ldw, scale, shift, gate, residual, out, (unsigned*)amax_out, st);
@@ -332,14 +342,30 @@ extern "C" int creste_conv2d_ex(const creste_conv_desc* d, const float* x, const
               "(C=%d K=%d R=%d stride=%d); use precision 0", d->precision, d->C, d->K, d->R, d->stride);
     return CRESTE_ERR_ARG;
   }
-  return conv_tc_launch(d, x, w_packed, scale, shift, gate, residual, out, amax_in, (unsigned*)amax_out, ws, ws_bytes, st);
+  return conv_tc_launch(d, x, w_packed, scale, shift, gate, residual, out, amax_in, (unsigned*)amax_out, ws, ws_bytes, st, so);
 }
 
-extern "C" int creste_conv2d_presplit(const creste_conv_desc* d, const void* x_hi, const void* x_lo,
-                                      const float* x_scal, const float* w_packed, const float* scale,
-                                      const float* shift, const float* residual, float* out, float* amax_out,
-                                      void* stream) {
-  CRESTE_CHECK_ARG(d && x_hi && x_scal && w_packed && out, "creste_conv2d_presplit: null pointer");
+extern "C" int creste_conv2d_ex(const creste_conv_desc* d, const float* x, const float* w_packed,
+                                const float* scale, const float* shift, const float* gate,
+                                const float* residual, float* out, const float* amax_in, float* amax_out,
+                                void* ws, size_t ws_bytes, void* stream) {
+  return conv2d_impl(d, x, w_packed, scale, shift, gate, residual, out, amax_in, amax_out, nullptr, ws, ws_bytes, stream);
+}
+
+extern "C" int creste_conv2d_split_out(const creste_conv_desc* d, const float* x, const float* w_packed,
+                                       const float* scale, const float* shift, const float* gate,
+                                       const float* residual, float* out, const float* amax_in, float* amax_out,
+                                       void* out_hi, void* out_lo, float* out_scal, float bound_mul, float bound_add,
+                                       void* ws, size_t ws_bytes, void* stream) {
+  CRESTE_CHECK_ARG(out_hi && out_scal, "creste_conv2d_split_out: null pointer");
+  const TcSplitOut so = {out_hi, out_lo, out_scal, bound_mul, bound_add};
+  return conv2d_impl(d, x, w_packed, scale, shift, gate, residual, out, amax_in, amax_out, &so, ws, ws_bytes, stream);
+}
+
+static int conv2d_presplit_impl(const creste_conv_desc* d, const void* x_hi, const void* x_lo, const float* x_scal,
+                                const float* w_packed, const float* scale, const float* shift, const float* residual,
+                                float* out, float* amax_out, const TcSplitOut* so, void* stream) {
+  CRESTE_CHECK_ARG(d && x_hi && x_scal && w_packed && (out || (so && so->hi)), "creste_conv2d_presplit: null pointer");
   CRESTE_CHECK_ARG(d->precision == 4 || d->precision == 5, "creste_conv2d_presplit: precision must be 4 (3xFP16) or 5 (fp16)");
   CRESTE_CHECK_ARG(d->precision == 5 || x_lo, "creste_conv2d_presplit: the 3xFP16 mode needs the lo halves");
   if (!conv_tc_supported(d)) {
@@ -349,7 +375,24 @@ extern "C" int creste_conv2d_presplit(const creste_conv_desc* d, const void* x_h
   }
   cudaStream_t st = (cudaStream_t)stream;
   if (amax_out) CRESTE_CUDA(cudaMemsetAsync(amax_out, 0, sizeof(float), st));
-  return conv_tc_presplit_launch(d, x_hi, x_lo, x_scal, w_packed, scale, shift, residual, out, (unsigned*)amax_out, st);
+  return conv_tc_presplit_launch(d, x_hi, x_lo, x_scal, w_packed, scale, shift, residual, out, (unsigned*)amax_out, st, so);
+}
+
+extern "C" int creste_conv2d_presplit(const creste_conv_desc* d, const void* x_hi, const void* x_lo,
+                                      const float* x_scal, const float* w_packed, const float* scale,
+                                      const float* shift, const float* residual, float* out, float* amax_out,
+                                      void* stream) {
+  return conv2d_presplit_impl(d, x_hi, x_lo, x_scal, w_packed, scale, shift, residual, out, amax_out, nullptr, stream);
+}
+
+extern "C" int creste_conv2d_presplit_split_out(const creste_conv_desc* d, const void* x_hi, const void* x_lo,
+                                                const float* x_scal, const float* w_packed, const float* scale,
+                                                const float* shift, const float* residual, float* out, float* amax_out,
+                                                void* out_hi, void* out_lo, float* out_scal, float bound_mul,
+                                                float bound_add, void* stream) {
+  CRESTE_CHECK_ARG(out_hi && out_scal, "creste_conv2d_presplit_split_out: null pointer");
+  const TcSplitOut so = {out_hi, out_lo, out_scal, bound_mul, bound_add};
+  return conv2d_presplit_impl(d, x_hi, x_lo, x_scal, w_packed, scale, shift, residual, out, amax_out, &so, stream);
 }
 
 extern "C" int creste_dwconv_num_parts(int N, int P, int Q) {
@@ -367,23 +410,36 @@ extern "C" int creste_dwconv_bn_swish(const float* x, const float* w, const floa
                                       const float* shift, int N, int H, int W, int C, int R,
                                       int stride, int pad_t, int pad_l, int P, int Q, float* out,
                                       float* chan_part, int nparts, void* stream) {
+  return creste_dwconv_bn_swish_ex(x, w, scale, shift, N, H, W, C, R, stride, pad_t, pad_l, P, Q, out, chan_part, nparts,
+                                   nullptr, stream);
+}
+
+extern "C" int creste_dwconv_bn_swish_ex(const float* x, const float* w, const float* scale,
+                                         const float* shift, int N, int H, int W, int C, int R,
+                                         int stride, int pad_t, int pad_l, int P, int Q, float* out,
+                                         float* chan_part, int nparts, float* amax_out, void* stream) {
   CRESTE_CHECK_ARG(x && w && scale && shift && out && chan_part, "creste_dwconv_bn_swish: null pointer");
   CRESTE_CHECK_ARG(C % 4 == 0 && (R == 3 || R == 5), "creste_dwconv_bn_swish: C%%4==0, R in {3,5}");
   CRESTE_CHECK_ARG(nparts == creste_dwconv_num_parts(N, P, Q), "creste_dwconv_bn_swish: nparts");
   cudaStream_t st = (cudaStream_t)stream;
+  unsigned* am = (unsigned*)amax_out;
+  if (am) CRESTE_CUDA(cudaMemsetAsync(am, 0, sizeof(float), st));
   dim3 grid(nparts, N, ceil_div(C / 4, 256));
   if (stride == 1 && R == 3)
-    dwconv_xb_kernel<3, 1, 4><<<grid, 256, 0, st>>>(x, w, scale, shift, N, H, W, C, pad_t, pad_l, P, Q, out, chan_part);
+    dwconv_xb_kernel<3, 1, 4><<<grid, 256, 0, st>>>(x, w, scale, shift, N, H, W, C, pad_t, pad_l, P, Q, out, chan_part, am);
   else if (stride == 1 && R == 5)
-    dwconv_xb_kernel<5, 1, 4><<<grid, 256, 0, st>>>(x, w, scale, shift, N, H, W, C, pad_t, pad_l, P, Q, out, chan_part);
+    dwconv_xb_kernel<5, 1, 4><<<grid, 256, 0, st>>>(x, w, scale, shift, N, H, W, C, pad_t, pad_l, P, Q, out, chan_part, am);
   else if (stride == 2 && R == 3)
-    dwconv_xb_kernel<3, 2, 4><<<grid, 256, 0, st>>>(x, w, scale, shift, N, H, W, C, pad_t, pad_l, P, Q, out, chan_part);
+    dwconv_xb_kernel<3, 2, 4><<<grid, 256, 0, st>>>(x, w, scale, shift, N, H, W, C, pad_t, pad_l, P, Q, out, chan_part, am);
   else if (stride == 2 && R == 5)
-    dwconv_xb_kernel<5, 2, 4><<<grid, 256, 0, st>>>(x, w, scale, shift, N, H, W, C, pad_t, pad_l, P, Q, out, chan_part);
-  else if (R == 3)
-    dwconv_kernel<3><<<grid, 256, 0, st>>>(x, w, scale, shift, N, H, W, C, stride, pad_t, pad_l, P, Q, out, chan_part);
-  else
-    dwconv_kernel<5><<<grid, 256, 0, st>>>(x, w, scale, shift, N, H, W, C, stride, pad_t, pad_l, P, Q, out, chan_part);
+    dwconv_xb_kernel<5, 2, 4><<<grid, 256, 0, st>>>(x, w, scale, shift, N, H, W, C, pad_t, pad_l, P, Q, out, chan_part, am);
+  else {
+    CRESTE_CHECK_ARG(!am, "creste_dwconv_bn_swish_ex: amax_out needs stride 1 or 2");
+    if (R == 3)
+      dwconv_kernel<3><<<grid, 256, 0, st>>>(x, w, scale, shift, N, H, W, C, stride, pad_t, pad_l, P, Q, out, chan_part);
+    else
+      dwconv_kernel<5><<<grid, 256, 0, st>>>(x, w, scale, shift, N, H, W, C, stride, pad_t, pad_l, P, Q, out, chan_part);
+  }
   return launch_check("dwconv_kernel");
 }
 

@@ -286,6 +286,18 @@ struct TcParams {
   int kelems;                  // operand elements per 128-byte swizzle row: 32 (tf32) or 64 (fp16)
   int n_tiles;                 // number of N tiles (output-channel blocks)
   unsigned* amax_out;          // optional: atomicMax of |out| (float bits), carried with the output tensor
+  // optional (3xFP16 / fp16 modes): the output written as the NEXT tensor-core conv's operand -- fp16 hi / lo of
+  // out * s_out with a power-of-two s_out derived from an a-priori bound of max|out|:
+  //   |out| <= max|x| * max_k(sum|w_k| * |scale_k|) + max_k|shift_k| = (2^15 / s_in) * bound_mul + bound_add
+  // (any power-of-two scale with amax * s in [2^-4, 2^15] keeps the split at 22 bits, so the loose bound costs
+  // nothing).  `out` may then be null: the fp32 tensor is not written and the consumer's split pre-pass disappears.
+  uint2* out_hi; uint2* out_lo; float* out_scal;
+  float bound_mul, bound_add;
+};
+
+// optional extra outputs of one conv launch (see TcParams::out_hi)
+struct TcSplitOut {
+  void* hi; void* lo; float* scal; float bound_mul, bound_add;
 };
 
 constexpr int TC_THREADS = 320;     // warp 0 TMA, warp 1 MMA, warps 2..9 epilogue (two per TMEM lane quarter)
@@ -491,6 +503,19 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_consta
     const bool pix_ok = (ox < p.Q) && (oy < p.P) && (img < p.N);
     const size_t pix = ((size_t)img * p.P + oy) * p.Q + ox;
     float amx = 0.0f;
+    float s_out = 1.0f;
+    if (F16 && p.out_hi) {
+      const float bound = fmaf(32768.0f * __ldg(p.act_inv), p.bound_mul, p.bound_add);
+      const unsigned bb = __float_as_uint(bound);
+      int e = (int)((bb >> 23) & 0xffu) - 127;
+      if (bb == 0u || !isfinite(bound)) e = 14;
+      const int k = max(-100, min(100, 14 - e));
+      s_out = __uint_as_float((unsigned)(127 + k) << 23);
+      if (blockIdx.x == 0 && threadIdx.x == 64) {
+        p.out_scal[0] = s_out;
+        p.out_scal[1] = __uint_as_float((unsigned)(127 - k) << 23);
+      }
+    }
     mbar_wait(&tmem_full_bar, 0);
     tc_fence_after();
     TC_STAMP(3);
@@ -539,7 +564,22 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_consta
               }
               const float4 o4 = make_float4(tc_act(o[0], p.act), tc_act(o[1], p.act), tc_act(o[2], p.act), tc_act(o[3], p.act));
               amx = fmaxf(fmaxf(amx, fmaxf(fabsf(o4.x), fabsf(o4.y))), fmaxf(fabsf(o4.z), fabsf(o4.w)));
-              *reinterpret_cast<float4*>(dst) = o4;
+              if (p.out) *reinterpret_cast<float4*>(dst) = o4;
+              if (F16 && p.out_hi) {
+                // same arithmetic per element as f16_split_kernel
+                const float xs[4] = {o4.x * s_out, o4.y * s_out, o4.z * s_out, o4.w * s_out};
+                unsigned short h[4], l[4];
+#pragma unroll
+                for (int q = 0; q < 4; ++q) {
+                  const __half hh = __float2half_rn(xs[q]);
+                  h[q] = __half_as_ushort(hh);
+                  l[q] = __half_as_ushort(__float2half_rn((xs[q] - __half2float(hh)) * 2048.0f));
+                }
+                const size_t o8 = ((size_t)rpix * p.K + n) >> 2;
+                p.out_hi[o8] = make_uint2((unsigned)h[0] | ((unsigned)h[1] << 16), (unsigned)h[2] | ((unsigned)h[3] << 16));
+                if (p.out_lo)
+                  p.out_lo[o8] = make_uint2((unsigned)l[0] | ((unsigned)l[1] << 16), (unsigned)l[2] | ((unsigned)l[3] << 16));
+              }
             } else {
 #pragma unroll
               for (int q = 0; q < 4; ++q)
@@ -790,11 +830,11 @@ size_t conv_tc_workspace_bytes(const creste_conv_desc* d) {
 
 static int conv_tc_main(const creste_conv_desc* d, float* x_hi, float* x_lo, float* scal, const float* w_packed,
                         const float* scale, const float* shift, const float* residual, float* out, unsigned* amax_out,
-                        cudaStream_t st);
+                        const TcSplitOut* so, cudaStream_t st);
 
 int conv_tc_launch(const creste_conv_desc* d, const float* x, const float* w_packed, const float* scale,
                    const float* shift, const float* gate, const float* residual, float* out, const float* amax_in,
-                   unsigned* amax_out, void* ws, size_t ws_bytes, cudaStream_t st) {
+                   unsigned* amax_out, void* ws, size_t ws_bytes, cudaStream_t st, const TcSplitOut* so) {
   if (ws_bytes < conv_tc_workspace_bytes(d) || !ws) {
     set_error("creste_conv2d(tc): workspace %zu < %zu", ws_bytes, conv_tc_workspace_bytes(d));
     return CRESTE_ERR_WORKSPACE;
@@ -842,20 +882,29 @@ int conv_tc_launch(const creste_conv_desc* d, const float* x, const float* w_pac
     int rc = launch_check("tf32_split_kernel");
     if (rc) return rc;
   }
-  return conv_tc_main(d, x_hi, x_lo, scal, w_packed, scale, shift, residual, out, amax_out, st);
+  return conv_tc_main(d, x_hi, x_lo, scal, w_packed, scale, shift, residual, out, amax_out, so, st);
 }
 
 // operands already split (by the pre-pass above, or written that way by the producing kernel)
 int conv_tc_presplit_launch(const creste_conv_desc* d, const void* x_hi, const void* x_lo, const float* x_scal,
                             const float* w_packed, const float* scale, const float* shift, const float* residual,
-                            float* out, unsigned* amax_out, cudaStream_t st) {
-  return conv_tc_main(d, (float*)x_hi, (float*)x_lo, (float*)x_scal, w_packed, scale, shift, residual, out, amax_out, st);
+                            float* out, unsigned* amax_out, cudaStream_t st, const TcSplitOut* so) {
+  return conv_tc_main(d, (float*)x_hi, (float*)x_lo, (float*)x_scal, w_packed, scale, shift, residual, out, amax_out, so, st);
 }
 
 static int conv_tc_main(const creste_conv_desc* d, float* x_hi, float* x_lo, float* scal, const float* w_packed,
                         const float* scale, const float* shift, const float* residual, float* out, unsigned* amax_out,
-                        cudaStream_t st) {
+                        const TcSplitOut* so, cudaStream_t st) {
   const bool f16 = d->precision == 4 || d->precision == 5;
+  if (so && so->hi) {
+    if (!f16 || d->out_nchw || d->K % 8 != 0 || !so->scal || ((uintptr_t)so->hi & 7u) || ((uintptr_t)so->lo & 7u)) {
+      set_error("creste_conv2d(tc): the split output needs a 3xFP16 / fp16 mode, NHWC output and K %% 8 == 0");
+      return CRESTE_ERR_ARG;
+    }
+  } else if (!out) {
+    set_error("creste_conv2d(tc): no output");
+    return CRESTE_ERR_ARG;
+  }
   const int split = d->precision == 1 || d->precision == 4;
   int block_n, npad, cpad;
   conv_tc_layout(d->K, d->C, d->R, d->S, &block_n, &npad, &cpad);
@@ -871,6 +920,11 @@ static int conv_tc_main(const creste_conv_desc* d, float* x_hi, float* x_lo, flo
   p.tiles_y = ceil_div(d->P, p.hbox);
   p.block_n = block_n; p.act = d->act; p.split = split; p.out_nchw = d->out_nchw;
   p.amax_out = amax_out;
+  p.out_hi = so ? (uint2*)so->hi : nullptr;
+  p.out_lo = so ? (uint2*)so->lo : nullptr;
+  p.out_scal = so ? so->scal : nullptr;
+  p.bound_mul = so ? so->bound_mul : 0.0f;
+  p.bound_add = so ? so->bound_add : 0.0f;
 
   // two CTAs on adjacent M tiles form a tcgen05 CTA pair (cta_group::2, M = 256)
   const int m_tiles = d->N * p.tiles_y * p.tiles_x;

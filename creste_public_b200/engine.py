@@ -179,10 +179,41 @@ class FusedConv:
         stride = conv.stride[0] if isinstance(conv.stride, tuple) else conv.stride
         return pick_mode(tuple(x_shape), K, R, S, stride, pad, precision or _PRECISION)
 
+    def out_bound(self, mode):
+        """(bound_mul, bound_add) of this conv's output: |out| <= max|x| * bound_mul + bound_add with
+        bound_mul = max_k(sum|w_k| * |scale_k|), bound_add = max_k|shift_k| (two host floats, cached per parameter
+        version; the 0.1 % head-room covers the rounding of the fp32 accumulation)."""
+        conv, bn = self.conv, self.bn
+        tensors = [conv.weight, conv.bias] + ([bn.weight, bn.bias, bn.running_mean, bn.running_var]
+                                              if bn is not None else [])
+
+        def build():
+            _, scale, shift = self.packed(mode)
+            l1 = conv.weight.detach().float().abs().sum(dim=(1, 2, 3))
+            if scale is not None:
+                l1 = l1 * scale.abs()
+            badd = float(shift.abs().max()) if shift is not None else 0.0
+            return float(l1.max()) * 1.001, badd * 1.001
+        return self.cache.get("bound_" + mode, tensors, build)
+
+    def split_ok(self, x_shape, gate=None, precision=None):
+        """True if this conv, fed an [N,H,W,C] activation of `x_shape`, runs in the fp16 tensor-core mode and can
+        therefore take a SplitAct written by its producer's epilogue."""
+        mode = precision or _PRECISION
+        return (mode in ("3xfp16", "fp16") and gate is None and not torch.jit.is_tracing() and x_shape[-1] % 8 == 0
+                and self.tc_mode(x_shape, precision=precision) == mode)
+
     def __call__(self, x_nhwc, act="none", pad=None, gate=None, residual=None, out_nchw=False,
-                 precision=None):
+                 precision=None, split_out=None):
+        """split_out: None | "only" | "both" -- ask the epilogue to write the output (also) as the 3xFP16 operand of
+        the next tensor-core conv ("only": a SplitAct is returned and the fp32 tensor never exists; "both": the fp32
+        tensor is returned with the SplitAct attached as `._split`).  Honoured only when this conv itself runs in the
+        fp16 tensor-core mode without a residual; otherwise the plain fp32 tensor is returned."""
         if isinstance(x_nhwc, ops.SplitAct):
-            return self._call_presplit(x_nhwc, act, pad, residual, out_nchw, precision)
+            return self._call_presplit(x_nhwc, act, pad, residual, out_nchw, precision, split_out)
+        pre = getattr(x_nhwc, "_split", None)
+        if pre is not None and gate is None and self.split_ok(x_nhwc.shape, None, precision):
+            return self._call_presplit(pre, act, pad, residual, out_nchw, precision, split_out)
         conv = self.conv
         K, _, R, S = (int(v) for v in conv.weight.shape)      # ints also under torch.jit.trace
         if pad is None:
@@ -199,14 +230,27 @@ class FusedConv:
         # 3xFP16: max|out| is produced by this conv's epilogue and travels with the tensor (`_amax`), so the next
         # tensor-core conv derives its operand scale from it instead of making an extra amax pass over its input
         amax_out = torch.empty(1, device=x_nhwc.device) if track else None
+        so = None
+        if (split_out is not None and mode in ("3xfp16", "fp16") and residual is None and not out_nchw and K % 8 == 0
+                and not torch.jit.is_tracing()):
+            so = (split_out,) + self.out_bound(mode)
         out = ops.conv2d(x_nhwc, w, K, R, S, stride, pad, scale, shift, gate, residual, act, out_nchw, mode,
-                         amax_in=carried_amax(x_nhwc) if mode in ("3xfp16", "fp16") else None, amax_out=amax_out)
-        if track:
-            out._amax = amax_out
-        return out
+                         amax_in=carried_amax(x_nhwc) if mode in ("3xfp16", "fp16") else None, amax_out=amax_out,
+                         **({"split_out": so} if so is not None else {}))
+        return _finish_split(out, so, amax_out if track else None)
 
 
-def _fused_presplit(self, xs, act, pad, residual, out_nchw, precision):
+def _finish_split(out, so, amax_out):
+    """Attach the carried bound / the SplitAct to what ops.conv2d(_presplit) returned."""
+    if so is not None and so[0] == "both":
+        out, sp = out
+        out._split = sp
+    if amax_out is not None and not isinstance(out, ops.SplitAct):
+        out._amax = amax_out
+    return out
+
+
+def _fused_presplit(self, xs, act, pad, residual, out_nchw, precision, split_out=None):
     conv = self.conv
     K, _, R, S = (int(v) for v in conv.weight.shape)
     if pad is None:
@@ -218,9 +262,12 @@ def _fused_presplit(self, xs, act, pad, residual, out_nchw, precision):
         raise RuntimeError(f"pre-split operand handed to a conv that runs in mode {mode}")
     w, scale, shift = self.packed(mode)
     amax_out = torch.empty(1, device=xs.device)
-    out = ops.conv2d_presplit(xs, w, K, R, S, stride, pad, scale, shift, residual, act, out_nchw, mode, amax_out)
-    out._amax = amax_out
-    return out
+    so = None
+    if split_out is not None and residual is None and not out_nchw and K % 8 == 0:
+        so = (split_out,) + self.out_bound(mode)
+    out = ops.conv2d_presplit(xs, w, K, R, S, stride, pad, scale, shift, residual, act, out_nchw, mode, amax_out,
+                              split_out=so)
+    return _finish_split(out, so, amax_out)
 
 
 FusedConv._call_presplit = _fused_presplit

@@ -320,23 +320,40 @@ def tc_supported(x_shape, K, R, S, stride, pad, precision):
 
 
 def conv2d(x_nhwc, w_packed, K, R, S, stride=1, pad=(0, 0, 0, 0), scale=None, shift=None,
-           gate=None, residual=None, act="none", out_nchw=False, precision="fp32", amax_in=None, amax_out=None):
+           gate=None, residual=None, act="none", out_nchw=False, precision="fp32", amax_in=None, amax_out=None,
+           split_out=None):
     """NHWC conv + folded BN/bias + residual + activation.  pad = (top, bottom, left, right).
     amax_in / amax_out: optional device float[1] tensors -- an upper bound of max|x * gate| that lets the 3xFP16
-    operand pre-pass skip its amax pass, and the slot that receives max|out| from the epilogue."""
+    operand pre-pass skip its amax pass, and the slot that receives max|out| from the epilogue.
+    split_out = (mode, bound_mul, bound_add), mode "only" | "both": the output is (also) written as the next
+    tensor-core conv's SplitAct operand from the epilogue; returns the SplitAct ("only") or (out, SplitAct)."""
     N, H, W, Cc = x_nhwc.shape
     pt, pb, pl, pr = pad
     P = (H + pt + pb - R) // stride + 1
     Q = (W + pl + pr - S) // stride + 1
     d = ConvDesc(N, H, W, Cc, K, R, S, stride, pt, pl, P, Q, ACT[act], int(out_nchw),
                  PRECISION[precision])
-    out = torch.empty((N, K, P, Q) if out_nchw else (N, P, Q, K), device=x_nhwc.device)
     n = lib().creste_conv2d_workspace_bytes(C.byref(d))
     ws = _ws(n, x_nhwc.device) if n else None
+    if split_out is not None:
+        mode, bmul, badd = split_out
+        so = _new_split((N, P, Q, K), x_nhwc.device, want_lo=(precision == "3xfp16"))
+        out = torch.empty(N, P, Q, K, device=x_nhwc.device) if mode == "both" else None
+        check(lib().creste_conv2d_split_out(C.byref(d), ptr(x_nhwc), ptr(w_packed), ptr(scale), ptr(shift), ptr(gate),
+                                            ptr(residual), ptr(out), ptr(amax_in), ptr(amax_out), ptr(so.hi), ptr(so.lo),
+                                            ptr(so.scal), C.c_float(bmul), C.c_float(badd), ptr(ws), C.c_size_t(n),
+                                            stream()), "creste_conv2d_split_out")
+        return so if out is None else (out, so)
+    out = torch.empty((N, K, P, Q) if out_nchw else (N, P, Q, K), device=x_nhwc.device)
     check(lib().creste_conv2d_ex(C.byref(d), ptr(x_nhwc), ptr(w_packed), ptr(scale), ptr(shift),
                                  ptr(gate), ptr(residual), ptr(out), ptr(amax_in), ptr(amax_out), ptr(ws),
                                  C.c_size_t(n), stream()), "creste_conv2d")
     return out
+
+
+def _new_split(shape, device, want_lo=True):
+    hi = torch.empty(shape, dtype=torch.float16, device=device)
+    return SplitAct(hi, torch.empty_like(hi) if want_lo else None, torch.empty(2, device=device), shape)
 
 
 class SplitAct:
@@ -370,13 +387,22 @@ def upsample_concat_split(skip_nhwc, x_nhwc, out_hw, scale_factor, amax_skip, am
 
 
 def conv2d_presplit(xs, w_packed, K, R, S, stride=1, pad=(0, 0, 0, 0), scale=None, shift=None, residual=None,
-                    act="none", out_nchw=False, precision="3xfp16", amax_out=None):
-    """Tensor-core conv on a SplitAct input (no activation pre-pass)."""
+                    act="none", out_nchw=False, precision="3xfp16", amax_out=None, split_out=None):
+    """Tensor-core conv on a SplitAct input (no activation pre-pass).  split_out: as in conv2d."""
     N, H, W, Cc = xs.shape
     pt, pb, pl, pr = pad
     P = (H + pt + pb - R) // stride + 1
     Q = (W + pl + pr - S) // stride + 1
     d = ConvDesc(N, H, W, Cc, K, R, S, stride, pt, pl, P, Q, ACT[act], int(out_nchw), PRECISION[precision])
+    if split_out is not None:
+        mode, bmul, badd = split_out
+        so = _new_split((N, P, Q, K), xs.device, want_lo=(precision == "3xfp16"))
+        out = torch.empty(N, P, Q, K, device=xs.device) if mode == "both" else None
+        check(lib().creste_conv2d_presplit_split_out(C.byref(d), ptr(xs.hi), ptr(xs.lo), ptr(xs.scal), ptr(w_packed),
+                                                     ptr(scale), ptr(shift), ptr(residual), ptr(out), ptr(amax_out),
+                                                     ptr(so.hi), ptr(so.lo), ptr(so.scal), C.c_float(bmul),
+                                                     C.c_float(badd), stream()), "creste_conv2d_presplit_split_out")
+        return so if out is None else (out, so)
     out = torch.empty((N, K, P, Q) if out_nchw else (N, P, Q, K), device=xs.device)
     check(lib().creste_conv2d_presplit(C.byref(d), ptr(xs.hi), ptr(xs.lo), ptr(xs.scal), ptr(w_packed), ptr(scale),
                                        ptr(shift), ptr(residual), ptr(out), ptr(amax_out), stream()),
@@ -384,8 +410,9 @@ def conv2d_presplit(xs, w_packed, K, R, S, stride=1, pad=(0, 0, 0, 0), scale=Non
     return out
 
 
-def dwconv_bn_swish(x_nhwc, w_rsc, scale, shift, R, stride, pad):
-    """Depthwise conv + BN + swish; returns (out NHWC, chan_part [N,nparts,C] SE partial sums)."""
+def dwconv_bn_swish(x_nhwc, w_rsc, scale, shift, R, stride, pad, amax_out=None):
+    """Depthwise conv + BN + swish; returns (out NHWC, chan_part [N,nparts,C] SE partial sums).
+    amax_out: optional device float[1] that receives max|out|."""
     N, H, W, Cc = x_nhwc.shape
     pt, pb, pl, pr = pad
     P = (H + pt + pb - R) // stride + 1
@@ -393,8 +420,8 @@ def dwconv_bn_swish(x_nhwc, w_rsc, scale, shift, R, stride, pad):
     out = torch.empty(N, P, Q, Cc, device=x_nhwc.device)
     nparts = lib().creste_dwconv_num_parts(N, P, Q)
     csum = torch.empty(N, nparts, Cc, device=x_nhwc.device)
-    check(lib().creste_dwconv_bn_swish(ptr(x_nhwc), ptr(w_rsc), ptr(scale), ptr(shift), N, H, W, Cc,
-                                       R, stride, pt, pl, P, Q, ptr(out), ptr(csum), nparts, stream()),
+    check(lib().creste_dwconv_bn_swish_ex(ptr(x_nhwc), ptr(w_rsc), ptr(scale), ptr(shift), N, H, W, Cc,
+                                          R, stride, pt, pl, P, Q, ptr(out), ptr(csum), nparts, ptr(amax_out), stream()),
           "creste_dwconv_bn_swish")
     return out, csum
 
@@ -1053,18 +1080,18 @@ def _tracing():
 
 
 def _t_conv2d(x_nhwc, w_packed, K, R, S, stride=1, pad=(0, 0, 0, 0), scale=None, shift=None, gate=None, residual=None,
-              act="none", out_nchw=False, precision="fp32", amax_in=None, amax_out=None):
+              act="none", out_nchw=False, precision="fp32", amax_in=None, amax_out=None, split_out=None):
     if _tracing():
         return torch.ops.creste.conv2d(x_nhwc, w_packed, int(K), int(R), int(S), int(stride), [int(p) for p in pad], scale,
                                        shift, gate, residual, act or "none", bool(out_nchw), precision)
     return _RAW["conv2d"](x_nhwc, w_packed, K, R, S, stride, pad, scale, shift, gate, residual, act, out_nchw, precision,
-                          amax_in, amax_out)
+                          amax_in, amax_out, split_out)
 
 
-def _t_dwconv_bn_swish(x_nhwc, w_rsc, scale, shift, R, stride, pad):
+def _t_dwconv_bn_swish(x_nhwc, w_rsc, scale, shift, R, stride, pad, amax_out=None):
     if _tracing():
         return torch.ops.creste.dwconv_bn_swish(x_nhwc, w_rsc, scale, shift, int(R), int(stride), [int(p) for p in pad])
-    return _RAW["dwconv_bn_swish"](x_nhwc, w_rsc, scale, shift, R, stride, pad)
+    return _RAW["dwconv_bn_swish"](x_nhwc, w_rsc, scale, shift, R, stride, pad, amax_out)
 
 
 def _t_se_gate(chan_part, hw, w_red, b_red, w_exp, b_exp):

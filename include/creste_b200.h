@@ -198,7 +198,21 @@ int creste_conv2d_ex(const creste_conv_desc* d, const float* x, const float* w_p
 int creste_conv2d_presplit(const creste_conv_desc* d, const void* x_hi, const void* x_lo, const float* x_scal,
                            const float* w_packed, const float* scale, const float* shift, const float* residual,
                            float* out, float* amax_out, void* stream);
-
+/* The two calls above with the output ALSO (out != NULL) or ONLY (out == NULL) written as the next tensor-core conv's
+ * 3xFP16 operand: out_hi / out_lo fp16 [N,P,Q,K] (out_lo may be NULL for precision 5), out_scal = DEVICE float[2]
+ * {s, 1/s}.  The power-of-two scale comes from an a-priori bound of max|out| the caller supplies as two host floats:
+ *   bound_mul = max_k(sum_{c,r,s} |w[k,c,r,s]| * |scale[k]|),  bound_add = max_k |shift[k]|
+ * (|out| <= max|x| * bound_mul + bound_add; residual must be NULL).  Replaces the split pre-pass of the consuming conv
+ * in conv -> BN -> ReLU -> conv chains (reference creste/models/blocks/effnet.py:12-28, inpainting.py:52-68 and the
+ * torchvision BasicBlocks of :80-103).  Precision 4 / 5, NHWC output, K % 8 == 0. */
+int creste_conv2d_split_out(const creste_conv_desc* d, const float* x, const float* w_packed, const float* scale,
+                            const float* shift, const float* gate, const float* residual, float* out,
+                            const float* amax_in, float* amax_out, void* out_hi, void* out_lo, float* out_scal,
+                            float bound_mul, float bound_add, void* ws, size_t ws_bytes, void* stream);
+int creste_conv2d_presplit_split_out(const creste_conv_desc* d, const void* x_hi, const void* x_lo, const float* x_scal,
+                                     const float* w_packed, const float* scale, const float* shift,
+                                     const float* residual, float* out, float* amax_out, void* out_hi, void* out_lo,
+                                     float* out_scal, float bound_mul, float bound_add, void* stream);
 
 size_t creste_conv2d_workspace_bytes(const creste_conv_desc* d);
 /* tcgen05 path (precision 1, 2): 1 if the shape is served by the tensor-core kernel (stride 1 or 2, R, S <= 7,
@@ -222,6 +236,12 @@ int creste_dwconv_num_parts(int N, int P, int Q);
 int creste_dwconv_bn_swish(const float* x, const float* w, const float* scale, const float* shift,
                            int N, int H, int W, int C, int R, int stride, int pad_t, int pad_l,
                            int P, int Q, float* out, float* chan_part, int nparts, void* stream);
+/* the same with max|out| published to amax_out (DEVICE float[1], zeroed first; may be NULL): the bound travels with
+ * the tensor so that the project conv's 3xFP16 operand pre-pass needs no amax pass (the SE gate is a sigmoid:
+ * max|out * gate| <= max|out|).  Stride 1 or 2. */
+int creste_dwconv_bn_swish_ex(const float* x, const float* w, const float* scale, const float* shift, int N, int H,
+                              int W, int C, int R, int stride, int pad_t, int pad_l, int P, int Q, float* out,
+                              float* chan_part, int nparts, float* amax_out, void* stream);
 
 /* SE gate: mean -> 1x1 reduce(+b) -> swish -> 1x1 expand(+b) -> sigmoid.
  *   chan_part [N,nparts,C] (summed in order); w_red [Csq,C], b_red [Csq], w_exp [C,Csq],

@@ -124,3 +124,50 @@ def test_tc_unsupported_shapes_are_refused(cuda):
     w = ops.pack_conv_weight(torch.randn(6, 64, 1, 1, device=cuda))
     with pytest.raises(RuntimeError, match="precision mode"):
         ops.conv2d(x, w, 6, 1, 1, 1, (0, 0, 0, 0), precision="3xtf32")
+
+
+@pytest.mark.parametrize("C,K1,K2,H,W,R", [(64, 64, 32, 32, 48, 3), (496, 496, 256, 16, 30, 3), (320, 256, 256, 24, 24, 3),
+                                           (256, 128, 128, 20, 28, 1)])
+def test_split_output_epilogue_feeds_the_next_conv(cuda, C, K1, K2, H, W, R):
+    """conv -> BN -> ReLU -> conv with the first conv's epilogue writing the second conv's 3xFP16 operand
+    (creste_conv2d_split_out / creste_conv2d_presplit_split_out): the hi / lo halves reconstruct the fp32 output to
+    2^-21 of its bound, the fp32 output of the "both" form is untouched, and the chain gives the same result as the
+    split pre-pass (the two power-of-two scales differ, so elements that are fp16-subnormal under the looser one may
+    differ in their last bits: 1e-6 of the maximum)."""
+    import creste_public_b200 as cb
+    from creste_public_b200 import ops
+    from creste_public_b200.engine import FusedConv
+    from torch import nn
+    torch.manual_seed(C + K1)
+    cb.set_precision("3xfp16")
+    try:
+        c1, b1 = nn.Conv2d(C, K1, R, padding=R // 2, bias=False).to(cuda), nn.BatchNorm2d(K1).to(cuda).eval()
+        c2, b2 = nn.Conv2d(K1, K2, 3, padding=1, bias=False).to(cuda), nn.BatchNorm2d(K2).to(cuda).eval()
+        for b in (b1, b2):
+            b.running_mean.normal_(0, 0.1); b.running_var.uniform_(0.5, 1.5); b.weight.data.uniform_(0.5, 1.5)
+            b.bias.data.normal_(0, 0.1)
+        f1, f2 = FusedConv(c1, b1), FusedConv(c2, b2)
+        x = torch.randn(2, H, W, C, device=cuda)
+        with torch.no_grad():
+            mid = f1(x, act="relu")
+            ref = f2(mid, act="relu")
+            sp = f1(x, act="relu", split_out="only")
+            assert isinstance(sp, ops.SplitAct) and f2.split_ok(mid.shape)
+            s, inv = float(sp.scal[0]), float(sp.scal[1])
+            assert s * inv == 1.0 and float(mid.abs().max()) * s <= 32768.0
+            rec = (sp.hi.float() + sp.lo.float() / 2048.0) * inv
+            assert float((rec - mid).abs().max()) <= 2.0 ** -21 * (32768.0 * inv)
+            out_only = f2(sp, act="relu")
+            both = f1(x, act="relu", split_out="both")
+            assert torch.equal(both, mid) and isinstance(both._split, ops.SplitAct)
+            assert torch.equal(both._split.hi, sp.hi) and torch.equal(both._split.lo, sp.lo)
+            out_both = f2(both, act="relu")
+            # a SplitAct input and a split output in the same launch (creste_conv2d_presplit_split_out)
+            sp2 = f2(sp, act="relu", split_out="only")
+            rec2 = (sp2.hi.float() + sp2.lo.float() / 2048.0) * float(sp2.scal[1])
+        tol = 1e-6 * float(ref.abs().max())
+        assert float((out_only - ref).abs().max()) <= tol
+        assert torch.equal(out_both, out_only)
+        assert float((rec2 - out_only).abs().max()) <= 2.0 ** -21 * 32768.0 * float(sp2.scal[1])
+    finally:
+        cb.set_precision("fp32")

@@ -34,7 +34,16 @@ def test_traced_model_equals_eager(cuda, mode, tmp_path):
             eager = model((b.cuda(), p2p.cuda()))
             got = traced((b.cuda(), p2p.cuda()))
         assert set(got.keys()) == set(eager.keys())
-        for k in ("depth_preds_feats", "depth_preds_logits", "depth_preds_bins", "dino_pe_feats", "bev_coords"):
+        # fp32: the traced ops ARE the eager ops.  3xfp16: the eager path lets conv epilogues write the next conv's
+        # fp16 hi / lo operand with a scale from an a-priori bound, the traced (pure-function) ops derive it from the
+        # carried maximum -- two power-of-two scales, identical products except for elements that are fp16-subnormal
+        # under the looser one: last-bit differences, bounded here at 2e-6 of the tensor maximum; the integers agree
+        for k in ("depth_preds_feats", "depth_preds_logits", "dino_pe_feats"):
+            if mode == "fp32":
+                assert torch.equal(got[k], eager[k]), k
+            else:
+                assert float((got[k] - eager[k]).abs().max()) <= 2e-6 * float(eager[k].abs().max()), k
+        for k in ("depth_preds_bins", "bev_coords"):
             assert torch.equal(got[k], eager[k]), k
         for k in ("bev_features", "inpainting_sam_preds", "elevation_features", "input_view", "traversability_preds",
                   "traversability_preds_full"):
@@ -45,7 +54,7 @@ def test_traced_model_equals_eager(cuda, mode, tmp_path):
         loaded = torch.jit.load(path)
         with torch.no_grad():
             again = loaded((b.cuda(), p2p.cuda()))
-        assert torch.equal(again["depth_preds_feats"], eager["depth_preds_feats"])
+        assert torch.equal(again["depth_preds_feats"], got["depth_preds_feats"])
         assert float((again["traversability_preds"] - eager["traversability_preds"]).abs().max()) <= 1e-4
     finally:
         cb.set_precision("fp32")

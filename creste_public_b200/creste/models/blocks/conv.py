@@ -33,7 +33,9 @@ class _ConvStack(nn.Module):
             while i < len(layers):
                 conv = layers[i]
                 bn = layers[i + 1] if isinstance(layers[i + 1], nn.BatchNorm2d) else None
-                fc.append(FusedConv(conv, bn))
+                # layers after the first are fed a pre-split operand by their producer's epilogue (forward_nhwc):
+                # with no pre-pass to pay, 1x1 convs with 64 <= C <= 192 also belong on the tensor cores
+                fc.append(FusedConv(conv, bn, prefer_tc=len(fc) > 0))
                 i += 3 if bn is not None else 2
             object.__setattr__(self, "_fc", fc)
         return self._fc
@@ -55,8 +57,18 @@ class _ConvStack(nn.Module):
     def forward_nhwc(self, x):
         if self.training:
             return self.forward_train(x)
-        for f in self._fused(self._seq()):
-            x = f(x, act="relu")
+        fs = self._fused(self._seq())
+        for i, f in enumerate(fs):
+            so = None
+            if i + 1 < len(fs):
+                # conv (+BN) + ReLU -> conv: the intermediate has one consumer; write it as that conv's operand
+                N, H, W = x.shape[0], x.shape[1], x.shape[2]
+                kh, kw = f.conv.kernel_size
+                ph, pw = f.conv.padding if isinstance(f.conv.padding, tuple) else (f.conv.padding,) * 2
+                st = f.conv.stride[0] if isinstance(f.conv.stride, tuple) else f.conv.stride
+                mid = (N, (H + 2 * ph - kh) // st + 1, (W + 2 * pw - kw) // st + 1, f.conv.out_channels)
+                so = "only" if fs[i + 1].split_ok(mid) else None
+            x = f(x, act="relu", split_out=so)
         return x
 
     def forward(self, x):

@@ -9,7 +9,7 @@ int conv_simt_launch(const creste_conv_desc* d, const float* x, const float* w, 
 int conv1x1_stream_launch(const creste_conv_desc* d, const float* x, const float* w, int ldw, const float* scale,
                           const float* shift, const float* gate, const float* residual, float* out,
                           unsigned* amax_out, cudaStream_t st);
-struct TcSplitOut { void* hi; void* lo; float* scal; float bound_mul, bound_add; };   // conv_tc.cu
+struct TcSplitOut { void* hi; void* lo; float* scal; float bound_mul, bound_add; const float* in_amax; };   // conv_tc.cu
 int conv_tc_launch(const creste_conv_desc* d, const float* x, const float* w_packed,
                    const float* scale, const float* shift, const float* gate, const float* residual,
                    float* out, const float* amax_in, unsigned* amax_out, void* ws, size_t ws_bytes,
@@ -358,7 +358,7 @@ extern "C" int creste_conv2d_split_out(const creste_conv_desc* d, const float* x
                                        void* out_hi, void* out_lo, float* out_scal, float bound_mul, float bound_add,
                                        void* ws, size_t ws_bytes, void* stream) {
   CRESTE_CHECK_ARG(out_hi && out_scal, "creste_conv2d_split_out: null pointer");
-  const TcSplitOut so = {out_hi, out_lo, out_scal, bound_mul, bound_add};
+  const TcSplitOut so = {out_hi, out_lo, out_scal, bound_mul, bound_add, amax_in};
   return conv2d_impl(d, x, w_packed, scale, shift, gate, residual, out, amax_in, amax_out, &so, ws, ws_bytes, stream);
 }
 
@@ -389,9 +389,9 @@ extern "C" int creste_conv2d_presplit_split_out(const creste_conv_desc* d, const
                                                 const float* x_scal, const float* w_packed, const float* scale,
                                                 const float* shift, const float* residual, float* out, float* amax_out,
                                                 void* out_hi, void* out_lo, float* out_scal, float bound_mul,
-                                                float bound_add, void* stream) {
+                                                float bound_add, const float* x_amax, void* stream) {
   CRESTE_CHECK_ARG(out_hi && out_scal, "creste_conv2d_presplit_split_out: null pointer");
-  const TcSplitOut so = {out_hi, out_lo, out_scal, bound_mul, bound_add};
+  const TcSplitOut so = {out_hi, out_lo, out_scal, bound_mul, bound_add, x_amax};
   return conv2d_presplit_impl(d, x_hi, x_lo, x_scal, w_packed, scale, shift, residual, out, amax_out, &so, stream);
 }
 

@@ -293,11 +293,14 @@ struct TcParams {
   // nothing).  `out` may then be null: the fp32 tensor is not written and the consumer's split pre-pass disappears.
   uint2* out_hi; uint2* out_lo; float* out_scal;
   float bound_mul, bound_add;
+  // max|x| for that bound: the TRUE maximum carried with the input (device float[1]) when there is one -- chained
+  // a-priori bounds would compound (each is 2^7 .. 2^10 loose) -- else 2^15 / s_in from the operand's scale record
+  const float* in_amax;
 };
 
 // optional extra outputs of one conv launch (see TcParams::out_hi)
 struct TcSplitOut {
-  void* hi; void* lo; float* scal; float bound_mul, bound_add;
+  void* hi; void* lo; float* scal; float bound_mul, bound_add; const float* in_amax;
 };
 
 constexpr int TC_THREADS = 320;     // warp 0 TMA, warp 1 MMA, warps 2..9 epilogue (two per TMEM lane quarter)
@@ -505,7 +508,8 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_consta
     float amx = 0.0f;
     float s_out = 1.0f;
     if (F16 && p.out_hi) {
-      const float bound = fmaf(32768.0f * __ldg(p.act_inv), p.bound_mul, p.bound_add);
+      const float xmax = p.in_amax ? __ldg(p.in_amax) : 32768.0f * __ldg(p.act_inv);
+      const float bound = fmaf(xmax, p.bound_mul, p.bound_add);
       const unsigned bb = __float_as_uint(bound);
       int e = (int)((bb >> 23) & 0xffu) - 127;
       if (bb == 0u || !isfinite(bound)) e = 14;
@@ -925,6 +929,7 @@ static int conv_tc_main(const creste_conv_desc* d, float* x_hi, float* x_lo, flo
   p.out_scal = so ? so->scal : nullptr;
   p.bound_mul = so ? so->bound_mul : 0.0f;
   p.bound_add = so ? so->bound_add : 0.0f;
+  p.in_amax = so ? so->in_amax : nullptr;
 
   // two CTAs on adjacent M tiles form a tcgen05 CTA pair (cta_group::2, M = 256)
   const int m_tiles = d->N * p.tiles_y * p.tiles_x;

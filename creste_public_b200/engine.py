@@ -54,7 +54,7 @@ def drop_connect_scale(B, rate, device):
 _SIMT_MAX_REDUCTION = int(os.environ.get("CRESTE_SIMT_MAX_REDUCTION", "192"))
 
 
-def pick_mode(x_shape, K, R, S, stride, pad, mode):
+def pick_mode(x_shape, K, R, S, stride, pad, mode, prefer_tc=False):
     """Requested precision, or the next stricter one the shape is served by:
     3xfp16 -> 3xtf32 -> fp32 (never a looser one)."""
     x_shape = tuple(int(v) for v in x_shape)
@@ -62,7 +62,9 @@ def pick_mode(x_shape, K, R, S, stride, pad, mode):
     # short reductions (1x1 convs with C <= 192: the MBConv expand / project and head convs) are
     # HBM-bound; measured per shape, the exact-fp32 FFMA kernel beats the tensor-core kernel there
     # (no operand pre-pass, no per-CTA TMEM / barrier set-up): 0.79 vs 1.32 ms at C16->K96 @256x480
-    if R * S * x_shape[3] <= _SIMT_MAX_REDUCTION:
+    # prefer_tc: the caller feeds this conv a pre-split operand from its producer's epilogue (conv stacks), which
+    # removes the pre-pass the measurement above charges to the tensor-core path
+    if R * S * x_shape[3] <= _SIMT_MAX_REDUCTION and not (prefer_tc and x_shape[3] >= 64):
         return "fp32"
     for m in chain:
         if ops.tc_supported(x_shape, K, R, S, stride, pad, m):
@@ -143,8 +145,8 @@ def carry_amax(out, *sources):
 class FusedConv:
     """conv (+bias) (+BN eval) packed for creste_conv2d; built lazily from live parameters."""
 
-    def __init__(self, conv, bn=None):
-        self.conv, self.bn = conv, bn
+    def __init__(self, conv, bn=None, prefer_tc=False):
+        self.conv, self.bn, self.prefer_tc = conv, bn, prefer_tc
         self.cache = PackCache()
 
     def packed(self, mode="fp32"):
@@ -177,7 +179,7 @@ class FusedConv:
             ph, pw = conv.padding if isinstance(conv.padding, tuple) else (conv.padding,) * 2
             pad = (ph, ph, pw, pw)
         stride = conv.stride[0] if isinstance(conv.stride, tuple) else conv.stride
-        return pick_mode(tuple(x_shape), K, R, S, stride, pad, precision or _PRECISION)
+        return pick_mode(tuple(x_shape), K, R, S, stride, pad, precision or _PRECISION, self.prefer_tc)
 
     def out_bound(self, mode):
         """(bound_mul, bound_add) of this conv's output: |out| <= max|x| * bound_mul + bound_add with
@@ -225,7 +227,7 @@ class FusedConv:
         # the exact-fp32 CUDA-core kernel -- a stricter precision, never a looser one
         # (not under torch.jit.trace: the traced `creste::conv2d` op is a pure function of its inputs)
         track = (precision or _PRECISION) in ("3xfp16", "fp16") and not torch.jit.is_tracing()
-        mode = pick_mode(tuple(x_nhwc.shape), K, R, S, stride, pad, mode)
+        mode = pick_mode(tuple(x_nhwc.shape), K, R, S, stride, pad, mode, self.prefer_tc)
         w, scale, shift = self.packed(mode)
         # 3xFP16: max|out| is produced by this conv's epilogue and travels with the tensor (`_amax`), so the next
         # tensor-core conv derives its operand scale from it instead of making an extra amax pass over its input
@@ -245,8 +247,12 @@ def _finish_split(out, so, amax_out):
     if so is not None and so[0] == "both":
         out, sp = out
         out._split = sp
-    if amax_out is not None and not isinstance(out, ops.SplitAct):
-        out._amax = amax_out
+        sp.amax = amax_out
+    if amax_out is not None:
+        if isinstance(out, ops.SplitAct):
+            out.amax = amax_out
+        else:
+            out._amax = amax_out
     return out
 
 
@@ -257,7 +263,7 @@ def _fused_presplit(self, xs, act, pad, residual, out_nchw, precision, split_out
         ph, pw = conv.padding if isinstance(conv.padding, tuple) else (conv.padding,) * 2
         pad = (ph, ph, pw, pw)
     stride = conv.stride[0] if isinstance(conv.stride, tuple) else conv.stride
-    mode = pick_mode(tuple(xs.shape), K, R, S, stride, pad, precision or _PRECISION)
+    mode = pick_mode(tuple(xs.shape), K, R, S, stride, pad, precision or _PRECISION, self.prefer_tc)
     if mode not in ("3xfp16", "fp16"):
         raise RuntimeError(f"pre-split operand handed to a conv that runs in mode {mode}")
     w, scale, shift = self.packed(mode)

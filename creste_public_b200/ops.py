@@ -360,9 +360,10 @@ class SplitAct:
     """An activation tensor held as the 3xFP16 operand of a tensor-core conv: fp16 hi / lo halves [N,H,W,C] and the
     device scale record {s, 1/s}.  Produced by upsample_concat_split, consumed by conv2d_presplit."""
 
-    def __init__(self, hi, lo, scal, shape):
+    def __init__(self, hi, lo, scal, shape, amax=None):
         self.hi, self.lo, self.scal, self.shape = hi, lo, scal, tuple(shape)
         self.device = hi.device
+        self.amax = amax          # device float[1]: the true max|x| of the fp32 values, when the producer measured it
 
 
 def upsample_concat_split(skip_nhwc, x_nhwc, out_hw, scale_factor, amax_skip, amax_x, x_first=False, want_lo=True):
@@ -401,7 +402,8 @@ def conv2d_presplit(xs, w_packed, K, R, S, stride=1, pad=(0, 0, 0, 0), scale=Non
         check(lib().creste_conv2d_presplit_split_out(C.byref(d), ptr(xs.hi), ptr(xs.lo), ptr(xs.scal), ptr(w_packed),
                                                      ptr(scale), ptr(shift), ptr(residual), ptr(out), ptr(amax_out),
                                                      ptr(so.hi), ptr(so.lo), ptr(so.scal), C.c_float(bmul),
-                                                     C.c_float(badd), stream()), "creste_conv2d_presplit_split_out")
+                                                     C.c_float(badd), ptr(xs.amax), stream()),
+              "creste_conv2d_presplit_split_out")
         return so if out is None else (out, so)
     out = torch.empty((N, K, P, Q) if out_nchw else (N, P, Q, K), device=xs.device)
     check(lib().creste_conv2d_presplit(C.byref(d), ptr(xs.hi), ptr(xs.lo), ptr(xs.scal), ptr(w_packed), ptr(scale),

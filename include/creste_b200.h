@@ -202,7 +202,9 @@ int creste_conv2d_presplit(const creste_conv_desc* d, const void* x_hi, const vo
  * 3xFP16 operand: out_hi / out_lo fp16 [N,P,Q,K] (out_lo may be NULL for precision 5), out_scal = DEVICE float[2]
  * {s, 1/s}.  The power-of-two scale comes from an a-priori bound of max|out| the caller supplies as two host floats:
  *   bound_mul = max_k(sum_{c,r,s} |w[k,c,r,s]| * |scale[k]|),  bound_add = max_k |shift[k]|
- * (|out| <= max|x| * bound_mul + bound_add; residual must be NULL).  Replaces the split pre-pass of the consuming conv
+ * (|out| <= max|x| * bound_mul + bound_add; residual must be NULL).  max|x| is read on the device: amax_in / x_amax
+ * (DEVICE float[1], the TRUE maximum carried with the input -- chained a-priori bounds would compound) when given, else
+ * 2^15 / s_in from the input's scale record.  Replaces the split pre-pass of the consuming conv
  * in conv -> BN -> ReLU -> conv chains (reference creste/models/blocks/effnet.py:12-28, inpainting.py:52-68 and the
  * torchvision BasicBlocks of :80-103).  Precision 4 / 5, NHWC output, K % 8 == 0. */
 int creste_conv2d_split_out(const creste_conv_desc* d, const float* x, const float* w_packed, const float* scale,
@@ -212,7 +214,8 @@ int creste_conv2d_split_out(const creste_conv_desc* d, const float* x, const flo
 int creste_conv2d_presplit_split_out(const creste_conv_desc* d, const void* x_hi, const void* x_lo, const float* x_scal,
                                      const float* w_packed, const float* scale, const float* shift,
                                      const float* residual, float* out, float* amax_out, void* out_hi, void* out_lo,
-                                     float* out_scal, float bound_mul, float bound_add, void* stream);
+                                     float* out_scal, float bound_mul, float bound_add, const float* x_amax,
+                                     void* stream);
 
 size_t creste_conv2d_workspace_bytes(const creste_conv_desc* d);
 /* tcgen05 path (precision 1, 2): 1 if the shape is served by the tensor-core kernel (stride 1 or 2, R, S <= 7,

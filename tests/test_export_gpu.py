@@ -43,8 +43,11 @@ def test_traced_model_equals_eager(cuda, mode, tmp_path):
                 assert torch.equal(got[k], eager[k]), k
             else:
                 assert float((got[k] - eager[k]).abs().max()) <= 2e-6 * float(eager[k].abs().max()), k
-        for k in ("depth_preds_bins", "bev_coords"):
-            assert torch.equal(got[k], eager[k]), k
+        assert torch.equal(got["depth_preds_bins"], eager["depth_preds_bins"])
+        if mode == "fp32":
+            assert torch.equal(got["bev_coords"], eager["bev_coords"])
+        else:       # float voxel coordinates: 10 voxels per metre of a depth that differs in its last bits
+            assert float((got["bev_coords"] - eager["bev_coords"]).abs().max()) <= 1e-3
         for k in ("bev_features", "inpainting_sam_preds", "elevation_features", "input_view", "traversability_preds",
                   "traversability_preds_full"):
             assert float((got[k] - eager[k]).abs().max()) <= 1e-4 * max(1.0, float(eager[k].abs().max())), k   # splat atomics

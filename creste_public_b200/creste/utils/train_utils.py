@@ -108,6 +108,170 @@ def get_save_paths(cfg, model_type="ssc", stage="train"):
     return out
 
 
+# ---------------------------------------------------------------------------------------------------------------
+# On-device input pipeline.  The reference builds these warps on the CPU dataloader
+# workers through kornia; here the per-pixel work is one CUDA kernel each (csrc/augment.cu) and only the 2x3 matrix
+# algebra stays on the host, written out in the order kornia evaluates it (kornia is not a dependency of the mirror).
+def _rotation_matrix2d(center, angle_deg, scale):
+    """kornia.geometry.transform.get_rotation_matrix2d: center [1,2], angle [1] degrees, scale [1,2] -> [1,2,3]."""
+    a = torch.deg2rad(angle_deg)
+    c, s_ = torch.cos(a), torch.sin(a)
+    rot = torch.stack([c, s_, -s_, c], dim=-1).view(-1, 2, 2)
+    sr = rot @ torch.diag_embed(scale)
+    alpha, beta = sr[:, 0, 0], sr[:, 0, 1]
+    x, y = center[..., 0], center[..., 1]
+    M = torch.zeros(center.shape[0], 2, 3, dtype=center.dtype)
+    M[..., 0:2, 0:2] = sr
+    M[..., 0, 2] = (1.0 - alpha) * x - beta * y
+    M[..., 1, 2] = beta * x + (1.0 - alpha) * y
+    return M
+
+
+def _homography(M):
+    Hm = F.pad(M, [0, 0, 0, 1], "constant", value=0.0)
+    Hm[..., -1, -1] += 1.0
+    return Hm
+
+
+def get_affine_matrix2d(translations, center, scale, angle):
+    """kornia.geometry.transform.get_affine_matrix2d (no shear): [B,3,3]."""
+    t = _rotation_matrix2d(center, -angle, scale)
+    t[..., 2] += translations
+    return _homography(t)
+
+
+def _pixel_to_norm(h, w, eps=1e-14):
+    tr = torch.tensor([[1.0, 0.0, -1.0], [0.0, 1.0, -1.0], [0.0, 0.0, 1.0]])
+    tr[0, 0] = tr[0, 0] * 2.0 / (eps if w == 1 else w - 1.0)
+    tr[1, 1] = tr[1, 1] * 2.0 / (eps if h == 1 else h - 1.0)
+    return tr.unsqueeze(0)
+
+
+def affine_theta(M, src_hw, dst_hw):
+    """The [B,2,3] theta kornia's warp_affine passes to F.affine_grid for the pixel-space map M [B,2,3] (src -> dst):
+    normalise with the (size - 1) pixel transforms on both sides, invert."""
+    M = M.detach().float().cpu()
+    n_src, n_dst = _pixel_to_norm(*src_hw), _pixel_to_norm(*dst_hw)
+    dst_norm_trans_src_norm = n_dst @ (_homography(M) @ torch.linalg.inv(n_src))
+    return torch.linalg.inv(dst_norm_trans_src_norm)[:, :2, :]
+
+
+def warp(input_tensor, transform, interpolation, precision=None, output_size=None, padding_mode="zeros"):
+    """Reference creste/utils/utils.py:6-38 on the device: kornia warp_affine (align_corners=False) of the tensor plus a
+    ones-channel; returns (output in the input's dtype, mask = warped ones > 0.99)."""
+    if padding_mode != "zeros":
+        raise NotImplementedError("warp: only zeros padding is used by the reference")
+    assert input_tensor.ndim == 4 and transform.ndim == 3
+    from creste_public_b200 import ops
+    H, W = input_tensor.shape[-2:]
+    out_hw = (H, W) if output_size is None else tuple(output_size)
+    theta = affine_theta(transform, (H, W), out_hw)
+    out, mask = ops.affine_warp(input_tensor.float(), theta, out_hw, nearest=(interpolation == "nearest"),
+                                align_corners=False)
+    return out.to(input_tensor.dtype), mask
+
+
+class DepthAugmentation(object):
+    """Reference train_utils.py:110-181 with the per-pixel work on the device (one fused pass: dropout mask, bilinear
+    miscalibration warp, additive noise).  The random draws are made in the reference's order -- rand_like(depth),
+    normal(calib mean, calib std), randn_like(depth) -- on the depth map's device (`draws` lets a caller supply them)."""
+
+    def __init__(self, dropout_prob=0.1, calib_error_mean=[0.0, 0.0, 0.0], calib_error_std=[0.02, 0.02, 0.01],
+                 depth_noise_std=0.2):
+        self.dropout_prob = dropout_prob
+        self.calib_error_mean = calib_error_mean
+        self.calib_error_std = calib_error_std
+        self.depth_noise_std = depth_noise_std
+
+    def miscalibration_theta(self, noise, H, W):
+        tx, ty = noise[0], noise[1]
+        angle = noise[2] * (180.0 / torch.pi)
+        T = get_affine_matrix2d(torch.tensor([[tx, ty]]), torch.tensor([[W / 2, H / 2]]), torch.tensor([[1.0, 1.0]]),
+                                torch.tensor([angle]))
+        return affine_theta(T[:, :2, :], (H, W), (H, W))[0]
+
+    def __call__(self, depth_map, draws=None):
+        assert depth_map.ndim == 3 and depth_map.shape[0] == 1, "Input depth map must have shape (1, H, W)."
+        from creste_public_b200 import ops
+        _, H, W = depth_map.shape
+        if draws is None:
+            u = torch.rand_like(depth_map)
+            noise = torch.normal(mean=torch.tensor(self.calib_error_mean), std=torch.tensor(self.calib_error_std))
+            g = torch.randn_like(depth_map)
+        else:
+            u, noise, g = draws
+        theta = self.miscalibration_theta(noise.float().cpu(), H, W)
+        return ops.depth_augment(depth_map, u, g, theta, self.dropout_prob, self.depth_noise_std)
+
+
+class RotateAndTranslate(object):
+    """Reference train_utils.py:183-318: the BEV map / FOV-mask warps run on the device (`transform_map`); the SE(2)
+    matrices are host scalars.  `renew_transformation` draws like the reference."""
+
+    def __init__(self, augmentations, map_size, voxel_size):
+        self.augmentations = {}
+        for aug in augmentations:
+            kwargs = dict(aug)
+            name = kwargs.pop("name")
+            if name == "rotate":
+                self.augmentations["rotate"] = kwargs.pop("max_rotation", 0.0)
+            elif name == "translate":
+                self.augmentations["translate"] = kwargs.pop("max_translation", 0.0)
+            else:
+                raise ValueError(f"Augmentation {name} not supported")
+        self.map_size = torch.tensor(map_size).float()
+        self.voxel_size = torch.tensor(voxel_size).float()
+        self.center = (self.map_size / self.voxel_size / 2).float().unsqueeze(0)
+        self.scale = torch.tensor([1.0, 1.0]).float().unsqueeze(0)
+        assert len(self.augmentations) > 0
+
+    def transform_map(self, map, R_init=None, interpolation="nearest"):
+        """map [H,W,C] -> (tmap [H,W,C], mask [H,W])."""
+        m = map.permute(2, 0, 1).unsqueeze(0)
+        RT = self.mapRT
+        if R_init is not None:
+            RT = RT @ R_init
+        tmap, mask = warp(m, RT, interpolation=interpolation)
+        return tmap.squeeze(0).permute(1, 2, 0), mask.squeeze(0)
+
+    def transform(self, inputs):
+        assert inputs.shape[0] == 4, "Points must be Nx4 tensor"
+        return self.RT.to(inputs.device) @ inputs
+
+    def renew_transformation(self):
+        RT = torch.eye(4)
+        angle = torch.zeros(())
+        if "translate" in self.augmentations:
+            RT[:2, 3] = (2 * torch.rand(2) - 1) * self.augmentations["translate"]
+        if "rotate" in self.augmentations:
+            angle = (2 * torch.rand(1)[0] - 1) * self.augmentations["rotate"]
+            a = angle * torch.pi / 180
+            RT[:2, :2] = torch.tensor([[torch.cos(a), -torch.sin(a)], [torch.sin(a), torch.cos(a)]])
+        self.RT = RT
+        self.mapRT = _rotation_matrix2d(self.center, angle.reshape(1), self.scale)
+
+    def compute_transformation_fromSE3(self, RT):
+        R, t = RT[:2, :2], RT[:2, 3]
+        offset = (t / self.voxel_size).float().unsqueeze(0)
+        angle = (torch.atan2(R[1, 0], R[0, 0]) * 180 / torch.pi).reshape(1)
+        return get_affine_matrix2d(offset, self.center, self.scale, angle)
+
+
+def load_fov_mask(frustrum_mask, pc_augmentation, pose):
+    """CodaPEFreeDataset._load_fov_mask (codapefree_dataloader.py:691-709; only the current pose contributes there):
+    the trapezoidal frustum mask warped into the frame of `pose` on the device."""
+    mask = frustrum_mask.clone().unsqueeze(-1).long()
+    RT = pc_augmentation.compute_transformation_fromSE3(pose.cpu())
+    mask, _ = pc_augmentation.transform_map(mask, R_init=RT)
+    return mask.squeeze().bool()
+
+
+def load_traverse(lidar_poses, voxel_size, bev_size):
+    """CodaPEFreeDataset._load_traverse (codapefree_dataloader.py:590-615) from the relative LiDAR poses, on the device."""
+    from creste_public_b200 import ops
+    return ops.traverse_to_bev(lidar_poses, voxel_size, bev_size)
+
+
 def extract_max_per_class(tensor, max_per_class=100, return_indices=True):
     """Up to `max_per_class` random members of every class of a 1-D label tensor (reference :324-352).  The random
     subsets are drawn with torch.randperm from the DEFAULT (CPU) generator, class by class in ascending label

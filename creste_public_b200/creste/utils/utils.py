@@ -18,5 +18,12 @@ def remap_labels_in_batch(gt, ignore_idx=0):
 
 
 # names this mirror does not define fall through to the reference's file when the mirror is overlaid on a checkout
+def warp(input_tensor, transform, interpolation, precision=None, output_size=None, padding_mode="zeros"):
+    """Reference creste/utils/utils.py:6-38 (kornia warp_affine + validity mask) on the device; the implementation
+    lives beside its callers in creste/utils/train_utils.py."""
+    from .train_utils import warp as _warp
+    return _warp(input_tensor, transform, interpolation, precision, output_size, padding_mode)
+
+
 from creste_public_b200.creste import _overlay  # noqa: E402
 __getattr__ = _overlay.fallback(__name__, "utils/utils.py")

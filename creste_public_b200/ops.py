@@ -488,6 +488,42 @@ def nhwc_to_nchw(x):
     return out
 
 
+def affine_warp(x, theta, out_hw=None, nearest=False, align_corners=False, want_mask=True):
+    """kornia warp_affine / the reference's `warp` on the device: x [B,C,H,W] fp32, theta [B,2,3] (normalised output
+    -> normalised input coordinates) -> (out [B,C,Ho,Wo], mask [B,Ho,Wo] bool | None)."""
+    B, Cc, H, W = x.shape
+    Ho, Wo = (H, W) if out_hw is None else (int(out_hw[0]), int(out_hw[1]))
+    x = x.float().contiguous()
+    theta = theta.to(device=x.device, dtype=torch.float32).reshape(B, 6).contiguous()
+    out = torch.empty(B, Cc, Ho, Wo, device=x.device)
+    mask = torch.empty(B, Ho, Wo, dtype=torch.uint8, device=x.device) if want_mask else None
+    check(lib().creste_affine_warp(ptr(x), B, Cc, H, W, ptr(theta), Ho, Wo, int(bool(nearest)), int(bool(align_corners)),
+                                   ptr(out), ptr(mask), stream()), "creste_affine_warp")
+    return out, (mask.bool() if want_mask else None)
+
+
+def depth_augment(depth, u, g, theta, dropout_prob, noise_std):
+    """DepthAugmentation.__call__ given its draws, one pass: depth / u / g [1,H,W] or [H,W] fp32, theta [2,3]."""
+    shp = depth.shape
+    H, W = int(shp[-2]), int(shp[-1])
+    depth, u, g = (t.float().contiguous() for t in (depth, u, g))
+    theta = theta.to(device=depth.device, dtype=torch.float32).reshape(6).contiguous()
+    out = torch.empty(shp, device=depth.device)
+    check(lib().creste_depth_augment(ptr(depth), ptr(u), ptr(g), H, W, C.c_float(dropout_prob), ptr(theta),
+                                     C.c_float(noise_std), ptr(out), stream()), "creste_depth_augment")
+    return out
+
+
+def traverse_to_bev(lidar_poses, voxel_size, bev_size):
+    """CodaPEFreeDataset._load_traverse from the relative LiDAR poses [T,4,4] -> clamped BEV grid poses [T,3,3]."""
+    P = lidar_poses.float().contiguous()
+    T = P.shape[0]
+    out = torch.empty(T, 3, 3, device=P.device)
+    check(lib().creste_traverse_to_bev(ptr(P), T, C.c_float(float(voxel_size[0])), C.c_float(float(voxel_size[1])),
+                                       int(bev_size[0]), int(bev_size[1]), ptr(out), stream()), "creste_traverse_to_bev")
+    return out
+
+
 def proj_head(x_nhwc, w_kc, bias, want_nchw=True, want_x_nchw=True):
     """1x1 conv C -> K (K <= 32) + the NCHW copies the output dict wants, one pass over x.
     -> (pred NHWC [N,H,W,K], pred NCHW [N,K,H,W] | None, x NCHW [N,C,H,W] | None)."""

@@ -504,6 +504,25 @@ int creste_supcon_bwd(const float* f, const float* a, const int64_t* lf, const i
                       int self_off, float temperature, const float* class_weights, const float* stats4,
                       const float* scale_dev, float* df, float* da, void* stream);
 
+/* ---- on-device input pipeline: the per-frame warps of the reference's CPU dataloader.
+ * theta = DEVICE float[B][6]: the 2x3 map from normalised OUTPUT to normalised INPUT coordinates that kornia's
+ * warp_affine hands to F.affine_grid (the host derives it from the pixel-space matrix: mirror
+ * creste/utils/train_utils.py `affine_theta`).
+ * creste_affine_warp: reference creste/utils/utils.py:6-38 `warp` (kornia warp_affine + the ones-channel validity
+ *   mask thresholded at 0.99), used by RotateAndTranslate.transform_map (creste/utils/train_utils.py:213-232) and the
+ *   FOV-mask pose warp (creste/datasets/codapefree_dataloader.py:691-709).  in [B][C][H][W] fp32 -> out
+ *   [B][C][Ho][Wo], mask [B][Ho][Wo] uint8 (may be NULL); nearest: 0 = bilinear, 1 = nearest; zeros padding.
+ * creste_depth_augment: DepthAugmentation.__call__ (creste/utils/train_utils.py:110-181) in one pass given its draws:
+ *   out = warp_bilinear(depth * (u > p_drop), theta, align_corners = true) + g * noise_std, all [H][W] fp32.
+ * creste_traverse_to_bev: CodaPEFreeDataset._load_traverse (creste/datasets/codapefree_dataloader.py:590-615):
+ *   poses [T][4][4] (LiDAR frame, relative to the first) -> clamped BEV grid poses [T][3][3]. */
+int creste_affine_warp(const float* in, int B, int C, int H, int W, const float* theta, int Ho, int Wo, int nearest,
+                       int align_corners, float* out, unsigned char* mask, void* stream);
+int creste_depth_augment(const float* depth, const float* u, const float* g, int H, int W, float p_drop,
+                         const float* theta, float noise_std, float* out, void* stream);
+int creste_traverse_to_bev(const float* poses, int T, float voxel_x, float voxel_y, int bev_h, int bev_w, float* out,
+                           void* stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -360,7 +360,7 @@ def run_irl_steps(args, dev, rank, world, barrier, Bi=8, Hm=256, Wm=256, steps=5
     import creste_public_b200 as cb
     from creste_public_b200 import _lib, configs
     from creste_public_b200.config import as_cfg
-    from creste_public_b200.creste.train_traversability import HeadStep
+    from creste_public_b200.creste.train_traversability import GraphedHeadStep
     from creste_public_b200.creste.utils.loss_utils import LossManager
     import synth_data as synth   # seeded synthetic inputs (pure generators, not the oracle)
     if args.no_irl:
@@ -369,11 +369,13 @@ def run_irl_steps(args, dev, rank, world, barrier, Bi=8, Hm=256, Wm=256, steps=5
     model = cb.build_maxentirl(cfg).to(dev)
     model.backbone.eval()
     model.traversability_head.train()
-    step = HeadStep(model, LossManager(as_cfg(cfg)))
     feat, expert, fov, cfs = synth.head_inputs(Bi, Hm, Wm, seed=rank)
     keys = ("inpainting_sam_preds", "inpainting_sam_dynamic_preds", "elevation_preds")
     feat = {k: t.to(dev) for k, t in zip(keys, feat)}
     expert, fov = expert.to(dev), fov.to(dev)
+    # forward + loss + double backward replayed from a CUDA graph; label prepass, all-reduce and Adam eager
+    # (bit-identical to the eager HeadStep: tests/test_train_gpu.py::test_graphed_head_step_equals_eager)
+    step = GraphedHeadStep(model, LossManager(as_cfg(cfg)), (feat, expert, fov, cfs))
     for _ in range(3):
         loss, out, _ = step(feat, expert, fov, cfs)
     barrier()
@@ -385,7 +387,7 @@ def run_irl_steps(args, dev, rank, world, barrier, Bi=8, Hm=256, Wm=256, steps=5
     e1.record()
     barrier()
     ms = e0.elapsed_time(e1) / steps
-    launches = (_lib.lib().creste_launch_count() - n0) / steps
+    launches = (_lib.lib().creste_launch_count() - n0) / steps + step.launches_per_replay
     if world > 1:
         t = torch.tensor([ms], device=dev)
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
@@ -393,7 +395,7 @@ def run_irl_steps(args, dev, rank, world, barrier, Bi=8, Hm=256, Wm=256, steps=5
     return {"metric": "IRL steps/sec @ 256x256", "value": 1e3 / ms, "unit": "steps/s",
             "samples_per_s": Bi * world * 1e3 / ms, "ms_per_step": ms,
             "workload": f"configs[3] shard: counterfactual IRL head-only training step, B={Bi}/GPU "
-                        f"(global {Bi * world}), {Hm}x{Wm} grid (reward FCN fwd/bwd + VI + SVF + loss + all-reduce + Adam)",
+                        f"(global {Bi * world}), {Hm}x{Wm} grid (reward FCN fwd/bwd + VI + SVF + loss + all-reduce + Adam; forward + loss + backward replayed from a CUDA graph)",
             "vi_sweeps": int(model.traversability_head.last_vi_info[0]),
             "loss": float(loss), "gpu_launches_per_step": launches,
             "precision": args.precision}
@@ -413,18 +415,24 @@ def run_stage1_steps(args, dev, rank, world, barrier, Bi=16, H=512, W=960, steps
     torch.manual_seed(1234)          # identical initial replicas on every rank (DDP); the data is per-rank
     m = DistillationModel(configs.distill_cfg((H, W))).to(dev).train()
     batch = {k: v.to(dev) for k, v in synth.distill_batch(Bi, H, W, seed=rank).items()}
+    n_eager = _lib.lib().creste_launch_count()
     for _ in range(2):
         out = m.training_step(batch)
+    launches = (_lib.lib().creste_launch_count() - n_eager) / 2        # kernels per step (the graph replays the same)
+    # forward + losses + backward replayed from a CUDA graph; buffer broadcast, all-reduce and Adam eager
+    # (bit-identical to the eager step: tests/test_train_gpu.py::test_graphed_stage1_step_equals_eager)
+    from creste_public_b200 import engine
+    gstep = engine.GraphedTrainStep(m, batch)
+    for _ in range(2):
+        out = gstep(batch)
     barrier()
-    n0 = _lib.lib().creste_launch_count()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     e0.record()
     for _ in range(steps):
-        out = m.training_step(batch)
+        out = gstep(batch)
     e1.record()
     barrier()
     ms = e0.elapsed_time(e1) / steps
-    launches = (_lib.lib().creste_launch_count() - n0) / steps
     if world > 1:
         t = torch.tensor([ms], device=dev)
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
@@ -433,7 +441,7 @@ def run_stage1_steps(args, dev, rank, world, barrier, Bi=16, H=512, W=960, steps
     res = {"metric": "stage-1 training frames/sec @ 512x960", "value": Bi * world * 1e3 / ms, "unit": "frames/s",
            "ms_per_step": ms, "frames_per_step_per_gpu": Bi,
            "workload": f"configs[2] shard: distillation.yaml backbone training step, B={Bi}/GPU (global {Bi * world}), "
-                       f"{H}x{W} (fwd + 3 losses + bwd + all-reduce + Adam)",
+                       f"{H}x{W} (fwd + 3 losses + bwd + all-reduce + Adam; fwd + losses + bwd replayed from a CUDA graph)",
            "loss": float(out["loss"]), "gpu_launches_per_step": launches, "precision": args.precision,
            "achieved_tflops": flop / (ms * 1e-3) / 1e12,
            "peak_mem_gib": torch.cuda.max_memory_allocated() / 2 ** 30}

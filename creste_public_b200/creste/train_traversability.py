@@ -243,3 +243,90 @@ class HeadStep:
         loss.backward()
         self.opt.step()
         return loss.detach(), outputs, meta
+
+
+class GraphedHeadStep(HeadStep):
+    """HeadStep whose forward + loss + backward is replayed from a CUDA graph (static shapes).
+
+    The eager step issues ~800 small launches (ours + ATen's) from Python for ~8 ms of GPU work at B = 8, 256 x 256:
+    the host, not the GPU, bounds it.  The label-only half of the loss (MaxEntIRLLoss.prepare_labels: expert and
+    counterfactual visitation rasters -- per-sample Python lists and one `.item()` each) runs eagerly BEFORE the
+    replay; everything that depends on the model (reward FCN, value iteration, state-visitation frequencies, the loss
+    with its double-backward gradient penalty, backward) is captured once; the gradient exchange and the fused Adam
+    launch stay eager after it (no collective and no step-dependent scalar inside the graph).  Same arithmetic, same
+    kernels, same order as HeadStep: the two agree bit for bit (tests/test_train_gpu.py)."""
+
+    def __init__(self, model, loss_manager, example, lr=5e-4, betas=(0.9, 0.999), warmup=2):
+        super().__init__(model, loss_manager, lr=lr, betas=betas)
+        from creste_public_b200.creste.utils.loss_utils import MaxEntIRLLoss
+        assert len(loss_manager.losses) == 1 and isinstance(loss_manager.losses[0], MaxEntIRLLoss), \
+            "GraphedHeadStep captures the MaxEntIRLLoss-only configuration of train_traversability.py"
+        self.irl = loss_manager.losses[0]
+        feat_map, expert, fov_mask, cfs = example
+        self.s_feat = {k: v.clone() for k, v in feat_map.items()}
+        self.s_expert = expert.clone()
+        head = model.traversability_head
+        self.s_labels = {k: (v.clone() if torch.is_tensor(v) else v)
+                         for k, v in self._labels(expert, fov_mask, cfs).items()}
+        bufs = list(head.buffers())
+        saved = [b.clone() for b in bufs]
+        side = torch.cuda.Stream()
+        side.wait_stream(torch.cuda.current_stream())
+        from creste_public_b200 import _lib
+        with torch.cuda.stream(side):
+            for _ in range(warmup):
+                n0 = _lib.lib().creste_launch_count()
+                self._fwd_bwd()
+                self.launches_per_replay = int(_lib.lib().creste_launch_count() - n0)   # our kernels inside the graph
+        torch.cuda.current_stream().wait_stream(side)
+        torch.cuda.synchronize()
+        self.graph = torch.cuda.CUDAGraph()
+        with torch.cuda.graph(self.graph):
+            self.s_loss, self.s_out, self.s_meta = self._fwd_bwd()
+        with torch.no_grad():
+            for b, s_ in zip(bufs, saved):
+                b.copy_(s_)
+        self.opt.zero_grad()
+
+    def _labels(self, expert, fov_mask, cfs):
+        m = self.model
+        td = {"inputs/traversability_label": expert, "inputs/fov_mask": fov_mask, "inputs/counterfactuals_label": cfs}
+        return self.irl.prepare_labels(td, (expert.shape[0], m.map_size[0], m.map_size[1]), device=expert.device)
+
+    def _fwd_bwd(self):
+        m = self.model
+        self.opt.zero_grad()
+        keys = m.traversability_head.reward_cfg.input_keys
+        Wo = self.s_feat[keys[0]].shape[-1]
+        map_ds = Wo // m.map_size[1]
+        S = self.s_expert[:, :, :2, 2].long() // map_ds
+        S[:, :, 0] = S[:, :, 0].clamp(0, m.map_size[0] - 1)
+        S[:, :, 1] = S[:, :, 1].clamp(0, m.map_size[1] - 1)
+        outputs = m.traversability_head(self.s_feat, S, solve_mdp=True)
+        with torch.no_grad():
+            outputs.update(m.expected_state_visitation_frequency(outputs["policy"], self.s_expert))
+        td = {f"outputs/{k}": v for k, v in outputs.items()}
+        assert self.irl.config.get("logvar_key", None) is None
+        ld, md = self.irl.loss_from_labels(td, self.s_labels)
+        name = self.irl.name
+        # Loss.forward / LossManager.forward: (weight, value) pairs under "<loss name>/<key>"
+        loss_dict = {f"{name}/{k}": (self.irl.weight * 1.0, v) for k, v in ld.items()}
+        meta = {f"{name}/{k}": v for k, v in md.items()}
+        loss = sum(w * v for w, v in loss_dict.values())
+        loss.backward()
+        return loss.detach(), outputs, meta
+
+    def __call__(self, feat_map, expert, fov_mask, counterfactuals):
+        labels = self._labels(expert, fov_mask, counterfactuals)         # eager: host lists, H2D copies, .item()
+        with torch.no_grad():
+            for k, v in feat_map.items():
+                self.s_feat[k].copy_(v, non_blocking=True)
+            self.s_expert.copy_(expert, non_blocking=True)
+            for k, v in labels.items():
+                if torch.is_tensor(v):
+                    self.s_labels[k].copy_(v, non_blocking=True)
+        broadcast_buffers(self.model.traversability_head, self.opt.group)
+        self.graph.replay()
+        self.opt.step()
+        engine.mark_written(list(self.model.traversability_head.buffers()))
+        return self.s_loss, self.s_out, self.s_meta

@@ -329,26 +329,25 @@ class MaxEntIRLLoss(Loss):
         max_steps = int(torch.ceil(torch.norm(seg, dim=-1)).long().max().item())
         return None, ops.expert_visitation(xy, map_ds, max_steps, H, W)
 
-    def loss(self, tensor_dict):
-        exp_svf = tensor_dict[self.pred_key]
+    def prepare_labels(self, tensor_dict, shape, device=None):
+        """The label-only half of `loss` (reference loss_utils.py:1118-1180): FOV mask crop, expert visitation
+        distribution, counterfactual visitation distributions.  Depends on the batch, not on the model, and contains
+        every host-side step of the loss (the per-sample trajectory lists, the `.item()` of the interpolation length),
+        so a caller may run it ahead of -- and outside -- a captured forward / backward graph.
+        -> dict(mask uint8 [B,H,W] | None, svf [B,H,W], cf [B,H,W], has_cf float [B,1,1])"""
         gt = tensor_dict[self.lab_key]
         fov_mask = tensor_dict[self.fov_key]
-        reward_preds = tensor_dict["outputs/traversability_preds"]
-        state_features = tensor_dict["outputs/input_view"]
-        reward_preds = reward_preds.squeeze(1)                         # [B,H,W]
-        dev = reward_preds.device
+        B, H, W = shape
+        dev = device if device is not None else tensor_dict["outputs/traversability_preds"].device
         _, Ho, Wo = fov_mask.shape
-        B, H, W = exp_svf.shape
         fov_mask = tu.resize_and_crop(fov_mask.to(dev).unsqueeze(1).byte(), (Ho // 2, Wo // 2),
                                       (0, H, 0, W)).squeeze(1).contiguous()        # uint8 [B,H,W]
         mask = fov_mask if self.use_fov_mask else None
-
         with torch.no_grad():
             _, svf = self.compute_expert_visitation(gt.to(dev), self.map_ds, self.map_sz)
             svf = ops.row_normalize(svf, mask, 1e-5)
-            exp_svf = ops.row_normalize(exp_svf.detach().float(), mask, 1e-5)
             cf_svf_total = torch.zeros_like(svf)
-            exp_svf_total = exp_svf.clone()
+            has_cf = torch.zeros(B, 1, 1, device=dev)
             if self.cf_key is not None and self.alpha is not None:
                 for idx, cf_dict in enumerate(tensor_dict[self.cf_key]):
                     if cf_dict is None:
@@ -360,9 +359,24 @@ class MaxEntIRLLoss(Loss):
                     _, cf = self.compute_expert_visitation(invalid, self.map_ds, self.map_sz)
                     # sum over the trajectories, then normalise to a distribution over cells
                     cf = _sum_rows(cf)
-                    cf = ops.row_normalize(cf.view(1, H, W), None, 1e-5)[0]
-                    exp_svf[idx] = self.alpha * cf + (1 - self.alpha) * exp_svf[idx]
-                    cf_svf_total[idx] = cf
+                    cf_svf_total[idx] = ops.row_normalize(cf.view(1, H, W), None, 1e-5)[0]
+                    has_cf[idx] = 1.0
+        return {"mask": mask, "svf": svf, "cf": cf_svf_total, "has_cf": has_cf}
+
+    def loss_from_labels(self, tensor_dict, labels):
+        """The model-dependent half of `loss`: device work only, static shapes (capturable in a CUDA graph)."""
+        exp_svf = tensor_dict[self.pred_key]
+        reward_preds = tensor_dict["outputs/traversability_preds"]
+        state_features = tensor_dict["outputs/input_view"]
+        reward_preds = reward_preds.squeeze(1)                         # [B,H,W]
+        dev = reward_preds.device
+        mask, svf, cf_svf_total, has_cf = labels["mask"], labels["svf"], labels["cf"], labels["has_cf"]
+        with torch.no_grad():
+            exp_svf = ops.row_normalize(exp_svf.detach().float(), mask, 1e-5)
+            exp_svf_total = exp_svf.clone()
+            if self.cf_key is not None and self.alpha is not None:
+                # exp_svf[idx] = alpha * cf + (1 - alpha) * exp_svf[idx] for the samples that have counterfactuals
+                exp_svf = torch.where(has_cf > 0, self.alpha * cf_svf_total + (1 - self.alpha) * exp_svf, exp_svf)
 
         # differentiable part: sums of rewards under the two visitation distributions; the
         # reference masks the reward (reward_preds * ones_mask) -- here the mask rides in RowDot
@@ -372,7 +386,7 @@ class MaxEntIRLLoss(Loss):
         mean_svf_rewards = svf_rewards.mean()
         visitation_loss = mean_exp_svf_rewards - mean_svf_rewards
 
-        reward_penalty = torch.tensor(0.0, device=dev)
+        reward_penalty = torch.zeros((), device=dev)
         if reward_preds.requires_grad and self.reward_weight > 0:
             # sum of the (FOV-masked) reward map, as reward_preds.sum() in the reference
             rp_sum = ag.RowDotFn.apply(reward_preds, torch.ones_like(reward_preds), mask).sum()
@@ -387,9 +401,9 @@ class MaxEntIRLLoss(Loss):
             r = reward_preds.detach()
             cf_rewards = ops.row_dot(r, cf_svf_total, mask)
             opt_rewards = ops.row_dot(r, exp_svf_total, mask)
-            valid = cf_rewards != 0
-            cf_rewards = cf_rewards[valid].sum()
-            opt_rewards = opt_rewards[valid].sum()
+            valid = (cf_rewards != 0).to(cf_rewards.dtype)
+            cf_rewards = (cf_rewards * valid).sum()         # sum over the samples with a counterfactual reward
+            opt_rewards = (opt_rewards * valid).sum()
         meta = {
             "reward_penalty": self.reward_weight * reward_penalty,
             "mean_expected_svf_rewards": mean_exp_svf_rewards,
@@ -398,6 +412,10 @@ class MaxEntIRLLoss(Loss):
             "sum_opt_rewards": opt_rewards,
         }
         return {"maxentirl_loss": loss}, meta
+
+    def loss(self, tensor_dict):
+        B, H, W = tensor_dict[self.pred_key].shape
+        return self.loss_from_labels(tensor_dict, self.prepare_labels(tensor_dict, (B, H, W)))
 
 
 def _sum_rows(x):

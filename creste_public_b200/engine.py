@@ -322,3 +322,71 @@ class GraphedForward:
             dst.copy_(src, non_blocking=True)
         self.graph.replay()
         return self.static_out
+
+
+class GraphedTrainStep:
+    """CUDA-graph replay of the forward + losses + backward of a training step with static input shapes.
+
+    A stage-1 step is ~2 500 kernel launches (ours + ATen's) issued from Python through ctypes; at B = 16 that host
+    work (~100 ms) exceeds the GPU time of the step (~75 ms).  Capturing zero_grad + forward + losses + backward once
+    and replaying it removes it.  What stays eager, by design: the DDP-style buffer broadcast before the step, the
+    gradient exchange (ONE flat NCCL all-reduce) and the fused Adam launch after it -- three calls, so the captured
+    graph contains no collective and no step-dependent scalar (Adam's bias correction).
+
+        step = GraphedTrainStep(lightning_like_module, example_batch)     # module: _losses(batch), optimizers()
+        out = step(batch)                                                 # {"loss": tensor}
+
+    The module's `_losses(batch)` must be free of host synchronisation and data-dependent shapes (stage 1 is; the
+    stage-2 contrastive loss samples a data-dependent number of cells and is not).  Warm-up iterations run the same
+    forward + backward eagerly on a side stream WITHOUT an optimizer step; BatchNorm running statistics and the RNG
+    state are restored afterwards so that the first replayed step starts from the state the caller had."""
+
+    def __init__(self, module, example_batch, warmup=2):
+        self.m = module
+        self.opt = module.optimizers()
+        self.static = {k: (v.clone() if torch.is_tensor(v) else v) for k, v in example_batch.items()}
+        bufs = [b for b in module.buffers()]
+        saved = [b.clone() for b in bufs]
+        rng = torch.cuda.get_rng_state()
+        side = torch.cuda.Stream()
+        side.wait_stream(torch.cuda.current_stream())
+        from . import _lib
+        with torch.cuda.stream(side):
+            for _ in range(warmup):
+                n0 = _lib.lib().creste_launch_count()
+                self._fwd_bwd()
+                self.launches_per_replay = int(_lib.lib().creste_launch_count() - n0)   # our kernels inside the graph
+        torch.cuda.current_stream().wait_stream(side)
+        torch.cuda.synchronize()
+        self.graph = torch.cuda.CUDAGraph()
+        with torch.cuda.graph(self.graph):
+            self.loss = self._fwd_bwd()
+        with torch.no_grad():
+            for b, s_ in zip(bufs, saved):
+                b.copy_(s_)
+        torch.cuda.set_rng_state(rng)
+        self.opt.zero_grad()
+
+    def _fwd_bwd(self):
+        self.opt.zero_grad()
+        _, loss_dict, meta, loss = self.m._losses(self.static)
+        loss.backward()
+        self._logged = ({k: w * v.detach() for k, (w, v) in loss_dict.items()}, {k: v.detach() for k, v in meta.items()})
+        return loss.detach()
+
+    def __call__(self, batch):
+        from .creste.train_traversability import broadcast_buffers
+        with torch.no_grad():
+            for k, v in batch.items():
+                if torch.is_tensor(v):
+                    self.static[k].copy_(v, non_blocking=True)
+        broadcast_buffers(self.m.model, self.opt.group)
+        self.graph.replay()
+        self.opt.step()
+        # BatchNorm running statistics were written through raw pointers by the replayed kernels
+        mark_written([b for b in self.m.buffers()])
+        ld, meta = self._logged
+        self.m.logged.update({f"train/{k}": v for k, v in ld.items()})
+        self.m.logged.update({f"train/{k}": v for k, v in meta.items()})
+        self.m.logged["train/loss"] = self.loss
+        return {"loss": self.loss}

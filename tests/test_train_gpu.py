@@ -318,3 +318,76 @@ def test_stage1_validation_losses_match_reference_golden(cuda, golden):
     assert set(got) == set(g.files), (set(got), set(g.files))
     for k in g.files:
         np.testing.assert_allclose(got[k], float(g[k]), rtol=5e-6, atol=1e-7, err_msg=k)
+
+
+def test_graphed_head_step_equals_eager(cuda):
+    """GraphedHeadStep (label prepass eager, forward + loss + double backward replayed from a CUDA graph, all-reduce +
+    Adam eager) against HeadStep on the same replica and batches: losses, parameters, BatchNorm buffers, the reward map
+    and the sweep count agree bit for bit over three steps with different inputs."""
+    import copy
+    import creste_public_b200 as cb
+    from creste_public_b200.creste.train_traversability import GraphedHeadStep, HeadStep
+    from creste_public_b200.creste.utils.loss_utils import LossManager
+    from creste_public_b200.config import as_cfg
+    from creste_public_b200 import configs
+    from oracle import net_oracle
+    Hm, Wm, B = 32, 64, 2
+    cfg = configs.irl_cfg(image_size=(64, 96), map_size=(Hm, Wm), solve_mdp=True, action_horizon=20)
+    torch.manual_seed(11)
+    ma = cb.build_maxentirl(cfg).to(cuda)
+    ma.backbone.eval()
+    ma.traversability_head.train()
+    mb = copy.deepcopy(ma)
+
+    def inputs(seed):
+        g = np.random.default_rng(seed)
+        feat = {k: torch.from_numpy(g.standard_normal((B, c, 4 * Hm, 2 * Wm)).astype(np.float32)).to(cuda)
+                for k, c in (("inpainting_sam_preds", 32), ("inpainting_sam_dynamic_preds", 6), ("elevation_preds", 2))}
+        expert = torch.from_numpy(synth.expert_poses(B, 20, 4 * Hm, 2 * Wm, 1 + seed)).to(cuda)
+        cfs = synth.counterfactuals(expert.cpu().numpy(), every=2, shift=8.0)
+        fov = torch.from_numpy(np.ascontiguousarray(net_oracle.trapezoid_fov_mask(4 * Hm, 2 * Wm, 70, 70, 3, 100)))
+        return feat, expert, fov.unsqueeze(0).repeat(B, 1, 1).to(cuda), cfs
+    data = [inputs(s) for s in range(3)]
+    ea = HeadStep(ma, LossManager(as_cfg(cfg)))
+    eb = GraphedHeadStep(mb, LossManager(as_cfg(cfg)), data[0])
+    for d in data:
+        la, oa, meta_a = ea(*d)
+        lb, ob, meta_b = eb(*d)
+        assert torch.equal(la, lb)
+        assert torch.equal(oa["traversability_preds"], ob["traversability_preds"])
+        assert torch.equal(ma.traversability_head.last_vi_info, mb.traversability_head.last_vi_info)
+        assert torch.equal(ea.opt.flat_p, eb.opt.flat_p)
+        for x, y in zip(ma.traversability_head.buffers(), mb.traversability_head.buffers()):
+            assert torch.equal(x, y)
+        assert set(meta_a) == set(meta_b)
+
+
+def test_graphed_stage1_step_equals_eager(cuda):
+    """engine.GraphedTrainStep against DistillationModel.training_step (drop-connect off: its RNG stream is consumed
+    differently under graph replay): identical losses, parameters and BatchNorm statistics step for step."""
+    import copy
+    import creste_public_b200 as cb
+    import synth_data
+    from creste_public_b200 import configs, engine
+    from creste_public_b200.creste.models.blocks import effnet
+    from creste_public_b200.creste.train_pefree import DistillationModel
+    cb.set_precision("3xfp16")
+    old = effnet.EfficientNetB0.DROP_CONNECT
+    effnet.EfficientNetB0.DROP_CONNECT = 0.0
+    try:
+        torch.manual_seed(7)
+        H, W = 128, 192
+        a = DistillationModel(configs.distill_cfg((H, W))).to(cuda).train()
+        b = copy.deepcopy(a)
+        batches = [{k: v.to(cuda) for k, v in synth_data.distill_batch(2, H, W, seed=s).items()} for s in range(3)]
+        step = engine.GraphedTrainStep(b, batches[0])
+        for bt in batches:
+            la = a.training_step(bt)["loss"]
+            lb = step(bt)["loss"]
+            assert torch.equal(la, lb)
+            assert torch.equal(a.optimizers().flat_p, b.optimizers().flat_p)
+            for x, y in zip(a.model.buffers(), b.model.buffers()):
+                assert torch.equal(x, y)
+    finally:
+        effnet.EfficientNetB0.DROP_CONNECT = old
+        cb.set_precision("fp32")

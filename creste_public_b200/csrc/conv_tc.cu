@@ -319,7 +319,7 @@ __device__ __forceinline__ float tc_act(float v, int act) {
 // TMEM.  Operand bytes read from shared memory per MMA-cycle halve -- the single-CTA form is bound
 // by shared-memory bandwidth ((128 + 256) rows x 32 B per 128-cycle MMA + the TMA fill).
 template <bool PAIR, bool F16>
-__global__ void __launch_bounds__(TC_THREADS, 1)
+__global__ void __launch_bounds__(TC_THREADS, 2)
 conv_tc_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_constant__ CUtensorMap map_a_lo,
                const __grid_constant__ CUtensorMap map_b_hi, const __grid_constant__ CUtensorMap map_b_lo,
                TcParams p, int nstages) {
@@ -964,7 +964,14 @@ static int conv_tc_main(const creste_conv_desc* d, float* x_hi, float* x_lo, flo
 
   const int nops = split ? 2 : 1;
   const size_t stage_bytes = (size_t)nops * (A_TILE_BYTES + (block_n / (cl >= 2 ? 2 : 1)) * 128);
-  int nstages = (int)((200 * 1024) / stage_bytes);
+  // N tiles of <= 128 channels need <= 256 TMEM columns (main + cross accumulators): TWO CTAs fit on an SM if each
+  // keeps its operand ring under ~100 KB, and then one CTA's prologue / epilogue (TMEM -> registers -> transpose ->
+  // global, now including the fp16 split) runs under the other's MMAs.  One tile per CTA with the whole SM to itself
+  // left the tensor pipe idle for ~38 % of the tile time on these layers (profiles/r1b_conv_tc_bottleneck.md).
+  // CRESTE_TC_SMEM_KB overrides the per-CTA ring budget (200 = one CTA per SM, the round-1 behaviour).
+  int ring_kb = block_n <= 128 ? 100 : 200;
+  if (const char* e = getenv("CRESTE_TC_SMEM_KB")) { const int v = atoi(e); if (v >= 64 && v <= 200) ring_kb = v; }
+  int nstages = (int)(((size_t)ring_kb * 1024) / stage_bytes);
   if (nstages > 8) nstages = 8;
   if (nstages < 2) { set_error("creste_conv2d(tc): stage too large"); return CRESTE_ERR_ARG; }
   const size_t smem = (size_t)nstages * stage_bytes + 1024;

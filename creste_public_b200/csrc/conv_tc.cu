@@ -571,18 +571,11 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_consta
               if (p.out) *reinterpret_cast<float4*>(dst) = o4;
               if (F16 && p.out_hi) {
                 // same arithmetic per element as f16_split_kernel
-                const float xs[4] = {o4.x * s_out, o4.y * s_out, o4.z * s_out, o4.w * s_out};
-                unsigned short h[4], l[4];
-#pragma unroll
-                for (int q = 0; q < 4; ++q) {
-                  const __half hh = __float2half_rn(xs[q]);
-                  h[q] = __half_as_ushort(hh);
-                  l[q] = __half_as_ushort(__float2half_rn((xs[q] - __half2float(hh)) * 2048.0f));
-                }
+                uint2 h2, l2;
+                split4_f16(o4.x * s_out, o4.y * s_out, o4.z * s_out, o4.w * s_out, h2, l2);
                 const size_t o8 = ((size_t)rpix * p.K + n) >> 2;
-                p.out_hi[o8] = make_uint2((unsigned)h[0] | ((unsigned)h[1] << 16), (unsigned)h[2] | ((unsigned)h[3] << 16));
-                if (p.out_lo)
-                  p.out_lo[o8] = make_uint2((unsigned)l[0] | ((unsigned)l[1] << 16), (unsigned)l[2] | ((unsigned)l[3] << 16));
+                p.out_hi[o8] = h2;
+                if (p.out_lo) p.out_lo[o8] = l2;
               }
             } else {
 #pragma unroll
@@ -722,17 +715,10 @@ __global__ void __launch_bounds__(256) f16_split_kernel(const float4* __restrict
       const float4 g = __ldg(reinterpret_cast<const float4*>(gate + (size_t)img * C + c));
       v.x *= g.x; v.y *= g.y; v.z *= g.z; v.w *= g.w;
     }
-    const float xs[4] = {v.x * s, v.y * s, v.z * s, v.w * s};
-    unsigned short h[4], l[4];
-#pragma unroll
-    for (int j = 0; j < 4; ++j) {
-      const __half hh = __float2half_rn(xs[j]);
-      const float res = (xs[j] - __half2float(hh)) * 2048.0f;
-      h[j] = __half_as_ushort(hh);
-      l[j] = __half_as_ushort(__float2half_rn(res));
-    }
-    hi[i] = make_uint2((unsigned)h[0] | ((unsigned)h[1] << 16), (unsigned)h[2] | ((unsigned)h[3] << 16));
-    if (lo) lo[i] = make_uint2((unsigned)l[0] | ((unsigned)l[1] << 16), (unsigned)l[2] | ((unsigned)l[3] << 16));
+    uint2 h2, l2;
+    split4_f16(v.x * s, v.y * s, v.z * s, v.w * s, h2, l2);
+    hi[i] = h2;
+    if (lo) lo[i] = l2;
   }
 }
 

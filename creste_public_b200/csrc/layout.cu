@@ -230,16 +230,10 @@ __global__ void __launch_bounds__(256) upsample_concat_kernel(const float* __res
       if (!SPLIT) {
         reinterpret_cast<float4*>(out + pix * Ct)[c4] = v;
       } else {
-        const float xs[4] = {v.x * sc, v.y * sc, v.z * sc, v.w * sc};
-        unsigned short h[4], l[4];
-#pragma unroll
-        for (int j = 0; j < 4; ++j) {
-          const __half hh = __float2half_rn(xs[j]);
-          h[j] = __half_as_ushort(hh);
-          l[j] = __half_as_ushort(__float2half_rn((xs[j] - __half2float(hh)) * 2048.0f));
-        }
-        hi[pix * c4t + c4] = make_uint2((unsigned)h[0] | ((unsigned)h[1] << 16), (unsigned)h[2] | ((unsigned)h[3] << 16));
-        if (lo) lo[pix * c4t + c4] = make_uint2((unsigned)l[0] | ((unsigned)l[1] << 16), (unsigned)l[2] | ((unsigned)l[3] << 16));
+        uint2 h2, l2;
+        split4_f16(v.x * sc, v.y * sc, v.z * sc, v.w * sc, h2, l2);
+        hi[pix * c4t + c4] = h2;
+        if (lo) lo[pix * c4t + c4] = l2;
       }
     }
   }
@@ -283,16 +277,10 @@ __global__ void __launch_bounds__(256, 2) upsample_block_kernel(const float* __r
     if (!SPLIT) {
       reinterpret_cast<float4*>(out + pix * Ct)[c4] = v;
     } else {
-      const float xs[4] = {v.x * sc, v.y * sc, v.z * sc, v.w * sc};
-      unsigned short h[4], l[4];
-#pragma unroll
-      for (int j = 0; j < 4; ++j) {
-        const __half hh = __float2half_rn(xs[j]);
-        h[j] = __half_as_ushort(hh);
-        l[j] = __half_as_ushort(__float2half_rn((xs[j] - __half2float(hh)) * 2048.0f));
-      }
-      hi[pix * c4t + c4] = make_uint2((unsigned)h[0] | ((unsigned)h[1] << 16), (unsigned)h[2] | ((unsigned)h[3] << 16));
-      if (lo) lo[pix * c4t + c4] = make_uint2((unsigned)l[0] | ((unsigned)l[1] << 16), (unsigned)l[2] | ((unsigned)l[3] << 16));
+      uint2 h2, l2;
+      split4_f16(v.x * sc, v.y * sc, v.z * sc, v.w * sc, h2, l2);
+      hi[pix * c4t + c4] = h2;
+      if (lo) lo[pix * c4t + c4] = l2;
     }
   };
   for (long long item = warp0; item < nin; item += nwarps) {

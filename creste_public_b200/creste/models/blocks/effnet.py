@@ -203,14 +203,22 @@ class Up(nn.Module):
         x = ag.bn_act(ag.conv2d(x, self.conv[0]), self.conv[1], "relu")
         return ag.bn_act(ag.conv2d(x, self.conv[3]), self.conv[4], "relu")
 
-    def forward_nhwc(self, x1, x2, split_out=None):
-        """split_out ("only" | "both" | None): how the consumer wants the block's output (engine.FusedConv.__call__)."""
-        if self.training:
-            return self.forward_train(x1, x2)
+    def upcat_nhwc(self, x1, x2):
+        """cat([x2, bilinear(x1)]) as the first conv's input (its 3xFP16 operand when that conv runs on the tensor
+        cores).  Separate from forward_nhwc so that sibling blocks fed the SAME (x1, x2) -- the three DeconvHeads of the
+        BEV decoder -- share one up-sampling pass."""
         sf = self.up.scale_factor
         sh, sw = (sf, sf) if not isinstance(sf, (tuple, list)) else sf
         Ho, Wo = int(math.floor(x1.shape[1] * sh)), int(math.floor(x1.shape[2] * sw))
-        x = engine.upsample_concat_for(self._f0, x2, x1, (Ho, Wo), sf)
+        return engine.upsample_concat_for(self._f0, x2, x1, (Ho, Wo), sf)
+
+    def forward_nhwc(self, x1, x2, split_out=None, upcat=None):
+        """split_out ("only" | "both" | None): how the consumer wants the block's output (engine.FusedConv.__call__).
+        upcat: the result of a sibling's upcat_nhwc(x1, x2) with the same channel counts and scale factor."""
+        if self.training:
+            return self.forward_train(x1, x2)
+        x = self.upcat_nhwc(x1, x2) if upcat is None else upcat
+        Ho, Wo = x.shape[1], x.shape[2]
         # conv -> BN -> ReLU -> conv: the intermediate has one consumer, so the first conv's epilogue writes it
         # directly as the second conv's 3xFP16 operand (no fp32 tensor, no split pre-pass)
         mid = (x.shape[0], Ho, Wo, self.conv[0].weight.shape[0])

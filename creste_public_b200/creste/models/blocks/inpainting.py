@@ -113,11 +113,11 @@ class DeconvHead(nn.Module):
         x = self._f_up2(x, act="relu")
         return self._f_proj(x, act="none"), x
 
-    def forward_fused_nhwc(self, x1, x2, want_nchw=True):
+    def forward_fused_nhwc(self, x1, x2, want_nchw=True, upcat=None):
         """Eval path with the projection head, the NCHW copy of the predictions and the NCHW copy of the 128-channel
         features in ONE pass over the features (creste_proj_head) instead of a generic conv + two transposes.
-        -> (pred NHWC, features NHWC, pred NCHW | None, features NCHW | None)."""
-        x = self.up1.forward_nhwc(x1, x2)
+        -> (pred NHWC, features NHWC, pred NCHW | None, features NCHW | None).  upcat: see Up.forward_nhwc."""
+        x = self.up1.forward_nhwc(x1, x2, upcat=upcat)
         N, H, W, _ = x.shape
         x = upsample_concat_for(self._f_up2, None, x, (2 * H, 2 * W), 2)
         x = self._f_up2(x, act="relu")
@@ -173,9 +173,18 @@ class InpaintingResNet18MultiHead(Inpainting):
         for blk in list(self.layer2) + list(self.layer3):
             x = blk.forward_nhwc(x)
         ret, preds_nhwc = {}, {}
+        upcat = None
+        if not self.training:
+            # the heads' first stage, Up(320, 256, x4)(x, x1), sees the same two tensors in every head: one up-sampling +
+            # concat pass (written once as the 3xFP16 operand) feeds the three first convs
+            h0 = self.out_heads[0].up1
+            same = all(h.up1.up.scale_factor == h0.up.scale_factor and
+                       h.up1.conv[0].weight.shape == h0.conv[0].weight.shape for h in self.out_heads)
+            if same:
+                upcat = h0.upcat_nhwc(x, x1)
         for head, prefix in zip(self.out_heads, self.output_prefix):
             if not self.training:
-                pred, fea, pred_nchw, fea_nchw = head.forward_fused_nhwc(x, x1, want_nchw)
+                pred, fea, pred_nchw, fea_nchw = head.forward_fused_nhwc(x, x1, want_nchw, upcat=upcat)
                 preds_nhwc[prefix] = pred
                 if want_nchw:
                     ret[f"{prefix}_preds"], ret[f"{prefix}_features"] = pred_nchw, fea_nchw

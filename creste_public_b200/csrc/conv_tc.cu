@@ -1227,6 +1227,9 @@ size_t wgrad_tc_workspace_bytes(const creste_conv_desc* d) {
          (size_t)w.splits * d->R * d->S * d->C * d->K * sizeof(float);
 }
 
+static int wgrad_tc_core(const creste_conv_desc* d, const void* x_hi, const void* x_lo, const float* x_scal,
+                         const void* g_hi, const void* g_lo, const float* g_scal, float* part, float* dw, cudaStream_t st);
+
 int wgrad_tc_launch(const creste_conv_desc* d, const float* x, const float* g, float* dw, void* ws, size_t ws_bytes,
                     cudaStream_t st) {
   if (!wgrad_tc_supported(d)) { set_error("creste_conv2d_wgrad_tc: shape not served (C, K multiples of 8, stride 1, >= 512 output pixels)"); return CRESTE_ERR_ARG; }
@@ -1241,6 +1244,31 @@ int wgrad_tc_launch(const creste_conv_desc* d, const float* x, const float* g, f
   int rc;
   if ((rc = wg_split(x, w.nx, d->C, x_hi, x_lo, scal, st))) return rc;
   if ((rc = wg_split(g, w.ng, d->K, g_hi, g_lo, scal + 4, st))) return rc;
+  return wgrad_tc_core(d, x_hi, x_lo, scal, g_hi, g_lo, scal + 4, part, dw, st);
+}
+
+// operands already split (the forward conv's saved operand, the output gradient split once for the data and the
+// weight gradient): only the partial-tile region of the workspace is used
+int wgrad_tc_presplit_launch(const creste_conv_desc* d, const void* x_hi, const void* x_lo, const float* x_scal,
+                             const void* g_hi, const void* g_lo, const float* g_scal, float* dw, void* ws,
+                             size_t ws_bytes, cudaStream_t st) {
+  if (!wgrad_tc_supported(d)) { set_error("creste_conv2d_wgrad_tc_presplit: shape not served"); return CRESTE_ERR_ARG; }
+  if (!ws || ws_bytes < wgrad_tc_workspace_bytes(d)) { set_error("creste_conv2d_wgrad_tc_presplit: workspace"); return CRESTE_ERR_WORKSPACE; }
+  const WgPlan w = wg_plan(d);
+  float* part = (float*)((char*)ws + 2 * align_up(w.nx * 2, 1024) + 2 * align_up(w.ng * 2, 1024) + 1024);
+  return wgrad_tc_core(d, x_hi, x_lo, x_scal, g_hi, g_lo, g_scal, part, dw, st);
+}
+
+// amax -> power-of-two scale -> fp16 hi / lo of a dense fp32 tensor (the pre-pass of creste_conv2d, stand-alone);
+// scal = DEVICE float[4]: {s, 1/s, amax bits, -}
+int f16_split_launch(const float* x, size_t numel, void* hi, void* lo, float* scal, cudaStream_t st) {
+  return wg_split(x, numel, 4, hi, lo, scal, st);
+}
+
+static int wgrad_tc_core(const creste_conv_desc* d, const void* x_hi, const void* x_lo, const float* scal_x,
+                         const void* g_hi, const void* g_lo, const float* scal_g, float* part, float* dw, cudaStream_t st) {
+  const WgPlan w = wg_plan(d);
+  int rc;
   CUtensorMap mg_hi, mg_lo, mx_hi, mx_lo;
   // box {64 channels, wbox, hbox, 1}: make_map_a's f16 form with a 64-pixel box
   if ((rc = make_map_a(&mg_hi, g_hi, d->N, d->P, d->Q, d->K, w.wbox, w.hbox, true, 1))) return rc;
@@ -1248,7 +1276,7 @@ int wgrad_tc_launch(const creste_conv_desc* d, const float* x, const float* g, f
   if ((rc = make_map_a(&mx_hi, x_hi, d->N, d->H, d->W, d->C, w.wbox, w.hbox, true, 1))) return rc;
   if ((rc = make_map_a(&mx_lo, x_lo, d->N, d->H, d->W, d->C, w.wbox, w.hbox, true, 1))) return rc;
   WgParams p;
-  p.part = part; p.sx = scal; p.sg = scal + 4;
+  p.part = part; p.sx = scal_x; p.sg = scal_g;
   p.N = d->N; p.P = d->P; p.Q = d->Q; p.C = d->C; p.K = d->K; p.R = d->R; p.S = d->S;
   p.pad_t = d->pad_t; p.pad_l = d->pad_l;
   p.wbox = w.wbox; p.hbox = w.hbox; p.tiles_x = w.tiles_x; p.tiles_y = w.tiles_y; p.ntiles = w.ntiles;
@@ -1361,6 +1389,20 @@ extern "C" int creste_conv2d_wgrad_tc(const creste_conv_desc* d, const float* x,
                                       size_t ws_bytes, void* stream) {
   if (!d || !x || !g || !dw) { creste::set_error("creste_conv2d_wgrad_tc: bad args"); return CRESTE_ERR_ARG; }
   return creste::wgrad_tc_launch(d, x, g, dw, ws, ws_bytes, (cudaStream_t)stream);
+}
+
+extern "C" int creste_conv2d_wgrad_tc_presplit(const creste_conv_desc* d, const void* x_hi, const void* x_lo,
+                                               const float* x_scal, const void* g_hi, const void* g_lo,
+                                               const float* g_scal, float* dw, void* ws, size_t ws_bytes, void* stream) {
+  if (!d || !x_hi || !x_lo || !x_scal || !g_hi || !g_lo || !g_scal || !dw) {
+    creste::set_error("creste_conv2d_wgrad_tc_presplit: bad args");
+    return CRESTE_ERR_ARG;
+  }
+  return creste::wgrad_tc_presplit_launch(d, x_hi, x_lo, x_scal, g_hi, g_lo, g_scal, dw, ws, ws_bytes, (cudaStream_t)stream);
+}
+extern "C" int creste_f16_split(const float* x, long long numel, void* hi, void* lo, float* scal, void* stream) {
+  if (!x || !hi || !lo || !scal || numel <= 0 || (numel & 7)) { creste::set_error("creste_f16_split: bad args (numel %% 8 == 0)"); return CRESTE_ERR_ARG; }
+  return creste::f16_split_launch(x, (size_t)numel, hi, lo, scal, (cudaStream_t)stream);
 }
 
 /* 3xFP16 weight operand of creste_conv2d (precision 4) in one launch: logical w[k][c][r][s] read through element

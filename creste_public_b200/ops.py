@@ -964,6 +964,33 @@ def conv2d_wgrad_tc(x_nhwc, g_nhwc, R, S, pad):
     return dw.view(R, S, Cc, K).permute(3, 2, 0, 1).contiguous()
 
 
+def split_f16(x_nhwc):
+    """The 3xFP16 operand of a dense fp32 NHWC tensor (amax -> power-of-two scale -> fp16 hi / lo) as a SplitAct."""
+    x_nhwc = x_nhwc.contiguous()
+    hi = torch.empty(x_nhwc.shape, dtype=torch.float16, device=x_nhwc.device)
+    lo = torch.empty_like(hi)
+    scal = torch.empty(4, device=x_nhwc.device)
+    check(lib().creste_f16_split(ptr(x_nhwc), C.c_longlong(x_nhwc.numel()), ptr(hi), ptr(lo), ptr(scal), stream()),
+          "creste_f16_split")
+    return SplitAct(hi, lo, scal, x_nhwc.shape)
+
+
+def conv2d_wgrad_tc_presplit(xs, gs, R, S, pad):
+    """conv2d_wgrad_tc on SplitAct operands (x: the forward conv's saved operand, g: the split output gradient)."""
+    N, H, W, Cc = xs.shape
+    _, P, Q, K = gs.shape
+    pt, pb, pl, pr = pad
+    assert P == H + pt + pb - R + 1 and Q == W + pl + pr - S + 1
+    d = ConvDesc(N, H, W, Cc, K, R, S, 1, pt, pl, P, Q, 0, 0, 4)
+    n = lib().creste_conv2d_wgrad_tc_workspace_bytes(C.byref(d))
+    ws = _ws(n, xs.device)
+    dw = torch.empty(R * S * Cc, K, device=xs.device)
+    check(lib().creste_conv2d_wgrad_tc_presplit(C.byref(d), ptr(xs.hi), ptr(xs.lo), ptr(xs.scal), ptr(gs.hi), ptr(gs.lo),
+                                                ptr(gs.scal), ptr(dw), ptr(ws), C.c_size_t(n), stream()),
+          "creste_conv2d_wgrad_tc_presplit")
+    return dw.view(R, S, Cc, K).permute(3, 2, 0, 1).contiguous()
+
+
 def wgrad_rows(x, g):
     """dw [K,C,1,1] of a 1x1 conv over a handful of rows: x [...,C], g [...,K] with <= 4096 rows."""
     x, g = x.contiguous(), g.contiguous()

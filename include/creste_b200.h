@@ -460,6 +460,15 @@ int creste_conv2d_wgrad_tc_supported(const creste_conv_desc* d);
 size_t creste_conv2d_wgrad_tc_workspace_bytes(const creste_conv_desc* d);
 int creste_conv2d_wgrad_tc(const creste_conv_desc* d, const float* x, const float* g, float* dw, void* ws,
                            size_t ws_bytes, void* stream);
+/* The 3xFP16 operand pre-pass of the tensor-core convs, stand-alone: amax -> power-of-two scale -> fp16 hi / lo of a
+ * dense fp32 tensor (numel % 8 == 0); scal = DEVICE float[4] {s, 1/s, amax bits, -}.  Training: the forward conv's
+ * operand is split ONCE and saved for the weight gradient, the output gradient is split ONCE for the data and the
+ * weight gradient (creste_conv2d_presplit / creste_conv2d_wgrad_tc_presplit) -- 2 pre-passes per conv instead of 4. */
+int creste_f16_split(const float* x, long long numel, void* hi, void* lo, float* scal, void* stream);
+/* creste_conv2d_wgrad_tc on operands that are already split (same workspace size). */
+int creste_conv2d_wgrad_tc_presplit(const creste_conv_desc* d, const void* x_hi, const void* x_lo, const float* x_scal,
+                                    const void* g_hi, const void* g_lo, const float* g_scal, float* dw, void* ws,
+                                    size_t ws_bytes, void* stream);
 
 /* The 3xFP16 weight operand of creste_conv2d (precision 4) packed in ONE launch (training re-packs every step):
  * logical w[k][c][r][s] is read through element strides (sK, sC, sR, sS) -- the data-gradient conv passes the

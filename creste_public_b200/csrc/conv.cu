@@ -1,5 +1,7 @@
 // conv.cu -- dispatcher of the conv family (creste_conv2d) + the EfficientNet trunk's
 // memory-bound kernels (depthwise conv + BN + swish + SE partial sums, SE gate).
+#include <stdlib.h>
+
 #include "common.cuh"
 
 namespace creste {
@@ -187,6 +189,112 @@ __global__ void __launch_bounds__(256) dwconv_xb_kernel(const float* __restrict_
       tot.x += o.x; tot.y += o.y; tot.z += o.z; tot.w += o.w;
     }
     reinterpret_cast<float4*>(chan_part + ((size_t)n * gridDim.x + blockIdx.x) * C)[cg] = tot;
+  }
+}
+
+// ---- tiled variant (round 2b): the x-blocked kernel above reads every tap straight from global memory with per-column
+// bounds checks and re-derives its indices per unit -- ncu: 272 instructions per float4 output, issue-bound at 0.25-0.35
+// of the HBM rate.  Here a CTA stages the input tile of TH x TW outputs x 32 channels (with its halo, zero-filled outside
+// the image: exactly the static TF-SAME padding) in shared memory with coalesced loads, and the taps come from there
+// without checks.  Same FMA order per output (taps in (r,s) raster order from acc = 0, out-of-image taps add an exact
+// 0), same epilogue; the SE partial sums are again reduced in a fixed order (thread: its units in order, outputs left
+// to right; CTA: the 32 unit lanes in order; one row of chan_part per tile), so results are reproducible run to run and
+// independent of the batch size -- but the rows are tiles now, so the squeeze-excite MEAN is summed in a different
+// order than with the x-blocked kernel (last-bit differences; both are within the parity bars).
+template <int R, int STRIDE>
+__global__ void __launch_bounds__(256) dwconv_tile_kernel(const float* __restrict__ x, const float* __restrict__ w,
+                                                          const float* __restrict__ scale, const float* __restrict__ shift,
+                                                          int H, int W, int C, int pad_t, int pad_l, int P, int Q,
+                                                          int tiles_x, float* __restrict__ out,
+                                                          float* __restrict__ chan_part, unsigned* __restrict__ amax_out) {
+  constexpr int TH = 8, TW = STRIDE == 1 ? 32 : 16, XB = 4, CG = 8;
+  constexpr int IH = (TH - 1) * STRIDE + R, IW = (TW - 1) * STRIDE + R;
+  constexpr int NC = (XB - 1) * STRIDE + R;
+  constexpr int UNITS = TH * (TW / XB);           // 64 (stride 1) / 32 (stride 2) units of XB outputs
+  extern __shared__ __align__(16) float4 dw_smem[];
+  float4* tile = dw_smem;                          // [IH][IW][CG]
+  float4* wsm = dw_smem + IH * IW * CG;            // [R*R][CG]
+  __shared__ float4 s_part[256];
+  const int C4 = C / 4;
+  const int n = blockIdx.y;
+  const int tx = blockIdx.x % tiles_x, ty = blockIdx.x / tiles_x;
+  const int oy0 = ty * TH, ox0 = tx * TW;
+  const int cg0 = blockIdx.z * CG;
+  const int cgs = min(CG, C4 - cg0);
+  const int tid = threadIdx.x;
+  const float4* xn = reinterpret_cast<const float4*>(x + (size_t)n * H * W * C);
+  const int iy0 = oy0 * STRIDE - pad_t, ix0 = ox0 * STRIDE - pad_l;
+  for (int i = tid; i < IH * IW * CG; i += 256) {
+    const int g = i % CG, p = i / CG;
+    const int ix = ix0 + p % IW, iy = iy0 + p / IW;
+    float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+    if (g < cgs && iy >= 0 && iy < H && ix >= 0 && ix < W) v = __ldg(xn + ((size_t)iy * W + ix) * C4 + cg0 + g);
+    tile[i] = v;
+  }
+  for (int i = tid; i < R * R * CG; i += 256) {
+    const int g = i % CG, t = i / CG;
+    wsm[i] = g < cgs ? __ldg(reinterpret_cast<const float4*>(w) + (size_t)t * C4 + cg0 + g) : make_float4(0.f, 0.f, 0.f, 0.f);
+  }
+  __syncthreads();
+  const int g = tid % CG, ul = tid / CG;           // 32 unit lanes
+  float4 sum = make_float4(0.f, 0.f, 0.f, 0.f);
+  float amx = 0.0f;
+  if (g < cgs) {
+    const float4 sc = __ldg(reinterpret_cast<const float4*>(scale) + cg0 + g);
+    const float4 sh = __ldg(reinterpret_cast<const float4*>(shift) + cg0 + g);
+#pragma unroll 1
+    for (int u = ul; u < UNITS; u += 32) {
+      const int ly = u / (TW / XB), lx = (u - ly * (TW / XB)) * XB;
+      const int oy = oy0 + ly;
+      if (oy >= P || ox0 + lx >= Q) continue;
+      float4 acc[XB];
+#pragma unroll
+      for (int b = 0; b < XB; ++b) acc[b] = make_float4(0.f, 0.f, 0.f, 0.f);
+      const float4* t0 = tile + ((size_t)(ly * STRIDE) * IW + lx * STRIDE) * CG + g;
+#pragma unroll
+      for (int r = 0; r < R; ++r) {
+        float4 col[NC];
+#pragma unroll
+        for (int c = 0; c < NC; ++c) col[c] = t0[((size_t)r * IW + c) * CG];
+#pragma unroll
+        for (int s_ = 0; s_ < R; ++s_) {
+          const float4 k = wsm[(r * R + s_) * CG + g];
+#pragma unroll
+          for (int b = 0; b < XB; ++b) {
+            const float4 v = col[b * STRIDE + s_];
+            acc[b].x = fmaf(v.x, k.x, acc[b].x); acc[b].y = fmaf(v.y, k.y, acc[b].y);
+            acc[b].z = fmaf(v.z, k.z, acc[b].z); acc[b].w = fmaf(v.w, k.w, acc[b].w);
+          }
+        }
+      }
+#pragma unroll
+      for (int b = 0; b < XB; ++b) {
+        if (ox0 + lx + b < Q) {
+          float4 o;
+          o.x = fmaf(acc[b].x, sc.x, sh.x); o.y = fmaf(acc[b].y, sc.y, sh.y);
+          o.z = fmaf(acc[b].z, sc.z, sh.z); o.w = fmaf(acc[b].w, sc.w, sh.w);
+          o.x = o.x / (1.0f + expf(-o.x)); o.y = o.y / (1.0f + expf(-o.y));
+          o.z = o.z / (1.0f + expf(-o.z)); o.w = o.w / (1.0f + expf(-o.w));
+          reinterpret_cast<float4*>(out + (((size_t)n * P + oy) * Q + ox0 + lx + b) * C)[cg0 + g] = o;
+          sum.x += o.x; sum.y += o.y; sum.z += o.z; sum.w += o.w;
+          amx = fmaxf(fmaxf(amx, fmaxf(fabsf(o.x), fabsf(o.y))), fmaxf(fabsf(o.z), fabsf(o.w)));
+        }
+      }
+    }
+  }
+  if (amax_out) {
+    amx = warp_max(amx);
+    if ((tid & 31) == 0 && amx > 0.0f) atomicMax(amax_out, __float_as_uint(amx));
+  }
+  s_part[tid] = sum;
+  __syncthreads();
+  if (tid < cgs) {
+    float4 tot = s_part[tid];
+    for (int l = 1; l < 32; ++l) {
+      const float4 o = s_part[l * CG + tid];
+      tot.x += o.x; tot.y += o.y; tot.z += o.z; tot.w += o.w;
+    }
+    reinterpret_cast<float4*>(chan_part + ((size_t)n * gridDim.x + blockIdx.x) * C)[cg0 + tid] = tot;
   }
 }
 
@@ -406,6 +514,22 @@ extern "C" int creste_dwconv_num_parts(int N, int P, int Q) {
   return tiles > 592 ? 592 : tiles;
 }
 
+extern "C" int creste_dwconv_tile_parts(int P, int Q, int stride) {
+  // chan_part rows of the tiled depthwise kernel: one per 8 x 32 (stride 1) / 8 x 16 (stride 2) output tile
+  return ceil_div(P, 8) * ceil_div(Q, stride == 1 ? 32 : 16);
+}
+
+extern "C" int creste_dwconv_parts(int N, int P, int Q, int R, int stride) {
+  // the chan_part row count of the kernel that is faster for this layer (measured, tools/kernel_bench.py): the tiled
+  // kernel wins on the low-resolution stages (<= 32 x 60 outputs) and on the 5 x 5 stride-1 layers up to 64 x 120; the
+  // x-blocked one on the large early layers (its L1-served taps beat the tile fill there)
+  const long long pq = (long long)P * Q;
+  const bool tiled = !getenv("CRESTE_NO_DWTILE") && (stride == 1 || stride == 2) &&
+                     (pq <= 2048 || (R == 5 && stride == 1 && pq <= 7680) || getenv("CRESTE_DWTILE_ALL"));
+  const int t = creste_dwconv_tile_parts(P, Q, stride), o = creste_dwconv_num_parts(N, P, Q);
+  return tiled ? t : o;
+}
+
 extern "C" int creste_dwconv_bn_swish(const float* x, const float* w, const float* scale,
                                       const float* shift, int N, int H, int W, int C, int R,
                                       int stride, int pad_t, int pad_l, int P, int Q, float* out,
@@ -420,10 +544,32 @@ extern "C" int creste_dwconv_bn_swish_ex(const float* x, const float* w, const f
                                          float* chan_part, int nparts, float* amax_out, void* stream) {
   CRESTE_CHECK_ARG(x && w && scale && shift && out && chan_part, "creste_dwconv_bn_swish: null pointer");
   CRESTE_CHECK_ARG(C % 4 == 0 && (R == 3 || R == 5), "creste_dwconv_bn_swish: C%%4==0, R in {3,5}");
-  CRESTE_CHECK_ARG(nparts == creste_dwconv_num_parts(N, P, Q), "creste_dwconv_bn_swish: nparts");
+  CRESTE_CHECK_ARG(nparts == creste_dwconv_num_parts(N, P, Q) || nparts == creste_dwconv_tile_parts(P, Q, stride),
+                   "creste_dwconv_bn_swish: nparts");
   cudaStream_t st = (cudaStream_t)stream;
   unsigned* am = (unsigned*)amax_out;
   if (am) CRESTE_CUDA(cudaMemsetAsync(am, 0, sizeof(float), st));
+  // tiled kernel: selected by the caller through the chan_part row count it allocated (creste_dwconv_tile_parts)
+  if ((stride == 1 || stride == 2) && nparts == creste_dwconv_tile_parts(P, Q, stride) &&
+      nparts != creste_dwconv_num_parts(N, P, Q)) {
+    const int TW = stride == 1 ? 32 : 16;
+    const int tiles_x = ceil_div(Q, TW);
+    const int IH = 7 * stride + R, IW = (TW - 1) * stride + R;
+    const size_t smem = ((size_t)IH * IW * 8 + (size_t)R * R * 8) * sizeof(float4);
+    dim3 tgrid(nparts, N, ceil_div(C / 4, 8));
+#define CRESTE_DWT(RR, SS)                                                                                            \
+    do {                                                                                                              \
+      CRESTE_CUDA(cudaFuncSetAttribute(dwconv_tile_kernel<RR, SS>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)); \
+      dwconv_tile_kernel<RR, SS><<<tgrid, 256, smem, st>>>(x, w, scale, shift, H, W, C, pad_t, pad_l, P, Q, tiles_x, out, \
+                                                          chan_part, am);                                            \
+    } while (0)
+    if (stride == 1 && R == 3) CRESTE_DWT(3, 1);
+    else if (stride == 1) CRESTE_DWT(5, 1);
+    else if (R == 3) CRESTE_DWT(3, 2);
+    else CRESTE_DWT(5, 2);
+#undef CRESTE_DWT
+    return launch_check("dwconv_tile_kernel");
+  }
   dim3 grid(nparts, N, ceil_div(C / 4, 256));
   if (stride == 1 && R == 3)
     dwconv_xb_kernel<3, 1, 4><<<grid, 256, 0, st>>>(x, w, scale, shift, N, H, W, C, pad_t, pad_l, P, Q, out, chan_part, am);

@@ -71,7 +71,7 @@ std::tuple<Tensor, Tensor> dwconv_bn_swish(const Tensor& x_, const Tensor& w, co
   Tensor x = x_.contiguous();
   const int N = x.size(0), H = x.size(1), W = x.size(2), C = x.size(3);
   const int P = (H + pad[0] + pad[1] - R) / stride + 1, Q = (W + pad[2] + pad[3] - R) / stride + 1;
-  const int nparts = creste_dwconv_num_parts(N, P, Q);
+  const int nparts = creste_dwconv_parts(N, P, Q, (int)R, (int)stride);   // same kernel choice as the Python mirror
   Tensor out = at::empty({N, P, Q, C}, x.options()), part = at::empty({N, nparts, C}, x.options());
   check(creste_dwconv_bn_swish(fp(x), fp(w), fp(scale), fp(shift), N, H, W, C, (int)R, (int)stride, (int)pad[0],
                                (int)pad[2], P, Q, out.data_ptr<float>(), part.data_ptr<float>(), nparts, stream()),

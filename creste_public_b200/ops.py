@@ -5,6 +5,7 @@ allocates outputs / scratch with torch's caching allocator on the same device an
 sm_100a kernels on torch's current stream.  No function has a CPU or PyTorch-eager fallback.
 """
 import ctypes as C
+import os
 
 import torch
 
@@ -420,7 +421,8 @@ def dwconv_bn_swish(x_nhwc, w_rsc, scale, shift, R, stride, pad, amax_out=None):
     P = (H + pt + pb - R) // stride + 1
     Q = (W + pl + pr - R) // stride + 1
     out = torch.empty(N, P, Q, Cc, device=x_nhwc.device)
-    nparts = lib().creste_dwconv_num_parts(N, P, Q)
+    # the chan_part row count selects the kernel: tiled (shared-memory input tile) or x-blocked, whichever is faster
+    nparts = lib().creste_dwconv_parts(N, P, Q, R, stride)
     csum = torch.empty(N, nparts, Cc, device=x_nhwc.device)
     check(lib().creste_dwconv_bn_swish_ex(ptr(x_nhwc), ptr(w_rsc), ptr(scale), ptr(shift), N, H, W, Cc,
                                           R, stride, pt, pl, P, Q, ptr(out), ptr(csum), nparts, ptr(amax_out), stream()),

@@ -236,6 +236,13 @@ int creste_conv2d_tc_layout(int K, int C, int R, int S, int* block_n, int* npad,
  *   x NHWC [N,H,W,C]; w [R*S, C]; out NHWC [N,P,Q,C];
  *   chan_part [N, nparts, C] with nparts = creste_dwconv_num_parts(N, P, Q). */
 int creste_dwconv_num_parts(int N, int P, int Q);
+/* Row count of chan_part for the TILED depthwise kernel (one row per 8 x 32 / 8 x 16 output tile, stride 1 / 2): a
+ * caller that allocates chan_part with this many rows (and passes it as nparts) gets the shared-memory-tiled kernel,
+ * creste_dwconv_num_parts rows the x-blocked one.  Same results per output element; the squeeze-excite partial sums
+ * are grouped by tile instead of by pixel run. */
+int creste_dwconv_tile_parts(int P, int Q, int stride);
+/* the row count of whichever of the two kernels is faster for this layer (what the mirror allocates) */
+int creste_dwconv_parts(int N, int P, int Q, int R, int stride);
 int creste_dwconv_bn_swish(const float* x, const float* w, const float* scale, const float* shift,
                            int N, int H, int W, int C, int R, int stride, int pad_t, int pad_l,
                            int P, int Q, float* out, float* chan_part, int nparts, void* stream);

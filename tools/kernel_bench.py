@@ -104,3 +104,19 @@ for K in (32, 6, 2):
         torch.equal(x_nchw, x.permute(0, 3, 1, 2).contiguous())
     report(f"proj_head C128->K{K} @256x256", timeit(lambda: ops.proj_head(x, w, bias)), None,
            4 * B * 256 * 256 * (2 * 128 + 2 * K), same)
+
+# ---- depthwise conv + BN + swish (+ SE partial sums): tiled kernel vs the x-blocked one (CRESTE_NO_DWTILE)
+for (Cc, H, W, R, st) in [(32, 256, 480, 3, 1), (96, 256, 480, 3, 2), (144, 128, 240, 3, 1), (144, 128, 240, 5, 2),
+                          (240, 64, 120, 5, 1), (240, 64, 120, 3, 2), (480, 32, 60, 3, 1), (672, 32, 60, 5, 1),
+                          (672, 32, 60, 5, 2), (1152, 16, 30, 5, 1), (1152, 16, 30, 3, 1)]:
+    x = torch.randn(B, H, W, Cc, device=dev)
+    w = torch.randn(R * R, Cc, device=dev) / R
+    sc, sh = torch.rand(Cc, device=dev) + 0.5, torch.randn(Cc, device=dev) * 0.1
+    tot = (R - 1) if st == 1 else max(R - st, 0)
+    pad = (tot // 2, tot - tot // 2) * 2
+    f = lambda: ops.dwconv_bn_swish(x, w, sc, sh, R, st, pad)  # noqa: E731
+    new, old, tn, to = ab("CRESTE_NO_DWTILE", f)
+    same = torch.equal(new[0], old[0]) and \
+        float((new[1].sum(1) - old[1].sum(1)).abs().max()) <= 1e-5 * float(old[1].sum(1).abs().max())
+    P, Q = new[0].shape[1], new[0].shape[2]
+    report(f"dwconv C{Cc} @{H}x{W} k{R} s{st}", tn, to, 4 * B * Cc * (H * W + P * Q), same)

@@ -23,6 +23,7 @@
 // final pass; HBM-bound if streamed, here served from L2/SMEM.
 #include <cooperative_groups.h>
 
+#include <algorithm>
 #include <type_traits>
 
 #include "common.cuh"
@@ -554,6 +555,7 @@ struct ViStripParams {
   unsigned long long* gword;   // [max_sweeps + 2] : low 32 = max|dv| bits, high 32 = arrival count
   int* sweeps_out;
   int B, H, W, R, c, max_sweeps, G, nt, lag;   // nt = compute threads (multiple of 32)
+  int rgn, nfull;              // row groups per strip; the LAST nfull groups own RT rows, the others RT - 1
   float gamma, thr;
 };
 
@@ -739,18 +741,28 @@ __global__ void __launch_bounds__(RT <= 2 ? 896 : (RT == 3 ? 608 : 544), 1) vi_s
     // hoisted: shared-memory addresses are 32-bit registers set up once, the sweeps come in blocks of `lag` with
     // a compile-time tile parity, and the stop decision is consumed once per block instead of once per sweep.
     const int cgn = W >> 2;
-    const int rgn = (p.R + RT - 1) / RT;
+    const int rgn = p.rgn;
     const bool thread_on = tid < cgn * rgn;
     const int cgi = thread_on ? tid % cgn : 0, rg = thread_on ? tid / cgn : 0;
-    const int lr0 = rg * RT;
+    // Row groups of RT - 1 rows first, then p.nfull groups of RT rows (the host only mixes the two when a warp never
+    // spans two groups, so the row count is warp-uniform): with W = 256, R = 26 this is 6 x 3 + 2 x 4 rows on 16
+    // compute warps = 13 rows per scheduler, where 9 uniform groups of 3 on 18 warps put 15 (one of them junk) on two of
+    // the four schedulers.
+    const int nshort = rgn - p.nfull;
+    const int my_rows = rg >= nshort ? RT : RT - 1;
+    const int lr0 = rg * (RT - 1) + max(0, rg - nshort);
     const int x0 = cgi << 2;
-    bool on[RT];
-    float4 rr[RT], v[RT];
+    bool failed = false;
+    int K = p.max_sweeps, hit_max = 1;
+    auto body = [&](auto nr_c) {
+    constexpr int NR = decltype(nr_c)::value;
+    bool on[NR];
+    float4 rr[NR], v[NR];
     float* ckpt = sm + 2 * tile;                 // snapshot slot q at ckpt + q * R * W (zero = v_0)
     const int ck_stride = p.R * W;
     const size_t base = ((size_t)b * H + row0) * W;
 #pragma unroll
-    for (int i = 0; i < RT; ++i) {
+    for (int i = 0; i < NR; ++i) {
       on[i] = thread_on && (lr0 + i < n);
       rr[i] = on[i] ? __ldg(reinterpret_cast<const float4*>(p.r + base + (size_t)(lr0 + i) * W + x0))
                     : make_float4(0.f, 0.f, 0.f, 0.f);
@@ -758,7 +770,7 @@ __global__ void __launch_bounds__(RT <= 2 ? 896 : (RT == 3 ? 608 : 544), 1) vi_s
     }
     const uint32_t sm_base = vi_smem_u32(sm);
     const bool push_up = has_up && thread_on && lr0 == 0;                       // owns strip row 0
-    const int dn_i = (has_dn && thread_on && n - 1 >= lr0 && n - 1 < lr0 + RT) ? n - 1 - lr0 : -1;
+    const int dn_i = (has_dn && thread_on && n - 1 >= lr0 && n - 1 < lr0 + NR) ? n - 1 - lr0 : -1;
     // remote byte addresses (tile 0): my top row -> bottom halo (row R+1) of the strip above; my
     // bottom row -> top halo (row 0) of the strip below
     uint32_t up_dst = push_up ? vi_mapa(sm_base, (uint32_t)(cr - 1)) + (uint32_t)(((p.R + 1) * P + 4 + x0) * 4) : 0u;
@@ -777,29 +789,28 @@ __global__ void __launch_bounds__(RT <= 2 ? 896 : (RT == 3 ? 608 : 544), 1) vi_s
     // kernel parameters and %cluster_ctaid at every use (a dozen integer instructions per shared-memory access)
     asm volatile("" : "+r"(win_a), "+r"(P4), "+r"(tile4), "+r"(mbar_a), "+r"(wmax_a), "+r"(post_a));
     asm volatile("" : "+r"(up_dst), "+r"(dn_dst), "+r"(up_bar0), "+r"(dn_bar0), "+r"(my_tx));
-    bool failed = false;
 
     // X = r + gamma*v of the own cells into tile `buf` (+ halo pushes), arrive, wait for the phase
     auto exchange = [&](const uint32_t buf, const uint32_t parity) {
       const uint32_t boff = buf ? tile4 : 0u;
       const uint32_t a = win_a + boff;
-      float4 X[RT];
+      float4 X[NR];
 #pragma unroll
-      for (int i = 0; i < RT; ++i) {
+      for (int i = 0; i < NR; ++i) {
         X[i].x = __fadd_rn(rr[i].x, __fmul_rn(v[i].x, gamma));
         X[i].y = __fadd_rn(rr[i].y, __fmul_rn(v[i].y, gamma));
         X[i].z = __fadd_rn(rr[i].z, __fmul_rn(v[i].z, gamma));
         X[i].w = __fadd_rn(rr[i].w, __fmul_rn(v[i].w, gamma));
       }
       if constexpr (PW > 0) {
-        vi_static_for<0, RT>([&](auto ic) {
+        vi_static_for<0, NR>([&](auto ic) {
           constexpr int i = decltype(ic)::value;
           if (on[i]) vi_sts_v4<(i + 1) * PW * 4>(a, X[i]);
         });
       } else {
         uint32_t ai = a;
 #pragma unroll
-        for (int i = 0; i < RT; ++i) {
+        for (int i = 0; i < NR; ++i) {
           ai += P4;
           if (on[i]) vi_sts_v4<0>(ai, X[i]);
         }
@@ -808,7 +819,7 @@ __global__ void __launch_bounds__(RT <= 2 ? 896 : (RT == 3 ? 608 : 544), 1) vi_s
       if (dn_i >= 0) {
         float4 Xd = X[0];
 #pragma unroll
-        for (int i = 1; i < RT; ++i) if (dn_i == i) Xd = X[i];
+        for (int i = 1; i < NR; ++i) if (dn_i == i) Xd = X[i];
         vi_st_async_v4(dn_dst + boff, Xd, dn_bar0 + buf * 8u);
       }
       const uint32_t bar = mbar_a + buf * 8u;
@@ -827,9 +838,9 @@ __global__ void __launch_bounds__(RT <= 2 ? 896 : (RT == 3 ? 608 : 544), 1) vi_s
     // one Bellman sweep on tile `buf`: v <- max_a q ; returns max |dv| over the own cells
     auto sweep = [&](const uint32_t buf) -> float {
       const uint32_t ra = win_a + (buf ? tile4 : 0u);
-      float a[RT + 2][6];
+      float a[NR + 2][6];
       if constexpr (PW > 0) {
-        vi_static_for<0, RT + 2>([&](auto ic) {
+        vi_static_for<0, NR + 2>([&](auto ic) {
           constexpr int i = decltype(ic)::value;
           const float4 m = vi_lds_v4<i * PW * 4>(ra);
           a[i][0] = vi_lds<i * PW * 4 - 4>(ra); a[i][1] = m.x; a[i][2] = m.y; a[i][3] = m.z; a[i][4] = m.w;
@@ -838,7 +849,7 @@ __global__ void __launch_bounds__(RT <= 2 ? 896 : (RT == 3 ? 608 : 544), 1) vi_s
       } else {
         uint32_t ri = ra;
 #pragma unroll
-        for (int i = 0; i < RT + 2; ++i) {
+        for (int i = 0; i < NR + 2; ++i) {
           const float4 m = vi_lds_v4<0>(ri);
           a[i][0] = vi_lds<-4>(ri); a[i][1] = m.x; a[i][2] = m.y; a[i][3] = m.z; a[i][4] = m.w; a[i][5] = vi_lds<16>(ri);
           ri += P4;
@@ -846,7 +857,7 @@ __global__ void __launch_bounds__(RT <= 2 ? 896 : (RT == 3 ? 608 : 544), 1) vi_s
       }
       float dmax = 0.f;
 #pragma unroll
-      for (int i = 0; i < RT; ++i) {
+      for (int i = 0; i < NR; ++i) {
         float nv[4];
 #pragma unroll
         for (int j = 0; j < 4; ++j) {
@@ -883,7 +894,7 @@ __global__ void __launch_bounds__(RT <= 2 ? 896 : (RT == 3 ? 608 : 544), 1) vi_s
     // `lag` sweeps old, so the wait is normally already satisfied -- and only then v_s is snapshotted into slot m & 1:
     // a stop at K in ((m-2)*lag, (m-1)*lag] finds both candidate snapshots, (m-2)*lag and (m-1)*lag, still alive.
     const int lag = p.lag;
-    int K = p.max_sweeps, hit_max = 1, s = 0;
+    int s = 0;
     uint32_t par = 0;                       // mbarrier phase parity of both tiles for the current pair of sweeps
     for (int m = 1; !failed; ++m) {
       for (int t = 0; t < lag; t += 2) {
@@ -911,7 +922,7 @@ __global__ void __launch_bounds__(RT <= 2 ? 896 : (RT == 3 ? 608 : 544), 1) vi_s
       }
       float* dst = ckpt + (m & 1) * ck_stride;      // snapshot v_s, s = m * lag (own cells only)
 #pragma unroll
-      for (int i = 0; i < RT; ++i)
+      for (int i = 0; i < NR; ++i)
         if (on[i]) *reinterpret_cast<float4*>(dst + (lr0 + i) * W + x0) = v[i];
     }
     int ph = s;                                      // even: the next exchange uses tile 0
@@ -921,7 +932,7 @@ __global__ void __launch_bounds__(RT <= 2 ? 896 : (RT == 3 ? 608 : 544), 1) vi_s
       const int c0 = (K / lag) * lag;
       const float* src = ckpt + ((c0 / lag) & 1) * ck_stride;
 #pragma unroll
-      for (int i = 0; i < RT; ++i)
+      for (int i = 0; i < NR; ++i)
         if (on[i]) v[i] = *reinterpret_cast<const float4*>(src + (lr0 + i) * W + x0);
       for (int r = c0; r < K && !failed; ++r) {
         exchange((uint32_t)(ph & 1), (uint32_t)((ph >> 1) & 1));
@@ -935,7 +946,7 @@ __global__ void __launch_bounds__(RT <= 2 ? 896 : (RT == 3 ? 608 : 544), 1) vi_s
       const float* X = sm + (ph & 1) * tile;
       const size_t HW = (size_t)H * W;
 #pragma unroll
-      for (int i = 0; i < RT; ++i) {
+      for (int i = 0; i < NR; ++i) {
         const int lr = lr0 + i;
         if (on[i] && !failed) {
           const int y = row0 + lr;
@@ -969,6 +980,9 @@ __global__ void __launch_bounds__(RT <= 2 ? 896 : (RT == 3 ? 608 : 544), 1) vi_s
         }
       }
     }
+    };   // body
+    if (my_rows == RT) body(std::integral_constant<int, RT>{});
+    else if constexpr (RT > 1) body(std::integral_constant<int, RT - 1>{});
     if (blockIdx.x == 0 && tid == 0 && p.sweeps_out) {
       p.sweeps_out[0] = failed ? -1 : K;
       p.sweeps_out[1] = failed ? -1 : hit_max;
@@ -1008,8 +1022,12 @@ static int vi_try_strip(ViStripParams& p, int c, int threads, size_t smem, cudaS
   }
   *max_clusters_out = max_clusters;
   if (max_clusters < p.B) {              // every cluster must be co-resident (global delta exchange)
-    if (getenv("CRESTE_VI_DEBUG"))
-      fprintf(stderr, "[creste_vi strip] c=%d R=%d RT=%d: max_clusters=%d < B=%d\n", c, p.R, RT, max_clusters, p.B);
+    if (getenv("CRESTE_VI_DEBUG")) {
+      cudaFuncAttributes fa;
+      cudaFuncGetAttributes(&fa, kern);
+      fprintf(stderr, "[creste_vi strip] c=%d R=%d RT=%d: max_clusters=%d < B=%d (threads %d, regs %d, maxThreadsPerBlock %d, smem %zu + %zu)\n",
+              c, p.R, RT, max_clusters, p.B, threads + 32, fa.numRegs, fa.maxThreadsPerBlock, smem, fa.sharedSizeBytes);
+    }
     return 0;
   }
   p.c = c; p.G = p.B * c; p.nt = threads;
@@ -1094,18 +1112,50 @@ extern "C" int creste_vi_solve(const float* r, float* v_out, float* q_out, float
       if (c > H) continue;
       const int R = ceil_div(H, c);
       if ((c - 1) * R >= H) continue;                 // every strip needs at least one row
-      int RT = 0;
-      for (int t = 1; t <= 4; ++t)
-        if ((long long)cgn * ceil_div(R, t) <= (t <= 2 ? vi_rt2_limit() : (t == 3 ? 576 : 512))) { RT = t; break; }
-      if (const char* e = getenv("CRESTE_VI_RT")) {          // experiment knob: force the rows-per-thread blocking
+      // rows per thread RT and row groups rgn: the LAST nfull = R - rgn * (RT - 1) groups own RT rows, the others
+      // RT - 1 (mixed only when a warp never spans two groups).  Cost = the largest number of row-sweeps any of the four
+      // warp schedulers carries (warp w runs on scheduler w % 4); ties go to the configuration with more warps.
+      int RT = 0, rgn = 0, nfull = 0;
+      {
+        long long best = -1;
+        int best_threads = 0;
+        const int wpr = cgn >= 32 ? cgn / 32 : 0;        // warps per row group (0: several groups share a warp)
+        for (int t = 1; t <= 4; ++t) {
+          const int lim = t <= 2 ? vi_rt2_limit() : (t == 3 ? 576 : 512);
+          const int g_min = ceil_div(R, t), g_max = (t > 1 && wpr > 0 && cgn % 32 == 0 && !getenv("CRESTE_VI_UNIFORM")) ? R / (t - 1) : g_min;
+          for (int g = g_min; g <= g_max; ++g) {
+            if ((long long)cgn * g > lim) break;
+            const int nf = t > 1 ? R - g * (t - 1) : g;
+            if (nf < 0 || nf > g) continue;
+            long long load[4] = {0, 0, 0, 0};
+            if (wpr > 0) {
+              for (int q = 0; q < g; ++q)
+                for (int h = 0; h < wpr; ++h) load[(q * wpr + h) & 3] += (q >= g - nf ? t : t - 1);
+            } else {
+              const int warps = ceil_div(cgn * g, 32);
+              for (int w = 0; w < warps; ++w) load[w & 3] += t;
+            }
+            const long long cost = std::max(std::max(load[0], load[1]), std::max(load[2], load[3]));
+            const int threads_g = cgn * g;
+            if (best < 0 || cost < best || (cost == best && threads_g > best_threads)) {
+              best = cost; best_threads = threads_g; RT = t; rgn = g; nfull = nf;
+            }
+          }
+        }
+      }
+      if (const char* e = getenv("CRESTE_VI_RT")) {          // experiment knob: force uniform rows-per-thread blocking
         const int t = atoi(e);
-        if (t >= 1 && t <= 4 && (long long)cgn * ceil_div(R, t) <= (t <= 2 ? 864 : (t == 3 ? 576 : 512))) RT = t;
+        if (t >= 1 && t <= 4 && (long long)cgn * ceil_div(R, t) <= (t <= 2 ? 864 : (t == 3 ? 576 : 512))) {
+          RT = t; rgn = ceil_div(R, t); nfull = t > 1 ? R - rgn * (t - 1) : rgn;
+          if (nfull < rgn && cgn % 32 != 0) { nfull = rgn; }
+        }
       }
       if (!RT) continue;
-      int threads = cgn * ceil_div(R, RT);
+      int threads = cgn * rgn;
       threads = (threads + 31) / 32 * 32;
       const size_t ssmem = ((size_t)2 * (R + 2) * (W + 8) + (size_t)2 * R * W) * sizeof(float);
       if (ssmem > 200 * 1024) continue;
+      sp.rgn = rgn; sp.nfull = nfull;
       sp.R = R;
       sp.lag = (long long)R * W >= 2048 ? 8 : 16;   // even, 2 * lag <= RING
       if (const char* e = getenv("CRESTE_VI_LAG")) { const int l = atoi(e); if (l >= 2 && 2 * l <= VI2_RING && (l & 1) == 0) sp.lag = l; }

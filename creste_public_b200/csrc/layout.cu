@@ -248,7 +248,7 @@ __global__ void __launch_bounds__(256) upsample_concat_kernel(const float* __res
 // fma(l0, a, l1 * b) pairs, and at the borders the clamped neighbour carries weight exactly 0 or duplicates the tap
 // (1 * a + 0 * b = a for finite b).
 template <int F, bool SPLIT>
-__global__ void __launch_bounds__(256, 2) upsample_block_kernel(const float* __restrict__ skip, int Cs,
+__global__ void __launch_bounds__(256, 3) upsample_block_kernel(const float* __restrict__ skip, int Cs,
                                                              const float* __restrict__ x, int N, int Hi, int Wi, int Cx,
                                                              int x_first, float* __restrict__ out,
                                                              const unsigned* __restrict__ amax_a,

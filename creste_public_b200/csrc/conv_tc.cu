@@ -776,8 +776,11 @@ static int make_map_b(CUtensorMap* m, const void* base, int ktot, int npad, int 
 // otherwise the divisor-friendliest tile <= 256
 static int pick_block_n(int K) {
   const int k16 = (K + 15) / 16 * 16;
-  if (k16 <= 256) return k16;
-  const int tiles = (k16 + 255) / 256;
+  // experiment knob: cap the N tile (<= 128 lets two CTAs share an SM: 2 x 256 TMEM columns)
+  int cap = 256;
+  if (const char* e = getenv("CRESTE_TC_MAX_BN")) { const int v = atoi(e); if (v >= 32 && v <= 256 && v % 16 == 0) cap = v; }
+  if (k16 <= cap) return k16;
+  const int tiles = (k16 + cap - 1) / cap;
   return ((k16 + tiles - 1) / tiles + 15) / 16 * 16;
 }
 

@@ -16,7 +16,7 @@ EXPORTS = [
     "creste_version", "creste_last_error", "creste_num_sms", "creste_launch_count",
     "creste_vi_workspace_bytes", "creste_vi_solve",
     "creste_svf_workspace_bytes", "creste_svf",
-    "creste_frustum_to_bev", "creste_camera_to_world", "creste_points_to_voxels", "creste_zmlp_concat",
+    "creste_frustum_to_bev", "creste_camera_to_world", "creste_points_to_voxels", "creste_zmlp_concat", "creste_zmlp_concat_ex",
     "creste_splat_workspace_bytes", "creste_splat_soft", "creste_splat_bwd_workspace_bytes", "creste_splat_soft_bwd",
     "creste_frustum_bwd", "creste_depth_expectation_bwd", "creste_dilate", "creste_phase_slice",
     "creste_lidar_raster", "creste_depth_expectation", "creste_bin_depths",

@@ -8,7 +8,7 @@ conv + BN + ReLU), creste_splat_soft (bilinear scatter-add + mean normalisation)
 import torch
 from torch import nn
 
-from creste_public_b200 import ops
+from creste_public_b200 import engine, ops
 from creste_public_b200.engine import PackCache, require_eval
 from .conv import ConvEncoder
 
@@ -83,12 +83,22 @@ class Camera2MapMulti(nn.Module):
         xy, z, mask = self.frustum(depth, p2p)
         l0, l2 = self.z_proj[0], self.z_proj[2]
         w1, b1, w2, b2 = self._zmlp_weights(l0, l2)
-        cat = ops.zmlp_concat(feats_nhwc, z, w1, b1, w2, b2)
+        # the maxima travel with the tensors (no amax passes in front of the tensor-core convs): the z-MLP kernel
+        # publishes max|cat|; the splat is a weighted mean (sum w f / max(sum w, min_weight), min_weight > 0), so the
+        # fusion conv's max|f| bounds the BEV map too
+        track = engine.get_precision() in ("3xfp16", "fp16") and not torch.jit.is_tracing()
+        amax = torch.empty(1, device=feats_nhwc.device) if track else None
+        cat = ops.zmlp_concat(feats_nhwc, z, w1, b1, w2, b2, **({"amax_out": amax} if track else {}))
+        if track:
+            cat._amax = amax
         fused = self.vision_fusion.forward_nhwc(cat)                     # [M,Hs,Ws,96]
         Cf = fused.shape[-1]
         # grid_size = (nx, ny, nz); the BEV map is [grid[0] rows, grid[1] cols] (:248-250)
         out = ops.splat_soft(xy, fused.view(M, Hs * Ws, Cf), mask, grid[0], grid[1], self.min_weight,
                              want_nhwc=True, want_nchw=want_nchw)
+        fa = engine.carried_amax(fused)
+        if track and fa is not None and self.min_weight > 0:
+            out["bev_nhwc"]._amax = fa
         ret = {"bev_densities": out["dens"], "bev_coords": xy}
         if want_nchw:
             ret["bev_features"] = out["bev_nchw"]

@@ -98,7 +98,7 @@ __global__ void __launch_bounds__(256) zmlp_concat_kernel(const float* __restric
                                                           const float* __restrict__ b1,
                                                           const float* __restrict__ w2,
                                                           const float* __restrict__ b2,
-                                                          float* __restrict__ out) {
+                                                          float* __restrict__ out, unsigned* __restrict__ amax_out) {
   __shared__ float s_w1[64], s_b1[64], s_b2[32];
   __shared__ float s_w2[32 * 65];  // padded: lane j reads row j
   for (int i = threadIdx.x; i < 64; i += blockDim.x) { s_w1[i] = w1[i]; s_b1[i] = b1[i]; }
@@ -107,11 +107,16 @@ __global__ void __launch_bounds__(256) zmlp_concat_kernel(const float* __restric
   __syncthreads();
   const int lane = threadIdx.x & 31;
   const int warps_per_block = blockDim.x >> 5;
+  float amx = 0.0f;
   for (int pt = blockIdx.x * warps_per_block + (threadIdx.x >> 5); pt < NP;
        pt += gridDim.x * warps_per_block) {
     const float4* src = reinterpret_cast<const float4*>(feats + (size_t)pt * C);
     float4* dst = reinterpret_cast<float4*>(out + (size_t)pt * (C + 32));
-    for (int c = lane; c < C / 4; c += 32) dst[c] = __ldg(src + c);
+    for (int c = lane; c < C / 4; c += 32) {
+      const float4 v = __ldg(src + c);
+      dst[c] = v;
+      amx = fmaxf(fmaxf(amx, fmaxf(fabsf(v.x), fabsf(v.y))), fmaxf(fabsf(v.z), fabsf(v.w)));
+    }
     const float zz = z[pt];
     // hidden layer: lane computes h[lane], h[lane+32]  (Linear(1,64) + ReLU)
     const float h0 = fmaxf(__fmaf_rn(s_w1[lane], zz, s_b1[lane]), 0.0f);
@@ -122,7 +127,14 @@ __global__ void __launch_bounds__(256) zmlp_concat_kernel(const float* __restric
     for (int k = 0; k < 32; ++k) acc = __fmaf_rn(s_w2[lane * 65 + k], __shfl_sync(0xffffffffu, h0, k), acc);
 #pragma unroll
     for (int k = 0; k < 32; ++k) acc = __fmaf_rn(s_w2[lane * 65 + 32 + k], __shfl_sync(0xffffffffu, h1, k), acc);
-    out[(size_t)pt * (C + 32) + C + lane] = fmaxf(acc + s_b2[lane], 0.0f);
+    const float zf = fmaxf(acc + s_b2[lane], 0.0f);
+    out[(size_t)pt * (C + 32) + C + lane] = zf;
+    amx = fmaxf(amx, zf);
+  }
+  // max|out| travels with the tensor: the fusion conv derives its 3xFP16 operand scale from it (no amax pass)
+  if (amax_out) {
+    amx = warp_max(amx);
+    if (lane == 0 && amx > 0.0f) atomicMax(amax_out, __float_as_uint(amx));
   }
 }
 
@@ -248,10 +260,18 @@ extern "C" int creste_points_to_voxels(const float* pts, long long NP, const flo
 extern "C" int creste_zmlp_concat(const float* feats, const float* z, int NP, int C, const float* w1,
                                   const float* b1, const float* w2, const float* b2, float* out,
                                   void* stream) {
+  return creste_zmlp_concat_ex(feats, z, NP, C, w1, b1, w2, b2, out, nullptr, stream);
+}
+
+extern "C" int creste_zmlp_concat_ex(const float* feats, const float* z, int NP, int C, const float* w1,
+                                     const float* b1, const float* w2, const float* b2, float* out,
+                                     float* amax_out, void* stream) {
   CRESTE_CHECK_ARG(feats && z && w1 && b1 && w2 && b2 && out, "creste_zmlp_concat: null pointer");
   CRESTE_CHECK_ARG(NP > 0 && C > 0 && C % 4 == 0, "creste_zmlp_concat: C must be a multiple of 4");
+  if (amax_out) CRESTE_CUDA(cudaMemsetAsync(amax_out, 0, sizeof(float), (cudaStream_t)stream));
   const int blocks = min(ceil_div(NP, 8), 148 * 8);
-  zmlp_concat_kernel<<<blocks, 256, 0, (cudaStream_t)stream>>>(feats, z, NP, C, w1, b1, w2, b2, out);
+  zmlp_concat_kernel<<<blocks, 256, 0, (cudaStream_t)stream>>>(feats, z, NP, C, w1, b1, w2, b2, out,
+                                                             (unsigned*)amax_out);
   return launch_check("zmlp_concat_kernel");
 }
 

@@ -103,13 +103,14 @@ def points_to_voxels(points, lidar2map, voxel):
     return xy
 
 
-def zmlp_concat(feats_nhwc, z, w1, b1, w2, b2):
-    """feats NHWC [...,C] + MLP(z) -> NHWC [...,C+32] (reference splat_projection.py:152-158)."""
+def zmlp_concat(feats_nhwc, z, w1, b1, w2, b2, amax_out=None):
+    """feats NHWC [...,C] + MLP(z) -> NHWC [...,C+32] (reference splat_projection.py:152-158).
+    amax_out: optional device float[1] that receives max|out|."""
     Cc = feats_nhwc.shape[-1]
     NP = feats_nhwc.numel() // Cc
     out = torch.empty(*feats_nhwc.shape[:-1], Cc + 32, device=feats_nhwc.device)
-    check(lib().creste_zmlp_concat(ptr(feats_nhwc), ptr(z.contiguous()), NP, Cc, ptr(w1), ptr(b1),
-                                   ptr(w2), ptr(b2), ptr(out), stream()), "creste_zmlp_concat")
+    check(lib().creste_zmlp_concat_ex(ptr(feats_nhwc), ptr(z.contiguous()), NP, Cc, ptr(w1), ptr(b1),
+                                      ptr(w2), ptr(b2), ptr(out), ptr(amax_out), stream()), "creste_zmlp_concat")
     return out
 
 
@@ -1209,10 +1210,10 @@ def _t_frustum_to_bev(depth, p2p, pc_range, voxel):
     return _RAW["frustum_to_bev"](depth, p2p, pc_range, voxel)
 
 
-def _t_zmlp_concat(feats_nhwc, z, w1, b1, w2, b2):
+def _t_zmlp_concat(feats_nhwc, z, w1, b1, w2, b2, amax_out=None):
     if _tracing():
         return torch.ops.creste.zmlp_concat(feats_nhwc, z, w1, b1, w2, b2)
-    return _RAW["zmlp_concat"](feats_nhwc, z, w1, b1, w2, b2)
+    return _RAW["zmlp_concat"](feats_nhwc, z, w1, b1, w2, b2, amax_out)
 
 
 def _t_splat_soft(xy, feats_nhwc, mask, H, W, min_weight=1.0, want_nhwc=True, want_nchw=True, want_idx=False):

@@ -81,6 +81,9 @@ int creste_frustum_to_bev(const float* depth, const float* p2p, int N, int Hs, i
  *   feats NHWC [NP, C]; z [NP]; w1[64], b1[64], w2[32,64], b2[32]; out NHWC [NP, C+32]. */
 int creste_zmlp_concat(const float* feats, const float* z, int NP, int C, const float* w1,
                        const float* b1, const float* w2, const float* b2, float* out, void* stream);
+/* the same with max|out| published to amax_out (DEVICE float[1] or NULL) for the fusion conv's operand scale */
+int creste_zmlp_concat_ex(const float* feats, const float* z, int NP, int C, const float* w1, const float* b1,
+                          const float* w2, const float* b2, float* out, float* amax_out, void* stream);
 
 /* Camera2World.forward as a stand-alone op, creste/models/blocks/splat_projection.py:19-51:
  * xyz[n, :, v, u] = (p2p[n] @ [u*d, v*d, d, 1])[:3] (K = 4 in-order FMA chain, the CPU bmm order).

@@ -20,6 +20,8 @@
 //   ce_depth_bwd, masked_mse_bwd   loss gradients
 //
 // All activations NHWC fp32.  The reductions of this file are two-stage with a fixed order (no atomics).
+#include <stdlib.h>
+
 #include "common.cuh"
 
 namespace creste {
@@ -394,6 +396,83 @@ __global__ void __launch_bounds__(256) dwconv_wgrad_kernel(const float* __restri
   }
 }
 
+// Tiled form (round 2b): the kernel above keeps R*R float4 accumulators per thread (100+ registers at R = 5, two CTAs
+// per SM), re-derives three 64-bit divisions per pixel, reads every tap from global memory and idles most lanes of the
+// second channel block when C is not a multiple of 128 -- 650 us per 5x5 layer at B = 16, 15x its HBM floor.  Here a
+// CTA stages the x tile (with halo, zero outside the image) and the g tile of 8 x TW outputs x 32 channels in shared
+// memory; thread (tap, 4-channel group, row lane) accumulates g * x over its rows of the tile in fp32 (<= 256 pixels),
+// the row lanes are added in a fixed order and the tile's [R*R][32] partial goes out in double;
+// reduce_parts_kernel adds the tiles in its fixed order.
+template <int R, int STRIDE>
+__global__ void __launch_bounds__(256) dwconv_wgrad_tile_kernel(const float* __restrict__ x, const float* __restrict__ g,
+                                                                int H, int W, int C, int pt, int pl, int P, int Q,
+                                                                int tiles_x, double* __restrict__ part) {
+  constexpr int TH = 8, TW = STRIDE == 1 ? 32 : 16, CG = 8;
+  constexpr int IH = (TH - 1) * STRIDE + R, IW = (TW - 1) * STRIDE + R;
+  constexpr int RR = R * R;
+  constexpr int PG = 32 / RR >= 1 ? 32 / RR : 1;      // row lanes per (tap, channel group): 3 at R = 3, 1 at R = 5
+  extern __shared__ __align__(16) float4 wg_smem[];
+  float4* xt = wg_smem;                                // [IH][IW][CG]
+  float4* gt = wg_smem + IH * IW * CG;                 // [TH][TW][CG]
+  float4* red = gt + TH * TW * CG;                     // [PG][RR][CG]
+  const int C4 = C / 4;
+  const int n = blockIdx.y;
+  const int tx = blockIdx.x % tiles_x, ty = blockIdx.x / tiles_x;
+  const int oy0 = ty * TH, ox0 = tx * TW;
+  const int cg0 = blockIdx.z * CG;
+  const int cgs = min(CG, C4 - cg0);
+  const int tid = threadIdx.x;
+  const float4* xn = reinterpret_cast<const float4*>(x + (size_t)n * H * W * C);
+  const float4* gn = reinterpret_cast<const float4*>(g + (size_t)n * P * Q * C);
+  const int iy0 = oy0 * STRIDE - pt, ix0 = ox0 * STRIDE - pl;
+  for (int i = tid; i < IH * IW * CG; i += 256) {
+    const int c = i % CG, p = i / CG;
+    const int ix = ix0 + p % IW, iy = iy0 + p / IW;
+    float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+    if (c < cgs && iy >= 0 && iy < H && ix >= 0 && ix < W) v = __ldg(xn + ((size_t)iy * W + ix) * C4 + cg0 + c);
+    xt[i] = v;
+  }
+  for (int i = tid; i < TH * TW * CG; i += 256) {
+    const int c = i % CG, p = i / CG;
+    const int ox = ox0 + p % TW, oy = oy0 + p / TW;
+    float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+    if (c < cgs && oy < P && ox < Q) v = __ldg(gn + ((size_t)oy * Q + ox) * C4 + cg0 + c);
+    gt[i] = v;
+  }
+  __syncthreads();
+  const int c = tid % CG, t2 = tid / CG;               // t2 = pg * RR + tap
+  const int tap = t2 % RR, pg = t2 / RR;
+  if (pg < PG) {
+    const int r = tap / R, s_ = tap - r * R;
+    float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
+    for (int ly = pg; ly < TH; ly += PG) {
+      const float4* xr = xt + ((size_t)(ly * STRIDE + r) * IW + s_) * CG + c;
+      const float4* gr = gt + (size_t)ly * TW * CG + c;
+#pragma unroll 8
+      for (int lx = 0; lx < TW; ++lx) {
+        const float4 gv = gr[lx * CG], xv = xr[(size_t)lx * STRIDE * CG];
+        acc.x = fmaf(gv.x, xv.x, acc.x); acc.y = fmaf(gv.y, xv.y, acc.y);
+        acc.z = fmaf(gv.z, xv.z, acc.z); acc.w = fmaf(gv.w, xv.w, acc.w);
+      }
+    }
+    red[(pg * RR + tap) * CG + c] = acc;
+  }
+  __syncthreads();
+  if (tid < RR * CG) {
+    const int cc = tid % CG, tp = tid / CG;
+    if (cc < cgs) {
+      const float4 a0 = red[tp * CG + cc];
+      double d0 = (double)a0.x, d1 = (double)a0.y, d2 = (double)a0.z, d3 = (double)a0.w;
+      for (int l = 1; l < PG; ++l) {
+        const float4 a = red[(l * RR + tp) * CG + cc];
+        d0 += (double)a.x; d1 += (double)a.y; d2 += (double)a.z; d3 += (double)a.w;
+      }
+      double* dst = part + (((size_t)n * gridDim.x + blockIdx.x) * RR + tp) * C + (size_t)(cg0 + cc) * 4;
+      dst[0] = d0; dst[1] = d1; dst[2] = d2; dst[3] = d3;
+    }
+  }
+}
+
 // ------------------------------------------------------------------- strided dense wgrad (C == 4)
 // thread -> (tap, k); part[bx][(tap*4 + c)*K + k] = sum over the block's output pixels.
 __global__ void __launch_bounds__(1024) wgrad_strided_c4_kernel(const float* __restrict__ x,
@@ -610,7 +689,10 @@ extern "C" int creste_dwconv_dgrad(const float* g, const float* w, int N, int H,
 }
 
 extern "C" size_t creste_dwconv_wgrad_workspace_bytes(int N, int C, int R, int P, int Q) {
-  return (size_t)reduce_pb((long long)N * P * Q, 1) * R * R * C * sizeof(double);
+  // the tiled kernel writes one [R*R][C] partial per 8 x 16 (stride 2) / 8 x 32 (stride 1) output tile: size for 8 x 16
+  const size_t tiled = (size_t)N * ceil_div(P, 8) * ceil_div(Q, 16) * R * R * C * sizeof(double);
+  const size_t flat = (size_t)reduce_pb((long long)N * P * Q, 1) * R * R * C * sizeof(double);
+  return tiled > flat ? tiled : flat;
 }
 
 extern "C" int creste_dwconv_wgrad(const float* x, const float* g, int N, int H, int W, int C, int R, int stride,
@@ -619,6 +701,30 @@ extern "C" int creste_dwconv_wgrad(const float* x, const float* g, int N, int H,
   CRESTE_CHECK_ARG(x && g && dw && ws && dw_geom_ok(N, H, W, C, R, stride, P, Q), "creste_dwconv_wgrad: bad args");
   CRESTE_CHECK_ARG(ws_bytes >= creste_dwconv_wgrad_workspace_bytes(N, C, R, P, Q), "creste_dwconv_wgrad: workspace");
   cudaStream_t st = (cudaStream_t)stream;
+  if (!getenv("CRESTE_NO_DWWGRAD_TILE")) {
+    const int TW = stride == 1 ? 32 : 16;
+    const int tiles_x = ceil_div(Q, TW), tiles = tiles_x * ceil_div(P, 8);
+    const int IH = 7 * stride + R, IW = (TW - 1) * stride + R;
+    const int PG = 32 / (R * R) >= 1 ? 32 / (R * R) : 1;
+    const size_t smem = ((size_t)IH * IW * 8 + (size_t)8 * TW * 8 + (size_t)PG * R * R * 8) * sizeof(float4);
+    const dim3 tgrid(tiles, N, ceil_div(C / 4, 8));
+#define CRESTE_DWWG(RR_, SS_)                                                                                          \
+    do {                                                                                                               \
+      CRESTE_CUDA(cudaFuncSetAttribute(dwconv_wgrad_tile_kernel<RR_, SS_>, cudaFuncAttributeMaxDynamicSharedMemorySize, \
+                                       (int)smem));                                                                    \
+      dwconv_wgrad_tile_kernel<RR_, SS_><<<tgrid, 256, smem, st>>>(x, g, H, W, C, pad_t, pad_l, P, Q, tiles_x,           \
+                                                                  (double*)ws);                                        \
+    } while (0)
+    if (R == 3 && stride == 1) CRESTE_DWWG(3, 1);
+    else if (R == 3) CRESTE_DWWG(3, 2);
+    else if (stride == 1) CRESTE_DWWG(5, 1);
+    else CRESTE_DWWG(5, 2);
+#undef CRESTE_DWWG
+    int rc = launch_check("dwconv_wgrad_tile_kernel");
+    if (rc) return rc;
+    reduce_parts_kernel<float><<<ceil_div(R * R * C, 32), 256, 0, st>>>((const double*)ws, N * tiles, R * R * C, 1, 1.0, dw);
+    return launch_check("reduce_parts_kernel");
+  }
   const int PB = reduce_pb((long long)N * P * Q, 1);
   const dim3 grid(PB, ceil_div(C, 128), 1);
   if (R == 3) dwconv_wgrad_kernel<3><<<grid, 256, 0, st>>>(x, g, N, H, W, C, stride, pad_t, pad_l, P, Q, (double*)ws);

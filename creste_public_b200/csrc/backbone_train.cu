@@ -336,6 +336,75 @@ __global__ void __launch_bounds__(256) dwconv_dgrad_kernel(const float* __restri
   }
 }
 
+// Stride-1 data gradient from a shared-memory tile of g (with halo, zero outside the output grid): the same (r, s)
+// ascending FMA order per element as dwconv_dgrad_kernel, so the results are bit-identical to it; 4 adjacent outputs
+// per thread, taps without bounds checks.
+template <int R>
+__global__ void __launch_bounds__(256) dwconv_dgrad_tile_kernel(const float* __restrict__ g, const float* __restrict__ w,
+                                                                int H, int W, int C, int pt, int pl, int P, int Q,
+                                                                int tiles_x, float* __restrict__ dx) {
+  constexpr int TH = 8, TW = 32, XB = 4, CG = 8;
+  constexpr int IH = TH + R - 1, IW = TW + R - 1, NC = XB + R - 1;
+  constexpr int UNITS = TH * (TW / XB);
+  extern __shared__ __align__(16) float4 dg_smem[];
+  float4* tile = dg_smem;                          // g rows iy0 + pt - (R-1) .. , cols ix0 + pl - (R-1) ..
+  float4* wsm = dg_smem + IH * IW * CG;            // [R*R][CG]
+  const int C4 = C / 4;
+  const int n = blockIdx.y;
+  const int tx = blockIdx.x % tiles_x, ty = blockIdx.x / tiles_x;
+  const int iy0 = ty * TH, ix0 = tx * TW;
+  const int cg0 = blockIdx.z * CG;
+  const int cgs = min(CG, C4 - cg0);
+  const int tid = threadIdx.x;
+  const float4* gn = reinterpret_cast<const float4*>(g + (size_t)n * P * Q * C);
+  const int p0 = iy0 + pt - (R - 1), q0 = ix0 + pl - (R - 1);
+  for (int i = tid; i < IH * IW * CG; i += 256) {
+    const int c = i % CG, e = i / CG;
+    const int q = q0 + e % IW, p = p0 + e / IW;
+    float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+    if (c < cgs && p >= 0 && p < P && q >= 0 && q < Q) v = __ldg(gn + ((size_t)p * Q + q) * C4 + cg0 + c);
+    tile[i] = v;
+  }
+  for (int i = tid; i < R * R * CG; i += 256) {
+    const int c = i % CG, t = i / CG;
+    wsm[i] = c < cgs ? __ldg(reinterpret_cast<const float4*>(w) + (size_t)t * C4 + cg0 + c) : make_float4(0.f, 0.f, 0.f, 0.f);
+  }
+  __syncthreads();
+  const int c = tid % CG, ul = tid / CG;
+  if (c >= cgs) return;
+#pragma unroll 1
+  for (int u = ul; u < UNITS; u += 32) {
+    const int ly = u / (TW / XB), lx = (u - ly * (TW / XB)) * XB;
+    const int iy = iy0 + ly;
+    if (iy >= H || ix0 + lx >= W) continue;
+    float4 acc[XB];
+#pragma unroll
+    for (int b = 0; b < XB; ++b) acc[b] = make_float4(0.f, 0.f, 0.f, 0.f);
+#pragma unroll
+    for (int r = 0; r < R; ++r) {
+      // tap (r, s) of output (ly, lx + b) reads g at tile row ly + (R-1) - r, tile col lx + b + (R-1) - s
+      const float4* row = tile + ((size_t)(ly + R - 1 - r) * IW + lx) * CG + c;
+      float4 col[NC];
+#pragma unroll
+      for (int k = 0; k < NC; ++k) col[k] = row[(size_t)k * CG];
+#pragma unroll
+      for (int s_ = 0; s_ < R; ++s_) {
+        const float4 k4 = wsm[(r * R + s_) * CG + c];
+#pragma unroll
+        for (int b = 0; b < XB; ++b) {
+          const float4 v = col[b + R - 1 - s_];
+          acc[b].x = fmaf(v.x, k4.x, acc[b].x); acc[b].y = fmaf(v.y, k4.y, acc[b].y);
+          acc[b].z = fmaf(v.z, k4.z, acc[b].z); acc[b].w = fmaf(v.w, k4.w, acc[b].w);
+        }
+      }
+    }
+#pragma unroll
+    for (int b = 0; b < XB; ++b)
+      if (ix0 + lx + b < W)
+        reinterpret_cast<float4*>(dx + ((size_t)(n * (size_t)H + iy) * W + ix0 + lx + b) * C)[cg0 + c] = acc[b];
+  }
+}
+
 // part[bx][tap][c] = sum over the block's output pixels of g[pix,c] * x[shifted pix,c]; per-thread
 // fp32 partial sums over <= a few hundred pixels, the cross-lane / cross-block stages in double.
 template <int R>
@@ -682,6 +751,19 @@ extern "C" int creste_dwconv_dgrad(const float* g, const float* w, int N, int H,
                                    int pad_t, int pad_l, int P, int Q, float* dx, void* stream) {
   CRESTE_CHECK_ARG(g && w && dx && dw_geom_ok(N, H, W, C, R, stride, P, Q), "creste_dwconv_dgrad: bad args");
   cudaStream_t st = (cudaStream_t)stream;
+  if (stride == 1 && !getenv("CRESTE_NO_DWDGRAD_TILE")) {
+    const int tiles_x = ceil_div(W, 32), tiles = tiles_x * ceil_div(H, 8);
+    const size_t smem = ((size_t)(8 + R - 1) * (32 + R - 1) * 8 + (size_t)R * R * 8) * sizeof(float4);
+    const dim3 tgrid(tiles, N, ceil_div(C / 4, 8));
+    if (R == 3) {
+      CRESTE_CUDA(cudaFuncSetAttribute(dwconv_dgrad_tile_kernel<3>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+      dwconv_dgrad_tile_kernel<3><<<tgrid, 256, smem, st>>>(g, w, H, W, C, pad_t, pad_l, P, Q, tiles_x, dx);
+    } else {
+      CRESTE_CUDA(cudaFuncSetAttribute(dwconv_dgrad_tile_kernel<5>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+      dwconv_dgrad_tile_kernel<5><<<tgrid, 256, smem, st>>>(g, w, H, W, C, pad_t, pad_l, P, Q, tiles_x, dx);
+    }
+    return launch_check("dwconv_dgrad_tile_kernel");
+  }
   const int grid = ELT_GRID((long long)N * H * W * (C / 4));
   if (R == 3) dwconv_dgrad_kernel<3><<<grid, 256, 0, st>>>(g, w, N, H, W, C, stride, pad_t, pad_l, P, Q, dx);
   else dwconv_dgrad_kernel<5><<<grid, 256, 0, st>>>(g, w, N, H, W, C, stride, pad_t, pad_l, P, Q, dx);

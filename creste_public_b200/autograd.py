@@ -609,7 +609,9 @@ class BNActFn(Function):
             engine.mark_written([bn.running_mean, bn.running_var])
         ctx.save_for_backward(x, ab, mi)
         ctx.act, ctx.M = act, M
-        return ops.chan_affine_act(x, ab[0], ab[1], act)
+        # 3xFP16 training: the affine / activation pass also measures max|y|, so the conv that consumes y (and the
+        # data- / weight-gradient convs that consume dx below) split their operand without an amax pass
+        return ops.chan_affine_act(x, ab[0], ab[1], act, want_amax=(engine.get_precision() == "3xfp16"))
 
     @staticmethod
     @once
@@ -617,7 +619,8 @@ class BNActFn(Function):
         x, ab, mi = ctx.saved_tensors
         gu, sums = ops.bn_act_bwd(g, x, ab[0], ab[1], ctx.act)
         out4 = ops.bn_bwd_finalize(sums, ab, mi, ctx.M)
-        dx = ops.chan_axpby(gu, x, ab[0], out4[2], out4[3]) if ctx.needs_input_grad[0] else None
+        dx = (ops.chan_axpby(gu, x, ab[0], out4[2], out4[3], want_amax=(engine.get_precision() == "3xfp16"))
+              if ctx.needs_input_grad[0] else None)
         return dx, out4[0], out4[1], None, None
 
 

@@ -53,9 +53,11 @@ __device__ __forceinline__ float act_grad(float u, int act) {
 __global__ void __launch_bounds__(256) chan_affine_act_kernel(const float* __restrict__ x,
                                                               const float* __restrict__ a,
                                                               const float* __restrict__ b, int C, long long n,
-                                                              int act, float* __restrict__ y) {
+                                                              int act, float* __restrict__ y,
+                                                              unsigned* __restrict__ amax_bits) {
   const long long nv = n / 4;
   const int CV = C / 4;
+  float m = 0.f;
   for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < nv;
        i += (long long)gridDim.x * blockDim.x) {
     const int c = (int)(i % CV) * 4;
@@ -65,6 +67,12 @@ __global__ void __launch_bounds__(256) chan_affine_act_kernel(const float* __res
     v.x = act_fwd(fmaf(v.x, aa.x, bb.x), act); v.y = act_fwd(fmaf(v.y, aa.y, bb.y), act);
     v.z = act_fwd(fmaf(v.z, aa.z, bb.z), act); v.w = act_fwd(fmaf(v.w, aa.w, bb.w), act);
     reinterpret_cast<float4*>(y)[i] = v;
+    m = fmaxf(fmaxf(m, fmaxf(fabsf(v.x), fabsf(v.y))), fmaxf(fabsf(v.z), fabsf(v.w)));
+  }
+  // max|y| for the consumer's 3xFP16 operand scale (the same reduction as f16_amax_kernel: same bits)
+  if (amax_bits) {
+    m = warp_max(m);
+    if ((threadIdx.x & 31) == 0 && m > 0.f) atomicMax(amax_bits, __float_as_uint(m));
   }
 }
 
@@ -72,9 +80,10 @@ __global__ void __launch_bounds__(256) chan_affine_act_kernel(const float* __res
 __global__ void __launch_bounds__(256) chan_axpby_kernel(const float* __restrict__ u, const float* __restrict__ x,
                                                          const float* __restrict__ p, const float* __restrict__ q,
                                                          const float* __restrict__ r, int C, long long n,
-                                                         float* __restrict__ out) {
+                                                         float* __restrict__ out, unsigned* __restrict__ amax_bits) {
   const long long nv = n / 4;
   const int CV = C / 4;
+  float m = 0.f;
   for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < nv;
        i += (long long)gridDim.x * blockDim.x) {
     const int c = (int)(i % CV) * 4;
@@ -87,6 +96,11 @@ __global__ void __launch_bounds__(256) chan_axpby_kernel(const float* __restrict
     o.x = fmaf(uv.x, pp.x, fmaf(xv.x, qq.x, rr.x)); o.y = fmaf(uv.y, pp.y, fmaf(xv.y, qq.y, rr.y));
     o.z = fmaf(uv.z, pp.z, fmaf(xv.z, qq.z, rr.z)); o.w = fmaf(uv.w, pp.w, fmaf(xv.w, qq.w, rr.w));
     reinterpret_cast<float4*>(out)[i] = o;
+    m = fmaxf(fmaxf(m, fmaxf(fabsf(o.x), fabsf(o.y))), fmaxf(fabsf(o.z), fabsf(o.w)));
+  }
+  if (amax_bits) {
+    m = warp_max(m);
+    if ((threadIdx.x & 31) == 0 && m > 0.f) atomicMax(amax_bits, __float_as_uint(m));
   }
 }
 
@@ -705,7 +719,17 @@ extern "C" int creste_chan_affine_act(const float* x, const float* a, const floa
                                       float* y, void* stream) {
   CRESTE_CHECK_ARG(x && y && npix > 0 && C > 0 && C % 4 == 0 && act >= 0 && act <= 2, "creste_chan_affine_act: bad args");
   const long long n = npix * C;
-  chan_affine_act_kernel<<<ELT_GRID(n / 4), 256, 0, (cudaStream_t)stream>>>(x, a, b, C, n, act, y);
+  chan_affine_act_kernel<<<ELT_GRID(n / 4), 256, 0, (cudaStream_t)stream>>>(x, a, b, C, n, act, y, nullptr);
+  return launch_check("chan_affine_act_kernel");
+}
+
+extern "C" int creste_chan_affine_act_amax(const float* x, const float* a, const float* b, long long npix, int C,
+                                           int act, float* y, float* amax_out, void* stream) {
+  CRESTE_CHECK_ARG(x && y && amax_out && npix > 0 && C > 0 && C % 4 == 0 && act >= 0 && act <= 2,
+                   "creste_chan_affine_act_amax: bad args");
+  const long long n = npix * C;
+  CRESTE_CUDA(cudaMemsetAsync(amax_out, 0, 4, (cudaStream_t)stream));
+  chan_affine_act_kernel<<<ELT_GRID(n / 4), 256, 0, (cudaStream_t)stream>>>(x, a, b, C, n, act, y, (unsigned*)amax_out);
   return launch_check("chan_affine_act_kernel");
 }
 
@@ -729,7 +753,17 @@ extern "C" int creste_chan_axpby(const float* u, const float* x, const float* p,
                                  long long npix, int C, float* out, void* stream) {
   CRESTE_CHECK_ARG(u && x && p && q && r && out && npix > 0 && C > 0 && C % 4 == 0, "creste_chan_axpby: bad args");
   const long long n = npix * C;
-  chan_axpby_kernel<<<ELT_GRID(n / 4), 256, 0, (cudaStream_t)stream>>>(u, x, p, q, r, C, n, out);
+  chan_axpby_kernel<<<ELT_GRID(n / 4), 256, 0, (cudaStream_t)stream>>>(u, x, p, q, r, C, n, out, nullptr);
+  return launch_check("chan_axpby_kernel");
+}
+
+extern "C" int creste_chan_axpby_amax(const float* u, const float* x, const float* p, const float* q, const float* r,
+                                      long long npix, int C, float* out, float* amax_out, void* stream) {
+  CRESTE_CHECK_ARG(u && x && p && q && r && out && amax_out && npix > 0 && C > 0 && C % 4 == 0,
+                   "creste_chan_axpby_amax: bad args");
+  const long long n = npix * C;
+  CRESTE_CUDA(cudaMemsetAsync(amax_out, 0, 4, (cudaStream_t)stream));
+  chan_axpby_kernel<<<ELT_GRID(n / 4), 256, 0, (cudaStream_t)stream>>>(u, x, p, q, r, C, n, out, (unsigned*)amax_out);
   return launch_check("chan_axpby_kernel");
 }
 

@@ -1172,6 +1172,17 @@ static int wg_split(const float* x, size_t numel, int C, void* hi, void* lo, flo
   return launch_check("f16_split_kernel");
 }
 
+// the same with max|x| already known (published by the kernel that produced x): no amax pass, no scale kernel
+static int wg_split_known(const float* x, size_t numel, int C, void* hi, void* lo, float* scal, const float* amax,
+                          cudaStream_t st) {
+  const long long n4 = (long long)(numel / 4);
+  long long blocks = (n4 + 255) / 256;
+  if (blocks > 148 * 16) blocks = 148 * 16;
+  f16_split_kernel<<<(int)blocks, 256, 0, st>>>((const float4*)x, nullptr, C, 1, n4, scal, (const unsigned*)amax,
+                                                (uint2*)hi, (uint2*)lo);
+  return launch_check("f16_split_kernel");
+}
+
 static void wg_pick_box(int P, int Q, int* wbox, int* hbox) {
   int best_w = 8;
   double best = -1.0;
@@ -1228,6 +1239,11 @@ size_t wgrad_tc_workspace_bytes(const creste_conv_desc* d) {
   const WgPlan w = wg_plan(d);
   return 2 * align_up(w.nx * 2, 1024) + 2 * align_up(w.ng * 2, 1024) + 1024 +
          (size_t)w.splits * d->R * d->S * d->C * d->K * sizeof(float);
+}
+
+int f16_split_known_launch(const float* x, size_t numel, void* hi, void* lo, float* scal, const float* amax,
+                           cudaStream_t st) {
+  return wg_split_known(x, numel, 4, hi, lo, scal, amax, st);
 }
 
 static int wgrad_tc_core(const creste_conv_desc* d, const void* x_hi, const void* x_lo, const float* x_scal,
@@ -1406,6 +1422,11 @@ extern "C" int creste_conv2d_wgrad_tc_presplit(const creste_conv_desc* d, const 
 extern "C" int creste_f16_split(const float* x, long long numel, void* hi, void* lo, float* scal, void* stream) {
   if (!x || !hi || !lo || !scal || numel <= 0 || (numel & 7)) { creste::set_error("creste_f16_split: bad args (numel %% 8 == 0)"); return CRESTE_ERR_ARG; }
   return creste::f16_split_launch(x, (size_t)numel, hi, lo, scal, (cudaStream_t)stream);
+}
+extern "C" int creste_f16_split_amax(const float* x, long long numel, const float* amax, void* hi, void* lo, float* scal,
+                                     void* stream) {
+  if (!x || !amax || !hi || !lo || !scal || numel <= 0 || (numel & 7)) { creste::set_error("creste_f16_split_amax: bad args (numel %% 8 == 0)"); return CRESTE_ERR_ARG; }
+  return creste::f16_split_known_launch(x, (size_t)numel, hi, lo, scal, amax, (cudaStream_t)stream);
 }
 
 /* 3xFP16 weight operand of creste_conv2d (precision 4) in one launch: logical w[k][c][r][s] read through element

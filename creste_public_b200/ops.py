@@ -773,11 +773,29 @@ def chan_moments(x):
     return out
 
 
-def chan_affine_act(x, a, b, act):
-    """y = act(x * a[c] + b[c]), act in {'none', 'relu', 'swish'}."""
+def publish_amax(t, amax):
+    """Attach the exact max|t| (device float[1]) the producing kernel measured; split_f16 then skips its amax pass.
+    Valid while the tensor is not written again (checked through torch's version counter)."""
+    t._amax_exact = (amax, t._version)
+    return t
+
+
+def published_amax(t):
+    rec = getattr(t, "_amax_exact", None)
+    return rec[0] if rec is not None and rec[1] == t._version else None
+
+
+def chan_affine_act(x, a, b, act, want_amax=False):
+    """y = act(x * a[c] + b[c]), act in {'none', 'relu', 'swish'}.  want_amax: the kernel also measures max|y| and
+    the result carries it (publish_amax) for the 3xFP16 operand split of the conv that consumes y."""
     x = x.contiguous()
     npix, Cc = _npix_c(x)
     y = torch.empty_like(x)
+    if want_amax:
+        amax = torch.empty(1, device=x.device)
+        check(lib().creste_chan_affine_act_amax(ptr(x), ptr(a), ptr(b), C.c_longlong(npix), Cc, ACT[act], ptr(y),
+                                                ptr(amax), stream()), "creste_chan_affine_act_amax")
+        return publish_amax(y, amax)
     check(lib().creste_chan_affine_act(ptr(x), ptr(a), ptr(b), C.c_longlong(npix), Cc, ACT[act], ptr(y),
                                        stream()), "creste_chan_affine_act")
     return y
@@ -797,11 +815,17 @@ def bn_act_bwd(g, x, a, b, act):
     return (gu if gu is not None else g), sums
 
 
-def chan_axpby(u, x, p, q, r):
-    """out = u*p[c] + x*q[c] + r[c]."""
+def chan_axpby(u, x, p, q, r, want_amax=False):
+    """out = u*p[c] + x*q[c] + r[c].  want_amax: as in chan_affine_act."""
     u, x = u.contiguous(), x.contiguous()
     npix, Cc = _npix_c(x)
     out = torch.empty_like(x)
+    if want_amax:
+        amax = torch.empty(1, device=x.device)
+        check(lib().creste_chan_axpby_amax(ptr(u), ptr(x), ptr(p.contiguous()), ptr(q.contiguous()), ptr(r.contiguous()),
+                                           C.c_longlong(npix), Cc, ptr(out), ptr(amax), stream()),
+              "creste_chan_axpby_amax")
+        return publish_amax(out, amax)
     check(lib().creste_chan_axpby(ptr(u), ptr(x), ptr(p.contiguous()), ptr(q.contiguous()), ptr(r.contiguous()),
                                   C.c_longlong(npix), Cc, ptr(out), stream()), "creste_chan_axpby")
     return out
@@ -967,12 +991,20 @@ def conv2d_wgrad_tc(x_nhwc, g_nhwc, R, S, pad):
     return dw.view(R, S, Cc, K).permute(3, 2, 0, 1).contiguous()
 
 
+USE_PUBLISHED_AMAX = os.environ.get("CRESTE_NO_PUBLISHED_AMAX") is None     # experiment / test switch
+
+
 def split_f16(x_nhwc):
     """The 3xFP16 operand of a dense fp32 NHWC tensor (amax -> power-of-two scale -> fp16 hi / lo) as a SplitAct."""
+    amax = published_amax(x_nhwc)
     x_nhwc = x_nhwc.contiguous()
     hi = torch.empty(x_nhwc.shape, dtype=torch.float16, device=x_nhwc.device)
     lo = torch.empty_like(hi)
     scal = torch.empty(4, device=x_nhwc.device)
+    if amax is not None and USE_PUBLISHED_AMAX:     # measured by the producer: one pass, same scale, same halves
+        check(lib().creste_f16_split_amax(ptr(x_nhwc), C.c_longlong(x_nhwc.numel()), ptr(amax), ptr(hi), ptr(lo),
+                                          ptr(scal), stream()), "creste_f16_split_amax")
+        return SplitAct(hi, lo, scal, x_nhwc.shape)
     check(lib().creste_f16_split(ptr(x_nhwc), C.c_longlong(x_nhwc.numel()), ptr(hi), ptr(lo), ptr(scal), stream()),
           "creste_f16_split")
     return SplitAct(hi, lo, scal, x_nhwc.shape)

@@ -414,6 +414,12 @@ int creste_bn_bwd_finalize(const double* sums2, const float* ab, const double* m
 /* y = act(x*a[c] + b[c])  (BatchNorm affine + ReLU / swish in one pass) */
 int creste_chan_affine_act(const float* x, const float* a, const float* b, long long npix, int C, int act,
                            float* y, void* stream);
+/* the same, also publishing max|y| (DEVICE float[1], zeroed here) for the 3xFP16 operand scale of the conv that
+ * consumes y (creste_f16_split_amax): the consumer makes no amax pass.  Same reduction as the split pre-pass, same
+ * bits.  Replaces nothing in the reference (torch's cuDNN path has no operand scale); it is part of
+ * F.batch_norm + activation, creste/models/blocks/effnet.py:14-20 / efficientnet_pytorch MBConvBlock. */
+int creste_chan_affine_act_amax(const float* x, const float* a, const float* b, long long npix, int C, int act,
+                                float* y, float* amax_out, void* stream);
 /* first half of the BatchNorm(+act) backward: gu = g * act'(x*a[c]+b[c]) (written when act != 0) and
  * sums2 DEVICE double[2*C] = {sum gu}, {sum gu*x}; ws >= creste_chan_reduce_workspace_bytes(npix,C,2,1) */
 int creste_bn_act_bwd(const float* g, const float* x, const float* a, const float* b, long long npix, int C,
@@ -421,6 +427,10 @@ int creste_bn_act_bwd(const float* g, const float* x, const float* a, const floa
 /* second half: out = u*p[c] + x*q[c] + r[c] */
 int creste_chan_axpby(const float* u, const float* x, const float* p, const float* q, const float* r,
                       long long npix, int C, float* out, void* stream);
+/* the same, also publishing max|out| (DEVICE float[1], zeroed here): out is the gradient the data- / weight-gradient
+ * convs of the layer below split into their 3xFP16 operand */
+int creste_chan_axpby_amax(const float* u, const float* x, const float* p, const float* q, const float* r,
+                           long long npix, int C, float* out, float* amax_out, void* stream);
 /* depthwise R x R conv (R in {3,5}, stride in {1,2}) with the static TF-'SAME' padding of
  * efficientnet_pytorch (low pads given, high implied by P, Q): w [R*R][C]; x [N,H,W,C]; y [N,P,Q,C];
  * _dgrad: dx from g [N,P,Q,C]; _wgrad: dw [R*R][C]. */
@@ -475,6 +485,10 @@ int creste_conv2d_wgrad_tc(const creste_conv_desc* d, const float* x, const floa
  * operand is split ONCE and saved for the weight gradient, the output gradient is split ONCE for the data and the
  * weight gradient (creste_conv2d_presplit / creste_conv2d_wgrad_tc_presplit) -- 2 pre-passes per conv instead of 4. */
 int creste_f16_split(const float* x, long long numel, void* hi, void* lo, float* scal, void* stream);
+/* the same with max|x| known (DEVICE float[1], published by the kernel that produced x: creste_chan_affine_act_amax,
+ * creste_chan_axpby_amax, the amax_out of creste_conv2d): one pass instead of three launches; bit-identical halves */
+int creste_f16_split_amax(const float* x, long long numel, const float* amax, void* hi, void* lo, float* scal,
+                          void* stream);
 /* creste_conv2d_wgrad_tc on operands that are already split (same workspace size). */
 int creste_conv2d_wgrad_tc_presplit(const creste_conv_desc* d, const void* x_hi, const void* x_lo, const float* x_scal,
                                     const void* g_hi, const void* g_lo, const float* g_scal, float* dw, void* ws,

@@ -197,11 +197,37 @@ class PortLoss:
                                           "sum_cf_rewards": cr[v].sum(), "sum_opt_rewards": orr[v].sum()}
 
 
-def port_step(case, steps=1, dtype=torch.float32):
-    """dtype=float64 gives the 'exact' answer used as the yardstick of fp32 conditioning."""
+def pool_argmax(x_nchw):
+    """Per 2x2/2 window of [B,C,H,W]: (index 0..3 of the maximum in row-major window order, top-1 minus top-2)."""
+    B, Cc, H, W = x_nchw.shape
+    w = x_nchw.reshape(B, Cc, H // 2, 2, W // 2, 2).permute(0, 1, 2, 4, 3, 5).reshape(B, Cc, H // 2, W // 2, 4)
+    top = w.topk(2, dim=-1)
+    return top.indices[..., 0], top.values[..., 0] - top.values[..., 1]
+
+
+def port_step(case, steps=1, dtype=torch.float32, pool_hook=None, relu_hook=None):
+    """dtype=float64 gives the 'exact' answer used as the yardstick of fp32 conditioning.
+    pool_hook(x) -> x' | None is called on the max-pool's input (NCHW), relu_hook(i, u) -> u' | None on the input of
+    the i-th ReLU in execution order: parity tests use them to read the oracle's DISCRETE decisions (pool routing,
+    ReLU masks) and to break near-ties (two window values, or a pre-activation and zero, closer than fp32 rounding
+    noise) the way the implementation under test broke them, so that the comparison of the gradients is not a
+    comparison of coin flips."""
     net = PortMSFCN()
     net.load_state_dict(case["state_dict"])
     net.train()
+    if pool_hook is not None:
+        net.trunk[0].register_forward_pre_hook(lambda mod, args: pool_hook(args[0]))
+    if relu_hook is not None:
+        count = [0]
+
+        def pre(mod, args):
+            i = count[0]
+            count[0] += 1
+            return relu_hook(i, args[0])
+
+        for m in net.modules():
+            if isinstance(m, nn.ReLU):
+                m.register_forward_pre_hook(pre)
     if dtype != torch.float32:
         net = net.to(dtype)
         case = dict(case)

@@ -193,3 +193,45 @@ def test_training_loss_decreases(cuda):
     losses = [float(m.training_step({k: v.clone() for k, v in inputs.items()})["loss"]) for _ in range(5)]
     assert losses[-1] < losses[0], losses
     assert all(torch.isfinite(p).all() for p in m.model.parameters())
+
+
+@pytest.mark.parametrize("act", ["none", "relu", "swish"])
+def test_producers_publish_exact_amax(cuda, act):
+    """chan_affine_act / chan_axpby with want_amax: same output bits as without, the published maximum equals
+    max|out| exactly, and split_f16 from the published maximum gives the same halves and scale as its own amax pass."""
+    from creste_public_b200 import ops
+    g = np.random.default_rng(7)
+    C = 144
+    x, u = _t(g, 2, 11, 13, C, scale=3.0).to(cuda), _t(g, 2, 11, 13, C).to(cuda)
+    a, b, r = _t(g, C).to(cuda), _t(g, C).to(cuda), _t(g, C).to(cuda)
+    for plain, pub in ((ops.chan_affine_act(x, a, b, act), ops.chan_affine_act(x, a, b, act, want_amax=True)),
+                       (ops.chan_axpby(u, x, a, b, r), ops.chan_axpby(u, x, a, b, r, want_amax=True))):
+        assert torch.equal(plain, pub)
+        am = ops.published_amax(pub)
+        assert am is not None and ops.published_amax(plain) is None
+        assert float(am) == float(pub.abs().max())
+        s_pub, s_own = ops.split_f16(pub), ops.split_f16(plain)
+        assert torch.equal(s_pub.hi, s_own.hi) and torch.equal(s_pub.lo, s_own.lo)
+        assert torch.equal(s_pub.scal[:2], s_own.scal[:2])
+        pub.mul_(2.0)                                    # written again: the record is stale and must not be used
+        assert ops.published_amax(pub) is None
+
+
+def test_training_step_identical_with_published_amax(cuda):
+    """The stage-1 step with the producers' published maxima (no amax passes in front of the tensor-core convs) is
+    bit-identical to the step that measures every operand maximum in its own pass."""
+    from creste_public_b200 import engine, ops
+    case = do.make_case()
+    old = engine.get_precision()
+    engine.set_precision("3xfp16")
+    try:
+        a = ours_step(case, device=cuda)
+        ops.USE_PUBLISHED_AMAX = False
+        b = ours_step(case, device=cuda)
+    finally:
+        ops.USE_PUBLISHED_AMAX = True
+        engine.set_precision(old)
+    assert a["loss"] == b["loss"]
+    assert np.array_equal(a["logits"], b["logits"])
+    for k in a["grads"]:
+        assert np.array_equal(a["grads"][k], b["grads"][k]), k

@@ -136,6 +136,61 @@ def _rel_l2(a, b):
     return float(np.linalg.norm((a - b).ravel()) / max(np.linalg.norm(b.ravel()), 1e-30))
 
 
+def _oracle_with_our_decisions(case, ours_relu_out_nhwc, ours_pool_in_nhwc, tau):
+    """The float64 oracle step with its discrete decisions -- the 2x2 max-pool's routing and the ReLU masks -- taken
+    the way the GPU run took them wherever float64 itself calls them a near-tie.
+
+    On the 64x128 case the net has ~4 M pool windows and ~10 M ReLU inputs under ~1e-6 relative activation noise, so
+    a handful of windows have their two largest values, and a handful of pre-activations have zero, closer than the
+    noise; which side wins decides where a whole gradient contribution goes (tools/irl_diag4.py: up to 25 % of a
+    prepool bias gradient in this synthetic case).  Instead of a loose bar, the oracle is run twice: pass 0 reads its
+    decisions and compares them with ours; every disagreement must be a near-tie (float64 gap <= tau of the activation
+    maximum -- anything above is a real error and fails here); pass 1 nudges exactly those elements (by <= 2 tau of
+    the maximum: the forward values do not move) so that its decisions equal ours.  Returns (oracle result, number of
+    nudged pool windows, number of nudged ReLU inputs)."""
+    ours_idx, _ = irl_oracle.pool_argmax(ours_pool_in_nhwc.permute(0, 3, 1, 2).double())
+    ours_mask = [(y > 0).permute(0, 3, 1, 2) for y in ours_relu_out_nhwc]
+    st = {"pass": 0, "relu": {}, "pool": None, "n_pool": 0, "n_relu": 0}
+
+    def relu_hook(i, u):
+        if st["pass"] == 1:
+            return u + st["relu"][i] if i in st["relu"] else None
+        ud = u.detach()
+        st["seen"] = i + 1
+        differ = (ud > 0) != ours_mask[i]
+        if differ.any():
+            amax = float(ud.abs().max())
+            worst = float(ud.abs()[differ].max())
+            assert worst <= tau * amax, f"ReLU {i}: {int(differ.sum())} masks differ, largest |u64| {worst:.3e} of {amax:.3e}"
+            side = torch.where(ours_mask[i], 1.0, -1.0).double()
+            st["relu"][i] = (side * (ud.abs() + 1e-3 * tau * amax) - ud) * differ
+            st["n_relu"] += int(differ.sum())
+        return None
+
+    def pool_hook(x):
+        idx, gap = irl_oracle.pool_argmax(x.detach())
+        differ = (idx != ours_idx) & (gap > 0)            # exact ties sit behind a ReLU's zeros: no gradient either way
+        if st["pass"] == 1:
+            assert not differ.any(), "pool routing still differs after the nudge"
+            return x + st["pool"] if st["pool"] is not None else None
+        if differ.any():
+            amax, worst = float(x.detach().abs().max()), float(gap[differ].max())
+            assert worst <= tau * amax, f"{int(differ.sum())} pool windows routed differently, largest gap {worst:.3e}"
+            B, Cc, Hp, Wp = idx.shape
+            b4 = torch.zeros(B, Cc, Hp, Wp, 4, dtype=torch.float64)
+            b4.scatter_(-1, ours_idx.unsqueeze(-1), (2.0 * gap * differ).unsqueeze(-1))
+            st["pool"] = b4.reshape(B, Cc, Hp, Wp, 2, 2).permute(0, 1, 2, 4, 3, 5).reshape(B, Cc, 2 * Hp, 2 * Wp)
+            st["n_pool"] = int(differ.sum())
+        return None
+
+    p64 = irl_oracle.port_step(case, steps=1, dtype=torch.float64, pool_hook=pool_hook, relu_hook=relu_hook)
+    assert st["seen"] == len(ours_mask), (st["seen"], len(ours_mask))      # same ReLUs, same order
+    if st["n_pool"] or st["n_relu"]:
+        st["pass"] = 1
+        p64 = irl_oracle.port_step(case, steps=1, dtype=torch.float64, pool_hook=pool_hook, relu_hook=relu_hook)
+    return p64, st["n_pool"], st["n_relu"]
+
+
 @pytest.mark.parametrize("precision", ["fp32", "3xtf32", "3xfp16"])
 @pytest.mark.parametrize("size", [(2, 8, 16), (1, 16, 32), (2, 64, 128)])
 def test_irl_step_matches_oracle(cuda, precision, size):
@@ -143,25 +198,40 @@ def test_irl_step_matches_oracle(cuda, precision, size):
     one training step against the oracle port.
 
     Yardstick for the forward quantities: the oracle's own fp32-vs-fp64 distance on the reward map
-    (the net amplifies rounding: r up to ~20, |r32 - r64| ~ 1e-5).  Gradients: tight on the small
-    cases.  On 64x128 the 2x2 max-pool sees 131072 windows and ~1e-6 relative activation noise,
-    so about one window has its two largest values closer than the noise and routes its gradient
-    (up to ~25% of the whole bias gradient in this synthetic case) to the other pixel -- measured
-    with tools/irl_diag4.py: every tensor's gradient agrees to <= 1e-6 except exactly 1-2 elements
-    behind the pool.  Layers not behind the pool are therefore held to 2e-4, the prepool layers to a
-    relative L2 bound; the kernels themselves are checked at full size in the tests above."""
+    (the net amplifies rounding: r up to ~20, |r32 - r64| ~ 1e-5).  Gradients: ONE bar for every layer, size and
+    precision mode (2e-4 of the tensor's maximum; the round-1 test allowed 35 % relative L2 on the prepool layers of the
+    large case), against the
+    float64 oracle whose near-tie decisions (max-pool routing, ReLU masks) are taken like ours
+    (_oracle_with_our_decisions)."""
     import creste_public_b200 as cb
+    from creste_public_b200 import ops
     from test_train_cpu import _ours
     B, H, W = size
     case = irl_oracle.make_case(seed=3, B=B, H=H, W=W)
     p32 = irl_oracle.port_step(case, steps=1)
-    p64 = irl_oracle.port_step(case, steps=1, dtype=torch.float64)
+    tight = precision == "fp32"
+    pool_in, relu_out = [], []
+    real_pool, real_affine = ops.maxpool2, ops.chan_affine
+
+    def spy_pool(x):
+        pool_in.append(x.detach().cpu())
+        return real_pool(x)
+
+    def spy_affine(x, a=None, b=None, relu=False):
+        y = real_affine(x, a, b, relu)
+        if relu:
+            relu_out.append(y.detach().cpu())
+        return y
+
     cb.set_precision(precision)
+    ops.maxpool2, ops.chan_affine = spy_pool, spy_affine
     try:
         ours = _ours(case, steps=1, device=cuda)
     finally:
+        ops.maxpool2, ops.chan_affine = real_pool, real_affine
         cb.set_precision("fp32")
-    tight = precision == "fp32"
+    assert len(pool_in) == 1
+    p64, n_pool, n_relu = _oracle_with_our_decisions(case, relu_out, pool_in[0], tau=1e-5 if tight else 2e-4)
     slack = 4.0 if tight else 40.0
     yard = np.abs(p32["r"] - p64["r"]).max()
     assert np.abs(ours["r"] - p64["r"]).max() <= slack * yard + 1e-6 * np.abs(p64["r"]).max()
@@ -169,19 +239,22 @@ def test_irl_step_matches_oracle(cuda, precision, size):
               ("mean_expected_svf_rewards", "mean_svf_rewards", "sum_cf_rewards", "sum_opt_rewards")}
     for k, (o, a32, a64) in report.items():     # weighted sums of r: bounded by r's own error
         assert abs(o - a64) <= slack * max(abs(a32 - a64), yard) + 2e-6 * (1 + abs(a64)), (k, report)
-    big = H * W >= 64 * 128
-    pen_tol = (2e-3 if big else 5e-4) * (1 if tight else 5)
+    pen_tol = 1e-4          # measured <= 8.4e-6 in every mode and size once the decisions are matched
     np.testing.assert_allclose(ours["reward_penalty"][0], p64["reward_penalty"][0], rtol=pen_tol, atol=1e-7)
     np.testing.assert_allclose(ours["loss"][0], p64["loss"][0], rtol=pen_tol, atol=slack * yard + 2e-6)
+    bad = []
     for k in p64["grads"]:
         g64 = p64["grads"][k]
-        if big and k.startswith("prepool"):
-            assert _rel_l2(ours["grads"][k], g64) <= 0.35, (k, _rel_l2(ours["grads"][k], g64))
-            continue
-        tol = (2e-4 if tight else 5e-3) * max(np.abs(g64).max(), 1e-3)
-        if big:   # the penalty term (1% of the loss) also flows through the flipped window
-            tol = max(tol, 0.02 * np.abs(g64).max())
-        assert np.abs(ours["grads"][k] - g64).max() <= tol, (k, np.abs(ours["grads"][k] - g64).max(), tol)
+        tol = 2e-4 * max(np.abs(g64).max(), 1e-3)        # every mode; measured worst 6.8e-5 (3xtf32, smallest case)
+        err = np.abs(ours["grads"][k] - g64).max()
+        if err > tol:
+            bad.append((k, float(err), float(tol), float(np.abs(g64).max())))
+    worst = max(float(np.abs(ours["grads"][k] - p64["grads"][k]).max() / max(np.abs(p64["grads"][k]).max(), 1e-3))
+                for k in p64["grads"])
+    print(f"[irl step {precision} {size}] worst gradient error {worst:.2e} of the tensor maximum; "
+          f"{n_pool} pool windows / {n_relu} ReLU inputs nudged in the oracle; penalty rel "
+          f"{abs(float(ours['reward_penalty'][0]) / float(p64['reward_penalty'][0]) - 1):.1e}")
+    assert not bad, (bad, f"{n_pool} pool windows / {n_relu} ReLU inputs nudged in the oracle")
     for k in p32["params"]:
         if "running" in k:
             np.testing.assert_allclose(ours["params"][k], p32["params"][k], rtol=1e-4 if tight else 2e-3,

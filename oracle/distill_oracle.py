@@ -189,12 +189,26 @@ def port_step(case, lr=5e-4):
     return _finish(model, out)
 
 
-def port_grads_fp64(case):
+def port_grads_fp64(case, relu_hook=None):
     """The same step evaluated in float64 (same drop-connect masks): the yardstick that separates an
-    implementation's error from the fp32 rounding noise of the reference itself.  -> (grads, loss)"""
+    implementation's error from the fp32 rounding noise of the reference itself.  -> (grads, loss)
+    relu_hook(i, u) -> u' | None is called on the input of the i-th ReLU in execution order (the six of the Up
+    blocks, the depth head's, the dino head's three): parity tests read the oracle's ReLU masks through it and break
+    near-ties (a pre-activation closer to zero than fp32 rounding noise) the way the implementation under test did."""
     model = PortDistillation(case["image_size"])
     model.load_state_dict(case["state_dict"])
     model.double().train()
+    if relu_hook is not None:
+        count = [0]
+
+        def pre(mod, args):
+            i = count[0]
+            count[0] += 1
+            return relu_hook(i, args[0])
+
+        for m in model.modules():
+            if isinstance(m, nn.ReLU):
+                m.register_forward_pre_hook(pre)
     orig = effs.drop_connect
 
     def drop_connect32(inputs, p, training):          # the fp32 run's uniforms, whatever the dtype

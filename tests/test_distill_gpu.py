@@ -180,6 +180,73 @@ def test_training_step_matches_port_and_golden(cuda, golden, precision):
     check_golden(ours, golden("distill_step.npz"), rtol=2e-4)
 
 
+def _fp64_with_our_relu_masks(case, ours_relu_out_nhwc, tau):
+    """Float64 gradients of the oracle port with every ReLU near-tie (|pre-activation| <= tau of the layer's maximum)
+    decided the way the GPU run decided it: pass 0 reads the oracle's masks and requires every disagreement to be
+    such a near-tie, pass 1 nudges exactly those inputs across zero.  -> (grads, number of nudged inputs)"""
+    ours_mask = [(y > 0).permute(0, 3, 1, 2) for y in ours_relu_out_nhwc]
+    st = {"pass": 0, "bump": {}, "n": 0, "seen": 0}
+
+    def hook(i, u):
+        if st["pass"] == 1:
+            return u + st["bump"][i] if i in st["bump"] else None
+        ud = u.detach()
+        st["seen"] = i + 1
+        assert ud.shape == ours_mask[i].shape, (i, ud.shape, ours_mask[i].shape)
+        differ = (ud > 0) != ours_mask[i]
+        if differ.any():
+            amax, worst = float(ud.abs().max()), float(ud.abs()[differ].max())
+            assert worst <= tau * amax, f"ReLU {i}: {int(differ.sum())} masks differ, largest |u64| {worst:.3e} of {amax:.3e}"
+            side = torch.where(ours_mask[i], 1.0, -1.0).double()
+            st["bump"][i] = (side * (ud.abs() + 1e-3 * tau * amax) - ud) * differ
+            st["n"] += int(differ.sum())
+        return None
+
+    g = do.port_grads_fp64(case, relu_hook=hook)[0]
+    assert st["seen"] == len(ours_mask), (st["seen"], len(ours_mask))
+    if st["n"]:
+        st["pass"] = 1
+        g = do.port_grads_fp64(case, relu_hook=hook)[0]
+    return g, st["n"]
+
+
+@pytest.mark.parametrize("precision", ["fp32", "3xfp16"])
+def test_training_step_gradients_with_matched_relu_masks(cuda, precision):
+    """Every parameter gradient of the stage-1 step, per tensor, against the float64 oracle whose ReLU near-ties are
+    decided like ours -- the strict form of the comparison above: no median, no relative-L2 fallback.  The noise the
+    fallback absorbed is discrete (one flipped element of the last ReLUs moves every upstream gradient by ~1e-3,
+    profiles/r1c_distill_parity.md); with the ten masks matched what is left is rounding."""
+    from creste_public_b200 import engine, ops
+    case = do.make_case()
+    relu_out = []
+    real = ops.chan_affine_act
+
+    def spy(x, a, b, act, **kw):
+        y = real(x, a, b, act, **kw)
+        if act == "relu":
+            relu_out.append(y.detach().cpu())
+        return y
+
+    old = engine.get_precision()
+    engine.set_precision(precision)
+    ops.chan_affine_act = spy
+    try:
+        ours = ours_step(case, device=cuda)
+    finally:
+        ops.chan_affine_act = real
+        engine.set_precision(old)
+    truth, nudged = _fp64_with_our_relu_masks(case, relu_out, tau=1e-4 if precision == "fp32" else 5e-4)
+    rows = []
+    for k, t in truth.items():
+        err, tmax = float(np.abs(ours["grads"][k] - t).max()), float(np.abs(t).max())
+        rows.append((err / max(tmax, 1e-6), k, err, tmax))
+    rows.sort(reverse=True)
+    print(f"[stage-1 step {precision}] {nudged} ReLU inputs nudged in the oracle; worst tensors: "
+          + "; ".join(f"{k} {r:.1e} (max {m:.1e})" for r, k, e, m in [q for q in rows if q[3] > 1e-6][:4]))
+    bad = [(r, k, e, m) for r, k, e, m in rows if e > 5e-4 * m + 1e-6]
+    assert not bad, bad[:10]
+
+
 def test_training_loss_decreases(cuda):
     """Five steps on one batch: the loss goes down and every parameter stays finite."""
     from creste_public_b200 import configs

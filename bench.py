@@ -366,6 +366,7 @@ def run_irl_steps(args, dev, rank, world, barrier, Bi=8, Hm=256, Wm=256, steps=5
     if args.no_irl:
         return None
     cfg = configs.irl_cfg(image_size=(64, 96), map_size=(Hm, Wm), solve_mdp=True, action_horizon=50)
+    torch.manual_seed(0)      # the reward net's xavier init decides the VI sweep count K (~870-1080): fixed for repeatability
     model = cb.build_maxentirl(cfg).to(dev)
     model.backbone.eval()
     model.traversability_head.train()

@@ -55,6 +55,11 @@ def _conv_raw(x, w, ph, pw, stride=1):
         mode = "fp32"      # squeeze-excite vectors [B,1,1,C]: a handful of rows, no tensor-core tile
     if mode == "fp32":
         packed = ops.pack_conv_weight(wp.detach().float())
+    elif mode == "3xfp16" and PRESPLIT_REUSE and stride == 1 and Cp == Cc and Kp == K and Cc % 8 == 0 and K % 8 == 0:
+        # the operand split is remembered on the tensor (and takes the producer's published maximum): the same x
+        # is split once for this conv, its weight gradient and their double-backward counterparts
+        packed = ops.pack_conv_weight_f16_strided(wp.detach().float())
+        return ops.conv2d_presplit(ops.split_f16_cached(xp), packed, K, R, S, 1, pad, precision="3xfp16")
     elif mode in ("3xfp16", "fp16"):
         packed = ops.pack_conv_weight_f16_strided(wp.detach().float())      # one launch, strided read
     else:
@@ -78,6 +83,8 @@ def _wgrad_raw(x, g, R, S, ph, pw):
     if WGRAD_TC and engine.get_precision() != "fp32" and x.dim() == 4:
         Cp, Kp = Cc + (-Cc) % 8, K + (-K) % 8
         if ops.wgrad_tc_supported(tuple(x.shape[:3]) + (Cp,), Kp, R, S, pad):      # tcgen05, 3xFP16 split
+            if PRESPLIT_REUSE and Cp == Cc and Kp == K and g.dim() == 4:
+                return ops.conv2d_wgrad_tc_presplit(ops.split_f16_cached(x), ops.split_f16_cached(g), R, S, pad)
             dw = ops.conv2d_wgrad_tc(_pad_last(x, 8), _pad_last(g, 8), R, S, pad)
             return dw if (Cp == Cc and Kp == K) else dw[:K, :Cc].contiguous()
     if Cc <= WGRAD_TILE and K <= WGRAD_TILE:
@@ -129,7 +136,7 @@ class Conv2dFn(Function):
         ctx.fast = bool(PRESPLIT_REUSE and x.dim() == 4 and _tc_f16(x.shape, K, R, S, pad)
                         and ops.wgrad_tc_supported(tuple(x.shape), K, R, S, pad))
         if ctx.fast:
-            xs = ops.split_f16(x)
+            xs = ops.split_f16_cached(x)
             ctx.save_for_backward(x, w, xs.hi, xs.lo, xs.scal)
             return _conv_presplit(xs, w, pad)
         ctx.save_for_backward(x, w)

@@ -32,9 +32,11 @@ template <int V>
 __global__ void __launch_bounds__(256) chan_affine_kernel(const float* __restrict__ x,
                                                           const float* __restrict__ a,
                                                           const float* __restrict__ b, int C,
-                                                          long long n, int relu, float* __restrict__ y) {
+                                                          long long n, int relu, float* __restrict__ y,
+                                                          unsigned* __restrict__ amax_bits) {
   const long long nv = n / V;
   const int CV = C / V;
+  float m = 0.f;
   for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < nv;
        i += (long long)gridDim.x * blockDim.x) {
     const int c = (int)(i % CV) * V;
@@ -46,19 +48,27 @@ __global__ void __launch_bounds__(256) chan_affine_kernel(const float* __restric
       v.z = fmaf(v.z, aa.z, bb.z); v.w = fmaf(v.w, aa.w, bb.w);
       if (relu) { v.x = fmaxf(v.x, 0.f); v.y = fmaxf(v.y, 0.f); v.z = fmaxf(v.z, 0.f); v.w = fmaxf(v.w, 0.f); }
       reinterpret_cast<float4*>(y)[i] = v;
+      m = fmaxf(fmaxf(m, fmaxf(fabsf(v.x), fabsf(v.y))), fmaxf(fabsf(v.z), fabsf(v.w)));
     } else {
       float v = fmaf(__ldg(x + i), a ? __ldg(a + c) : 1.0f, b ? __ldg(b + c) : 0.0f);
       if (relu) v = fmaxf(v, 0.f);
       y[i] = v;
+      m = fmaxf(m, fabsf(v));
     }
+  }
+  // max|y| for the 3xFP16 operand scale of the conv that consumes y (same reduction as f16_amax_kernel: same bits)
+  if (amax_bits) {
+    m = warp_max(m);
+    if ((threadIdx.x & 31) == 0 && m > 0.f) atomicMax(amax_bits, __float_as_uint(m));
   }
 }
 
 // out = g * (y > 0)
 __global__ void __launch_bounds__(256) relu_bwd_kernel(const float* __restrict__ g,
                                                        const float* __restrict__ y, long long n,
-                                                       float* __restrict__ out) {
+                                                       float* __restrict__ out, unsigned* __restrict__ amax_bits) {
   const long long n4 = n / 4;
+  float m = 0.f;
   for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n4;
        i += (long long)gridDim.x * blockDim.x) {
     float4 gv = __ldg(reinterpret_cast<const float4*>(g) + i);
@@ -66,10 +76,18 @@ __global__ void __launch_bounds__(256) relu_bwd_kernel(const float* __restrict__
     gv.x = yv.x > 0.f ? gv.x : 0.f; gv.y = yv.y > 0.f ? gv.y : 0.f;
     gv.z = yv.z > 0.f ? gv.z : 0.f; gv.w = yv.w > 0.f ? gv.w : 0.f;
     reinterpret_cast<float4*>(out)[i] = gv;
+    m = fmaxf(fmaxf(m, fmaxf(fabsf(gv.x), fabsf(gv.y))), fmaxf(fabsf(gv.z), fabsf(gv.w)));
   }
   for (long long i = n4 * 4 + (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n;
-       i += (long long)gridDim.x * blockDim.x)
-    out[i] = __ldg(y + i) > 0.f ? __ldg(g + i) : 0.f;
+       i += (long long)gridDim.x * blockDim.x) {
+    const float v = __ldg(y + i) > 0.f ? __ldg(g + i) : 0.f;
+    out[i] = v;
+    m = fmaxf(m, fabsf(v));
+  }
+  if (amax_bits) {
+    m = warp_max(m);
+    if ((threadIdx.x & 31) == 0 && m > 0.f) atomicMax(amax_bits, __float_as_uint(m));
+  }
 }
 
 // ------------------------------------------------------------------------------------ chan_dot
@@ -633,15 +651,37 @@ extern "C" int creste_chan_affine(const float* x, const float* a, const float* b
   const long long n = npix * C;
   cudaStream_t st = (cudaStream_t)stream;
   if (C % 4 == 0)
-    chan_affine_kernel<4><<<grid_cap(n / 4, 256, 148 * 16), 256, 0, st>>>(x, a, b, C, n, relu, y);
+    chan_affine_kernel<4><<<grid_cap(n / 4, 256, 148 * 16), 256, 0, st>>>(x, a, b, C, n, relu, y, nullptr);
   else
-    chan_affine_kernel<1><<<grid_cap(n, 256, 148 * 16), 256, 0, st>>>(x, a, b, C, n, relu, y);
+    chan_affine_kernel<1><<<grid_cap(n, 256, 148 * 16), 256, 0, st>>>(x, a, b, C, n, relu, y, nullptr);
+  return launch_check("chan_affine_kernel");
+}
+
+extern "C" int creste_chan_affine_amax(const float* x, const float* a, const float* b, long long npix, int C,
+                                       int relu, float* y, float* amax_out, void* stream) {
+  CRESTE_CHECK_ARG(x && y && amax_out && npix > 0 && C > 0, "creste_chan_affine_amax: bad args");
+  const long long n = npix * C;
+  cudaStream_t st = (cudaStream_t)stream;
+  CRESTE_CUDA(cudaMemsetAsync(amax_out, 0, 4, st));
+  if (C % 4 == 0)
+    chan_affine_kernel<4><<<grid_cap(n / 4, 256, 148 * 16), 256, 0, st>>>(x, a, b, C, n, relu, y, (unsigned*)amax_out);
+  else
+    chan_affine_kernel<1><<<grid_cap(n, 256, 148 * 16), 256, 0, st>>>(x, a, b, C, n, relu, y, (unsigned*)amax_out);
   return launch_check("chan_affine_kernel");
 }
 
 extern "C" int creste_relu_bwd(const float* g, const float* y, long long n, float* out, void* stream) {
   CRESTE_CHECK_ARG(g && y && out && n > 0, "creste_relu_bwd: bad args");
-  relu_bwd_kernel<<<grid_cap(n / 4 + 1, 256, 148 * 16), 256, 0, (cudaStream_t)stream>>>(g, y, n, out);
+  relu_bwd_kernel<<<grid_cap(n / 4 + 1, 256, 148 * 16), 256, 0, (cudaStream_t)stream>>>(g, y, n, out, nullptr);
+  return launch_check("relu_bwd_kernel");
+}
+
+extern "C" int creste_relu_bwd_amax(const float* g, const float* y, long long n, float* out, float* amax_out,
+                                    void* stream) {
+  CRESTE_CHECK_ARG(g && y && out && amax_out && n > 0, "creste_relu_bwd_amax: bad args");
+  CRESTE_CUDA(cudaMemsetAsync(amax_out, 0, 4, (cudaStream_t)stream));
+  relu_bwd_kernel<<<grid_cap(n / 4 + 1, 256, 148 * 16), 256, 0, (cudaStream_t)stream>>>(g, y, n, out,
+                                                                                       (unsigned*)amax_out);
   return launch_check("relu_bwd_kernel");
 }
 

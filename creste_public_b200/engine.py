@@ -22,6 +22,7 @@ def set_precision(mode):
     global _PRECISION
     assert mode in ops.PRECISION, mode
     _PRECISION = mode
+    ops.PUBLISH_AMAX_MODE = mode
 
 
 def get_precision():

@@ -560,6 +560,11 @@ def chan_affine(x, a=None, b=None, relu=False):
     x = x.contiguous()
     Cc = x.shape[-1]
     y = torch.empty_like(x)
+    if _want_amax(x):
+        amax = torch.empty(1, device=x.device)
+        check(lib().creste_chan_affine_amax(ptr(x), ptr(a), ptr(b), C.c_longlong(x.numel() // Cc), Cc,
+                                            int(bool(relu)), ptr(y), ptr(amax), stream()), "creste_chan_affine_amax")
+        return publish_amax(y, amax)
     check(lib().creste_chan_affine(ptr(x), ptr(a), ptr(b), C.c_longlong(x.numel() // Cc), Cc,
                                    int(bool(relu)), ptr(y), stream()), "creste_chan_affine")
     return y
@@ -568,6 +573,11 @@ def chan_affine(x, a=None, b=None, relu=False):
 def relu_bwd(g, y):
     g, y = g.contiguous(), y.contiguous()
     out = torch.empty_like(g)
+    if _want_amax(g):
+        amax = torch.empty(1, device=g.device)
+        check(lib().creste_relu_bwd_amax(ptr(g), ptr(y), C.c_longlong(g.numel()), ptr(out), ptr(amax), stream()),
+              "creste_relu_bwd_amax")
+        return publish_amax(out, amax)
     check(lib().creste_relu_bwd(ptr(g), ptr(y), C.c_longlong(g.numel()), ptr(out), stream()),
           "creste_relu_bwd")
     return out
@@ -771,6 +781,16 @@ def chan_moments(x):
     check(lib().creste_chan_moments(ptr(x), C.c_longlong(npix), Cc, ptr(out), ptr(ws), C.c_size_t(n),
                                     stream()), "creste_chan_moments")
     return out
+
+
+USE_PUBLISHED_AMAX = os.environ.get("CRESTE_NO_PUBLISHED_AMAX") is None     # experiment / test switch
+PUBLISH_AMAX_MODE = None       # set by engine.set_precision: producers measure max|out| only in the 3xFP16 mode
+
+
+def _want_amax(t):
+    """The generic elementwise producers (chan_affine, relu_bwd) measure max|out| when a tensor-core conv may consume
+    the result: 3xFP16 mode, a 4-D activation with a channel count the tensor-core path takes."""
+    return PUBLISH_AMAX_MODE == "3xfp16" and USE_PUBLISHED_AMAX and t.dim() == 4 and t.shape[-1] % 8 == 0
 
 
 def publish_amax(t, amax):
@@ -991,9 +1011,6 @@ def conv2d_wgrad_tc(x_nhwc, g_nhwc, R, S, pad):
     return dw.view(R, S, Cc, K).permute(3, 2, 0, 1).contiguous()
 
 
-USE_PUBLISHED_AMAX = os.environ.get("CRESTE_NO_PUBLISHED_AMAX") is None     # experiment / test switch
-
-
 def split_f16(x_nhwc):
     """The 3xFP16 operand of a dense fp32 NHWC tensor (amax -> power-of-two scale -> fp16 hi / lo) as a SplitAct."""
     amax = published_amax(x_nhwc)
@@ -1008,6 +1025,19 @@ def split_f16(x_nhwc):
     check(lib().creste_f16_split(ptr(x_nhwc), C.c_longlong(x_nhwc.numel()), ptr(hi), ptr(lo), ptr(scal), stream()),
           "creste_f16_split")
     return SplitAct(hi, lo, scal, x_nhwc.shape)
+
+
+def split_f16_cached(x_nhwc):
+    """split_f16 remembered on the tensor (until it is written again): in the stage-3 graph the same activation /
+    gradient is the operand of up to four tensor-core convs (forward conv, weight gradient, and their counterparts in
+    the double backward of the gradient penalty), in stage 1 the decoder features feed two heads."""
+    rec = getattr(x_nhwc, "_split_rec", None)
+    if rec is not None and rec[1] == x_nhwc._version and USE_PUBLISHED_AMAX:
+        return rec[0]
+    sa = split_f16(x_nhwc)
+    if x_nhwc.is_contiguous():
+        x_nhwc._split_rec = (sa, x_nhwc._version)
+    return sa
 
 
 def conv2d_wgrad_tc_presplit(xs, gs, R, S, pad):

@@ -331,6 +331,11 @@ int creste_chan_affine(const float* x, const float* a, const float* b, long long
                        int relu, float* y, void* stream);
 /* out = g * (y > 0): ReLU backward (autograd's threshold_backward). */
 int creste_relu_bwd(const float* g, const float* y, long long n, float* out, void* stream);
+/* the two above, also publishing max|out| (DEVICE float[1], zeroed here) for creste_f16_split_amax: in the stage-3
+ * graph (conv.py:117-126 differentiated twice) these are the producers of most tensor-core conv operands */
+int creste_chan_affine_amax(const float* x, const float* a, const float* b, long long npix, int C,
+                            int relu, float* y, float* amax_out, void* stream);
+int creste_relu_bwd_amax(const float* g, const float* y, long long n, float* out, float* amax_out, void* stream);
 /* out[c] = sum_pix x[pix,c] * (y ? y[pix,c] : 1): BatchNorm batch statistics and the channel
  * reductions of its backward; two-stage fixed-order reduction.  ws >= the _workspace_bytes. */
 size_t creste_chan_dot_workspace_bytes(long long npix, int C);

@@ -558,34 +558,69 @@ __global__ void __launch_bounds__(256) dwconv_wgrad_tile_kernel(const float* __r
 
 // ------------------------------------------------------------------- strided dense wgrad (C == 4)
 // thread -> (tap, k); part[bx][(tap*4 + c)*K + k] = sum over the block's output pixels.
+// A CTA walks tiles of WG_TQ output pixels of one output row: the tile's g [WG_TQ][K] and the R input rows it touches
+// ([R][(WG_TQ-1)*st + S] float4, zero outside the image) are staged in shared memory with coalesced loads, then every
+// thread runs the pixel loop out of shared memory (g: consecutive k, conflict-free; x: one float4 broadcast per warp).
+// fp32 accumulation inside a tile, double across tiles.  The round-2b form read g and x from global memory inside a
+// per-thread pixel loop with two 64-bit divisions per pixel: 2.1 ms for the 512x960 stem at B = 16; this one is
+// bound by the 380 MB it reads.
+constexpr int WG_TQ = 64;
 __global__ void __launch_bounds__(1024) wgrad_strided_c4_kernel(const float* __restrict__ x,
                                                                 const float* __restrict__ g, int N, int H, int W,
                                                                 int K, int R, int S, int st, int pt, int pl, int P,
-                                                                int Q, double* __restrict__ part) {
+                                                                int Q, int tiles_q, long long ntiles,
+                                                                double* __restrict__ part) {
+  extern __shared__ float4 wg_smem[];
+  const int XW = (WG_TQ - 1) * st + S;                 // input columns a tile touches
+  float4* sx = wg_smem;                                // [R][XW]
+  float* sg = reinterpret_cast<float*>(wg_smem + R * XW);      // [WG_TQ][K]
   const int t = threadIdx.x;
   const int tap = t / K, k = t - tap * K;
-  if (tap >= R * S) return;
-  const int r = tap / S, s = tap - r * S;
-  const long long npix = (long long)N * P * Q;
-  const long long per = (npix + gridDim.x - 1) / gridDim.x;
-  const long long p0 = (long long)blockIdx.x * per;
-  const long long p1 = p0 + per < npix ? p0 + per : npix;
-  float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
-  for (long long pix = p0; pix < p1; ++pix) {
-    const int q = (int)(pix % Q);
-    const long long t2 = pix / Q;
-    const int p = (int)(t2 % P);
-    const int n = (int)(t2 / P);
-    const int iy = p * st + r - pt, ix = q * st + s - pl;
-    if (iy < 0 || iy >= H || ix < 0 || ix >= W) continue;
-    const float gv = __ldg(g + (size_t)pix * K + k);
-    const float4 xv = __ldg(reinterpret_cast<const float4*>(x + (((size_t)n * H + iy) * W + ix) * 4));
-    acc.x = fmaf(gv, xv.x, acc.x); acc.y = fmaf(gv, xv.y, acc.y);
-    acc.z = fmaf(gv, xv.z, acc.z); acc.w = fmaf(gv, xv.w, acc.w);
+  const bool live = tap < R * S;
+  const int r = live ? tap / S : 0, s = live ? tap - r * S : 0;
+  double a0 = 0.0, a1 = 0.0, a2 = 0.0, a3 = 0.0;
+  for (long long tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
+    const int tq = (int)(tile % tiles_q);
+    const long long row = tile / tiles_q;              // n * P + p
+    const int p = (int)(row % P), n = (int)(row / P);
+    const int q0 = tq * WG_TQ;
+    const int nq = min(WG_TQ, Q - q0);
+    __syncthreads();                                   // the previous tile's readers are done
+    for (int i = t; i < R * XW; i += blockDim.x) {
+      const int rr = i / XW, cc = i - rr * XW;
+      const int iy = p * st + rr - pt, ix = q0 * st + cc - pl;
+      float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+      if (iy >= 0 && iy < H && ix >= 0 && ix < W)
+        v = __ldg(reinterpret_cast<const float4*>(x + (((size_t)n * H + iy) * W + ix) * 4));
+      sx[i] = v;
+    }
+    const float* gsrc = g + ((size_t)row * Q + q0) * K;
+    const int ng = nq * K;                             // contiguous in global memory
+    if ((K & 3) == 0) {
+      for (int i = t; i < ng / 4; i += blockDim.x)
+        reinterpret_cast<float4*>(sg)[i] = __ldg(reinterpret_cast<const float4*>(gsrc) + i);
+    } else {
+      for (int i = t; i < ng; i += blockDim.x) sg[i] = __ldg(gsrc + i);
+    }
+    __syncthreads();
+    if (live) {
+      float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
+      const float4* xr = sx + r * XW + s;
+#pragma unroll 4
+      for (int j = 0; j < nq; ++j) {
+        const float gv = sg[j * K + k];
+        const float4 xv = xr[j * st];
+        acc.x = fmaf(gv, xv.x, acc.x); acc.y = fmaf(gv, xv.y, acc.y);
+        acc.z = fmaf(gv, xv.z, acc.z); acc.w = fmaf(gv, xv.w, acc.w);
+      }
+      a0 += (double)acc.x; a1 += (double)acc.y; a2 += (double)acc.z; a3 += (double)acc.w;
+    }
   }
-  double* dst = part + (size_t)blockIdx.x * (R * S * 4 * K);
-  dst[(tap * 4 + 0) * K + k] = (double)acc.x; dst[(tap * 4 + 1) * K + k] = (double)acc.y;
-  dst[(tap * 4 + 2) * K + k] = (double)acc.z; dst[(tap * 4 + 3) * K + k] = (double)acc.w;
+  if (live) {
+    double* dst = part + (size_t)blockIdx.x * (R * S * 4 * K);
+    dst[(tap * 4 + 0) * K + k] = a0; dst[(tap * 4 + 1) * K + k] = a1;
+    dst[(tap * 4 + 2) * K + k] = a2; dst[(tap * 4 + 3) * K + k] = a3;
+  }
 }
 
 // ---------------------------------------------------------------- BatchNorm per-channel algebra
@@ -900,9 +935,9 @@ extern "C" int creste_chan_slice(const float* x, long long npix, int C, int c0, 
 }
 
 static int wgrad_strided_pb(long long npix) {
-  long long b = npix / 256;
+  long long b = npix / WG_TQ;               // one tile of WG_TQ output pixels at least
   if (b < 1) b = 1;
-  return (int)(b > 1776 ? 1776 : b);        // 12 CTAs per SM: the per-thread pixel loop is latency-bound
+  return (int)(b > 148 * 4 ? 148 * 4 : b);  // 4 CTAs per SM: one CTA's tile loads run under the others' pixel loops
 }
 
 extern "C" size_t creste_wgrad_strided_workspace_bytes(int N, int P, int Q, int C, int K, int R, int S) {
@@ -920,7 +955,13 @@ extern "C" int creste_wgrad_strided(const float* x, const float* g, int N, int H
   cudaStream_t st = (cudaStream_t)stream;
   const int PB = wgrad_strided_pb((long long)N * P * Q);
   const int threads = (R * S * K + 31) / 32 * 32;
-  wgrad_strided_c4_kernel<<<PB, threads, 0, st>>>(x, g, N, H, W, K, R, S, stride, pad_t, pad_l, P, Q, (double*)ws);
+  const int tiles_q = ceil_div(Q, WG_TQ);
+  const long long ntiles = (long long)N * P * tiles_q;
+  const size_t smem = (size_t)R * ((WG_TQ - 1) * stride + S) * sizeof(float4) + (size_t)WG_TQ * K * sizeof(float);
+  CRESTE_CHECK_ARG(smem <= 200 * 1024, "creste_wgrad_strided: tile does not fit shared memory");
+  CRESTE_CUDA(cudaFuncSetAttribute(wgrad_strided_c4_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  wgrad_strided_c4_kernel<<<PB, threads, smem, st>>>(x, g, N, H, W, K, R, S, stride, pad_t, pad_l, P, Q, tiles_q, ntiles,
+                                                    (double*)ws);
   int rc = launch_check("wgrad_strided_c4_kernel");
   if (rc) return rc;
   const int n = R * S * C * K;

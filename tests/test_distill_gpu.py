@@ -92,11 +92,17 @@ def test_se_and_small_kernels(cuda):
     _close(ops.chan_slice(x.to(cuda), 112, 320), tb.chan_slice(x, 112, 320), 0, "slice")
 
 
-def test_stem_wgrad(cuda):
+@pytest.mark.parametrize("N,H,W,K,pad", [(2, 32, 48, 32, (0, 1, 0, 1)),       # one ragged tile per output row
+                                         (1, 18, 300, 32, (0, 1, 0, 1)),      # 150 output columns: 2 full tiles + a tail
+                                         (3, 33, 131, 32, (1, 1, 1, 1)),      # odd sizes, padding on every side
+                                         (2, 16, 140, 24, (0, 1, 0, 1))])     # warps straddling two taps (K = 24)
+def test_stem_wgrad(cuda, N, H, W, K, pad):
+    """Weight gradient of the strided C = 4 stem conv (tiled shared-memory kernel) against torch's autograd."""
     from creste_public_b200 import ops
     g = np.random.default_rng(12)
-    x, gy = _t(g, 2, 32, 48, 4), _t(g, 2, 16, 24, 32)
-    pad = (0, 1, 0, 1)
+    P = (H + pad[0] + pad[1] - 3) // 2 + 1
+    Q = (W + pad[2] + pad[3] - 3) // 2 + 1
+    x, gy = _t(g, N, H, W, 4), _t(g, N, P, Q, K)
     _close(ops.wgrad_strided(x.to(cuda), gy.to(cuda), 3, 3, 2, pad), tb.wgrad_strided(x, gy, 3, 3, 2, pad), 1e-5, "stem wgrad")
 
 

@@ -22,7 +22,7 @@ EXPORTS = [
     "creste_lidar_raster", "creste_depth_expectation", "creste_bin_depths",
     "creste_conv2d", "creste_conv2d_ex", "creste_conv2d_presplit", "creste_conv2d_split_out", "creste_conv2d_presplit_split_out", "creste_upsample_concat_split", "creste_conv2d_workspace_bytes", "creste_conv2d_tc_supported",
     "creste_conv2d_tc_layout", "creste_conv2d_tc_debug",
-    "creste_f16_split", "creste_f16_split_amax", "creste_chan_affine_amax", "creste_relu_bwd_amax", "creste_chan_affine_act_amax", "creste_chan_axpby_amax", "creste_conv2d_wgrad_tc_presplit", "creste_affine_warp", "creste_depth_augment", "creste_traverse_to_bev", "creste_dwconv_num_parts", "creste_dwconv_tile_parts", "creste_dwconv_parts", "creste_dwconv_bn_swish", "creste_dwconv_bn_swish_ex", "creste_se_gate",
+    "creste_f16_split", "creste_f16_split_amax", "creste_chan_axpby_act", "creste_chan_affine_amax", "creste_relu_bwd_amax", "creste_chan_affine_act_amax", "creste_chan_axpby_amax", "creste_conv2d_wgrad_tc_presplit", "creste_affine_warp", "creste_depth_augment", "creste_traverse_to_bev", "creste_dwconv_num_parts", "creste_dwconv_tile_parts", "creste_dwconv_parts", "creste_dwconv_bn_swish", "creste_dwconv_bn_swish_ex", "creste_se_gate",
     "creste_upsample_concat", "creste_maxpool2_concat",
     "creste_nchw_to_nhwc", "creste_nhwc_to_nchw", "creste_proj_head",
     "creste_expert_visitation",

@@ -593,6 +593,9 @@ def _update_running(bn, mean, var, M):
         bn.running_var.mul_(1 - mom).add_((var * (M / max(M - 1, 1))).float(), alpha=mom)
 
 
+FUSED_BN_BWD = True       # BatchNorm(+act) backward: second pass recomputes gu instead of reading it back
+
+
 class BNActFn(Function):
     """BatchNorm2d with batch statistics + activation ('none' | 'relu' | 'swish') as ONE node:
     forward = one moments pass + one [C]-sized finalize launch + one affine/act pass; backward = one pass
@@ -624,10 +627,15 @@ class BNActFn(Function):
     @once
     def backward(ctx, g):
         x, ab, mi = ctx.saved_tensors
-        gu, sums = ops.bn_act_bwd(g, x, ab[0], ab[1], ctx.act)
+        # gu = g * act'(u) is not stored: the second pass recomputes it from g (20 instead of 24 bytes per element)
+        fused = ctx.act != "none" and FUSED_BN_BWD
+        gu, sums = ops.bn_act_bwd(g, x, ab[0], ab[1], ctx.act, want_gu=not fused)
         out4 = ops.bn_bwd_finalize(sums, ab, mi, ctx.M)
-        dx = (ops.chan_axpby(gu, x, ab[0], out4[2], out4[3], want_amax=(engine.get_precision() == "3xfp16"))
-              if ctx.needs_input_grad[0] else None)
+        pub = engine.get_precision() == "3xfp16"
+        dx = None
+        if ctx.needs_input_grad[0]:
+            dx = (ops.chan_axpby_act(g, x, ab[0], ab[1], ctx.act, ab[0], out4[2], out4[3], want_amax=pub) if fused
+                  else ops.chan_axpby(gu, x, ab[0], out4[2], out4[3], want_amax=pub))
         return dx, out4[0], out4[1], None, None
 
 

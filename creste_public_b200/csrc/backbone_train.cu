@@ -104,6 +104,42 @@ __global__ void __launch_bounds__(256) chan_axpby_kernel(const float* __restrict
   }
 }
 
+// out = (g * act'(x*a[c] + b[c])) * p[c] + x*q[c] + r[c]: the second half of the BatchNorm(+act) backward with gu
+// recomputed from g instead of read back (the first half then does not store it): same expressions as BnActBwdOp
+// followed by chan_axpby_kernel, same bits, 20 instead of 24 bytes per element over the two passes.
+__global__ void __launch_bounds__(256) chan_axpby_act_kernel(const float* __restrict__ g, const float* __restrict__ x,
+                                                             const float* __restrict__ a, const float* __restrict__ b,
+                                                             int act, const float* __restrict__ p,
+                                                             const float* __restrict__ q, const float* __restrict__ r,
+                                                             int C, long long n, float* __restrict__ out,
+                                                             unsigned* __restrict__ amax_bits) {
+  const long long nv = n / 4;
+  const int CV = C / 4;
+  float m = 0.f;
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < nv;
+       i += (long long)gridDim.x * blockDim.x) {
+    const int c = (int)(i % CV) * 4;
+    float4 gv = __ldg(reinterpret_cast<const float4*>(g) + i);
+    const float4 xv = __ldg(reinterpret_cast<const float4*>(x) + i);
+    const float4 aa = __ldg(reinterpret_cast<const float4*>(a + c));
+    const float4 bb = __ldg(reinterpret_cast<const float4*>(b + c));
+    gv.x *= act_grad(fmaf(xv.x, aa.x, bb.x), act); gv.y *= act_grad(fmaf(xv.y, aa.y, bb.y), act);
+    gv.z *= act_grad(fmaf(xv.z, aa.z, bb.z), act); gv.w *= act_grad(fmaf(xv.w, aa.w, bb.w), act);
+    const float4 pp = __ldg(reinterpret_cast<const float4*>(p + c));
+    const float4 qq = __ldg(reinterpret_cast<const float4*>(q + c));
+    const float4 rr = __ldg(reinterpret_cast<const float4*>(r + c));
+    float4 o;
+    o.x = fmaf(gv.x, pp.x, fmaf(xv.x, qq.x, rr.x)); o.y = fmaf(gv.y, pp.y, fmaf(xv.y, qq.y, rr.y));
+    o.z = fmaf(gv.z, pp.z, fmaf(xv.z, qq.z, rr.z)); o.w = fmaf(gv.w, pp.w, fmaf(xv.w, qq.w, rr.w));
+    reinterpret_cast<float4*>(out)[i] = o;
+    m = fmaxf(fmaxf(m, fmaxf(fabsf(o.x), fabsf(o.y))), fmaxf(fabsf(o.z), fabsf(o.w)));
+  }
+  if (amax_bits) {
+    m = warp_max(m);
+    if ((threadIdx.x & 31) == 0 && m > 0.f) atomicMax(amax_bits, __float_as_uint(m));
+  }
+}
+
 // out[b,pix,c] = (x ? x[b,pix,c] * (a ? a[b,c] : 1) : 0) + (bb ? bb[b,c] : 0)
 __global__ void __launch_bounds__(256) sample_affine_kernel(const float* __restrict__ x,
                                                             const float* __restrict__ a,
@@ -772,7 +808,7 @@ extern "C" int creste_bn_act_bwd(const float* g, const float* x, const float* a,
                                  int act, float* gu, double* sums2, void* ws, size_t ws_bytes, void* stream) {
   CRESTE_CHECK_ARG(g && x && sums2 && ws && npix > 0 && C > 0 && C % 4 == 0 && act >= 0 && act <= 2,
                    "creste_bn_act_bwd: bad args");
-  CRESTE_CHECK_ARG(act == ACT_NONE || (a && b && gu), "creste_bn_act_bwd: act needs a, b and gu");
+  CRESTE_CHECK_ARG(act == ACT_NONE || (a && b), "creste_bn_act_bwd: act needs a and b");
   CRESTE_CHECK_ARG(ws_bytes >= creste_chan_reduce_workspace_bytes(npix, C, 2, 1), "creste_bn_act_bwd: workspace");
   cudaStream_t st = (cudaStream_t)stream;
   const int PB = reduce_pb(npix, 1);
@@ -790,6 +826,18 @@ extern "C" int creste_chan_axpby(const float* u, const float* x, const float* p,
   const long long n = npix * C;
   chan_axpby_kernel<<<ELT_GRID(n / 4), 256, 0, (cudaStream_t)stream>>>(u, x, p, q, r, C, n, out, nullptr);
   return launch_check("chan_axpby_kernel");
+}
+
+extern "C" int creste_chan_axpby_act(const float* g, const float* x, const float* a, const float* b, int act,
+                                     const float* p, const float* q, const float* r, long long npix, int C, float* out,
+                                     float* amax_out, void* stream) {
+  CRESTE_CHECK_ARG(g && x && a && b && p && q && r && out && npix > 0 && C > 0 && C % 4 == 0 && act >= 0 && act <= 2,
+                   "creste_chan_axpby_act: bad args");
+  const long long n = npix * C;
+  if (amax_out) CRESTE_CUDA(cudaMemsetAsync(amax_out, 0, 4, (cudaStream_t)stream));
+  chan_axpby_act_kernel<<<ELT_GRID(n / 4), 256, 0, (cudaStream_t)stream>>>(g, x, a, b, act, p, q, r, C, n, out,
+                                                                           (unsigned*)amax_out);
+  return launch_check("chan_axpby_act_kernel");
 }
 
 extern "C" int creste_chan_axpby_amax(const float* u, const float* x, const float* p, const float* q, const float* r,

@@ -821,18 +821,31 @@ def chan_affine_act(x, a, b, act, want_amax=False):
     return y
 
 
-def bn_act_bwd(g, x, a, b, act):
+def bn_act_bwd(g, x, a, b, act, want_gu=True):
     """-> (gu, sums float64 [2, C]) with gu = g * act'(x*a+b) (gu is g itself for act 'none') and
-    sums = (sum gu, sum gu*x) per channel."""
+    sums = (sum gu, sum gu*x) per channel.  want_gu=False: gu is not stored (None is returned for act != 'none';
+    chan_axpby_act recomputes it)."""
     g, x = g.contiguous(), x.contiguous()
     npix, Cc = _npix_c(x)
-    gu = torch.empty_like(g) if ACT[act] != 0 else None
+    gu = torch.empty_like(g) if (ACT[act] != 0 and want_gu) else None
     sums = torch.empty(2, Cc, dtype=torch.float64, device=x.device)
     n = lib().creste_chan_reduce_workspace_bytes(C.c_longlong(npix), Cc, 2, 1)
     ws = _ws(n, x.device)
     check(lib().creste_bn_act_bwd(ptr(g), ptr(x), ptr(a), ptr(b), C.c_longlong(npix), Cc, ACT[act], ptr(gu),
                                   ptr(sums), ptr(ws), C.c_size_t(n), stream()), "creste_bn_act_bwd")
-    return (gu if gu is not None else g), sums
+    return (gu if (gu is not None or ACT[act] != 0) else g), sums
+
+
+def chan_axpby_act(g, x, a, b, act, p, q, r, want_amax=False):
+    """out = (g * act'(x*a[c]+b[c])) * p[c] + x*q[c] + r[c]: chan_axpby on the gu that bn_act_bwd would have stored."""
+    g, x = g.contiguous(), x.contiguous()
+    npix, Cc = _npix_c(x)
+    out = torch.empty_like(x)
+    amax = torch.empty(1, device=x.device) if want_amax else None
+    check(lib().creste_chan_axpby_act(ptr(g), ptr(x), ptr(a.contiguous()), ptr(b.contiguous()), ACT[act],
+                                      ptr(p.contiguous()), ptr(q.contiguous()), ptr(r.contiguous()), C.c_longlong(npix),
+                                      Cc, ptr(out), ptr(amax), stream()), "creste_chan_axpby_act")
+    return publish_amax(out, amax) if want_amax else out
 
 
 def chan_axpby(u, x, p, q, r, want_amax=False):

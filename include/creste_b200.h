@@ -426,7 +426,8 @@ int creste_chan_affine_act(const float* x, const float* a, const float* b, long 
 int creste_chan_affine_act_amax(const float* x, const float* a, const float* b, long long npix, int C, int act,
                                 float* y, float* amax_out, void* stream);
 /* first half of the BatchNorm(+act) backward: gu = g * act'(x*a[c]+b[c]) (written when act != 0) and
- * sums2 DEVICE double[2*C] = {sum gu}, {sum gu*x}; ws >= creste_chan_reduce_workspace_bytes(npix,C,2,1) */
+ * sums2 DEVICE double[2*C] = {sum gu}, {sum gu*x}; ws >= creste_chan_reduce_workspace_bytes(npix,C,2,1);
+ * gu may be NULL (not stored: creste_chan_axpby_act recomputes it) */
 int creste_bn_act_bwd(const float* g, const float* x, const float* a, const float* b, long long npix, int C,
                       int act, float* gu, double* sums2, void* ws, size_t ws_bytes, void* stream);
 /* second half: out = u*p[c] + x*q[c] + r[c] */
@@ -436,6 +437,11 @@ int creste_chan_axpby(const float* u, const float* x, const float* p, const floa
  * convs of the layer below split into their 3xFP16 operand */
 int creste_chan_axpby_amax(const float* u, const float* x, const float* p, const float* q, const float* r,
                            long long npix, int C, float* out, float* amax_out, void* stream);
+/* second half with gu recomputed: out = (g * act'(x*a[c]+b[c])) * p[c] + x*q[c] + r[c]  (creste_bn_act_bwd may then be
+ * called with gu = NULL); amax_out optional (DEVICE float[1], zeroed here).  Same bits as the two-kernel form. */
+int creste_chan_axpby_act(const float* g, const float* x, const float* a, const float* b, int act, const float* p,
+                          const float* q, const float* r, long long npix, int C, float* out, float* amax_out,
+                          void* stream);
 /* depthwise R x R conv (R in {3,5}, stride in {1,2}) with the static TF-'SAME' padding of
  * efficientnet_pytorch (low pads given, high implied by P, Q): w [R*R][C]; x [N,H,W,C]; y [N,P,Q,C];
  * _dgrad: dx from g [N,P,Q,C]; _wgrad: dw [R*R][C]. */

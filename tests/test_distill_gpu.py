@@ -290,6 +290,24 @@ def test_producers_publish_exact_amax(cuda, act):
         assert ops.published_amax(pub) is None
 
 
+@pytest.mark.parametrize("act", ["relu", "swish"])
+def test_bn_backward_second_pass_recomputes_gu(cuda, act):
+    """chan_axpby_act(g, ...) == chan_axpby(gu, ...) bit for bit, and bn_act_bwd without the gu store returns the
+    same sums."""
+    from creste_public_b200 import ops
+    g = np.random.default_rng(3)
+    C = 96
+    x, gy = _t(g, 2, 13, 9, C, scale=2.0).to(cuda), _t(g, 2, 13, 9, C).to(cuda)
+    a, b, q, r = (_t(g, C).to(cuda) for _ in range(4))
+    gu, sums = ops.bn_act_bwd(gy, x, a, b, act)
+    none, sums2 = ops.bn_act_bwd(gy, x, a, b, act, want_gu=False)
+    assert none is None and torch.equal(sums, sums2)
+    two = ops.chan_axpby(gu, x, a, q, r)
+    one = ops.chan_axpby_act(gy, x, a, b, act, a, q, r, want_amax=True)
+    assert torch.equal(one, two)
+    assert float(ops.published_amax(one)) == float(two.abs().max())
+
+
 def test_training_step_identical_with_published_amax(cuda):
     """The stage-1 step with the producers' published maxima (no amax passes in front of the tensor-core convs) is
     bit-identical to the step that measures every operand maximum in its own pass."""
@@ -297,12 +315,15 @@ def test_training_step_identical_with_published_amax(cuda):
     case = do.make_case()
     old = engine.get_precision()
     engine.set_precision("3xfp16")
+    from creste_public_b200 import autograd as ag
     try:
         a = ours_step(case, device=cuda)
         ops.USE_PUBLISHED_AMAX = False
+        ag.FUSED_BN_BWD = False                 # and the two-kernel BatchNorm backward with gu stored
         b = ours_step(case, device=cuda)
     finally:
         ops.USE_PUBLISHED_AMAX = True
+        ag.FUSED_BN_BWD = True
         engine.set_precision(old)
     assert a["loss"] == b["loss"]
     assert np.array_equal(a["logits"], b["logits"])

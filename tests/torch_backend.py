@@ -318,19 +318,24 @@ def bn_bwd_finalize(sums, ab, mean_inv, M):
     return torch.stack([dgamma.float(), s1.float(), q.float(), r.float()])
 
 
-def chan_affine_act(x, a, b, act):
+def chan_affine_act(x, a, b, act, want_amax=False):
     return _act(x * a + b, act)
 
 
-def bn_act_bwd(g, x, a, b, act):
+def bn_act_bwd(g, x, a, b, act, want_gu=True):
     gu = g if act in ("none", None) else g * _act_grad(x * a + b, act)
     Cc = x.shape[-1]
     gd, xd = gu.reshape(-1, Cc).double(), x.reshape(-1, Cc).double()
-    return gu, torch.stack([gd.sum(0), (gd * xd).sum(0)])
+    keep = want_gu or act in ("none", None)
+    return (gu if keep else None), torch.stack([gd.sum(0), (gd * xd).sum(0)])
 
 
-def chan_axpby(u, x, p, q, r):
+def chan_axpby(u, x, p, q, r, want_amax=False):
     return u * p + x * q + r
+
+
+def chan_axpby_act(g, x, a, b, act, p, q, r, want_amax=False):
+    return (g * _act_grad(x * a + b, act)) * p + x * q + r
 
 
 def _dw_w(w_rsc, R):
@@ -604,7 +609,7 @@ def maxpool2_concat(srcs_nhwc, rows_out=None, want_nchw=False):
     return (y, _nchw(y)) if want_nchw else y
 
 
-STAGE1_NAMES = ["bn_fwd_finalize", "bn_bwd_finalize", "chan_moments", "chan_affine_act", "bn_act_bwd", "chan_axpby", "dwconv_fwd", "dwconv_dgrad",
+STAGE1_NAMES = ["bn_fwd_finalize", "bn_bwd_finalize", "chan_moments", "chan_affine_act", "bn_act_bwd", "chan_axpby", "chan_axpby_act", "dwconv_fwd", "dwconv_dgrad",
                 "dwconv_wgrad", "sample_dot", "sample_affine", "act", "act_bwd", "add_scaled", "chan_slice",
                 "wgrad_strided", "wgrad_rows", "conv2d", "pack_conv_weight", "upsample_concat", "stage1_depth_losses",
                 "ce_depth_bwd", "masked_mse", "masked_mse_bwd", "depth_expectation"]

@@ -26,7 +26,7 @@ def _close(a, b, rtol=1e-5, what=""):
     assert err <= rtol * max(ref, 1e-6), (what, err, ref)
 
 
-@pytest.mark.parametrize("C", [32, 144, 1152])
+@pytest.mark.parametrize("C", [16, 24, 32, 40, 144, 1152])
 @pytest.mark.parametrize("act", ["none", "relu", "swish"])
 def test_bn_kernels(cuda, C, act):
     from creste_public_b200 import ops

@@ -922,6 +922,23 @@ static int conv_tc_main(const creste_conv_desc* d, float* x_hi, float* x_lo, flo
 
   // two CTAs on adjacent M tiles form a tcgen05 CTA pair (cta_group::2, M = 256)
   const int m_tiles = d->N * p.tiles_y * p.tiles_x;
+  // Low-resolution layers (the deep MBConv stages, the BEV decoder's layer 3 / 4; every layer at B = 1) have a
+  // handful of M tiles: 4 - 32 CTAs each walking the whole K loop while 120 SMs idle.  Their N tile is cut into
+  // f equal slices (a divisor of the packed tile, so the weight layout does not change; >= 32 channels, multiples of
+  // 32 so that a CTA pair still splits whole swizzle atoms): f x as many CTAs, each k-step f x shorter.
+  if (!getenv("CRESTE_TC_NO_SHRINK")) {
+    const int ctas = m_tiles * (npad / block_n);
+    if (ctas < 96) {
+      int best = 1;
+      for (int f = 2; f <= 8; ++f) {
+        if (block_n % f || (block_n / f) % 32 || block_n / f < 32) continue;
+        best = f;
+        if (ctas * f >= 120) break;
+      }
+      block_n /= best;
+      p.block_n = block_n;
+    }
+  }
   // cluster = 1 (no pairing), 2 (one CTA pair, the default) or 4 / 8 (CRESTE_TC_CLUSTER: 2 / 4 pairs
   // sharing the weight tile by TMA multicast; each slice keeps whole 8-row swizzle atoms).
   // Measured on the up3 conv: multicast cuts the L2->SM weight traffic by 25 % / 37 % but the

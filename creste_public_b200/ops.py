@@ -795,14 +795,17 @@ def _want_amax(t):
 
 def publish_amax(t, amax):
     """Attach the exact max|t| (device float[1]) the producing kernel measured; split_f16 then skips its amax pass.
-    Valid while the tensor is not written again (checked through torch's version counter)."""
-    t._amax_exact = (amax, t._version)
+    Valid while the tensor is not written again (checked through torch's version counter) and within the same
+    capture state (a value measured by an eager warm-up is not consumed inside a CUDA-graph capture)."""
+    t._amax_exact = (amax, t._version, t.is_cuda and torch.cuda.is_current_stream_capturing())
     return t
 
 
 def published_amax(t):
     rec = getattr(t, "_amax_exact", None)
-    return rec[0] if rec is not None and rec[1] == t._version else None
+    if rec is None or rec[1] != t._version:
+        return None
+    return rec[0] if rec[2] == (t.is_cuda and torch.cuda.is_current_stream_capturing()) else None
 
 
 def chan_affine_act(x, a, b, act, want_amax=False):
@@ -1043,13 +1046,16 @@ def split_f16(x_nhwc):
 def split_f16_cached(x_nhwc):
     """split_f16 remembered on the tensor (until it is written again): in the stage-3 graph the same activation /
     gradient is the operand of up to four tensor-core convs (forward conv, weight gradient, and their counterparts in
-    the double backward of the gradient penalty), in stage 1 the decoder features feed two heads."""
+    the double backward of the gradient penalty), in stage 1 the decoder features feed two heads.
+    A record made outside a CUDA-graph capture is never used inside one (and vice versa): a split of a static input
+    computed by the eager warm-up would otherwise be missing from the captured graph and go stale on replay."""
+    capturing = x_nhwc.is_cuda and torch.cuda.is_current_stream_capturing()
     rec = getattr(x_nhwc, "_split_rec", None)
-    if rec is not None and rec[1] == x_nhwc._version and USE_PUBLISHED_AMAX:
+    if rec is not None and rec[1] == x_nhwc._version and rec[2] == capturing and USE_PUBLISHED_AMAX:
         return rec[0]
     sa = split_f16(x_nhwc)
     if x_nhwc.is_contiguous():
-        x_nhwc._split_rec = (sa, x_nhwc._version)
+        x_nhwc._split_rec = (sa, x_nhwc._version, capturing)
     return sa
 
 

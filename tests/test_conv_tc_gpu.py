@@ -171,3 +171,32 @@ def test_split_output_epilogue_feeds_the_next_conv(cuda, C, K1, K2, H, W, R):
         assert float((rec2 - out_only).abs().max()) <= 2.0 ** -21 * 32768.0 * float(sp2.scal[1])
     finally:
         cb.set_precision("fp32")
+
+
+def test_cached_split_is_not_carried_into_a_graph_capture(cuda):
+    """A split (or a published maximum) recorded on a STATIC input by the eager warm-up must not be reused while a
+    CUDA graph is captured: the split kernel would be missing from the graph and every replay would convolve the
+    warm-up's contents.  Replay on new contents has to equal the eager result on those contents, bit for bit."""
+    from creste_public_b200 import ops
+    g = torch.Generator().manual_seed(5)
+    C, K = 64, 64
+    w = torch.randn(K, C, 3, 3, generator=g).to(cuda)
+    packed = ops.pack_conv_weight_f16_strided(w)
+
+    def f(x):
+        return ops.conv2d_presplit(ops.split_f16_cached(x), packed, K, 3, 3, 1, (1, 1, 1, 1), precision="3xfp16")
+
+    x = torch.randn(2, 16, 24, C, generator=g).to(cuda)          # the static input buffer
+    side = torch.cuda.Stream()
+    side.wait_stream(torch.cuda.current_stream())
+    with torch.cuda.stream(side):
+        f(x)                                                      # eager warm-up: records a split on x
+    torch.cuda.current_stream().wait_stream(side)
+    graph = torch.cuda.CUDAGraph()
+    with torch.cuda.graph(graph):
+        out = f(x)
+    x2 = torch.randn(2, 16, 24, C, generator=g).to(cuda) * 3.0
+    x.copy_(x2)
+    graph.replay()
+    torch.cuda.synchronize()
+    assert torch.equal(out, f(x2.clone()))

@@ -1024,6 +1024,7 @@ struct WgParams {
   int wbox, hbox, tiles_x, tiles_y, ntiles;
   int bn, nb;                  // input-channel tile (multiple of 64) and its 64-channel box count
   int m_tiles, n_tiles, splits;
+  int tg, ngroups;             // filter taps per CTA (they share the g tile) and tap groups = ceil(R*S / tg)
   uint32_t lbo, sbo;           // descriptor offsets in bytes
 };
 constexpr int WG_THREADS = 192;
@@ -1046,23 +1047,27 @@ wgrad_tc_kernel(const __grid_constant__ CUtensorMap map_g_hi, const __grid_const
 
   int t = blockIdx.x;
   const int split = t % p.splits; t /= p.splits;
-  const int tap = t % (p.R * p.S); t /= (p.R * p.S);
+  const int group = t % p.ngroups; t /= p.ngroups;
   const int n_tile = t % p.n_tiles;
   const int m_tile = t / p.n_tiles;
-  const int r = tap / p.S, s = tap - r * p.S;
+  // Narrow layers (input-channel tile <= 128: accumulators of <= 2 x 128 TMEM columns per tap) put several filter
+  // taps in one CTA: the g tile of a pixel block is fetched once for all of them and only the shifted x boxes differ.
+  // One CTA per tap moved 25 x (g + x) through L2 for the reward FCN's 5x5 layer: L2-bandwidth bound at 89 TFLOP/s.
+  const int tap0 = group * p.tg;
+  const int gcount = min(p.tg, p.R * p.S - tap0);
   const int m0 = m_tile * 128, n0 = n_tile * p.bn;
   const int per = (p.ntiles + p.splits - 1) / p.splits;
   const int t0 = split * per, t1 = min(t0 + per, p.ntiles);
   const int iters = max(t1 - t0, 0);
   const int a_bytes = 2 * WG_BOX_BYTES, b_bytes = p.nb * WG_BOX_BYTES;
-  const int stage_bytes = 2 * (a_bytes + b_bytes);
+  const int stage_bytes = 2 * (a_bytes + p.tg * b_bytes);
   // 64-channel boxes that lie entirely beyond K / C are not fetched: their accumulator rows / columns hold
   // garbage that the epilogue never stores (rows and columns of D are independent)
   const int a_boxes = (p.K - m0 > 64) ? 2 : 1;
   const int b_boxes = min(p.nb, (p.C - n0 + 63) / 64);
-  const uint32_t tx_bytes = (uint32_t)(2 * (a_boxes + b_boxes) * WG_BOX_BYTES);
+  const uint32_t tx_bytes = (uint32_t)(2 * (a_boxes + gcount * b_boxes) * WG_BOX_BYTES);
   const uint32_t acc_cols = p.bn <= 64 ? 64 : (p.bn <= 128 ? 128 : 256);
-  const uint32_t tmem_cols = 2 * acc_cols;
+  const uint32_t tmem_cols = p.tg * 2 * acc_cols;      // 128 / 256 / 512: a power of two by construction of tg
 
   if (warp == 0 && lane == 0) {
     prefetch_tmap(&map_g_hi); prefetch_tmap(&map_g_lo); prefetch_tmap(&map_x_hi); prefetch_tmap(&map_x_lo);
@@ -1088,16 +1093,20 @@ wgrad_tc_kernel(const __grid_constant__ CUtensorMap map_g_hi, const __grid_const
         const int q0 = tx * p.wbox, p0 = ty * p.hbox;
         uint8_t* st = smem + (size_t)stage * stage_bytes;
         uint8_t* a_hi = st; uint8_t* a_lo = st + a_bytes;
-        uint8_t* b_hi = st + 2 * a_bytes; uint8_t* b_lo = b_hi + b_bytes;
         mbar_expect_tx(&full_bar[stage], tx_bytes);
         for (int j = 0; j < a_boxes; ++j) {
           tma_load_4d(&map_g_hi, &full_bar[stage], a_hi + j * WG_BOX_BYTES, m0 + j * 64, q0, p0, img);
           tma_load_4d(&map_g_lo, &full_bar[stage], a_lo + j * WG_BOX_BYTES, m0 + j * 64, q0, p0, img);
         }
-        const int cx = q0 + s - p.pad_l, cy = p0 + r - p.pad_t;
-        for (int j = 0; j < b_boxes; ++j) {
-          tma_load_4d(&map_x_hi, &full_bar[stage], b_hi + j * WG_BOX_BYTES, n0 + j * 64, cx, cy, img);
-          tma_load_4d(&map_x_lo, &full_bar[stage], b_lo + j * WG_BOX_BYTES, n0 + j * 64, cx, cy, img);
+        for (int tj = 0; tj < gcount; ++tj) {
+          const int tap = tap0 + tj;
+          const int r = tap / p.S, s = tap - r * p.S;
+          uint8_t* b_hi = st + 2 * a_bytes + (size_t)tj * 2 * b_bytes; uint8_t* b_lo = b_hi + b_bytes;
+          const int cx = q0 + s - p.pad_l, cy = p0 + r - p.pad_t;
+          for (int j = 0; j < b_boxes; ++j) {
+            tma_load_4d(&map_x_hi, &full_bar[stage], b_hi + j * WG_BOX_BYTES, n0 + j * 64, cx, cy, img);
+            tma_load_4d(&map_x_lo, &full_bar[stage], b_lo + j * WG_BOX_BYTES, n0 + j * 64, cx, cy, img);
+          }
         }
       }
     }
@@ -1111,16 +1120,20 @@ wgrad_tc_kernel(const __grid_constant__ CUtensorMap map_g_hi, const __grid_const
       tc_fence_after();
       if (elect_one()) {
         const uint32_t st = smem_u32(smem + (size_t)stage * stage_bytes);
-        const uint32_t a_hi = st, a_lo = st + a_bytes, b_hi = st + 2 * a_bytes, b_lo = b_hi + b_bytes;
+        const uint32_t a_hi = st, a_lo = st + a_bytes;
+        for (int tj = 0; tj < gcount; ++tj) {
+          const uint32_t b_hi = st + 2 * a_bytes + (uint32_t)tj * 2 * b_bytes, b_lo = b_hi + b_bytes;
+          const uint32_t acc = tmem_base + (uint32_t)tj * 2 * acc_cols;
 #pragma unroll
-        for (int k = 0; k < 4; ++k) {          // 4 x 16 pixels per 64-pixel box
-          const uint32_t koff = k * 16 * 128;
-          const uint32_t first = (it | k) != 0;
-          const uint64_t dah = make_mn_sw128_desc(a_hi + koff, p.lbo, p.sbo), dal = make_mn_sw128_desc(a_lo + koff, p.lbo, p.sbo);
-          const uint64_t dbh = make_mn_sw128_desc(b_hi + koff, p.lbo, p.sbo), dbl = make_mn_sw128_desc(b_lo + koff, p.lbo, p.sbo);
-          umma_f16(tmem_base + acc_cols, dal, dbh, idesc, first);
-          umma_f16(tmem_base + acc_cols, dah, dbl, idesc, 1);
-          umma_f16(tmem_base, dah, dbh, idesc, first);
+          for (int k = 0; k < 4; ++k) {          // 4 x 16 pixels per 64-pixel box
+            const uint32_t koff = k * 16 * 128;
+            const uint32_t first = (it | k) != 0;
+            const uint64_t dah = make_mn_sw128_desc(a_hi + koff, p.lbo, p.sbo), dal = make_mn_sw128_desc(a_lo + koff, p.lbo, p.sbo);
+            const uint64_t dbh = make_mn_sw128_desc(b_hi + koff, p.lbo, p.sbo), dbl = make_mn_sw128_desc(b_lo + koff, p.lbo, p.sbo);
+            umma_f16(acc + acc_cols, dal, dbh, idesc, first);
+            umma_f16(acc + acc_cols, dah, dbl, idesc, 1);
+            umma_f16(acc, dah, dbh, idesc, first);
+          }
         }
         umma_commit(&empty_bar[stage]);
         if (it == iters - 1) umma_commit(&tmem_full_bar);
@@ -1131,27 +1144,29 @@ wgrad_tc_kernel(const __grid_constant__ CUtensorMap map_g_hi, const __grid_const
     // epilogue warps 2..5: TMEM lane quarter = warp % 4; lane = output channel k, columns = input channel c
     const int quarter = warp & 3;
     const int k = m0 + quarter * 32 + lane;
-    float* dst = p.part + ((size_t)split * (p.R * p.S) + tap) * (size_t)p.C * p.K;
     if (iters > 0) {
       mbar_wait(&tmem_full_bar, 0);
       tc_fence_after();
     }
     const float inv = __ldg(p.sx + 1) * __ldg(p.sg + 1);
     const float cross = 1.0f / 2048.0f;
-    for (int c0 = 0; c0 < p.bn; c0 += 32) {
-      uint32_t vm[32], vc[32];
-      if (iters > 0) {
-        const uint32_t taddr = tmem_base + ((uint32_t)(quarter * 32) << 16) + (uint32_t)c0;
-        tmem_ld32(taddr, vm);
-        tmem_ld32(taddr + acc_cols, vc);
-        tmem_ld_wait();
-      }
+    for (int tj = 0; tj < gcount; ++tj) {
+      float* dst = p.part + ((size_t)split * (p.R * p.S) + tap0 + tj) * (size_t)p.C * p.K;
+      for (int c0 = 0; c0 < p.bn; c0 += 32) {
+        uint32_t vm[32], vc[32];
+        if (iters > 0) {
+          const uint32_t taddr = tmem_base + ((uint32_t)(quarter * 32) << 16) + (uint32_t)tj * 2 * acc_cols + (uint32_t)c0;
+          tmem_ld32(taddr, vm);
+          tmem_ld32(taddr + acc_cols, vc);
+          tmem_ld_wait();
+        }
 #pragma unroll
-      for (int j = 0; j < 32; ++j) {
-        const int c = n0 + c0 + j;
-        if (c < p.C && k < p.K) {
-          const float v = iters > 0 ? (__uint_as_float(vm[j]) + __uint_as_float(vc[j]) * cross) * inv : 0.0f;
-          dst[(size_t)c * p.K + k] = v;
+        for (int j = 0; j < 32; ++j) {
+          const int c = n0 + c0 + j;
+          if (c < p.C && k < p.K) {
+            const float v = iters > 0 ? (__uint_as_float(vm[j]) + __uint_as_float(vc[j]) * cross) * inv : 0.0f;
+            dst[(size_t)c * p.K + k] = v;
+          }
         }
       }
     }
@@ -1213,7 +1228,7 @@ static void wg_pick_box(int P, int Q, int* wbox, int* hbox) {
   *hbox = 64 / best_w;
 }
 
-struct WgPlan { int bn, nb, m_tiles, n_tiles, wbox, hbox, tiles_x, tiles_y, ntiles, splits; size_t nx, ng; };
+struct WgPlan { int bn, nb, m_tiles, n_tiles, wbox, hbox, tiles_x, tiles_y, ntiles, splits, tg, ngroups; size_t nx, ng; };
 
 static WgPlan wg_plan(const creste_conv_desc* d) {
   WgPlan w;
@@ -1230,7 +1245,14 @@ static WgPlan wg_plan(const creste_conv_desc* d) {
   // pixel splits: minimise (waves over the 148 SMs) x (pixel tiles per CTA + a fixed per-CTA cost of ~6 tiles for
   // the prologue / epilogue), so that the grid does not spill a nearly empty last wave (25 taps x 12 splits = 300
   // CTAs ran as three waves on the reward FCN's 5x5 layers)
-  const int base = w.m_tiles * w.n_tiles * d->R * d->S;
+  // taps per CTA: as many as the 512 TMEM columns hold main + cross accumulators for (4 / 2 / 1 for input-channel
+  // tiles of 64 / 128 / 256), rounded down to a power of two so that the TMEM allocation is one
+  int tg = w.bn <= 64 ? 4 : (w.bn <= 128 ? 2 : 1);
+  if (const char* e = getenv("CRESTE_WGRAD_TAPS")) { const int v = atoi(e); if (v == 1 || v == 2 || v == 4) tg = v < tg ? v : tg; }
+  while (tg > 1 && tg > d->R * d->S) tg >>= 1;
+  w.tg = tg;
+  w.ngroups = ceil_div(d->R * d->S, tg);
+  const int base = w.m_tiles * w.n_tiles * w.ngroups;
   const int max_splits = w.ntiles / 8 > 1 ? w.ntiles / 8 : 1;
   int best_s = 1;
   long long best_cost = -1;
@@ -1317,15 +1339,16 @@ static int wgrad_tc_core(const creste_conv_desc* d, const void* x_hi, const void
   p.pad_t = d->pad_t; p.pad_l = d->pad_l;
   p.wbox = w.wbox; p.hbox = w.hbox; p.tiles_x = w.tiles_x; p.tiles_y = w.tiles_y; p.ntiles = w.ntiles;
   p.bn = w.bn; p.nb = w.nb; p.m_tiles = w.m_tiles; p.n_tiles = w.n_tiles; p.splits = w.splits;
+  p.tg = w.tg; p.ngroups = w.ngroups;
   p.lbo = WG_BOX_BYTES; p.sbo = 1024;
   if (const char* e = getenv("CRESTE_WGRAD_SWAP")) if (atoi(e)) { p.lbo = 1024; p.sbo = WG_BOX_BYTES; }
-  const size_t stage_bytes = (size_t)2 * (2 + w.nb) * WG_BOX_BYTES;
+  const size_t stage_bytes = (size_t)2 * (2 + w.tg * w.nb) * WG_BOX_BYTES;
   int nstages = (int)((200 * 1024) / stage_bytes);
   if (nstages > 8) nstages = 8;
   if (nstages < 2) { set_error("creste_conv2d_wgrad_tc: stage too large"); return CRESTE_ERR_ARG; }
   const size_t smem = (size_t)nstages * stage_bytes + 1024;
   CRESTE_CUDA(cudaFuncSetAttribute(wgrad_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-  const int grid = w.m_tiles * w.n_tiles * d->R * d->S * w.splits;
+  const int grid = w.m_tiles * w.n_tiles * w.ngroups * w.splits;
   wgrad_tc_kernel<<<grid, WG_THREADS, smem, st>>>(mg_hi, mg_lo, mx_hi, mx_lo, p, nstages);
   if ((rc = launch_check("wgrad_tc_kernel"))) return rc;
   const long long n = (long long)d->R * d->S * d->C * d->K;

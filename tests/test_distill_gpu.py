@@ -147,7 +147,11 @@ def test_loss_gradients(cuda):
 @pytest.mark.parametrize("N,H,W,C,K,R", [(2, 16, 24, 64, 64, 1), (2, 16, 24, 128, 256, 3), (2, 16, 30, 496, 496, 3),
                                          (2, 20, 28, 112, 72, 3), (3, 17, 23, 72, 200, 1), (1, 32, 60, 432, 432, 3),
                                          (2, 16, 24, 1152, 192, 1), (1, 24, 40, 64, 64, 5), (2, 32, 32, 40, 64, 5),
-                                         (2, 32, 32, 32, 16, 1), (2, 32, 32, 48, 8, 1), (2, 24, 24, 16, 96, 1), (1, 32, 32, 144, 24, 1)])
+                                         (2, 32, 32, 32, 16, 1), (2, 32, 32, 48, 8, 1), (2, 24, 24, 16, 96, 1), (1, 32, 32, 144, 24, 1),
+                                         # tap groups (several taps per CTA share the g tile): 9 taps = 4 + 4 + 1,
+                                         # 25 = 6 x 4 + 1, 128-channel tiles 2 + 2 + 2 + 2 + 1, 7x7 = 12 x 4 + 1
+                                         (2, 24, 24, 32, 32, 3), (2, 32, 40, 64, 32, 3), (1, 32, 32, 128, 136, 3),
+                                         (1, 32, 32, 24, 40, 7), (2, 16, 24, 96, 64, 3)])
 def test_wgrad_tcgen05(cuda, N, H, W, C, K, R):
     """Weight gradient on the tensor cores (MN-major tcgen05 operands, 3xFP16 split) against torch CPU
     float64: ragged pixel boxes, channel tails (C, K not multiples of 64 / 128), 1x1 / 3x3 / 5x5 taps."""

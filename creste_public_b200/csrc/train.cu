@@ -291,7 +291,7 @@ __device__ __forceinline__ float up_weight(int o, float ratio, int isz, int i) {
 template <int V>
 __global__ void __launch_bounds__(256) upsample_adjoint_kernel(const float* __restrict__ g, int N, int Hi,
                                                                int Wi, int C, int Ho, int Wo, float rh,
-                                                               float rw, float* __restrict__ dx) {
+                                                               float rw, float* __restrict__ dx, int hoist) {
   const int CV = C / V;
   const long long total = (long long)N * Hi * Wi * CV;
   for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total;
@@ -312,22 +312,49 @@ __global__ void __launch_bounds__(256) upsample_adjoint_kernel(const float* __re
     float acc[V];
 #pragma unroll
     for (int u = 0; u < V; ++u) acc[u] = 0.f;
+    // the column weights depend on ox only: computed once per thread instead of once per (oy, ox) candidate (a x4
+    // adjoint has ~100 candidates per input pixel, 64 of them with a non-zero weight); same values, same order
+    constexpr int WXMAX = 16;
+    float wxs[WXMAX];
+    const int nx = ox1 - ox0 + 1;
+    const bool hoisted = hoist && nx <= WXMAX;
+    if (hoisted) {
+#pragma unroll
+      for (int j = 0; j < WXMAX; ++j) wxs[j] = j < nx ? up_weight(ox0 + j, rw, Wi, ix) : 0.f;
+    }
     for (int oy = oy0; oy <= oy1; ++oy) {
       const float wy = up_weight(oy, rh, Hi, iy);
       if (wy == 0.f) continue;
       float row[V];
 #pragma unroll
       for (int u = 0; u < V; ++u) row[u] = 0.f;
-      for (int ox = ox0; ox <= ox1; ++ox) {
-        const float wx = up_weight(ox, rw, Wi, ix);
-        if (wx == 0.f) continue;
-        const float* src = g + (((size_t)n * Ho + oy) * Wo + ox) * C + c;
-        if (V == 4) {
-          const float4 gv = __ldg(reinterpret_cast<const float4*>(src));
-          row[0] = fmaf(wx, gv.x, row[0]); row[1 % V] = fmaf(wx, gv.y, row[1 % V]);
-          row[2 % V] = fmaf(wx, gv.z, row[2 % V]); row[3 % V] = fmaf(wx, gv.w, row[3 % V]);
-        } else {
-          row[0] = fmaf(wx, __ldg(src), row[0]);
+      const float* srow = g + (((size_t)n * Ho + oy) * Wo + ox0) * C + c;
+      if (hoisted) {
+#pragma unroll
+        for (int j = 0; j < WXMAX; ++j) {
+          const float wx = wxs[j];
+          if (wx == 0.f) continue;
+          const float* src = srow + (size_t)j * C;
+          if (V == 4) {
+            const float4 gv = __ldg(reinterpret_cast<const float4*>(src));
+            row[0] = fmaf(wx, gv.x, row[0]); row[1 % V] = fmaf(wx, gv.y, row[1 % V]);
+            row[2 % V] = fmaf(wx, gv.z, row[2 % V]); row[3 % V] = fmaf(wx, gv.w, row[3 % V]);
+          } else {
+            row[0] = fmaf(wx, __ldg(src), row[0]);
+          }
+        }
+      } else {
+        for (int ox = ox0; ox <= ox1; ++ox) {
+          const float wx = up_weight(ox, rw, Wi, ix);
+          if (wx == 0.f) continue;
+          const float* src = srow + (size_t)(ox - ox0) * C;
+          if (V == 4) {
+            const float4 gv = __ldg(reinterpret_cast<const float4*>(src));
+            row[0] = fmaf(wx, gv.x, row[0]); row[1 % V] = fmaf(wx, gv.y, row[1 % V]);
+            row[2 % V] = fmaf(wx, gv.z, row[2 % V]); row[3 % V] = fmaf(wx, gv.w, row[3 % V]);
+          } else {
+            row[0] = fmaf(wx, __ldg(src), row[0]);
+          }
         }
       }
 #pragma unroll
@@ -757,12 +784,13 @@ extern "C" int creste_upsample_adjoint(const float* g, int N, int Hi, int Wi, in
   CRESTE_CHECK_ARG(g && dx && N > 0 && Hi > 0 && Wi > 0 && C > 0 && Ho > 0 && Wo > 0 && rh > 0 && rw > 0,
                    "creste_upsample_adjoint: bad args");
   const long long total = (long long)N * Hi * Wi * C;
+  const int hoist = getenv("CRESTE_ADJ_NOHOIST") ? 0 : 1;
   if (C % 4 == 0 && (((uintptr_t)g | (uintptr_t)dx) & 15u) == 0)
     upsample_adjoint_kernel<4><<<grid_cap(total / 4, 256, 148 * 16), 256, 0, (cudaStream_t)stream>>>(g, N, Hi, Wi, C, Ho,
-                                                                                                   Wo, rh, rw, dx);
+                                                                                                   Wo, rh, rw, dx, hoist);
   else
     upsample_adjoint_kernel<1><<<grid_cap(total, 256, 148 * 16), 256, 0, (cudaStream_t)stream>>>(g, N, Hi, Wi, C, Ho,
-                                                                                               Wo, rh, rw, dx);
+                                                                                               Wo, rh, rw, dx, hoist);
   return launch_check("upsample_adjoint_kernel");
 }
 

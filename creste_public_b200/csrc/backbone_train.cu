@@ -435,6 +435,49 @@ __global__ void __launch_bounds__(256) dwconv_dgrad_kernel(const float* __restri
   }
 }
 
+// Stride 2: only the taps of the right parity contribute (r = (iy + pt) & 1, +2, ...), so the loops visit <= ceil(R/2)^2
+// taps instead of testing R*R (runtime `% st` per tap in the generic kernel); same ascending (r, s) FMA order over the
+// contributing taps: bit-identical to dwconv_dgrad_kernel.
+template <int R>
+__global__ void __launch_bounds__(256) dwconv_dgrad_s2_kernel(const float* __restrict__ g, const float* __restrict__ w,
+                                                              int N, int H, int W, int C, int pt, int pl, int P,
+                                                              int Q, float* __restrict__ dx) {
+  const int CV = C / 4;
+  const long long nv = (long long)N * H * W * CV;
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < nv;
+       i += (long long)gridDim.x * blockDim.x) {
+    const unsigned iu = (unsigned)i;                       // nv < 2^32 checked by the launcher
+    const int c = (int)(iu % (unsigned)CV) * 4;
+    unsigned pix = iu / (unsigned)CV;
+    const int ix = (int)(pix % (unsigned)W); pix /= (unsigned)W;
+    const int iy = (int)(pix % (unsigned)H);
+    const int n = (int)(pix / (unsigned)H);
+    float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
+    const int r0 = (iy + pt) & 1, s0 = (ix + pl) & 1;
+#pragma unroll
+    for (int rr = 0; rr < (R + 1) / 2; ++rr) {
+      const int r = r0 + 2 * rr;
+      const int ty = iy + pt - r;
+      if (r >= R || ty < 0) continue;
+      const int p = ty >> 1;
+      if (p >= P) continue;
+#pragma unroll
+      for (int ss = 0; ss < (R + 1) / 2; ++ss) {
+        const int sx = s0 + 2 * ss;
+        const int tx = ix + pl - sx;
+        if (sx >= R || tx < 0) continue;
+        const int q = tx >> 1;
+        if (q >= Q) continue;
+        const float4 gv = __ldg(reinterpret_cast<const float4*>(g + (((size_t)n * P + p) * Q + q) * C + c));
+        const float4 wv = __ldg(reinterpret_cast<const float4*>(w + (size_t)(r * R + sx) * C + c));
+        acc.x = fmaf(gv.x, wv.x, acc.x); acc.y = fmaf(gv.y, wv.y, acc.y);
+        acc.z = fmaf(gv.z, wv.z, acc.z); acc.w = fmaf(gv.w, wv.w, acc.w);
+      }
+    }
+    reinterpret_cast<float4*>(dx)[i] = acc;
+  }
+}
+
 // Stride-1 data gradient from a shared-memory tile of g (with halo, zero outside the output grid): the same (r, s)
 // ascending FMA order per element as dwconv_dgrad_kernel, so the results are bit-identical to it; 4 adjacent outputs
 // per thread, taps without bounds checks.
@@ -930,6 +973,11 @@ extern "C" int creste_dwconv_dgrad(const float* g, const float* w, int N, int H,
     return launch_check("dwconv_dgrad_tile_kernel");
   }
   const int grid = ELT_GRID((long long)N * H * W * (C / 4));
+  if (stride == 2 && (long long)N * H * W * (C / 4) < (1LL << 32) && !getenv("CRESTE_NO_DWDGRAD_S2")) {
+    if (R == 3) dwconv_dgrad_s2_kernel<3><<<grid, 256, 0, st>>>(g, w, N, H, W, C, pad_t, pad_l, P, Q, dx);
+    else dwconv_dgrad_s2_kernel<5><<<grid, 256, 0, st>>>(g, w, N, H, W, C, pad_t, pad_l, P, Q, dx);
+    return launch_check("dwconv_dgrad_s2_kernel");
+  }
   if (R == 3) dwconv_dgrad_kernel<3><<<grid, 256, 0, st>>>(g, w, N, H, W, C, stride, pad_t, pad_l, P, Q, dx);
   else dwconv_dgrad_kernel<5><<<grid, 256, 0, st>>>(g, w, N, H, W, C, stride, pad_t, pad_l, P, Q, dx);
   return launch_check("dwconv_dgrad_kernel");

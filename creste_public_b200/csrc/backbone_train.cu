@@ -398,6 +398,58 @@ __global__ void __launch_bounds__(256) dwconv_fwd_kernel(const float* __restrict
   }
 }
 
+// x-blocked form (as the eval path's dwconv_xb_kernel, without its BatchNorm / swish / squeeze-excite epilogue): a
+// thread produces 4 adjacent outputs of one row for its 4 channels and loads each input column once per filter row
+// (3*STRIDE + R float4 loads for 4*R FMAs-by-4 instead of 4*R).  Same (r, s) ascending FMA order per output; a tap
+// outside the image adds an exact 0 where dwconv_fwd_kernel skips it.
+template <int R, int STRIDE>
+__global__ void __launch_bounds__(256) dwconv_fwd_xb_kernel(const float* __restrict__ x, const float* __restrict__ w,
+                                                            int N, int H, int W, int C, int pt, int pl, int P, int Q,
+                                                            float* __restrict__ y) {
+  constexpr int XB = 4, NC = (XB - 1) * STRIDE + R;
+  const unsigned C4 = (unsigned)(C / 4), Qb = (unsigned)((Q + XB - 1) / XB);
+  const long long total = (long long)N * P * Qb * C4;              // < 2^32 checked by the launcher
+  const float4* wv0 = reinterpret_cast<const float4*>(w);
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total;
+       i += (long long)gridDim.x * blockDim.x) {
+    unsigned u = (unsigned)i;
+    const unsigned cg = u % C4; u /= C4;
+    const int ox0 = (int)(u % Qb) * XB; u /= Qb;
+    const int oy = (int)(u % (unsigned)P);
+    const int n = (int)(u / (unsigned)P);
+    const int iy0 = oy * STRIDE - pt, ix0 = ox0 * STRIDE - pl;
+    const float4* xn = reinterpret_cast<const float4*>(x + (size_t)n * H * W * C) + cg;
+    const float4* wv = wv0 + cg;
+    float4 acc[XB];
+#pragma unroll
+    for (int b = 0; b < XB; ++b) acc[b] = make_float4(0.f, 0.f, 0.f, 0.f);
+#pragma unroll
+    for (int r = 0; r < R; ++r) {
+      const int iy = iy0 + r;
+      if (iy < 0 || iy >= H) continue;
+      float4 col[NC];
+#pragma unroll
+      for (int c = 0; c < NC; ++c) {
+        const int ix = ix0 + c;
+        col[c] = (ix >= 0 && ix < W) ? __ldg(xn + ((size_t)iy * W + ix) * C4) : make_float4(0.f, 0.f, 0.f, 0.f);
+      }
+#pragma unroll
+      for (int s = 0; s < R; ++s) {
+        const float4 k = __ldg(wv + (size_t)(r * R + s) * C4);
+#pragma unroll
+        for (int b = 0; b < XB; ++b) {
+          const float4 v = col[b * STRIDE + s];
+          acc[b].x = fmaf(v.x, k.x, acc[b].x); acc[b].y = fmaf(v.y, k.y, acc[b].y);
+          acc[b].z = fmaf(v.z, k.z, acc[b].z); acc[b].w = fmaf(v.w, k.w, acc[b].w);
+        }
+      }
+    }
+#pragma unroll
+    for (int b = 0; b < XB; ++b)
+      if (ox0 + b < Q) reinterpret_cast<float4*>(y + (((size_t)n * P + oy) * Q + ox0 + b) * C)[cg] = acc[b];
+  }
+}
+
 // dx[n,iy,ix,c] = sum over taps (r,s) with (iy+pt-r) = p*st, (ix+pl-s) = q*st of w[r,s,c] * g[n,p,q,c]
 template <int R>
 __global__ void __launch_bounds__(256) dwconv_dgrad_kernel(const float* __restrict__ g, const float* __restrict__ w,
@@ -949,6 +1001,15 @@ extern "C" int creste_dwconv_fwd(const float* x, const float* w, int N, int H, i
                                  int pad_t, int pad_l, int P, int Q, float* y, void* stream) {
   CRESTE_CHECK_ARG(x && w && y && dw_geom_ok(N, H, W, C, R, stride, P, Q), "creste_dwconv_fwd: bad args");
   cudaStream_t st = (cudaStream_t)stream;
+  const long long units = (long long)N * P * ((Q + 3) / 4) * (C / 4);
+  if ((stride == 1 || stride == 2) && units < (1LL << 32) && !getenv("CRESTE_NO_DWFWD_XB")) {
+    const int xgrid = ELT_GRID(units);
+    if (R == 3 && stride == 1) dwconv_fwd_xb_kernel<3, 1><<<xgrid, 256, 0, st>>>(x, w, N, H, W, C, pad_t, pad_l, P, Q, y);
+    else if (R == 3) dwconv_fwd_xb_kernel<3, 2><<<xgrid, 256, 0, st>>>(x, w, N, H, W, C, pad_t, pad_l, P, Q, y);
+    else if (stride == 1) dwconv_fwd_xb_kernel<5, 1><<<xgrid, 256, 0, st>>>(x, w, N, H, W, C, pad_t, pad_l, P, Q, y);
+    else dwconv_fwd_xb_kernel<5, 2><<<xgrid, 256, 0, st>>>(x, w, N, H, W, C, pad_t, pad_l, P, Q, y);
+    return launch_check("dwconv_fwd_xb_kernel");
+  }
   const int grid = ELT_GRID((long long)N * P * Q * (C / 4));
   if (R == 3) dwconv_fwd_kernel<3><<<grid, 256, 0, st>>>(x, w, N, H, W, C, stride, pad_t, pad_l, P, Q, y);
   else dwconv_fwd_kernel<5><<<grid, 256, 0, st>>>(x, w, N, H, W, C, stride, pad_t, pad_l, P, Q, y);

@@ -27,7 +27,7 @@ EXPORTS = [
     "creste_nchw_to_nhwc", "creste_nhwc_to_nchw", "creste_proj_head",
     "creste_expert_visitation",
     "creste_chan_affine", "creste_relu_bwd", "creste_chan_dot_workspace_bytes", "creste_chan_dot", "creste_chan_stats",
-    "creste_maxpool2_bwd", "creste_maxpool2_gather", "creste_upsample_adjoint",
+    "creste_maxpool2_bwd", "creste_maxpool2_gather", "creste_upsample_adjoint", "creste_upsample_adjoint_slice",
     "creste_conv2d_wgrad_workspace_bytes", "creste_conv2d_wgrad",
     "creste_row_dot", "creste_row_scale", "creste_row_normalize",
     "creste_grad_penalty_workspace_bytes", "creste_grad_penalty", "creste_grad_penalty_bwd",

@@ -779,7 +779,7 @@ class UpCatFn(Function):
         dskip = ops.chan_slice(g, 0, ctx.cs) if ctx.needs_input_grad[1] else None
         dx = None
         if ctx.needs_input_grad[0]:
-            dx = ops.upsample_adjoint(ops.chan_slice(g, ctx.cs, ctx.cx), ctx.hw[0], ctx.hw[1], 1.0 / ctx.sf)
+            dx = ops.upsample_adjoint_slice(g, ctx.cs, ctx.cx, ctx.hw[0], ctx.hw[1], 1.0 / ctx.sf)
         return dx, dskip, None
 
 

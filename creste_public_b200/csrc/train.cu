@@ -291,7 +291,7 @@ __device__ __forceinline__ float up_weight(int o, float ratio, int isz, int i) {
 template <int V>
 __global__ void __launch_bounds__(256) upsample_adjoint_kernel(const float* __restrict__ g, int N, int Hi,
                                                                int Wi, int C, int Ho, int Wo, float rh,
-                                                               float rw, float* __restrict__ dx, int hoist) {
+                                                               float rw, float* __restrict__ dx, int hoist, int ldg) {
   const int CV = C / V;
   const long long total = (long long)N * Hi * Wi * CV;
   for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total;
@@ -328,13 +328,13 @@ __global__ void __launch_bounds__(256) upsample_adjoint_kernel(const float* __re
       float row[V];
 #pragma unroll
       for (int u = 0; u < V; ++u) row[u] = 0.f;
-      const float* srow = g + (((size_t)n * Ho + oy) * Wo + ox0) * C + c;
+      const float* srow = g + (((size_t)n * Ho + oy) * Wo + ox0) * ldg + c;      // ldg: pixel pitch of g (>= C)
       if (hoisted) {
 #pragma unroll
         for (int j = 0; j < WXMAX; ++j) {
           const float wx = wxs[j];
           if (wx == 0.f) continue;
-          const float* src = srow + (size_t)j * C;
+          const float* src = srow + (size_t)j * ldg;
           if (V == 4) {
             const float4 gv = __ldg(reinterpret_cast<const float4*>(src));
             row[0] = fmaf(wx, gv.x, row[0]); row[1 % V] = fmaf(wx, gv.y, row[1 % V]);
@@ -347,7 +347,7 @@ __global__ void __launch_bounds__(256) upsample_adjoint_kernel(const float* __re
         for (int ox = ox0; ox <= ox1; ++ox) {
           const float wx = up_weight(ox, rw, Wi, ix);
           if (wx == 0.f) continue;
-          const float* src = srow + (size_t)(ox - ox0) * C;
+          const float* src = srow + (size_t)(ox - ox0) * ldg;
           if (V == 4) {
             const float4 gv = __ldg(reinterpret_cast<const float4*>(src));
             row[0] = fmaf(wx, gv.x, row[0]); row[1 % V] = fmaf(wx, gv.y, row[1 % V]);
@@ -779,19 +779,33 @@ extern "C" int creste_maxpool2_gather(const float* x, const float* gg, int N, in
   return launch_check("maxpool2_route_kernel");
 }
 
+static int upsample_adjoint_launch(const float* g, int ldg, int N, int Hi, int Wi, int C, int Ho, int Wo, float rh, float rw,
+                                   float* dx, cudaStream_t st) {
+  const long long total = (long long)N * Hi * Wi * C;
+  const int hoist = getenv("CRESTE_ADJ_NOHOIST") ? 0 : 1;
+  if (C % 4 == 0 && ldg % 4 == 0 && (((uintptr_t)g | (uintptr_t)dx) & 15u) == 0)
+    upsample_adjoint_kernel<4><<<grid_cap(total / 4, 256, 148 * 16), 256, 0, st>>>(g, N, Hi, Wi, C, Ho, Wo, rh, rw, dx,
+                                                                                   hoist, ldg);
+  else
+    upsample_adjoint_kernel<1><<<grid_cap(total, 256, 148 * 16), 256, 0, st>>>(g, N, Hi, Wi, C, Ho, Wo, rh, rw, dx, hoist,
+                                                                               ldg);
+  return launch_check("upsample_adjoint_kernel");
+}
+
 extern "C" int creste_upsample_adjoint(const float* g, int N, int Hi, int Wi, int C, int Ho, int Wo, float rh,
                                        float rw, float* dx, void* stream) {
   CRESTE_CHECK_ARG(g && dx && N > 0 && Hi > 0 && Wi > 0 && C > 0 && Ho > 0 && Wo > 0 && rh > 0 && rw > 0,
                    "creste_upsample_adjoint: bad args");
-  const long long total = (long long)N * Hi * Wi * C;
-  const int hoist = getenv("CRESTE_ADJ_NOHOIST") ? 0 : 1;
-  if (C % 4 == 0 && (((uintptr_t)g | (uintptr_t)dx) & 15u) == 0)
-    upsample_adjoint_kernel<4><<<grid_cap(total / 4, 256, 148 * 16), 256, 0, (cudaStream_t)stream>>>(g, N, Hi, Wi, C, Ho,
-                                                                                                   Wo, rh, rw, dx, hoist);
-  else
-    upsample_adjoint_kernel<1><<<grid_cap(total, 256, 148 * 16), 256, 0, (cudaStream_t)stream>>>(g, N, Hi, Wi, C, Ho,
-                                                                                               Wo, rh, rw, dx, hoist);
-  return launch_check("upsample_adjoint_kernel");
+  return upsample_adjoint_launch(g, C, N, Hi, Wi, C, Ho, Wo, rh, rw, dx, (cudaStream_t)stream);
+}
+
+/* the same reading a channel slice [c0, c0 + C) of a wider tensor g [N,Ho,Wo,Cg] in place (the backward of
+ * cat([skip, up(x)]): no chan_slice copy of the up-sampled part) */
+extern "C" int creste_upsample_adjoint_slice(const float* g, int Cg, int c0, int N, int Hi, int Wi, int C, int Ho, int Wo,
+                                             float rh, float rw, float* dx, void* stream) {
+  CRESTE_CHECK_ARG(g && dx && N > 0 && Hi > 0 && Wi > 0 && C > 0 && Ho > 0 && Wo > 0 && rh > 0 && rw > 0 && c0 >= 0 &&
+                       c0 + C <= Cg, "creste_upsample_adjoint_slice: bad args");
+  return upsample_adjoint_launch(g + c0, Cg, N, Hi, Wi, C, Ho, Wo, rh, rw, dx, (cudaStream_t)stream);
 }
 
 static bool wgrad_use_halo(const creste_conv_desc* d) {

@@ -659,6 +659,16 @@ def upsample_adjoint(g_nhwc, Hi, Wi, ratio):
     return dx
 
 
+def upsample_adjoint_slice(g_nhwc, c0, Cc, Hi, Wi, ratio):
+    """upsample_adjoint of the channel slice g[..., c0:c0+Cc], read in place (no chan_slice copy)."""
+    g_nhwc = g_nhwc.contiguous()
+    N, Ho, Wo, Cg = g_nhwc.shape
+    dx = torch.empty(N, Hi, Wi, Cc, device=g_nhwc.device)
+    check(lib().creste_upsample_adjoint_slice(ptr(g_nhwc), Cg, int(c0), N, Hi, Wi, int(Cc), Ho, Wo, C.c_float(ratio),
+                                              C.c_float(ratio), ptr(dx), stream()), "creste_upsample_adjoint_slice")
+    return dx
+
+
 def conv2d_wgrad(x_nhwc, g_nhwc, R, S, pad):
     """dw [K,C,R,S] (torch layout) of a stride-1 conv: x [N,H,W,C], g [N,P,Q,K]."""
     x_nhwc, g_nhwc = x_nhwc.contiguous(), g_nhwc.contiguous()

@@ -355,6 +355,10 @@ int creste_maxpool2_gather(const float* x, const float* gg, int N, int H, int W,
  * g [N,Ho,Wo,C] -> dx [N,Hi,Wi,C]; rh, rw = source-per-destination ratios. */
 int creste_upsample_adjoint(const float* g, int N, int Hi, int Wi, int C, int Ho, int Wo, float rh,
                             float rw, float* dx, void* stream);
+/* the same reading the channel slice [c0, c0 + C) of g [N,Ho,Wo,Cg] in place: backward of `cat([x2, up(x1)])`
+ * (effnet.py:22-28, inpainting.py:56) without a copy of the up-sampled part */
+int creste_upsample_adjoint_slice(const float* g, int Cg, int c0, int N, int Hi, int Wi, int C, int Ho, int Wo,
+                                  float rh, float rw, float* dx, void* stream);
 /* weight gradient of a stride-1 conv (autograd's convolution_backward, weight part):
  * x [N,H,W,C], g [N,P,Q,K] -> dw_packed [R*S*C, K]; C, K multiples of 8, <= 64. */
 size_t creste_conv2d_wgrad_workspace_bytes(const creste_conv_desc* d);

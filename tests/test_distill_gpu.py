@@ -312,6 +312,16 @@ def test_bn_backward_second_pass_recomputes_gu(cuda, act):
     assert float(ops.published_amax(one)) == float(two.abs().max())
 
 
+def test_upsample_adjoint_reads_a_channel_slice_in_place(cuda):
+    from creste_public_b200 import ops
+    g = _t(np.random.default_rng(2), 2, 12, 20, 40).to(cuda)
+    for c0, Cc, f in ((8, 32, 2), (0, 40, 2), (16, 24, 4)):
+        Hi, Wi = 12 // f, 20 // f
+        a = ops.upsample_adjoint_slice(g, c0, Cc, Hi, Wi, 1.0 / f)
+        b = ops.upsample_adjoint(ops.chan_slice(g, c0, Cc), Hi, Wi, 1.0 / f)
+        assert torch.equal(a, b), (c0, Cc, f)
+
+
 def test_training_step_identical_with_published_amax(cuda):
     """The stage-1 step with the producers' published maxima (no amax passes in front of the tensor-core convs) is
     bit-identical to the step that measures every operand maximum in its own pass."""

@@ -127,6 +127,10 @@ def upsample_adjoint(g, Hi, Wi, ratio):
     return _nhwc(dx)
 
 
+def upsample_adjoint_slice(g, c0, Cc, Hi, Wi, ratio):
+    return upsample_adjoint(g[..., c0:c0 + Cc].contiguous(), Hi, Wi, ratio)
+
+
 def _frustum(depth, p2p, rng, vox):
     M, Hs, Ws = depth.shape
     u, v = torch.meshgrid(torch.arange(Ws), torch.arange(Hs), indexing="xy")
@@ -613,7 +617,7 @@ STAGE1_NAMES = ["bn_fwd_finalize", "bn_bwd_finalize", "chan_moments", "chan_affi
                 "dwconv_wgrad", "sample_dot", "sample_affine", "act", "act_bwd", "add_scaled", "chan_slice",
                 "wgrad_strided", "wgrad_rows", "conv2d", "pack_conv_weight", "upsample_concat", "stage1_depth_losses",
                 "ce_depth_bwd", "masked_mse", "masked_mse_bwd", "depth_expectation"]
-STAGE2_NAMES = ["dilate", "phase_slice", "upsample_adjoint", "frustum_to_bev", "frustum_bwd", "splat_soft",
+STAGE2_NAMES = ["dilate", "phase_slice", "upsample_adjoint", "upsample_adjoint_slice", "frustum_to_bev", "frustum_bwd", "splat_soft",
                 "splat_soft_bwd", "depth_expectation_bwd", "bin_depths", "smooth_l1", "smooth_l1_bwd", "ce_weighted",
                 "ce_weighted_bwd", "l2norm_rows", "l2norm_rows_bwd", "supcon_fwd", "supcon_bwd", "vi_solve", "svf",
                 "maxpool2_concat"]

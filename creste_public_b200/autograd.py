@@ -17,6 +17,8 @@ differentiation and `torch.autograd.grad(..., create_graph=True)` works to any o
 Tensors are channels-last fp32.  The only torch-native differentiable ops in the graph are
 views / permutations / pads of tiny tensors (weights, per-channel vectors) and `torch.cat`.
 """
+import os
+
 import torch
 from torch.autograd import Function
 
@@ -108,13 +110,19 @@ def _flip_t(w):
     return w.flip(2, 3).transpose(0, 1)
 
 
+TRAIN_TC_BIG_1X1 = os.environ.get("CRESTE_TRAIN_NO_TC_1X1") is None      # experiment / test switch
 PRESPLIT_REUSE = True     # first-order training: split each conv operand once (forward x saved, g shared by dgrad / wgrad)
 
 
 def _tc_f16(shape, K, R, S, pad):
     """True if a stride-1 conv of an [N,H,W,C] tensor runs in the 3xFP16 tensor-core mode with no channel padding."""
+    # Large 1x1 convs with 64 <= C <= 192 AND >= 64 output channels over >= 64 K pixels (the dino head's 128 -> 128 /
+    # 128 -> 256 layers at 16x128x240: 32 - 64 GFLOP each, 0.48 - 0.95 ms on the FFMA kernel, which the eval path keeps
+    # for short reductions to save the operand pre-pass) run on the tensor cores in a training graph: the weight
+    # gradient needs the split operands anyway.  Routing EVERY such conv there measured slower (profiles/r2d_experiments.md).
+    big = TRAIN_TC_BIG_1X1 and K >= 64 and shape[0] * shape[1] * shape[2] >= 65536
     return (engine.get_precision() == "3xfp16" and shape[-1] % 8 == 0 and K % 8 == 0 and shape[1] * shape[2] >= 16
-            and engine.pick_mode(tuple(shape), K, R, S, 1, pad, "3xfp16") == "3xfp16")
+            and engine.pick_mode(tuple(shape), K, R, S, 1, pad, "3xfp16", prefer_tc=big) == "3xfp16")
 
 
 def _conv_presplit(xs, w, pad):

@@ -132,21 +132,27 @@ int conv1x1_stream_launch(const creste_conv_desc* d, const float* x, const float
   if (getenv("CRESTE_NO_CONV1X1")) return 0;
   if (d->R != 1 || d->S != 1 || d->stride != 1 || d->pad_t != 0 || d->pad_l != 0 || d->out_nchw) return 0;
   if (d->P != d->H || d->Q != d->W) return 0;
-  if (d->K % 4 != 0 || d->K > 256 || d->C % 4 != 0 || d->C > 96) return 0;   // measured: wider reductions are no faster here
+  // C <= 96 for any K <= 256 (measured: wider reductions are no faster here than conv_simt_kernel); round 2d: also the
+  // PROJECT shape -- up to 192 input channels onto <= 32 output channels (MBConv 144 -> 24; 144 -> 40 measured no faster; and the data
+  // gradient of the expand convs), which the generic kernel ran at 1/6 of the HBM rate with its 32-wide N tile
+  const bool project = d->C > 96 && d->C <= 192 && d->K <= 32 && !getenv("CRESTE_C11_NO_PROJECT");
+  if (d->K % 4 != 0 || d->K > 256 || d->C % 4 != 0 || (d->C > 96 && !project)) return 0;
   auto al16 = [](const void* q) { return q == nullptr || ((uintptr_t)q & 15u) == 0; };
   if (!al16(x) || !al16(w) || !al16(out) || !al16(residual) || !al16(scale) || !al16(shift) || !al16(gate) || ldw % 4 != 0)
     return 0;
   const int KG = d->K / 4;
-  const int S = 256 / KG;
-  const int T = S * KG;
-  if (S < 1 || T < 128) return 0;
   const int CP = d->C + 4;                                  // row pitch: neighbouring pixels land 4 banks apart
   const size_t wbytes = (size_t)d->C * d->K * sizeof(float);
   if (wbytes > 64 * 1024) return 0;
-  int PP = 0;
+  // pixels per step S (threads T = S * KG in [128, 256]) and pixels per thread PP: the largest tile whose x rows fit
+  // the shared-memory budget; few output channels mean many pixels per step, so S is halved until the tile fits
+  const size_t budget = (project ? 56 : 40) * 1024;
   const int pp_max = getenv("CRESTE_C11_PP") ? atoi(getenv("CRESTE_C11_PP")) : 4;   // 4: <= 64 registers, 4 CTAs per SM (measured faster than 8)
-  for (int pp : {8, 4, 2})
-    if (pp <= pp_max && (size_t)S * pp * CP * sizeof(float) <= 40 * 1024) { PP = pp; break; }
+  int S = 0, T = 0, PP = 0;
+  for (int s_try = 256 / KG; s_try >= 1 && s_try * KG >= 128 && !PP; s_try = s_try / 2) {
+    for (int pp : {8, 4, 2})
+      if (pp <= pp_max && (size_t)s_try * pp * CP * sizeof(float) <= budget) { PP = pp; S = s_try; T = s_try * KG; break; }
+  }
   if (!PP) return 0;
   const size_t smem = wbytes + (size_t)S * PP * CP * sizeof(float);
   Conv1x1P p;

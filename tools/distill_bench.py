@@ -45,7 +45,7 @@ if os.environ.get("PROFILE"):
         ms = e0.elapsed_time(e1); by[name][0] += 1; by[name][1] += ms; byt[tag][0] += 1; byt[tag][1] += ms
     print(f"profiled step: {tot:.2f} ms, {len(rec)} op calls, sum of ops {sum(v[1] for v in by.values()):.2f} ms")
     for k, v in sorted(by.items(), key=lambda kv: -kv[1][1])[:16]: print(f"  {k:22s} n={v[0]:4d} {v[1]:8.2f} ms")
-    for k, v in sorted(byt.items(), key=lambda kv: -kv[1][1])[:14]: print(f"    {k:64s} n={v[0]:3d} {v[1]:7.2f} ms")
+    for k, v in [kv for kv in sorted(byt.items(), key=lambda kv: -kv[1][1]) if " " in kv[0]][:int(os.environ.get("PROFILE_TAGS", "14"))]: print(f"    {k:64s} n={v[0]:3d} {v[1]:7.2f} ms")
     sys.exit(0)
 n0 = _lib.lib().creste_launch_count()
 a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)

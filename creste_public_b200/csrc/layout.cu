@@ -37,6 +37,29 @@ __global__ void __launch_bounds__(256) nchw4_to_nhwc_kernel(const float* __restr
   }
 }
 
+// NCHW -> NHWC for a handful of channels (C <= 8, C != 4: the 6- and 2-channel head predictions that enter the reward
+// net at 1024 x 512): one pixel per thread, C coalesced plane reads, C consecutive floats stored.  The 32 x 32 tile of
+// transpose_kernel has C valid rows of 32 there (190 us for 100 MB).
+template <int C>
+__global__ void __launch_bounds__(256) nchw_small_to_nhwc_kernel(const float* __restrict__ in, long long HW,
+                                                                 long long total, float* __restrict__ out) {
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
+    const long long n = i / HW, p = i - n * HW;
+    const float* b = in + n * C * HW + p;
+    float v[C];
+#pragma unroll
+    for (int c = 0; c < C; ++c) v[c] = __ldg(b + c * HW);
+    float* o = out + i * C;
+    if (C % 2 == 0) {
+#pragma unroll
+      for (int c = 0; c < C; c += 2) *reinterpret_cast<float2*>(o + c) = make_float2(v[c], v[c + 1 < C ? c + 1 : c]);
+    } else {
+#pragma unroll
+      for (int c = 0; c < C; ++c) o[c] = v[c];
+    }
+  }
+}
+
 // 128-bit form of transpose_kernel for rows % 4 == 0 && cols % 4 == 0: a 64 x 64 tile, float4 loads along the
 // columns and float4 stores along the rows (the scalar form moved 4 bytes per lane per instruction and ran the
 // 126 MB layout changes at the module boundary at ~0.25 of the HBM rate)
@@ -462,6 +485,19 @@ extern "C" int creste_nchw_to_nhwc(const float* in, int N, int C, int H, int W, 
     nchw4_to_nhwc_kernel<<<grid_for(total), 256, 0, (cudaStream_t)stream>>>(in, (long long)H * W, total,
                                                                           reinterpret_cast<float4*>(out));
     return launch_check("nchw4_to_nhwc_kernel");
+  }
+  if (C <= 8 && C != 4 && C != 8 && (((uintptr_t)out & 7u) == 0 || C % 2) && !getenv("CRESTE_NO_SMALL_TRANSPOSE")) {
+    const long long total = (long long)N * H * W, HW = (long long)H * W;
+    cudaStream_t st = (cudaStream_t)stream;
+    switch (C) {
+      case 1: nchw_small_to_nhwc_kernel<1><<<grid_for(total), 256, 0, st>>>(in, HW, total, out); break;
+      case 2: nchw_small_to_nhwc_kernel<2><<<grid_for(total), 256, 0, st>>>(in, HW, total, out); break;
+      case 3: nchw_small_to_nhwc_kernel<3><<<grid_for(total), 256, 0, st>>>(in, HW, total, out); break;
+      case 5: nchw_small_to_nhwc_kernel<5><<<grid_for(total), 256, 0, st>>>(in, HW, total, out); break;
+      case 6: nchw_small_to_nhwc_kernel<6><<<grid_for(total), 256, 0, st>>>(in, HW, total, out); break;
+      default: nchw_small_to_nhwc_kernel<7><<<grid_for(total), 256, 0, st>>>(in, HW, total, out); break;
+    }
+    return launch_check("nchw_small_to_nhwc_kernel");
   }
   if (C % 4 == 0 && (H * W) % 4 == 0 && al16(in) && al16(out)) {
     dim3 grid4(ceil_div(H * W, 64), ceil_div(C, 64), N);

@@ -155,11 +155,15 @@ __global__ void __launch_bounds__(SVF_THREADS) svf_kernel(SvfParams p) {
       prop_sync();
     }
     {
+      // after t - 1 steps the mass lies within t - 1 cells of S0, so only the cells within t of it can receive any:
+      // everything outside this box is zero in both buffers and is skipped (adds of exact zeros; same results)
+      const int by0 = s0r - oy - t, by1 = s0r - oy + t, bx0 = s0c - ox - t, bx1 = s0c - ox + t;
 #pragma unroll
       for (int j = 0; j < SVF_MAX_CELLS_PER_THREAD; ++j) {
         const int i = tid + j * nprop;
         if (i < ncell) {
           const int wy = i / Ww, wx = i - wy * Ww;
+          if (wy < by0 || wy > by1 || wx < bx0 || wx > bx1) continue;
           acc[j] = __fadd_rn(acc[j], cur[(wy + 1) * pitch + wx + 1]);
           float sum = 0.0f;
 #pragma unroll
